@@ -1,0 +1,183 @@
+"""`_C` operator module of the drop-in rasterizer package.
+
+Same operator names, argument order and return tuples as the reference's
+pybind module (submodules/hierarchy-rasterizer/ext.cpp:15-18,
+rasterize_points.h:18-80), implemented as a thin marshalling layer over the
+C-ABI (include/hidegs_raster.h): tensors are only used for device memory and
+the current CUDA stream.
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+
+
+def _ptr(t):
+    """data_ptr of a tensor or NULL for an empty one (reference: empty == absent)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32(t):
+    if t is None:
+        return None
+    if t.numel() and (t.dtype != torch.float32 or not t.is_cuda):
+        raise RuntimeError("expected a float32 CUDA tensor, got %s on %s" % (t.dtype, t.device))
+    return t.contiguous()
+
+
+def _i32(t):
+    if t is None:
+        return None
+    if t.numel() and (t.dtype != torch.int32 or not t.is_cuda):
+        raise RuntimeError("expected an int32 CUDA tensor, got %s on %s" % (t.dtype, t.device))
+    return t.contiguous()
+
+
+class _Scratch:
+    """Growable byte buffer handed to the library through hg_alloc_fn
+    (the reference's resizeFunctional, rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, nbytes):
+        try:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:  # surfaces as HG_ERR_ALLOC
+            return None
+
+
+def _inputs(P, N, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, render_geo, debug,
+            bg, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D, sh, colors,
+            all_map, opacity, scales, rotations, cov3D_precomp):
+    s = _lib.RasterInputs()
+    s.P, s.N, s.D, s.M, s.W, s.H = P, N, degree, M, W, H
+    s.tan_fovx, s.tan_fovy, s.scale_modifier = tan_fovx, tan_fovy, scale_modifier
+    s.prefiltered, s.render_geo, s.debug = int(prefiltered), int(render_geo), int(debug)
+    s.background, s.viewmatrix, s.projmatrix, s.campos = _ptr(bg), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
+    s.indices, s.parent_indices, s.ts, s.kids = _ptr(indices), _ptr(parent_indices), _ptr(ts), _ptr(kids)
+    s.means3D, s.shs, s.colors_precomp, s.all_map = _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(all_map)
+    s.opacities, s.scales, s.rotations, s.cov3D_precomp = _ptr(opacity), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp)
+    return s
+
+
+def rasterize_gaussians(background, indices, parent_indices, ts, kids, means3D, colors, all_map, opacity,
+                        scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
+                        tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, render_geo, debug,
+                        do_depth):
+    """RasterizeGaussiansCUDA (rasterize_points.cu:35-147)."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("hidegs_b200 rasterizer needs CUDA tensors (there is no CPU path)")
+    dev = means3D.device
+    background, viewmatrix, projmatrix, campos = _f32(background), _f32(viewmatrix), _f32(projmatrix), _f32(campos)
+    means3D, colors, all_map, opacity = _f32(means3D), _f32(colors), _f32(all_map), _f32(opacity)
+    scales, rotations, cov3D_precomp, sh, ts = _f32(scales), _f32(rotations), _f32(cov3D_precomp), _f32(sh), _f32(ts)
+    indices, parent_indices, kids = _i32(indices), _i32(parent_indices), _i32(kids)
+
+    N = means3D.size(0)
+    P = N if indices.numel() == 0 else indices.size(0)
+    H, W = int(image_height), int(image_width)
+    M = sh.size(1) if sh.numel() != 0 else 0
+    f32 = dict(dtype=torch.float32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    # The library writes every element of these outputs, so no zero fill is needed.
+    out_color = torch.empty((3, H, W), **f32)
+    out_invdepth = torch.empty((1 if do_depth else 0, H, W), **f32)
+    radii = torch.empty((P,), **i32)
+    out_observe = torch.empty((P,), **i32)
+    out_all_map = torch.empty((5, H, W), **f32)
+    out_plane_depth = torch.empty((1, H, W), **f32)
+    geom, binning, img = _Scratch(dev), _Scratch(dev), _Scratch(dev)
+    rendered = ctypes.c_int32(0)
+    if P != 0 and all_map.numel() != 0 and all_map.size(0) < P:
+        raise RuntimeError("all_map must have one row per rendered slot")
+
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        s = _inputs(P, N, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, render_geo, debug,
+                    background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D, sh,
+                    colors, all_map, opacity, scales, rotations, cov3D_precomp)
+        rc = _lib.lib().hg_raster_forward(
+            ctypes.byref(s), geom.cb, None, binning.cb, None, img.cb, None,
+            _ptr(out_color), _ptr(out_invdepth), _ptr(out_observe), _ptr(out_all_map), _ptr(out_plane_depth),
+            _ptr(radii), ctypes.byref(rendered), stream)
+    _lib.check(rc, "rasterize_gaussians")
+    return (rendered.value, out_color, radii, out_observe, out_all_map, out_plane_depth, geom.tensor,
+            binning.tensor, img.tensor, out_invdepth)
+
+
+def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_indices, ts, kids, means3D, radii,
+                                 colors, all_maps, opacities, scales, rotations, scale_modifier, cov3D_precomp,
+                                 viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_all_map,
+                                 dL_dout_plane_depth, dL_dout_invdepth, sh, degree, campos, geomBuffer, R,
+                                 binningBuffer, imageBuffer, render_geo, debug):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:149-279)."""
+    dev = means3D.device
+    background, viewmatrix, projmatrix, campos = _f32(background), _f32(viewmatrix), _f32(projmatrix), _f32(campos)
+    means3D, colors, all_maps, opacities = _f32(means3D), _f32(colors), _f32(all_maps), _f32(opacities)
+    scales, rotations, cov3D_precomp, sh, ts = _f32(scales), _f32(rotations), _f32(cov3D_precomp), _f32(sh), _f32(ts)
+    indices, parent_indices, kids, radii = _i32(indices), _i32(parent_indices), _i32(kids), _i32(radii)
+    all_map_pixels = _f32(all_map_pixels)
+    dL_dout_color, dL_dout_all_map = _f32(dL_dout_color), _f32(dL_dout_all_map)
+    dL_dout_plane_depth, dL_dout_invdepth = _f32(dL_dout_plane_depth), _f32(dL_dout_invdepth)
+
+    fullP = means3D.size(0)
+    P = fullP if indices.numel() == 0 else indices.size(0)
+    H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+    M = sh.size(1) if sh.numel() != 0 else 0
+    # With an index remap or parents the library accumulates into pre-zeroed rows.
+    prezero = indices.numel() != 0 or parent_indices.numel() != 0 or P == 0
+    new = torch.zeros if prezero else torch.empty
+    opt = dict(dtype=torch.float32, device=dev)
+    dL_dmeans3D = new((fullP, 3), **opt)
+    dL_dmeans2D = new((fullP, 3), **opt)
+    dL_dcolors = new((fullP, 3), **opt)
+    dL_dall_map = new((fullP, 5), **opt)
+    dL_dopacity = new((fullP, 1), **opt)
+    dL_dcov3D = new((fullP, 6), **opt)
+    dL_dsh = new((fullP, M, 3), **opt)
+    dL_dscales = new((fullP, 3), **opt)
+    dL_drotations = new((fullP, 4), **opt)
+    has_depth_grad = dL_dout_invdepth is not None and dL_dout_invdepth.numel() != 0
+    dL_dinvdepths = new((fullP, 1), **opt) if has_depth_grad else torch.zeros((0, 1), **opt)
+
+    if P != 0:
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            accum = torch.empty(_lib.lib().hg_raster_backward_accum_bytes(P), dtype=torch.uint8, device=dev)
+            s = _inputs(P, fullP, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, False, render_geo, debug,
+                        background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D,
+                        sh, colors, all_maps, opacities, scales, rotations, cov3D_precomp)
+            rc = _lib.lib().hg_raster_backward(
+                ctypes.byref(s), int(R), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                _ptr(all_map_pixels), _ptr(dL_dout_color), _ptr(dL_dout_all_map), _ptr(dL_dout_plane_depth),
+                _ptr(dL_dout_invdepth) if has_depth_grad else None, _ptr(accum),
+                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
+                _ptr(dL_dinvdepths) if has_depth_grad else None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
+                _ptr(dL_dscales), _ptr(dL_drotations), _ptr(dL_dall_map), stream)
+        _lib.check(rc, "rasterize_gaussians_backward")
+    return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
+            dL_dall_map)
+
+
+def mark_visible(positions, viewmatrix, projmatrix):
+    """markVisible (rasterizer_impl.cu:145-157).  The reference's Python calls
+    `_C.mark_visible` (diff_gaussian_rasterization/__init__.py:187) but never
+    binds it (ext.cpp:15-18); it is bound here."""
+    positions, viewmatrix, projmatrix = _f32(positions), _f32(viewmatrix), _f32(projmatrix)
+    P = positions.size(0)
+    present = torch.empty((P,), dtype=torch.bool, device=positions.device)
+    if P:
+        with torch.cuda.device(positions.device):
+            rc = _lib.lib().hg_mark_visible(P, _ptr(positions), _ptr(viewmatrix), _ptr(projmatrix), present.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "mark_visible")
+    return present

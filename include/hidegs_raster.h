@@ -1,0 +1,197 @@
+/*
+ * hidegs_raster.h — C-ABI of the B200-native HiDeGS rasterizer hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes only POD
+ * (device pointers, sizes, scalars, a cudaStream_t passed as void*) and
+ * returns an int status (0 = ok, otherwise see hg_status).  No C++ exceptions
+ * cross the ABI and no torch types appear in any signature.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the
+ * reference tree, submodules/hierarchy-rasterizer/):
+ *
+ *   hg_raster_forward   <- CudaRasterizer::Rasterizer::forward
+ *                          (cuda_rasterizer/rasterizer.h:33-72,
+ *                           cuda_rasterizer/rasterizer_impl.cu:203-405), as
+ *                          driven by RasterizeGaussiansCUDA
+ *                          (rasterize_points.cu:35-147)
+ *   hg_raster_backward  <- CudaRasterizer::Rasterizer::backward
+ *                          (cuda_rasterizer/rasterizer.h:74-117,
+ *                           cuda_rasterizer/rasterizer_impl.cu:409-535), as
+ *                          driven by RasterizeGaussiansBackwardCUDA
+ *                          (rasterize_points.cu:149-279)
+ *   hg_mark_visible     <- CudaRasterizer::Rasterizer::markVisible
+ *                          (cuda_rasterizer/rasterizer_impl.cu:145-157)
+ *   hg_alloc_fn         <- std::function<char*(size_t)> geometryBuffer /
+ *                          binningBuffer / imageBuffer
+ *                          (cuda_rasterizer/rasterizer.h:34-36)
+ *   hg_raster_layout    <- GeometryState/ImageState/BinningState::fromChunk
+ *                          (cuda_rasterizer/rasterizer_impl.cu:159-199); the
+ *                          layout itself is this library's own (SoA + one
+ *                          64-byte splat record per slot) and is only exposed
+ *                          so that parity tests can read keys / ranges.
+ *
+ * Conventions kept from the reference: a NULL pointer means "tensor absent"
+ * (rasterizer_impl.cu:376,471,506; forward.cu:276,290,328,402,503); matrices
+ * are the 16 floats of a row-vector-convention 4x4 (cameras.py:127-129) read
+ * as in auxiliary.h:83-102; quaternions are NOT normalised here
+ * (forward.cu:190).
+ */
+#ifndef HIDEGS_RASTER_H
+#define HIDEGS_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HG_API __attribute__((visibility("default")))
+#else
+#define HG_API
+#endif
+
+#define HG_NUM_CHANNELS 3 /* config.h:15 */
+#define HG_NUM_ALL_MAP 5  /* config.h:16 */
+#define HG_BLOCK_X 16     /* config.h:17 */
+#define HG_BLOCK_Y 16     /* config.h:18 */
+
+enum hg_status {
+  HG_OK = 0,
+  HG_ERR_INVALID_ARG = 1, /* bad shape / missing mandatory pointer        */
+  HG_ERR_CUDA = 2,        /* a CUDA runtime call or kernel launch failed  */
+  HG_ERR_ALLOC = 3        /* a scratch allocator callback returned NULL   */
+};
+
+/* Scratch allocator: must return a device pointer to >= bytes bytes that
+ * stays valid until the matching backward call has completed. */
+typedef char *(*hg_alloc_fn)(void *ctx, size_t bytes);
+
+/* Per-call inputs shared by forward and backward (all pointers are device
+ * pointers, nullable where the reference accepts an empty tensor). */
+typedef struct hg_raster_inputs {
+  int32_t P;      /* rendered slots: indices ? len(indices) : N           */
+  int32_t N;      /* rows of means3D ("fullP", rasterize_points.cu:184)   */
+  int32_t D;      /* active SH degree                                     */
+  int32_t M;      /* SH coefficients per channel (0 if shs absent)        */
+  int32_t W, H;   /* image size                                           */
+  float tan_fovx, tan_fovy;
+  float scale_modifier;
+  int32_t prefiltered;
+  int32_t render_geo;
+  int32_t debug;  /* synchronise + check after every launch               */
+  const float *background;     /* [3]                                     */
+  const float *viewmatrix;     /* [16]                                    */
+  const float *projmatrix;     /* [16]                                    */
+  const float *campos;         /* [3]                                     */
+  const int32_t *indices;        /* [P] or NULL                           */
+  const int32_t *parent_indices; /* [P] or NULL                           */
+  const float *ts;               /* interpolation weights or NULL         */
+  const int32_t *kids;           /* num_node_kids or NULL                 */
+  const float *means3D;        /* [N,3]                                   */
+  const float *shs;            /* [N,M,3] or NULL                         */
+  const float *colors_precomp; /* [N,3] or NULL                           */
+  const float *all_map;        /* [P,5] or NULL                           */
+  const float *opacities;      /* [N,1]                                   */
+  const float *scales;         /* [N,3] or NULL                           */
+  const float *rotations;      /* [N,4] or NULL                           */
+  const float *cov3D_precomp;  /* [N,6] or NULL                           */
+} hg_raster_inputs;
+
+/* Byte offsets of the arrays inside the three opaque scratch buffers
+ * (test/diagnostic accessor). */
+typedef struct hg_raster_layout {
+  /* geometry buffer */
+  size_t geom_bytes;
+  size_t depths;        /* f32[P]                                         */
+  size_t tiles_touched; /* u32[P]                                         */
+  size_t point_offsets; /* u32[P] inclusive prefix sum                    */
+  size_t rects;         /* i32[P,2]                                       */
+  size_t cov3D;         /* f32[P,6]                                       */
+  size_t clamped;       /* u8[P] bit0..2 = r,g,b clamped                  */
+  size_t records;       /* f32[P,16] splat record, see DESIGN.md          */
+  size_t scan_temp;
+  size_t scan_temp_bytes;
+  /* image buffer */
+  size_t image_bytes;
+  size_t final_T;   /* f32[H*W]                                           */
+  size_t n_contrib; /* u32[H*W]                                           */
+  size_t ranges;    /* u32[T,2]                                           */
+  /* binning buffer (sized for R instances) */
+  size_t binning_bytes;
+  size_t keys_unsorted; /* u64[R]                                         */
+  size_t keys;          /* u64[R]                                         */
+  size_t vals_unsorted; /* u32[R]                                         */
+  size_t vals;          /* u32[R] == reference point_list                 */
+  size_t sort_temp;
+  size_t sort_temp_bytes;
+} hg_raster_layout;
+
+HG_API int hg_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R,
+                           hg_raster_layout *out);
+
+/* Forward.  Outputs are fully written by the call (no pre-zeroing needed):
+ *   out_color [3,H,W], out_invdepth [1,H,W] or NULL (do_depth=false),
+ *   out_observe [P] i32, out_all_map [5,H,W], out_plane_depth [1,H,W],
+ *   radii [P] i32.  *num_rendered receives R (host int, one stream sync as in
+ *   rasterizer_impl.cu:329-330). */
+HG_API int hg_raster_forward(const hg_raster_inputs *in,
+                      hg_alloc_fn geom_alloc, void *geom_ctx,
+                      hg_alloc_fn binning_alloc, void *binning_ctx,
+                      hg_alloc_fn image_alloc, void *image_ctx,
+                      float *out_color, float *out_invdepth,
+                      int32_t *out_observe, float *out_all_map,
+                      float *out_plane_depth, int32_t *radii,
+                      int32_t *num_rendered, void *stream);
+
+/* Backward.  `accum` is caller-provided scratch of
+ * hg_raster_backward_accum_bytes(P) bytes (contents ignored).  All gradient
+ * outputs are fully written (rows of culled Gaussians receive zeros), except
+ * when in->indices != NULL, in which case the caller must pre-zero them
+ * (rows that no slot maps to are not touched).  dL_dconic and dL_dinvdepths
+ * may be NULL. */
+HG_API size_t hg_raster_backward_accum_bytes(int32_t P);
+
+HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
+                       const int32_t *radii,
+                       const char *geom_buffer, const char *binning_buffer,
+                       const char *image_buffer,
+                       const float *all_map_pixels,     /* [5,H,W]        */
+                       const float *dL_dpix,            /* [3,H,W]        */
+                       const float *dL_dout_all_map,    /* [5,H,W]        */
+                       const float *dL_dout_plane_depth,/* [1,H,W]        */
+                       const float *dL_dout_invdepth,   /* [1,H,W] or NULL*/
+                       char *accum,
+                       float *dL_dmeans2D,   /* [N,3] */
+                       float *dL_dconic,     /* [N,2,2] or NULL */
+                       float *dL_dopacity,   /* [N,1] */
+                       float *dL_dcolors,    /* [N,3] */
+                       float *dL_dinvdepths, /* [N,1] or NULL */
+                       float *dL_dmeans3D,   /* [N,3] */
+                       float *dL_dcov3D,     /* [N,6] */
+                       float *dL_dsh,        /* [N,M,3] */
+                       float *dL_dscales,    /* [N,3] */
+                       float *dL_drotations, /* [N,4] */
+                       float *dL_dall_map,   /* [N,5] */
+                       void *stream);
+
+/* Frustum test of rasterizer_impl.cu:54-66 (present[i] = p_view.z > 0.2). */
+HG_API int hg_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,
+                    const float *projmatrix, uint8_t *present, void *stream);
+
+/* Launch counter: number of kernels this library has launched since the last
+ * hg_reset_launch_count() (used for bench.py's gpu_launches). */
+HG_API int64_t hg_launch_count(void);
+HG_API void hg_reset_launch_count(void);
+
+/* Text of the last error on this host thread ("" if none). */
+HG_API const char *hg_last_error(void);
+
+/* Library identification: "hidegs_b200 <version> sm_100a". */
+HG_API const char *hg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIDEGS_RASTER_H */
