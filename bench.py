@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the rasterizer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic 1M-Gaussian
+scene, SH degree 3, one 1920x1080 view per step, rasterizer forward + backward with
+all outputs on (colour, 5-channel geometry map, plane depth, inverse depth).
+One "step" = one view forward+backward per GPU; with N > 1 every rank renders its own
+camera of the replicated scene and the ranks all-reduce the 59-float/Gaussian gradient
+arena over NCCL (view-sharded data parallelism, weak scaling).
+
+Rank 0 prints ONE JSON line:
+  value     fwd+bwd Mpix/s with every input resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public API (GaussianRasterizer + autograd) with the
+            step's host inputs (camera matrices + ground-truth image, pinned) copied H2D
+            and the loss read back D2H inside the timed region
+  roofline  dominant kernel: algorithmic bytes / live CUDA-event time vs measured HBM peak
+  cpu_baseline  the CPU restatement (oracle/) timed on the host cores on the same workload
+
+`--impl reference` runs the UNMODIFIED reference CUDA rasterizer rebuilt for sm_100
+(oracle/_ref/ref_rasterizer_C.so) on the same inputs / metric; the reference has no CPU
+implementation of this path, so its own implementation is timed on the same GPU.  If that
+build is absent the CPU restatement is timed instead (kind "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_GAUSS = int(os.environ.get("HG_BENCH_N", 1_000_000))
+WIDTH = int(os.environ.get("HG_BENCH_W", 1920))
+HEIGHT = int(os.environ.get("HG_BENCH_H", 1080))
+METRIC = "fwd+bwd Mpix/s @1M Gaussians 1080p"
+UNIT = "Mpix/s"
+
+
+# ----------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def camera_for(rank, step):
+    """Rank/step specific camera around the config-2 pose (rank 0, step 0 == the BASELINE pose)."""
+    from hidegs_b200 import synthetic as syn
+    dx = 0.25 * ((rank * 7 + step * 3) % 5 - 2) if (rank or step) else 0.0
+    dy = 0.15 * ((rank * 5 + step) % 3 - 1) if (rank or step) else 0.0
+    return syn.default_camera(WIDTH, HEIGHT, eye=(dx, dy, -5.0))
+
+
+def stage_bytes(N, Nv, R, HW, T):
+    """Algorithmic bytes per launch of each stage."""
+    return {
+        "preprocess_fwd": 56 * N + 335 * Nv,   # always: xyz+scale+rot+opacity 44, radii/tiles/observe 12; visible: SH 192, all_map 20, record 64, cov3D 24, depth/rect/clamp 13, ...
+        "scan": 8 * N,
+        "binning": 12 * N + 12 * Nv + (12 + 24 + 8) * R + 8 * T,   # emit 12R, sort >= 24R, ranges 8R
+        "blend_fwd": 68 * R + 48 * HW + 8 * T,  # id 4 + record 64 per instance; 12 floats out per pixel
+        "accum_zero": 64 * N,
+        "blend_bwd": 68 * R + 72 * HW + 128 * Nv + 8 * T,  # gathers; 18 floats in per pixel; accumulator RMW
+        "preprocess_bwd": 4 * N + (64 + 44 + 24 + 192 + 1 + 32) * Nv + 324 * N,  # rows read + all gradient rows written
+    }
+
+
+# ----------------------------------------------------------------------------- arms
+def load_scene(dev):
+    from hidegs_b200 import synthetic as syn
+    sc = syn.make_scene(N_GAUSS, seed=0)
+    return {k: v.to(dev) for k, v in sc.items()}, sc
+
+
+def op_tuple(C, scene, cam, all_map, dev, bg):
+    e_i = torch.empty(0, dtype=torch.int32, device=dev)
+    e_f = torch.empty(0, dtype=torch.float32, device=dev)
+    return (bg, e_i, e_i, e_f, e_i, scene["means3D"], e_f, all_map, scene["opacity"], scene["scales"],
+            scene["rotations"], 1.0, e_f, cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy,
+            HEIGHT, WIDTH, scene["shs"], 3, cam.camera_center, False, True, False, True)
+
+
+def bwd_tuple(fa, fwd, g):
+    (bg, indices, parents, ts, kids, means3D, colors, all_map, opacity, scales, rotations, sm, cov3D, view, proj, tfx,
+     tfy, H, W, sh, degree, campos, prefiltered, render_geo, debug, do_depth) = fa
+    R, color, radii, observe, out_all_map, plane_depth, geom, binning, img, invdepth = fwd
+    return (bg, out_all_map, indices, parents, ts, kids, means3D, radii, colors, all_map, opacity, scales, rotations, sm,
+            cov3D, view, proj, tfx, tfy, g["color"], g["all_map"], g["plane_depth"], g["invdepth"], sh, degree, campos,
+            geom, R, binning, img, render_geo, debug)
+
+
+class RefAutograd(torch.autograd.Function):
+    """Autograd glue around the reference's `_C` operators, as its own
+    diff_gaussian_rasterization/__init__.py:42-155 wires them (that Python file is not
+    shipped to the GPU box; only the compiled operators are)."""
+
+    @staticmethod
+    def forward(ctx, C, fa, means3D, sh, opacity, scales, rotations, all_map):
+        out = C.rasterize_gaussians(*fa)
+        ctx.C, ctx.fa, ctx.out = C, fa, out
+        ctx.mark_non_differentiable(out[2], out[3])
+        return out[1], out[2], out[3], out[4], out[5], out[9]
+
+    @staticmethod
+    def backward(ctx, g_color, _r, _o, g_all_map, g_plane, g_inv):
+        g = dict(color=g_color.contiguous(), all_map=g_all_map.contiguous(), plane_depth=g_plane.contiguous(),
+                 invdepth=g_inv.contiguous())
+        (d2, dcol, dop, dm3, dcov, dsh, dsc, drot, dam) = ctx.C.rasterize_gaussians_backward(*bwd_tuple(ctx.fa, ctx.out, g))
+        return None, None, dm3, dsh, dop, dsc, drot, dam
+
+
+def run_gpu_arm(args, impl):
+    import torch.distributed as dist
+    from hidegs_b200 import _lib, synthetic as syn
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if impl == "reference" and rank != 0:
+        return  # the reference is single-GPU: rank 0 alone runs it
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ddp = world > 1 and impl == "ours"
+    if ddp:
+        dist.init_process_group("nccl", device_id=dev)
+
+    if impl == "ours":
+        from hidegs_b200.diff_gaussian_rasterization import _C as C
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        import ref_rasterizer_C as C
+
+    scene, scene_cpu = load_scene(dev)
+    bg = torch.zeros(3, device=dev)
+    K, Wm = args.steps, args.warmup
+    cams = [camera_for(rank, s) for s in range(K + Wm)]
+    all_maps = [syn.geometry_all_map(scene["means3D"], scene["scales"], scene["rotations"], c.to(dev)) for c in cams[:1]]
+    g = {k: v.to(dev) for k, v in syn.upstream_grads(WIDTH, HEIGHT, seed=1).items()}
+    HW = WIDTH * HEIGHT
+    arena = torch.empty(59 * N_GAUSS, device=dev) if ddp else None
+
+    def pack_and_allreduce(grads):
+        # (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map)
+        off = 0
+        for t in (grads[3], grads[5], grads[2], grads[6], grads[7]):  # xyz 3, sh 48, opacity 1, scale 3, rot 4 = 59
+            n = t.numel()
+            arena[off:off + n].copy_(t.reshape(-1))
+            off += n
+        dist.all_reduce(arena)
+
+    # ------------------------------------------------ device-resident leg ("value")
+    def step_resident(s):
+        cam = cams[s]
+        fa = op_tuple(C, scene, cam, all_maps[0], dev, bg)
+        fwd = C.rasterize_gaussians(*fa)
+        grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
+        if ddp:
+            pack_and_allreduce(grads)
+        return fwd
+
+    for c in cams:
+        c.to(dev)
+    for s in range(Wm):
+        fwd = step_resident(s)
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if impl == "ours":
+        _lib.lib().hg_reset_launch_count()
+        _lib.profile_enable(True)
+        _lib.profile_collect()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    torch.cuda.synchronize()
+    e0.record()
+    for s in range(Wm, Wm + K):
+        fwd = step_resident(s)
+    e1.record()
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches, stages = None, None
+    if impl == "ours":
+        _lib.profile_enable(False)
+        stages = _lib.profile_collect()
+        launches = int(_lib.lib().hg_launch_count())
+    R = int(fwd[0])
+    Nv = int((fwd[2] > 0).sum())
+    t_ms = torch.tensor([ms_total], device=dev)
+    if ddp:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_step = float(t_ms) / K
+    value = world * HW / (ms_step * 1e-3) / 1e6 if impl == "ours" else HW / (ms_step * 1e-3) / 1e6
+
+    # ------------------------------------------------ end-to-end leg ("e2e"): public API + host inputs
+    if impl == "ours":
+        from hidegs_b200.diff_gaussian_rasterization import GaussianRasterizer
+    params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacity", "scales", "rotations")}
+    gen = torch.Generator().manual_seed(7)
+    gt_host = torch.rand(3, HEIGHT, WIDTH, generator=gen).pin_memory()
+    cam_host = [torch.cat([c.world_view_transform.flatten().cpu(), c.full_proj_transform.flatten().cpu(),
+                           c.camera_center.cpu()]).pin_memory() for c in cams]
+    w_geo, w_pd, w_inv = g["all_map"] * 1e-3, g["plane_depth"] * 1e-3, g["invdepth"] * 1e-3
+    h2d_bytes = gt_host.numel() * 4 + cam_host[0].numel() * 4
+    am_param = all_maps[0].clone().requires_grad_(True)
+
+    def step_e2e(s):
+        cam = cams[s]
+        cd = cam_host[s].to(dev, non_blocking=True)
+        gt = gt_host.to(dev, non_blocking=True)
+        view, proj, campos = cd[:16].view(4, 4), cd[16:32].view(4, 4), cd[32:35]
+        for p in params.values():
+            p.grad = None
+        if impl == "ours":
+            rs = syn.raster_settings(cam, dev)._replace(viewmatrix=view, projmatrix=proj, campos=campos, bg=bg)
+            means2D = torch.zeros_like(params["means3D"], requires_grad=True)
+            color, radii, obs, amap, pdepth, inv = GaussianRasterizer(rs)(
+                means3D=params["means3D"], means2D=means2D, opacities=params["opacity"], shs=params["shs"],
+                scales=params["scales"], rotations=params["rotations"], all_map=am_param)
+        else:
+            e_i = torch.empty(0, dtype=torch.int32, device=dev)
+            e_f = torch.empty(0, dtype=torch.float32, device=dev)
+            fa = (bg, e_i, e_i, e_f, e_i, params["means3D"], e_f, am_param, params["opacity"], params["scales"],
+                  params["rotations"], 1.0, e_f, view, proj, cam.tanfovx, cam.tanfovy, HEIGHT, WIDTH, params["shs"], 3,
+                  campos, False, True, False, True)
+            color, radii, obs, amap, pdepth, inv = RefAutograd.apply(C, fa, params["means3D"], params["shs"],
+                                                                     params["opacity"], params["scales"],
+                                                                     params["rotations"], am_param)
+        loss = (color - gt).abs().mean() + (amap * w_geo).mean() + (pdepth * w_pd).mean() + (inv * w_inv).mean()
+        loss.backward()
+        if ddp:
+            pack_and_allreduce((None, None, params["opacity"].grad, params["means3D"].grad, None, params["shs"].grad,
+                                params["scales"].grad, params["rotations"].grad))
+        return float(loss.item())  # D2H read of the step's result
+
+    for s in range(Wm):
+        step_e2e(s)
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    e0.record()
+    for s in range(Wm, Wm + K):
+        step_e2e(s)
+    e1.record()
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if ddp:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t2) / K
+    e2e_value = (world if impl == "ours" else 1) * HW / (ms_e2e * 1e-3) / 1e6
+
+    if rank != 0:
+        if ddp:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world if impl == "ours" else 1,
+        "steps": K, "warmup": Wm, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1M Gaussians, SH degree 3, one 1920x1080 view fwd+bwd per GPU per step"
+                               if (N_GAUSS, WIDTH, HEIGHT) == (1_000_000, 1920, 1080) else
+                               "REDUCED %d Gaussians %dx%d" % (N_GAUSS, WIDTH, HEIGHT),
+                   "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "visible": Nv, "num_rendered": R,
+                   "outputs": "color+all_map+plane_depth+invdepth", "parallelism": "view-sharded dp%d" % world,
+                   "l2": "inputs_exceed_l2 (SH 192 MB + records 64 MB + sort buffers > 126 MB)"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "api": "GaussianRasterizer(settings)(...) + L1 loss + autograd backward"},
+    }
+    if impl == "ours":
+        bytes_per = stage_bytes(N_GAUSS, Nv, R, HW, ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16))
+        peak, how = measured_peaks()
+        per_stage = {k: round(v[0] / max(v[1], 1), 4) for k, v in stages.items()}
+        dom = max(stages, key=lambda k: stages[k][0])
+        dom_ms = stages[dom][0] / max(stages[dom][1], 1)
+        achieved = bytes_per[dom] / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": how,
+                            "algorithmic_bytes": bytes_per[dom], "kernel_ms": round(dom_ms, 4),
+                            "share_of_step": round(stages[dom][0] / max(sum(v[0] for v in stages.values()), 1e-9), 3),
+                            "stage_ms": per_stage,
+                            "note": "blend kernels are FP32-issue / shared-memory bound, not HBM bound (DESIGN.md §4)"}
+        line["gpu_launches"] = launches
+        line["cpu_baseline"] = cpu_baseline(scene_cpu)
+    else:
+        line["impl"] = "reference"
+        line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": 0, "kind": "reference",
+                                "sample": "unmodified reference CUDA rasterizer rebuilt for sm_100 (oracle/_ref), full "
+                                          "workload on the same B200; the reference has no CPU implementation of this path"}
+    print(json.dumps(line), flush=True)
+    if ddp:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(scene_cpu, iters=1, tile_step=1):
+    """CPU restatement (oracle port) on the host cores, same workload."""
+    from hidegs_b200 import synthetic as syn
+    from oracle.raster_oracle import OracleRasterizer
+    cores = os.cpu_count() or 1
+    cam = syn.default_camera(WIDTH, HEIGHT)
+    am = syn.geometry_all_map(scene_cpu["means3D"], scene_cpu["scales"], scene_cpu["rotations"], cam)
+    o = OracleRasterizer(bg=np.zeros(3, np.float32), viewmatrix=cam.world_view_transform.numpy(),
+                         projmatrix=cam.full_proj_transform.numpy(), campos=cam.camera_center.numpy(),
+                         means3D=scene_cpu["means3D"].numpy(), opacities=scene_cpu["opacity"].numpy(),
+                         image_height=HEIGHT, image_width=WIDTH, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                         shs=scene_cpu["shs"].numpy(), all_map=am.numpy(), scales=scene_cpu["scales"].numpy(),
+                         rotations=scene_cpu["rotations"].numpy(), sh_degree=3, nthreads=cores)
+    g = syn.upstream_grads(WIDTH, HEIGHT, seed=1)
+    gn = {k: v.numpy() for k, v in g.items()}
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        o.forward(tile_step=tile_step)
+        o.backward(gn["color"], gn["all_map"], gn["plane_depth"], gn["invdepth"], tile_step=tile_step)
+        ts.append(time.perf_counter() - t0)
+    t = float(np.median(ts))
+    frac = 1.0 / tile_step
+    return {"value": round(WIDTH * HEIGHT * frac / t / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "seconds": round(t, 2),
+            "sample": "oracle/raster_oracle.c (C restatement of the reference algorithm), %d pthreads, full scene, "
+                      "%s fwd+bwd, %d iteration(s)" % (cores, "every %d-th tile of the view" % tile_step if tile_step > 1 else "whole 1080p view", iters)}
+
+
+def run_cpu_reference(args):
+    """--impl reference without the reference CUDA build: time the CPU restatement."""
+    from hidegs_b200 import synthetic as syn
+    sc = syn.make_scene(N_GAUSS, seed=0)
+    cb = cpu_baseline(sc, iters=max(1, min(args.steps, 3)))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(cb["seconds"] * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 1M Gaussians, SH degree 3, one 1920x1080 view fwd+bwd"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    if args.impl == "reference":
+        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_rasterizer_C.so"))
+        if rank != 0:
+            return
+        if have_ref and torch.cuda.is_available():
+            run_gpu_arm(args, "reference")
+        else:
+            run_cpu_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU fallback")
+    run_gpu_arm(args, "ours")
+
+
+if __name__ == "__main__":
+    main()

@@ -43,7 +43,10 @@ class RasterLayout(ctypes.Structure):
 EXPORTED_SYMBOLS = (
     "hg_raster_layout_query", "hg_raster_forward", "hg_raster_backward_accum_bytes", "hg_raster_backward",
     "hg_mark_visible", "hg_launch_count", "hg_reset_launch_count", "hg_last_error", "hg_version",
+    "hg_profile_enable", "hg_profile_collect",
 )
+
+STAGES = ("preprocess_fwd", "scan", "binning", "blend_fwd", "accum_zero", "blend_bwd", "preprocess_bwd")
 
 _lib = None
 
@@ -79,6 +82,10 @@ def lib():
     L.hg_last_error.restype = ctypes.c_char_p
     L.hg_version.argtypes = []
     L.hg_version.restype = ctypes.c_char_p
+    L.hg_profile_enable.argtypes = [ctypes.c_int]
+    L.hg_profile_enable.restype = None
+    L.hg_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+    L.hg_profile_collect.restype = ctypes.c_int
     _lib = L
     return L
 
@@ -94,3 +101,16 @@ def layout(P, W, H, R=0):
     out = RasterLayout()
     check(lib().hg_raster_layout_query(P, W, H, R, ctypes.byref(out)), "hg_raster_layout_query")
     return out
+
+
+def profile_enable(on):
+    lib().hg_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """{stage: (total_ms, launches)} since the last collect."""
+    n = len(STAGES)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_int64 * n)()
+    check(lib().hg_profile_collect(ms, cnt, n), "hg_profile_collect")
+    return {STAGES[i]: (ms[i], cnt[i]) for i in range(n)}

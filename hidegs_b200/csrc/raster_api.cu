@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace hg {
 
@@ -23,6 +25,31 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static constexpr size_t kAlign = 256;
+
+// ---- optional per-stage device timing (CUDA events on the launch stream) ------
+// Events are only recorded while profiling is enabled and are resolved lazily in
+// hg_profile_collect(), so the timed region gains no host synchronisation.
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+
+struct StageTimer {
+  int stage; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on;
+  StageTimer(int stage_, cudaStream_t st_) : stage(stage_), st(st_), on(g_prof_on.load() != 0) {
+    if (on) {
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+      cudaEventRecord(a, st);
+    }
+  }
+  ~StageTimer() {
+    if (on) {
+      cudaEventRecord(b, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof.push_back({stage, a, b});
+    }
+  }
+};
 
 static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_layout* L) {
   memset(L, 0, sizeof(*L));
@@ -166,9 +193,15 @@ int hg_raster_forward(const hg_raster_inputs* in, hg_alloc_fn geom_alloc, void* 
   const float focal_x = in->W / (2.0f * in->tan_fovx);
   const dim3 grid((in->W + HG_BLOCK_X - 1) / HG_BLOCK_X, (in->H + HG_BLOCK_Y - 1) / HG_BLOCK_Y, 1);
 
-  rc = launch_preprocess_fwd(*in, g, radii, out_observe, grid, focal_x, focal_y, stream);
+  {
+    StageTimer t(HG_STAGE_PREPROCESS_FWD, stream);
+    rc = launch_preprocess_fwd(*in, g, radii, out_observe, grid, focal_x, focal_y, stream);
+  }
   if (rc) return rc;
-  rc = launch_scan(g, in->P, L.scan_temp_bytes, stream, in->debug != 0);
+  {
+    StageTimer t(HG_STAGE_SCAN, stream);
+    rc = launch_scan(g, in->P, L.scan_temp_bytes, stream, in->debug != 0);
+  }
   if (rc) return rc;
 
   // R is part of the API contract (returned to Python as an int,
@@ -189,9 +222,13 @@ int hg_raster_forward(const hg_raster_inputs* in, hg_alloc_fn geom_alloc, void* 
       return HG_ERR_ALLOC;
     }
     b = bin_from(align_ptr(bin_raw, kAlign), LB);
-    rc = launch_binning(*in, g, b, img, radii, (int)R, grid, LB.sort_temp_bytes, stream);
+    {
+      StageTimer t(HG_STAGE_BINNING, stream);
+      rc = launch_binning(*in, g, b, img, radii, (int)R, grid, LB.sort_temp_bytes, stream);
+    }
     if (rc) return rc;
   }
+  StageTimer t(HG_STAGE_BLEND_FWD, stream);
   return launch_blend_fwd(*in, g, b, img, grid, focal_x, focal_y, out_color, out_invdepth,
                           out_observe, out_all_map, out_plane_depth, R == 0, stream);
 }
@@ -230,16 +267,48 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
   const dim3 grid((in->W + HG_BLOCK_X - 1) / HG_BLOCK_X, (in->H + HG_BLOCK_Y - 1) / HG_BLOCK_Y, 1);
 
   float* acc = (float*)align_ptr(accum, kAlign);
-  HG_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)in->P * HG_ACC_FLOATS * sizeof(float), stream));
+  {
+    StageTimer t(HG_STAGE_ACCUM_ZERO, stream);
+    HG_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)in->P * HG_ACC_FLOATS * sizeof(float), stream));
+  }
   if (R > 0) {
+    StageTimer t(HG_STAGE_BLEND_BWD, stream);
     rc = launch_blend_bwd(*in, g, b, img, grid, focal_x, focal_y, all_map_pixels, dL_dpix,
                           dL_dout_all_map, dL_dout_plane_depth, dL_dout_invdepth, acc, stream);
     if (rc) return rc;
   }
+  StageTimer t(HG_STAGE_PREPROCESS_BWD, stream);
   return launch_preprocess_bwd(*in, g, radii, focal_x, focal_y, acc, dL_dout_invdepth != nullptr,
                                dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
                                dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
                                dL_dall_map, stream);
+}
+
+void hg_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+int hg_profile_collect(double* ms_per_stage, int64_t* count_per_stage, int n_stages) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < n_stages; ++i) {
+    if (ms_per_stage) ms_per_stage[i] = 0.0;
+    if (count_per_stage) count_per_stage[i] = 0;
+  }
+  int rc = HG_OK;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.a, r.b);
+    if (e != cudaSuccess) {
+      set_error("hg_profile_collect: %s", cudaGetErrorString(e));
+      rc = HG_ERR_CUDA;
+    } else if (r.stage >= 0 && r.stage < n_stages) {
+      if (ms_per_stage) ms_per_stage[r.stage] += ms;
+      if (count_per_stage) count_per_stage[r.stage] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return rc;
 }
 
 int hg_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

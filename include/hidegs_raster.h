@@ -107,7 +107,7 @@ typedef struct hg_raster_layout {
   size_t depths;        /* f32[P]                                         */
   size_t tiles_touched; /* u32[P]                                         */
   size_t point_offsets; /* u32[P] inclusive prefix sum                    */
-  size_t rects;         /* i32[P,2]                                       */
+  size_t rects;         /* u32[P,2] tile bounds: minx|miny<<16, maxx|maxy<<16 */
   size_t cov3D;         /* f32[P,6]                                       */
   size_t clamped;       /* u8[P] bit0..2 = r,g,b clamped                  */
   size_t records;       /* f32[P,16] splat record, see DESIGN.md          */
@@ -149,7 +149,8 @@ HG_API int hg_raster_forward(const hg_raster_inputs *in,
  * hg_raster_backward_accum_bytes(P) bytes (contents ignored).  All gradient
  * outputs are fully written (rows of culled Gaussians receive zeros), except
  * when in->indices != NULL, in which case the caller must pre-zero them
- * (rows that no slot maps to are not touched).  dL_dconic and dL_dinvdepths
+ * (rows that no slot maps to are not touched; the same holds when
+ * in->parent_indices != NULL, because parents receive atomic pushes).  dL_dconic and dL_dinvdepths
  * may be NULL. */
 HG_API size_t hg_raster_backward_accum_bytes(int32_t P);
 
@@ -184,6 +185,25 @@ HG_API int hg_mark_visible(int32_t P, const float *means3D, const float *viewmat
  * hg_reset_launch_count() (used for bench.py's gpu_launches). */
 HG_API int64_t hg_launch_count(void);
 HG_API void hg_reset_launch_count(void);
+
+/* Optional per-stage device timing.  While enabled, every stage launched by
+ * hg_raster_forward / hg_raster_backward is bracketed by CUDA events on the
+ * launch stream (no host synchronisation is added); hg_profile_collect()
+ * synchronises, sums the elapsed milliseconds and launch counts per stage into
+ * the caller's arrays (n_stages entries, indexed by hg_stage) and clears the
+ * record.  Used by bench.py for the live roofline numbers. */
+enum hg_stage {
+  HG_STAGE_PREPROCESS_FWD = 0,
+  HG_STAGE_SCAN = 1,
+  HG_STAGE_BINNING = 2, /* key emit + radix sort + tile ranges */
+  HG_STAGE_BLEND_FWD = 3,
+  HG_STAGE_ACCUM_ZERO = 4,
+  HG_STAGE_BLEND_BWD = 5,
+  HG_STAGE_PREPROCESS_BWD = 6,
+  HG_STAGE_COUNT = 7
+};
+HG_API void hg_profile_enable(int on);
+HG_API int hg_profile_collect(double *ms_per_stage, int64_t *count_per_stage, int n_stages);
 
 /* Text of the last error on this host thread ("" if none). */
 HG_API const char *hg_last_error(void);

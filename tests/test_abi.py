@@ -1,0 +1,117 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every
+symbol include/hidegs_raster.h declares, and rejects bad arguments before any
+CUDA work (mirrors the reference's AT_ERROR / Exception paths,
+rasterize_points.cu:64-66, diff_gaussian_rasterization/__init__.py:198-202)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from hidegs_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols(path):
+    text = open(path).read()
+    return sorted(set(re.findall(r"HG_API[^;(]*?\b(hg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = []
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if h.endswith(".h"):
+            names += header_symbols(os.path.join(ROOT, "include", h))
+    assert "hg_raster_forward" in names and "hg_raster_backward" in names
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in include/ but not exported" % n
+    assert set(_lib.EXPORTED_SYMBOLS) <= set(names)
+    assert b"sm_100a" in lib.hg_version()
+
+
+def test_layout_query_is_consistent():
+    L = _lib.layout(1000, 1920, 1080, 5000)
+    offs = [L.depths, L.tiles_touched, L.point_offsets, L.rects, L.cov3D, L.clamped, L.records, L.scan_temp]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
+    assert L.records - L.clamped >= 1000 and L.geom_bytes >= L.records + 64 * 1000
+    assert L.ranges + 8 * 120 * 68 <= L.image_bytes
+    assert L.keys - L.keys_unsorted >= 8 * 5000 and L.vals - L.vals_unsorted >= 4 * 5000
+    # (the CUB temp-size query needs a device, so sort_temp_bytes is 0 on a CPU-only box)
+    assert L.binning_bytes >= L.sort_temp + L.sort_temp_bytes
+    # binning layout only depends on R, geometry layout only on P
+    L2 = _lib.layout(1000, 1920, 1080, 0)
+    assert L2.records == L.records and L2.keys_unsorted == 0
+
+
+def test_layout_query_rejects_bad_sizes():
+    out = _lib.RasterLayout()
+    assert _lib.lib().hg_raster_layout_query(-1, 16, 16, 0, ctypes.byref(out)) == 1
+    assert _lib.lib().hg_raster_layout_query(1, 0, 16, 0, ctypes.byref(out)) == 1
+    assert b"bad argument" in _lib.lib().hg_last_error()
+
+
+def _dummy_alloc():
+    return _lib.ALLOC_FN(lambda ctx, n: None)
+
+
+def test_forward_validates_before_touching_the_gpu():
+    lib = _lib.lib()
+    s = _lib.RasterInputs()
+    s.P, s.N, s.W, s.H = 4, 4, 32, 32
+    cb = _dummy_alloc()
+    r = ctypes.c_int32(0)
+    # mandatory pointers missing
+    rc = lib.hg_raster_forward(ctypes.byref(s), cb, None, cb, None, cb, None, 1, None, 1, 1, 1, 1, ctypes.byref(r), None)
+    assert rc == 1 and b"mandatory" in lib.hg_last_error()
+    # both SH and precomputed colours (fake non-null pointers are never dereferenced)
+    for f in ("means3D", "opacities", "background", "viewmatrix", "projmatrix", "campos", "shs", "colors_precomp"):
+        setattr(s, f, 256)
+    s.M, s.D = 16, 3
+    rc = lib.hg_raster_forward(ctypes.byref(s), cb, None, cb, None, cb, None, 1, None, 1, 1, 1, 1, ctypes.byref(r), None)
+    assert rc == 1 and b"excatly one of either SHs" in lib.hg_last_error()
+    s.colors_precomp = None
+    rc = lib.hg_raster_forward(ctypes.byref(s), cb, None, cb, None, cb, None, 1, None, 1, 1, 1, 1, ctypes.byref(r), None)
+    assert rc == 1 and b"scale/rotation pair" in lib.hg_last_error()
+    s.scales, s.rotations = 256, 256
+    s.D = 4  # degree 4 does not fit 16 coefficients
+    rc = lib.hg_raster_forward(ctypes.byref(s), cb, None, cb, None, cb, None, 1, None, 1, 1, 1, 1, ctypes.byref(r), None)
+    assert rc == 1 and b"SH degree" in lib.hg_last_error()
+
+
+def test_python_api_surface_matches_reference():
+    import diff_gaussian_rasterization as d
+    assert d.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug", "render_indices", "parent_indices", "interpolation_weights",
+        "num_node_kids", "do_depth", "render_geo")
+    assert hasattr(d._C, "rasterize_gaussians") and hasattr(d._C, "rasterize_gaussians_backward")
+    rs = d.GaussianRasterizationSettings(*([None] * 18))
+    r = d.GaussianRasterizer(rs)
+    x = torch.zeros(2, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs"):
+        r(means3D=x, means2D=x, opacities=x[:, :1])
+    with pytest.raises(Exception, match="scale/rotation pair"):
+        r(means3D=x, means2D=x, opacities=x[:, :1], shs=torch.zeros(2, 16, 3))
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of falling back."""
+    import diff_gaussian_rasterization as d
+    e_i, e_f = torch.empty(0, dtype=torch.int32), torch.empty(0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        d._C.rasterize_gaussians(torch.zeros(3), e_i, e_i, e_f, e_i, torch.zeros(2, 3), e_f, e_f, torch.zeros(2, 1),
+                                 torch.ones(2, 3), torch.ones(2, 4), 1.0, e_f, torch.eye(4), torch.eye(4), 1.0, 1.0,
+                                 16, 16, torch.zeros(2, 16, 3), 3, torch.zeros(3), False, True, False, True)
+
+
+def test_product_package_never_imports_the_oracle():
+    """Nothing under hidegs_b200/ may reference oracle/ (the oracle is test infrastructure)."""
+    pkg = os.path.join(ROOT, "hidegs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "raster_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f

@@ -1,0 +1,306 @@
+"""GPU parity tests of the rasterizer hot path (run on the B200 box: `pytest -m gpu`).
+
+Every test calls the product path through the C-ABI (hidegs_b200._C -> ctypes ->
+libhidegs_b200.so) and compares with
+  * the UNMODIFIED reference CUDA rasterizer built for sm_100 (oracle/_ref, when present),
+  * golden fixtures produced by that reference (tests/golden/raster_ref_*.npz),
+  * the CPU restatement (oracle/raster_oracle.c) on small seeded scenes,
+and, at BASELINE.json's full size, through size-independent properties.
+
+Tolerances (BASELINE.json north_star): tile keys / sort order / tile ranges bit-exact;
+images and depths <= 1e-4 absolute; gradients <= 1e-3 relative.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import raster_utils as ru
+from hidegs_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+IMG_ATOL = 1e-4
+CASES = {
+    "plain": dict(n=6000, W=208, H=120, seed=21),
+    "hier": dict(n=6000, W=208, H=120, seed=22, with_hier=True),
+    "raw_indices": dict(n=6000, W=208, H=120, seed=23, with_hier=True, with_indices=True),
+    "ragged": dict(n=4000, W=203, H=117, seed=24),
+}
+
+
+def run_ours(case, dev, render_geo=True, do_depth=True, colors_precomp=None, backward=True):
+    fa = ru.op_args(case, dev, render_geo=render_geo, do_depth=do_depth, colors_precomp=colors_precomp)
+    fwd = ru.OUR_C.rasterize_gaussians(*fa)
+    grads = syn.upstream_grads(case["W"], case["H"], do_depth=do_depth)
+    bwd = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fa, fwd, grads, dev)) if backward else None
+    torch.cuda.synchronize()
+    return fa, fwd, grads, bwd
+
+
+def img_close(a, b, atol=IMG_ATOL, rtol=0.0, max_outliers=0):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    return int(bad.sum()) <= max_outliers
+
+
+# ------------------------------------------------------------------ vs reference (GPU)
+@pytest.mark.parametrize("name", list(CASES))
+def test_bit_exact_binning_and_images_vs_reference(cuda_device, name):
+    if not ru.ref_available():
+        pytest.skip("oracle/_ref/ref_rasterizer_C.so not built")
+    dev = cuda_device
+    p = CASES[name]
+    case = ru.build_case(**p)
+    fa, ours, grads, ours_b = run_ours(case, dev)
+    REF = ru.ref_module()
+    ref = REF.rasterize_gaussians(*fa)
+    ref_b = REF.rasterize_gaussians_backward(*ru.bwd_args(fa, ref, grads, dev))
+    torch.cuda.synchronize()
+    so, sr = ru.our_state(ours, case["P"], p["W"], p["H"]), ru.ref_state(ref, case["P"], p["W"], p["H"])
+    assert ours[0] == ref[0] and ours[0] > 0
+    for k in ("keys_unsorted", "keys", "point_list", "ranges", "n_contrib", "tiles_touched"):
+        assert torch.equal(so[k], sr[k]), k
+    assert torch.equal(ours[2], ref[2])  # radii
+    assert torch.equal(ours[3], ref[3])  # out_observe
+    assert torch.equal(so["final_T"].view(torch.int32), sr["final_T"].view(torch.int32))
+    for i in (1, 4, 9):  # color, all_map, invdepth
+        assert img_close(ours[i], ref[i]), i
+    assert img_close(ours[5], ref[5], atol=IMG_ATOL, rtol=1e-5)  # plane depth is a quotient
+    ru.assert_grads_close(ours_b, ref_b, what=name)
+
+
+# ------------------------------------------------------------------ vs golden fixtures
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "raster_ref_*.npz"))))
+def test_against_reference_golden(cuda_device, path):
+    dev = cuda_device
+    gold = np.load(path)
+    p = json.loads(bytes(gold["params"]).decode())
+    case = ru.build_case(p["n"], p["W"], p["H"], seed=p["seed"], with_hier=p["with_hier"], with_indices=p["with_indices"])
+    fa, ours, grads, ours_b = run_ours(case, dev, render_geo=p["render_geo"], do_depth=p["do_depth"])
+    so = ru.our_state(ours, case["P"], p["W"], p["H"])
+    assert ours[0] == int(gold["num_rendered"])
+    assert np.array_equal(ours[2].cpu().numpy(), gold["radii"])
+    if ours[0] > 0:
+        for k in ("keys", "point_list", "keys_unsorted"):
+            assert np.array_equal(so[k].cpu().numpy(), gold[k]), k
+    for k in ("ranges", "n_contrib", "tiles_touched"):
+        assert np.array_equal(so[k].cpu().numpy(), gold[k]), k
+    assert np.array_equal(ours[3].cpu().numpy(), gold["out_observe"])
+    assert img_close(ours[1], gold["color"]) and img_close(ours[4], gold["all_map"])
+    assert img_close(ours[5], gold["plane_depth"], rtol=1e-5) and img_close(ours[9], gold["invdepth"])
+    ru.assert_grads_close(ours_b, [torch.from_numpy(gold[n]) for n in ru.GRAD_NAMES], what=os.path.basename(path))
+
+
+# ------------------------------------------------------------------ vs CPU oracle
+@pytest.mark.parametrize("name", list(CASES))
+def test_parity_vs_cpu_oracle(cuda_device, name):
+    dev = cuda_device
+    p = CASES[name]
+    case = ru.build_case(**p)
+    fa, ours, grads, ours_b = run_ours(case, dev)
+    so = ru.our_state(ours, case["P"], p["W"], p["H"])
+    o = ru.oracle_for_case(case)
+    oo = o.forward()
+    og = o.backward(grads["color"].numpy(), grads["all_map"].numpy(), grads["plane_depth"].numpy(), grads["invdepth"].numpy())
+    assert ours[0] == oo["num_rendered"]
+    assert np.array_equal(so["keys"].cpu().numpy().view(np.uint64), oo["keys"])
+    assert np.array_equal(so["point_list"].cpu().numpy().view(np.uint32), oo["point_list"])
+    assert np.array_equal(so["ranges"].cpu().numpy().view(np.uint32), oo["ranges"])
+    assert np.array_equal(ours[2].cpu().numpy(), oo["radii"])
+    # With ts/kids the reference evaluates pow with the GPU's approximate lg2/ex2 (forward.cu:550),
+    # which libm cannot reproduce bit for bit: a handful of alpha ~ 1/255 decisions may flip.
+    hier = p.get("with_hier", False)
+    out = 16 if hier else 0
+    assert int((so["n_contrib"].cpu().numpy().view(np.uint32) != oo["n_contrib"]).sum()) <= out
+    assert int((ours[3].cpu().numpy() != oo["out_observe"]).sum()) <= out
+    assert img_close(ours[1], oo["color"], max_outliers=out) and img_close(ours[4], oo["all_map"], atol=2e-4 if hier else IMG_ATOL, max_outliers=3 * out)
+    assert img_close(ours[5], oo["plane_depth"], rtol=1e-4, max_outliers=out) and img_close(ours[9], oo["invdepth"], max_outliers=out)
+    theirs = [torch.from_numpy(og[n]) for n in ru.GRAD_NAMES]
+    if hier:
+        for a, b in zip(ours_b, theirs):
+            assert ru.rel_report(a.cpu(), b)[2] < 2e-3
+    else:
+        ru.assert_grads_close([g.cpu() for g in ours_b], theirs, what=name)
+
+
+# ------------------------------------------------------------------ variants
+@pytest.mark.parametrize("render_geo,do_depth", [(False, False), (True, False), (False, True)])
+def test_output_switches(cuda_device, render_geo, do_depth):
+    dev = cuda_device
+    case = ru.build_case(3000, 160, 96, seed=31)
+    fa, ours, grads, ours_b = run_ours(case, dev, render_geo=render_geo, do_depth=do_depth)
+    o = ru.oracle_for_case(case, render_geo=render_geo, do_depth=do_depth)
+    oo = o.forward()
+    og = o.backward(grads["color"].numpy(), grads["all_map"].numpy(), grads["plane_depth"].numpy(),
+                    grads["invdepth"].numpy() if do_depth else None)
+    assert ours[9].shape == ((1 if do_depth else 0), 96, 160)
+    assert img_close(ours[1], oo["color"]) and img_close(ours[4], oo["all_map"]) and img_close(ours[5], oo["plane_depth"], rtol=1e-4)
+    if not render_geo:
+        assert float(ours[4].abs().max()) == 0.0 and float(ours[5].abs().max()) == 0.0
+    ru.assert_grads_close([g.cpu() for g in ours_b], [torch.from_numpy(og[n]) for n in ru.GRAD_NAMES])
+
+
+@pytest.mark.parametrize("degree", [0, 1, 2, 3])
+def test_sh_degrees(cuda_device, degree):
+    dev = cuda_device
+    case = ru.build_case(2500, 128, 80, seed=40 + degree, sh_degree=degree)
+    fa, ours, grads, ours_b = run_ours(case, dev)
+    o = ru.oracle_for_case(case)
+    oo = o.forward()
+    og = o.backward(grads["color"].numpy(), grads["all_map"].numpy(), grads["plane_depth"].numpy(), grads["invdepth"].numpy())
+    assert img_close(ours[1], oo["color"])
+    ru.assert_grads_close([g.cpu() for g in ours_b], [torch.from_numpy(og[n]) for n in ru.GRAD_NAMES])
+    k = (degree + 1) ** 2
+    assert float(ours_b[5][:, k:, :].abs().max() if k < 16 else 0.0) == 0.0  # inactive bands get zero gradient
+
+
+def test_precomputed_colors(cuda_device):
+    dev = cuda_device
+    case = ru.build_case(2500, 128, 80, seed=50)
+    cols = torch.rand(case["P"], 3, generator=torch.Generator().manual_seed(5))
+    fa, ours, grads, ours_b = run_ours(case, dev, colors_precomp=cols)
+    o = ru.oracle_for_case(case, colors_precomp=cols)
+    oo = o.forward()
+    og = o.backward(grads["color"].numpy(), grads["all_map"].numpy(), grads["plane_depth"].numpy(), grads["invdepth"].numpy())
+    assert img_close(ours[1], oo["color"])
+    assert ours_b[5].numel() == 0  # dL_dsh has shape (N, 0, 3)
+    names = [n for n in ru.GRAD_NAMES if n != "dL_dsh"]
+    ru.assert_grads_close([g.cpu() for n, g in zip(ru.GRAD_NAMES, ours_b) if n != "dL_dsh"],
+                          [torch.from_numpy(og[n]) for n in names], names=names)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_inputs(cuda_device):
+    dev = cuda_device
+    case = ru.build_case(8, 64, 48, seed=60)
+    for k in ("means3D", "scales", "rotations", "opacity", "shs", "all_map"):
+        case[k] = case[k][:0].contiguous()
+    case["P"] = 0
+    fa, ours, grads, ours_b = run_ours(case, dev)
+    assert ours[0] == 0 and ours[2].numel() == 0
+    assert float(ours[1].abs().max()) == 0.0  # rasterize_points.cu:100: nothing rendered, zeros (not background)
+    assert all(g.shape[0] == 0 for g in ours_b)
+
+
+def test_everything_culled(cuda_device):
+    dev = cuda_device
+    case = ru.build_case(500, 64, 48, seed=61, eye=(0.0, 0.0, 50.0))  # scene is behind the camera
+    fa, ours, grads, ours_b = run_ours(case, dev)
+    assert ours[0] == 0 and int((ours[2] > 0).sum()) == 0
+    assert float(ours[1].abs().max()) == 0.0  # rasterizer_impl.cu:332-333 returns before blending
+    assert all(float(g.abs().max()) == 0.0 for g in ours_b if g.numel())
+
+
+def test_single_instance_quirk(cuda_device):
+    """R == 1: identifyTileRanges never closes the range (rasterizer_impl.cu:129-141) -> background only."""
+    dev = cuda_device
+    case = ru.build_case(1, 64, 48, seed=62)
+    case["means3D"][:] = torch.tensor([[0.02, 0.02, 0.0]])
+    case["scales"][:] = 1e-4
+    case["all_map"] = syn.geometry_all_map(case["means3D"], case["scales"], case["rotations"], case["cam"])
+    fa, ours, grads, ours_b = run_ours(case, dev)
+    oo = ru.oracle_for_case(case).forward()
+    assert ours[0] == oo["num_rendered"]
+    assert img_close(ours[1], oo["color"])
+    if ours[0] == 1:
+        bg = torch.tensor([0.1, 0.2, 0.3], device=dev).view(3, 1, 1)
+        assert torch.allclose(ours[1], bg.expand_as(ours[1]))
+
+
+def test_debug_mode_and_repeatability(cuda_device):
+    dev = cuda_device
+    case = ru.build_case(3000, 160, 96, seed=63)
+    fa = list(ru.op_args(case, dev))
+    a = ru.OUR_C.rasterize_gaussians(*fa)
+    fa[24] = True  # debug: synchronise + check after every launch
+    b = ru.OUR_C.rasterize_gaussians(*fa)
+    for i in (1, 2, 3, 4, 5, 9):
+        assert torch.equal(a[i], b[i])  # the forward is deterministic, bit for bit
+
+
+def test_mark_visible(cuda_device):
+    dev = cuda_device
+    case = ru.build_case(4000, 64, 48, seed=64, eye=(0.0, 0.0, -1.0))
+    cam = case["cam"]
+    from hidegs_b200.diff_gaussian_rasterization import GaussianRasterizer
+    r = GaussianRasterizer(syn.raster_settings(cam, dev))
+    vis = r.markVisible(case["means3D"].to(dev))
+    W = cam.world_view_transform
+    z = (case["means3D"] @ W[:3, 2] + W[3, 2])
+    assert vis.dtype == torch.bool and int((vis.cpu() != (z > 0.2)).sum()) <= 2  # <=2: fp contraction at the threshold
+
+
+# ------------------------------------------------------------------ public autograd API
+def test_autograd_module_matches_operator(cuda_device):
+    dev = cuda_device
+    from hidegs_b200.diff_gaussian_rasterization import GaussianRasterizer
+    case = ru.build_case(3000, 160, 96, seed=70)
+    cam = case["cam"]
+    rs = syn.raster_settings(cam, dev, bg=(0.1, 0.2, 0.3))
+    t = {k: case[k].to(dev).requires_grad_(True) for k in ("means3D", "shs", "opacity", "scales", "rotations", "all_map")}
+    means2D = torch.zeros_like(t["means3D"], requires_grad=True)
+    color, radii, observe, all_map, plane_depth, invdepth = GaussianRasterizer(rs)(
+        means3D=t["means3D"], means2D=means2D, opacities=t["opacity"], shs=t["shs"], scales=t["scales"],
+        rotations=t["rotations"], all_map=t["all_map"])
+    g = {k: v.to(dev) for k, v in syn.upstream_grads(160, 96).items()}
+    loss = (color * g["color"]).sum() + (all_map * g["all_map"]).sum() + (plane_depth * g["plane_depth"]).sum() + (invdepth * g["invdepth"]).sum()
+    loss.backward()
+    fa, fwd, grads, bwd = run_ours(case, dev)
+    named = dict(zip(ru.GRAD_NAMES, bwd))
+    ru.assert_grads_close([means2D.grad, t["opacity"].grad, t["means3D"].grad, t["shs"].grad, t["scales"].grad, t["rotations"].grad, t["all_map"].grad],
+                          [named[n] for n in ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations", "dL_dall_map")],
+                          names=("means2D", "opacity", "means3D", "sh", "scales", "rotations", "all_map"))
+    assert not radii.requires_grad and not observe.requires_grad
+
+
+# ------------------------------------------------------------------ full size (BASELINE config 2)
+def test_full_size_properties(cuda_device):
+    """1M Gaussians, 1920x1080, SH degree 3: size-independent properties of the binning and the blend."""
+    dev = cuda_device
+    W, H, n = 1920, 1080, 1_000_000
+    case = ru.build_case(n, W, H, seed=0)
+    fa, ours, grads, bwd = run_ours(case, dev)
+    so = ru.our_state(ours, n, W, H)
+    R = ours[0]
+    assert R == int(so["tiles_touched"].long().sum()) and R > n
+    keys = so["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())  # sortedness
+    assert torch.equal(keys.sort()[0], so["keys_unsorted"].sort()[0])  # the sort is a permutation
+    # values follow their keys: recompute each key from its value
+    pl = so["point_list"].long()
+    depth_bits = so["depths"].view(torch.int32)[pl].long() & 0xFFFFFFFF
+    assert torch.equal(keys & 0xFFFFFFFF, depth_bits)
+    # tile ranges partition [0, R)
+    rg = so["ranges"].long()
+    nz = rg[rg[:, 1] > rg[:, 0]]
+    assert int((nz[:, 1] - nz[:, 0]).sum()) == R and int(nz[0, 0]) == 0 and int(nz[-1, 1]) == R
+    assert torch.equal(nz[1:, 0], nz[:-1, 1])
+    tiles = (keys >> 32)
+    assert torch.equal(tiles[nz[:, 0]], torch.arange(rg.shape[0], device=dev)[rg[:, 1] > rg[:, 0]])
+    # blend: transmittance in (0,1], n_contrib inside its range, colour = C + T*bg bounded
+    assert float(so["final_T"].min()) > 0.0 and float(so["final_T"].max()) <= 1.0
+    assert all(bool(torch.isfinite(ours[i]).all()) for i in (1, 4, 9))
+    # stable tie order: equal keys keep ascending slot order
+    same = keys[1:] == keys[:-1]
+    assert bool((pl[1:][same] > pl[:-1][same]).all())
+    # backward is linear in the upstream gradient
+    g2 = {k: 2.0 * v for k, v in grads.items()}
+    bwd2 = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fa, ours, g2, dev))
+    ru.assert_grads_close(bwd2, [2.0 * g for g in bwd], what="linearity")
+    # culled Gaussians receive exactly zero gradient
+    dead = ours[2] <= 0
+    assert all(float(g[dead].abs().max()) == 0.0 for g in bwd if g.numel())
+    if ru.ref_available():
+        REF = ru.ref_module()
+        ref = REF.rasterize_gaussians(*fa)
+        sr = ru.ref_state(ref, n, W, H)
+        assert ref[0] == R
+        for k in ("keys", "point_list", "ranges", "n_contrib"):
+            assert torch.equal(so[k], sr[k]), k
+        assert img_close(ours[1], ref[1]) and img_close(ours[9], ref[9])
+        ref_b = REF.rasterize_gaussians_backward(*ru.bwd_args(fa, ref, grads, dev))
+        ru.assert_grads_close(bwd, ref_b, what="config2 vs reference")
