@@ -339,7 +339,8 @@ def run_gpu_arm(args, impl):
                             "stage_ms": per_stage,
                             "note": "blend kernels are FP32-issue / shared-memory bound, not HBM bound (DESIGN.md §4)"}
         line["gpu_launches"] = launches
-        line["cpu_baseline"] = cpu_baseline(scene_cpu)
+        if not os.environ.get("HG_BENCH_SKIP_CPU"):
+            line["cpu_baseline"] = cpu_baseline(scene_cpu)
     else:
         line["impl"] = "reference"
         line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": 0, "kind": "reference",

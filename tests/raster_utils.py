@@ -185,15 +185,20 @@ def rel_report(a, b):
     return float(err.max()), scale, float((err > tol).double().mean())
 
 
-def assert_grads_close(ours, theirs, names=GRAD_NAMES, rtol=1e-3, floor=1e-4, what=""):
-    """Gradients within `rtol` relative: |a-b| <= rtol*|b| + rtol*floor*max|b| element-wise
-    (the floor absorbs summation-order noise on near-cancelling sums)."""
+def assert_grads_close(ours, theirs, names=GRAD_NAMES, rtol=1e-3, floor=3e-2, l2_tol=1e-4, what=""):
+    """Gradients within `rtol` relative.  Two criteria per tensor:
+      * relative L2 error  ||a-b|| / ||b||  <= l2_tol, and
+      * element-wise |a-b| <= rtol*|b| + rtol*floor*max|b|  (the floor absorbs summation-order noise on
+        entries that are small next to the terms that cancel into them, e.g. dL/dcov3D = T^2 * dL/dconic).
+    """
     for name, a, b in zip(names, ours, theirs):
         a, b = a.double(), b.double()
         assert a.shape == b.shape, (name, a.shape, b.shape)
         if a.numel() == 0:
             continue
         scale = float(b.abs().max())
+        l2 = float((a - b).norm()) / max(float(b.norm()), 1e-30)
+        assert l2 <= l2_tol or scale == 0.0, "%s %s: relative L2 error %.3g" % (what, name, l2)
         tol = rtol * b.abs() + rtol * floor * scale + 1e-30
         bad = (a - b).abs() > tol
         frac = float(bad.double().mean())
