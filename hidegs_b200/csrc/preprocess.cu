@@ -372,7 +372,10 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
   depths[t_idx] = depth;
   radii[t_idx] = my_radius;
   rects[t_idx] = make_uint2(minx | (miny << 16), maxx | (maxy << 16));
-  clamped[t_idx] = clamp_bits;
+  // With a parent the reference records the clamp flags in `p_clamped` (forward.cu:411) but its
+  // backward reads `clamped` (backward.cu:453), which that path never wrote: the flags are
+  // effectively "not clamped".  We store exactly that instead of uninitialised memory.
+  clamped[t_idx] = has_parent ? (uint8_t)0 : clamp_bits;
   tiles_touched[t_idx] = (maxy - miny) * (maxx - minx);
   float4* rec = records + 4 * (size_t)t_idx;
   rec[0] = make_float4(pix_x, pix_y, conic_a, conic_b);

@@ -247,7 +247,7 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
   if (rc) return rc;
   if (in->P == 0) return HG_OK;
   if (!radii || !geom_buffer || !image_buffer || !dL_dpix || !accum || !dL_dmeans2D ||
-      !dL_dopacity || !dL_dcolors || !dL_dmeans3D || !dL_dcov3D || !dL_dsh || !dL_dscales ||
+      !dL_dopacity || !dL_dcolors || !dL_dmeans3D || !dL_dcov3D || (in->shs && !dL_dsh) || !dL_dscales ||
       !dL_drotations || !dL_dall_map || (R > 0 && !binning_buffer) ||
       (in->render_geo && (!all_map_pixels || !dL_dout_all_map || !dL_dout_plane_depth)) ||
       ((dL_dout_invdepth != nullptr) != (dL_dinvdepths != nullptr))) {

@@ -13,6 +13,9 @@ import torch
 from .. import _lib
 
 
+_ROUND = 32 << 20  # scratch size granularity (bytes)
+
+
 def _ptr(t):
     """data_ptr of a tensor or NULL for an empty one (reference: empty == absent)."""
     if t is None or t.numel() == 0:
@@ -36,6 +39,30 @@ def _i32(t):
     return t.contiguous()
 
 
+_POOLS = {}
+
+
+def _pool(device):
+    """Private torch.cuda.MemPool per device for the library's scratch buffers.
+
+    Geometry / image / binning / accumulator scratch has a handful of (rounded) sizes that repeat
+    every view; keeping it out of the general caching allocator stops it from fragmenting against
+    the user's tensors (which showed up as cudaMalloc churn of 10-30 ms per training step)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _POOLS.get(idx)
+    if pool is None:
+        pool = _POOLS[idx] = torch.cuda.MemPool()
+    return pool
+
+
+def _scratch_empty(nbytes, device):
+    nbytes = int(nbytes)
+    if nbytes > _ROUND:
+        nbytes = (nbytes + _ROUND - 1) // _ROUND * _ROUND
+    with torch.cuda.use_mem_pool(_pool(device), device=device):
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
 class _Scratch:
     """Growable byte buffer handed to the library through hg_alloc_fn
     (the reference's resizeFunctional, rasterize_points.cu:27-33)."""
@@ -47,7 +74,7 @@ class _Scratch:
 
     def _alloc(self, _ctx, nbytes):
         try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.tensor = _scratch_empty(nbytes, self.device)
             return self.tensor.data_ptr()
         except Exception:  # surfaces as HG_ERR_ALLOC
             return None
@@ -88,13 +115,18 @@ def rasterize_gaussians(background, indices, parent_indices, ts, kids, means3D, 
     M = sh.size(1) if sh.numel() != 0 else 0
     f32 = dict(dtype=torch.float32, device=dev)
     i32 = dict(dtype=torch.int32, device=dev)
-    # The library writes every element of these outputs, so no zero fill is needed.
-    out_color = torch.empty((3, H, W), **f32)
-    out_invdepth = torch.empty((1 if do_depth else 0, H, W), **f32)
-    radii = torch.empty((P,), **i32)
-    out_observe = torch.empty((P,), **i32)
-    out_all_map = torch.empty((5, H, W), **f32)
-    out_plane_depth = torch.empty((1, H, W), **f32)
+    # The library writes every element of these outputs, so no zero fill is needed.  All float
+    # images come from one allocation and both int vectors from another (two blocks of constant
+    # size per view instead of six).
+    HW = H * W
+    nd = 1 if do_depth else 0
+    out_f = torch.empty(((9 + nd) * HW,), **f32)
+    out_color = out_f[:3 * HW].view(3, H, W)
+    out_all_map = out_f[3 * HW:8 * HW].view(5, H, W)
+    out_plane_depth = out_f[8 * HW:9 * HW].view(1, H, W)
+    out_invdepth = out_f[9 * HW:].view(nd, H, W)
+    out_i = torch.empty((2 * P,), **i32)
+    radii, out_observe = out_i[:P], out_i[P:]
     geom, binning, img = _Scratch(dev), _Scratch(dev), _Scratch(dev)
     rendered = ctypes.c_int32(0)
     if P != 0 and all_map.numel() != 0 and all_map.size(0) < P:
@@ -135,24 +167,27 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
     M = sh.size(1) if sh.numel() != 0 else 0
     # With an index remap or parents the library accumulates into pre-zeroed rows.
     prezero = indices.numel() != 0 or parent_indices.numel() != 0 or P == 0
-    new = torch.zeros if prezero else torch.empty
-    opt = dict(dtype=torch.float32, device=dev)
-    dL_dmeans3D = new((fullP, 3), **opt)
-    dL_dmeans2D = new((fullP, 3), **opt)
-    dL_dcolors = new((fullP, 3), **opt)
-    dL_dall_map = new((fullP, 5), **opt)
-    dL_dopacity = new((fullP, 1), **opt)
-    dL_dcov3D = new((fullP, 6), **opt)
-    dL_dsh = new((fullP, M, 3), **opt)
-    dL_dscales = new((fullP, 3), **opt)
-    dL_drotations = new((fullP, 4), **opt)
     has_depth_grad = dL_dout_invdepth is not None and dL_dout_invdepth.numel() != 0
-    dL_dinvdepths = new((fullP, 1), **opt) if has_depth_grad else torch.zeros((0, 1), **opt)
+    # One flat fp32 arena per backward.  The trainable parameters come first
+    # (xyz 3 | sh 3M | opacity 1 | scale 3 | rotation 4 = 59 floats per Gaussian at M = 16), so the
+    # view-sharded trainer can all-reduce `arena[:59 N]` in place without a pack kernel.
+    widths = (("means3D", 3), ("sh", 3 * M), ("opacity", 1), ("scales", 3), ("rotations", 4), ("means2D", 3),
+              ("colors", 3), ("cov3D", 6), ("all_map", 5), ("invdepths", 1 if has_depth_grad else 0))
+    total = fullP * sum(w for _, w in widths)
+    arena = (torch.zeros if prezero else torch.empty)((total,), dtype=torch.float32, device=dev)
+    g, off = {}, 0
+    for name, w in widths:
+        g[name] = arena[off:off + fullP * w].view(fullP, w)
+        off += fullP * w
+    dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dall_map = g["means3D"], g["means2D"], g["colors"], g["all_map"]
+    dL_dopacity, dL_dcov3D, dL_dscales, dL_drotations = g["opacity"], g["cov3D"], g["scales"], g["rotations"]
+    dL_dsh = g["sh"].view(fullP, M, 3)
+    dL_dinvdepths = g["invdepths"] if has_depth_grad else torch.zeros((0, 1), dtype=torch.float32, device=dev)
 
     if P != 0:
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
-            accum = torch.empty(_lib.lib().hg_raster_backward_accum_bytes(P), dtype=torch.uint8, device=dev)
+            accum = _scratch_empty(_lib.lib().hg_raster_backward_accum_bytes(P), dev)
             s = _inputs(P, fullP, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, False, render_geo, debug,
                         background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D,
                         sh, colors, all_maps, opacities, scales, rotations, cov3D_precomp)

@@ -171,7 +171,7 @@ HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
                        float *dL_dinvdepths, /* [N,1] or NULL */
                        float *dL_dmeans3D,   /* [N,3] */
                        float *dL_dcov3D,     /* [N,6] */
-                       float *dL_dsh,        /* [N,M,3] */
+                       float *dL_dsh,        /* [N,M,3] (may be NULL when shs is) */
                        float *dL_dscales,    /* [N,3] */
                        float *dL_drotations, /* [N,4] */
                        float *dL_dall_map,   /* [N,5] */

@@ -37,6 +37,7 @@ def main(out_dir):
     for name, p in CASES.items():
         case = ru.build_case(p["n"], p["W"], p["H"], seed=p["seed"], with_hier=p["with_hier"], with_indices=p["with_indices"])
         fa = ru.op_args(case, dev, render_geo=p["render_geo"], do_depth=p["do_depth"])
+        ru.zero_prime(dev)  # deterministic "unwritten clamp flags" for slots with parents (see raster_utils)
         ref = REF.rasterize_gaussians(*fa)
         torch.cuda.synchronize()
         st = ru.ref_state(ref, case["P"], p["W"], p["H"])

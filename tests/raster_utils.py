@@ -173,6 +173,21 @@ def ref_state(fwd_out, P, W, H):
     return st
 
 
+def zero_prime(dev):
+    """Make the memory the caching allocator will recycle next read as zeros.
+
+    The reference's backward reads SH clamp flags that its forward never wrote for slots that have a
+    parent (forward.cu:411 writes p_clamped, backward.cu:453 reads clamped): it sees whatever bytes the
+    allocator recycles.  Our implementation (and the oracle) define those flags as zero; priming makes
+    the reference deterministic so that it can be compared."""
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    z = [torch.zeros(512 << 10, dtype=torch.uint8, device=dev) for _ in range(64)]
+    z += [torch.zeros(8 << 20, dtype=torch.uint8, device=dev) for _ in range(8)]
+    torch.cuda.synchronize()
+    del z
+
+
 # ----------------------------------------------------------------- comparisons
 def rel_report(a, b):
     """(max abs err, max |b|, fraction of elements outside rtol 1e-3 / atol 1e-5*max|b|)."""
@@ -192,7 +207,7 @@ def assert_grads_close(ours, theirs, names=GRAD_NAMES, rtol=1e-3, floor=3e-2, l2
         entries that are small next to the terms that cancel into them, e.g. dL/dcov3D = T^2 * dL/dconic).
     """
     for name, a, b in zip(names, ours, theirs):
-        a, b = a.double(), b.double()
+        a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
         assert a.shape == b.shape, (name, a.shape, b.shape)
         if a.numel() == 0:
             continue

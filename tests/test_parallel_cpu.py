@@ -1,0 +1,90 @@
+"""CPU (gloo, world_size 2) tests of the view-sharded data-parallel plumbing."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hidegs_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make_arena(n, seed, shared=True):
+    """Gradient tensors laid out like the backward's arena (xyz 3 | sh 48 | opacity 1 | scale 3 | rot 4)."""
+    g = torch.Generator().manual_seed(seed)
+    widths = (3, 48, 1, 3, 4)
+    if shared:
+        arena = torch.randn(n * 76, generator=g)
+        out, off = [], 0
+        for w in widths:
+            out.append(arena[off:off + n * w].view(n, w))
+            off += n * w
+        return arena, out
+    return None, [torch.randn(n, w, generator=g) for w in widths]
+
+
+def _worker(rank, world, port, shared, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 257
+        arena, grads = _make_arena(n, seed=100 + rank, shared=shared)
+        tail_before = arena[59 * n:].clone() if shared else None
+        flat = parallel.flat_view(grads)
+        assert (flat is not None) == shared
+        if shared:
+            assert flat.numel() == 59 * n and flat.data_ptr() == arena.data_ptr()
+        _, nbytes = parallel.allreduce_gradients(grads, average=False)
+        assert nbytes == 59 * n * 4
+        expect = [sum(_make_arena(n, seed=100 + r, shared=shared)[1][i] for r in range(world)) for i in range(5)]
+        for a, b in zip(grads, expect):
+            assert torch.allclose(a, b, rtol=0, atol=1e-6)
+        if shared:  # nothing outside the 59-float parameter block is touched
+            assert torch.equal(arena[59 * n:], tail_before)
+        views = list(range(10))
+        mine = parallel.shard_views(views)
+        assert mine == views[rank::world]
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(shared):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, shared, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_allreduce_in_place_on_shared_arena():
+    _run(shared=True)
+
+
+def test_allreduce_packs_when_storage_is_not_shared():
+    _run(shared=False)
+
+
+def test_flat_view_detects_gaps_and_single_process_path():
+    arena, grads = _make_arena(16, 1)
+    assert parallel.flat_view(grads).numel() == 59 * 16
+    assert parallel.flat_view([grads[0], grads[2]]) is None  # not back to back
+    assert parallel.flat_view([grads[1].t()]) is None  # not contiguous
+    before = [g.clone() for g in grads]
+    work, nbytes = parallel.allreduce_gradients(grads)  # no process group: a no-op
+    assert work is None and nbytes == 59 * 16 * 4 and all(torch.equal(a, b) for a, b in zip(grads, before))
