@@ -39,45 +39,69 @@ def _i32(t):
     return t.contiguous()
 
 
-_POOLS = {}
+_R_HINT = {}  # (device index, P, W, H) -> largest num_rendered seen: sizes the binning part of the workspace
 
 
-def _pool(device):
-    """Private torch.cuda.MemPool per device for the library's scratch buffers.
-
-    Geometry / image / binning / accumulator scratch has a handful of (rounded) sizes that repeat
-    every view; keeping it out of the general caching allocator stops it from fragmenting against
-    the user's tensors (which showed up as cudaMalloc churn of 10-30 ms per training step)."""
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    pool = _POOLS.get(idx)
-    if pool is None:
-        pool = _POOLS[idx] = torch.cuda.MemPool()
-    return pool
+def _up(n, a=256):
+    return (int(n) + a - 1) // a * a
 
 
-def _scratch_empty(nbytes, device):
-    nbytes = int(nbytes)
-    if nbytes > _ROUND:
-        nbytes = (nbytes + _ROUND - 1) // _ROUND * _ROUND
-    with torch.cuda.use_mem_pool(_pool(device), device=device):
-        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+class _Workspace:
+    """ONE allocation per forward call that holds all of the library's scratch:
 
+        [ geometry | image | backward accumulator | binning (capacity from the last views' R) ]
 
-class _Scratch:
-    """Growable byte buffer handed to the library through hg_alloc_fn
-    (the reference's resizeFunctional, rasterize_points.cu:27-33)."""
+    The reference makes three growable byte tensors per call (resizeFunctional,
+    rasterize_points.cu:27-33, 91-97).  A single block of (nearly) constant size per view lets torch's
+    caching allocator reach a steady state after one step; separate, differently sized blocks kept
+    fragmenting it (10-100 ms of cudaMalloc per training step).  If a view needs more binning space
+    than the hint, that part alone falls back to its own allocation and the hint is raised."""
 
-    def __init__(self, device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = _lib.ALLOC_FN(self._alloc)
+    def __init__(self, device, P, W, H):
+        self.device, self.key = device, (device.index, P, W, H)
+        L0 = _lib.layout(P, W, H, 0)
+        self.geom_bytes, self.image_bytes = L0.geom_bytes, L0.image_bytes
+        self.accum_bytes = _lib.lib().hg_raster_backward_accum_bytes(P)
+        self.off_image = _up(self.geom_bytes)
+        self.off_accum = self.off_image + _up(self.image_bytes)
+        self.off_binning = self.off_accum + _up(self.accum_bytes)
+        hint = _R_HINT.get(self.key, 0)
+        self.binning_cap = 0
+        if hint > 0:
+            r_cap = _up(int(hint * 1.125) + 4096, 1 << 18)
+            self.binning_cap = _up(_lib.layout(P, W, H, r_cap).binning_bytes, _ROUND)
+        self.tensor = torch.empty(self.off_binning + self.binning_cap, dtype=torch.uint8, device=device)
+        self.binning = self.tensor[:0]
+        base = self.tensor.data_ptr()
+        self.cb_geom = _lib.ALLOC_FN(lambda ctx, n: base if n <= self.geom_bytes else None)
+        self.cb_image = _lib.ALLOC_FN(lambda ctx, n: base + self.off_image if n <= self.image_bytes else None)
+        self.cb_binning = _lib.ALLOC_FN(self._alloc_binning)
 
-    def _alloc(self, _ctx, nbytes):
+    def _alloc_binning(self, _ctx, nbytes):
         try:
-            self.tensor = _scratch_empty(nbytes, self.device)
-            return self.tensor.data_ptr()
+            if nbytes <= self.binning_cap:
+                self.binning = self.tensor[self.off_binning:self.off_binning + int(nbytes)]
+            else:
+                self.binning = torch.empty(_up(nbytes, _ROUND), dtype=torch.uint8, device=self.device)
+            return self.binning.data_ptr()
         except Exception:  # surfaces as HG_ERR_ALLOC
             return None
+
+    def finish(self, R):
+        if R > _R_HINT.get(self.key, 0):
+            _R_HINT[self.key] = int(R)
+        image = self.tensor[self.off_image:self.off_image + self.image_bytes]
+        return self.tensor, self.binning, image
+
+
+def _accum_ptr(geomBuffer, P, W, H):
+    """Address of the backward accumulator inside the forward's workspace (see _Workspace)."""
+    L0 = _lib.layout(P, W, H, 0)
+    off = _up(L0.geom_bytes) + _up(L0.image_bytes)
+    need = off + _lib.lib().hg_raster_backward_accum_bytes(P)
+    if geomBuffer.numel() < need:
+        return None
+    return geomBuffer.data_ptr() + off
 
 
 def _inputs(P, N, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, render_geo, debug,
@@ -127,23 +151,24 @@ def rasterize_gaussians(background, indices, parent_indices, ts, kids, means3D, 
     out_invdepth = out_f[9 * HW:].view(nd, H, W)
     out_i = torch.empty((2 * P,), **i32)
     radii, out_observe = out_i[:P], out_i[P:]
-    geom, binning, img = _Scratch(dev), _Scratch(dev), _Scratch(dev)
     rendered = ctypes.c_int32(0)
     if P != 0 and all_map.numel() != 0 and all_map.size(0) < P:
         raise RuntimeError("all_map must have one row per rendered slot")
 
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
+        ws = _Workspace(dev, P, W, H)
         s = _inputs(P, N, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, render_geo, debug,
                     background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D, sh,
                     colors, all_map, opacity, scales, rotations, cov3D_precomp)
         rc = _lib.lib().hg_raster_forward(
-            ctypes.byref(s), geom.cb, None, binning.cb, None, img.cb, None,
+            ctypes.byref(s), ws.cb_geom, None, ws.cb_binning, None, ws.cb_image, None,
             _ptr(out_color), _ptr(out_invdepth), _ptr(out_observe), _ptr(out_all_map), _ptr(out_plane_depth),
             _ptr(radii), ctypes.byref(rendered), stream)
     _lib.check(rc, "rasterize_gaussians")
-    return (rendered.value, out_color, radii, out_observe, out_all_map, out_plane_depth, geom.tensor,
-            binning.tensor, img.tensor, out_invdepth)
+    geomBuffer, binningBuffer, imgBuffer = ws.finish(rendered.value)
+    return (rendered.value, out_color, radii, out_observe, out_all_map, out_plane_depth, geomBuffer,
+            binningBuffer, imgBuffer, out_invdepth)
 
 
 def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_indices, ts, kids, means3D, radii,
@@ -187,14 +212,17 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
     if P != 0:
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
-            accum = _scratch_empty(_lib.lib().hg_raster_backward_accum_bytes(P), dev)
+            accum_ptr = _accum_ptr(geomBuffer, P, W, H)
+            if accum_ptr is None:  # foreign geometry buffer: fall back to a separate accumulator
+                accum = torch.empty(_lib.lib().hg_raster_backward_accum_bytes(P), dtype=torch.uint8, device=dev)
+                accum_ptr = accum.data_ptr()
             s = _inputs(P, fullP, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, False, render_geo, debug,
                         background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D,
                         sh, colors, all_maps, opacities, scales, rotations, cov3D_precomp)
             rc = _lib.lib().hg_raster_backward(
                 ctypes.byref(s), int(R), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
                 _ptr(all_map_pixels), _ptr(dL_dout_color), _ptr(dL_dout_all_map), _ptr(dL_dout_plane_depth),
-                _ptr(dL_dout_invdepth) if has_depth_grad else None, _ptr(accum),
+                _ptr(dL_dout_invdepth) if has_depth_grad else None, accum_ptr,
                 _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
                 _ptr(dL_dinvdepths) if has_depth_grad else None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
                 _ptr(dL_dscales), _ptr(dL_drotations), _ptr(dL_dall_map), stream)

@@ -26,6 +26,7 @@ CASES = {
     "plain": dict(n=1500, W=96, H=64, seed=11, with_hier=False, with_indices=False, render_geo=True, do_depth=True),
     "hier": dict(n=1500, W=96, H=64, seed=12, with_hier=True, with_indices=False, render_geo=True, do_depth=True),
     "raw_indices": dict(n=1500, W=96, H=64, seed=13, with_hier=True, with_indices=True, render_geo=True, do_depth=True),
+    "raw_indices_d0": dict(n=1500, W=96, H=64, seed=15, with_hier=True, with_indices=True, render_geo=True, do_depth=True, sh_degree=0),
     "nogeo": dict(n=1500, W=100, H=70, seed=14, with_hier=False, with_indices=False, render_geo=False, do_depth=False),
 }
 
@@ -35,9 +36,9 @@ def main(out_dir):
     dev = torch.device("cuda:0")
     REF = ru.ref_module()
     for name, p in CASES.items():
-        case = ru.build_case(p["n"], p["W"], p["H"], seed=p["seed"], with_hier=p["with_hier"], with_indices=p["with_indices"])
+        case = ru.build_case(p["n"], p["W"], p["H"], seed=p["seed"], with_hier=p["with_hier"], with_indices=p["with_indices"],
+                             sh_degree=p.get("sh_degree", 3))
         fa = ru.op_args(case, dev, render_geo=p["render_geo"], do_depth=p["do_depth"])
-        ru.zero_prime(dev)  # deterministic "unwritten clamp flags" for slots with parents (see raster_utils)
         ref = REF.rasterize_gaussians(*fa)
         torch.cuda.synchronize()
         st = ru.ref_state(ref, case["P"], p["W"], p["H"])

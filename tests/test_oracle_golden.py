@@ -28,7 +28,8 @@ def test_golden_fixtures_exist():
 def test_oracle_reproduces_reference(path):
     gold = np.load(path)
     p = json.loads(bytes(gold["params"]).decode())
-    case = ru.build_case(p["n"], p["W"], p["H"], seed=p["seed"], with_hier=p["with_hier"], with_indices=p["with_indices"])
+    case = ru.build_case(p["n"], p["W"], p["H"], seed=p["seed"], with_hier=p["with_hier"], with_indices=p["with_indices"],
+                         sh_degree=p.get("sh_degree", 3))
     o = ru.oracle_for_case(case, render_geo=p["render_geo"], do_depth=p["do_depth"])
     out = o.forward()
     assert out["num_rendered"] == int(gold["num_rendered"])
@@ -59,8 +60,9 @@ def test_oracle_reproduces_reference(path):
     g = syn.upstream_grads(p["W"], p["H"], do_depth=p["do_depth"])
     og = o.backward(g["color"].numpy(), g["all_map"].numpy(), g["plane_depth"].numpy(),
                     g["invdepth"].numpy() if p["do_depth"] else None)
-    ours = [torch.from_numpy(og[n]) for n in ru.GRAD_NAMES]
-    theirs = [torch.from_numpy(gold[n]) for n in ru.GRAD_NAMES]
+    a = ru.mask_undefined_parent_rows(case, {n: torch.from_numpy(og[n]) for n in ru.GRAD_NAMES})
+    b = ru.mask_undefined_parent_rows(case, {n: torch.from_numpy(gold[n]) for n in ru.GRAD_NAMES})
+    ours, theirs = [a[n] for n in ru.GRAD_NAMES], [b[n] for n in ru.GRAD_NAMES]
     if p["with_hier"]:
         for name, a, b in zip(ru.GRAD_NAMES, ours, theirs):
             assert ru.rel_report(a, b)[2] < 3e-3, name
