@@ -139,25 +139,25 @@ def rasterize_gaussians(background, indices, parent_indices, ts, kids, means3D, 
     M = sh.size(1) if sh.numel() != 0 else 0
     f32 = dict(dtype=torch.float32, device=dev)
     i32 = dict(dtype=torch.int32, device=dev)
-    # The library writes every element of these outputs, so no zero fill is needed.  All float
-    # images come from one allocation and both int vectors from another (two blocks of constant
-    # size per view instead of six).
-    HW = H * W
-    nd = 1 if do_depth else 0
-    out_f = torch.empty(((9 + nd) * HW,), **f32)
-    out_color = out_f[:3 * HW].view(3, H, W)
-    out_all_map = out_f[3 * HW:8 * HW].view(5, H, W)
-    out_plane_depth = out_f[8 * HW:9 * HW].view(1, H, W)
-    out_invdepth = out_f[9 * HW:].view(nd, H, W)
-    out_i = torch.empty((2 * P,), **i32)
-    radii, out_observe = out_i[:P], out_i[P:]
     rendered = ctypes.c_int32(0)
     if P != 0 and all_map.numel() != 0 and all_map.size(0) < P:
         raise RuntimeError("all_map must have one row per rendered slot")
 
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream().cuda_stream
-        ws = _Workspace(dev, P, W, H)
+        ws = _Workspace(dev, P, W, H)  # largest block first: keeps the allocator from splitting it
+        # The library writes every element of these outputs, so no zero fill is needed.  All float
+        # images come from one allocation and both int vectors from another (two blocks of constant
+        # size per view instead of six).
+        HW = H * W
+        nd = 1 if do_depth else 0
+        out_f = torch.empty(((9 + nd) * HW,), **f32)
+        out_color = out_f[:3 * HW].view(3, H, W)
+        out_all_map = out_f[3 * HW:8 * HW].view(5, H, W)
+        out_plane_depth = out_f[8 * HW:9 * HW].view(1, H, W)
+        out_invdepth = out_f[9 * HW:].view(nd, H, W)
+        out_i = torch.empty((2 * P,), **i32)
+        radii, out_observe = out_i[:P], out_i[P:]
         s = _inputs(P, N, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, render_geo, debug,
                     background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D, sh,
                     colors, all_map, opacity, scales, rotations, cov3D_precomp)
