@@ -1,0 +1,868 @@
+// freq_loss.cu — multi-scale frequency regulariser: gray pyramid, Sobel/Laplacian loss, shared-memory
+// mixed-radix FFT, spectral (log-magnitude / phase / band-energy) loss, its gradient back to the
+// rendered image, and the high-frequency mask.
+//
+// Replaces TrueFrequencyPyramidRegularizer of scripts/frequency_regularization.py: build_pyramid
+// (:1073-1082), _compute_spatial_frequency_loss (:1327-1360), compute_fft_features (:1084-1164),
+// _compute_fft_frequency_loss (:1362-1401), compute_true_frequency_loss (:1293-1325) and
+// detect_true_high_frequency_regions (:1166-1271), including the autograd backward of all of them
+// (torch.clamp passes gradient only inside [min, max]; torch.min(a, b) splits it on ties; angle/abs
+// have zero gradient at 0).
+//
+// FFT (sizes factor as 2^a 3^b 5^c, e.g. 1080 x 1920): Stockham autosort in shared memory, radix
+// 4/2/3/5 butterflies, twiddles from sincospif (no tables).  Rows: one CTA per image row, real input
+// -> W/2+1 complex outputs.  Columns: one CTA per group of adjacent columns, whole column resident in
+// shared memory (<= 96 KB).  The spectrum of a level (<= 8.3 MB) stays in L2 between the two passes.
+// The inverse used by the backward is the conjugate of the forward (conj -> FFT -> conj) followed by
+// a Hermitian completion per row, i.e. an unnormalised C2R.
+//
+// No dense matmul / tensor-core DFT: at fp32 accuracy (the loss takes log|F| of coefficients down to
+// the noise floor) a TF32 DFT-as-GEMM does not meet the 1e-3 loss tolerance, and the FFT work here is
+// a few MFLOP per level.
+#include "common.cuh"
+#include "../../include/hidegs_losses.h"
+
+namespace hg {
+
+namespace {
+
+constexpr int kMaxRadices = 14;
+constexpr int kFftThreads = 256;
+constexpr float kPi = 3.14159265358979323846f;
+
+struct Plan {
+  int n;
+  int nr;
+  int radix[kMaxRadices];
+};
+
+bool make_plan(int n, Plan* p) {
+  p->n = n;
+  p->nr = 0;
+  int m = n;
+  while (m % 4 == 0) { p->radix[p->nr++] = 4; m /= 4; }
+  while (m % 2 == 0) { p->radix[p->nr++] = 2; m /= 2; }
+  while (m % 3 == 0) { p->radix[p->nr++] = 3; m /= 3; }
+  while (m % 5 == 0) { p->radix[p->nr++] = 5; m /= 5; }
+  return m == 1 && p->nr <= kMaxRadices;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward transform convention e^{-i...})
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+template <int R>
+__device__ __forceinline__ void dft(float2* v);
+template <>
+__device__ __forceinline__ void dft<2>(float2* v) {
+  const float2 a = v[0], b = v[1];
+  v[0] = cadd(a, b);
+  v[1] = csub(a, b);
+}
+template <>
+__device__ __forceinline__ void dft<4>(float2* v) {
+  const float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+  const float2 c = cadd(v[1], v[3]), d = mul_mi(csub(v[1], v[3]));
+  v[0] = cadd(a, c);
+  v[1] = cadd(b, d);
+  v[2] = csub(a, c);
+  v[3] = csub(b, d);
+}
+template <>
+__device__ __forceinline__ void dft<3>(float2* v) {
+  const float s = 0.86602540378443864676f;  // sin(2 pi / 3)
+  const float2 t1 = cadd(v[1], v[2]);
+  const float2 t2 = make_float2(v[0].x - 0.5f * t1.x, v[0].y - 0.5f * t1.y);
+  const float2 d = csub(v[1], v[2]);
+  const float2 t3 = make_float2(s * d.y, -s * d.x);  // -i * s * d
+  v[0] = cadd(v[0], t1);
+  v[1] = cadd(t2, t3);
+  v[2] = csub(t2, t3);
+}
+template <>
+__device__ __forceinline__ void dft<5>(float2* v) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;  // cos(2pi/5), cos(4pi/5)
+  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;   // sin(2pi/5), sin(4pi/5)
+  const float2 a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+  const float2 a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+  const float2 x0 = v[0];
+  const float2 m1 = make_float2(x0.x + c1 * a1.x + c2 * a2.x, x0.y + c1 * a1.y + c2 * a2.y);
+  const float2 m2 = make_float2(x0.x + c2 * a1.x + c1 * a2.x, x0.y + c2 * a1.y + c1 * a2.y);
+  // -i * (s1 b1 + s2 b2) and -i * (s2 b1 - s1 b2)
+  const float2 n1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));
+  const float2 n2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));
+  v[0] = make_float2(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
+  v[1] = cadd(m1, n1);
+  v[4] = csub(m1, n1);
+  v[2] = cadd(m2, n2);
+  v[3] = csub(m2, n2);
+}
+
+// One Stockham pass of radix R over `batch` independent length-n sequences stored back to back.
+template <int R>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst, int n,
+                                              int ns, int batch) {
+  const int per = n / R;
+  for (int w = threadIdx.x; w < per * batch; w += blockDim.x) {
+    const int b = w / per, j = w - b * per;
+    const float2* s = src + b * n;
+    float2* d = dst + b * n;
+    const int k = j % ns;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = s[j + r * per];
+    if (ns > 1) {
+      const float base = -2.0f * (float)k / (float)(ns * R);
+#pragma unroll
+      for (int r = 1; r < R; ++r) {
+        float sn, cs;
+        sincospif(base * (float)r, &sn, &cs);
+        v[r] = cmul(v[r], make_float2(cs, sn));
+      }
+    }
+    dft<R>(v);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) d[j0 + r * ns] = v[r];
+  }
+}
+
+// Forward FFT of `batch` sequences in shared memory; returns the buffer that holds the result.
+__device__ float2* fft_smem(float2* a, float2* b, const Plan& p, int batch) {
+  int ns = 1;
+  float2 *src = a, *dst = b;
+  for (int i = 0; i < p.nr; ++i) {
+    const int R = p.radix[i];
+    if (R == 4) stockham_pass<4>(src, dst, p.n, ns, batch);
+    else if (R == 2) stockham_pass<2>(src, dst, p.n, ns, batch);
+    else if (R == 3) stockham_pass<3>(src, dst, p.n, ns, batch);
+    else stockham_pass<5>(src, dst, p.n, ns, batch);
+    ns *= R;
+    __syncthreads();
+    float2* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+// ---- rows: real [H][W] (optionally clamped to [0,1]) -> half spectrum [H][W/2+1]
+__global__ void __launch_bounds__(kFftThreads)
+fft_rows_r2c_kernel(const float* __restrict__ img, int W, int clamp01, float2* __restrict__ spec, Plan plan) {
+  extern __shared__ float2 sm[];
+  float2 *a = sm, *b = sm + W;
+  const int row = blockIdx.x;
+  const float* src = img + (size_t)row * W;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    float v = __ldg(src + i);
+    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+    a[i] = make_float2(v, 0.f);
+  }
+  __syncthreads();
+  const float2* r = fft_smem(a, b, plan, 1);
+  const int Wh = W / 2 + 1;
+  float2* dst = spec + (size_t)row * Wh;
+  for (int i = threadIdx.x; i < Wh; i += blockDim.x) dst[i] = r[i];
+}
+
+// ---- columns, in place on [H][Wh]; INVERSE: conj -> FFT -> conj (unnormalised inverse)
+template <bool INVERSE>
+__global__ void __launch_bounds__(kFftThreads)
+fft_cols_kernel(float2* __restrict__ spec, int H, int Wh, int tc, Plan plan) {
+  extern __shared__ float2 sm[];
+  float2 *a = sm, *b = sm + (size_t)tc * H;
+  const int c0 = blockIdx.x * tc;
+  const int nc = min(tc, Wh - c0);
+  for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
+    const int y = i / tc, c = i - y * tc;
+    float2 v = make_float2(0.f, 0.f);
+    if (c < nc) v = spec[(size_t)y * Wh + c0 + c];
+    if (INVERSE) v.y = -v.y;
+    a[c * H + y] = v;
+  }
+  __syncthreads();
+  const float2* r = fft_smem(a, b, plan, tc);
+  for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
+    const int y = i / tc, c = i - y * tc;
+    if (c < nc) {
+      float2 v = r[c * H + y];
+      if (INVERSE) v.y = -v.y;
+      spec[(size_t)y * Wh + c0 + c] = v;
+    }
+  }
+}
+
+// ---- rows of the inverse: Hermitian completion of the half row, inverse FFT, real part * scale
+__global__ void __launch_bounds__(kFftThreads)
+fft_rows_c2r_kernel(const float2* __restrict__ spec, int W, float scale, float* __restrict__ img, Plan plan) {
+  extern __shared__ float2 sm[];
+  float2 *a = sm, *b = sm + W;
+  const int row = blockIdx.x;
+  const int Wh = W / 2 + 1;
+  const float2* src = spec + (size_t)row * Wh;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    // conj of the completed row: X[k] for k <= W/2, conj(X[W-k]) above; then conjugate for the inverse
+    float2 v;
+    if (i < Wh) { v = src[i]; v.y = -v.y; }
+    else v = src[W - i];
+    a[i] = v;
+  }
+  __syncthreads();
+  const float2* r = fft_smem(a, b, plan, 1);
+  float* dst = img + (size_t)row * W;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) dst[i] = r[i].x * scale;
+}
+
+struct FftCfg {
+  Plan row, col;
+  int tc;
+  size_t smem_row, smem_col;
+};
+
+int make_cfg(int H, int W, FftCfg* c) {
+  if (H <= 0 || W <= 1 || H > 4096 || W > 4096 || !make_plan(W, &c->row) || !make_plan(H, &c->col)) {
+    set_error("FFT size %dx%d unsupported (needs factors 2,3,5 and <= 4096)", H, W);
+    return HG_ERR_INVALID_ARG;
+  }
+  c->tc = (int)((96 * 1024) / (16 * (size_t)H));
+  if (c->tc > 8) c->tc = 8;
+  if (c->tc < 1) c->tc = 1;
+  c->smem_row = 2 * (size_t)W * sizeof(float2);
+  c->smem_col = 2 * (size_t)c->tc * H * sizeof(float2);
+  return HG_OK;
+}
+
+int set_smem_attrs() {
+  static bool done = false;
+  if (done) return HG_OK;
+  const int maxb = 100 * 1024;
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_rows_r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_rows_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  done = true;
+  return HG_OK;
+}
+
+int fft2_r2c(const float* img, int H, int W, int clamp01, float2* spec, cudaStream_t st) {
+  FftCfg c;
+  int rc = make_cfg(H, W, &c);
+  if (rc) return rc;
+  rc = set_smem_attrs();
+  if (rc) return rc;
+  const int Wh = W / 2 + 1;
+  fft_rows_r2c_kernel<<<H, kFftThreads, c.smem_row, st>>>(img, W, clamp01, spec, c.row);
+  HG_POST_LAUNCH(false, st, "fft_rows_r2c");
+  fft_cols_kernel<false><<<(Wh + c.tc - 1) / c.tc, kFftThreads, c.smem_col, st>>>(spec, H, Wh, c.tc, c.col);
+  HG_POST_LAUNCH(false, st, "fft_cols");
+  return HG_OK;
+}
+
+// spec is destroyed (the column pass runs in place)
+int fft2_c2r(float2* spec, int H, int W, float scale, float* img, cudaStream_t st) {
+  FftCfg c;
+  int rc = make_cfg(H, W, &c);
+  if (rc) return rc;
+  rc = set_smem_attrs();
+  if (rc) return rc;
+  const int Wh = W / 2 + 1;
+  fft_cols_kernel<true><<<(Wh + c.tc - 1) / c.tc, kFftThreads, c.smem_col, st>>>(spec, H, Wh, c.tc, c.col);
+  HG_POST_LAUNCH(false, st, "ifft_cols");
+  fft_rows_c2r_kernel<<<H, kFftThreads, c.smem_row, st>>>(spec, W, scale, img, c.row);
+  HG_POST_LAUNCH(false, st, "ifft_rows_c2r");
+  return HG_OK;
+}
+
+// =============================================================== pyramid / spatial terms
+__global__ void gray_kernel(const float* __restrict__ img, int64_t hw, float* __restrict__ gray) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hw) gray[i] = (__ldg(img + i) + __ldg(img + hw + i) + __ldg(img + 2 * hw + i)) / 3.0f;
+}
+
+__global__ void pool_kernel(const float* __restrict__ src, int Ws, int Hd, int Wd, float* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= Wd || y >= Hd) return;
+  const float* p = src + (size_t)(2 * y) * Ws + 2 * x;
+  dst[(size_t)y * Wd + x] = (p[0] + p[1] + p[Ws] + p[Ws + 1]) * 0.25f;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* smem, int tid, int nthreads) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  const int nw = (nthreads + 31) >> 5;
+  v = (tid < nw) ? smem[tid] : 0.f;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  __syncthreads();
+  return v;
+}
+
+// Per-level control block written by the finalize kernel and read by the gradient kernels.
+struct LevelCtl {
+  float c_sobel, c_lap;      // coefficients of d(loss)/d(response) = c * response
+  float c_mag, c_phase;      // spectral coefficients
+  float c_band[4];
+  float band_count[4];
+};
+
+constexpr int kSpTile = 16;
+// d = gray_r - gray_g (zero outside), responses of Sobel-x / Sobel-y / Laplacian (cross-correlation, zero pad 1)
+__device__ __forceinline__ void responses(const float (*d)[kSpTile + 4 + 1], int r, int c, float& sx, float& sy,
+                                          float& lp) {
+  // d[r][c] is the centre; neighbours at +-1
+  const float a00 = d[r - 1][c - 1], a01 = d[r - 1][c], a02 = d[r - 1][c + 1];
+  const float a10 = d[r][c - 1], a11 = d[r][c], a12 = d[r][c + 1];
+  const float a20 = d[r + 1][c - 1], a21 = d[r + 1][c], a22 = d[r + 1][c + 1];
+  sx = -a00 + a02 - 2.f * a10 + 2.f * a12 - a20 + a22;
+  sy = -a00 - 2.f * a01 - a02 + a20 + 2.f * a21 + a22;
+  lp = -a01 - a10 + 4.f * a11 - a12 - a21;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kSpTile * kSpTile)
+spatial_kernel(const float* __restrict__ gr, const float* __restrict__ gg, int H, int W,
+               double* __restrict__ partial, const LevelCtl* __restrict__ ctl, float* __restrict__ dgray) {
+  __shared__ float d[kSpTile + 4][kSpTile + 4 + 1];
+  __shared__ float rx[kSpTile + 2][kSpTile + 2 + 1], ry[kSpTile + 2][kSpTile + 2 + 1], rl[kSpTile + 2][kSpTile + 2 + 1];
+  __shared__ float red[32];
+  const int x0 = blockIdx.x * kSpTile, y0 = blockIdx.y * kSpTile;
+  const int tid = threadIdx.y * kSpTile + threadIdx.x;
+  for (int i = tid; i < (kSpTile + 4) * (kSpTile + 4); i += kSpTile * kSpTile) {
+    const int r = i / (kSpTile + 4), c = i % (kSpTile + 4);
+    const int y = y0 + r - 2, x = x0 + c - 2;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    d[r][c] = in ? (__ldg(gr + (size_t)y * W + x) - __ldg(gg + (size_t)y * W + x)) : 0.f;
+  }
+  __syncthreads();
+  if (!GRAD) {
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    float sx = 0.f, sy = 0.f, lp = 0.f;
+    if (x < W && y < H) responses(d, threadIdx.y + 2, threadIdx.x + 2, sx, sy, lp);
+    const float s0 = block_sum(sx * sx, red, tid, kSpTile * kSpTile);
+    const float s1 = block_sum(sy * sy, red, tid, kSpTile * kSpTile);
+    const float s2 = block_sum(lp * lp, red, tid, kSpTile * kSpTile);
+    if (tid == 0) {
+      double* p = partial + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+      p[0] = s0; p[1] = s1; p[2] = s2;
+    }
+    return;
+  }
+  // responses on the tile + halo 1, scaled by their loss coefficients, zero outside the image
+  const float cs = ctl->c_sobel, cl = ctl->c_lap;
+  for (int i = tid; i < (kSpTile + 2) * (kSpTile + 2); i += kSpTile * kSpTile) {
+    const int r = i / (kSpTile + 2), c = i % (kSpTile + 2);
+    const int y = y0 + r - 1, x = x0 + c - 1;
+    float sx = 0.f, sy = 0.f, lp = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) responses(d, r + 1, c + 1, sx, sy, lp);
+    rx[r][c] = cs * sx; ry[r][c] = cs * sy; rl[r][c] = cl * lp;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  // dL/dd(p) = sum_{u,v} K[u][v] * R(p - (u-1, v-1))
+  const int r = threadIdx.y + 1, c = threadIdx.x + 1;
+  const float gx = -rx[r + 1][c + 1] + rx[r + 1][c - 1] - 2.f * rx[r][c + 1] + 2.f * rx[r][c - 1] - rx[r - 1][c + 1] + rx[r - 1][c - 1];
+  const float gy = -ry[r + 1][c + 1] - 2.f * ry[r + 1][c] - ry[r + 1][c - 1] + ry[r - 1][c + 1] + 2.f * ry[r - 1][c] + ry[r - 1][c - 1];
+  const float gl = -rl[r + 1][c] - rl[r][c + 1] + 4.f * rl[r][c] - rl[r][c - 1] - rl[r - 1][c];
+  dgray[(size_t)y * W + x] += gx + gy + gl;
+}
+
+// =============================================================== spectral terms
+__device__ __forceinline__ int signed_freq(int k, int n) { return (k < (n + 1) / 2) ? k : k - n; }
+
+__device__ __forceinline__ int band_of(int ky, int kx, int H, int W) {
+  const int fy = signed_freq(ky, H), fx = signed_freq(kx, W);
+  const float dist = sqrtf((float)(fy * fy + fx * fx));
+  const float md = (float)min(H / 2, W / 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (dist >= (float)i * md / 4.0f && dist < (float)(i + 1) * md / 4.0f) return i;
+  return -1;
+}
+
+constexpr int kSpecVals = 14;  // mag, phase, band_r[4], band_g[4], count[4]
+__global__ void __launch_bounds__(256)
+spectral_sums_kernel(const float2* __restrict__ fr, const float2* __restrict__ fg, int H, int W,
+                     double* __restrict__ partial) {
+  __shared__ float red[32];
+  const int Wh = W / 2 + 1;
+  float acc[kSpecVals];
+#pragma unroll
+  for (int i = 0; i < kSpecVals; ++i) acc[i] = 0.f;
+  const int64_t n = (int64_t)H * Wh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
+    const float w = (kx == 0 || (2 * kx == W)) ? 1.f : 2.f;  // Hermitian twin outside the half spectrum
+    const float2 a = fr[i], b = fg[i];
+    const float ma = hypotf(a.x, a.y), mb = hypotf(b.x, b.y);
+    const float dl = __logf(ma + 1e-6f) - __logf(mb + 1e-6f);
+    acc[0] += w * dl * dl;
+    const float pa = atan2f(a.y, a.x), pb = atan2f(b.y, b.x);
+    const float ad = fabsf(pa - pb);
+    acc[1] += w * fminf(ad, 2.f * kPi - ad);
+    const int band = band_of(ky, kx, H, W);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (band == q) { acc[2 + q] += w * ma; acc[6 + q] += w * mb; acc[10 + q] += w; }
+  }
+#pragma unroll
+  for (int q = 0; q < kSpecVals; ++q) {
+    const float s = block_sum(acc[q], red, threadIdx.x, 256);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * kSpecVals + q] = (double)s;
+  }
+}
+
+// band energies of a single spectrum (debug_info['freq_band_energies'] of the level-0 GT)
+__global__ void __launch_bounds__(256)
+band_energy_kernel(const float2* __restrict__ f, int H, int W, double* __restrict__ partial) {
+  __shared__ float red[32];
+  const int Wh = W / 2 + 1;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int64_t n = (int64_t)H * Wh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
+    const float w = (kx == 0 || (2 * kx == W)) ? 1.f : 2.f;
+    const int band = band_of(ky, kx, H, W);
+    if (band >= 0) {
+      const float2 a = f[i];
+      const float m = hypotf(a.x, a.y);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (band == q) { acc[q] += w * m; acc[4 + q] += w; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float s = block_sum(acc[q], red, threadIdx.x, 256);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * 8 + q] = (double)s;
+  }
+}
+
+constexpr int kSumBlocks = 148 * 2;
+
+struct LevelDims { int H, W; };
+struct FreqFinalizeArgs {
+  int levels;
+  LevelDims dim[3];
+  const double* spatial_partial[3];
+  int spatial_blocks[3];
+  const double* spectral_partial[3];
+  const double* band0_partial;  // level-0 GT band energies
+  LevelCtl* ctl;
+  float* stats;
+};
+
+__device__ __forceinline__ bool within(float v, float lo, float hi) { return v >= lo && v <= hi; }
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// Scalar epilogue of compute_true_frequency_loss, and the coefficients its backward needs.
+__global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
+  if (threadIdx.x != 0) return;
+  const float w_lvl[3] = {0.1f, 0.05f, 0.025f};
+  float total = 0.f;
+  float lvl_raw[3] = {0, 0, 0};
+  float sp_raw[3], fft_raw[3], mag_raw[3], ph_raw[3], band_raw[3];
+  float er[3][4], eg[3][4], cnt[3][4];
+  for (int l = 0; l < a.levels; ++l) {
+    const double n = (double)a.dim[l].H * a.dim[l].W;
+    double s[3] = {0, 0, 0};
+    for (int i = 0; i < a.spatial_blocks[l]; ++i)
+      for (int q = 0; q < 3; ++q) s[q] += a.spatial_partial[l][3 * i + q];
+    const float gx = (float)(s[0] / n), gy = (float)(s[1] / n), lap = (float)(s[2] / n);
+    sp_raw[l] = 0.7f * (gx + gy) + 0.3f * lap;
+    double v[kSpecVals];
+    for (int q = 0; q < kSpecVals; ++q) v[q] = 0.0;
+    for (int i = 0; i < kSumBlocks; ++i)
+      for (int q = 0; q < kSpecVals; ++q) v[q] += a.spectral_partial[l][(size_t)i * kSpecVals + q];
+    mag_raw[l] = (float)(v[0] / n);
+    ph_raw[l] = (float)(v[1] / n);
+    float bl = 0.f;
+    for (int q = 0; q < 4; ++q) {
+      cnt[l][q] = (float)v[10 + q];
+      er[l][q] = cnt[l][q] > 0.f ? (float)(v[2 + q] / (v[10 + q] + 1e-8)) : 0.f;
+      eg[l][q] = cnt[l][q] > 0.f ? (float)(v[6 + q] / (v[10 + q] + 1e-8)) : 0.f;
+      bl += (er[l][q] - eg[l][q]) * (er[l][q] - eg[l][q]);
+    }
+    band_raw[l] = bl / 4.f;
+    const float mag = clampf(mag_raw[l], 0.f, 10.f), ph = clampf(ph_raw[l], 0.f, kPi), band = clampf(band_raw[l], 0.f, 100.f);
+    fft_raw[l] = 0.6f * mag + 0.2f * ph + 0.2f * band;
+    const float sp = clampf(sp_raw[l], 0.f, 1.f), ff = clampf(fft_raw[l], 0.f, 10.f);
+    lvl_raw[l] = 0.7f * sp + 0.3f * ff;
+    const float lvl = clampf(lvl_raw[l], 0.f, 0.1f);
+    total += w_lvl[l] * lvl;
+    float* st = a.stats + 1 + 6 * l;
+    st[0] = sp; st[1] = ff; st[2] = lvl; st[3] = mag; st[4] = ph; st[5] = band;
+  }
+  a.stats[0] = clampf(total, 0.f, 0.1f);
+  const float g_total = within(total, 0.f, 0.1f) ? 1.f : 0.f;
+  for (int l = 0; l < a.levels; ++l) {
+    const float n = (float)a.dim[l].H * (float)a.dim[l].W;
+    const float g_level = g_total * w_lvl[l] * (within(lvl_raw[l], 0.f, 0.1f) ? 1.f : 0.f);
+    const float g_sp = g_level * 0.7f * (within(sp_raw[l], 0.f, 1.f) ? 1.f : 0.f);
+    const float g_fft = g_level * 0.3f * (within(fft_raw[l], 0.f, 10.f) ? 1.f : 0.f);
+    LevelCtl& c = a.ctl[l];
+    c.c_sobel = g_sp * 0.7f * 2.f / n;
+    c.c_lap = g_sp * 0.3f * 2.f / n;
+    c.c_mag = g_fft * 0.6f * (within(mag_raw[l], 0.f, 10.f) ? 1.f : 0.f) * 2.f / n;
+    c.c_phase = g_fft * 0.2f * (within(ph_raw[l], 0.f, kPi) ? 1.f : 0.f) / n;
+    const float gb = g_fft * 0.2f * (within(band_raw[l], 0.f, 100.f) ? 1.f : 0.f);
+    for (int q = 0; q < 4; ++q) {
+      c.band_count[q] = cnt[l][q];
+      c.c_band[q] = cnt[l][q] > 0.f ? gb * (2.f / 4.f) * (er[l][q] - eg[l][q]) / (cnt[l][q] + 1e-8f) : 0.f;
+    }
+  }
+  // band energies of the level-0 ground truth (debug_info)
+  double e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < kSumBlocks; ++i)
+    for (int q = 0; q < 8; ++q) e[q] += a.band0_partial[(size_t)i * 8 + q];
+  for (int q = 0; q < 4; ++q) a.stats[19 + q] = e[4 + q] > 0.0 ? (float)(e[q] / (e[4 + q] + 1e-8)) : 0.f;
+}
+
+// Gradient of the spectral loss w.r.t. the rendered spectrum, written in place over `fr`.
+__global__ void __launch_bounds__(256)
+spectral_grad_kernel(float2* __restrict__ fr, const float2* __restrict__ fg, int H, int W,
+                     const LevelCtl* __restrict__ ctl) {
+  const int Wh = W / 2 + 1;
+  const int64_t n = (int64_t)H * Wh;
+  const float c_mag = ctl->c_mag, c_phase = ctl->c_phase;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
+    const float2 a = fr[i], b = fg[i];
+    const float ma = hypotf(a.x, a.y), mb = hypotf(b.x, b.y);
+    float gre = 0.f, gim = 0.f;
+    if (ma > 0.f) {
+      float dmag = c_mag * (__logf(ma + 1e-6f) - __logf(mb + 1e-6f)) / (ma + 1e-6f);
+      const int band = band_of(ky, kx, H, W);
+      if (band >= 0) dmag += ctl->c_band[band];
+      gre = dmag * a.x / ma;
+      gim = dmag * a.y / ma;
+      const float pa = atan2f(a.y, a.x), pb = atan2f(b.y, b.x);
+      const float dlt = pa - pb, ad = fabsf(dlt);
+      const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+      const float other = 2.f * kPi - ad;
+      // d min(|D|, 2pi - |D|) / dD, with torch.min's even split on ties
+      const float dw = ad < other ? sgn : (ad > other ? -sgn : 0.f);
+      const float gp = c_phase * dw / (ma * ma);
+      gre += gp * (-a.y);
+      gim += gp * a.x;
+    }
+    fr[i] = make_float2(gre, gim);
+  }
+}
+
+// dgray (from the inverse FFT, w.r.t. the CLAMPED gray) -> gate by the clamp and overwrite
+__global__ void clamp_gate_kernel(const float* __restrict__ gray, int64_t n, float* __restrict__ dgray) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float g = gray[i];
+    if (!(g >= 0.f && g <= 1.f)) dgray[i] = 0.f;
+  }
+}
+
+// dgray_fine += 0.25 * dgray_coarse (avg_pool2d backward)
+__global__ void unpool_add_kernel(const float* __restrict__ dcoarse, int Hc, int Wc, int Wf, float* __restrict__ dfine) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= 2 * Wc || y >= 2 * Hc) return;
+  dfine[(size_t)y * Wf + x] += 0.25f * dcoarse[(size_t)(y >> 1) * Wc + (x >> 1)];
+}
+
+__global__ void gray_to_rgb_grad_kernel(const float* __restrict__ dgray, int64_t hw, float* __restrict__ dimg) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < hw) {
+    const float g = dgray[i] / 3.0f;
+    dimg[i] = g; dimg[hw + i] = g; dimg[2 * hw + i] = g;
+  }
+}
+
+// =============================================================== high-frequency mask
+__global__ void __launch_bounds__(kSpTile * kSpTile)
+hf_spatial_kernel(const float* __restrict__ gray, int H, int W, float* __restrict__ score) {
+  __shared__ float d[kSpTile + 4][kSpTile + 4 + 1];
+  const int x0 = blockIdx.x * kSpTile, y0 = blockIdx.y * kSpTile;
+  const int tid = threadIdx.y * kSpTile + threadIdx.x;
+  for (int i = tid; i < (kSpTile + 4) * (kSpTile + 4); i += kSpTile * kSpTile) {
+    const int r = i / (kSpTile + 4), c = i % (kSpTile + 4);
+    const int y = y0 + r - 2, x = x0 + c - 2;
+    d[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(gray + (size_t)y * W + x) : 0.f;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  float sx, sy, lp;
+  responses(d, threadIdx.y + 2, threadIdx.x + 2, sx, sy, lp);
+  score[(size_t)y * W + x] = 0.6f * sqrtf(sx * sx + sy * sy + 1e-8f) + 0.4f * fabsf(lp);
+}
+
+__global__ void highpass_kernel(float2* __restrict__ spec, int H, int W) {
+  const int Wh = W / 2 + 1;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)H * Wh) return;
+  const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
+  const int fy = signed_freq(ky, H), fx = signed_freq(kx, W);
+  const float dist = sqrtf((float)(fy * fy + fx * fx));
+  const float radius = (float)((double)min(H / 2, W / 2) * 0.3);
+  if (!(dist > radius)) spec[i] = make_float2(0.f, 0.f);
+}
+
+// op 0: v = |x| -> max;  op 1: combined score -> min/max;  partial: [blocks][2]
+__global__ void __launch_bounds__(256)
+hf_reduce_kernel(float* __restrict__ hs, const float* __restrict__ spatial, const float* __restrict__ mm_in, int64_t n,
+                 int op, float* __restrict__ pmin, float* __restrict__ pmax) {
+  __shared__ float smin[8], smax[8];
+  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (op == 0) {
+      v = fabsf(hs[i]);
+      hs[i] = v;
+    } else {
+      float h = hs[i];
+      const float mx = mm_in[1];
+      if (mx > 1e-8f) h = h / mx;
+      v = fminf(fmaxf(0.7f * spatial[i] + 0.3f * h, 0.f), 5.0f);
+      hs[i] = v;
+    }
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { lo = fminf(lo, smin[i]); hi = fmaxf(hi, smax[i]); }
+    pmin[blockIdx.x] = lo;
+    pmax[blockIdx.x] = hi;
+  }
+}
+
+__global__ void hf_minmax_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax, int n,
+                                 float* __restrict__ mm) {
+  if (threadIdx.x != 0) return;
+  float lo = pmin[0], hi = pmax[0];
+  for (int i = 1; i < n; ++i) { lo = fminf(lo, pmin[i]); hi = fmaxf(hi, pmax[i]); }
+  mm[0] = lo; mm[1] = hi;
+}
+
+__global__ void __launch_bounds__(256)
+hf_threshold_kernel(const float* __restrict__ score, const float* __restrict__ mm, int64_t n, float thresh,
+                    float* __restrict__ mask, double* __restrict__ partial) {
+  __shared__ float red[32];
+  float cnt = 0.f;
+  const float lo = mm[0], range = mm[1] - mm[0];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float s = range > 1e-6f ? (score[i] - lo) / range : 0.f;
+    const float m = s > thresh ? 1.f : 0.f;
+    mask[i] = m;
+    cnt += m;
+  }
+  const float s = block_sum(cnt, red, threadIdx.x, 256);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
+}
+
+__global__ void hf_count_kernel(const double* __restrict__ partial, int n, float* __restrict__ count) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += partial[i];
+  count[0] = (float)s;
+}
+
+struct Carver {
+  char* p;
+  explicit Carver(void* base) : p((char*)(((uintptr_t)base + 255) / 256 * 256)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* r = (T*)p;
+    p += (count * sizeof(T) + 255) / 256 * 256;
+    return r;
+  }
+};
+
+size_t level_bytes(int H, int W) {
+  const size_t hw = (size_t)H * W, sp = (size_t)H * (W / 2 + 1);
+  const size_t tiles = (size_t)((W + kSpTile - 1) / kSpTile) * ((H + kSpTile - 1) / kSpTile);
+  return 3 * (hw * 4 + 256) + 2 * (sp * 8 + 256) + (tiles * 3 * 8 + 256) + ((size_t)kSumBlocks * kSpecVals * 8 + 256);
+}
+
+}  // namespace
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+size_t hg_fft2_workspace_bytes(int32_t H, int32_t W) { return (size_t)H * (W / 2 + 1) * 8 + 512; }
+
+int hg_fft2_r2c(const float* img, int32_t H, int32_t W, float* spec, void* ws, void* st) {
+  (void)ws;
+  if (!img || !spec) { set_error("hg_fft2_r2c: NULL pointer"); return HG_ERR_INVALID_ARG; }
+  return fft2_r2c(img, H, W, 0, (float2*)spec, (cudaStream_t)st);
+}
+
+int hg_fft2_c2r(const float* spec, int32_t H, int32_t W, float* img, int scale_inv, void* ws, void* st_) {
+  if (!img || !spec || !ws) { set_error("hg_fft2_c2r: NULL pointer"); return HG_ERR_INVALID_ARG; }
+  cudaStream_t st = (cudaStream_t)st_;
+  Carver cv(ws);
+  const size_t n = (size_t)H * (W / 2 + 1);
+  float2* tmp = cv.take<float2>(n);
+  HG_CUDA_TRY(cudaMemcpyAsync(tmp, spec, n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  return fft2_c2r(tmp, H, W, scale_inv ? 1.0f / ((float)H * (float)W) : 1.0f, img, st);
+}
+
+size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels) {
+  size_t total = 4096 + (size_t)kSumBlocks * 8 * 8;
+  int h = H, w = W;
+  for (int l = 0; l < levels; ++l) {
+    total += level_bytes(h, w);
+    h /= 2;
+    w /= 2;
+  }
+  return total;
+}
+
+int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, int32_t levels, float* stats,
+                 float* grad_rendered, void* ws, void* st_) {
+  if (!rendered || !gt || !stats || !ws || levels < 1 || levels > 3 || H < 4 || W < 4) {
+    set_error("hg_freq_loss: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  int hs[3], wsz[3];
+  hs[0] = H; wsz[0] = W;
+  for (int l = 1; l < levels; ++l) { hs[l] = hs[l - 1] / 2; wsz[l] = wsz[l - 1] / 2; }
+  for (int l = 0; l < levels; ++l) {
+    FftCfg c;
+    int rc = make_cfg(hs[l], wsz[l], &c);
+    if (rc) return rc;
+  }
+  Carver cv(ws);
+  LevelCtl* ctl = cv.take<LevelCtl>(3);
+  double* band0 = cv.take<double>((size_t)kSumBlocks * 8);
+  float *gr[3], *gg[3], *dg[3];
+  float2 *fr[3], *fg[3];
+  double *sp_part[3], *spec_part[3];
+  int sp_blocks[3];
+  for (int l = 0; l < levels; ++l) {
+    const size_t hw = (size_t)hs[l] * wsz[l], sp = (size_t)hs[l] * (wsz[l] / 2 + 1);
+    gr[l] = cv.take<float>(hw);
+    gg[l] = cv.take<float>(hw);
+    dg[l] = cv.take<float>(hw);
+    fr[l] = cv.take<float2>(sp);
+    fg[l] = cv.take<float2>(sp);
+    sp_blocks[l] = ((wsz[l] + kSpTile - 1) / kSpTile) * ((hs[l] + kSpTile - 1) / kSpTile);
+    sp_part[l] = cv.take<double>((size_t)sp_blocks[l] * 3);
+    spec_part[l] = cv.take<double>((size_t)kSumBlocks * kSpecVals);
+  }
+  // ---- forward
+  const int64_t hw0 = (int64_t)H * W;
+  gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(rendered, hw0, gr[0]);
+  gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(gt, hw0, gg[0]);
+  HG_POST_LAUNCH(false, st, "gray");
+  for (int l = 1; l < levels; ++l) {
+    const dim3 grid((wsz[l] + 127) / 128, hs[l]);
+    pool_kernel<<<grid, 128, 0, st>>>(gr[l - 1], wsz[l - 1], hs[l], wsz[l], gr[l]);
+    pool_kernel<<<grid, 128, 0, st>>>(gg[l - 1], wsz[l - 1], hs[l], wsz[l], gg[l]);
+    HG_POST_LAUNCH(false, st, "pool");
+  }
+  FreqFinalizeArgs fa{};
+  fa.levels = levels;
+  for (int l = 0; l < levels; ++l) {
+    const dim3 grid((wsz[l] + kSpTile - 1) / kSpTile, (hs[l] + kSpTile - 1) / kSpTile);
+    spatial_kernel<false><<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gr[l], gg[l], hs[l], wsz[l], sp_part[l], nullptr, nullptr);
+    HG_POST_LAUNCH(false, st, "spatial");
+    int rc = fft2_r2c(gr[l], hs[l], wsz[l], 1, fr[l], st);
+    if (rc) return rc;
+    rc = fft2_r2c(gg[l], hs[l], wsz[l], 1, fg[l], st);
+    if (rc) return rc;
+    spectral_sums_kernel<<<kSumBlocks, 256, 0, st>>>(fr[l], fg[l], hs[l], wsz[l], spec_part[l]);
+    HG_POST_LAUNCH(false, st, "spectral_sums");
+    fa.dim[l] = {hs[l], wsz[l]};
+    fa.spatial_partial[l] = sp_part[l];
+    fa.spatial_blocks[l] = sp_blocks[l];
+    fa.spectral_partial[l] = spec_part[l];
+  }
+  band_energy_kernel<<<kSumBlocks, 256, 0, st>>>(fg[0], hs[0], wsz[0], band0);
+  HG_POST_LAUNCH(false, st, "band_energy");
+  fa.band0_partial = band0;
+  fa.ctl = ctl;
+  fa.stats = stats;
+  freq_finalize_kernel<<<1, 32, 0, st>>>(fa);
+  HG_POST_LAUNCH(false, st, "freq_finalize");
+  if (!grad_rendered) return HG_OK;
+  // ---- backward (unit upstream gradient on freq_loss)
+  for (int l = 0; l < levels; ++l) {
+    spectral_grad_kernel<<<kSumBlocks, 256, 0, st>>>(fr[l], fg[l], hs[l], wsz[l], ctl + l);
+    HG_POST_LAUNCH(false, st, "spectral_grad");
+    int rc = fft2_c2r(fr[l], hs[l], wsz[l], 1.0f, dg[l], st);
+    if (rc) return rc;
+    const int64_t hw = (int64_t)hs[l] * wsz[l];
+    clamp_gate_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, st>>>(gr[l], hw, dg[l]);
+    HG_POST_LAUNCH(false, st, "clamp_gate");
+    const dim3 grid((wsz[l] + kSpTile - 1) / kSpTile, (hs[l] + kSpTile - 1) / kSpTile);
+    spatial_kernel<true><<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gr[l], gg[l], hs[l], wsz[l], nullptr, ctl + l, dg[l]);
+    HG_POST_LAUNCH(false, st, "spatial_grad");
+  }
+  for (int l = levels - 1; l >= 1; --l) {
+    const dim3 grid((2 * wsz[l] + 127) / 128, 2 * hs[l]);
+    unpool_add_kernel<<<grid, 128, 0, st>>>(dg[l], hs[l], wsz[l], wsz[l - 1], dg[l - 1]);
+    HG_POST_LAUNCH(false, st, "unpool_add");
+  }
+  gray_to_rgb_grad_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(dg[0], hw0, grad_rendered);
+  HG_POST_LAUNCH(false, st, "gray_to_rgb_grad");
+  return HG_OK;
+}
+
+size_t hg_hf_mask_workspace_bytes(int32_t H, int32_t W) {
+  const size_t hw = (size_t)H * W;
+  return 3 * (hw * 4 + 256) + (size_t)H * (W / 2 + 1) * 8 + 256 + 4 * (kSumBlocks * 8 + 256) + 1024;
+}
+
+int hg_hf_mask(const float* gt, int32_t H, int32_t W, float thresh, float* mask, float* count, void* ws, void* st_) {
+  if (!gt || !mask || !count || !ws || H < 4 || W < 4) {
+    set_error("hg_hf_mask: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  Carver cv(ws);
+  const int64_t hw = (int64_t)H * W;
+  float* gray = cv.take<float>(hw);
+  float* spatial = cv.take<float>(hw);
+  float* hsp = cv.take<float>(hw);
+  float2* spec = cv.take<float2>((size_t)H * (W / 2 + 1));
+  float* pmin = cv.take<float>(kSumBlocks);
+  float* pmax = cv.take<float>(kSumBlocks);
+  float* mm = cv.take<float>(4);
+  double* part = cv.take<double>(kSumBlocks);
+  gray_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, st>>>(gt, hw, gray);
+  HG_POST_LAUNCH(false, st, "gray");
+  const dim3 grid((W + kSpTile - 1) / kSpTile, (H + kSpTile - 1) / kSpTile);
+  hf_spatial_kernel<<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gray, H, W, spatial);
+  HG_POST_LAUNCH(false, st, "hf_spatial");
+  int rc = fft2_r2c(gray, H, W, 0, spec, st);  // unclamped here (frequency_regularization.py:1221)
+  if (rc) return rc;
+  const int64_t nsp = (int64_t)H * (W / 2 + 1);
+  highpass_kernel<<<(unsigned)((nsp + 255) / 256), 256, 0, st>>>(spec, H, W);
+  HG_POST_LAUNCH(false, st, "highpass");
+  rc = fft2_c2r(spec, H, W, 1.0f / ((float)H * (float)W), hsp, st);
+  if (rc) return rc;
+  hf_reduce_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, spatial, mm, hw, 0, pmin, pmax);
+  hf_minmax_kernel<<<1, 32, 0, st>>>(pmin, pmax, kSumBlocks, mm);
+  hf_reduce_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, spatial, mm, hw, 1, pmin, pmax);
+  hf_minmax_kernel<<<1, 32, 0, st>>>(pmin, pmax, kSumBlocks, mm + 2);
+  hf_threshold_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, mm + 2, hw, thresh, mask, part);
+  hf_count_kernel<<<1, 32, 0, st>>>(part, kSumBlocks, count);
+  HG_POST_LAUNCH(false, st, "hf_mask");
+  return HG_OK;
+}
+
+}  // extern "C"

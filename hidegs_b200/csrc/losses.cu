@@ -1,0 +1,538 @@
+// losses.cu — image / patch losses of the HiDeGS training step as fused sm_100a kernels.
+//
+// Replaces the PyTorch op chains of utils/loss_utils.py (l1_loss :18-19, l2_loss :21-22, ssim :24-64,
+// get_img_grad_weight :66-78, lncc :80-115) and compute_scale_regularization
+// (scripts/frequency_regularization.py:1403-1444).  All of them are HBM-bound streaming passes: every
+// image is read once (plus a 5-pixel halo for SSIM), reductions are two-stage and deterministic
+// (per-block partials in fixed order, final sum in double), nothing synchronises with the host.
+#include "common.cuh"
+#include "../../include/hidegs_losses.h"
+
+#include <cmath>
+
+namespace hg {
+
+namespace {
+
+constexpr int kRedBlocks = 148 * 4;  // a multiple of the SM count
+constexpr int kRedThreads = 256;
+
+// Sum over the CTA (any block shape); `tid` is the linear thread index.  Valid in thread 0.
+__device__ __forceinline__ float block_sum(float v, float* smem, int tid, int nthreads) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  const int nw = (nthreads + 31) >> 5;
+  v = (tid < nw) ? smem[tid] : 0.f;
+  if (warp == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  __syncthreads();
+  return v;
+}
+
+// ---------------------------------------------------------------- l1 / l2
+template <bool L2>
+__global__ void __launch_bounds__(kRedThreads)
+pixel_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                  float* __restrict__ grad, double* __restrict__ partial) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const float inv_n = 1.0f / (float)n;
+  const int64_t n4 = n / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg((const float4*)a + i), y = __ldg((const float4*)b + i);
+    const float d[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
+    float4 g;
+    float* gp = &g.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (L2) {
+        acc += d[k] * d[k];
+        gp[k] = 2.0f * d[k] * inv_n;
+      } else {
+        acc += fabsf(d[k]);
+        gp[k] = (d[k] > 0.f ? 1.f : (d[k] < 0.f ? -1.f : 0.f)) * inv_n;
+      }
+    }
+    if (grad) ((float4*)grad)[i] = g;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = a[i] - b[i];
+    acc += L2 ? d * d : fabsf(d);
+    if (grad) grad[i] = L2 ? 2.0f * d * inv_n : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n;
+  }
+  const float s = block_sum(acc, red, threadIdx.x, kRedThreads);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
+}
+
+__global__ void finalize_mean_kernel(const double* __restrict__ partial, int n_partial, double denom,
+                                     float* __restrict__ out) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x) s += partial[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sm[0] / denom);
+}
+
+template <bool L2>
+int run_pixel_loss(const float* a, const float* b, int64_t n, float* out, float* grad, void* ws,
+                   cudaStream_t st) {
+  if (!a || !b || !out || !ws || n <= 0) {
+    set_error("pixel loss: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  const bool vec_ok = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)grad) & 15) == 0;
+  if (!vec_ok) {
+    set_error("pixel loss: pointers must be 16-byte aligned");
+    return HG_ERR_INVALID_ARG;
+  }
+  double* partial = (double*)ws;
+  pixel_loss_kernel<L2><<<kRedBlocks, kRedThreads, 0, st>>>(a, b, n, grad, partial);
+  HG_POST_LAUNCH(false, st, "pixel_loss");
+  finalize_mean_kernel<<<1, 256, 0, st>>>(partial, kRedBlocks, (double)n, out);
+  HG_POST_LAUNCH(false, st, "finalize_mean");
+  return HG_OK;
+}
+
+// ---------------------------------------------------------------- SSIM
+__constant__ float c_gauss[11];
+constexpr int kTile = 16, kHalo = 5, kIn = kTile + 2 * kHalo;  // 26
+
+__global__ void __launch_bounds__(kTile * kTile)
+ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W,
+                float* __restrict__ maps, size_t map_stride, double* __restrict__ partial) {
+  __shared__ float s1[kIn][kIn + 1], s2[kIn][kIn + 1];
+  __shared__ float h[5][kIn][kTile + 1];
+  __shared__ float red[32];
+  const int plane = blockIdx.z;
+  const size_t base = (size_t)plane * H * W;
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const int tid = threadIdx.y * kTile + threadIdx.x;
+  for (int i = tid; i < kIn * kIn; i += kTile * kTile) {
+    const int r = i / kIn, c = i % kIn;
+    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;  // zero padding (F.conv2d padding=5)
+    s1[r][c] = in ? __ldg(img1 + base + (size_t)y * W + x) : 0.f;
+    s2[r][c] = in ? __ldg(img2 + base + (size_t)y * W + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < kIn * kTile; i += kTile * kTile) {
+    const int r = i / kTile, c = i % kTile;
+    float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = c_gauss[k], x = s1[r][c + k], y = s2[r][c + k];
+      a += g * x; b += g * y; aa += g * x * x; bb += g * y * y; ab += g * x * y;
+    }
+    h[0][r][c] = a; h[1][r][c] = b; h[2][r][c] = aa; h[3][r][c] = bb; h[4][r][c] = ab;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const float g = c_gauss[k];
+    mu1 += g * h[0][ty + k][tx]; mu2 += g * h[1][ty + k][tx];
+    e11 += g * h[2][ty + k][tx]; e22 += g * h[3][ty + k][tx]; e12 += g * h[4][ty + k][tx];
+  }
+  const int x = x0 + tx, y = y0 + ty;
+  float val = 0.f;
+  if (x < W && y < H) {
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+    const float sg1 = e11 - mu1_sq, sg2 = e22 - mu2_sq, sg12 = e12 - mu12;
+    const float A = mu1_sq + mu2_sq + C1, B = sg1 + sg2 + C2, C = 2.f * mu12 + C1, D = 2.f * sg12 + C2;
+    val = (C * D) / (A * B);
+    if (maps) {
+      const size_t p = base + (size_t)y * W + x;
+      maps[p] = (mu2 * 2.f * D) / (A * B) - (mu2 * 2.f * C) / (A * B) - (mu1 * 2.f * C * D) / (A * A * B) +
+                (mu1 * 2.f * C * D) / (A * B * B);
+      maps[map_stride + p] = -(C * D) / (A * B * B);
+      maps[2 * map_stride + p] = (2.f * C) / (A * B);
+    }
+  }
+  const float s = block_sum(val, red, tid, kTile * kTile);
+  if (tid == 0) partial[((size_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (double)s;
+}
+
+__global__ void ssim_finalize_kernel(const double* __restrict__ partial, int per_item, double denom,
+                                     float* __restrict__ out) {
+  __shared__ double sm[256];
+  double s = 0.0;
+  const double* p = partial + (size_t)blockIdx.x * per_item;
+  for (int i = threadIdx.x; i < per_item; i += blockDim.x) s += p[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(sm[0] / denom);
+}
+
+__global__ void __launch_bounds__(kTile * kTile)
+ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                const float* __restrict__ maps, size_t map_stride, const float* __restrict__ gscale,
+                int C, int H, int W, float* __restrict__ grad) {
+  __shared__ float m[3][kIn][kIn + 1];
+  __shared__ float h[3][kIn][kTile + 1];
+  const int plane = blockIdx.z;
+  const size_t base = (size_t)plane * H * W;
+  const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+  const int tid = threadIdx.y * kTile + threadIdx.x;
+  for (int i = tid; i < kIn * kIn; i += kTile * kTile) {
+    const int r = i / kIn, c = i % kIn;
+    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    const size_t p = base + (size_t)y * W + x;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) m[q][r][c] = in ? __ldg(maps + q * map_stride + p) : 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < kIn * kTile; i += kTile * kTile) {
+    const int r = i / kTile, c = i % kTile;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const float g = c_gauss[k];
+      a0 += g * m[0][r][c + k]; a1 += g * m[1][r][c + k]; a2 += g * m[2][r][c + k];
+    }
+    h[0][r][c] = a0; h[1][r][c] = a1; h[2][r][c] = a2;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x, ty = threadIdx.y, x = x0 + tx, y = y0 + ty;
+  if (x >= W || y >= H) return;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 11; ++k) {
+    const float g = c_gauss[k];
+    c0 += g * h[0][ty + k][tx]; c1 += g * h[1][ty + k][tx]; c2 += g * h[2][ty + k][tx];
+  }
+  const size_t p = base + (size_t)y * W + x;
+  const float s = __ldg(gscale + plane / C) / ((float)C * (float)H * (float)W);
+  grad[p] = s * (c0 + 2.f * __ldg(img1 + p) * c1 + __ldg(img2 + p) * c2);
+}
+
+// ---------------------------------------------------------------- get_img_grad_weight
+__global__ void __launch_bounds__(256)
+grad_weight_raw_kernel(const float* __restrict__ img, int C, int H, int W, float* __restrict__ out,
+                       float* __restrict__ pmin, float* __restrict__ pmax) {
+  __shared__ float smin[8], smax[8];
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  float v = 0.f;
+  const bool interior = x >= 1 && x < W - 1 && y >= 1 && y < H - 1;
+  if (interior) {
+    float gx = 0.f, gy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float* p = img + ((size_t)c * H + y) * W + x;
+      gx += fabsf(__ldg(p + 1) - __ldg(p - 1));
+      gy += fabsf(__ldg(p - W) - __ldg(p + W));
+    }
+    v = fmaxf(gx / (float)C, gy / (float)C);
+    out[(size_t)y * W + x] = v;
+  }
+  float lo = interior ? v : __int_as_float(0x7f800000), hi = interior ? v : -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { lo = fminf(lo, smin[i]); hi = fmaxf(hi, smax[i]); }
+    pmin[blockIdx.y * gridDim.x + blockIdx.x] = lo;
+    pmax[blockIdx.y * gridDim.x + blockIdx.x] = hi;
+  }
+}
+
+__global__ void minmax_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax,
+                                       int n, float* __restrict__ mm) {
+  __shared__ float smin[256], smax[256];
+  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { lo = fminf(lo, pmin[i]); hi = fmaxf(hi, pmax[i]); }
+  smin[threadIdx.x] = lo; smax[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + o]);
+      smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { mm[0] = smin[0]; mm[1] = smax[0]; }
+}
+
+__global__ void __launch_bounds__(256)
+grad_weight_norm_kernel(int H, int W, const float* __restrict__ mm, float* __restrict__ out) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const bool interior = x >= 1 && x < W - 1 && y >= 1 && y < H - 1;
+  const size_t p = (size_t)y * W + x;
+  out[p] = interior ? (out[p] - mm[0]) / (mm[1] - mm[0]) : 1.0f;
+}
+
+// ---------------------------------------------------------------- lncc (one warp per patch row)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+lncc_kernel(const float* __restrict__ ref, const float* __restrict__ nea, int bs, int tps,
+            float* __restrict__ ncc, uint8_t* __restrict__ mask, const float* __restrict__ grad_ncc,
+            float* __restrict__ grad_ref, float* __restrict__ grad_nea) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= bs) return;
+  const float* r = ref + (size_t)row * tps;
+  const float* n = nea + (size_t)row * tps;
+  float sr = 0.f, sn = 0.f, srr = 0.f, snn = 0.f, srn = 0.f;
+  for (int i = lane; i < tps; i += 32) {
+    const float a = __ldg(r + i), b = __ldg(n + i);
+    sr += a; sn += b; srr += a * a; snn += b * b; srn += a * b;
+  }
+  sr = warp_sum(sr); sn = warp_sum(sn); srr = warp_sum(srr); snn = warp_sum(snn); srn = warp_sum(srn);
+  const float ra = sr / (float)tps, na = sn / (float)tps;
+  const float cross = srn - na * sr, rv = srr - ra * sr, nv = snn - na * sn;
+  const float den = rv * nv + 1e-8f;
+  const float cc = cross * cross / den;
+  const float raw = 1.f - cc;
+  const float v = fminf(fmaxf(raw, 0.f), 2.f);
+  if (!BWD) {
+    if (lane == 0) { ncc[row] = v; mask[row] = v < 0.9f ? 1 : 0; }
+    return;
+  }
+  // clamp passes the gradient where 0 <= raw <= 2 (torch.clamp); mean over a single column is the identity
+  const float g = (raw >= 0.f && raw <= 2.f) ? -__ldg(grad_ncc + row) : 0.f;
+  const float k1 = 2.f * cross / den, k2 = cross * cross / (den * den);
+  for (int i = lane; i < tps; i += 32) {
+    const float a = __ldg(r + i), b = __ldg(n + i);
+    grad_ref[(size_t)row * tps + i] = g * (k1 * (b - na) - k2 * nv * 2.f * (a - ra));
+    grad_nea[(size_t)row * tps + i] = g * (k1 * (a - ra) - k2 * rv * 2.f * (b - na));
+  }
+}
+
+// ---------------------------------------------------------------- scale regularisation
+struct ScaleRegCtl { double sum; double count; float coef; float pad; };
+
+__global__ void __launch_bounds__(kRedThreads)
+scale_reg_sum_kernel(const float* __restrict__ scaling, int64_t N, const int64_t* __restrict__ vis_idx,
+                     const uint8_t* __restrict__ vis_mask, int64_t n_items, double* __restrict__ psum,
+                     double* __restrict__ pcnt) {
+  __shared__ float red[32];
+  float acc = 0.f, cnt = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g;
+    if (vis_idx) {
+      g = vis_idx[i];
+      if (g < 0 || g >= N) continue;
+    } else {
+      if (!vis_mask[i]) continue;
+      g = i;
+    }
+    const float m = fmaxf(fmaxf(scaling[3 * g], scaling[3 * g + 1]), scaling[3 * g + 2]);
+    if (m > 0.01f) { acc += (m - 0.01f) * (m - 0.01f); cnt += 1.f; }
+  }
+  const float s = block_sum(acc, red, threadIdx.x, kRedThreads);
+  const float c = block_sum(cnt, red, threadIdx.x, kRedThreads);
+  if (threadIdx.x == 0) { psum[blockIdx.x] = (double)s; pcnt[blockIdx.x] = (double)c; }
+}
+
+__global__ void scale_reg_finalize_kernel(const double* __restrict__ psum, const double* __restrict__ pcnt,
+                                          int n, float* __restrict__ out, ScaleRegCtl* __restrict__ ctl) {
+  if (threadIdx.x != 0) return;
+  double s = 0.0, c = 0.0;
+  for (int i = 0; i < n; ++i) { s += psum[i]; c += pcnt[i]; }
+  float loss = 0.f, coef = 0.f;
+  if (c > 0.0) {
+    const float raw = (float)(s / c);
+    loss = fminf(fmaxf(raw, 0.f), 0.01f);
+    coef = (raw >= 0.f && raw <= 0.01f) ? (float)(2.0 / c) : 0.f;  // saturated clamp: zero gradient
+  }
+  out[0] = loss;
+  ctl->sum = s; ctl->count = c; ctl->coef = coef;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+scale_reg_grad_kernel(const float* __restrict__ scaling, int64_t N, const int64_t* __restrict__ vis_idx,
+                      const uint8_t* __restrict__ vis_mask, int64_t n_items,
+                      const ScaleRegCtl* __restrict__ ctl, float* __restrict__ grad) {
+  const float coef = ctl->coef;
+  if (coef == 0.f) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g;
+    if (vis_idx) {
+      g = vis_idx[i];
+      if (g < 0 || g >= N) continue;
+    } else {
+      if (!vis_mask[i]) continue;
+      g = i;
+    }
+    const float a = scaling[3 * g], b = scaling[3 * g + 1], c = scaling[3 * g + 2];
+    const float m = fmaxf(fmaxf(a, b), c);
+    if (m > 0.01f) {
+      const int arg = (a == m) ? 0 : ((b == m) ? 1 : 2);  // first maximum, as torch.max(dim)
+      atomicAdd(grad + 3 * g + arg, coef * (m - 0.01f));
+    }
+  }
+}
+
+bool g_gauss_ready = false;
+int ensure_gauss() {
+  if (g_gauss_ready) return HG_OK;
+  // gaussian(11, 1.5) of the reference (loss_utils.py:24-26): float32 values normalised by their float32 sum.
+  float g[11], sum = 0.f;
+  for (int x = 0; x < 11; ++x) {
+    g[x] = (float)std::exp(-(double)((x - 5) * (x - 5)) / (2.0 * 1.5 * 1.5));
+    sum += g[x];
+  }
+  for (int x = 0; x < 11; ++x) g[x] = g[x] / sum;
+  HG_CUDA_TRY(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
+  g_gauss_ready = true;
+  return HG_OK;
+}
+
+}  // namespace
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" {
+
+size_t hg_reduce_workspace_bytes(int64_t) { return sizeof(double) * 2 * kRedBlocks + 256; }
+
+int hg_l1_loss(const float* a, const float* b, int64_t n, float* out, float* grad_a, void* ws, void* st) {
+  return run_pixel_loss<false>(a, b, n, out, grad_a, ws, (cudaStream_t)st);
+}
+int hg_l2_loss(const float* a, const float* b, int64_t n, float* out, float* grad_a, void* ws, void* st) {
+  return run_pixel_loss<true>(a, b, n, out, grad_a, ws, (cudaStream_t)st);
+}
+
+size_t hg_ssim_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+  const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+  return sizeof(double) * tiles * (size_t)B * C + 256;
+}
+
+int hg_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t H, int32_t W, float* out,
+            float* maps, void* ws, void* st_) {
+  if (!img1 || !img2 || !out || !ws || B <= 0 || C <= 0 || H <= 0 || W <= 0 || (size_t)B * C > 65535) {
+    set_error("hg_ssim: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  int rc = ensure_gauss();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)st_;
+  const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
+  ssim_fwd_kernel<<<grid, dim3(kTile, kTile), 0, st>>>(img1, img2, H, W, maps, (size_t)B * C * H * W, (double*)ws);
+  HG_POST_LAUNCH(false, st, "ssim_fwd");
+  ssim_finalize_kernel<<<B, 256, 0, st>>>((const double*)ws, (int)(grid.x * grid.y * C), (double)C * H * W, out);
+  HG_POST_LAUNCH(false, st, "ssim_finalize");
+  return HG_OK;
+}
+
+int hg_ssim_backward(const float* img1, const float* img2, const float* maps, const float* gscale, int32_t B,
+                     int32_t C, int32_t H, int32_t W, float* grad_img1, void* st_) {
+  if (!img1 || !img2 || !maps || !gscale || !grad_img1 || B <= 0 || C <= 0 || H <= 0 || W <= 0) {
+    set_error("hg_ssim_backward: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  int rc = ensure_gauss();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)st_;
+  const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
+  ssim_bwd_kernel<<<grid, dim3(kTile, kTile), 0, st>>>(img1, img2, maps, (size_t)B * C * H * W, gscale, C, H, W,
+                                                      grad_img1);
+  HG_POST_LAUNCH(false, st, "ssim_bwd");
+  return HG_OK;
+}
+
+size_t hg_img_grad_weight_workspace_bytes(int32_t H, int32_t W) {
+  const size_t blocks = (size_t)((W + 31) / 32) * ((H + 7) / 8);
+  return sizeof(float) * (2 * blocks + 2) + 256;
+}
+
+int hg_img_grad_weight(const float* img, int32_t C, int32_t H, int32_t W, float* out, void* ws, void* st_) {
+  if (!img || !out || !ws || C <= 0 || H < 3 || W < 3) {
+    set_error("hg_img_grad_weight: bad argument (needs H, W >= 3)");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  const dim3 grid((W + 31) / 32, (H + 7) / 8);
+  const int blocks = grid.x * grid.y;
+  float* pmin = (float*)ws;
+  float* pmax = pmin + blocks;
+  float* mm = pmax + blocks;
+  grad_weight_raw_kernel<<<grid, 256, 0, st>>>(img, C, H, W, out, pmin, pmax);
+  HG_POST_LAUNCH(false, st, "grad_weight_raw");
+  minmax_finalize_kernel<<<1, 256, 0, st>>>(pmin, pmax, blocks, mm);
+  HG_POST_LAUNCH(false, st, "minmax_finalize");
+  grad_weight_norm_kernel<<<grid, 256, 0, st>>>(H, W, mm, out);
+  HG_POST_LAUNCH(false, st, "grad_weight_norm");
+  return HG_OK;
+}
+
+int hg_lncc(const float* ref, const float* nea, int32_t bs, int32_t tps, float* ncc, uint8_t* mask, void* st_) {
+  if (!ref || !nea || !ncc || !mask || bs < 0 || tps <= 0) {
+    set_error("hg_lncc: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (bs == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  lncc_kernel<false><<<(bs + 7) / 8, 256, 0, st>>>(ref, nea, bs, tps, ncc, mask, nullptr, nullptr, nullptr);
+  HG_POST_LAUNCH(false, st, "lncc");
+  return HG_OK;
+}
+
+int hg_lncc_backward(const float* ref, const float* nea, const float* grad_ncc, int32_t bs, int32_t tps,
+                     float* grad_ref, float* grad_nea, void* st_) {
+  if (!ref || !nea || !grad_ncc || !grad_ref || !grad_nea || bs < 0 || tps <= 0) {
+    set_error("hg_lncc_backward: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (bs == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  lncc_kernel<true><<<(bs + 7) / 8, 256, 0, st>>>(ref, nea, bs, tps, nullptr, nullptr, grad_ncc, grad_ref, grad_nea);
+  HG_POST_LAUNCH(false, st, "lncc_bwd");
+  return HG_OK;
+}
+
+size_t hg_scale_reg_workspace_bytes(int64_t) { return sizeof(double) * 2 * kRedBlocks + sizeof(ScaleRegCtl) + 256; }
+
+int hg_scale_reg(const float* scaling, int64_t N, const int64_t* vis_idx, const uint8_t* vis_mask, int64_t n_vis,
+                 float* out, float* grad_scaling, void* ws, void* st_) {
+  if (!scaling || !out || !ws || N < 0 || (!vis_idx && !vis_mask)) {
+    set_error("hg_scale_reg: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  const int64_t n_items = vis_idx ? n_vis : N;
+  double* psum = (double*)ws;
+  double* pcnt = psum + kRedBlocks;
+  ScaleRegCtl* ctl = (ScaleRegCtl*)(pcnt + kRedBlocks);
+  scale_reg_sum_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(scaling, N, vis_idx, vis_mask, n_items, psum, pcnt);
+  HG_POST_LAUNCH(false, st, "scale_reg_sum");
+  scale_reg_finalize_kernel<<<1, 32, 0, st>>>(psum, pcnt, kRedBlocks, out, ctl);
+  HG_POST_LAUNCH(false, st, "scale_reg_finalize");
+  if (grad_scaling) {
+    HG_CUDA_TRY(cudaMemsetAsync(grad_scaling, 0, sizeof(float) * 3 * (size_t)N, st));
+    scale_reg_grad_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(scaling, N, vis_idx, vis_mask, n_items, ctl, grad_scaling);
+    HG_POST_LAUNCH(false, st, "scale_reg_grad");
+  }
+  return HG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""Drop-in for `frequency_regularization_pyramid_scale` of the reference
+(scripts/frequency_regularization.py:1579-1676), same signature and return triple
+`(loss, high_freq_mask or None, debug_info)`.
+
+The multi-scale Sobel/Laplacian + FFT (log-magnitude, phase, band-energy) loss, its gradient w.r.t.
+the rendered image, the ground-truth high-frequency mask and the scale regulariser run as fused CUDA
+kernels (hidegs_b200/csrc/freq_loss.cu, losses.cu) without any host synchronisation.  The reference
+fills `debug_info` with six `.item()` calls per step; here `debug_info` is a dict that copies its
+numbers from the device the first time it is read, so a training loop that ignores it never syncs.
+"""
+import torch
+
+from . import _lib
+from ._losses_lib import FREQ_STATS, lib as _L
+from .loss_utils import _check_cuda, _stream, _ws
+
+
+class _FreqLoss(torch.autograd.Function):
+    """compute_true_frequency_loss(build_pyramid(rendered), build_pyramid(gt))  (:1293-1325)."""
+
+    @staticmethod
+    def forward(ctx, rendered, gt, levels):
+        _check_cuda(rendered, gt)
+        r, g = rendered.contiguous(), gt.contiguous()
+        _, H, W = r.shape
+        stats = torch.empty(FREQ_STATS, dtype=torch.float32, device=r.device)
+        need = ctx.needs_input_grad[0]
+        grad = torch.empty_like(r) if need else None
+        with torch.cuda.device(r.device):
+            ws = _ws(_L().hg_freq_loss_workspace_bytes(H, W, levels), r.device)
+            rc = _L().hg_freq_loss(r.data_ptr(), g.data_ptr(), H, W, levels, stats.data_ptr(),
+                                   grad.data_ptr() if need else None, ws.data_ptr(), _stream())
+        _lib.check(rc, "frequency loss")
+        ctx.grad = grad
+        ctx.mark_non_differentiable(stats)
+        return stats[0].clone(), stats
+
+    @staticmethod
+    def backward(ctx, g, _gs):
+        return (g * ctx.grad if ctx.needs_input_grad[0] else None), None, None
+
+
+class _ScaleReg(torch.autograd.Function):
+    """compute_scale_regularization (:1403-1444)."""
+
+    @staticmethod
+    def forward(ctx, scaling, visibility_filter):
+        _check_cuda(scaling)
+        s = scaling.contiguous()
+        N = s.size(0)
+        out = torch.empty(1, dtype=torch.float32, device=s.device)
+        need = ctx.needs_input_grad[0]
+        grad = torch.empty_like(s) if need else None
+        idx = mask = None
+        if visibility_filter.dtype == torch.bool:
+            mask = visibility_filter.to(s.device).contiguous().view(torch.uint8)
+            n_vis = -1
+        else:
+            idx = visibility_filter.to(device=s.device, dtype=torch.int64).contiguous()
+            n_vis = idx.numel()
+        with torch.cuda.device(s.device):
+            ws = _ws(_L().hg_scale_reg_workspace_bytes(N), s.device)
+            rc = _L().hg_scale_reg(s.data_ptr(), N, idx.data_ptr() if idx is not None and n_vis else None,
+                                   mask.data_ptr() if mask is not None else None, n_vis, out.data_ptr(),
+                                   grad.data_ptr() if need else None, ws.data_ptr(), _stream())
+        _lib.check(rc, "scale regularization")
+        ctx.grad = grad
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g * ctx.grad if ctx.needs_input_grad[0] else None), None
+
+
+def detect_true_high_frequency_regions(gt_image, high_freq_thresh=0.2):
+    """detect_true_high_frequency_regions (:1166-1271): (mask [H,W] float 0/1, count tensor [1])."""
+    _check_cuda(gt_image)
+    g = gt_image.detach()
+    if g.dim() == 4:
+        g = g[0]
+    g = g.contiguous()
+    _, H, W = g.shape
+    mask = torch.empty((H, W), dtype=torch.float32, device=g.device)
+    count = torch.empty(1, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        ws = _ws(_L().hg_hf_mask_workspace_bytes(H, W), g.device)
+        rc = _L().hg_hf_mask(g.data_ptr(), H, W, float(high_freq_thresh), mask.data_ptr(), count.data_ptr(),
+                             ws.data_ptr(), _stream())
+    _lib.check(rc, "high frequency mask")
+    return mask, count
+
+
+class LazyDebugInfo(dict):
+    """`debug_info` of the reference, filled from device scalars on first read (one D2H copy)."""
+
+    def __init__(self, fill):
+        super().__init__()
+        self._fill = fill
+
+    def _materialize(self):
+        if self._fill is not None:
+            fill, self._fill = self._fill, None
+            super().update(fill())
+
+    def __getitem__(self, k):
+        self._materialize()
+        return super().__getitem__(k)
+
+    def get(self, k, d=None):
+        self._materialize()
+        return super().get(k, d)
+
+    def __contains__(self, k):
+        self._materialize()
+        return super().__contains__(k)
+
+    def __iter__(self):
+        self._materialize()
+        return super().__iter__()
+
+    def __len__(self):
+        self._materialize()
+        return super().__len__()
+
+    def keys(self):
+        self._materialize()
+        return super().keys()
+
+    def items(self):
+        self._materialize()
+        return super().items()
+
+    def values(self):
+        self._materialize()
+        return super().values()
+
+    def __repr__(self):
+        self._materialize()
+        return super().__repr__()
+
+
+def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, scene, viewpoint_cam,
+                                           visibility_filter, iteration, lambda_freq=0.001, lambda_scale=0.005,
+                                           num_levels=3, high_freq_thresh=0.2, save_results=False, save_dir=None,
+                                           warmup_iterations=1000, debug=False):
+    if iteration < warmup_iterations:
+        return torch.tensor(0.0, device=rendered_image.device), None, {'warmup': True}
+    if not 1 <= num_levels <= 3:
+        raise NotImplementedError("hidegs_b200 frequency regularisation supports 1..3 pyramid levels")
+    device = rendered_image.device
+    r = rendered_image[0] if rendered_image.dim() == 4 else rendered_image
+    g = gt_image[0] if gt_image.dim() == 4 else gt_image
+    total = torch.zeros((), dtype=torch.float32, device=device)
+    stats = None
+    if lambda_freq > 0:
+        freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels))
+        total = total + lambda_freq * freq_loss
+    mask, count = detect_true_high_frequency_regions(g, high_freq_thresh)
+    scale_loss = None
+    if lambda_scale > 0:
+        if hasattr(gaussians, 'get_scaling'):
+            scaling = gaussians.get_scaling
+        elif hasattr(gaussians, '_scaling'):
+            scaling = gaussians._scaling
+        else:
+            scaling = None
+        if scaling is not None:
+            scale_loss = _ScaleReg.apply(scaling, visibility_filter)
+            # the reference applies the term only if the mask is non-empty (:1644); same, without a host sync
+            total = total + lambda_scale * scale_loss * (count[0] > 0).float()
+    total = torch.clamp(total, 0, 1.0)
+
+    def fill():
+        info = {'pyramid_levels': int(num_levels)}
+        vals = [total.detach().reshape(1), count]
+        if stats is not None:
+            vals.append(stats)
+        if scale_loss is not None:
+            vals.append(scale_loss.detach().reshape(1))
+        host = torch.cat(vals).cpu().tolist()
+        n_mask = host[1]
+        if stats is not None:
+            st = host[2:2 + FREQ_STATS]
+            info['freq_loss'] = st[0]
+            info['levels'] = [dict(zip(('spatial', 'fft', 'level', 'mag', 'phase', 'band'), st[1 + 6 * l:7 + 6 * l]))
+                              for l in range(int(num_levels))]
+            info['fft_valid'] = True
+            info['freq_band_energies'] = st[19:23]
+        info['high_freq_pixels'] = n_mask
+        info['high_freq_ratio'] = n_mask / float(mask.numel())
+        if scale_loss is not None and n_mask > 0:
+            info['scale_loss'] = host[-1]
+        info['total_loss'] = host[0]
+        return info
+
+    debug_info = LazyDebugInfo(fill)
+    if debug:
+        print("frequency regularisation loss: %.6f" % debug_info['total_loss'])
+    return total, mask, debug_info

@@ -1,0 +1,170 @@
+"""Drop-in for the reference's utils/loss_utils.py (same function names and signatures), backed by
+fused sm_100a kernels through the C-ABI of include/hidegs_losses.h.
+
+  l1_loss(network_output, gt)                      utils/loss_utils.py:18-19
+  l2_loss(network_output, gt)                      utils/loss_utils.py:21-22
+  ssim(img1, img2, window_size=11, size_average=True)   :34-64
+  get_img_grad_weight(img, beta=2.0)               :66-78
+  lncc(ref, nea)                                   :80-115
+
+CUDA tensors only (no CPU fallback).  Each loss computes its value and the gradient w.r.t. the
+rendered image in one pass; autograd's backward only scales that gradient.
+"""
+import torch
+
+from . import _lib
+from ._losses_lib import lib as _L
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("hidegs_b200 losses need CUDA tensors (there is no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError("hidegs_b200 losses expect float32 tensors, got %s" % t.dtype)
+
+
+def _ws(nbytes, device):
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _PixelLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, l2):
+        _check_cuda(a, b)
+        if a.shape != b.shape:
+            raise RuntimeError("l1/l2 loss: shapes differ %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+        a_c, b_c = a.contiguous(), b.contiguous()
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
+        grad = torch.empty_like(a_c) if need else None
+        with torch.cuda.device(a.device):
+            ws = _ws(_L().hg_reduce_workspace_bytes(a_c.numel()), a.device)
+            fn = _L().hg_l2_loss if l2 else _L().hg_l1_loss
+            rc = fn(a_c.data_ptr(), b_c.data_ptr(), a_c.numel(), out.data_ptr(), grad.data_ptr() if need else None,
+                    ws.data_ptr(), _stream())
+        _lib.check(rc, "l2_loss" if l2 else "l1_loss")
+        ctx.grad = grad
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        ga = g * ctx.grad if ctx.needs_input_grad[0] else None
+        gb = -(g * ctx.grad) if ctx.needs_input_grad[1] else None
+        return ga, gb, None
+
+
+def l1_loss(network_output, gt):
+    return _PixelLoss.apply(network_output, gt, False)
+
+
+def l2_loss(network_output, gt):
+    return _PixelLoss.apply(network_output, gt, True)
+
+
+class _SSIM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img1, img2, size_average):
+        _check_cuda(img1, img2)
+        if img1.shape != img2.shape or img1.dim() not in (3, 4):
+            raise RuntimeError("ssim: expected two (C,H,W) or (B,C,H,W) tensors of the same shape")
+        x, y = img1.contiguous(), img2.contiguous()
+        B = x.size(0) if x.dim() == 4 else 1
+        C, H, W = x.shape[-3:]
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        out = torch.empty(B, dtype=torch.float32, device=x.device)
+        maps = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=x.device) if need1 else None
+        with torch.cuda.device(x.device):
+            ws = _ws(_L().hg_ssim_workspace_bytes(B, C, H, W), x.device)
+            rc = _L().hg_ssim(x.data_ptr(), y.data_ptr(), B, C, H, W, out.data_ptr(), maps.data_ptr() if need1 else None,
+                              ws.data_ptr(), _stream())
+        _lib.check(rc, "ssim")
+        ctx.save_for_backward(x, y)
+        ctx.maps, ctx.dims, ctx.size_average, ctx.need2 = maps, (B, C, H, W), size_average, need2
+        if size_average:
+            return out.mean() if B > 1 else out.reshape(())
+        if x.dim() != 4:
+            raise RuntimeError("ssim(size_average=False) needs a batched (B,C,H,W) input, as in the reference")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        B, C, H, W = ctx.dims
+        gs = (g.reshape(1).expand(B) / B if ctx.size_average else g).contiguous().float()
+        g1 = g2 = None
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                g1 = torch.empty_like(x)
+                rc = _L().hg_ssim_backward(x.data_ptr(), y.data_ptr(), ctx.maps.data_ptr(), gs.data_ptr(), B, C, H, W,
+                                           g1.data_ptr(), _stream())
+                _lib.check(rc, "ssim_backward")
+            if ctx.need2:  # SSIM is symmetric in its arguments: swap roles for d/d img2
+                out = torch.empty(B, dtype=torch.float32, device=x.device)
+                maps = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=x.device)
+                ws = _ws(_L().hg_ssim_workspace_bytes(B, C, H, W), x.device)
+                rc = _L().hg_ssim(y.data_ptr(), x.data_ptr(), B, C, H, W, out.data_ptr(), maps.data_ptr(), ws.data_ptr(), _stream())
+                _lib.check(rc, "ssim")
+                g2 = torch.empty_like(x)
+                rc = _L().hg_ssim_backward(y.data_ptr(), x.data_ptr(), maps.data_ptr(), gs.data_ptr(), B, C, H, W,
+                                           g2.data_ptr(), _stream())
+                _lib.check(rc, "ssim_backward")
+        return g1, g2, None
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    if window_size != 11:
+        raise NotImplementedError("hidegs_b200.ssim implements the reference's default 11x11 window only")
+    return _SSIM.apply(img1, img2, size_average)
+
+
+def get_img_grad_weight(img, beta=2.0):
+    """Edge-aware weight map of an image (used on ground-truth images; returned without autograd history)."""
+    _check_cuda(img)
+    if img.dim() != 3:
+        raise RuntimeError("get_img_grad_weight expects a (C,H,W) image")
+    x = img.detach().contiguous()
+    C, H, W = x.shape
+    out = torch.empty((H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _ws(_L().hg_img_grad_weight_workspace_bytes(H, W), x.device)
+        rc = _L().hg_img_grad_weight(x.data_ptr(), C, H, W, out.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "get_img_grad_weight")
+    return out
+
+
+class _LNCC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, nea):
+        _check_cuda(ref, nea)
+        if ref.shape != nea.shape or ref.dim() != 2:
+            raise RuntimeError("lncc expects two (batch, patch*patch) tensors of the same shape")
+        r, n = ref.contiguous(), nea.contiguous()
+        bs, tps = n.shape
+        ncc = torch.empty((bs, 1), dtype=torch.float32, device=r.device)
+        mask = torch.empty((bs, 1), dtype=torch.bool, device=r.device)
+        with torch.cuda.device(r.device):
+            rc = _L().hg_lncc(r.data_ptr(), n.data_ptr(), bs, tps, ncc.data_ptr(), mask.data_ptr(), _stream())
+        _lib.check(rc, "lncc")
+        ctx.save_for_backward(r, n)
+        ctx.mark_non_differentiable(mask)
+        return ncc, mask
+
+    @staticmethod
+    def backward(ctx, g_ncc, _g_mask):
+        r, n = ctx.saved_tensors
+        bs, tps = n.shape
+        gr, gn = torch.empty_like(r), torch.empty_like(n)
+        g = g_ncc.contiguous().float()
+        with torch.cuda.device(r.device):
+            rc = _L().hg_lncc_backward(r.data_ptr(), n.data_ptr(), g.data_ptr(), bs, tps, gr.data_ptr(), gn.data_ptr(), _stream())
+        _lib.check(rc, "lncc_backward")
+        return gr, gn
+
+
+def lncc(ref, nea):
+    return _LNCC.apply(ref, nea)

@@ -1,0 +1,97 @@
+/*
+ * hidegs_losses.h — C-ABI of the B200-native HiDeGS training losses.
+ *
+ * Every entry point takes device pointers (fp32, contiguous, CHW images), sizes, scalars, a
+ * caller-provided workspace and a cudaStream_t (as void*); results stay on the device (no host
+ * synchronisation inside); status codes as in hidegs_raster.h.
+ *
+ * Reference functions replaced (paths relative to the reference tree):
+ *   hg_l1_loss, hg_l2_loss      utils/loss_utils.py:18-22  l1_loss / l2_loss
+ *   hg_ssim, hg_ssim_backward   utils/loss_utils.py:24-64  ssim / _ssim / create_window / gaussian
+ *   hg_img_grad_weight          utils/loss_utils.py:66-78  get_img_grad_weight
+ *   hg_lncc, hg_lncc_backward   utils/loss_utils.py:80-115 lncc
+ *   hg_scale_reg                scripts/frequency_regularization.py:1403-1444 compute_scale_regularization
+ *   hg_fft2_r2c, hg_fft2_c2r    torch.fft.fft2 / ifft2 as used at scripts/frequency_regularization.py:1110,1221,1227
+ *   hg_freq_loss                scripts/frequency_regularization.py:1073-1082 build_pyramid, :1327-1360
+ *                               _compute_spatial_frequency_loss, :1084-1164 compute_fft_features, :1362-1401
+ *                               _compute_fft_frequency_loss, :1293-1325 compute_true_frequency_loss
+ *   hg_hf_mask                  scripts/frequency_regularization.py:1166-1271 detect_true_high_frequency_regions
+ *
+ * Value-and-gradient convention: the losses that feed a training step return their value AND the
+ * gradient w.r.t. the rendered image for a unit upstream gradient in the same call (the autograd
+ * wrapper scales it by the incoming scalar), so the image is read once.
+ */
+#ifndef HIDEGS_LOSSES_H
+#define HIDEGS_LOSSES_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "hidegs_raster.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mean |a-b| (l1) or mean (a-b)^2 (l2) over n elements -> out[0]; grad_a (nullable): d out / d a. */
+HG_API size_t hg_reduce_workspace_bytes(int64_t n);
+HG_API int hg_l1_loss(const float *a, const float *b, int64_t n, float *out, float *grad_a,
+                      void *workspace, void *stream);
+HG_API int hg_l2_loss(const float *a, const float *b, int64_t n, float *out, float *grad_a,
+                      void *workspace, void *stream);
+
+/* SSIM with the reference's 11x11 sigma=1.5 window, zero padding 5, C1=1e-4, C2=9e-4.
+ * img1/img2: [B,C,H,W].  out[b] = mean over (C,H,W) of the SSIM map of batch item b (the Python
+ * wrapper averages over b for size_average=True).  If `maps` != NULL (3*B*C*H*W floats) the three
+ * partial-derivative maps needed by hg_ssim_backward are stored. */
+HG_API size_t hg_ssim_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+HG_API int hg_ssim(const float *img1, const float *img2, int32_t B, int32_t C, int32_t H, int32_t W,
+                   float *out, float *maps, void *workspace, void *stream);
+/* grad_img1 = d (sum_b gscale[b] * out[b]) / d img1, gscale: device [B]. */
+HG_API int hg_ssim_backward(const float *img1, const float *img2, const float *maps, const float *gscale,
+                            int32_t B, int32_t C, int32_t H, int32_t W, float *grad_img1, void *stream);
+
+/* get_img_grad_weight: img [C,H,W] -> out [H,W] (border = 1.0). */
+HG_API size_t hg_img_grad_weight_workspace_bytes(int32_t H, int32_t W);
+HG_API int hg_img_grad_weight(const float *img, int32_t C, int32_t H, int32_t W, float *out,
+                              void *workspace, void *stream);
+
+/* lncc: ref/nea [bs,tps] -> ncc [bs], mask [bs] (u8: ncc < 0.9). */
+HG_API int hg_lncc(const float *ref, const float *nea, int32_t bs, int32_t tps, float *ncc,
+                   uint8_t *mask, void *stream);
+HG_API int hg_lncc_backward(const float *ref, const float *nea, const float *grad_ncc, int32_t bs,
+                            int32_t tps, float *grad_ref, float *grad_nea, void *stream);
+
+/* compute_scale_regularization on index list `vis` (int64 [n_vis]; out-of-range entries ignored, as
+ * in the reference) or a bool mask (u8 [N], n_vis < 0).  out[0] = loss; grad_scaling [N,3] (nullable)
+ * is fully written (zeros where no gradient flows). */
+HG_API size_t hg_scale_reg_workspace_bytes(int64_t n);
+HG_API int hg_scale_reg(const float *scaling, int64_t N, const int64_t *vis_idx, const uint8_t *vis_mask,
+                        int64_t n_vis, float *out, float *grad_scaling, void *workspace, void *stream);
+
+/* 2-D FFT of a real H x W image -> half spectrum [H, W/2+1] interleaved complex (unnormalised, as
+ * torch.fft.fft2), and the inverse (normalised by 1/(H*W), as torch.fft.ifft2 of a Hermitian
+ * spectrum; real output).  H and W must factor into 2, 3 and 5 and be <= 4096. */
+HG_API size_t hg_fft2_workspace_bytes(int32_t H, int32_t W);
+HG_API int hg_fft2_r2c(const float *img, int32_t H, int32_t W, float *spec, void *workspace, void *stream);
+HG_API int hg_fft2_c2r(const float *spec, int32_t H, int32_t W, float *img, int scale_by_inverse_size,
+                       void *workspace, void *stream);
+
+/* Frequency regulariser core: rendered/gt [3,H,W].  Writes
+ *   stats[0]  freq_loss (clamp(sum_l w_l level_l, 0, 0.1))
+ *   stats[1 + 6*l + {0..5}]  level l: spatial, fft, level (clamped), mag, phase, band   (l < levels <= 3)
+ *   stats[19..22]  band energies of the level-0 ground-truth spectrum
+ * and, if grad_rendered != NULL, d freq_loss / d rendered [3,H,W]. */
+#define HG_FREQ_STATS 24
+HG_API size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels);
+HG_API int hg_freq_loss(const float *rendered, const float *gt, int32_t H, int32_t W, int32_t levels,
+                        float *stats, float *grad_rendered, void *workspace, void *stream);
+
+/* detect_true_high_frequency_regions on gt [3,H,W] -> mask [H,W] float (0/1); count[0] = sum(mask). */
+HG_API size_t hg_hf_mask_workspace_bytes(int32_t H, int32_t W);
+HG_API int hg_hf_mask(const float *gt, int32_t H, int32_t W, float thresh, float *mask, float *count,
+                      void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIDEGS_LOSSES_H */

@@ -1,0 +1,181 @@
+"""GPU parity tests of the loss path (run on the B200 box): CUDA kernels vs the CPU oracle
+(oracle/loss_oracle.py, itself pinned to the reference by tests/test_loss_oracle.py) and vs golden vectors
+produced by the reference's own code.  Tolerances (BASELINE.json): losses and gradients 1e-3 relative."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import loss_utils_t as lt
+from hidegs_b200 import _lib, frequency_regularization as hfr, loss_utils as hlu
+from hidegs_b200._losses_lib import lib as L
+from oracle import loss_oracle as lo
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "loss_ref_*.npz")))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def grad_ok(a, b, tol=1e-3):
+    """max |a-b| <= tol * max|b|  and  relative L2 <= tol."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return rel(a, b) <= tol and np.linalg.norm(a - b) <= tol * max(np.linalg.norm(b), 1e-30)
+
+
+# ------------------------------------------------------------------ FFT building block
+@pytest.mark.parametrize("H,W", [(1080, 1920), (540, 960), (270, 480), (54, 96), (45, 75), (27, 48), (16, 16), (60, 100), (4, 6), (125, 243)])
+def test_fft2_matches_torch(cuda_device, H, W):
+    dev = cuda_device
+    x = torch.rand(H, W, generator=torch.Generator().manual_seed(H * 7 + W))
+    ref = torch.fft.rfft2(x.double())
+    xd = x.to(dev)
+    spec = torch.empty((H, W // 2 + 1, 2), dtype=torch.float32, device=dev)
+    ws = torch.empty(L().hg_fft2_workspace_bytes(H, W), dtype=torch.uint8, device=dev)
+    _lib.check(L().hg_fft2_r2c(xd.data_ptr(), H, W, spec.data_ptr(), ws.data_ptr(), None), "fft2")
+    got = torch.view_as_complex(spec.cpu().double())
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 2e-6 * scale + 1e-3 * np.sqrt(H * W) * 1e-3
+    # energy of the error relative to the signal (fp32 FFT accuracy)
+    assert float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt()) < 1e-6
+    back = torch.empty((H, W), dtype=torch.float32, device=dev)
+    _lib.check(L().hg_fft2_c2r(spec.data_ptr(), H, W, back.data_ptr(), 1, ws.data_ptr(), None), "ifft2")
+    assert float((back.cpu() - x).abs().max()) < 5e-6
+
+
+def test_fft2_rejects_unsupported_sizes(cuda_device):
+    dev = cuda_device
+    x = torch.zeros(14, 22, device=dev)  # 7 and 11 are not supported radices
+    spec = torch.empty((14, 12, 2), device=dev)
+    assert L().hg_fft2_r2c(x.data_ptr(), 14, 22, spec.data_ptr(), None, None) == 1
+    assert b"unsupported" in _lib.lib().hg_last_error()
+
+
+# ------------------------------------------------------------------ utils/loss_utils.py
+@pytest.mark.parametrize("path", GOLDEN)
+def test_loss_utils_vs_reference_golden(cuda_device, path):
+    dev = cuda_device
+    gold = np.load(path)
+    p = json.loads(bytes(gold["params"]).decode())
+    inp = lt.make_loss_inputs(**p)
+    gt = inp["gt"].to(dev)
+    for name, fn in (("l1", hlu.l1_loss), ("l2", hlu.l2_loss), ("ssim", hlu.ssim)):
+        r = inp["render"].to(dev).requires_grad_(True)
+        v = fn(r, gt)
+        v.backward()
+        assert abs(v.item() - float(gold[name])) <= 1e-3 * abs(float(gold[name])) + 1e-9, name
+        assert grad_ok(r.grad.cpu().numpy(), gold[name + "_grad"]), name
+    sb = hlu.ssim(torch.stack([inp["render"], inp["gt"]]).to(dev), torch.stack([inp["gt"], inp["gt"]]).to(dev), size_average=False)
+    assert rel(sb.cpu().numpy(), gold["ssim_batched"]) < 1e-4
+    assert float(np.abs(hlu.get_img_grad_weight(gt).cpu().numpy() - gold["grad_weight"]).max()) < 1e-5
+    a = inp["patch_ref"].to(dev).requires_grad_(True)
+    b = inp["patch_nea"].to(dev).requires_grad_(True)
+    ncc, mask = hlu.lncc(a, b)
+    (ncc * inp["patch_w"].to(dev)).sum().backward()
+    assert float(np.abs(ncc.detach().cpu().numpy() - gold["lncc"]).max()) < 1e-5
+    assert np.array_equal(mask.cpu().numpy(), gold["lncc_mask"]) and mask.dtype == torch.bool and ncc.shape == (a.shape[0], 1)
+    assert grad_ok(a.grad.cpu().numpy(), gold["lncc_grad_ref"]) and grad_ok(b.grad.cpu().numpy(), gold["lncc_grad_nea"])
+
+
+def test_ssim_gradient_wrt_second_image_and_batch(cuda_device):
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    x, y = torch.rand(2, 3, 37, 53, generator=g), torch.rand(2, 3, 37, 53, generator=g)
+    xo, yo = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    lo.ssim(xo, yo).backward()
+    xd, yd = x.to(dev).requires_grad_(True), y.to(dev).requires_grad_(True)
+    v = hlu.ssim(xd, yd)
+    v.backward()
+    assert abs(v.item() - lo.ssim(x, y).item()) < 1e-5
+    assert grad_ok(xd.grad.cpu().numpy(), xo.grad.numpy()) and grad_ok(yd.grad.cpu().numpy(), yo.grad.numpy())
+    with pytest.raises(NotImplementedError):
+        hlu.ssim(xd, yd, window_size=7)
+
+
+def test_losses_reject_cpu_tensors():
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hlu.l1_loss(torch.zeros(3, 8, 8), torch.zeros(3, 8, 8))
+
+
+# ------------------------------------------------------------------ frequency regulariser
+def run_freq(inp, dev, **kw):
+    r = inp["render"].to(dev).requires_grad_(True)
+    s = inp["scaling"].to(dev).requires_grad_(True)
+    total, mask, info = hfr.frequency_regularization_pyramid_scale(r, inp["gt"].to(dev), lt.GaussiansShim(s), None, None,
+                                                                   inp["visibility"].to(dev), 2000, **kw)
+    total.backward()
+    return total, mask, info, r.grad, s.grad
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_frequency_regularization_vs_reference_golden(cuda_device, path):
+    dev = cuda_device
+    gold = np.load(path)
+    p = json.loads(bytes(gold["params"]).decode())
+    inp = lt.make_loss_inputs(**p)
+    total, mask, info, gr, gs = run_freq(inp, dev)
+    assert abs(total.item() - float(gold["freq_total"])) <= 1e-3 * float(gold["freq_total"])
+    assert abs(info["freq_loss"] - float(gold["info_freq_loss"])) <= 1e-3 * float(gold["info_freq_loss"])
+    assert abs(info["scale_loss"] - float(gold["info_scale_loss"])) <= 1e-4 * float(gold["info_scale_loss"])
+    for lvl in range(3):
+        assert abs(info["levels"][lvl]["spatial"] - float(gold["lvl%d_spatial" % lvl])) <= 1e-3 * float(gold["lvl%d_spatial" % lvl])
+        assert abs(info["levels"][lvl]["fft"] - float(gold["lvl%d_fft" % lvl])) <= 1e-3 * float(gold["lvl%d_fft" % lvl])
+    assert rel(info["freq_band_energies"], gold["info_band_energies"]) < 1e-4
+    diff = int((mask.cpu().numpy().astype(np.uint8) != gold["freq_mask"]).sum())
+    assert diff <= 2 and abs(info["high_freq_pixels"] - float(gold["info_high_freq_pixels"])) <= 2  # threshold ties
+    assert grad_ok(gr.cpu().numpy(), gold["freq_grad_render"]) and grad_ok(gs.cpu().numpy(), gold["freq_grad_scaling"])
+    assert info["pyramid_levels"] == 3 and info["fft_valid"] is True and "total_loss" in info
+
+
+@pytest.mark.parametrize("noise", [0.05, 0.002])
+def test_frequency_regularization_full_size_vs_oracle(cuda_device, noise):
+    """Config 1 (3x1080x1920): far variant saturates the level-0/1 clamps, near variant does not."""
+    dev = cuda_device
+    torch.manual_seed(0)
+    gt = F.avg_pool2d(torch.rand(3, 1080, 1920)[None], 5, stride=1, padding=2)[0].clamp(0, 1)
+    render = (gt + noise * torch.randn(3, 1080, 1920)).clamp(0, 1)
+    inp = dict(gt=gt, render=render, scaling=torch.rand(100000, 3) * 0.05, visibility=torch.arange(0, 100000, 2))
+    ro = render.clone().requires_grad_(True)
+    so = inp["scaling"].clone().requires_grad_(True)
+    t_o, m_o, i_o = lo.frequency_regularization_pyramid_scale(ro, gt, lt.GaussiansShim(so), None, None, inp["visibility"], 2000)
+    t_o.backward()
+    total, mask, info, gr, gs = run_freq(inp, dev)
+    assert abs(total.item() - t_o.item()) <= 1e-3 * t_o.item()
+    assert abs(info["freq_loss"] - i_o["freq_loss"]) <= 1e-3 * i_o["freq_loss"]
+    for lvl in range(3):
+        for k in ("spatial", "fft", "mag", "phase", "band"):
+            assert abs(info["levels"][lvl][k] - i_o["levels"][lvl][k]) <= 1e-3 * abs(i_o["levels"][lvl][k]) + 1e-9, (lvl, k)
+    assert rel(info["freq_band_energies"], i_o["freq_band_energies"]) < 1e-4
+    assert int((mask.cpu() != m_o).sum()) <= 8 and abs(info["high_freq_pixels"] - i_o["high_freq_pixels"]) <= 8
+    assert grad_ok(gr.cpu().numpy(), ro.grad.numpy()) and grad_ok(gs.cpu().numpy(), so.grad.numpy())
+    if noise == 0.05:  # known answers of BASELINE.md
+        assert abs(total.item() - 2.0789e-05) <= 1e-3 * 2.0789e-05 and abs(info["high_freq_pixels"] - 32364) <= 8
+    assert abs(hlu.l1_loss(render.to(dev), gt.to(dev)).item() - lo.l1_loss(render, gt).item()) < 1e-6
+    assert abs(hlu.ssim(render.to(dev), gt.to(dev)).item() - lo.ssim(render, gt).item()) < 1e-5
+
+
+def test_warmup_bool_filter_and_lazy_debug_info(cuda_device):
+    dev = cuda_device
+    inp = lt.make_loss_inputs(**lt.LOSS_CASES["near_small"])
+    z, m, info = hfr.frequency_regularization_pyramid_scale(inp["render"].to(dev), inp["gt"].to(dev), None, None, None,
+                                                            inp["visibility"].to(dev), iteration=10)
+    assert float(z) == 0.0 and m is None and info == {"warmup": True}
+    # boolean visibility filter == index list
+    vis_b = torch.zeros(inp["scaling"].shape[0], dtype=torch.bool)
+    vis_b[inp["visibility"]] = True
+    t1 = run_freq(inp, dev)
+    t2 = run_freq(dict(inp, visibility=vis_b), dev)
+    assert abs(t1[0].item() - t2[0].item()) < 1e-9 and torch.equal(t1[4], t2[4])
+    # out-of-range indices are ignored, empty filter gives a zero scale term
+    bad = torch.cat([inp["visibility"], torch.tensor([-5, 10 ** 7])])
+    assert abs(run_freq(dict(inp, visibility=bad), dev)[0].item() - t1[0].item()) < 1e-9
+    t3 = run_freq(dict(inp, visibility=torch.zeros(0, dtype=torch.int64)), dev)
+    assert float(t3[4].abs().max()) == 0.0 and t3[0].item() < t1[0].item()
+    assert t1[2]._fill is not None or len(t1[2]) > 0  # lazy until read
