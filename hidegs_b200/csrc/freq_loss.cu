@@ -9,8 +9,9 @@
 // (torch.clamp passes gradient only inside [min, max]; torch.min(a, b) splits it on ties; angle/abs
 // have zero gradient at 0).
 //
-// FFT (sizes factor as 2^a 3^b 5^c, e.g. 1080 x 1920): Stockham autosort in shared memory, radix
-// 4/2/3/5 butterflies, twiddles from sincospif (no tables).  Rows: one CTA per image row, real input
+// FFT: Stockham autosort in shared memory, radix 4/2/3/5 butterflies (1080 x 1920 and its pyramid
+// factor as 2^a 3^b 5^c) plus a generic O(R^2) butterfly for other prime factors, twiddles from
+// sincospif (no tables).  Rows: one CTA per image row, real input
 // -> W/2+1 complex outputs.  Columns: one CTA per group of adjacent columns, whole column resident in
 // shared memory (<= 96 KB).  The spectrum of a level (<= 8.3 MB) stays in L2 between the two passes.
 // The inverse used by the backward is the conjugate of the forward (conj -> FFT -> conj) followed by
@@ -44,6 +45,12 @@ bool make_plan(int n, Plan* p) {
   while (m % 2 == 0) { p->radix[p->nr++] = 2; m /= 2; }
   while (m % 3 == 0) { p->radix[p->nr++] = 3; m /= 3; }
   while (m % 5 == 0) { p->radix[p->nr++] = 5; m /= 5; }
+  // any other prime factor runs through the generic O(R^2) butterfly (a prime length is one pass of
+  // radix n, i.e. the plain DFT): every size works, sizes of the form 2^a 3^b 5^c are the fast path
+  for (int f = 7; m > 1 && p->nr < kMaxRadices; f += 2) {
+    while (m % f == 0 && p->nr < kMaxRadices) { p->radix[p->nr++] = f; m /= f; }
+    if (f * f > m && m > 1) { p->radix[p->nr++] = m; m = 1; }
+  }
   return m == 1 && p->nr <= kMaxRadices;
 }
 
@@ -131,6 +138,30 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
   }
 }
 
+// Generic radix (any R, used for prime factors > 5): one output element per work item.
+__device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__ src, float2* __restrict__ dst,
+                                                      int n, int ns, int R, int batch) {
+  const int per = n / R;
+  const int period = ns * R;
+  for (int w = threadIdx.x; w < n * batch; w += blockDim.x) {
+    const int b = w / n, e = w - b * n;
+    const int j = e / R, r = e - j * R;
+    const int k = j % ns;
+    const float2* s = src + b * n;
+    const int step = k + r * ns;  // phase advance per input index, in units of 2 pi / period
+    float2 acc = make_float2(0.f, 0.f);
+    int ph = 0;
+    for (int t = 0; t < R; ++t) {
+      float sn, cs;
+      sincospif(-2.0f * (float)ph / (float)period, &sn, &cs);
+      acc = cadd(acc, cmul(s[j + t * per], make_float2(cs, sn)));
+      ph += step;
+      if (ph >= period) ph -= period;
+    }
+    dst[b * n + (j - k) * R + k + r * ns] = acc;
+  }
+}
+
 // Forward FFT of `batch` sequences in shared memory; returns the buffer that holds the result.
 __device__ float2* fft_smem(float2* a, float2* b, const Plan& p, int batch) {
   int ns = 1;
@@ -140,7 +171,8 @@ __device__ float2* fft_smem(float2* a, float2* b, const Plan& p, int batch) {
     if (R == 4) stockham_pass<4>(src, dst, p.n, ns, batch);
     else if (R == 2) stockham_pass<2>(src, dst, p.n, ns, batch);
     else if (R == 3) stockham_pass<3>(src, dst, p.n, ns, batch);
-    else stockham_pass<5>(src, dst, p.n, ns, batch);
+    else if (R == 5) stockham_pass<5>(src, dst, p.n, ns, batch);
+    else stockham_pass_generic(src, dst, p.n, ns, R, batch);
     ns *= R;
     __syncthreads();
     float2* t = src; src = dst; dst = t;
@@ -223,7 +255,7 @@ struct FftCfg {
 
 int make_cfg(int H, int W, FftCfg* c) {
   if (H <= 0 || W <= 1 || H > 4096 || W > 4096 || !make_plan(W, &c->row) || !make_plan(H, &c->col)) {
-    set_error("FFT size %dx%d unsupported (needs factors 2,3,5 and <= 4096)", H, W);
+    set_error("FFT size %dx%d unsupported (each side must be in [1, 4096])", H, W);
     return HG_ERR_INVALID_ARG;
   }
   c->tc = (int)((96 * 1024) / (16 * (size_t)H));
@@ -387,7 +419,7 @@ __device__ __forceinline__ int band_of(int ky, int kx, int H, int W) {
   return -1;
 }
 
-constexpr int kSpecVals = 14;  // mag, phase, band_r[4], band_g[4], count[4]
+constexpr int kSpecVals = 14;  // mag, phase, band_r[4], band_r - band_g [4], count[4]
 __global__ void __launch_bounds__(256)
 spectral_sums_kernel(const float2* __restrict__ fr, const float2* __restrict__ fg, int H, int W,
                      double* __restrict__ partial) {
@@ -402,7 +434,7 @@ spectral_sums_kernel(const float2* __restrict__ fr, const float2* __restrict__ f
     const float w = (kx == 0 || (2 * kx == W)) ? 1.f : 2.f;  // Hermitian twin outside the half spectrum
     const float2 a = fr[i], b = fg[i];
     const float ma = hypotf(a.x, a.y), mb = hypotf(b.x, b.y);
-    const float dl = __logf(ma + 1e-6f) - __logf(mb + 1e-6f);
+    const float dl = logf(ma + 1e-6f) - logf(mb + 1e-6f);
     acc[0] += w * dl * dl;
     const float pa = atan2f(a.y, a.x), pb = atan2f(b.y, b.x);
     const float ad = fabsf(pa - pb);
@@ -410,7 +442,7 @@ spectral_sums_kernel(const float2* __restrict__ fr, const float2* __restrict__ f
     const int band = band_of(ky, kx, H, W);
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (band == q) { acc[2 + q] += w * ma; acc[6 + q] += w * mb; acc[10 + q] += w; }
+      if (band == q) { acc[2 + q] += w * ma; acc[6 + q] += w * (ma - mb); acc[10 + q] += w; }  // difference summed directly: Er - Eg cancels
   }
 #pragma unroll
   for (int q = 0; q < kSpecVals; ++q) {
@@ -469,7 +501,7 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
   float total = 0.f;
   float lvl_raw[3] = {0, 0, 0};
   float sp_raw[3], fft_raw[3], mag_raw[3], ph_raw[3], band_raw[3];
-  float er[3][4], eg[3][4], cnt[3][4];
+  float ediff[3][4], cnt[3][4];
   for (int l = 0; l < a.levels; ++l) {
     const double n = (double)a.dim[l].H * a.dim[l].W;
     double s[3] = {0, 0, 0};
@@ -486,9 +518,8 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
     float bl = 0.f;
     for (int q = 0; q < 4; ++q) {
       cnt[l][q] = (float)v[10 + q];
-      er[l][q] = cnt[l][q] > 0.f ? (float)(v[2 + q] / (v[10 + q] + 1e-8)) : 0.f;
-      eg[l][q] = cnt[l][q] > 0.f ? (float)(v[6 + q] / (v[10 + q] + 1e-8)) : 0.f;
-      bl += (er[l][q] - eg[l][q]) * (er[l][q] - eg[l][q]);
+      ediff[l][q] = cnt[l][q] > 0.f ? (float)(v[6 + q] / (v[10 + q] + 1e-8)) : 0.f;  // E_rendered - E_gt
+      bl += ediff[l][q] * ediff[l][q];
     }
     band_raw[l] = bl / 4.f;
     const float mag = clampf(mag_raw[l], 0.f, 10.f), ph = clampf(ph_raw[l], 0.f, kPi), band = clampf(band_raw[l], 0.f, 100.f);
@@ -515,7 +546,7 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
     const float gb = g_fft * 0.2f * (within(band_raw[l], 0.f, 100.f) ? 1.f : 0.f);
     for (int q = 0; q < 4; ++q) {
       c.band_count[q] = cnt[l][q];
-      c.c_band[q] = cnt[l][q] > 0.f ? gb * (2.f / 4.f) * (er[l][q] - eg[l][q]) / (cnt[l][q] + 1e-8f) : 0.f;
+      c.c_band[q] = cnt[l][q] > 0.f ? gb * (2.f / 4.f) * ediff[l][q] / (cnt[l][q] + 1e-8f) : 0.f;
     }
   }
   // band energies of the level-0 ground truth (debug_info)
@@ -538,7 +569,7 @@ spectral_grad_kernel(float2* __restrict__ fr, const float2* __restrict__ fg, int
     const float ma = hypotf(a.x, a.y), mb = hypotf(b.x, b.y);
     float gre = 0.f, gim = 0.f;
     if (ma > 0.f) {
-      float dmag = c_mag * (__logf(ma + 1e-6f) - __logf(mb + 1e-6f)) / (ma + 1e-6f);
+      float dmag = c_mag * (logf(ma + 1e-6f) - logf(mb + 1e-6f)) / (ma + 1e-6f);
       const int band = band_of(ky, kx, H, W);
       if (band >= 0) dmag += ctl->c_band[band];
       gre = dmag * a.x / ma;

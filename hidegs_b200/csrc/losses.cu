@@ -514,12 +514,12 @@ size_t hg_scale_reg_workspace_bytes(int64_t) { return sizeof(double) * 2 * kRedB
 
 int hg_scale_reg(const float* scaling, int64_t N, const int64_t* vis_idx, const uint8_t* vis_mask, int64_t n_vis,
                  float* out, float* grad_scaling, void* ws, void* st_) {
-  if (!scaling || !out || !ws || N < 0 || (!vis_idx && !vis_mask)) {
+  if (!scaling || !out || !ws || N < 0 || (!vis_idx && !vis_mask && n_vis != 0)) {
     set_error("hg_scale_reg: bad argument");
     return HG_ERR_INVALID_ARG;
   }
   cudaStream_t st = (cudaStream_t)st_;
-  const int64_t n_items = vis_idx ? n_vis : N;
+  const int64_t n_items = vis_mask ? N : (vis_idx ? n_vis : 0);  // an empty index list selects nothing
   double* psum = (double*)ws;
   double* pcnt = psum + kRedBlocks;
   ScaleRegCtl* ctl = (ScaleRegCtl*)(pcnt + kRedBlocks);

@@ -70,7 +70,8 @@ HG_API int hg_scale_reg(const float *scaling, int64_t N, const int64_t *vis_idx,
 
 /* 2-D FFT of a real H x W image -> half spectrum [H, W/2+1] interleaved complex (unnormalised, as
  * torch.fft.fft2), and the inverse (normalised by 1/(H*W), as torch.fft.ifft2 of a Hermitian
- * spectrum; real output).  H and W must factor into 2, 3 and 5 and be <= 4096. */
+ * spectrum; real output).  1 < W, H <= 4096; sizes 2^a 3^b 5^c use radix-4/2/3/5 butterflies, other
+ * prime factors a generic O(R^2) butterfly. */
 HG_API size_t hg_fft2_workspace_bytes(int32_t H, int32_t W);
 HG_API int hg_fft2_r2c(const float *img, int32_t H, int32_t W, float *spec, void *workspace, void *stream);
 HG_API int hg_fft2_c2r(const float *spec, int32_t H, int32_t W, float *img, int scale_by_inverse_size,
