@@ -21,6 +21,7 @@
 // the noise floor) a TF32 DFT-as-GEMM does not meet the 1e-3 loss tolerance, and the FFT work here is
 // a few MFLOP per level.
 #include "common.cuh"
+#include "reduce.cuh"
 #include "../../include/hidegs_losses.h"
 
 namespace hg {
@@ -489,10 +490,30 @@ struct FreqFinalizeArgs {
   const double* band0_partial;  // level-0 GT band energies
   LevelCtl* ctl;
   float* stats;
+  double* sums;  // [kFreqSums] second-stage sums
 };
 
 __device__ __forceinline__ bool within(float v, float lo, float hi) { return v >= lo && v <= hi; }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// Second reduction stage: block b sums one of the 3*17 per-level quantities (3 spatial + 14 spectral) or one of
+// the 8 level-0 ground-truth band sums into a.sums[b] (fixed order, double).
+constexpr int kPerLevelSums = 3 + kSpecVals;
+constexpr int kFreqSums = 3 * kPerLevelSums + 8;
+__global__ void __launch_bounds__(256) freq_reduce_kernel(FreqFinalizeArgs a) {
+  __shared__ double sm[32];
+  const int b = blockIdx.x;
+  double v = 0.0;
+  if (b < 3 * kPerLevelSums) {
+    const int l = b / kPerLevelSums, q = b - l * kPerLevelSums;
+    if (l >= a.levels) return;
+    if (q < 3) v = cta_sum_strided(a.spatial_partial[l], a.spatial_blocks[l], 3, q, sm);
+    else v = cta_sum_strided(a.spectral_partial[l], kSumBlocks, kSpecVals, q - 3, sm);
+  } else {
+    v = cta_sum_strided(a.band0_partial, kSumBlocks, 8, b - 3 * kPerLevelSums, sm);
+  }
+  if (threadIdx.x == 0) a.sums[b] = v;
+}
 
 // Scalar epilogue of compute_true_frequency_loss, and the coefficients its backward needs.
 __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
@@ -504,15 +525,10 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
   float ediff[3][4], cnt[3][4];
   for (int l = 0; l < a.levels; ++l) {
     const double n = (double)a.dim[l].H * a.dim[l].W;
-    double s[3] = {0, 0, 0};
-    for (int i = 0; i < a.spatial_blocks[l]; ++i)
-      for (int q = 0; q < 3; ++q) s[q] += a.spatial_partial[l][3 * i + q];
+    const double* s = a.sums + l * kPerLevelSums;
     const float gx = (float)(s[0] / n), gy = (float)(s[1] / n), lap = (float)(s[2] / n);
     sp_raw[l] = 0.7f * (gx + gy) + 0.3f * lap;
-    double v[kSpecVals];
-    for (int q = 0; q < kSpecVals; ++q) v[q] = 0.0;
-    for (int i = 0; i < kSumBlocks; ++i)
-      for (int q = 0; q < kSpecVals; ++q) v[q] += a.spectral_partial[l][(size_t)i * kSpecVals + q];
+    const double* v = s + 3;
     mag_raw[l] = (float)(v[0] / n);
     ph_raw[l] = (float)(v[1] / n);
     float bl = 0.f;
@@ -550,9 +566,7 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
     }
   }
   // band energies of the level-0 ground truth (debug_info)
-  double e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < kSumBlocks; ++i)
-    for (int q = 0; q < 8; ++q) e[q] += a.band0_partial[(size_t)i * 8 + q];
+  const double* e = a.sums + 3 * kPerLevelSums;
   for (int q = 0; q < 4; ++q) a.stats[19 + q] = e[4 + q] > 0.0 ? (float)(e[q] / (e[4 + q] + 1e-8)) : 0.f;
 }
 
@@ -677,12 +691,17 @@ hf_reduce_kernel(float* __restrict__ hs, const float* __restrict__ spatial, cons
   }
 }
 
+// one warp; min/max are order independent
 __global__ void hf_minmax_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax, int n,
                                  float* __restrict__ mm) {
-  if (threadIdx.x != 0) return;
-  float lo = pmin[0], hi = pmax[0];
-  for (int i = 1; i < n; ++i) { lo = fminf(lo, pmin[i]); hi = fmaxf(hi, pmax[i]); }
-  mm[0] = lo; mm[1] = hi;
+  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+  for (int i = threadIdx.x; i < n; i += 32) { lo = fminf(lo, pmin[i]); hi = fmaxf(hi, pmax[i]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (threadIdx.x == 0) { mm[0] = lo; mm[1] = hi; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -701,11 +720,10 @@ hf_threshold_kernel(const float* __restrict__ score, const float* __restrict__ m
   if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
 }
 
-__global__ void hf_count_kernel(const double* __restrict__ partial, int n, float* __restrict__ count) {
-  if (threadIdx.x != 0) return;
-  double s = 0.0;
-  for (int i = 0; i < n; ++i) s += partial[i];
-  count[0] = (float)s;
+__global__ void __launch_bounds__(256) hf_count_kernel(const double* __restrict__ partial, int n, float* __restrict__ count) {
+  __shared__ double sm[32];
+  const double s = cta_sum_strided(partial, n, 1, 0, sm);
+  if (threadIdx.x == 0) count[0] = (float)s;
 }
 
 struct Carver {
@@ -751,7 +769,7 @@ int hg_fft2_c2r(const float* spec, int32_t H, int32_t W, float* img, int scale_i
 }
 
 size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels) {
-  size_t total = 4096 + (size_t)kSumBlocks * 8 * 8;
+  size_t total = 4096 + (size_t)kSumBlocks * 8 * 8 + 1024;
   int h = H, w = W;
   for (int l = 0; l < levels; ++l) {
     total += level_bytes(h, w);
@@ -779,6 +797,7 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
   Carver cv(ws);
   LevelCtl* ctl = cv.take<LevelCtl>(3);
   double* band0 = cv.take<double>((size_t)kSumBlocks * 8);
+  double* sums = cv.take<double>(kFreqSums);
   float *gr[3], *gg[3], *dg[3];
   float2 *fr[3], *fg[3];
   double *sp_part[3], *spec_part[3];
@@ -827,6 +846,9 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
   fa.band0_partial = band0;
   fa.ctl = ctl;
   fa.stats = stats;
+  fa.sums = sums;
+  freq_reduce_kernel<<<kFreqSums, 256, 0, st>>>(fa);
+  HG_POST_LAUNCH(false, st, "freq_reduce");
   freq_finalize_kernel<<<1, 32, 0, st>>>(fa);
   HG_POST_LAUNCH(false, st, "freq_finalize");
   if (!grad_rendered) return HG_OK;
@@ -891,7 +913,7 @@ int hg_hf_mask(const float* gt, int32_t H, int32_t W, float thresh, float* mask,
   hf_reduce_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, spatial, mm, hw, 1, pmin, pmax);
   hf_minmax_kernel<<<1, 32, 0, st>>>(pmin, pmax, kSumBlocks, mm + 2);
   hf_threshold_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, mm + 2, hw, thresh, mask, part);
-  hf_count_kernel<<<1, 32, 0, st>>>(part, kSumBlocks, count);
+  hf_count_kernel<<<1, 256, 0, st>>>(part, kSumBlocks, count);
   HG_POST_LAUNCH(false, st, "hf_mask");
   return HG_OK;
 }

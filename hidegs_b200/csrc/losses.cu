@@ -6,6 +6,7 @@
 // image is read once (plus a 5-pixel halo for SSIM), reductions are two-stage and deterministic
 // (per-block partials in fixed order, final sum in double), nothing synchronises with the host.
 #include "common.cuh"
+#include "reduce.cuh"
 #include "../../include/hidegs_losses.h"
 
 #include <cmath>
@@ -72,16 +73,9 @@ pixel_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, int6
 
 __global__ void finalize_mean_kernel(const double* __restrict__ partial, int n_partial, double denom,
                                      float* __restrict__ out) {
-  __shared__ double sm[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n_partial; i += blockDim.x) s += partial[i];
-  sm[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = (float)(sm[0] / denom);
+  __shared__ double sm[32];
+  const double s = cta_sum_strided(partial, n_partial, 1, 0, sm);
+  if (threadIdx.x == 0) out[0] = (float)(s / denom);
 }
 
 template <bool L2>
@@ -167,17 +161,9 @@ ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, 
 
 __global__ void ssim_finalize_kernel(const double* __restrict__ partial, int per_item, double denom,
                                      float* __restrict__ out) {
-  __shared__ double sm[256];
-  double s = 0.0;
-  const double* p = partial + (size_t)blockIdx.x * per_item;
-  for (int i = threadIdx.x; i < per_item; i += blockDim.x) s += p[i];
-  sm[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[blockIdx.x] = (float)(sm[0] / denom);
+  __shared__ double sm[32];
+  const double s = cta_sum_strided(partial + (size_t)blockIdx.x * per_item, per_item, 1, 0, sm);
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(s / denom);
 }
 
 __global__ void __launch_bounds__(kTile * kTile)
@@ -353,9 +339,10 @@ scale_reg_sum_kernel(const float* __restrict__ scaling, int64_t N, const int64_t
 
 __global__ void scale_reg_finalize_kernel(const double* __restrict__ psum, const double* __restrict__ pcnt,
                                           int n, float* __restrict__ out, ScaleRegCtl* __restrict__ ctl) {
+  __shared__ double sm[32];
+  const double s = cta_sum_strided(psum, n, 1, 0, sm);
+  const double c = cta_sum_strided(pcnt, n, 1, 0, sm);
   if (threadIdx.x != 0) return;
-  double s = 0.0, c = 0.0;
-  for (int i = 0; i < n; ++i) { s += psum[i]; c += pcnt[i]; }
   float loss = 0.f, coef = 0.f;
   if (c > 0.0) {
     const float raw = (float)(s / c);
@@ -439,7 +426,7 @@ int hg_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t 
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
   ssim_fwd_kernel<<<grid, dim3(kTile, kTile), 0, st>>>(img1, img2, H, W, maps, (size_t)B * C * H * W, (double*)ws);
   HG_POST_LAUNCH(false, st, "ssim_fwd");
-  ssim_finalize_kernel<<<B, 256, 0, st>>>((const double*)ws, (int)(grid.x * grid.y * C), (double)C * H * W, out);
+  ssim_finalize_kernel<<<B, 1024, 0, st>>>((const double*)ws, (int)(grid.x * grid.y * C), (double)C * H * W, out);
   HG_POST_LAUNCH(false, st, "ssim_finalize");
   return HG_OK;
 }
@@ -525,7 +512,7 @@ int hg_scale_reg(const float* scaling, int64_t N, const int64_t* vis_idx, const 
   ScaleRegCtl* ctl = (ScaleRegCtl*)(pcnt + kRedBlocks);
   scale_reg_sum_kernel<<<kRedBlocks, kRedThreads, 0, st>>>(scaling, N, vis_idx, vis_mask, n_items, psum, pcnt);
   HG_POST_LAUNCH(false, st, "scale_reg_sum");
-  scale_reg_finalize_kernel<<<1, 32, 0, st>>>(psum, pcnt, kRedBlocks, out, ctl);
+  scale_reg_finalize_kernel<<<1, 256, 0, st>>>(psum, pcnt, kRedBlocks, out, ctl);
   HG_POST_LAUNCH(false, st, "scale_reg_finalize");
   if (grad_scaling) {
     HG_CUDA_TRY(cudaMemsetAsync(grad_scaling, 0, sizeof(float) * 3 * (size_t)N, st));
