@@ -299,6 +299,22 @@ def run_gpu_arm(args, impl):
     ms_e2e = float(t2) / K
     e2e_value = (world if impl == "ours" else 1) * HW / (ms_e2e * 1e-3) / 1e6
 
+    train = train_c3 = losses = None
+    if impl == "ours" and not os.environ.get("HG_BENCH_SKIP_TRAIN"):
+        # free the rasterizer legs' buffers before the 2M-Gaussian training legs
+        del params, am_param, scene, all_maps
+        torch.cuda.empty_cache()
+        n_train = int(os.environ.get("HG_BENCH_TRAIN_N", 2_000_000))
+        train = train_leg(dev, rank, world, ddp, steps=max(2, min(K, 5)), warmup=3, views_per_rank=8, n_gauss=n_train,
+                          recipe="uav")
+        if world == 1:
+            torch.cuda.empty_cache()
+            train_c3 = train_leg(dev, rank, world, False, steps=max(3, min(K, 10)), warmup=3, views_per_rank=1,
+                                 n_gauss=n_train, recipe="c2")
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import loss_bench
+            losses = loss_bench.measure(dev, iters=10, warmup=3, cpu=not os.environ.get("HG_BENCH_SKIP_CPU"))
+
     if rank != 0:
         if ddp:
             dist.destroy_process_group()
@@ -337,6 +353,12 @@ def run_gpu_arm(args, impl):
                             "stage_ms": per_stage,
                             "note": "blend kernels are FP32-issue / shared-memory bound, not HBM bound (DESIGN.md §4)"}
         line["gpu_launches"] = launches
+        if train is not None:
+            line["train"] = train
+        if train_c3 is not None:
+            line["train_config3"] = train_c3
+        if losses is not None:
+            line["losses_config0"] = losses
         if not os.environ.get("HG_BENCH_SKIP_CPU"):
             line["cpu_baseline"] = cpu_baseline(scene_cpu)
     else:
@@ -347,6 +369,74 @@ def run_gpu_arm(args, impl):
     print(json.dumps(line), flush=True)
     if ddp:
         dist.destroy_process_group()
+
+
+def make_gt_images(n, dev, seed=11):
+    """Synthetic ground-truth images (config-1 recipe: blurred uniform noise), generated on the device, kept on the
+    HOST in pinned memory: the training loop copies one per view, like a data loader would."""
+    import torch.nn.functional as F
+    g = torch.Generator(device=dev).manual_seed(seed)
+    out = []
+    for _ in range(n):
+        x = torch.rand(1, 3, HEIGHT, WIDTH, generator=g, device=dev)
+        out.append(F.avg_pool2d(x, 5, stride=1, padding=2)[0].clamp(0, 1).cpu().pin_memory())
+    return out
+
+
+def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, recipe):
+    """Training views/s (BASELINE.json metric 2): full HiDeGS step = render (prologue + rasterizer + epilogue) + L1 +
+    SSIM + frequency regularisation + scale regularisation + single-view normal term, backward, gradient all-reduce
+    over the ranks, fused Adam.  `recipe`: "uav" = configs[4] (8x8 survey cameras over the 400 m x 224 m slab, views
+    sharded views[rank::world]) or "c2" = configs[3] (config-2 scene / camera)."""
+    import torch.distributed as dist
+    from hidegs_b200 import synthetic as syn, trainer as tr, _lib
+    if recipe == "uav":
+        scene = syn.make_uav_scene(n_gauss, seed=0)
+        cams_all = [syn.uav_camera(i, j, width=WIDTH, height=HEIGHT).to(dev) for i in range(8) for j in range(8)]
+    else:
+        scene = syn.make_scene(n_gauss, seed=0)
+        cams_all = [camera_for(r, s).to(dev) for r in range(8) for s in range(8)]
+    total_views = views_per_rank * world
+    cams = cams_all[:total_views][rank::world]
+    gts = make_gt_images(views_per_rank, dev, seed=11 + rank)
+    params = tr.GaussianParams.from_scene(scene, dev)
+    trainer = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev))
+
+    def step():
+        views = [(c, g.to(dev, non_blocking=True)) for c, g in zip(cams, gts)]
+        loss = trainer.step(views, total_views=total_views)
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    _lib.lib().hg_reset_launch_count()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if ddp:
+        dist.barrier()
+    last = float(loss.item())
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if ddp:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / steps
+    return {"views_per_s": round(total_views / (ms_step * 1e-3), 2), "ms_per_step": round(ms_step, 3),
+            "ms_per_view": round(ms_step / views_per_rank, 3), "views_per_rank_per_step": views_per_rank,
+            "views_per_step": total_views, "gaussians": n_gauss, "steps": steps, "warmup": warmup,
+            "loss_last_step_rank0": round(last, 6), "gpu_launches": int(_lib.lib().hg_launch_count()),
+            "allreduce_bytes_per_step": params.grad_arena.numel() * 4 if world > 1 else 0,
+            "h2d_bytes_per_step": views_per_rank * 3 * HEIGHT * WIDTH * 4,
+            "workload": ("configs[4]: view-sharded training, %d UAV survey cameras per step over the 2M-Gaussian slab, %dx%d, "
+                         "views[rank::world], one fp32 gradient all-reduce + fused Adam per step" % (total_views, WIDTH, HEIGHT))
+            if recipe == "uav" else
+            ("configs[3]: full HiDeGS training step (L1 + SSIM + frequency + scale reg + single-view normal term) on the "
+             "config-2 scene with %d Gaussians, %d view(s) per step" % (n_gauss, total_views))}
 
 
 def cpu_baseline(scene_cpu, iters=1, tile_step=1):

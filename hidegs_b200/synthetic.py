@@ -48,6 +48,11 @@ class Camera:
         self.camera_center = torch.linalg.inv(self.world_view_transform)[3, :3].contiguous()
         self.tanfovx = math.tan(self.FoVx * 0.5)
         self.tanfovy = math.tan(self.FoVy * 0.5)
+        # scene/cameras.py:93-96
+        self.Fx = self.image_width / (2 * math.tan(self.FoVx / 2))
+        self.Fy = self.image_height / (2 * math.tan(self.FoVy / 2))
+        self.Cx, self.Cy = 0.5 * self.image_width, 0.5 * self.image_height
+        self.image_name = "synthetic"
 
     def to(self, device):
         for k in ("world_view_transform", "projection_matrix", "full_proj_transform", "camera_center"):
@@ -149,3 +154,32 @@ def raster_settings(cam, device, sh_degree=3, bg=(0.0, 0.0, 0.0), render_geo=Tru
         interpolation_weights=e_f if interpolation_weights is None else interpolation_weights,
         num_node_kids=e_i if num_node_kids is None else num_node_kids,
         do_depth=do_depth, render_geo=render_geo)
+
+
+# ---------------------------------------------------------------- UAV-scale scenes
+def make_uav_scene(n, seed=0, extent=(200.0, 112.0), height=30.0, log_scale_mean=math.log(0.08), log_scale_std=0.7,
+                   sh_coeffs=16):
+    """Ground slab x in [-200,200] m, y in [-112,112] m, z in [0,30] m (config 3 / 5 recipe)."""
+    g = torch.Generator().manual_seed(seed)
+    xyz = torch.rand(n, 3, generator=g)
+    xyz[:, 0] = (xyz[:, 0] * 2 - 1) * extent[0]
+    xyz[:, 1] = (xyz[:, 1] * 2 - 1) * extent[1]
+    xyz[:, 2] = xyz[:, 2] * height
+    scales = torch.exp(torch.randn(n, 3, generator=g) * log_scale_std + log_scale_mean)
+    q = torch.randn(n, 4, generator=g)
+    rotations = q / q.norm(dim=-1, keepdim=True)
+    opacity = torch.sigmoid(torch.randn(n, 1, generator=g) * 1.5)
+    shs = torch.randn(n, sh_coeffs, 3, generator=g) * 0.1
+    shs[:, 0, :] = torch.randn(n, 3, generator=g) * 0.5
+    return dict(means3D=xyz.contiguous(), scales=scales.contiguous(), rotations=rotations.contiguous(),
+                opacity=opacity.contiguous(), shs=shs.contiguous())
+
+
+def uav_camera(i, j, grid=8, width=1920, height=1080, altitude=120.0, fovx_deg=70.0, extent=(200.0, 112.0)):
+    """Camera (i, j) of the grid x grid survey over the slab: nadir on even i + j, 20 degrees oblique otherwise."""
+    cx = (-1 + (2 * i + 1) / grid) * extent[0] * 0.7
+    cy = (-1 + (2 * j + 1) / grid) * extent[1] * 0.7
+    eye = (cx, cy, altitude)
+    tilt = 0.0 if (i + j) % 2 == 0 else math.tan(math.radians(20.0)) * altitude
+    target = (cx + tilt, cy, 0.0)
+    return look_at_camera(eye, target, (0.0, 1.0, 0.0), math.radians(fovx_deg), width, height)

@@ -1,0 +1,191 @@
+"""View-sharded training step of HiDeGS on the B200 hot path (BASELINE.json configs[3] / [4]).
+
+The reference ships no train.py (README.md:175); the step below is the one its pieces compose into
+(gaussian_renderer.render -> l1 / ssim / frequency_regularization_pyramid_scale / single-view normal term ->
+backward -> OurAdam step), with the weights of arguments/__init__.py:100-135:
+
+    loss = (1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))
+         + frequency_regularization_pyramid_scale(image, gt, gaussians, scene, cam, visibility_filter, iteration)[0]
+         + single_view_weight * mean((1 - get_img_grad_weight(gt)).clamp(0, 1) ** 2 * |depth_normal - rendered_normal|.sum(0))
+
+Data parallelism: Gaussians are replicated, the views of a step are split `views[rank::world]`, every rank accumulates
+the gradients of its views in ONE flat fp32 arena (59 floats per Gaussian: xyz 3 | features 48 | opacity 1 | scaling 3 |
+rotation 4, SoA by group), the arena is all-reduced once per step (NCCL over NVLink) and the fused Adam kernel consumes
+it with grad_scale = 1 / views.  Parameters live in a matching flat arena, so the optimiser is 6 launches per step.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import gaussian_renderer as gr
+from . import loss_utils as lu
+from ._geometry_lib import lib as _G
+from . import _lib
+from .frequency_regularization import frequency_regularization_pyramid_scale
+
+GROUPS = (("xyz", 3), ("features", 48), ("opacity", 1), ("scaling", 3), ("rotation", 4))
+
+
+class PipelineParams:
+    """arguments/__init__.py PipelineParams defaults."""
+    convert_SHs_python = False
+    compute_cov3D_python = False
+    debug = False
+
+
+class OptimizationParams:
+    """The entries of arguments/__init__.py:83-135 the training step reads."""
+    position_lr_init = 0.00016
+    feature_lr = 0.0025
+    opacity_lr = 0.05
+    scaling_lr = 0.005
+    rotation_lr = 0.001
+    lambda_dssim = 0.2
+    single_view_weight = 0.015
+    lambda_freq = 0.001
+    lambda_scale = 0.005
+    freq_warmup_iterations = 1000
+
+
+class GaussianParams:
+    """Trainable Gaussians in the reference's parameterisation (scene/gaussian_model.py:60-140): raw leaves
+    `_xyz`, `_features` (N,16,3), `_opacity` (logit), `_scaling` (log), `_rotation` (un-normalised quaternion) and the
+    activated accessors render() reads.  All leaves are views into one flat parameter arena; their `.grad` are views
+    into one flat gradient arena of the same layout."""
+
+    def __init__(self, xyz, features, opacity_logit, scaling_log, rotation, sh_degree=3):
+        dev = xyz.device
+        N = xyz.size(0)
+        self.N = N
+        width = sum(w for _, w in GROUPS)
+        self.param_arena = torch.empty(N * width, dtype=torch.float32, device=dev)
+        self.grad_arena = torch.zeros(N * width, dtype=torch.float32, device=dev)
+        src = dict(xyz=xyz, features=features.reshape(N, -1), opacity=opacity_logit, scaling=scaling_log, rotation=rotation)
+        self.leaves, self.slices = {}, {}
+        off = 0
+        for name, w in GROUPS:
+            sl = slice(off, off + N * w)
+            self.slices[name] = sl
+            self.param_arena[sl].view(N, w).copy_(src[name].reshape(N, w))
+            shape = (N, 16, 3) if name == "features" else (N, w)
+            leaf = self.param_arena[sl].view(shape).requires_grad_(True)
+            leaf.grad = self.grad_arena[sl].view(shape)
+            self.leaves[name] = leaf
+            off += N * w
+        self._xyz, self._features = self.leaves["xyz"], self.leaves["features"]
+        self._opacity, self._scaling, self._rotation = self.leaves["opacity"], self.leaves["scaling"], self.leaves["rotation"]
+        self.active_sh_degree = self.max_sh_degree = sh_degree
+        self.skybox_points = 0
+
+    @classmethod
+    def from_scene(cls, scene, device):
+        """From a synthetic scene dict (hidegs_b200.synthetic.make_scene): activated values -> raw leaves."""
+        op = scene["opacity"].clamp(1e-6, 1 - 1e-6)
+        return cls(scene["means3D"].to(device), scene["shs"].to(device), torch.log(op / (1 - op)).to(device),
+                   torch.log(scene["scales"]).to(device), scene["rotations"].to(device))
+
+    get_xyz = property(lambda s: s._xyz)
+    get_features = property(lambda s: s._features)
+    get_opacity = property(lambda s: torch.sigmoid(s._opacity))
+    get_scaling = property(lambda s: torch.exp(s._scaling))
+    get_rotation = property(lambda s: torch.nn.functional.normalize(s._rotation))
+
+    def zero_grad(self):
+        self.grad_arena.zero_()
+        for name, leaf in self.leaves.items():  # autograd may have replaced .grad; point it back at the arena
+            shape = leaf.shape
+            leaf.grad = self.grad_arena[self.slices[name]].view(shape)
+
+
+class ArenaAdam:
+    """Fused Adam over the parameter arena (scene/OurAdam.py semantics, one launch per parameter group; the SH
+    block takes two: DC at feature_lr, the rest at feature_lr / 20, as GaussianModel.training_setup does)."""
+
+    def __init__(self, params: GaussianParams, opt=OptimizationParams, spatial_lr_scale=1.0, eps=1e-15):
+        self.p = params
+        self.exp_avg = torch.zeros_like(params.param_arena)
+        self.exp_avg_sq = torch.zeros_like(params.param_arena)
+        self.lr = dict(xyz=opt.position_lr_init * spatial_lr_scale, features=opt.feature_lr, opacity=opt.opacity_lr,
+                       scaling=opt.scaling_lr, rotation=opt.rotation_lr)
+        self.eps, self.step_count = eps, 0
+        # per-element learning-rate multiplier is only needed for the SH block: handled by two strided launches
+        self._sh_lr = torch.full((48,), opt.feature_lr / 20.0)
+        self._sh_lr[:3] = opt.feature_lr
+
+    @torch.no_grad()
+    def step(self, grad_scale=1.0, visible_mask=None):
+        self.step_count += 1
+        p = self.p
+        st = torch.cuda.current_stream().cuda_stream
+        mask = visible_mask.contiguous().view(torch.uint8).data_ptr() if visible_mask is not None else None
+        with torch.cuda.device(p.param_arena.device):
+            for name, w in GROUPS:
+                sl = p.slices[name]
+                base = sl.start * 4
+                if name == "features":
+                    # rows of 48 floats: [dc(3) | rest(45)]; the two learning rates need two passes over the block
+                    rc = self._launch(base, p.N, 48, mask, self.lr["features"] / 20.0, grad_scale, st)
+                    _lib.check(rc, "adam_step")
+                    self._fix_dc(sl, grad_scale)
+                    continue
+                rc = self._launch(base, p.N, w, mask, self.lr[name], grad_scale, st)
+                _lib.check(rc, "adam_step")
+
+    def _launch(self, byte_off, rows, width, mask, lr, grad_scale, st):
+        p = self.p
+        return _G().hg_adam_step(p.param_arena.data_ptr() + byte_off, p.grad_arena.data_ptr() + byte_off,
+                                 self.exp_avg.data_ptr() + byte_off, self.exp_avg_sq.data_ptr() + byte_off, rows, width,
+                                 mask, None, 0, lr, 0.9, 0.999, self.eps, self.step_count, grad_scale, st)
+
+    def _fix_dc(self, sl, grad_scale):
+        # The block was stepped at feature_lr / 20; Adam's update is linear in lr, so the DC columns get the
+        # remaining 19/20 of their step from the already-updated moments:  p -= (lr_dc - lr_rest) / bc1 * m / denom.
+        N = self.p.N
+        m = self.exp_avg[sl].view(N, 48)[:, :3]
+        v = self.exp_avg_sq[sl].view(N, 48)[:, :3]
+        bc1 = 1 - 0.9 ** self.step_count
+        bc2 = 1 - 0.999 ** self.step_count
+        extra = (self.lr["features"] - self.lr["features"] / 20.0) / bc1
+        self.p.param_arena[sl].view(N, 48)[:, :3].addcdiv_(m, v.sqrt() / math.sqrt(bc2) + self.eps, value=-extra)
+
+
+class ViewShardedTrainer:
+    def __init__(self, params: GaussianParams, background, opt=OptimizationParams, pipe=PipelineParams, group=None):
+        self.params, self.bg, self.opt, self.pipe, self.group = params, background, opt, pipe, group
+        self.adam = ArenaAdam(params, opt)
+        self.iteration = 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def view_loss(self, cam, gt, iteration):
+        """Forward of one view: returns (loss tensor, render package)."""
+        o = self.opt
+        pkg = gr.render(cam, self.params, self.pipe, self.bg)
+        image = pkg["render"]
+        loss = (1.0 - o.lambda_dssim) * lu.l1_loss(image, gt) + o.lambda_dssim * (1.0 - lu.ssim(image, gt))
+        freq, _mask, _info = frequency_regularization_pyramid_scale(
+            image, gt, self.params, None, cam, pkg["visibility_filter"], iteration, lambda_freq=o.lambda_freq,
+            lambda_scale=o.lambda_scale, warmup_iterations=o.freq_warmup_iterations)
+        loss = loss + freq
+        if o.single_view_weight > 0:
+            image_weight = (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2
+            loss = loss + gr.normal_consistency_loss(pkg["plane_depth"], pkg["out_all_map"], cam, image_weight,
+                                                     o.single_view_weight)
+        return loss, pkg
+
+    def step(self, views, total_views=None):
+        """One optimiser step over this rank's `views` = [(camera, gt_image), ...]; returns the summed loss tensor."""
+        self.iteration += 1
+        self.params.zero_grad()
+        total = None
+        for cam, gt in views:
+            loss, _pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations)
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        n_views = len(views)
+        if self.world > 1:
+            dist.all_reduce(self.params.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
+            n_views = total_views if total_views is not None else n_views * self.world
+        self.adam.step(grad_scale=1.0 / max(n_views, 1))
+        return total

@@ -1,0 +1,101 @@
+/*
+ * hidegs_geometry.h — C-ABI of the geometry prologue / epilogue that surround the rasterizer call in
+ * the reference's render() (gaussian_renderer/__init__.py:36-214), of the single-view normal-consistency
+ * term of the training loss, of the fused Adam step and of simple-knn's distCUDA2.
+ *
+ * Conventions as in hidegs_raster.h: device pointers (fp32 unless stated), sizes, scalars, a cudaStream_t
+ * passed as void*; int status return (hg_status); no host synchronisation inside unless stated.
+ *
+ * Reference functions replaced (paths relative to the reference tree):
+ *   hg_geometry_all_map            gaussian_renderer/__init__.py:161-169 (input_all_map) with
+ *                                  GaussianModel.get_normal / get_smallest_axis / get_rotation_matrix
+ *                                  (scene/gaussian_model.py:150-166; pytorch3d quaternion_to_matrix)
+ *   hg_geometry_all_map_backward   the autograd backward of the above (~10 PyTorch ops)
+ *   hg_depth_normal                render_normal (gaussian_renderer/__init__.py:21-33) ->
+ *                                  normal_from_depth_image / depth2point_world / depth2point_cam / ndc_2_cam /
+ *                                  depth_pcd2normal (utils/graphics_utils.py:17-23,108-166), offset=None,
+ *                                  scale=1, times rendered_alpha.detach() (gaussian_renderer/__init__.py:201)
+ *   hg_depth_normal_backward       its autograd backward w.r.t. the plane depth
+ *   hg_normal_consistency_loss     single-view term  w * mean(image_weight * sum_c |depth_normal_c - normal_c|)
+ *                                  (weights arguments/__init__.py:118-119; composed from render()'s
+ *                                  "depth_normal" / "rendered_normal" outputs and get_img_grad_weight,
+ *                                  utils/loss_utils.py:66-78; see DESIGN.md for the definition)
+ *   hg_adam_step                   scene/OurAdam.py:106-337 (Adam update of the parameter groups; dense and
+ *                                  visibility-masked "sparse" variant)
+ *   hg_dist2_knn3                  simple_knn: distCUDA2 -> SimpleKNN::knn (submodules/simple-knn/spatial.cu:15-26,
+ *                                  simple_knn.cu:186-222): mean squared distance to the 3 nearest neighbours
+ */
+#ifndef HIDEGS_GEOMETRY_H
+#define HIDEGS_GEOMETRY_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "hidegs_raster.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* all_map[n] = [ R_view^T normal_n (3), 1, |<normal_view, p_view>| ] with normal_n = the column of
+ * quaternion_to_matrix(rotation_n) that belongs to the smallest scaling axis, flipped to face campos.
+ * xyz [N,3], scaling [N,3] (activated), rotation [N,4] (real-first; need not be normalised),
+ * viewmatrix [16] (row-vector convention, cameras.py:127), campos [3]; out [N,5]. */
+HG_API int hg_geometry_all_map(const float *xyz, const float *scaling, const float *rotation,
+                               const float *viewmatrix, const float *campos, int64_t N, float *out_all_map,
+                               void *stream);
+
+/* dL/dxyz [N,3] and dL/drotation [N,4] from dL/dall_map [N,5]; both outputs are fully WRITTEN (not
+ * accumulated).  No gradient reaches the scaling (argmin) or the camera. */
+HG_API int hg_geometry_all_map_backward(const float *xyz, const float *scaling, const float *rotation,
+                                        const float *viewmatrix, const float *campos, int64_t N,
+                                        const float *dL_dall_map, float *dL_dxyz, float *dL_drotation,
+                                        void *stream);
+
+/* Camera intrinsics as Camera.get_calib_matrix_nerf builds them (scene/cameras.py:93-96,135-138). */
+typedef struct hg_intrinsics {
+  float fx, fy, cx, cy;
+} hg_intrinsics;
+
+/* depth_normal [3,H,W] = pad(normalize(cross(P(y,x+1)-P(y,x-1), P(y-1,x)-P(y+1,x)))) * alpha, P = the
+ * unprojected plane depth; alpha [H,W] may be NULL (plain render_normal). */
+HG_API int hg_depth_normal(const float *plane_depth, const float *alpha, int32_t H, int32_t W, hg_intrinsics K,
+                           float *out_normal, void *stream);
+
+/* dL/dplane_depth [H,W] (fully written) from dL/ddepth_normal [3,H,W]; alpha is treated as a constant
+ * (the reference detaches it). */
+HG_API int hg_depth_normal_backward(const float *plane_depth, const float *alpha, const float *dL_dnormal,
+                                    int32_t H, int32_t W, hg_intrinsics K, float *dL_dplane_depth, void *stream);
+
+/* Fused forward + backward of the single-view normal-consistency term:
+ *   loss = weight * mean_{H,W}( image_weight * sum_c | depth_normal_c - all_map_c | ),  c = 0..2,
+ * depth_normal as in hg_depth_normal with alpha = all_map[3] (detached).  image_weight [H,W] may be NULL (= 1).
+ * Writes out_loss[0]; if dL_dplane_depth / dL_dall_map are non-NULL they receive the gradient for a unit
+ * upstream gradient ([H,W] and [5,H,W]; channels 3, 4 of the latter are zero).  workspace:
+ * hg_normal_consistency_workspace_bytes(H, W) bytes. */
+HG_API size_t hg_normal_consistency_workspace_bytes(int32_t H, int32_t W);
+HG_API int hg_normal_consistency_loss(const float *plane_depth, const float *all_map, const float *image_weight,
+                                      int32_t H, int32_t W, hg_intrinsics K, float weight, float *out_loss,
+                                      float *dL_dplane_depth, float *dL_dall_map, void *workspace, void *stream);
+
+/* One Adam step over a flat fp32 parameter block of n_rows rows of row_width floats (torch.optim.Adam
+ * semantics as used by OurAdam.py: no weight decay, no amsgrad):
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+ * Row selection (the reference's `relevant`, OurAdam.py:249-337; rows not selected keep parameter AND state):
+ *   visible_mask (u8 [n_rows]) or visible_idx (int64 [n_idx], unique entries) or neither (every row, the
+ *   reference's _single_tensor_adam2 path for an empty `relevant`).  `step` is the 1-based step count of the
+ *   parameter; grad_scale multiplies g on the fly (e.g. 1/views after a SUM all-reduce).  lr / betas / eps are
+ *   doubles, as Python hands them to torch (`1 - beta2` is formed in double before it is narrowed to fp32). */
+HG_API int hg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n_rows,
+                        int32_t row_width, const uint8_t *visible_mask, const int64_t *visible_idx, int64_t n_idx,
+                        double lr, double beta1, double beta2, double eps, int32_t step, float grad_scale,
+                        void *stream);
+
+/* Mean squared distance of every point to its 3 nearest neighbours (exact).  points [N,3] -> out [N].
+ * workspace: hg_dist2_knn3_workspace_bytes(N) bytes.  No host synchronisation. */
+HG_API size_t hg_dist2_knn3_workspace_bytes(int64_t N);
+HG_API int hg_dist2_knn3(const float *points, int64_t N, float *out_mean_dist2, void *workspace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIDEGS_GEOMETRY_H */
