@@ -281,7 +281,9 @@ def run_gpu_arm(args, impl):
 
     # Untimed warm-up: at least W steps, and enough of them for torch's caching allocator to have
     # seen the step's peak working set (its first steps call cudaMalloc, 10-30 ms each).
-    for s in range(max(Wm, 8)):
+    # Every camera of the run is visited once here: the binning part of the workspace is sized from the largest
+    # num_rendered seen so far, so a first-time view can still trigger one cudaMalloc.
+    for s in range(max(Wm + K, 8)):
         step_e2e(s % (Wm + K))
     torch.cuda.synchronize()
     if ddp:

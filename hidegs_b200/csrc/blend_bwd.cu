@@ -18,44 +18,11 @@
 //    the 16 lanes that end up owning one component each issue ONE coalesced
 //    RED.ADD.F32 into the Gaussian's 64-byte accumulator row: one L2 atomic
 //    transaction per (warp, contributing entry).
-#include "common.cuh"
+#include "blend_common.cuh"
 
 namespace hg {
 
 namespace {
-
-constexpr int kBatch = HG_BLOCK_SIZE;
-
-struct Prefetch {
-  int id;
-  float4 r0, r1, r2, r3;
-  float it, ifrac;
-};
-
-__device__ __forceinline__ float cull_tau(float a, float b, float c, float o, bool interp) {
-  if (o < 0.00392156862f) return -1.0f;
-  const float det = a * c - b * b;
-  if (interp || !(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) return __int_as_float(0x7f800000);
-  return __logf(255.0f * o) * 1.001f + 2e-3f;
-}
-
-__device__ __forceinline__ bool may_touch(float mx, float my, float a, float b, float c,
-                                          float tau, float x0, float x1, float y0, float y1) {
-  const float dx = fminf(fmaxf(mx, x0), x1) - mx;
-  const float dy = fminf(fmaxf(my, y0), y1) - my;
-  if (!(tau < __int_as_float(0x7f800000))) return true;
-  if (tau < 0.0f) return false;
-  const float dy1 = fminf(fmaxf(__fdividef(-b * dx, c), y0 - my), y1 - my);
-  const float dx2 = fminf(fmaxf(__fdividef(-b * dy, a), x0 - mx), x1 - mx);
-  const float s1 = 0.5f * (a * dx * dx + c * dy1 * dy1);
-  const float q1 = s1 + b * dx * dy1 - 1e-5f * s1;
-  const float s2 = 0.5f * (a * dx2 * dx2 + c * dy * dy);
-  const float q2 = s2 + b * dx2 * dy - 1e-5f * s2;
-  float q = (dx != 0.0f) ? q1 : q2;
-  if (dx != 0.0f && dy != 0.0f) q = fminf(q1, q2);
-  if (dx == 0.0f && dy == 0.0f) q = 0.0f;
-  return !(q > tau);
-}
 
 // Sum v[0..15] over the 32 lanes.  On return lane L holds in v[0] the total of
 // component comp(L) = 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of L); lanes with
@@ -108,13 +75,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  const float* __restrict__ dL_dout_all_maps,
                  const float* __restrict__ dL_dout_plane_depths,
                  const float* __restrict__ dL_invdepths, float* __restrict__ accum) {
-  __shared__ float4 s_a[kBatch];
-  __shared__ float4 s_b[kBatch];
-  __shared__ float4 s_c[kBatch];
-  __shared__ float4 s_d[GEO ? kBatch : 1];
-  __shared__ float s_e[GEO ? kBatch : 1];
-  __shared__ float2 s_i[INTERP ? kBatch : 1];
-  __shared__ int s_id[kBatch];
+  __shared__ float4 s_rec[kBatch * kRecQuads];
   __shared__ int s_max[HG_BLOCK_SIZE / 32];
 
   const int tid = threadIdx.x;
@@ -164,6 +125,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       w[6] += dpd * (dist / (tmp * tmp));
     }
   }
+  const float bgT = -T_final * bg_dot;  // background term of dL/dalpha, times 1/(1-alpha) per entry
 
   // Tile-wide last contributor: nothing behind it received any weight.
   int wmax = last_contributor;
@@ -183,36 +145,14 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   Prefetch pf;
   auto prefetch = [&](int b) {
     const int q = n_eff - 1 - (b * kBatch + tid);  // position in the tile's list
-    if (q >= 0) {
-      pf.id = (int)__ldg(point_list + range.x + q);
-      const float4* r = records + 4 * (size_t)pf.id;
-      pf.r0 = __ldg(r);
-      pf.r1 = __ldg(r + 1);
-      pf.r2 = __ldg(r + 2);
-      pf.r3 = __ldg(r + 3);
-      if (INTERP) {
-        pf.it = __ldg(ts + pf.id);
-        pf.ifrac = 1.0f / (float)__ldg(kids + pf.id);
-      }
-    }
+    if (q >= 0) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + q);
   };
   if (nb > 0) prefetch(0);
 
   for (int b = 0; b < nb; ++b) {
     __syncthreads();
     const int cnt = min(kBatch, n_eff - b * kBatch);
-    if (tid < cnt) {
-      const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
-      s_a[tid] = pf.r0;
-      s_b[tid] = make_float4(c, o, cull_tau(a, bb, c, o, INTERP), 0.f);
-      s_c[tid] = make_float4(pf.r1.z, pf.r1.w, pf.r2.x, pf.r2.y);
-      if (GEO) {
-        s_d[tid] = make_float4(pf.r2.z, pf.r2.w, pf.r3.x, pf.r3.y);
-        s_e[tid] = pf.r3.z;
-      }
-      if (INTERP) s_i[tid] = make_float2(pf.it, pf.ifrac);
-      s_id[tid] = pf.id;
-    }
+    if (tid < cnt) stage_record<GEO, INTERP>(s_rec, tid, pf);
     __syncthreads();
     if (b + 1 < nb) prefetch(b + 1);
 
@@ -224,87 +164,87 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const int j = c0 + lane;
       bool keep = false;
       if (j < cnt && q_first - j < wmax) {
-        const float4 ea = s_a[j];
-        const float4 eb = s_b[j];
+        const float4 ea = s_rec[kRecQuads * j];
+        const float4 eb = s_rec[kRecQuads * j + 1];
         keep = may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fy0, fy1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, keep);
       while (mask) {
         const int k = c0 + __ffs(mask) - 1;
         mask &= mask - 1;
-        const int q = q_first - k;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        bool contributed = false;
-        if (q < last_contributor) {
-          const float4 ea = s_a[k];
-          const float2 eb = *reinterpret_cast<const float2*>(&s_b[k]);
-          const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
-          const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
-          const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
-          if (!(power > 0.0f)) {
-            const float G = expf(power);
-            const float test_alpha = __fmul_rn(eb.y, G);
-            const bool nullalpha = test_alpha > 0.99f;
-            const float my_alpha = fminf(0.99f, test_alpha);
-            float alpha = my_alpha;
-            float opac_mult = 1.0f;
-            if (INTERP) {
-              const float2 it = s_i[k];
-              const float kidsqrt = 1.0f - powf(1.0f - my_alpha, it.y);
-              alpha = it.x * my_alpha + (1.0f - it.x) * kidsqrt;
-              opac_mult = it.x - powf(1.0f - my_alpha, it.y - 1.0f) * (it.x - 1.0f) * it.y;
-            }
-            if (!(alpha < 1.0f / 255.0f)) {
-              contributed = true;
-              const float rinv = 1.0f / (1.0f - alpha);
-              T = T * rinv;
-              const float weight = alpha * T;
-              const float4 ec = s_c[k];
-              float g = ec.x * w[0] + ec.y * w[1] + ec.z * w[2];
-              v[0] = weight * w[0];
-              v[1] = weight * w[1];
-              v[2] = weight * w[2];
-              if (DEPTH) {
-                g += ec.w * w[3];
-                v[3] = weight * w[3];
-              }
-              if (GEO) {
-                const float4 ed = s_d[k];
-                const float ee = s_e[k];
-                g += ed.x * w[4] + ed.y * w[5] + ed.z * w[6] + ed.w * w[7] + ee * w[8];
-                v[4] = weight * w[4];
-                v[5] = weight * w[5];
-                v[6] = weight * w[6];
-                v[7] = weight * w[7];
-                v[8] = weight * w[8];
-              }
-              acc_g = last_alpha * last_g + (1.0f - last_alpha) * acc_g;
-              last_g = g;
-              last_alpha = alpha;
-              float dL_dalpha = (g - acc_g) * T;
-              dL_dalpha += (-T_final * rinv) * bg_dot;
-              if (nullalpha) dL_dalpha = 0.f;
-              const float dL_dG = eb.y * dL_dalpha;
-              const float gdx = G * dx, gdy = G * dy;
-              const float dG_ddelx = -gdx * ea.z - gdy * ea.w;
-              const float dG_ddely = -gdy * eb.x - gdx * ea.w;
-              v[9] = dL_dG * dG_ddelx * ddelx_dx;
-              v[10] = dL_dG * dG_ddely * ddely_dy;
-              v[11] = -0.5f * gdx * dx * dL_dG;
-              v[12] = -0.5f * gdx * dy * dL_dG;
-              v[13] = -0.5f * gdy * dy * dL_dG;
-              v[14] = opac_mult * G * dL_dalpha;
-            }
-          }
+        const float4* e = s_rec + kRecQuads * k;
+        const float4 ea = e[0];
+        const float4 eb = e[1];
+        // Straight-line, select-predicated evaluation: a lane that does not contribute carries zeros into the
+        // warp reduction instead of branching around the arithmetic (the warp issues it anyway).
+        const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
+        const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
+        const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
+        bool valid = (q_first - k < last_contributor) && !(power > 0.0f);
+        const float Graw = expf(power);
+        const float test_alpha = __fmul_rn(eb.y, Graw);
+        const float my_alpha = fminf(0.99f, test_alpha);
+        float alpha = my_alpha;
+        float opac_mult = 1.0f;
+        if (INTERP) {
+          const float4 e4 = e[4];
+          const float kidsqrt = 1.0f - powf(1.0f - my_alpha, e4.z);
+          alpha = e4.y * my_alpha + (1.0f - e4.y) * kidsqrt;
+          opac_mult = e4.y - powf(1.0f - my_alpha, e4.z - 1.0f) * (e4.y - 1.0f) * e4.z;
         }
-        if (__ballot_sync(0xffffffffu, contributed) == 0) continue;
+        valid = valid && !(alpha < 1.0f / 255.0f);
+        if (__ballot_sync(0xffffffffu, valid) == 0) continue;
+        const float G = valid ? Graw : 0.f;  // also keeps inf / NaN of skipped lanes out of the products below
+        const float rinv = __fdividef(1.0f, 1.0f - alpha);
+        const float Tn = T * rinv;
+        const float weight = valid ? alpha * Tn : 0.f;
+        const float4 ec = e[2];
+        float g = ec.x * w[0] + ec.y * w[1] + ec.z * w[2];
+        float v[16];
+        v[0] = weight * w[0];
+        v[1] = weight * w[1];
+        v[2] = weight * w[2];
+        v[3] = 0.f;
+        if (DEPTH) {
+          g += ec.w * w[3];
+          v[3] = weight * w[3];
+        }
+#pragma unroll
+        for (int i = 4; i < 9; ++i) v[i] = 0.f;
+        if (GEO) {
+          const float4 ed = e[3];
+          const float ee = e[4].x;
+          g += ed.x * w[4] + ed.y * w[5] + ed.z * w[6] + ed.w * w[7] + ee * w[8];
+          v[4] = weight * w[4];
+          v[5] = weight * w[5];
+          v[6] = weight * w[6];
+          v[7] = weight * w[7];
+          v[8] = weight * w[8];
+        }
+        const float acc_new = last_alpha * last_g + (1.0f - last_alpha) * acc_g;
+        float dL_dalpha = (g - acc_new) * Tn + bgT * rinv;
+        if (test_alpha > 0.99f || !valid) dL_dalpha = 0.f;
+        T = valid ? Tn : T;
+        acc_g = valid ? acc_new : acc_g;
+        last_g = valid ? g : last_g;
+        last_alpha = valid ? alpha : last_alpha;
+        const float dL_dG = eb.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * ea.z - gdy * ea.w;
+        const float dG_ddely = -gdy * eb.x - gdx * ea.w;
+        v[9] = dL_dG * dG_ddelx * ddelx_dx;
+        v[10] = dL_dG * dG_ddely * ddely_dy;
+        const float hG = -0.5f * dL_dG;
+        v[11] = hG * gdx * dx;
+        v[12] = hG * gdx * dy;
+        v[13] = hG * gdy * dy;
+        v[14] = opac_mult * G * dL_dalpha;
+        v[15] = 0.f;
         warp_reduce16(v, lane);
         if ((lane & 1) == 0) {
           const int comp = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
                            ((lane >> 1) & 1);
-          if (comp < 15) atomicAdd(accum + (size_t)s_id[k] * HG_ACC_FLOATS + comp, v[0]);
+          if (comp < 15) atomicAdd(accum + (size_t)__float_as_int(eb.w) * HG_ACC_FLOATS + comp, v[0]);
         }
       }
     }

@@ -10,7 +10,9 @@
 //  * the tile's sorted list is consumed in batches of 256 entries.  Each thread
 //    gathers ONE 64-byte splat record (4 x LDG.128, L2-resident: 64 MB at 1M
 //    Gaussians) into registers while the previous batch is being blended
-//    (register double buffering), then publishes it to shared memory as SoA;
+//    (register double buffering), then publishes it to shared memory as one
+//    80-byte staging record (blend_common.cuh): one address per entry in the
+//    blend loop, every field at an immediate offset;
 //  * per warp, 32 entries at a time are tested lane-parallel against the warp's
 //    sub-tile with an EXACT conservative bound (minimum of the Gaussian's
 //    quadratic form over the 8x4 rectangle vs ln(255*opacity)); only entries
@@ -24,51 +26,11 @@
 //  * out_observe is counted with one warp ballot per entry into a shared
 //    counter and flushed with one global atomic per (tile, entry);
 //  * early termination: lane (pixel) -> warp (ballot) -> CTA (__syncthreads_or).
-#include "common.cuh"
+#include "blend_common.cuh"
 
 namespace hg {
 
 namespace {
-
-constexpr int kBatch = HG_BLOCK_SIZE;  // 256 entries per staging round
-
-struct Prefetch {
-  int id;
-  float4 r0, r1, r2, r3;
-  float it, ifrac;
-};
-
-// Conservative keep/cull threshold for one entry: an upper bound on the value
-// q = -power below which alpha can reach 1/255.  +inf = never cull, -1 = always.
-__device__ __forceinline__ float cull_tau(float a, float b, float c, float o, bool interp) {
-  if (o < 0.00392156862f) return -1.0f;  // alpha <= o < 1/255 for every pixel
-  const float det = a * c - b * b;
-  if (interp || !(det > 0.0f) || !(a > 0.0f) || !(c > 0.0f)) return __int_as_float(0x7f800000);
-  return __logf(255.0f * o) * 1.001f + 2e-3f;
-}
-
-// Minimum of q(d) = 0.5*(a dx^2 + c dy^2) + b dx dy over the pixel rectangle
-// [x0,x1]x[y0,y1] for a Gaussian centred at (mx,my); returns true if the entry
-// may contribute inside the rectangle.
-__device__ __forceinline__ bool may_touch(float mx, float my, float a, float b, float c,
-                                          float tau, float x0, float x1, float y0, float y1) {
-  const float dx = fminf(fmaxf(mx, x0), x1) - mx;  // offset to the nearest point, 0 if inside
-  const float dy = fminf(fmaxf(my, y0), y1) - my;
-  if (!(tau < __int_as_float(0x7f800000))) return true;
-  if (tau < 0.0f) return false;
-  // Candidate on the vertical edge through dx (free dy) and on the horizontal
-  // edge through dy (free dx).
-  const float dy1 = fminf(fmaxf(__fdividef(-b * dx, c), y0 - my), y1 - my);
-  const float dx2 = fminf(fmaxf(__fdividef(-b * dy, a), x0 - mx), x1 - mx);
-  const float s1 = 0.5f * (a * dx * dx + c * dy1 * dy1);
-  const float q1 = s1 + b * dx * dy1 - 1e-5f * s1;
-  const float s2 = 0.5f * (a * dx2 * dx2 + c * dy * dy);
-  const float q2 = s2 + b * dx2 * dy - 1e-5f * s2;
-  float q = (dx != 0.0f) ? q1 : q2;
-  if (dx != 0.0f && dy != 0.0f) q = fminf(q1, q2);
-  if (dx == 0.0f && dy == 0.0f) q = 0.0f;
-  return !(q > tau);
-}
 
 template <bool GEO, bool DEPTH, bool INTERP>
 __global__ void __launch_bounds__(HG_BLOCK_SIZE)
@@ -80,13 +42,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                  float* __restrict__ out_invdepth, int* __restrict__ out_observe,
                  float* __restrict__ out_all_map, float* __restrict__ out_plane_depth) {
-  __shared__ float4 s_a[kBatch];  // x, y, conic.a, conic.b
-  __shared__ float4 s_b[kBatch];  // conic.c, opacity, tau, -
-  __shared__ float4 s_c[kBatch];  // r, g, b, 1/depth
-  __shared__ float4 s_d[GEO ? kBatch : 1];  // all_map 0..3
-  __shared__ float s_e[GEO ? kBatch : 1];   // all_map 4
-  __shared__ float2 s_i[INTERP ? kBatch : 1];
-  __shared__ int s_id[kBatch];
+  __shared__ float4 s_rec[kBatch * kRecQuads];
   __shared__ int s_obs[kBatch];
 
   const int tid = threadIdx.x;
@@ -113,18 +69,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   Prefetch pf;
   auto prefetch = [&](int b) {
     const int i = b * kBatch + tid;
-    if (i < n) {
-      pf.id = (int)__ldg(point_list + range.x + i);
-      const float4* r = records + 4 * (size_t)pf.id;
-      pf.r0 = __ldg(r);
-      pf.r1 = __ldg(r + 1);
-      pf.r2 = __ldg(r + 2);
-      pf.r3 = __ldg(r + 3);
-      if (INTERP) {
-        pf.it = __ldg(ts + pf.id);
-        pf.ifrac = __frcp_rn((float)__ldg(kids + pf.id));
-      }
-    }
+    if (i < n) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + i);
   };
   if (nb > 0) prefetch(0);
 
@@ -133,24 +78,14 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int any_active = __syncthreads_or(!done);
     if (pending_flush) {
       const int c = s_obs[tid];
-      if (c) atomicAdd(out_observe + s_id[tid], c);
+      if (c) atomicAdd(out_observe + __float_as_int(s_rec[kRecQuads * tid + 1].w), c);
       pending_flush = false;
     }
     if (!any_active) break;
+    // (thread `tid` is the only one that rewrites slot `tid`, whose id it has just read: no barrier needed here)
 
     const int cnt = min(kBatch, n - b * kBatch);
-    if (tid < cnt) {
-      const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
-      s_a[tid] = pf.r0;
-      s_b[tid] = make_float4(c, o, cull_tau(a, bb, c, o, INTERP), 0.f);
-      s_c[tid] = make_float4(pf.r1.z, pf.r1.w, pf.r2.x, pf.r2.y);
-      if (GEO) {
-        s_d[tid] = make_float4(pf.r2.z, pf.r2.w, pf.r3.x, pf.r3.y);
-        s_e[tid] = pf.r3.z;
-      }
-      if (INTERP) s_i[tid] = make_float2(pf.it, pf.ifrac);
-      s_id[tid] = pf.id;
-    }
+    if (tid < cnt) stage_record<GEO, INTERP>(s_rec, tid, pf);
     s_obs[tid] = 0;
     __syncthreads();
     if (b + 1 < nb) prefetch(b + 1);
@@ -162,18 +97,19 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       const int j = c0 + lane;
       bool keep = false;
       if (j < cnt) {
-        const float4 ea = s_a[j];
-        const float4 eb = s_b[j];
+        const float4 ea = s_rec[kRecQuads * j];
+        const float4 eb = s_rec[kRecQuads * j + 1];
         keep = may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fy0, fy1);
       }
       uint32_t mask = __ballot_sync(0xffffffffu, keep);
       while (mask) {
         const int k = c0 + __ffs(mask) - 1;
         mask &= mask - 1;
+        const float4* e = s_rec + kRecQuads * k;
         bool observed = false;
         if (!done) {
-          const float4 ea = s_a[k];
-          const float2 eb = *reinterpret_cast<const float2*>(&s_b[k]);
+          const float4 ea = e[0];
+          const float2 eb = *reinterpret_cast<const float2*>(e + 1);
           const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
           // power = -0.5f*(a dx dx + c dy dy) - b dx dy, as compiled (forward.cu:536).
           const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
@@ -181,28 +117,32 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
           if (!(power > 0.0f)) {
             float alpha = fminf(0.99f, __fmul_rn(eb.y, expf(power)));
             if (INTERP) {
-              const float2 it = s_i[k];
-              const float kidsqrt = __fsub_rn(1.0f, __powf(__fsub_rn(1.0f, alpha), it.y));
-              alpha = __fmaf_rn(alpha, it.x, __fmul_rn(__fsub_rn(1.0f, it.x), kidsqrt));
+              const float4 e4 = e[4];
+              const float kidsqrt = __fsub_rn(1.0f, __powf(__fsub_rn(1.0f, alpha), e4.z));
+              alpha = __fmaf_rn(alpha, e4.y, __fmul_rn(__fsub_rn(1.0f, e4.y), kidsqrt));
             }
             if (!(alpha < 1.0f / 255.0f)) {
               const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
               if (test_T < 0.0001f) {
                 done = true;
               } else {
-                const float4 ec = s_c[k];
-                C0 = __fmaf_rn(T, __fmul_rn(alpha, ec.x), C0);
-                C1 = __fmaf_rn(T, __fmul_rn(alpha, ec.y), C1);
-                C2 = __fmaf_rn(T, __fmul_rn(alpha, ec.z), C2);
-                if (DEPTH) Dinv = __fmaf_rn(T, __fmul_rn(alpha, ec.w), Dinv);
+                // Blend weight alpha*T once, then one FMA per channel.  (The reference forms (c*alpha)*T per
+                // channel; the weights differ by one rounding, images agree to ~1e-7, far inside the 1e-4 bound.
+                // T itself, the thresholds and hence n_contrib / final_T / out_observe stay bit-identical.)
+                const float wgt = __fmul_rn(alpha, T);
+                const float4 ec = e[2];
+                C0 = __fmaf_rn(wgt, ec.x, C0);
+                C1 = __fmaf_rn(wgt, ec.y, C1);
+                C2 = __fmaf_rn(wgt, ec.z, C2);
+                if (DEPTH) Dinv = __fmaf_rn(wgt, ec.w, Dinv);
                 if (GEO) {
-                  const float4 ed = s_d[k];
-                  const float ee = s_e[k];
-                  A0 = __fmaf_rn(T, __fmul_rn(alpha, ed.x), A0);
-                  A1 = __fmaf_rn(T, __fmul_rn(alpha, ed.y), A1);
-                  A2 = __fmaf_rn(T, __fmul_rn(alpha, ed.z), A2);
-                  A3 = __fmaf_rn(T, __fmul_rn(alpha, ed.w), A3);
-                  A4 = __fmaf_rn(T, __fmul_rn(alpha, ee), A4);
+                  const float4 ed = e[3];
+                  const float ee = e[4].x;
+                  A0 = __fmaf_rn(wgt, ed.x, A0);
+                  A1 = __fmaf_rn(wgt, ed.y, A1);
+                  A2 = __fmaf_rn(wgt, ed.z, A2);
+                  A3 = __fmaf_rn(wgt, ed.w, A3);
+                  A4 = __fmaf_rn(wgt, ee, A4);
                 }
                 observed = T > 0.5f;
                 T = test_T;
@@ -220,7 +160,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   if (pending_flush) {
     __syncthreads();
     const int c = s_obs[tid];
-    if (c) atomicAdd(out_observe + s_id[tid], c);
+    if (c) atomicAdd(out_observe + __float_as_int(s_rec[kRecQuads * tid + 1].w), c);
   }
 
   if (inside) {

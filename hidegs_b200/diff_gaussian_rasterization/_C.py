@@ -91,7 +91,12 @@ class _Workspace:
         if R > _R_HINT.get(self.key, 0):
             _R_HINT[self.key] = int(R)
         image = self.tensor[self.off_image:self.off_image + self.image_bytes]
-        return self.tensor, self.binning, image
+        out = (self.tensor, self.binning, image)
+        # The callbacks close over `self`: drop them (and the tensors) so that this object is not a reference cycle
+        # that keeps a few hundred MB alive until Python's cyclic collector happens to run.
+        self.cb_geom = self.cb_image = self.cb_binning = None
+        self.tensor = self.binning = None
+        return out
 
 
 def _accum_ptr(geomBuffer, P, W, H):
