@@ -34,7 +34,8 @@ class RasterLayout(ctypes.Structure):
     """struct hg_raster_layout (include/hidegs_raster.h)."""
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "geom_bytes", "depths", "tiles_touched", "point_offsets", "rects", "cov3D", "clamped", "records",
-        "scan_temp", "scan_temp_bytes",
+        "scan_temp", "scan_temp_bytes", "slot_ids", "depth_sorted", "depth_order", "offsets_sorted", "depth_sort_temp",
+        "depth_sort_temp_bytes",
         "image_bytes", "final_T", "n_contrib", "ranges",
         "binning_bytes", "keys_unsorted", "keys", "vals_unsorted", "vals", "sort_temp", "sort_temp_bytes")]
 
@@ -42,7 +43,7 @@ class RasterLayout(ctypes.Structure):
 # Every symbol include/hidegs_raster.h declares (checked by the CPU test-suite).
 EXPORTED_SYMBOLS = (
     "hg_raster_layout_query", "hg_raster_forward", "hg_raster_backward_accum_bytes", "hg_raster_backward",
-    "hg_mark_visible", "hg_launch_count", "hg_reset_launch_count", "hg_last_error", "hg_version",
+    "hg_mark_visible", "hg_raster_debug_keys", "hg_launch_count", "hg_reset_launch_count", "hg_last_error", "hg_version",
     "hg_profile_enable", "hg_profile_collect",
 )
 
@@ -72,6 +73,8 @@ def lib():
     L.hg_raster_backward.argtypes = [ctypes.POINTER(RasterInputs), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hg_raster_backward.restype = ctypes.c_int
+    L.hg_raster_debug_keys.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.hg_raster_debug_keys.restype = ctypes.c_int
     L.hg_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     L.hg_mark_visible.restype = ctypes.c_int
     L.hg_launch_count.argtypes = []

@@ -3,9 +3,10 @@
 // State layout (our own; opaque to callers, see hg_raster_layout):
 //   geometry buffer : depths f32[P] | tiles_touched u32[P] | point_offsets u32[P]
 //                     | rects u32[P,2] (packed tile bounds) | cov3D f32[P,6]
-//                     | clamped u8[P] | records f32[P,16] | scan temp
+//                     | clamped u8[P] | records f32[P,16] | scan temp | slot_ids u32[P]
+//                     | depth_sorted u32[P] | depth_order u32[P] | offsets_sorted u32[P] | depth-sort temp
 //   image buffer    : final_T f32[HW] | n_contrib u32[HW] | ranges u32[T,2]
-//   binning buffer  : keys_unsorted u64[R] | keys u64[R] | vals_unsorted u32[R]
+//   binning buffer  : tile ids u32[R] (depth order) | tile ids u32[R] (sorted) | vals_unsorted u32[R]
 //                     | vals u32[R] | sort temp
 //
 // Splat record (64 B, one per rendered slot, written by preprocess, gathered by
@@ -62,6 +63,11 @@ struct GeomState {
   uint8_t* clamped;
   float4* records;
   char* scan_temp;
+  uint32_t* slot_ids;
+  uint32_t* depth_sorted;
+  uint32_t* depth_order;
+  uint32_t* offsets_sorted;
+  char* depth_sort_temp;
 };
 struct ImageState {
   float* final_T;
@@ -69,8 +75,8 @@ struct ImageState {
   uint2* ranges;
 };
 struct BinState {
-  uint64_t* keys_unsorted;
-  uint64_t* keys;
+  uint32_t* keys_unsorted;  // tile ids, depth order
+  uint32_t* keys;           // tile ids, sorted
   uint32_t* vals_unsorted;
   uint32_t* vals;
   char* sort_temp;
@@ -78,6 +84,7 @@ struct BinState {
 
 size_t scan_temp_bytes(int P);
 size_t sort_temp_bytes(int64_t R);
+size_t depth_sort_temp_bytes(int P);
 
 static inline GeomState geom_from(char* base, const hg_raster_layout& L) {
   GeomState g;
@@ -89,6 +96,11 @@ static inline GeomState geom_from(char* base, const hg_raster_layout& L) {
   g.clamped = (uint8_t*)(base + L.clamped);
   g.records = (float4*)(base + L.records);
   g.scan_temp = base + L.scan_temp;
+  g.slot_ids = (uint32_t*)(base + L.slot_ids);
+  g.depth_sorted = (uint32_t*)(base + L.depth_sorted);
+  g.depth_order = (uint32_t*)(base + L.depth_order);
+  g.offsets_sorted = (uint32_t*)(base + L.offsets_sorted);
+  g.depth_sort_temp = base + L.depth_sort_temp;
   return g;
 }
 static inline ImageState image_from(char* base, const hg_raster_layout& L) {
@@ -100,8 +112,8 @@ static inline ImageState image_from(char* base, const hg_raster_layout& L) {
 }
 static inline BinState bin_from(char* base, const hg_raster_layout& L) {
   BinState b;
-  b.keys_unsorted = (uint64_t*)(base + L.keys_unsorted);
-  b.keys = (uint64_t*)(base + L.keys);
+  b.keys_unsorted = (uint32_t*)(base + L.keys_unsorted);
+  b.keys = (uint32_t*)(base + L.keys);
   b.vals_unsorted = (uint32_t*)(base + L.vals_unsorted);
   b.vals = (uint32_t*)(base + L.vals);
   b.sort_temp = base + L.sort_temp;
@@ -125,9 +137,13 @@ int launch_preprocess_fwd(const hg_raster_inputs& in, const GeomState& g, int* r
                           int* out_observe, dim3 grid, float focal_x, float focal_y,
                           cudaStream_t stream);
 int launch_scan(const GeomState& g, int P, size_t temp_bytes, cudaStream_t stream, bool debug);
+int launch_depth_sort(const GeomState& g, int P, size_t temp_bytes, cudaStream_t stream, bool debug);
+int launch_debug_keys(int P, const GeomState& g, const BinState& b, const int* radii, int R,
+                      dim3 grid, uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys_sorted,
+                      cudaStream_t stream);
 int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinState& b,
                    const ImageState& img, const int* radii, int R, dim3 grid, size_t sort_bytes,
-                   cudaStream_t stream);
+                   size_t depth_temp_bytes, cudaStream_t stream);
 int launch_blend_fwd(const hg_raster_inputs& in, const GeomState& g, const BinState& b,
                      const ImageState& img, dim3 grid, float focal_x, float focal_y,
                      float* out_color, float* out_invdepth, int* out_observe, float* out_all_map,

@@ -16,6 +16,7 @@
 // into shared memory and read back transposed; results go out as one 64-byte
 // splat record per slot plus the SoA arrays the binning stage reads.
 #include "common.cuh"
+#include "sh_stage.cuh"
 
 namespace hg {
 
@@ -73,34 +74,6 @@ __device__ __forceinline__ void eval_sh(int deg, const F& sh, float dx, float dy
   }
 }
 
-
-// Warp-cooperative, coalesced load of 32 consecutive SH rows into shared memory
-// (row-major, odd stride).  ROW > 0 fixes the row length at compile time.
-template <int ROW>
-__device__ __forceinline__ void stage_sh_rows(const float* __restrict__ shs, size_t base,
-                                              size_t total, int row_rt, int lane, float* dst) {
-  const int row = ROW > 0 ? ROW : row_rt;
-  const int stride = row | 1;
-  const int nfloat = 32 * row;  // multiple of 4
-  for (int i = lane * 4; i < nfloat; i += 128) {
-    const size_t gi = base + i;
-    float4 val;
-    if (gi + 3 < total) {
-      val = __ldg((const float4*)(shs + gi));
-    } else {
-      val.x = gi < total ? __ldg(shs + gi) : 0.f;
-      val.y = gi + 1 < total ? __ldg(shs + gi + 1) : 0.f;
-      val.z = gi + 2 < total ? __ldg(shs + gi + 2) : 0.f;
-      val.w = 0.f;
-    }
-    const float e[4] = {val.x, val.y, val.z, val.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int f = i + k;
-      dst[(f / row) * stride + (f % row)] = e[k];
-    }
-  }
-}
 
 // Sigma = (S R)^T (S R) in the reference's exact operation order
 // (forward.cu:181-215; PTX fma chains + the ptxas fusions of the quaternion
@@ -193,7 +166,7 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
                       int* __restrict__ out_observe, float* __restrict__ depths,
                       uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
                       float* __restrict__ cov3Ds, uint8_t* __restrict__ clamped,
-                      float4* __restrict__ records) {
+                      float4* __restrict__ records, uint32_t* __restrict__ slot_ids) {
   __shared__ float s_sh[kWarps][32 * kShStrideMax];
 
   const int t_idx = blockIdx.x * kThreads + threadIdx.x;
@@ -216,6 +189,9 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
     radii[t_idx] = 0;
     tiles_touched[t_idx] = 0;
     out_observe[t_idx] = 0;
+    // depth doubles as the key of the slot sort: culled slots sort behind every visible one
+    reinterpret_cast<uint32_t*>(depths)[t_idx] = 0xFFFFFFFFu;
+    slot_ids[t_idx] = (uint32_t)t_idx;
 
     px = __ldg(means3D + 3 * (size_t)r_idx);
     py = __ldg(means3D + 3 * (size_t)r_idx + 1);
@@ -331,8 +307,8 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
         const size_t base = (size_t)warp_first * row;         // float index, multiple of 4
         const size_t total = (size_t)N * row;
         float* dst = s_sh[warp];
-        if (row == 48) stage_sh_rows<48>(shs, base, total, row, lane, dst);
-        else stage_sh_rows<0>(shs, base, total, row, lane, dst);
+        if (row == 48) stage_sh_rows<48>(shs, base, total, row, lane, dst, any);  // rows of culled slots are skipped
+        else stage_sh_rows<0>(shs, base, total, row, lane, dst, any);
         __syncwarp();
         if (alive) {
           const float cx = __ldg(campos), cy = __ldg(campos + 1), cz = __ldg(campos + 2);
@@ -408,7 +384,7 @@ int launch_preprocess_fwd(const hg_raster_inputs& in, const GeomState& g, int* r
       in.scale_modifier, in.rotations, in.opacities, in.shs, in.cov3D_precomp, in.colors_precomp,
       in.all_map, in.viewmatrix, in.projmatrix, in.campos, in.W, in.H, in.tan_fovx, in.tan_fovy,
       focal_x, focal_y, grid.x, grid.y, radii, out_observe, g.depths, g.tiles_touched, g.rects,
-      g.cov3D, g.clamped, g.records);
+      g.cov3D, g.clamped, g.records, g.slot_ids);
   HG_POST_LAUNCH(in.debug, stream, "preprocess_fwd");
   return HG_OK;
 }

@@ -16,12 +16,15 @@
 // gradients are zeroed and (1-t) x mean gradient is pushed to the parent
 // (backward.cu:459-495).
 #include "common.cuh"
+#include "sh_stage.cuh"
 
 namespace hg {
 
 namespace {
 
 constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr int kShStrideMax = 48 + 1;  // M <= 16 coefficients x 3 channels, odd stride
 
 __device__ __forceinline__ void store_or_add3(float* dst, float a, float b, float c, bool atomic) {
   if (atomic) {
@@ -53,14 +56,33 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
                       float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D,
                       float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                       float* __restrict__ dL_drotations, float* __restrict__ dL_dall_map) {
+  // SH rows (read AND written, 2 x 192 B per Gaussian at degree 3: 60 % of this kernel's traffic) move through a
+  // per-warp shared-memory tile with coalesced 128-bit accesses when the warp's rows are contiguous (no index
+  // remap); each thread then works on its own row of the tile.
+  __shared__ float s_sh[kWarps][32 * kShStrideMax];
   const int t_idx = blockIdx.x * kThreads + threadIdx.x;
-  if (t_idx >= P) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_range = t_idx < P;
+  const int row = 3 * M;
+  const bool alive = in_range && radii[t_idx] > 0;
+  const uint32_t alive_mask = __ballot_sync(0xffffffffu, alive);
+  const bool staged = shs != nullptr && indices == nullptr && (row & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dsh)) & 15) == 0;
+  float* const tile = s_sh[warp];
+  const size_t warp_base = (size_t)(blockIdx.x * kThreads + warp * 32) * row;
+  const size_t sh_total = (size_t)P * row;
+  if (staged && alive_mask) {
+    if (row == 48) stage_sh_rows<48>(shs, warp_base, sh_total, row, lane, tile, alive_mask);
+    else stage_sh_rows<0>(shs, warp_base, sh_total, row, lane, tile, alive_mask);
+    __syncwarp();
+  }
+  do {  // single-trip block: `break` = this thread is done (it still joins the cooperative store below)
+  if (!in_range) break;
   const int idx = indices ? __ldg(indices + t_idx) : t_idx;
   const size_t g = (size_t)idx;
-  const int row = 3 * M;
 
-  if (!(radii[t_idx] > 0)) {
-    if (prezeroed) return;
+  if (!alive) {
+    if (prezeroed) break;
     // Culled slot: its gradient rows are all zero.
     dL_dmeans2D[3 * g] = dL_dmeans2D[3 * g + 1] = dL_dmeans2D[3 * g + 2] = 0.f;
     if (dL_dconic) dL_dconic[4 * g] = dL_dconic[4 * g + 1] = dL_dconic[4 * g + 2] = dL_dconic[4 * g + 3] = 0.f;
@@ -70,12 +92,13 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
     dL_dmeans3D[3 * g] = dL_dmeans3D[3 * g + 1] = dL_dmeans3D[3 * g + 2] = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) dL_dcov3D[6 * g + i] = 0.f;
-    for (int i = 0; i < row; ++i) dL_dsh[g * row + i] = 0.f;
+    if (!staged)
+      for (int i = 0; i < row; ++i) dL_dsh[g * row + i] = 0.f;
     dL_dscales[3 * g] = dL_dscales[3 * g + 1] = dL_dscales[3 * g + 2] = 0.f;
     dL_drotations[4 * g] = dL_drotations[4 * g + 1] = dL_drotations[4 * g + 2] = dL_drotations[4 * g + 3] = 0.f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) dL_dall_map[5 * g + i] = 0.f;
-    return;
+    break;
   }
 
   // ---- accumulator row --------------------------------------------------------
@@ -228,18 +251,18 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
 
   // ---- SH backward (backward.cu:23-142) -----------------------------------------
   if (shs) {
-    float* out = dL_dsh + g * row;
+    float* out = staged ? tile + lane * (row | 1) : dL_dsh + g * row;
     const float ox = mx - __ldg(campos), oy = my - __ldg(campos + 1), oz = mz - __ldg(campos + 2);
     const float len = sqrtf(ox * ox + oy * oy + oz * oz);
     const float x = ox / len, y = oy / len, z = oz / len;
     const uint8_t cb = clamped[t_idx];
     const float dr = (cb & 1) ? 0.f : dcol[0], dg = (cb & 2) ? 0.f : dcol[1],
                 db = (cb & 4) ? 0.f : dcol[2];
-    const float* sh = shs + g * row;
+    const float* sh = staged ? tile + lane * (row | 1) : shs + g * row;
     float basis[16];
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-    // s(k) = <sh[k], dL/dRGB>
-    auto s = [&](int k) { return __ldg(sh + 3 * k) * dr + __ldg(sh + 3 * k + 1) * dg + __ldg(sh + 3 * k + 2) * db; };
+    // s(k) = <sh[k], dL/dRGB>   (every s(k) is taken before the row is overwritten with the gradient below)
+    auto s = [&](int k) { return sh[3 * k] * dr + sh[3 * k + 1] * dg + sh[3 * k + 2] * db; };
     basis[0] = SH_C0;
     int nb = 1;
     if (D > 0) {
@@ -290,7 +313,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
     const float keep = has_parent ? 0.f : 1.f;
     for (int k = 0; k < M; ++k) {
       const float bk = (k < nb) ? basis[k] * keep : 0.f;
-      if (k < nb || !prezeroed) {
+      if (k < nb || !prezeroed || staged) {
         out[3 * k] = bk * dr;
         out[3 * k + 1] = bk * dg;
         out[3 * k + 2] = bk * db;
@@ -368,6 +391,11 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
     dL_drotations[4 * g + 1] = dqx;
     dL_drotations[4 * g + 2] = dqy;
     dL_drotations[4 * g + 3] = dqz;
+  }
+  } while (0);
+  if (staged && (alive_mask || !prezeroed)) {
+    __syncwarp();
+    unstage_sh_rows(dL_dsh, warp_base, sh_total, row, lane, tile, alive_mask, !prezeroed);
   }
 }
 

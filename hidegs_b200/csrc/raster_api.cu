@@ -51,6 +51,24 @@ struct StageTimer {
   }
 };
 
+// Pinned 4-byte landing slot for num_rendered and the event that signals its arrival (one per host thread and device).
+struct HostSlot { uint32_t* value = nullptr; cudaEvent_t ready = nullptr; int device = -1; };
+static HostSlot* host_slot() {
+  static thread_local HostSlot slots[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { set_error("cudaGetDevice failed"); return nullptr; }
+  HostSlot& s = slots[dev];
+  if (s.device != dev) {
+    if (cudaHostAlloc((void**)&s.value, 64, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("allocating the pinned num_rendered slot failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return nullptr;
+    }
+    s.device = dev;
+  }
+  return &s;
+}
+
 static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_layout* L) {
   memset(L, 0, sizeof(*L));
   const size_t p = (size_t)(P > 0 ? P : 0);
@@ -73,6 +91,12 @@ static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_la
   L->records = take(p * HG_REC_FLOATS * 4);
   L->scan_temp_bytes = p ? scan_temp_bytes((int)p) : 0;
   L->scan_temp = take(L->scan_temp_bytes);
+  L->slot_ids = take(p * 4);
+  L->depth_sorted = take(p * 4);
+  L->depth_order = take(p * 4);
+  L->offsets_sorted = take(p * 4);
+  L->depth_sort_temp_bytes = p ? depth_sort_temp_bytes((int)p) : 0;
+  L->depth_sort_temp = take(L->depth_sort_temp_bytes);
   L->geom_bytes = off + kAlign;
   // image
   off = 0;
@@ -82,8 +106,8 @@ static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_la
   L->image_bytes = off + kAlign;
   // binning
   off = 0;
-  L->keys_unsorted = take(r * 8);
-  L->keys = take(r * 8);
+  L->keys_unsorted = take(r * 4);
+  L->keys = take(r * 4);
   L->vals_unsorted = take(r * 4);
   L->vals = take(r * 4);
   L->sort_temp_bytes = r ? sort_temp_bytes((int64_t)r) : 0;
@@ -198,18 +222,24 @@ int hg_raster_forward(const hg_raster_inputs* in, hg_alloc_fn geom_alloc, void* 
     rc = launch_preprocess_fwd(*in, g, radii, out_observe, grid, focal_x, focal_y, stream);
   }
   if (rc) return rc;
+  // R is part of the API contract (returned to Python as an int,
+  // diff_gaussian_rasterization/__init__.py:89-93), so one sync is unavoidable.  The depth sort of the slots does
+  // not depend on R: it is queued behind the copy and runs while the host waits / allocates the binning buffer.
+  // (pinned landing slot + event per host thread and device: a pageable destination would make the "async" copy block)
+  HostSlot* slot = host_slot();
+  if (!slot) return HG_ERR_CUDA;
   {
     StageTimer t(HG_STAGE_SCAN, stream);
     rc = launch_scan(g, in->P, L.scan_temp_bytes, stream, in->debug != 0);
+    if (rc) return rc;
+    HG_CUDA_TRY(cudaMemcpyAsync(slot->value, g.point_offsets + in->P - 1, sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, stream));
+    HG_CUDA_TRY(cudaEventRecord(slot->ready, stream));
+    rc = launch_depth_sort(g, in->P, L.depth_sort_temp_bytes, stream, in->debug != 0);
   }
+  HG_CUDA_TRY(cudaEventSynchronize(slot->ready));
   if (rc) return rc;
-
-  // R is part of the API contract (returned to Python as an int,
-  // diff_gaussian_rasterization/__init__.py:89-93), so one sync is unavoidable.
-  uint32_t R = 0;
-  HG_CUDA_TRY(cudaMemcpyAsync(&R, g.point_offsets + in->P - 1, sizeof(uint32_t),
-                              cudaMemcpyDeviceToHost, stream));
-  HG_CUDA_TRY(cudaStreamSynchronize(stream));
+  const uint32_t R = *slot->value;
   *num_rendered = (int)R;
 
   BinState b{};
@@ -224,7 +254,7 @@ int hg_raster_forward(const hg_raster_inputs* in, hg_alloc_fn geom_alloc, void* 
     b = bin_from(align_ptr(bin_raw, kAlign), LB);
     {
       StageTimer t(HG_STAGE_BINNING, stream);
-      rc = launch_binning(*in, g, b, img, radii, (int)R, grid, LB.sort_temp_bytes, stream);
+      rc = launch_binning(*in, g, b, img, radii, (int)R, grid, LB.sort_temp_bytes, L.depth_sort_temp_bytes, stream);
     }
     if (rc) return rc;
   }
@@ -282,6 +312,27 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
                                dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
                                dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
                                dL_dall_map, stream);
+}
+
+int hg_raster_debug_keys(int32_t P, int32_t W, int32_t H, int32_t R, const int32_t* radii, const char* geom_buffer,
+                         const char* binning_buffer, uint64_t* keys_unsorted, uint32_t* vals_unsorted,
+                         uint64_t* keys_sorted, void* stream_) {
+  g_err[0] = 0;
+  if (P < 0 || W <= 0 || H <= 0 || R < 0) {
+    set_error("hg_raster_debug_keys: bad sizes");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (P == 0 || R == 0) return HG_OK;
+  if (!radii || !geom_buffer || !binning_buffer) {
+    set_error("hg_raster_debug_keys: a mandatory pointer is NULL");
+    return HG_ERR_INVALID_ARG;
+  }
+  hg_raster_layout L;
+  fill_layout(P, W, H, R, &L);
+  GeomState g = geom_from(align_ptr(const_cast<char*>(geom_buffer), kAlign), L);
+  BinState b = bin_from(align_ptr(const_cast<char*>(binning_buffer), kAlign), L);
+  const dim3 grid((W + HG_BLOCK_X - 1) / HG_BLOCK_X, (H + HG_BLOCK_Y - 1) / HG_BLOCK_Y, 1);
+  return launch_debug_keys(P, g, b, radii, R, grid, keys_unsorted, vals_unsorted, keys_sorted, (cudaStream_t)stream_);
 }
 
 void hg_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }

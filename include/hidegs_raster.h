@@ -104,7 +104,7 @@ typedef struct hg_raster_inputs {
 typedef struct hg_raster_layout {
   /* geometry buffer */
   size_t geom_bytes;
-  size_t depths;        /* f32[P]                                         */
+  size_t depths;        /* f32[P]; culled slots hold the bit pattern 0xFFFFFFFF (they sort last) */
   size_t tiles_touched; /* u32[P]                                         */
   size_t point_offsets; /* u32[P] inclusive prefix sum                    */
   size_t rects;         /* u32[P,2] tile bounds: minx|miny<<16, maxx|maxy<<16 */
@@ -113,6 +113,12 @@ typedef struct hg_raster_layout {
   size_t records;       /* f32[P,16] splat record, see DESIGN.md          */
   size_t scan_temp;
   size_t scan_temp_bytes;
+  size_t slot_ids;       /* u32[P] 0..P-1                                  */
+  size_t depth_sorted;   /* u32[P] depth bits ascending (stable)           */
+  size_t depth_order;    /* u32[P] slot of the i-th nearest splat          */
+  size_t offsets_sorted; /* u32[P] inclusive sum of tiles_touched in depth order */
+  size_t depth_sort_temp;
+  size_t depth_sort_temp_bytes;
   /* image buffer */
   size_t image_bytes;
   size_t final_T;   /* f32[H*W]                                           */
@@ -120,9 +126,9 @@ typedef struct hg_raster_layout {
   size_t ranges;    /* u32[T,2]                                           */
   /* binning buffer (sized for R instances) */
   size_t binning_bytes;
-  size_t keys_unsorted; /* u64[R]                                         */
-  size_t keys;          /* u64[R]                                         */
-  size_t vals_unsorted; /* u32[R]                                         */
+  size_t keys_unsorted; /* u32[R] tile id of every instance, emitted in depth order */
+  size_t keys;          /* u32[R] tile ids after the stable sort          */
+  size_t vals_unsorted; /* u32[R] slot of every instance, depth order     */
   size_t vals;          /* u32[R] == reference point_list                 */
   size_t sort_temp;
   size_t sort_temp_bytes;
@@ -177,6 +183,18 @@ HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
                        float *dL_dall_map,   /* [N,5] */
                        void *stream);
 
+/* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it sorts the
+ * visible splats by depth once (32-bit keys, P elements), emits the tile instances in that order and then sorts
+ * them stably by tile id alone (getHigherMsb(tiles) bits) -- same final order as the reference's 45..47-bit sort,
+ * ~5x less sort traffic.  This call reconstructs, from the buffers of a finished forward, what the reference holds:
+ *   keys_unsorted [R] u64, vals_unsorted [R] u32   duplicateWithKeys output (ascending slot, y-major / x-minor)
+ *   keys_sorted   [R] u64                          binningState.point_list_keys after the sort
+ * (any of the three may be NULL).  `radii` as returned by the forward. */
+HG_API int hg_raster_debug_keys(int32_t P, int32_t W, int32_t H, int32_t R, const int32_t *radii,
+                                const char *geom_buffer, const char *binning_buffer,
+                                uint64_t *keys_unsorted, uint32_t *vals_unsorted, uint64_t *keys_sorted,
+                                void *stream);
+
 /* Frustum test of rasterizer_impl.cu:54-66 (present[i] = p_view.z > 0.2). */
 HG_API int hg_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,
                     const float *projmatrix, uint8_t *present, void *stream);
@@ -194,8 +212,8 @@ HG_API void hg_reset_launch_count(void);
  * record.  Used by bench.py for the live roofline numbers. */
 enum hg_stage {
   HG_STAGE_PREPROCESS_FWD = 0,
-  HG_STAGE_SCAN = 1,
-  HG_STAGE_BINNING = 2, /* key emit + radix sort + tile ranges */
+  HG_STAGE_SCAN = 1,    /* tile-count scan + depth sort of the slots (overlaps the host's read of R) */
+  HG_STAGE_BINNING = 2, /* depth-order scan + instance emit + tile sort + tile ranges */
   HG_STAGE_BLEND_FWD = 3,
   HG_STAGE_ACCUM_ZERO = 4,
   HG_STAGE_BLEND_BWD = 5,

@@ -105,10 +105,20 @@ def our_state(fwd_out, P, W, H):
     st["n_contrib"] = view(img, L.n_contrib, 4 * W * H, torch.int32)
     st["ranges"] = view(img, L.ranges, 8 * T, torch.int32).view(T, 2)
     if R > 0:
-        st["keys_unsorted"] = view(binning, L.keys_unsorted, 8 * R, torch.int64)
-        st["keys"] = view(binning, L.keys, 8 * R, torch.int64)
-        st["vals_unsorted"] = view(binning, L.vals_unsorted, 4 * R, torch.int32)
         st["point_list"] = view(binning, L.vals, 4 * R, torch.int32)
+        st["tile_ids_sorted"] = view(binning, L.keys, 4 * R, torch.int32)
+        # The library sorts (depth, then tile) in two stages and never holds the reference's 64-bit tile|depth keys;
+        # hg_raster_debug_keys rebuilds them from its buffers (see include/hidegs_raster.h).
+        dev = geom.device
+        st["keys_unsorted"] = torch.empty(R, dtype=torch.int64, device=dev)
+        st["vals_unsorted"] = torch.empty(R, dtype=torch.int32, device=dev)
+        st["keys"] = torch.empty(R, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().hg_raster_debug_keys(P, W, H, R, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                                                 st["keys_unsorted"].data_ptr(), st["vals_unsorted"].data_ptr(),
+                                                 st["keys"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "hg_raster_debug_keys")
+        torch.cuda.synchronize(dev)
     return st
 
 

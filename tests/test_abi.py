@@ -34,11 +34,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_layout_query_is_consistent():
     L = _lib.layout(1000, 1920, 1080, 5000)
-    offs = [L.depths, L.tiles_touched, L.point_offsets, L.rects, L.cov3D, L.clamped, L.records, L.scan_temp]
+    offs = [L.depths, L.tiles_touched, L.point_offsets, L.rects, L.cov3D, L.clamped, L.records, L.scan_temp, L.slot_ids,
+            L.depth_sorted, L.depth_order, L.offsets_sorted, L.depth_sort_temp]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
     assert L.records - L.clamped >= 1000 and L.geom_bytes >= L.records + 64 * 1000
     assert L.ranges + 8 * 120 * 68 <= L.image_bytes
-    assert L.keys - L.keys_unsorted >= 8 * 5000 and L.vals - L.vals_unsorted >= 4 * 5000
+    assert L.keys - L.keys_unsorted >= 4 * 5000 and L.vals - L.vals_unsorted >= 4 * 5000
     # (the CUB temp-size query needs a device, so sort_temp_bytes is 0 on a CPU-only box)
     assert L.binning_bytes >= L.sort_temp + L.sort_temp_bytes
     # binning layout only depends on R, geometry layout only on P
