@@ -10,9 +10,10 @@
 // have zero gradient at 0).
 //
 // FFT: Stockham autosort in shared memory, radix 4/2/3/5 butterflies (1080 x 1920 and its pyramid
-// factor as 2^a 3^b 5^c) plus a generic O(R^2) butterfly for other prime factors, twiddles from
-// sincospif (no tables).  Rows: one CTA per image row, real input
-// -> W/2+1 complex outputs.  Columns: one CTA per group of adjacent columns, whole column resident in
+// factor as 2^a 3^b 5^c) plus a generic O(R^2) butterfly for other prime factors, twiddles from a per-length
+// table (host double precision, L1-resident).  Rows: one CTA per PAIR of image rows (two real rows ride one
+// complex transform) -> 2 x (W/2+1) complex outputs; the rendered image and the ground truth of a level share
+// a launch.  Columns: one CTA per group of adjacent columns, whole column resident in
 // shared memory (<= 96 KB).  The spectrum of a level (<= 8.3 MB) stays in L2 between the two passes.
 // The inverse used by the backward is the conjugate of the forward (conj -> FFT -> conj) followed by
 // a Hermitian completion per row, i.e. an unnormalised C2R.
@@ -24,6 +25,12 @@
 #include "reduce.cuh"
 #include "../../include/hidegs_losses.h"
 
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace hg {
 
 namespace {
@@ -32,11 +39,38 @@ constexpr int kMaxRadices = 14;
 constexpr int kFftThreads = 256;
 constexpr float kPi = 3.14159265358979323846f;
 
+// A length-n transform: radix schedule + the device table tw[k] = exp(-2 pi i k / n), k in [0, n), computed once
+// per (device, n) on the host in double precision and kept for the life of the process (<= 32 KB per length).
 struct Plan {
   int n;
   int nr;
   int radix[kMaxRadices];
+  const float2* tw;
 };
+
+const float2* twiddle_table(int n) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, float2*> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find({dev, n});
+  if (it != cache.end()) return it->second;
+  std::vector<float2> h((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    const double a = -2.0 * 3.14159265358979323846 * (double)k / (double)n;
+    h[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  float2* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(float2) * (size_t)n) != cudaSuccess) return nullptr;
+  // synchronous copy: the table is complete before any stream can launch a kernel that reads it
+  if (cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
+  cache[{dev, n}] = d;
+  return d;
+}
 
 bool make_plan(int n, Plan* p) {
   p->n = n;
@@ -52,7 +86,9 @@ bool make_plan(int n, Plan* p) {
     while (m % f == 0 && p->nr < kMaxRadices) { p->radix[p->nr++] = f; m /= f; }
     if (f * f > m && m > 1) { p->radix[p->nr++] = m; m = 1; }
   }
-  return m == 1 && p->nr <= kMaxRadices;
+  if (!(m == 1 && p->nr <= kMaxRadices)) return false;
+  p->tw = twiddle_table(n);
+  return p->tw != nullptr;
 }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -111,10 +147,12 @@ __device__ __forceinline__ void dft<5>(float2* v) {
 }
 
 // One Stockham pass of radix R over `batch` independent length-n sequences stored back to back.
+// Twiddle of butterfly input r at position k of a sub-transform of length ns*R:  tw[(k r) * n / (ns R)].
 template <int R>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst, int n,
-                                              int ns, int batch) {
+                                              int ns, int batch, const float2* __restrict__ tw) {
   const int per = n / R;
+  const int tstep = n / (ns * R);
   for (int w = threadIdx.x; w < per * batch; w += blockDim.x) {
     const int b = w / per, j = w - b * per;
     const float2* s = src + b * n;
@@ -124,13 +162,9 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = s[j + r * per];
     if (ns > 1) {
-      const float base = -2.0f * (float)k / (float)(ns * R);
+      const int t1 = k * tstep;
 #pragma unroll
-      for (int r = 1; r < R; ++r) {
-        float sn, cs;
-        sincospif(base * (float)r, &sn, &cs);
-        v[r] = cmul(v[r], make_float2(cs, sn));
-      }
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(tw + t1 * r));
     }
     dft<R>(v);
     const int j0 = (j - k) * R + k;
@@ -141,9 +175,11 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
 
 // Generic radix (any R, used for prime factors > 5): one output element per work item.
 __device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__ src, float2* __restrict__ dst,
-                                                      int n, int ns, int R, int batch) {
+                                                      int n, int ns, int R, int batch,
+                                                      const float2* __restrict__ tw) {
   const int per = n / R;
   const int period = ns * R;
+  const int tstep = n / period;
   for (int w = threadIdx.x; w < n * batch; w += blockDim.x) {
     const int b = w / n, e = w - b * n;
     const int j = e / R, r = e - j * R;
@@ -153,9 +189,7 @@ __device__ __forceinline__ void stockham_pass_generic(const float2* __restrict__
     float2 acc = make_float2(0.f, 0.f);
     int ph = 0;
     for (int t = 0; t < R; ++t) {
-      float sn, cs;
-      sincospif(-2.0f * (float)ph / (float)period, &sn, &cs);
-      acc = cadd(acc, cmul(s[j + t * per], make_float2(cs, sn)));
+      acc = cadd(acc, cmul(s[j + t * per], __ldg(tw + ph * tstep)));
       ph += step;
       if (ph >= period) ph -= period;
     }
@@ -169,11 +203,11 @@ __device__ float2* fft_smem(float2* a, float2* b, const Plan& p, int batch) {
   float2 *src = a, *dst = b;
   for (int i = 0; i < p.nr; ++i) {
     const int R = p.radix[i];
-    if (R == 4) stockham_pass<4>(src, dst, p.n, ns, batch);
-    else if (R == 2) stockham_pass<2>(src, dst, p.n, ns, batch);
-    else if (R == 3) stockham_pass<3>(src, dst, p.n, ns, batch);
-    else if (R == 5) stockham_pass<5>(src, dst, p.n, ns, batch);
-    else stockham_pass_generic(src, dst, p.n, ns, R, batch);
+    if (R == 4) stockham_pass<4>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 2) stockham_pass<2>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 3) stockham_pass<3>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 5) stockham_pass<5>(src, dst, p.n, ns, batch, p.tw);
+    else stockham_pass_generic(src, dst, p.n, ns, R, batch, p.tw);
     ns *= R;
     __syncthreads();
     float2* t = src; src = dst; dst = t;
@@ -181,31 +215,48 @@ __device__ float2* fft_smem(float2* a, float2* b, const Plan& p, int batch) {
   return src;
 }
 
-// ---- rows: real [H][W] (optionally clamped to [0,1]) -> half spectrum [H][W/2+1]
+// Up to two images per launch (blockIdx.y): the rendered image and the ground truth of a pyramid level.
+struct RealPair { const float* src[2]; float2* dst[2]; };
+struct SpecPair { float2* spec[2]; };
+struct InvPair { const float2* src[2]; float* dst[2]; };
+
+// ---- rows: real [H][W] (optionally clamped to [0,1]) -> half spectrum [H][W/2+1].
+// TWO image rows ride one complex transform (row 2j in the real part, row 2j+1 in the imaginary part):
+//   A[k] = (Z[k] + conj Z[N-k]) / 2,   B[k] = (Z[k] - conj Z[N-k]) / (2i).
 __global__ void __launch_bounds__(kFftThreads)
-fft_rows_r2c_kernel(const float* __restrict__ img, int W, int clamp01, float2* __restrict__ spec, Plan plan) {
+fft_rows_r2c_kernel(RealPair io, int H, int W, int clamp01, Plan plan) {
   extern __shared__ float2 sm[];
   float2 *a = sm, *b = sm + W;
-  const int row = blockIdx.x;
-  const float* src = img + (size_t)row * W;
+  const int r0 = 2 * blockIdx.x, r1 = r0 + 1;
+  const float* img = io.src[blockIdx.y];
+  float2* spec = io.dst[blockIdx.y];
+  const float* s0 = img + (size_t)r0 * W;
+  const float* s1 = img + (size_t)r1 * W;
+  const bool two = r1 < H;
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
-    float v = __ldg(src + i);
-    if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
-    a[i] = make_float2(v, 0.f);
+    float v0 = __ldg(s0 + i), v1 = two ? __ldg(s1 + i) : 0.f;
+    if (clamp01) { v0 = fminf(fmaxf(v0, 0.f), 1.f); v1 = fminf(fmaxf(v1, 0.f), 1.f); }
+    a[i] = make_float2(v0, v1);
   }
   __syncthreads();
-  const float2* r = fft_smem(a, b, plan, 1);
+  const float2* z = fft_smem(a, b, plan, 1);
   const int Wh = W / 2 + 1;
-  float2* dst = spec + (size_t)row * Wh;
-  for (int i = threadIdx.x; i < Wh; i += blockDim.x) dst[i] = r[i];
+  float2* d0 = spec + (size_t)r0 * Wh;
+  float2* d1 = spec + (size_t)r1 * Wh;
+  for (int k = threadIdx.x; k < Wh; k += blockDim.x) {
+    const float2 p = z[k], q = z[k == 0 ? 0 : W - k];
+    d0[k] = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));
+    if (two) d1[k] = make_float2(0.5f * (p.y + q.y), -0.5f * (p.x - q.x));
+  }
 }
 
 // ---- columns, in place on [H][Wh]; INVERSE: conj -> FFT -> conj (unnormalised inverse)
 template <bool INVERSE>
 __global__ void __launch_bounds__(kFftThreads)
-fft_cols_kernel(float2* __restrict__ spec, int H, int Wh, int tc, Plan plan) {
+fft_cols_kernel(SpecPair io, int H, int Wh, int tc, Plan plan) {
   extern __shared__ float2 sm[];
   float2 *a = sm, *b = sm + (size_t)tc * H;
+  float2* spec = io.spec[blockIdx.y];
   const int c0 = blockIdx.x * tc;
   const int nc = min(tc, Wh - c0);
   for (int i = threadIdx.x; i < H * tc; i += blockDim.x) {
@@ -227,25 +278,39 @@ fft_cols_kernel(float2* __restrict__ spec, int H, int Wh, int tc, Plan plan) {
   }
 }
 
-// ---- rows of the inverse: Hermitian completion of the half row, inverse FFT, real part * scale
+// ---- rows of the inverse: Hermitian completion of the half rows, inverse transform, real part * scale.
+// Two rows ride one transform again: Z = A + i B with A, B the completed (exactly Hermitian: the imaginary parts of
+// the DC / Nyquist bins cannot reach the real output and are dropped first) rows; the transform of conj(Z) is
+// conj(a + i b) for the real rows a, b.
 __global__ void __launch_bounds__(kFftThreads)
-fft_rows_c2r_kernel(const float2* __restrict__ spec, int W, float scale, float* __restrict__ img, Plan plan) {
+fft_rows_c2r_kernel(InvPair io, int H, int W, float scale, Plan plan) {
   extern __shared__ float2 sm[];
   float2 *a = sm, *b = sm + W;
-  const int row = blockIdx.x;
+  const int r0 = 2 * blockIdx.x, r1 = r0 + 1;
   const int Wh = W / 2 + 1;
-  const float2* src = spec + (size_t)row * Wh;
+  const float2* spec = io.src[blockIdx.y];
+  float* img = io.dst[blockIdx.y];
+  const float2* s0 = spec + (size_t)r0 * Wh;
+  const float2* s1 = spec + (size_t)r1 * Wh;
+  const bool two = r1 < H;
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
-    // conj of the completed row: X[k] for k <= W/2, conj(X[W-k]) above; then conjugate for the inverse
-    float2 v;
-    if (i < Wh) { v = src[i]; v.y = -v.y; }
-    else v = src[W - i];
-    a[i] = v;
+    const bool upper = i >= Wh;
+    const int k = upper ? W - i : i;
+    float2 A = s0[k], B = two ? s1[k] : make_float2(0.f, 0.f);
+    if (k == 0 || 2 * k == W) { A.y = 0.f; B.y = 0.f; }
+    if (upper) { A.y = -A.y; B.y = -B.y; }  // conj(S[N-k])
+    // conj(A + i B) = (A.x - B.y) - i (A.y + B.x)
+    a[i] = make_float2(A.x - B.y, -(A.y + B.x));
   }
   __syncthreads();
   const float2* r = fft_smem(a, b, plan, 1);
-  float* dst = img + (size_t)row * W;
-  for (int i = threadIdx.x; i < W; i += blockDim.x) dst[i] = r[i].x * scale;
+  float* d0 = img + (size_t)r0 * W;
+  float* d1 = img + (size_t)r1 * W;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    const float2 v = r[i];
+    d0[i] = v.x * scale;
+    if (two) d1[i] = -v.y * scale;
+  }
 }
 
 struct FftCfg {
@@ -259,8 +324,9 @@ int make_cfg(int H, int W, FftCfg* c) {
     set_error("FFT size %dx%d unsupported (each side must be in [1, 4096])", H, W);
     return HG_ERR_INVALID_ARG;
   }
+  // 4 adjacent columns = one 32-byte sector per spectrum row; two resident CTAs per SM up to H = 2048
   c->tc = (int)((96 * 1024) / (16 * (size_t)H));
-  if (c->tc > 8) c->tc = 8;
+  if (c->tc > 4) c->tc = 4;
   if (c->tc < 1) c->tc = 1;
   c->smem_row = 2 * (size_t)W * sizeof(float2);
   c->smem_col = 2 * (size_t)c->tc * H * sizeof(float2);
@@ -268,27 +334,34 @@ int make_cfg(int H, int W, FftCfg* c) {
 }
 
 int set_smem_attrs() {
-  static bool done = false;
-  if (done) return HG_OK;
+  static thread_local bool done[16] = {};
+  int dev = 0;
+  HG_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 16 && done[dev]) return HG_OK;
   const int maxb = 100 * 1024;
   HG_CUDA_TRY(cudaFuncSetAttribute(fft_rows_r2c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
   HG_CUDA_TRY(cudaFuncSetAttribute(fft_rows_c2r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
   HG_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
   HG_CUDA_TRY(cudaFuncSetAttribute(fft_cols_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
-  done = true;
+  if (dev >= 0 && dev < 16) done[dev] = true;
   return HG_OK;
 }
 
-int fft2_r2c(const float* img, int H, int W, int clamp01, float2* spec, cudaStream_t st) {
+// Forward 2-D transform of one or two real images of the same size (img1 / spec1 may be NULL).
+int fft2_r2c(const float* img0, float2* spec0, const float* img1, float2* spec1, int H, int W, int clamp01,
+             cudaStream_t st) {
   FftCfg c;
   int rc = make_cfg(H, W, &c);
   if (rc) return rc;
   rc = set_smem_attrs();
   if (rc) return rc;
   const int Wh = W / 2 + 1;
-  fft_rows_r2c_kernel<<<H, kFftThreads, c.smem_row, st>>>(img, W, clamp01, spec, c.row);
+  const int nimg = img1 ? 2 : 1;
+  RealPair rp{{img0, img1}, {spec0, spec1}};
+  fft_rows_r2c_kernel<<<dim3((H + 1) / 2, nimg), kFftThreads, c.smem_row, st>>>(rp, H, W, clamp01, c.row);
   HG_POST_LAUNCH(false, st, "fft_rows_r2c");
-  fft_cols_kernel<false><<<(Wh + c.tc - 1) / c.tc, kFftThreads, c.smem_col, st>>>(spec, H, Wh, c.tc, c.col);
+  SpecPair sp{{spec0, spec1}};
+  fft_cols_kernel<false><<<dim3((Wh + c.tc - 1) / c.tc, nimg), kFftThreads, c.smem_col, st>>>(sp, H, Wh, c.tc, c.col);
   HG_POST_LAUNCH(false, st, "fft_cols");
   return HG_OK;
 }
@@ -301,9 +374,11 @@ int fft2_c2r(float2* spec, int H, int W, float scale, float* img, cudaStream_t s
   rc = set_smem_attrs();
   if (rc) return rc;
   const int Wh = W / 2 + 1;
-  fft_cols_kernel<true><<<(Wh + c.tc - 1) / c.tc, kFftThreads, c.smem_col, st>>>(spec, H, Wh, c.tc, c.col);
+  SpecPair sp{{spec, nullptr}};
+  fft_cols_kernel<true><<<dim3((Wh + c.tc - 1) / c.tc, 1), kFftThreads, c.smem_col, st>>>(sp, H, Wh, c.tc, c.col);
   HG_POST_LAUNCH(false, st, "ifft_cols");
-  fft_rows_c2r_kernel<<<H, kFftThreads, c.smem_row, st>>>(spec, W, scale, img, c.row);
+  InvPair ip{{spec, nullptr}, {img, nullptr}};
+  fft_rows_c2r_kernel<<<dim3((H + 1) / 2, 1), kFftThreads, c.smem_row, st>>>(ip, H, W, scale, c.row);
   HG_POST_LAUNCH(false, st, "ifft_rows_c2r");
   return HG_OK;
 }
@@ -755,7 +830,7 @@ size_t hg_fft2_workspace_bytes(int32_t H, int32_t W) { return (size_t)H * (W / 2
 int hg_fft2_r2c(const float* img, int32_t H, int32_t W, float* spec, void* ws, void* st) {
   (void)ws;
   if (!img || !spec) { set_error("hg_fft2_r2c: NULL pointer"); return HG_ERR_INVALID_ARG; }
-  return fft2_r2c(img, H, W, 0, (float2*)spec, (cudaStream_t)st);
+  return fft2_r2c(img, (float2*)spec, nullptr, nullptr, H, W, 0, (cudaStream_t)st);
 }
 
 int hg_fft2_c2r(const float* spec, int32_t H, int32_t W, float* img, int scale_inv, void* ws, void* st_) {
@@ -830,9 +905,7 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
     const dim3 grid((wsz[l] + kSpTile - 1) / kSpTile, (hs[l] + kSpTile - 1) / kSpTile);
     spatial_kernel<false><<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gr[l], gg[l], hs[l], wsz[l], sp_part[l], nullptr, nullptr);
     HG_POST_LAUNCH(false, st, "spatial");
-    int rc = fft2_r2c(gr[l], hs[l], wsz[l], 1, fr[l], st);
-    if (rc) return rc;
-    rc = fft2_r2c(gg[l], hs[l], wsz[l], 1, fg[l], st);
+    int rc = fft2_r2c(gr[l], fr[l], gg[l], fg[l], hs[l], wsz[l], 1, st);  // rendered + ground truth in one launch pair
     if (rc) return rc;
     spectral_sums_kernel<<<kSumBlocks, 256, 0, st>>>(fr[l], fg[l], hs[l], wsz[l], spec_part[l]);
     HG_POST_LAUNCH(false, st, "spectral_sums");
@@ -901,7 +974,7 @@ int hg_hf_mask(const float* gt, int32_t H, int32_t W, float thresh, float* mask,
   const dim3 grid((W + kSpTile - 1) / kSpTile, (H + kSpTile - 1) / kSpTile);
   hf_spatial_kernel<<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gray, H, W, spatial);
   HG_POST_LAUNCH(false, st, "hf_spatial");
-  int rc = fft2_r2c(gray, H, W, 0, spec, st);  // unclamped here (frequency_regularization.py:1221)
+  int rc = fft2_r2c(gray, spec, nullptr, nullptr, H, W, 0, st);  // unclamped here (frequency_regularization.py:1221)
   if (rc) return rc;
   const int64_t nsp = (int64_t)H * (W / 2 + 1);
   highpass_kernel<<<(unsigned)((nsp + 255) / 256), 256, 0, st>>>(spec, H, W);

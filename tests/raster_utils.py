@@ -216,11 +216,13 @@ def rel_report(a, b):
     return float(err.max()), scale, float((err > tol).double().mean())
 
 
-def assert_grads_close(ours, theirs, names=GRAD_NAMES, rtol=1e-3, floor=3e-2, l2_tol=1e-4, what=""):
+def assert_grads_close(ours, theirs, names=GRAD_NAMES, rtol=1e-3, floor=3e-2, l2_tol=1e-4, what="", max_bad_frac=0.0):
     """Gradients within `rtol` relative.  Two criteria per tensor:
       * relative L2 error  ||a-b|| / ||b||  <= l2_tol, and
       * element-wise |a-b| <= rtol*|b| + rtol*floor*max|b|  (the floor absorbs summation-order noise on
         entries that are small next to the terms that cancel into them, e.g. dL/dcov3D = T^2 * dL/dconic).
+    `max_bad_frac`: fraction of elements allowed outside the element-wise bound (0 except for the multi-million
+    element full-size cases, where single cancellation-dominated entries of both implementations are atomic-order noise).
     """
     for name, a, b in zip(names, ours, theirs):
         a, b = torch.as_tensor(a).detach().cpu().double(), torch.as_tensor(b).detach().cpu().double()
@@ -233,7 +235,7 @@ def assert_grads_close(ours, theirs, names=GRAD_NAMES, rtol=1e-3, floor=3e-2, l2
         tol = rtol * b.abs() + rtol * floor * scale + 1e-30
         bad = (a - b).abs() > tol
         frac = float(bad.double().mean())
-        assert frac == 0.0, "%s %s: %.3g%% of elements off (max err %.3g, scale %.3g)" % (
+        assert frac <= max_bad_frac, "%s %s: %.3g%% of elements off (max err %.3g, scale %.3g)" % (
             what, name, 100 * frac, float((a - b).abs().max()), scale)
 
 

@@ -310,3 +310,101 @@ def test_full_size_properties(cuda_device):
         assert img_close(ours[1], ref[1]) and img_close(ours[9], ref[9])
         ref_b = REF.rasterize_gaussians_backward(*ru.bwd_args(fa, ref, grads, dev))
         ru.assert_grads_close(bwd, ref_b, what="config2 vs reference")
+
+
+# ------------------------------------------------------------------ full size (BASELINE config 3)
+def test_config3_uav_4k_lod_cut(cuda_device):
+    """configs[2]: 6M Gaussians on the UAV slab, 3840x2160 nadir view, synthetic hierarchy cut (60 % of the nodes,
+    random parents, half of the interpolation weights exactly 1, 2..8 kids), rendered the way render_post does it
+    (Python interpolation with the parent, then the rasterizer with weights / kid counts, no geometry, no depth) and,
+    additionally, through the raw indices / parent_indices API — ours vs the UNMODIFIED reference on the same inputs."""
+    import math
+    dev = cuda_device
+    W, H, n = 3840, 2160, 6_000_000
+    sc = syn.make_uav_scene(n, seed=0)
+    cam = syn.look_at_camera((0.0, 0.0, 120.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), math.radians(70.0), W, H)
+    g = torch.Generator().manual_seed(5)
+    keep = (torch.rand(n, generator=g) < 0.6).nonzero().flatten()
+    P = keep.numel()
+    rest = torch.ones(n, dtype=torch.bool)
+    rest[keep] = False
+    rest = rest.nonzero().flatten()
+    parents = rest[torch.randint(0, rest.numel(), (P,), generator=g)]
+    ts = torch.rand(P, generator=g)
+    ts[torch.rand(P, generator=g) < 0.5] = 1.0
+    kids = torch.randint(2, 9, (P,), generator=g, dtype=torch.int32)
+    d = {k: v.to(dev) for k, v in sc.items()}
+    keep_d, par_d, ts_d, kids_d = keep.to(dev), parents.to(dev), ts.to(dev), kids.to(dev)
+    e_i = torch.empty(0, dtype=torch.int32, device=dev)
+    e_f = torch.empty(0, dtype=torch.float32, device=dev)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    camd = cam.to(dev)
+
+    # ---- path A: render_post semantics (gaussian_renderer/__init__.py:278-324)
+    t1, t0 = ts_d[:, None], (1 - ts_d)[:, None]
+    m3 = (t1 * d["means3D"][keep_d] + t0 * d["means3D"][par_d]).contiguous()
+    scl = (t1 * d["scales"][keep_d] + t0 * d["scales"][par_d]).contiguous()
+    shs = (t1[:, :, None] * d["shs"][keep_d] + t0[:, :, None] * d["shs"][par_d]).contiguous()
+    rp, rc = d["rotations"][par_d].clone(), d["rotations"][keep_d]
+    rp[(rc * rp).sum(1) < 0] *= -1
+    rot = (t1 * rc + t0 * rp).contiguous()
+    op = (t1 * d["opacity"][keep_d] + t0 * d["opacity"][par_d]).contiguous()
+    fa = (bg, e_i, e_i, ts_d, kids_d, m3, e_f, e_f, op, scl, rot, 1.0, e_f, camd.world_view_transform,
+          camd.full_proj_transform, cam.tanfovx, cam.tanfovy, H, W, shs, 3, camd.camera_center, False, False, False, False)
+    ours = ru.OUR_C.rasterize_gaussians(*fa)
+    R = ours[0]
+    assert R > 0 and int((ours[2] > 0).sum()) > 100_000
+    gr = dict(color=torch.randn(3, H, W, generator=g).to(dev), all_map=torch.zeros(5, H, W, device=dev),
+              plane_depth=torch.zeros(1, H, W, device=dev), invdepth=torch.zeros(0, H, W, device=dev))
+    ours_b = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fa, ours, gr, dev))
+    so = ru.our_state(ours, P, W, H)
+    keys = so["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all()) and int(so["tiles_touched"].long().sum()) == R
+    assert int((keys >> 32).max()) < 240 * 135
+    if ru.ref_available():
+        REF = ru.ref_module()
+        ref = REF.rasterize_gaussians(*fa)
+        sr = ru.ref_state(ref, P, W, H)
+        assert ref[0] == R
+        for k in ("keys", "point_list", "ranges", "n_contrib"):
+            assert torch.equal(so[k], sr[k]), k
+        assert torch.equal(ours[2], ref[2]) and torch.equal(ours[3], ref[3])
+        assert img_close(ours[1], ref[1])
+        ref_b = REF.rasterize_gaussians_backward(*ru.bwd_args(fa, ref, gr, dev))
+        ru.assert_grads_close(ours_b, ref_b, what="config3 render_post path", max_bad_frac=1e-6)
+        del ref, ref_b, sr
+    del ours, ours_b, so, keys
+
+    # ---- path B: the raw API (indices / parent_indices inside the rasterizer), smaller image to bound the run time
+    W2, H2 = 1920, 1080
+    cam2 = syn.look_at_camera((0.0, 0.0, 120.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), math.radians(70.0), W2, H2).to(dev)
+    fb = (bg, keep_d.int(), par_d.int(), ts_d, kids_d, d["means3D"], e_f, e_f, d["opacity"], d["scales"], d["rotations"], 1.0,
+          e_f, cam2.world_view_transform, cam2.full_proj_transform, cam2.tanfovx, cam2.tanfovy, H2, W2, d["shs"], 0,
+          cam2.camera_center, False, False, False, False)
+    ours = ru.OUR_C.rasterize_gaussians(*fb)
+    gr2 = dict(color=torch.randn(3, H2, W2, generator=g).to(dev), all_map=torch.zeros(5, H2, W2, device=dev),
+               plane_depth=torch.zeros(1, H2, W2, device=dev), invdepth=torch.zeros(0, H2, W2, device=dev))
+    ours_b = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fb, ours, gr2, dev))
+    if ru.ref_available():
+        ref = REF.rasterize_gaussians(*fb)
+        assert ref[0] == ours[0]
+        so, sr = ru.our_state(ours, P, W2, H2), ru.ref_state(ref, P, W2, H2)
+        for k in ("keys", "point_list", "ranges", "n_contrib"):
+            assert torch.equal(so[k], sr[k]), k
+        assert img_close(ours[1], ref[1])
+        ref_b = REF.rasterize_gaussians_backward(*ru.bwd_args(fb, ref, gr2, dev))
+        # SH degree 0: the parent rows are fully defined (see mask_undefined_parent_rows)
+        ru.assert_grads_close(ours_b, ref_b, what="config3 raw indices path", max_bad_frac=1e-6)
+
+    # ---- scale regularisation on the visible set (frequency_regularization.py:1403-1444) vs the oracle
+    from hidegs_b200.frequency_regularization import _ScaleReg
+    import oracle.loss_oracle as lo
+    vis = (ours[2] > 0).nonzero().flatten()
+    s_gpu = d["scales"].clone().requires_grad_(True)
+    v_gpu = _ScaleReg.apply(s_gpu, keep_d[vis])
+    v_gpu.backward()
+    s_cpu = sc["scales"].clone().requires_grad_(True)
+    v_cpu = lo.scale_regularization(s_cpu, keep[vis.cpu()])
+    v_cpu.backward()
+    assert abs(v_gpu.item() - v_cpu.item()) <= 1e-5 * abs(v_cpu.item()) + 1e-12
+    ru.assert_grads_close([s_gpu.grad], [s_cpu.grad], names=("scaling",), what="scale regularisation")
