@@ -104,8 +104,8 @@ def stage_bytes(N, Nv, R, HW, T):
     """Algorithmic bytes per launch of each stage."""
     return {
         "preprocess_fwd": 56 * N + 335 * Nv,   # always: xyz+scale+rot+opacity 44, radii/tiles/observe 12; visible: SH 192, all_map 20, record 64, cov3D 24, depth/rect/clamp 13, ...
-        "scan": 8 * N,
-        "binning": 12 * N + 12 * Nv + (12 + 24 + 8) * R + 8 * T,   # emit 12R, sort >= 24R, ranges 8R
+        "scan": 8 * N + 16 * N,   # tile-count scan + depth sort of the slots (>= one read + one write of 8-byte pairs)
+        "binning": 12 * N + 16 * Nv + (8 + 16 + 4) * R + 8 * T,   # depth-order scan, emit 8R, tile sort >= 16R, ranges 4R
         "blend_fwd": 68 * R + 48 * HW + 8 * T,  # id 4 + record 64 per instance; 12 floats out per pixel
         "accum_zero": 64 * N,
         "blend_bwd": 68 * R + 72 * HW + 128 * Nv + 8 * T,  # gathers; 18 floats in per pixel; accumulator RMW
@@ -344,16 +344,22 @@ def run_gpu_arm(args, impl):
         dom = max(stages, key=lambda k: stages[k][0])
         dom_ms = stages[dom][0] / max(stages[dom][1], 1)
         achieved = bytes_per[dom] / (dom_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = issue_pct = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)
+            tj = json.load(open(tp))
+            traffic = tj.get(dom)
+            issue_pct = tj.get("_issue_active_pct", {}).get(dom)
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": how,
                             "algorithmic_bytes": bytes_per[dom], "kernel_ms": round(dom_ms, 4),
                             "share_of_step": round(stages[dom][0] / max(sum(v[0] for v in stages.values()), 1e-9), 3),
                             "stage_ms": per_stage,
-                            "note": "blend kernels are FP32-issue / shared-memory bound, not HBM bound (DESIGN.md §4)"}
+                            "binding_roofline": "fp32 instruction issue",
+                            "issue_active_pct_ncu": issue_pct,
+                            "note": "the blend kernels are FP32-issue bound, not HBM bound: frac (HBM) is reported as the "
+                                    "contract asks, issue_active_pct_ncu (profiles/r01_ncu_blend_full.md) is the binding "
+                                    "fraction (DESIGN.md §4)"}
         line["gpu_launches"] = launches
         if train is not None:
             line["train"] = train

@@ -116,3 +116,48 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "raster_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_install_routes_reference_imports():
+    """hidegs_b200.install(): the reference's import lines resolve to the drop-ins."""
+    import importlib
+    import sys
+    import hidegs_b200
+    saved = {k: sys.modules.get(k) for k in ("diff_gaussian_rasterization", "diff_gaussian_rasterization._C", "simple_knn",
+                                            "simple_knn._C")}
+    try:
+        done = hidegs_b200.install(patch_reference_modules=False)
+        assert "simple_knn._C" in done
+        from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C  # noqa: F401
+        from simple_knn._C import distCUDA2
+        assert _C is importlib.import_module("hidegs_b200.diff_gaussian_rasterization._C")
+        assert distCUDA2 is importlib.import_module("hidegs_b200.simple_knn._C").distCUDA2
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_drop_in_signatures_match_reference():
+    """Same parameter names / defaults as the reference's Python functions."""
+    import inspect
+    from hidegs_b200 import gaussian_renderer as gr, loss_utils as lu
+    from hidegs_b200.frequency_regularization import frequency_regularization_pyramid_scale as f
+    assert list(inspect.signature(gr.render).parameters) == [
+        "viewpoint_camera", "pc", "pipe", "bg_color", "scaling_modifier", "override_color", "indices", "use_trained_exp",
+        "return_plane", "return_depth_normal"]
+    assert list(inspect.signature(gr.render_post).parameters) == [
+        "viewpoint_camera", "pc", "pipe", "bg_color", "scaling_modifier", "override_color", "render_indices",
+        "parent_indices", "interpolation_weights", "num_node_kids", "interp_python", "use_trained_exp"]
+    assert list(inspect.signature(gr.render_normal).parameters) == ["viewpoint_cam", "depth", "offset", "normal", "scale"]
+    assert list(inspect.signature(f).parameters) == [
+        "rendered_image", "gt_image", "gaussians", "scene", "viewpoint_cam", "visibility_filter", "iteration", "lambda_freq",
+        "lambda_scale", "num_levels", "high_freq_thresh", "save_results", "save_dir", "warmup_iterations", "debug"]
+    sig = inspect.signature(f).parameters
+    assert (sig["lambda_freq"].default, sig["lambda_scale"].default, sig["num_levels"].default,
+            sig["high_freq_thresh"].default, sig["warmup_iterations"].default) == (0.001, 0.005, 3, 0.2, 1000)
+    assert list(inspect.signature(lu.ssim).parameters) == ["img1", "img2", "window_size", "size_average"]
+    assert list(inspect.signature(lu.get_img_grad_weight).parameters) == ["img", "beta"]
+    assert list(inspect.signature(lu.lncc).parameters) == ["ref", "nea"]
