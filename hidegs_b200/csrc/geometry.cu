@@ -127,6 +127,80 @@ all_map_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Parameter activations.
+__global__ void __launch_bounds__(256)
+activate_kernel(const float* __restrict__ rs, const float* __restrict__ rr, const float* __restrict__ ro, const int64_t N,
+                float* __restrict__ s, float* __restrict__ r, float* __restrict__ o) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) s[3 * n + i] = expf(rs[3 * n + i]);
+  o[n] = 1.0f / (1.0f + expf(-ro[n]));
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rr) + n);
+  const float inv = 1.0f / fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+  reinterpret_cast<float4*>(r)[n] = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+}
+
+// per-Gaussian part: xyz (pass-through), opacity, scaling, rotation
+__global__ void __launch_bounds__(256)
+activate_bwd_kernel(const float* __restrict__ rs, const float* __restrict__ rr, const float* __restrict__ ro,
+                    const int64_t N, const float* __restrict__ g_xyz, const float* __restrict__ g_o,
+                    const float* __restrict__ g_s, const float* __restrict__ g_r, const float beta,
+                    float* __restrict__ d_xyz, float* __restrict__ d_o, float* __restrict__ d_s,
+                    float* __restrict__ d_r) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const bool acc = beta != 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float gx = g_xyz ? g_xyz[3 * n + i] : 0.f;
+    d_xyz[3 * n + i] = acc ? d_xyz[3 * n + i] + gx : gx;
+    const float gs = g_s ? g_s[3 * n + i] * expf(rs[3 * n + i]) : 0.f;
+    d_s[3 * n + i] = acc ? d_s[3 * n + i] + gs : gs;
+  }
+  {
+    const float sg = 1.0f / (1.0f + expf(-ro[n]));
+    const float go = g_o ? g_o[n] * sg * (1.0f - sg) : 0.f;
+    d_o[n] = acc ? d_o[n] + go : go;
+  }
+  {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(rr) + n);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g_r) g = __ldg(reinterpret_cast<const float4*>(g_r) + n);
+    const float len = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    float4 d;
+    if (len > 1e-12f) {
+      const float inv = 1.0f / len;
+      const float4 y = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);
+      const float t = y.x * g.x + y.y * g.y + y.z * g.z + y.w * g.w;
+      d = make_float4((g.x - y.x * t) * inv, (g.y - y.y * t) * inv, (g.z - y.z * t) * inv, (g.w - y.w * t) * inv);
+    } else {  // clamp_min saturated: the denominator is the constant eps
+      d = make_float4(g.x * 1e12f, g.y * 1e12f, g.z * 1e12f, g.w * 1e12f);
+    }
+    float4* dst = reinterpret_cast<float4*>(d_r) + n;
+    if (acc) {
+      const float4 p = *dst;
+      d = make_float4(p.x + d.x, p.y + d.y, p.z + d.z, p.w + d.w);
+    }
+    *dst = d;
+  }
+}
+
+// features: dst = beta * dst + g, float4 grid-stride
+__global__ void __launch_bounds__(256)
+axpby4_kernel(const float4* __restrict__ g, const int64_t n4, const float beta, float4* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = g ? __ldg(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta != 0.0f) {
+      const float4 p = dst[i];
+      v = make_float4(p.x + v.x, p.y + v.y, p.z + v.z, p.w + v.w);
+    }
+    dst[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Depth -> normal.
 struct Unproj {
   float i00, i20, i11, i21;  // entries of K^-1: X = (u z) i00 + z i20, Y = (v z) i11 + z i21
@@ -415,6 +489,46 @@ int hg_geometry_all_map_backward(const float* xyz, const float* scaling, const f
   all_map_kernel<true><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(xyz, scaling, rotation, viewmatrix, campos, N,
                                                                      nullptr, dL_dall_map, dL_dxyz, dL_drotation);
   HG_POST_LAUNCH(false, st, "geometry_all_map_bwd");
+  return HG_OK;
+}
+
+int hg_activate_params(const float* raw_scaling, const float* raw_rotation, const float* raw_opacity, int64_t N,
+                       float* scaling, float* rotation, float* opacity, void* st_) {
+  if (N < 0 || (N > 0 && (!raw_scaling || !raw_rotation || !raw_opacity || !scaling || !rotation || !opacity)) ||
+      (((uintptr_t)raw_rotation | (uintptr_t)rotation) & 15) != 0) {
+    set_error("hg_activate_params: bad argument (rotation arrays must be 16-byte aligned)");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (N == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  activate_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(raw_scaling, raw_rotation, raw_opacity, N, scaling, rotation,
+                                                                 opacity);
+  HG_POST_LAUNCH(false, st, "activate_params");
+  return HG_OK;
+}
+
+int hg_activate_params_backward(const float* raw_scaling, const float* raw_rotation, const float* raw_opacity, int64_t N,
+                                int32_t F, const float* g_xyz, const float* g_features, const float* g_opacity,
+                                const float* g_scaling, const float* g_rotation, float beta, float* d_xyz,
+                                float* d_features, float* d_opacity, float* d_scaling, float* d_rotation, void* st_) {
+  if (N < 0 || F < 0 || !(beta == 0.0f || beta == 1.0f) ||
+      (N > 0 && (!raw_scaling || !raw_rotation || !raw_opacity || !d_xyz || !d_opacity || !d_scaling || !d_rotation ||
+                 (F > 0 && !d_features))) ||
+      (((uintptr_t)raw_rotation | (uintptr_t)g_rotation | (uintptr_t)d_rotation | (uintptr_t)g_features |
+        (uintptr_t)d_features) & 15) != 0 || ((N * (int64_t)F) & 3) != 0) {
+    set_error("hg_activate_params_backward: bad argument (rotation / feature arrays must be 16-byte aligned, N*F % 4 == 0)");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (N == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  activate_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(raw_scaling, raw_rotation, raw_opacity, N, g_xyz,
+                                                                     g_opacity, g_scaling, g_rotation, beta, d_xyz,
+                                                                     d_opacity, d_scaling, d_rotation);
+  HG_POST_LAUNCH(false, st, "activate_params_bwd");
+  if (F > 0) {
+    axpby4_kernel<<<148 * 8, 256, 0, st>>>((const float4*)g_features, N * (int64_t)F / 4, beta, (float4*)d_features);
+    HG_POST_LAUNCH(false, st, "features_grad_accumulate");
+  }
   return HG_OK;
 }
 

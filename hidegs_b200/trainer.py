@@ -48,6 +48,47 @@ class OptimizationParams:
     freq_warmup_iterations = 1000
 
 
+class _ActivateParams(torch.autograd.Function):
+    """get_scaling / get_rotation / get_opacity of the model (exp / normalize / sigmoid) in ONE kernel, and — in the
+    backward — their chain rule fused with the accumulation of all five parameter gradients into the flat gradient
+    arena (dst = beta * dst + grad).  Replaces ~6 elementwise launches forward and ~25 backward (activation backward +
+    autograd's AccumulateGrad of five leaves) per view.  The leaves receive no autograd gradient (None): their `.grad`
+    are views of the arena this Function writes."""
+
+    @staticmethod
+    def forward(ctx, xyz, features, opacity_raw, scaling_raw, rotation_raw, owner):
+        N = xyz.size(0)
+        dev = xyz.device
+        act = torch.empty(N * 8, dtype=torch.float32, device=dev)
+        scaling, rotation, opacity = act[:3 * N].view(N, 3), act[3 * N:7 * N].view(N, 4), act[7 * N:].view(N, 1)
+        with torch.cuda.device(dev):
+            rc = _G().hg_activate_params(scaling_raw.data_ptr(), rotation_raw.data_ptr(), opacity_raw.data_ptr(), N,
+                                         scaling.data_ptr(), rotation.data_ptr(), opacity.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "activate_params")
+        ctx.owner = owner
+        return xyz.view_as(xyz), features.view_as(features), opacity, scaling, rotation
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_feat, g_op, g_sc, g_rot):
+        p = ctx.owner
+        N = p.N
+
+        def ptr(t):
+            return t.contiguous().data_ptr() if t is not None else None
+        keep = [t.contiguous() if t is not None else None for t in (g_xyz, g_feat, g_op, g_sc, g_rot)]
+        d = {k: p.grad_arena[p.slices[k]] for k in ("xyz", "features", "opacity", "scaling", "rotation")}
+        with torch.cuda.device(p.param_arena.device):
+            rc = _G().hg_activate_params_backward(
+                p._scaling.data_ptr(), p._rotation.data_ptr(), p._opacity.data_ptr(), N, 48,
+                ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), ptr(keep[3]), ptr(keep[4]), 1.0 if p._grad_dirty else 0.0,
+                d["xyz"].data_ptr(), d["features"].data_ptr(), d["opacity"].data_ptr(), d["scaling"].data_ptr(),
+                d["rotation"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "activate_params_backward")
+        p._grad_dirty = True
+        return None, None, None, None, None, None
+
+
 class GaussianParams:
     """Trainable Gaussians in the reference's parameterisation (scene/gaussian_model.py:60-140): raw leaves
     `_xyz`, `_features` (N,16,3), `_opacity` (logit), `_scaling` (log), `_rotation` (un-normalised quaternion) and the
@@ -77,6 +118,10 @@ class GaussianParams:
         self._opacity, self._scaling, self._rotation = self.leaves["opacity"], self.leaves["scaling"], self.leaves["rotation"]
         self.active_sh_degree = self.max_sh_degree = sh_degree
         self.skybox_points = 0
+        # fused activations (CUDA only): one kernel per view forward, one backward that also accumulates into the arena
+        self.fused = xyz.is_cuda
+        self._act = None          # (xyz, features, opacity, scaling, rotation) of the current view
+        self._grad_dirty = False  # False: the next fused backward overwrites the arena (no zero fill needed)
 
     @classmethod
     def from_scene(cls, scene, device):
@@ -85,14 +130,27 @@ class GaussianParams:
         return cls(scene["means3D"].to(device), scene["shs"].to(device), torch.log(op / (1 - op)).to(device),
                    torch.log(scene["scales"]).to(device), scene["rotations"].to(device))
 
-    get_xyz = property(lambda s: s._xyz)
-    get_features = property(lambda s: s._features)
-    get_opacity = property(lambda s: torch.sigmoid(s._opacity))
-    get_scaling = property(lambda s: torch.exp(s._scaling))
-    get_rotation = property(lambda s: torch.nn.functional.normalize(s._rotation))
+    def _activated(self, i):
+        if self._act is None:
+            self._act = _ActivateParams.apply(self._xyz, self._features, self._opacity, self._scaling, self._rotation, self)
+        return self._act[i]
+
+    def begin_view(self):
+        """Fresh activation node for the next forward/backward (one autograd graph per view)."""
+        self._act = None
+
+    get_xyz = property(lambda s: s._activated(0) if s.fused else s._xyz)
+    get_features = property(lambda s: s._activated(1) if s.fused else s._features)
+    get_opacity = property(lambda s: s._activated(2) if s.fused else torch.sigmoid(s._opacity))
+    get_scaling = property(lambda s: s._activated(3) if s.fused else torch.exp(s._scaling))
+    get_rotation = property(lambda s: s._activated(4) if s.fused else torch.nn.functional.normalize(s._rotation))
 
     def zero_grad(self):
-        self.grad_arena.zero_()
+        self._act = None
+        if self.fused:
+            self._grad_dirty = False  # the first backward of the step overwrites the arena: no memset
+        else:
+            self.grad_arena.zero_()
         for name, leaf in self.leaves.items():  # autograd may have replaced .grad; point it back at the arena
             shape = leaf.shape
             leaf.grad = self.grad_arena[self.slices[name]].view(shape)
@@ -117,6 +175,7 @@ class ArenaAdam:
     def step(self, grad_scale=1.0, visible_mask=None):
         self.step_count += 1
         p = self.p
+        p._act = None  # the activated copies are stale after the update
         st = torch.cuda.current_stream().cuda_stream
         mask = visible_mask.contiguous().view(torch.uint8).data_ptr() if visible_mask is not None else None
         with torch.cuda.device(p.param_arena.device):
@@ -161,6 +220,7 @@ class ViewShardedTrainer:
     def view_loss(self, cam, gt, iteration):
         """Forward of one view: returns (loss tensor, render package)."""
         o = self.opt
+        self.params.begin_view()
         pkg = gr.render(cam, self.params, self.pipe, self.bg)
         image = pkg["render"]
         loss = (1.0 - o.lambda_dssim) * lu.l1_loss(image, gt) + o.lambda_dssim * (1.0 - lu.ssim(image, gt))
@@ -183,6 +243,9 @@ class ViewShardedTrainer:
             loss, _pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+        self.params.begin_view()
+        if self.params.fused and not self.params._grad_dirty:  # no view produced a gradient
+            self.params.grad_arena.zero_()
         n_views = len(views)
         if self.world > 1:
             dist.all_reduce(self.params.grad_arena, op=dist.ReduceOp.SUM, group=self.group)

@@ -20,6 +20,8 @@
  *                                  (weights arguments/__init__.py:118-119; composed from render()'s
  *                                  "depth_normal" / "rendered_normal" outputs and get_img_grad_weight,
  *                                  utils/loss_utils.py:66-78; see DESIGN.md for the definition)
+ *   hg_activate_params(+_backward) scene/gaussian_model.py:60-75,118-137 (exp / sigmoid / normalize activations and their
+ *                                  autograd backward, fused with the gradient accumulation of a multi-view step)
  *   hg_adam_step                   scene/OurAdam.py:106-337 (Adam update of the parameter groups; dense and
  *                                  visibility-masked "sparse" variant)
  *   hg_dist2_knn3                  simple_knn: distCUDA2 -> SimpleKNN::knn (submodules/simple-knn/spatial.cu:15-26,
@@ -50,6 +52,20 @@ HG_API int hg_geometry_all_map_backward(const float *xyz, const float *scaling, 
                                         const float *viewmatrix, const float *campos, int64_t N,
                                         const float *dL_dall_map, float *dL_dxyz, float *dL_drotation,
                                         void *stream);
+
+/* Parameter activations of GaussianModel (scene/gaussian_model.py:60-75,118-137): scaling = exp(raw), opacity =
+ * sigmoid(raw), rotation = raw / max(|raw|, 1e-12) (torch.nn.functional.normalize).  Forward writes the three
+ * activated arrays; backward chains the gradients w.r.t. the activated arrays (and the pass-through gradients of xyz
+ * [N,3] and features [N,F]) back to the raw parameters and stores them into the five destination arrays
+ *   dst = beta * dst + chain(grad),  beta = 0 (overwrite) or 1 (accumulate across the views of a step).
+ * Any gradient pointer may be NULL (= zero gradient). */
+HG_API int hg_activate_params(const float *raw_scaling, const float *raw_rotation, const float *raw_opacity,
+                              int64_t N, float *scaling, float *rotation, float *opacity, void *stream);
+HG_API int hg_activate_params_backward(const float *raw_scaling, const float *raw_rotation, const float *raw_opacity,
+                                       int64_t N, int32_t F, const float *g_xyz, const float *g_features,
+                                       const float *g_opacity, const float *g_scaling, const float *g_rotation,
+                                       float beta, float *d_xyz, float *d_features, float *d_opacity,
+                                       float *d_scaling, float *d_rotation, void *stream);
 
 /* Camera intrinsics as Camera.get_calib_matrix_nerf builds them (scene/cameras.py:93-96,135-138). */
 typedef struct hg_intrinsics {

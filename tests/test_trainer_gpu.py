@@ -41,7 +41,8 @@ def test_gradient_arena_accumulates_views(cuda_device):
         loss.backward()
         total += p2.grad_arena
     err = (arena - total).abs().max().item()
-    assert err <= 1e-6 * total.abs().max().item() + 1e-12, err
+    # two evaluations of the same view differ by the order of the backward blend's float atomics (~1e-6 relative)
+    assert err <= 1e-5 * total.abs().max().item() + 1e-12, err
     assert arena.abs().max().item() > 0
 
 
