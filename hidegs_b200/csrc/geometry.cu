@@ -392,14 +392,19 @@ int make_unproj(hg_intrinsics K, int H, int W, Unproj* U) {
 // Adam.
 struct AdamArgs {
   float beta1, beta2, one_m_b1, one_m_b2, step_size, inv_bc2_sqrt, eps, grad_scale;
+  float step_size_head;  // step size of the first `head_cols` columns of every row (the SH DC term)
+  int head_cols;
 };
 
-__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamArgs& a) {
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamArgs& a, float step_size) {
   g *= a.grad_scale;
   m = m * a.beta1 + a.one_m_b1 * g;             // exp_avg.mul_(beta1).add_(grad, alpha=1-beta1)
   v = v * a.beta2 + a.one_m_b2 * (g * g);       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
   const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
-  p = p - a.step_size * (m / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
+  p = p - step_size * (m / denom);              // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+__device__ __forceinline__ float adam_step_of(const AdamArgs& a, int col) {
+  return col < a.head_cols ? a.step_size_head : a.step_size;
 }
 
 __global__ void __launch_bounds__(256)
@@ -407,26 +412,61 @@ adam_dense_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
                   const int64_t n, const int row_width, const uint8_t* __restrict__ visible, const AdamArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if (visible && !visible[i / row_width]) continue;
+    const int64_t row = i / row_width;
+    if (visible && !visible[row]) continue;
     float pp = p[i], mm = m[i], vv = v[i];
-    adam_update(pp, __ldg(g + i), mm, vv, a);
+    adam_update(pp, __ldg(g + i), mm, vv, a, adam_step_of(a, (int)(i - row * row_width)));
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
 
 __global__ void __launch_bounds__(256)
 adam_dense4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
-                   float4* __restrict__ v, const int64_t n4, const AdamArgs a) {
+                   float4* __restrict__ v, const int64_t n4, const AdamArgs a) {  // head_cols == 0 only
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = p[i], mm = m[i], vv = v[i];
     const float4 gg = __ldg(g + i);
-    adam_update(pp.x, gg.x, mm.x, vv.x, a);
-    adam_update(pp.y, gg.y, mm.y, vv.y, a);
-    adam_update(pp.z, gg.z, mm.z, vv.z, a);
-    adam_update(pp.w, gg.w, mm.w, vv.w, a);
+    adam_update(pp.x, gg.x, mm.x, vv.x, a, a.step_size);
+    adam_update(pp.y, gg.y, mm.y, vv.y, a, a.step_size);
+    adam_update(pp.z, gg.z, mm.z, vv.z, a, a.step_size);
+    adam_update(pp.w, gg.w, mm.w, vv.w, a, a.step_size);
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
+}
+
+// row_width % 4 == 0: whole float4s belong to one row, masked rows cost no memory traffic
+__global__ void __launch_bounds__(256)
+adam_masked4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                    float4* __restrict__ v, const int64_t n4, const int row_width4,
+                    const uint8_t* __restrict__ visible, const AdamArgs a) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t row = i / row_width4;
+    if (visible && !visible[row]) continue;
+    const int c0 = 4 * (int)(i - row * row_width4);
+    float4 pp = p[i], mm = m[i], vv = v[i];
+    const float4 gg = __ldg(g + i);
+    adam_update(pp.x, gg.x, mm.x, vv.x, a, adam_step_of(a, c0));
+    adam_update(pp.y, gg.y, mm.y, vv.y, a, adam_step_of(a, c0 + 1));
+    adam_update(pp.z, gg.z, mm.z, vv.z, a, adam_step_of(a, c0 + 2));
+    adam_update(pp.w, gg.w, mm.w, vv.w, a, adam_step_of(a, c0 + 3));
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+// add_densification_stats (scene/gaussian_model.py:763-765) + the max_radii2D update of the training loop
+__global__ void __launch_bounds__(256)
+densification_stats_kernel(const float* __restrict__ grad_means2D, const int* __restrict__ radii, const int64_t N,
+                           float* __restrict__ accum, float* __restrict__ denom, float* __restrict__ max_radii2D) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int r = radii[n];
+  if (r <= 0) return;
+  const float gx = grad_means2D[3 * n], gy = grad_means2D[3 * n + 1];
+  accum[n] = fmaxf(sqrtf(gx * gx + gy * gy), accum[n]);
+  denom[n] += 1.0f;
+  if (max_radii2D) max_radii2D[n] = fmaxf(max_radii2D[n], (float)r);
 }
 
 __global__ void __launch_bounds__(256)
@@ -440,9 +480,10 @@ adam_indexed_kernel(float* __restrict__ p, const float* __restrict__ g, float* _
     int64_t row = idx[e];
     if (row < 0) row += n_rows;  // negative indices wrap, as torch indexing does
     if (row < 0 || row >= n_rows) continue;
-    const int64_t i = row * row_width + (t - e * row_width);
+    const int col = (int)(t - e * row_width);
+    const int64_t i = row * row_width + col;
     float pp = p[i], mm = m[i], vv = v[i];
-    adam_update(pp, __ldg(g + i), mm, vv, a);
+    adam_update(pp, __ldg(g + i), mm, vv, a, adam_step_of(a, col));
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
@@ -598,8 +639,10 @@ int hg_normal_consistency_loss(const float* plane_depth, const float* all_map, c
 
 int hg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n_rows,
                  int32_t row_width, const uint8_t* visible_mask, const int64_t* visible_idx, int64_t n_idx, double lr,
-                 double beta1, double beta2, double eps, int32_t step, float grad_scale, void* st_) {
-  if (n_rows < 0 || row_width <= 0 || step < 1 || (visible_mask && visible_idx) || n_idx < 0 ||
+                 double beta1, double beta2, double eps, int32_t step, float grad_scale, int32_t head_cols,
+                 double head_lr, void* st_) {
+  if (n_rows < 0 || row_width <= 0 || step < 1 || (visible_mask && visible_idx) || n_idx < 0 || head_cols < 0 ||
+      head_cols > row_width ||
       (n_rows > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) {
     set_error("hg_adam_step: bad argument");
     return HG_ERR_INVALID_ARG;
@@ -618,18 +661,38 @@ int hg_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
   a.inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
   a.eps = (float)eps;
   a.grad_scale = grad_scale;
+  a.head_cols = head_cols;
+  a.step_size_head = (float)(head_lr / bc1);
   const int blocks = 148 * 8;
   if (visible_idx) {
     if (n_idx == 0) return HG_OK;
     adam_indexed_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n_rows, row_width, visible_idx, n_idx, a);
-  } else if (!visible_mask && n % 4 == 0 &&
+  } else if (!visible_mask && head_cols == 0 && n % 4 == 0 &&
              (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) {
     adam_dense4_kernel<<<blocks, 256, 0, st>>>((float4*)param, (const float4*)grad, (float4*)exp_avg, (float4*)exp_avg_sq,
                                                n / 4, a);
+  } else if (row_width % 4 == 0 &&
+             (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0) {
+    adam_masked4_kernel<<<blocks, 256, 0, st>>>((float4*)param, (const float4*)grad, (float4*)exp_avg,
+                                                (float4*)exp_avg_sq, n / 4, row_width / 4, visible_mask, a);
   } else {
     adam_dense_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, row_width, visible_mask, a);
   }
   HG_POST_LAUNCH(false, st, "adam_step");
+  return HG_OK;
+}
+
+int hg_densification_stats(const float* grad_means2D, const int32_t* radii, int64_t N, float* xyz_gradient_accum,
+                           float* denom, float* max_radii2D, void* st_) {
+  if (N < 0 || (N > 0 && (!grad_means2D || !radii || !xyz_gradient_accum || !denom))) {
+    set_error("hg_densification_stats: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (N == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  densification_stats_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(grad_means2D, radii, N, xyz_gradient_accum, denom,
+                                                                            max_radii2D);
+  HG_POST_LAUNCH(false, st, "densification_stats");
   return HG_OK;
 }
 

@@ -51,6 +51,6 @@ class Adam(torch.optim.Optimizer):
                         p.data_ptr(), g.data_ptr(), state["exp_avg"].data_ptr(), state["exp_avg_sq"].data_ptr(), rows,
                         width, mask.data_ptr() if mask is not None else None, idx.data_ptr() if idx is not None else None,
                         idx.numel() if idx is not None else 0, float(group["lr"]), float(beta1), float(beta2),
-                        float(group["eps"]), int(state["step"]), float(grad_scale), torch.cuda.current_stream().cuda_stream)
+                        float(group["eps"]), int(state["step"]), float(grad_scale), 0, 0.0, torch.cuda.current_stream().cuda_stream)
                 _lib.check(rc, "adam_step")
         return loss

@@ -167,9 +167,6 @@ class ArenaAdam:
         self.lr = dict(xyz=opt.position_lr_init * spatial_lr_scale, features=opt.feature_lr, opacity=opt.opacity_lr,
                        scaling=opt.scaling_lr, rotation=opt.rotation_lr)
         self.eps, self.step_count = eps, 0
-        # per-element learning-rate multiplier is only needed for the SH block: handled by two strided launches
-        self._sh_lr = torch.full((48,), opt.feature_lr / 20.0)
-        self._sh_lr[:3] = opt.feature_lr
 
     @torch.no_grad()
     def step(self, grad_scale=1.0, visible_mask=None):
@@ -177,42 +174,44 @@ class ArenaAdam:
         p = self.p
         p._act = None  # the activated copies are stale after the update
         st = torch.cuda.current_stream().cuda_stream
-        mask = visible_mask.contiguous().view(torch.uint8).data_ptr() if visible_mask is not None else None
+        mask = None
+        if visible_mask is not None:
+            vm = visible_mask.contiguous()
+            self._mask_keepalive = vm = vm.view(torch.uint8) if vm.dtype == torch.bool else vm
+            mask = vm.data_ptr()
         with torch.cuda.device(p.param_arena.device):
             for name, w in GROUPS:
                 sl = p.slices[name]
                 base = sl.start * 4
                 if name == "features":
-                    # rows of 48 floats: [dc(3) | rest(45)]; the two learning rates need two passes over the block
-                    rc = self._launch(base, p.N, 48, mask, self.lr["features"] / 20.0, grad_scale, st)
+                    # rows of 48 floats: [dc(3) | rest(45)]: two learning rates in one pass
+                    rc = self._launch(base, p.N, 48, mask, self.lr["features"] / 20.0, grad_scale, st, 3, self.lr["features"])
                     _lib.check(rc, "adam_step")
-                    self._fix_dc(sl, grad_scale)
                     continue
                 rc = self._launch(base, p.N, w, mask, self.lr[name], grad_scale, st)
                 _lib.check(rc, "adam_step")
 
-    def _launch(self, byte_off, rows, width, mask, lr, grad_scale, st):
+    def _launch(self, byte_off, rows, width, mask, lr, grad_scale, st, head_cols=0, head_lr=0.0):
         p = self.p
         return _G().hg_adam_step(p.param_arena.data_ptr() + byte_off, p.grad_arena.data_ptr() + byte_off,
                                  self.exp_avg.data_ptr() + byte_off, self.exp_avg_sq.data_ptr() + byte_off, rows, width,
-                                 mask, None, 0, lr, 0.9, 0.999, self.eps, self.step_count, grad_scale, st)
-
-    def _fix_dc(self, sl, grad_scale):
-        # The block was stepped at feature_lr / 20; Adam's update is linear in lr, so the DC columns get the
-        # remaining 19/20 of their step from the already-updated moments:  p -= (lr_dc - lr_rest) / bc1 * m / denom.
-        N = self.p.N
-        m = self.exp_avg[sl].view(N, 48)[:, :3]
-        v = self.exp_avg_sq[sl].view(N, 48)[:, :3]
-        bc1 = 1 - 0.9 ** self.step_count
-        bc2 = 1 - 0.999 ** self.step_count
-        extra = (self.lr["features"] - self.lr["features"] / 20.0) / bc1
-        self.p.param_arena[sl].view(N, 48)[:, :3].addcdiv_(m, v.sqrt() / math.sqrt(bc2) + self.eps, value=-extra)
+                                 mask, None, 0, lr, 0.9, 0.999, self.eps, self.step_count, grad_scale, head_cols, head_lr, st)
 
 
 class ViewShardedTrainer:
-    def __init__(self, params: GaussianParams, background, opt=OptimizationParams, pipe=PipelineParams, group=None):
+    def __init__(self, params: GaussianParams, background, opt=OptimizationParams, pipe=PipelineParams, group=None,
+                 sparse_adam=True, densification_stats=False):
         self.params, self.bg, self.opt, self.pipe, self.group = params, background, opt, pipe, group
         self.adam = ArenaAdam(params, opt)
+        # the reference steps its optimiser on the rows that were visible (`optimizer.step(relevant)`, OurAdam.py:106)
+        self.sparse_adam = sparse_adam and params.param_arena.is_cuda
+        self.visible = torch.zeros(params.N, dtype=torch.uint8, device=params.param_arena.device)
+        self.densification_stats = densification_stats and params.param_arena.is_cuda
+        if self.densification_stats:  # GaussianModel.training_setup (scene/gaussian_model.py:282-294)
+            dev = params.param_arena.device
+            self.xyz_gradient_accum = torch.zeros((params.N, 1), device=dev)
+            self.denom = torch.zeros((params.N, 1), device=dev)
+            self.max_radii2D = torch.zeros(params.N, device=dev)
         self.iteration = 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -239,16 +238,37 @@ class ViewShardedTrainer:
         self.iteration += 1
         self.params.zero_grad()
         total = None
+        if self.sparse_adam:
+            self.visible.zero_()
         for cam, gt in views:
-            loss, _pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations)
+            loss, pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+            if self.sparse_adam:
+                self.visible.index_fill_(0, pkg["visibility_filter"], 1)
+            if self.densification_stats:
+                self._add_densification_stats(pkg)
         self.params.begin_view()
         if self.params.fused and not self.params._grad_dirty:  # no view produced a gradient
             self.params.grad_arena.zero_()
         n_views = len(views)
         if self.world > 1:
             dist.all_reduce(self.params.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
+            if self.sparse_adam:  # union of the ranks' visible sets
+                dist.all_reduce(self.visible, op=dist.ReduceOp.MAX, group=self.group)
             n_views = total_views if total_views is not None else n_views * self.world
-        self.adam.step(grad_scale=1.0 / max(n_views, 1))
+        self.adam.step(grad_scale=1.0 / max(n_views, 1), visible_mask=self.visible if self.sparse_adam else None)
         return total
+
+    def _add_densification_stats(self, pkg):
+        g = pkg["viewspace_points"].grad
+        if g is None:
+            return
+        N = self.params.N
+        radii_full = torch.zeros(N, dtype=torch.int32, device=g.device)
+        radii_full[pkg["visibility_filter"]] = pkg["radii"]
+        with torch.cuda.device(g.device):
+            rc = _G().hg_densification_stats(g.contiguous().data_ptr(), radii_full.data_ptr(), N,
+                                             self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(),
+                                             self.max_radii2D.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "densification_stats")

@@ -100,11 +100,20 @@ HG_API int hg_normal_consistency_loss(const float *plane_depth, const float *all
  *   visible_mask (u8 [n_rows]) or visible_idx (int64 [n_idx], unique entries) or neither (every row, the
  *   reference's _single_tensor_adam2 path for an empty `relevant`).  `step` is the 1-based step count of the
  *   parameter; grad_scale multiplies g on the fly (e.g. 1/views after a SUM all-reduce).  lr / betas / eps are
+ *   The first `head_cols` columns of every row step with `head_lr` instead of `lr` (the SH block [N,16,3] holds the DC
+ *   term, learning rate feature_lr, in its first 3 columns and the rest at feature_lr / 20, as the two parameter groups
+ *   of GaussianModel.training_setup do; head_cols = 0 for a uniform rate).  lr / betas / eps are
  *   doubles, as Python hands them to torch (`1 - beta2` is formed in double before it is narrowed to fp32). */
 HG_API int hg_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n_rows,
                         int32_t row_width, const uint8_t *visible_mask, const int64_t *visible_idx, int64_t n_idx,
                         double lr, double beta1, double beta2, double eps, int32_t step, float grad_scale,
-                        void *stream);
+                        int32_t head_cols, double head_lr, void *stream);
+
+/* GaussianModel.add_densification_stats (scene/gaussian_model.py:763-765) for update_filter = (radii > 0), fused with the
+ * training loop's max_radii2D update:  accum[n] = max(|grad_means2D[n, :2]|, accum[n]); denom[n] += 1;
+ * max_radii2D[n] = max(max_radii2D[n], radii[n]) (max_radii2D may be NULL).  grad_means2D [N,3], radii [N] i32. */
+HG_API int hg_densification_stats(const float *grad_means2D, const int32_t *radii, int64_t N,
+                                  float *xyz_gradient_accum, float *denom, float *max_radii2D, void *stream);
 
 /* Mean squared distance of every point to its 3 nearest neighbours (exact).  points [N,3] -> out [N].
  * workspace: hg_dist2_knn3_workspace_bytes(N) bytes.  No host synchronisation. */

@@ -29,6 +29,7 @@ def _make_trainer():
     t = tr.ViewShardedTrainer.__new__(tr.ViewShardedTrainer)
     t.params, t.bg, t.opt, t.pipe, t.group = params, None, tr.OptimizationParams, tr.PipelineParams, None
     t.iteration = 0
+    t.sparse_adam = t.densification_stats = False  # CUDA-only paths
     t.world = dist.get_world_size() if dist.is_initialized() else 1
     t.rank = dist.get_rank() if dist.is_initialized() else 0
 

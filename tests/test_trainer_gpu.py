@@ -89,3 +89,51 @@ def test_training_reduces_loss(cuda_device):
     losses = [float(trainer.step(views).item()) for _ in range(12)]
     assert np.isfinite(losses).all()
     assert losses[-1] < losses[0], losses
+
+
+def test_sparse_arena_adam_and_densification_stats(cuda_device):
+    """Rows outside the visibility mask keep parameters AND moments (OurAdam.step(relevant)); densification statistics
+    follow GaussianModel.add_densification_stats (max of the screen-space gradient norm, denom += 1) and the
+    max_radii2D update of the training loop."""
+    from hidegs_b200._geometry_lib import lib as G
+    dev = cuda_device
+    sc, cams, gts, tr = _setup(dev, n=5000)
+    params = tr.GaussianParams.from_scene(sc, dev)
+    adam = tr.ArenaAdam(params)
+    before = params.param_arena.clone()
+    g = torch.Generator().manual_seed(3)
+    params.grad_arena.copy_(torch.randn(params.grad_arena.numel(), generator=g).to(dev) * 0.01)
+    mask = (torch.rand(params.N, generator=g) < 0.3).to(dev)
+    adam.step(visible_mask=mask)
+    for name, w in tr.GROUPS:
+        sl = params.slices[name]
+        a, b = params.param_arena[sl].view(params.N, w), before[sl].view(params.N, w)
+        assert torch.equal(a[~mask], b[~mask]), name
+        assert not adam.exp_avg[sl].view(params.N, w)[~mask].any()
+        assert (a[mask] != b[mask]).any()
+    # reference arithmetic on the masked rows (dense torch Adam on a copy restricted to the rows)
+    sl = params.slices["xyz"]
+    ref = torch.nn.Parameter(before[sl].view(params.N, 3)[mask].clone())
+    ref.grad = params.grad_arena[sl].view(params.N, 3)[mask].clone()
+    torch.optim.Adam([ref], lr=tr.OptimizationParams.position_lr_init, eps=1e-15).step()
+    got = params.param_arena[sl].view(params.N, 3)[mask]
+    assert (got - ref.detach()).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    # densification statistics
+    N = 1000
+    grad = torch.randn(N, 3, generator=g).to(dev)
+    radii = torch.randint(-1, 30, (N,), generator=g, dtype=torch.int32).to(dev)
+    accum = torch.rand(N, 1, generator=g).to(dev) * 0.5
+    denom = torch.zeros(N, 1, device=dev)
+    maxr = torch.full((N,), 5.0, device=dev)
+    a0, m0 = accum.clone(), maxr.clone()
+    rc = G().hg_densification_stats(grad.data_ptr(), radii.data_ptr(), N, accum.data_ptr(), denom.data_ptr(), maxr.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    f = radii > 0
+    want = a0.clone()
+    want[f] = torch.max(torch.norm(grad[f, :2], dim=-1, keepdim=True), a0[f])   # gaussian_model.py:764
+    assert torch.allclose(accum, want, rtol=1e-6, atol=0)
+    assert torch.equal(denom[:, 0], f.float())
+    wr = m0.clone()
+    wr[f] = torch.max(m0[f], radii[f].float())
+    assert torch.equal(maxr, wr)
