@@ -14,7 +14,8 @@ __version__ = "0.1.0"
 def install(patch_reference_modules=True):
     """Route the reference's imports to this package (call once, before importing the reference's modules):
 
-        sys.modules: diff_gaussian_rasterization(+._C), simple_knn(+._C)  ->  hidegs_b200's drop-ins
+        sys.modules: diff_gaussian_rasterization(+._C), simple_knn(+._C), gaussian_hierarchy._C.{expand_to_size,
+        get_interpolation_weights}  ->  hidegs_b200's drop-ins
         if importable and `patch_reference_modules`: the reference's own `utils.loss_utils` (l1_loss, l2_loss, ssim,
         get_img_grad_weight, lncc), `scripts.frequency_regularization.frequency_regularization_pyramid_scale`,
         `gaussian_renderer` (render, render_post, render_normal) and `scene.OurAdam.Adam` get their hot functions
@@ -29,6 +30,20 @@ def install(patch_reference_modules=True):
                       ("simple_knn", knn), ("simple_knn._C", knn._C)):
         sys.modules[name] = mod
         done.append(name)
+    # gaussian_hierarchy: only the two run-time operators are replaced; a reference build that also provides the
+    # loaders (load_hierarchy / write_hierarchy) keeps them
+    from . import gaussian_hierarchy as gh
+    try:
+        ref_h = importlib.import_module("gaussian_hierarchy._C")
+    except Exception:
+        ref_h = None
+    if ref_h is None or "hidegs_b200" in (getattr(ref_h, "__file__", "") or ""):
+        sys.modules["gaussian_hierarchy"], sys.modules["gaussian_hierarchy._C"] = gh, gh._C
+        done += ["gaussian_hierarchy", "gaussian_hierarchy._C"]
+    else:
+        for n in ("expand_to_size", "get_interpolation_weights"):
+            setattr(ref_h, n, getattr(gh._C, n))
+            done.append("gaussian_hierarchy._C." + n)
     if not patch_reference_modules:
         return done
     from . import loss_utils as lu, frequency_regularization as fr, gaussian_renderer as gr, optim

@@ -183,3 +183,47 @@ def uav_camera(i, j, grid=8, width=1920, height=1080, altitude=120.0, fovx_deg=7
     tilt = 0.0 if (i + j) % 2 == 0 else math.tan(math.radians(20.0)) * altitude
     target = (cx + tilt, cy, 0.0)
     return look_at_camera(eye, target, (0.0, 1.0, 0.0), math.radians(fovx_deg), width, height)
+
+
+def make_hierarchy(n_leaves, seed=0, fanout=4, extent=(200.0, 112.0, 30.0)):
+    """Synthetic Gaussian hierarchy in the reference's run-time format (submodules/gaussianhierarchy/types.h:18-56,
+    hierarchy_loader.cpp): nodes [N,7] int32 = (depth, parent, start, count_leafs, count_merged, start_children,
+    count_children), boxes [N,2,4] float32 = (min xyz, extent | max xyz, 0).  Leaves (depth 0) hold one Gaussian each;
+    every inner node holds one merged Gaussian; children of a node are contiguous; Gaussians are numbered in node order."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n_leaves, 3), dtype=np.float32) * np.array(extent, np.float32)
+    # group leaves along a space-filling-ish order, then build levels bottom-up
+    order = np.lexsort((pts[:, 2], pts[:, 1] // 8, pts[:, 0] // 8))
+    pts = pts[order]
+    half = (rng.random((n_leaves, 3), dtype=np.float32) * 0.2 + 0.02).astype(np.float32)
+    levels = [dict(lo=pts - half, hi=pts + half, kids=None)]
+    while levels[-1]["lo"].shape[0] > 1:
+        lo, hi = levels[-1]["lo"], levels[-1]["hi"]
+        n = lo.shape[0]
+        groups = [(i, min(i + fanout, n)) for i in range(0, n, fanout)]
+        nlo = np.stack([lo[a:b].min(0) for a, b in groups])
+        nhi = np.stack([hi[a:b].max(0) for a, b in groups])
+        levels.append(dict(lo=nlo, hi=nhi, kids=groups))
+    # number nodes top-down (root first) so that children are contiguous
+    sizes = [lv["lo"].shape[0] for lv in levels]
+    base = np.cumsum([0] + sizes[::-1])[:-1][::-1]  # level l starts at base[l]
+    N = sum(sizes)
+    nodes = np.zeros((N, 7), np.int32)
+    boxes = np.zeros((N, 2, 4), np.float32)
+    for l, lv in enumerate(levels):
+        ids = base[l] + np.arange(sizes[l])
+        boxes[ids, 0, :3], boxes[ids, 1, :3] = lv["lo"], lv["hi"]
+        boxes[ids, 0, 3] = (lv["hi"] - lv["lo"]).max(1)
+        nodes[ids, 0] = l
+        nodes[ids, 1] = -1
+        nodes[ids, 3] = 1 if l == 0 else 0
+        nodes[ids, 4] = 0 if l == 0 else 1
+        nodes[ids, 5] = -1
+        if lv["kids"] is not None:
+            for j, (a, b) in enumerate(lv["kids"]):
+                nodes[ids[j], 5] = base[l - 1] + a
+                nodes[ids[j], 6] = b - a
+                nodes[base[l - 1] + a: base[l - 1] + b, 1] = ids[j]
+    nodes[:, 2] = np.arange(N)  # one Gaussian per node, numbered in node order
+    return torch.from_numpy(nodes), torch.from_numpy(boxes)

@@ -24,6 +24,8 @@
  *                                  autograd backward, fused with the gradient accumulation of a multi-view step)
  *   hg_adam_step                   scene/OurAdam.py:106-337 (Adam update of the parameter groups; dense and
  *                                  visibility-masked "sparse" variant)
+ *   hg_expand_to_size, hg_interpolation_weights   gaussian_hierarchy._C.expand_to_size / get_interpolation_weights
+ *                                  (submodules/gaussianhierarchy/runtime_switching.cu:402-527, torch/torch_interface.cpp:77-119)
  *   hg_dist2_knn3                  simple_knn: distCUDA2 -> SimpleKNN::knn (submodules/simple-knn/spatial.cu:15-26,
  *                                  simple_knn.cu:186-222): mean squared distance to the 3 nearest neighbours
  */
@@ -114,6 +116,23 @@ HG_API int hg_adam_step(float *param, const float *grad, float *exp_avg, float *
  * max_radii2D[n] = max(max_radii2D[n], radii[n]) (max_radii2D may be NULL).  grad_means2D [N,3], radii [N] i32. */
 HG_API int hg_densification_stats(const float *grad_means2D, const int32_t *radii, int64_t N,
                                   float *xyz_gradient_accum, float *denom, float *max_radii2D, void *stream);
+
+/* Hierarchy LOD cut.  nodes [N,7] i32 (types.h:47-56: depth, parent, start, count_leafs,
+ * count_merged, start_children, count_children), boxes [N,2,4] f32 (min xyz + extent, max xyz + pad), viewpoint [3] on
+ * the device.  hg_expand_to_size = Switching::expandToSize (runtime_switching.cu:496-527): for every node whose
+ * projected size is >= target (or whose parent's is), its Gaussians go to render_indices (with the parent node's first
+ * Gaussian in parent_indices and the node id in nodes_for_render_indices; both nullable; node_markers nullable), in
+ * node order.  *out_count (host) receives the number of indices; the index buffers hold `capacity` entries (the reference
+ * writes without a bound).  Synchronises the stream once, as the reference's blocking cudaMemcpy does.
+ * hg_interpolation_weights = Switching::getTsIndexed (:433-494): ts[i], kids[i] for node indices[i]. */
+HG_API size_t hg_expand_to_size_workspace_bytes(int32_t N);
+HG_API int hg_expand_to_size(const int32_t *nodes, const float *boxes, int32_t N, float target_size,
+                             const float *viewpoint, int32_t capacity, int32_t *render_indices,
+                             int32_t *parent_indices, int32_t *nodes_for_render_indices, int32_t *node_markers,
+                             void *workspace, int32_t *out_count, void *stream);
+HG_API int hg_interpolation_weights(const int32_t *indices, int32_t n, float target_size, const int32_t *nodes,
+                                    const float *boxes, float vx, float vy, float vz, float *ts, int32_t *kids,
+                                    void *stream);
 
 /* Mean squared distance of every point to its 3 nearest neighbours (exact).  points [N,3] -> out [N].
  * workspace: hg_dist2_knn3_workspace_bytes(N) bytes.  No host synchronisation. */
