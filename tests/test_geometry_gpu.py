@@ -275,3 +275,33 @@ def _depth_normal_torch(depth, alpha, K):
     n = torch.nn.functional.normalize(n, p=2, dim=-1)
     n = torch.nn.functional.pad(n.permute(2, 0, 1), (1, 1, 1, 1), mode="constant")
     return n * alpha
+
+
+def test_edge_cases(cuda_device):
+    """Empty inputs, minimum image sizes and argument errors of the geometry / optimiser / knn entry points."""
+    from hidegs_b200 import gaussian_renderer as gr
+    from hidegs_b200.optim import Adam
+    from hidegs_b200.simple_knn._C import distCUDA2
+    from hidegs_b200._geometry_lib import lib as G, Intrinsics
+    dev = cuda_device
+    e3, e4 = torch.zeros(0, 3, device=dev), torch.zeros(0, 4, device=dev)
+    am = gr.geometry_all_map(e3, e3, e4, torch.eye(4, device=dev), torch.zeros(3, device=dev))
+    assert am.shape == (0, 5)
+    assert distCUDA2(e3).shape == (0,)
+    p = torch.nn.Parameter(torch.zeros(0, 3, device=dev))
+    p.grad = torch.zeros(0, 3, device=dev)
+    Adam([p], lr=1e-3).step()
+    # 3x3 image: one interior pixel
+    d = torch.tensor([[1.0, 1.1, 1.2], [1.0, 1.2, 1.4], [1.1, 1.3, 1.6]], device=dev)
+    cam = Cam((2.0, 2.0, 1.5, 1.5), 3, 3)
+    n = gr.render_normal(cam, d)
+    want = go.render_normal(d.cpu(), go.intrinsic_matrix(2.0, 2.0, 1.5, 1.5))
+    assert (n.cpu() - want).abs().max().item() <= 1e-6 and n[:, 0].abs().sum().item() == 0
+    # too small an image / bad arguments fail loudly
+    out = torch.zeros(3, 2, 2, device=dev)
+    rc = G().hg_depth_normal(d.data_ptr(), None, 2, 2, Intrinsics(1, 1, 1, 1), out.data_ptr(), None)
+    assert rc == 1
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        distCUDA2(torch.zeros(4, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gr.geometry_all_map(torch.zeros(2, 3), torch.ones(2, 3), torch.ones(2, 4), torch.eye(4), torch.zeros(3))
