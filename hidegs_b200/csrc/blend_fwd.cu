@@ -28,6 +28,8 @@
 //  * early termination: lane (pixel) -> warp (ballot) -> CTA (__syncthreads_or).
 #include "blend_common.cuh"
 
+#include <cstdlib>
+
 namespace hg {
 
 namespace {
@@ -194,6 +196,201 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Variant B: warp per 8x8 sub-tile, TWO pixels per lane (rows r and r+4), 128-thread CTA per tile.  The loop control,
+// the broadcast reads of the staged entry and the observe bookkeeping are shared by the two pixels; each half of the
+// sub-tile has its own exact cull test.  Per-pixel arithmetic and decisions are those of variant A (bit-identical
+// n_contrib / final_T / out_observe).
+constexpr int kThreadsB = 128;
+constexpr int kBatchB = kThreadsB;
+
+struct FwdPixel {
+  float T, C0, C1, C2, Dinv, A0, A1, A2, A3, A4;
+  uint32_t last_contributor;
+  bool done;
+};
+
+template <bool GEO, bool DEPTH, bool INTERP>
+__device__ __forceinline__ bool fwd_pair(FwdPixel& s, const float4* __restrict__ e, const float4 ea, const float2 eb,
+                                         float pixx, float pixy, uint32_t index1) {
+  bool observed = false;
+  if (!s.done) {
+    const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
+    const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
+    const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
+    if (!(power > 0.0f)) {
+      float alpha = fminf(0.99f, __fmul_rn(eb.y, expf(power)));
+      if (INTERP) {
+        const float4 e4 = e[4];
+        const float kidsqrt = __fsub_rn(1.0f, __powf(__fsub_rn(1.0f, alpha), e4.z));
+        alpha = __fmaf_rn(alpha, e4.y, __fmul_rn(__fsub_rn(1.0f, e4.y), kidsqrt));
+      }
+      if (!(alpha < 1.0f / 255.0f)) {
+        const float test_T = __fmul_rn(s.T, __fsub_rn(1.0f, alpha));
+        if (test_T < 0.0001f) {
+          s.done = true;
+        } else {
+          const float wgt = __fmul_rn(alpha, s.T);
+          const float4 ec = e[2];
+          s.C0 = __fmaf_rn(wgt, ec.x, s.C0);
+          s.C1 = __fmaf_rn(wgt, ec.y, s.C1);
+          s.C2 = __fmaf_rn(wgt, ec.z, s.C2);
+          if (DEPTH) s.Dinv = __fmaf_rn(wgt, ec.w, s.Dinv);
+          if (GEO) {
+            const float4 ed = e[3];
+            const float ee = e[4].x;
+            s.A0 = __fmaf_rn(wgt, ed.x, s.A0);
+            s.A1 = __fmaf_rn(wgt, ed.y, s.A1);
+            s.A2 = __fmaf_rn(wgt, ed.z, s.A2);
+            s.A3 = __fmaf_rn(wgt, ed.w, s.A3);
+            s.A4 = __fmaf_rn(wgt, ee, s.A4);
+          }
+          observed = s.T > 0.5f;
+          s.T = test_T;
+          s.last_contributor = index1;
+        }
+      }
+    }
+  }
+  return observed;
+}
+
+template <bool GEO, bool DEPTH>
+__device__ __forceinline__ void write_pixel(const FwdPixel& s, bool inside, size_t pix, size_t HW, float pixx, float pixy,
+                                            float cx, float cy, float focal_x, float focal_y,
+                                            const float* __restrict__ bg_color, float* __restrict__ final_T,
+                                            uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+                                            float* __restrict__ out_invdepth, float* __restrict__ out_all_map,
+                                            float* __restrict__ out_plane_depth) {
+  if (!inside) return;
+  final_T[pix] = s.T;
+  n_contrib[pix] = s.last_contributor;
+  out_color[pix] = __fmaf_rn(s.T, __ldg(bg_color), s.C0);
+  out_color[HW + pix] = __fmaf_rn(s.T, __ldg(bg_color + 1), s.C1);
+  out_color[2 * HW + pix] = __fmaf_rn(s.T, __ldg(bg_color + 2), s.C2);
+  if (DEPTH) out_invdepth[pix] = s.Dinv;
+  if (GEO) {
+    out_all_map[pix] = s.A0;
+    out_all_map[HW + pix] = s.A1;
+    out_all_map[2 * HW + pix] = s.A2;
+    out_all_map[3 * HW + pix] = s.A3;
+    out_all_map[4 * HW + pix] = s.A4;
+    // plane depth (forward.cu:474,607): float ray, double add/div.
+    const float rayx = __fdiv_rn(__fsub_rn(pixx, cx), focal_x);
+    const float rayy = __fdiv_rn(__fsub_rn(pixy, cy), focal_y);
+    const float den = __fadd_rn(s.A2, __fmaf_rn(rayx, s.A0, __fmul_rn(rayy, s.A1)));
+    out_plane_depth[pix] = (float)__ddiv_rn((double)s.A4, -__dadd_rn((double)den, 1.0e-8));
+  } else {
+    out_all_map[pix] = 0.f;
+    out_all_map[HW + pix] = 0.f;
+    out_all_map[2 * HW + pix] = 0.f;
+    out_all_map[3 * HW + pix] = 0.f;
+    out_all_map[4 * HW + pix] = 0.f;
+    out_plane_depth[pix] = 0.f;
+  }
+}
+
+template <bool GEO, bool DEPTH, bool INTERP>
+__global__ void __launch_bounds__(kThreadsB)
+blend_fwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                  const float4* __restrict__ records, const float* __restrict__ ts,
+                  const int* __restrict__ kids, const int W, const int H, const float focal_x,
+                  const float focal_y, const float cx, const float cy,
+                  const float* __restrict__ bg_color, float* __restrict__ final_T,
+                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+                  float* __restrict__ out_invdepth, int* __restrict__ out_observe,
+                  float* __restrict__ out_all_map, float* __restrict__ out_plane_depth) {
+  __shared__ float4 s_rec[kBatchB * kRecQuads];
+  __shared__ int s_obs[kBatchB];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
+  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 8;
+  const int pxi = wx0 + (lane & 7), pyA = wy0 + (lane >> 3), pyB = pyA + 4;
+  const bool insideA = pxi < W && pyA < H, insideB = pxi < W && pyB < H;
+  const float pixx = (float)pxi, pixyA = (float)pyA, pixyB = (float)pyB;
+  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7);
+  const float fyA0 = (float)wy0, fyA1 = (float)(wy0 + 3), fyB0 = (float)(wy0 + 4), fyB1 = (float)(wy0 + 7);
+
+  const uint2 range = ranges[tile];
+  const int n = (int)(range.y - range.x);
+  const int nb = (n + kBatchB - 1) / kBatchB;
+
+  FwdPixel A{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0u, !insideA};
+  FwdPixel B{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0u, !insideB};
+
+  Prefetch pf;
+  auto prefetch = [&](int b) {
+    const int i = b * kBatchB + tid;
+    if (i < n) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + i);
+  };
+  if (nb > 0) prefetch(0);
+
+  bool pending_flush = false;
+  for (int b = 0; b < nb; ++b) {
+    const int any_active = __syncthreads_or(!(A.done && B.done));
+    if (pending_flush) {
+      const int c = s_obs[tid];
+      if (c) atomicAdd(out_observe + __float_as_int(s_rec[kRecQuads * tid + 1].w), c);
+      pending_flush = false;
+    }
+    if (!any_active) break;
+
+    const int cnt = min(kBatchB, n - b * kBatchB);
+    if (tid < cnt) stage_record<GEO, INTERP>(s_rec, tid, pf);
+    s_obs[tid] = 0;
+    __syncthreads();
+    if (b + 1 < nb) prefetch(b + 1);
+    pending_flush = true;
+
+    uint32_t liveA = __ballot_sync(0xffffffffu, !A.done), liveB = __ballot_sync(0xffffffffu, !B.done);
+    if ((liveA | liveB) == 0) continue;  // whole warp finished
+    const uint32_t base = (uint32_t)(b * kBatchB);
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+      const int j = c0 + lane;
+      bool keepA = false, keepB = false;
+      if (j < cnt) {
+        const float4 ea = s_rec[kRecQuads * j];
+        const float4 eb = s_rec[kRecQuads * j + 1];
+        keepA = liveA != 0 && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyA0, fyA1);
+        keepB = liveB != 0 && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyB0, fyB1);
+      }
+      const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
+      uint32_t mask = maskA | maskB;
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int k = c0 + bit;
+        const float4* e = s_rec + kRecQuads * k;
+        const float4 ea = e[0];
+        const float2 eb = *reinterpret_cast<const float2*>(e + 1);
+        const uint32_t index1 = base + (uint32_t)k + 1u;
+        bool obsA = false, obsB = false;
+        if ((maskA >> bit) & 1u) obsA = fwd_pair<GEO, DEPTH, INTERP>(A, e, ea, eb, pixx, pixyA, index1);
+        if ((maskB >> bit) & 1u) obsB = fwd_pair<GEO, DEPTH, INTERP>(B, e, ea, eb, pixx, pixyB, index1);
+        const uint32_t oa = __ballot_sync(0xffffffffu, obsA), ob = __ballot_sync(0xffffffffu, obsB);
+        if ((oa | ob) && lane == 0) atomicAdd(&s_obs[k], __popc(oa) + __popc(ob));
+      }
+      liveA = __ballot_sync(0xffffffffu, !A.done);
+      liveB = __ballot_sync(0xffffffffu, !B.done);
+      if ((liveA | liveB) == 0) break;
+    }
+  }
+  if (pending_flush) {
+    __syncthreads();
+    const int c = s_obs[tid];
+    if (c) atomicAdd(out_observe + __float_as_int(s_rec[kRecQuads * tid + 1].w), c);
+  }
+
+  const size_t HW = (size_t)H * W;
+  write_pixel<GEO, DEPTH>(A, insideA, (size_t)pyA * W + pxi, HW, pixx, pixyA, cx, cy, focal_x, focal_y, bg_color, final_T,
+                          n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
+  write_pixel<GEO, DEPTH>(B, insideB, (size_t)pyB * W + pxi, HW, pixx, pixyB, cx, cy, focal_x, focal_y, bg_color, final_T,
+                          n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
+}
+
 template <bool GEO, bool DEPTH>
 int dispatch(bool interp, dim3 grid, cudaStream_t stream, const uint2* ranges,
              const uint32_t* point_list, const float4* records, const float* ts, const int* kids,
@@ -201,6 +398,21 @@ int dispatch(bool interp, dim3 grid, cudaStream_t stream, const uint2* ranges,
              uint32_t* n_contrib, float* out_color, float* out_invdepth, int* out_observe,
              float* out_all_map, float* out_plane_depth) {
   const float cx = float(W * 0.5f), cy = float(H * 0.5f);
+  static const int variant = [] {
+    const char* e = getenv("HG_BLEND_FWD_VARIANT");
+    return e ? atoi(e) : 2;
+  }();
+  if (variant == 2) {
+    if (interp)
+      blend_fwd2_kernel<GEO, DEPTH, true><<<grid, kThreadsB, 0, stream>>>(
+          ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
+          out_color, out_invdepth, out_observe, out_all_map, out_plane_depth);
+    else
+      blend_fwd2_kernel<GEO, DEPTH, false><<<grid, kThreadsB, 0, stream>>>(
+          ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
+          out_color, out_invdepth, out_observe, out_all_map, out_plane_depth);
+    return 0;
+  }
   if (interp)
     blend_fwd_kernel<GEO, DEPTH, true><<<grid, HG_BLOCK_SIZE, 0, stream>>>(
         ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
