@@ -71,6 +71,15 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   float* const tile = s_sh[warp];
   const size_t warp_base = (size_t)(blockIdx.x * kThreads + warp * 32) * row;
   const size_t sh_total = (size_t)P * row;
+  // The thread's own rows are requested BEFORE the cooperative SH staging so that both are in flight together.
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  if (alive) {
+    const float4* ar = reinterpret_cast<const float4*>(accum) + 4 * (size_t)t_idx;
+    a0 = __ldg(ar); a1 = __ldg(ar + 1); a2 = __ldg(ar + 2); a3 = __ldg(ar + 3);
+    const size_t gpre = indices ? (size_t)__ldg(indices + t_idx) : (size_t)t_idx;
+    mx = __ldg(means3D + 3 * gpre); my = __ldg(means3D + 3 * gpre + 1); mz = __ldg(means3D + 3 * gpre + 2);
+  }
   if (staged && alive_mask) {
     if (row == 48) stage_sh_rows<48>(shs, warp_base, sh_total, row, lane, tile, alive_mask);
     else stage_sh_rows<0>(shs, warp_base, sh_total, row, lane, tile, alive_mask);
@@ -102,8 +111,6 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   }
 
   // ---- accumulator row --------------------------------------------------------
-  const float4* ar = reinterpret_cast<const float4*>(accum) + 4 * (size_t)t_idx;
-  const float4 a0 = ar[0], a1 = ar[1], a2 = ar[2], a3 = ar[3];
   const float dcol[3] = {a0.x, a0.y, a0.z};
   const float dinvd = a0.w;
   const float dam[5] = {a1.x, a1.y, a1.z, a1.w, a2.x};
@@ -133,8 +140,6 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
     v[i] = __ldg(viewmatrix + i);
     pm[i] = __ldg(projmatrix + i);
   }
-  const float mx = __ldg(means3D + 3 * g), my = __ldg(means3D + 3 * g + 1),
-              mz = __ldg(means3D + 3 * g + 2);
 
   // ---- conic -> 2-D covariance -> 3-D covariance / mean (backward.cu:147-326) --
   const float* c3 = cov_precomp ? (cov3Ds + 6 * g) : (cov3Ds + 6 * (size_t)t_idx);

@@ -14,23 +14,38 @@ __device__ __forceinline__ void stage_sh_rows(const float* __restrict__ shs, siz
   const int row = ROW > 0 ? ROW : row_rt;
   const int stride = row | 1;
   const int nfloat = 32 * row;  // multiple of 4
-  for (int i = lane * 4; i < nfloat; i += 128) {
-    const size_t gi = base + i;
-    if (!((row_mask >> (i / row)) & 1u)) continue;  // rows nobody will read (row % 4 == 0: a float4 never straddles rows)
-    float4 val;
-    if (gi + 3 < total) {
-      val = __ldg((const float4*)(shs + gi));
-    } else {
-      val.x = gi < total ? __ldg(shs + gi) : 0.f;
-      val.y = gi + 1 < total ? __ldg(shs + gi + 1) : 0.f;
-      val.z = gi + 2 < total ? __ldg(shs + gi + 2) : 0.f;
-      val.w = 0.f;
-    }
-    const float e[4] = {val.x, val.y, val.z, val.w};
+  // Loads are issued in groups of kGroup independent LDG.128 before any of them is consumed, so a warp keeps
+  // several 512-byte requests in flight (the staging is latency bound otherwise).
+  constexpr int kGroup = 4;
+  for (int i0 = lane * 4; i0 < nfloat; i0 += 128 * kGroup) {
+    float4 val[kGroup];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int f = i + k;
-      dst[(f / row) * stride + (f % row)] = e[k];
+    for (int u = 0; u < kGroup; ++u) {
+      const int i = i0 + 128 * u;
+      const size_t gi = base + i;
+      val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // skip rows nobody will read (row % 4 == 0: a float4 never straddles rows)
+      if (i < nfloat && ((row_mask >> (i / row)) & 1u)) {
+        if (gi + 3 < total) {
+          val[u] = __ldg((const float4*)(shs + gi));
+        } else {
+          val[u].x = gi < total ? __ldg(shs + gi) : 0.f;
+          val[u].y = gi + 1 < total ? __ldg(shs + gi + 1) : 0.f;
+          val[u].z = gi + 2 < total ? __ldg(shs + gi + 2) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int i = i0 + 128 * u;
+      if (i < nfloat && ((row_mask >> (i / row)) & 1u)) {
+        const float e[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int f = i + k;
+          dst[(f / row) * stride + (f % row)] = e[k];
+        }
+      }
     }
   }
 }
