@@ -175,6 +175,8 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
   const bool in_range = t_idx < P;
 
   bool alive = in_range;
+  float pre_s[3] = {0.f, 0.f, 0.f}, pre_o = 0.f, pre_am[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  float4 pre_q = make_float4(0.f, 0.f, 0.f, 0.f);
   int r_idx = 0, p_idx = -1;
   float t = 0.0f;
   bool has_parent = false;
@@ -196,6 +198,19 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
     px = __ldg(means3D + 3 * (size_t)r_idx);
     py = __ldg(means3D + 3 * (size_t)r_idx + 1);
     pz = __ldg(means3D + 3 * (size_t)r_idx + 2);
+    // Everything else this slot will need is requested now, next to the mean (one round trip instead of a chain of
+    // dependent ones; culled slots pay ~32 bytes of traffic that share their neighbours' sectors anyway).
+    if (cov3D_precomp == nullptr) {
+      pre_s[0] = __ldg(scales + 3 * (size_t)r_idx);
+      pre_s[1] = __ldg(scales + 3 * (size_t)r_idx + 1);
+      pre_s[2] = __ldg(scales + 3 * (size_t)r_idx + 2);
+      pre_q = __ldg((const float4*)rotations + r_idx);
+    }
+    pre_o = __ldg(opacities + r_idx);
+    if (all_map) {
+#pragma unroll
+      for (int c = 0; c < 5; ++c) pre_am[c] = __ldg(all_map + 5 * (size_t)t_idx + c);
+    }
     if (parent_indices) {
       p_idx = __ldg(parent_indices + t_idx);
       if (p_idx != -1) {
@@ -227,9 +242,8 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
     if (alive) {
       float c3[6];
       if (cov3D_precomp == nullptr) {
-        float sx = __ldg(scales + 3 * (size_t)r_idx), sy = __ldg(scales + 3 * (size_t)r_idx + 1),
-              sz = __ldg(scales + 3 * (size_t)r_idx + 2);
-        const float4 q4 = __ldg((const float4*)rotations + r_idx);
+        float sx = pre_s[0], sy = pre_s[1], sz = pre_s[2];
+        const float4 q4 = pre_q;
         float qr = q4.x, qx = q4.y, qy = q4.z, qz = q4.w;
         if (has_parent) {  // forward.cu:332-343
           const float omt = __fsub_rn(1.0f, t);
@@ -284,7 +298,7 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
         const int ey = __float2int_rz(ceilf(__fmul_rn(3.0f, __fsqrt_rn(dyy))));
         get_rect_ref(pix_x, pix_y, ex, ey, grid_x, grid_y, minx, miny, maxx, maxy);
         alive = ((maxx - minx) * (maxy - miny)) != 0;
-        float o = __ldg(opacities + r_idx);
+        float o = pre_o;
         if (has_parent) o = __fmaf_rn(t, o, __fmul_rn(__fsub_rn(1.0f, t), __ldg(opacities + p_idx)));
         opac = __fmul_rn(o, h_scale);
       }
@@ -340,11 +354,7 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
 
   if (!alive) return;
 
-  float am[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (all_map) {
-#pragma unroll
-    for (int c = 0; c < 5; ++c) am[c] = __ldg(all_map + 5 * (size_t)t_idx + c);
-  }
+  const float* am = pre_am;
   depths[t_idx] = depth;
   radii[t_idx] = my_radius;
   rects[t_idx] = make_uint2(minx | (miny << 16), maxx | (maxy << 16));

@@ -74,11 +74,23 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   // The thread's own rows are requested BEFORE the cooperative SH staging so that both are in flight together.
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
   float mx = 0.f, my = 0.f, mz = 0.f;
+  float pre_c3[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pre_opacity = 0.f, pre_scale[3] = {0.f, 0.f, 0.f};
+  float4 pre_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint8_t pre_clamped = 0;
   if (alive) {
     const float4* ar = reinterpret_cast<const float4*>(accum) + 4 * (size_t)t_idx;
     a0 = __ldg(ar); a1 = __ldg(ar + 1); a2 = __ldg(ar + 2); a3 = __ldg(ar + 3);
     const size_t gpre = indices ? (size_t)__ldg(indices + t_idx) : (size_t)t_idx;
     mx = __ldg(means3D + 3 * gpre); my = __ldg(means3D + 3 * gpre + 1); mz = __ldg(means3D + 3 * gpre + 2);
+    const float* c3p = cov_precomp ? (cov3Ds + 6 * gpre) : (cov3Ds + 6 * (size_t)t_idx);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pre_c3[i] = __ldg(c3p + i);
+    pre_opacity = __ldg(opacities + gpre);
+    if (scales) {
+      pre_scale[0] = __ldg(scales + 3 * gpre); pre_scale[1] = __ldg(scales + 3 * gpre + 1); pre_scale[2] = __ldg(scales + 3 * gpre + 2);
+      pre_rot = __ldg((const float4*)rotations + gpre);
+    }
+    if (shs) pre_clamped = clamped[t_idx];
   }
   if (staged && alive_mask) {
     if (row == 48) stage_sh_rows<48>(shs, warp_base, sh_total, row, lane, tile, alive_mask);
@@ -142,8 +154,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   }
 
   // ---- conic -> 2-D covariance -> 3-D covariance / mean (backward.cu:147-326) --
-  const float* c3 = cov_precomp ? (cov3Ds + 6 * g) : (cov3Ds + 6 * (size_t)t_idx);
-  const float V00 = c3[0], V01 = c3[1], V02 = c3[2], V11 = c3[3], V12 = c3[4], V22 = c3[5];
+  const float V00 = pre_c3[0], V01 = pre_c3[1], V02 = pre_c3[2], V11 = pre_c3[3], V12 = pre_c3[4], V22 = pre_c3[5];
 
   float tx = v[0] * mx + v[4] * my + v[8] * mz + v[12];
   float ty = v[1] * mx + v[5] * my + v[9] * mz + v[13];
@@ -180,7 +191,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   const float det_cov_plus_h = c_xx * c_yy - c_xy * c_xy;
   const float ratio = det_cov / det_cov_plus_h;
   const float h_scale = sqrtf(fmaxf(0.000025f, ratio));
-  const float d_h_scale = dopac_raw * __ldg(opacities + g);
+  const float d_h_scale = dopac_raw * pre_opacity;
   float dopac = dopac_raw * h_scale;
   const float d_inside_root = (ratio <= 0.000025f) ? 0.f : d_h_scale / (2.f * h_scale);
 
@@ -260,7 +271,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
     const float ox = mx - __ldg(campos), oy = my - __ldg(campos + 1), oz = mz - __ldg(campos + 2);
     const float len = sqrtf(ox * ox + oy * oy + oz * oz);
     const float x = ox / len, y = oy / len, z = oz / len;
-    const uint8_t cb = clamped[t_idx];
+    const uint8_t cb = pre_clamped;
     const float dr = (cb & 1) ? 0.f : dcol[0], dg = (cb & 2) ? 0.f : dcol[1],
                 db = (cb & 4) ? 0.f : dcol[2];
     const float* sh = staged ? tile + lane * (row | 1) : shs + g * row;
@@ -335,10 +346,10 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   // ---- 3-D covariance -> scale / rotation (backward.cu:330-393) -------------------
   float dsx = 0.f, dsy = 0.f, dsz = 0.f, dqr = 0.f, dqx = 0.f, dqy = 0.f, dqz = 0.f;
   if (scales) {
-    const float4 q4 = __ldg((const float4*)rotations + idx);
+    const float4 q4 = pre_rot;
     const float r = q4.x, x = q4.y, y = q4.z, z = q4.w;
-    const float s0 = scale_modifier * __ldg(scales + 3 * g), s1 = scale_modifier * __ldg(scales + 3 * g + 1),
-                s2 = scale_modifier * __ldg(scales + 3 * g + 2);
+    const float s0 = scale_modifier * pre_scale[0], s1 = scale_modifier * pre_scale[1],
+                s2 = scale_modifier * pre_scale[2];
     // R[c][r] as constructed in the forward (glm column-major argument order).
     const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
                            {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
