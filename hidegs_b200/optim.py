@@ -43,6 +43,8 @@ class Adam(torch.optim.Optimizer):
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state["step"] += 1
+                if p.numel() == 0:
+                    continue
                 g = p.grad.contiguous()
                 rows = p.size(0) if p.dim() > 0 else 1
                 width = p.numel() // max(rows, 1)
