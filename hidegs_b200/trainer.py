@@ -216,11 +216,14 @@ class ViewShardedTrainer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
-    def view_loss(self, cam, gt, iteration):
-        """Forward of one view: returns (loss tensor, render package)."""
+    def view_loss(self, cam, gt, iteration, gt_ready=None):
+        """Forward of one view: returns (loss tensor, render package).  `gt_ready`: CUDA event after which `gt` holds
+        the image (an upload running on a copy stream while the view renders)."""
         o = self.opt
         self.params.begin_view()
         pkg = gr.render(cam, self.params, self.pipe, self.bg)
+        if gt_ready is not None:
+            torch.cuda.current_stream().wait_event(gt_ready)
         image = pkg["render"]
         loss = (1.0 - o.lambda_dssim) * lu.l1_loss(image, gt) + o.lambda_dssim * (1.0 - lu.ssim(image, gt))
         freq, _mask, _info = frequency_regularization_pyramid_scale(
@@ -234,14 +237,17 @@ class ViewShardedTrainer:
         return loss, pkg
 
     def step(self, views, total_views=None):
-        """One optimiser step over this rank's `views` = [(camera, gt_image), ...]; returns the summed loss tensor."""
+        """One optimiser step over this rank's `views` = [(camera, gt_image[, gt_ready_event]), ...]; returns the summed
+        loss tensor."""
         self.iteration += 1
         self.params.zero_grad()
         total = None
         if self.sparse_adam:
             self.visible.zero_()
-        for cam, gt in views:
-            loss, pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations)
+        for view in views:
+            cam, gt = view[0], view[1]
+            loss, pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations,
+                                       view[2] if len(view) > 2 else None)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             if self.sparse_adam:

@@ -33,7 +33,7 @@ def _make_trainer():
     t.world = dist.get_world_size() if dist.is_initialized() else 1
     t.rank = dist.get_rank() if dist.is_initialized() else 0
 
-    def view_loss(cam, gt, iteration):  # cam: a seed-like float, gt: a target vector
+    def view_loss(cam, gt, iteration, gt_ready=None):  # cam: a seed-like float, gt: a target vector
         p = params
         val = ((p.get_xyz * cam).sum(1) + p.get_opacity[:, 0] * p.get_scaling.sum(1) + p.get_features.mean((1, 2))
                + (p.get_rotation * gt).sum(1))
