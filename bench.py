@@ -327,6 +327,11 @@ def run_gpu_arm(args, impl):
             torch.cuda.empty_cache()
             train_c3 = train_leg(dev, rank, world, False, steps=max(3, min(K, 10)), warmup=3, views_per_rank=1,
                                  n_gauss=n_train, recipe="c2")
+            torch.cuda.empty_cache()
+            # the same step with every ground-truth-only quantity recomputed at every visit (no per-camera cache)
+            unc = train_leg(dev, rank, world, False, steps=max(3, min(K, 10)), warmup=3, views_per_rank=1,
+                            n_gauss=n_train, recipe="c2", cache_gt=False)
+            train_c3["views_per_s_uncached_ground_truth"] = unc["views_per_s"]
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import loss_bench
             losses = loss_bench.measure(dev, iters=10, warmup=3, cpu=not os.environ.get("HG_BENCH_SKIP_CPU"))
@@ -406,7 +411,7 @@ def make_gt_images(n, dev, seed=11):
     return out
 
 
-def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, recipe):
+def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, recipe, cache_gt=True):
     """Training views/s (BASELINE.json metric 2): full HiDeGS step = render (prologue + rasterizer + epilogue) + L1 +
     SSIM + frequency regularisation + scale regularisation + single-view normal term, backward, gradient all-reduce
     over the ranks, fused Adam.  `recipe`: "uav" = configs[4] (8x8 survey cameras over the 400 m x 224 m slab, views
@@ -423,7 +428,7 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     cams = cams_all[:total_views][rank::world]
     gts = make_gt_images(views_per_rank, dev, seed=11 + rank)
     params = tr.GaussianParams.from_scene(scene, dev)
-    trainer = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev))
+    trainer = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev), cache_ground_truth=cache_gt)
 
     # Ground-truth images travel host -> device on a copy stream, one event per view (the losses of a view wait for
     # its image only), double buffered across steps so that uploads of step k+1 may start while step k still computes.
@@ -472,6 +477,7 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
             "ms_per_view": round(ms_step / views_per_rank, 3), "views_per_rank_per_step": views_per_rank,
             "views_per_step": total_views, "gaussians": n_gauss, "steps": steps, "warmup": warmup,
             "loss_last_step_rank0": round(last, 6), "gpu_launches": int(_lib.lib().hg_launch_count()),
+            "ground_truth_cache": bool(cache_gt),
             "allreduce_bytes_per_step": params.grad_arena.numel() * 4 if world > 1 else 0,
             "h2d_bytes_per_step": views_per_rank * 3 * HEIGHT * WIDTH * 4,
             "workload": ("configs[4]: view-sharded training, %d UAV survey cameras per step over the 2M-Gaussian slab, %dx%d, "

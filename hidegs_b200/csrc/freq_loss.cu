@@ -844,7 +844,7 @@ int hg_fft2_c2r(const float* spec, int32_t H, int32_t W, float* img, int scale_i
 }
 
 size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels) {
-  size_t total = 4096 + (size_t)kSumBlocks * 8 * 8 + 1024;
+  size_t total = 4096 + (size_t)kSumBlocks * 8 * 8 + 1024 + hg_freq_gt_state_bytes(H, W, levels);
   int h = H, w = W;
   for (int l = 0; l < levels; ++l) {
     total += level_bytes(h, w);
@@ -854,14 +854,27 @@ size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels) {
   return total;
 }
 
-int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, int32_t levels, float* stats,
-                 float* grad_rendered, void* ws, void* st_) {
-  if (!rendered || !gt || !stats || !ws || levels < 1 || levels > 3 || H < 4 || W < 4) {
-    set_error("hg_freq_loss: bad argument");
+// Ground-truth side of the frequency loss for one image: gray pyramid, its spectra and the level-0 band sums.
+struct GtState {
+  float* gg[3];
+  float2* fg[3];
+  double* band0;
+};
+
+static void carve_gt_state(void* base, int levels, const int* hs, const int* wsz, GtState* g) {
+  Carver cv(base);
+  for (int l = 0; l < levels; ++l) {
+    g->gg[l] = cv.take<float>((size_t)hs[l] * wsz[l]);
+    g->fg[l] = cv.take<float2>((size_t)hs[l] * (wsz[l] / 2 + 1));
+  }
+  g->band0 = cv.take<double>((size_t)kSumBlocks * 8);
+}
+
+static int level_sizes(int32_t H, int32_t W, int32_t levels, int* hs, int* wsz) {
+  if (levels < 1 || levels > 3 || H < 4 || W < 4) {
+    set_error("frequency loss: bad size / level count");
     return HG_ERR_INVALID_ARG;
   }
-  cudaStream_t st = (cudaStream_t)st_;
-  int hs[3], wsz[3];
   hs[0] = H; wsz[0] = W;
   for (int l = 1; l < levels; ++l) { hs[l] = hs[l - 1] / 2; wsz[l] = wsz[l - 1] / 2; }
   for (int l = 0; l < levels; ++l) {
@@ -869,35 +882,100 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
     int rc = make_cfg(hs[l], wsz[l], &c);
     if (rc) return rc;
   }
+  return HG_OK;
+}
+
+static int prepare_gt(const float* gt, int levels, const int* hs, const int* wsz, const GtState& g, cudaStream_t st) {
+  const int64_t hw0 = (int64_t)hs[0] * wsz[0];
+  gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(gt, hw0, g.gg[0]);
+  HG_POST_LAUNCH(false, st, "gray");
+  for (int l = 1; l < levels; ++l) {
+    const dim3 grid((wsz[l] + 127) / 128, hs[l]);
+    pool_kernel<<<grid, 128, 0, st>>>(g.gg[l - 1], wsz[l - 1], hs[l], wsz[l], g.gg[l]);
+    HG_POST_LAUNCH(false, st, "pool");
+  }
+  for (int l = 0; l < levels; ++l) {
+    int rc = fft2_r2c(g.gg[l], g.fg[l], nullptr, nullptr, hs[l], wsz[l], 1, st);
+    if (rc) return rc;
+  }
+  band_energy_kernel<<<kSumBlocks, 256, 0, st>>>(g.fg[0], hs[0], wsz[0], g.band0);
+  HG_POST_LAUNCH(false, st, "band_energy");
+  return HG_OK;
+}
+
+size_t hg_freq_gt_state_bytes(int32_t H, int32_t W, int32_t levels) {
+  size_t total = 1024 + (size_t)kSumBlocks * 8 * 8 + 256;
+  int h = H, w = W;
+  for (int l = 0; l < levels; ++l) {
+    total += ((size_t)h * w * 4 + 256) + ((size_t)h * (w / 2 + 1) * 8 + 256);
+    h /= 2;
+    w /= 2;
+  }
+  return total;
+}
+
+int hg_freq_gt_prepare(const float* gt, int32_t H, int32_t W, int32_t levels, void* gt_state, void* st_) {
+  if (!gt || !gt_state) {
+    set_error("hg_freq_gt_prepare: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  int hs[3], wsz[3];
+  int rc = level_sizes(H, W, levels, hs, wsz);
+  if (rc) return rc;
+  GtState g;
+  carve_gt_state(gt_state, levels, hs, wsz, &g);
+  return prepare_gt(gt, levels, hs, wsz, g, (cudaStream_t)st_);
+}
+
+// gt != NULL: the ground-truth side is computed into the workspace; gt_state != NULL: it is read from a state
+// prepared by hg_freq_gt_prepare (the ground truth of a camera does not change between its visits).
+static int freq_loss_impl(const float* rendered, const float* gt, void* gt_state, int32_t H, int32_t W, int32_t levels,
+                          float* stats, float* grad_rendered, void* ws, cudaStream_t st) {
+  if (!rendered || (!gt && !gt_state) || !stats || !ws) {
+    set_error("hg_freq_loss: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  int hs[3], wsz[3];
+  int rc0 = level_sizes(H, W, levels, hs, wsz);
+  if (rc0) return rc0;
   Carver cv(ws);
   LevelCtl* ctl = cv.take<LevelCtl>(3);
-  double* band0 = cv.take<double>((size_t)kSumBlocks * 8);
   double* sums = cv.take<double>(kFreqSums);
-  float *gr[3], *gg[3], *dg[3];
-  float2 *fr[3], *fg[3];
+  float *gr[3], *dg[3];
+  float2* fr[3];
   double *sp_part[3], *spec_part[3];
   int sp_blocks[3];
   for (int l = 0; l < levels; ++l) {
     const size_t hw = (size_t)hs[l] * wsz[l], sp = (size_t)hs[l] * (wsz[l] / 2 + 1);
     gr[l] = cv.take<float>(hw);
-    gg[l] = cv.take<float>(hw);
     dg[l] = cv.take<float>(hw);
     fr[l] = cv.take<float2>(sp);
-    fg[l] = cv.take<float2>(sp);
     sp_blocks[l] = ((wsz[l] + kSpTile - 1) / kSpTile) * ((hs[l] + kSpTile - 1) / kSpTile);
     sp_part[l] = cv.take<double>((size_t)sp_blocks[l] * 3);
     spec_part[l] = cv.take<double>((size_t)kSumBlocks * kSpecVals);
   }
+  GtState G;
+  const bool cached = gt_state != nullptr;
+  carve_gt_state(cached ? gt_state : (void*)cv.p, levels, hs, wsz, &G);
+  float** gg = G.gg;
+  float2** fg = G.fg;
+  double* band0 = G.band0;
   // ---- forward
   const int64_t hw0 = (int64_t)H * W;
   gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(rendered, hw0, gr[0]);
-  gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(gt, hw0, gg[0]);
   HG_POST_LAUNCH(false, st, "gray");
+  if (!cached) {
+    gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(gt, hw0, gg[0]);
+    HG_POST_LAUNCH(false, st, "gray");
+  }
   for (int l = 1; l < levels; ++l) {
     const dim3 grid((wsz[l] + 127) / 128, hs[l]);
     pool_kernel<<<grid, 128, 0, st>>>(gr[l - 1], wsz[l - 1], hs[l], wsz[l], gr[l]);
-    pool_kernel<<<grid, 128, 0, st>>>(gg[l - 1], wsz[l - 1], hs[l], wsz[l], gg[l]);
     HG_POST_LAUNCH(false, st, "pool");
+    if (!cached) {
+      pool_kernel<<<grid, 128, 0, st>>>(gg[l - 1], wsz[l - 1], hs[l], wsz[l], gg[l]);
+      HG_POST_LAUNCH(false, st, "pool");
+    }
   }
   FreqFinalizeArgs fa{};
   fa.levels = levels;
@@ -905,7 +983,9 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
     const dim3 grid((wsz[l] + kSpTile - 1) / kSpTile, (hs[l] + kSpTile - 1) / kSpTile);
     spatial_kernel<false><<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gr[l], gg[l], hs[l], wsz[l], sp_part[l], nullptr, nullptr);
     HG_POST_LAUNCH(false, st, "spatial");
-    int rc = fft2_r2c(gr[l], fr[l], gg[l], fg[l], hs[l], wsz[l], 1, st);  // rendered + ground truth in one launch pair
+    // rendered + ground truth in one launch pair (rendered alone when the ground-truth spectra are cached)
+    int rc = cached ? fft2_r2c(gr[l], fr[l], nullptr, nullptr, hs[l], wsz[l], 1, st)
+                    : fft2_r2c(gr[l], fr[l], gg[l], fg[l], hs[l], wsz[l], 1, st);
     if (rc) return rc;
     spectral_sums_kernel<<<kSumBlocks, 256, 0, st>>>(fr[l], fg[l], hs[l], wsz[l], spec_part[l]);
     HG_POST_LAUNCH(false, st, "spectral_sums");
@@ -914,8 +994,10 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
     fa.spatial_blocks[l] = sp_blocks[l];
     fa.spectral_partial[l] = spec_part[l];
   }
-  band_energy_kernel<<<kSumBlocks, 256, 0, st>>>(fg[0], hs[0], wsz[0], band0);
-  HG_POST_LAUNCH(false, st, "band_energy");
+  if (!cached) {
+    band_energy_kernel<<<kSumBlocks, 256, 0, st>>>(fg[0], hs[0], wsz[0], band0);
+    HG_POST_LAUNCH(false, st, "band_energy");
+  }
   fa.band0_partial = band0;
   fa.ctl = ctl;
   fa.stats = stats;
@@ -946,6 +1028,24 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
   gray_to_rgb_grad_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(dg[0], hw0, grad_rendered);
   HG_POST_LAUNCH(false, st, "gray_to_rgb_grad");
   return HG_OK;
+}
+
+int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, int32_t levels, float* stats,
+                 float* grad_rendered, void* ws, void* st_) {
+  if (!gt) {
+    set_error("hg_freq_loss: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  return freq_loss_impl(rendered, gt, nullptr, H, W, levels, stats, grad_rendered, ws, (cudaStream_t)st_);
+}
+
+int hg_freq_loss_cached(const float* rendered, void* gt_state, int32_t H, int32_t W, int32_t levels, float* stats,
+                        float* grad_rendered, void* ws, void* st_) {
+  if (!gt_state) {
+    set_error("hg_freq_loss_cached: NULL ground-truth state");
+    return HG_ERR_INVALID_ARG;
+  }
+  return freq_loss_impl(rendered, nullptr, gt_state, H, W, levels, stats, grad_rendered, ws, (cudaStream_t)st_);
 }
 
 size_t hg_hf_mask_workspace_bytes(int32_t H, int32_t W) {

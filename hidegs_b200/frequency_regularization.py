@@ -15,11 +15,35 @@ from ._losses_lib import FREQ_STATS, lib as _L
 from .loss_utils import _check_cuda, _stream, _ws
 
 
+class GroundTruthCache:
+    """Everything the frequency regulariser derives from the ground-truth image alone: its gray pyramid and spectra
+    (3 of the 6 forward FFTs of a call), the level-0 band energies and the high-frequency mask + pixel count
+    (2 more FFTs).  A camera's image does not change during training, so a loop that revisits cameras builds one cache
+    per camera and passes it as `gt_cache=`; results are bit-identical to the uncached call.  Opt-in: the plain call
+    (the reference's signature) recomputes everything every time."""
+
+    def __init__(self, gt_image, num_levels=3, high_freq_thresh=0.2):
+        g = gt_image[0] if gt_image.dim() == 4 else gt_image
+        _check_cuda(g)
+        g = g.detach().contiguous()
+        _, H, W = g.shape
+        self.shape, self.levels, self.thresh = (H, W), int(num_levels), float(high_freq_thresh)
+        with torch.cuda.device(g.device):
+            self.state = torch.empty(_L().hg_freq_gt_state_bytes(H, W, self.levels), dtype=torch.uint8, device=g.device)
+            rc = _L().hg_freq_gt_prepare(g.data_ptr(), H, W, self.levels, self.state.data_ptr(), _stream())
+        _lib.check(rc, "frequency loss ground-truth state")
+        self.mask, self.count = detect_true_high_frequency_regions(g, self.thresh)
+
+    def matches(self, gt_image, num_levels, high_freq_thresh):
+        g = gt_image[0] if gt_image.dim() == 4 else gt_image
+        return tuple(g.shape[-2:]) == self.shape and int(num_levels) == self.levels and float(high_freq_thresh) == self.thresh
+
+
 class _FreqLoss(torch.autograd.Function):
     """compute_true_frequency_loss(build_pyramid(rendered), build_pyramid(gt))  (:1293-1325)."""
 
     @staticmethod
-    def forward(ctx, rendered, gt, levels):
+    def forward(ctx, rendered, gt, levels, gt_state=None):
         _check_cuda(rendered, gt)
         r, g = rendered.contiguous(), gt.contiguous()
         _, H, W = r.shape
@@ -28,8 +52,12 @@ class _FreqLoss(torch.autograd.Function):
         grad = torch.empty_like(r) if need else None
         with torch.cuda.device(r.device):
             ws = _ws(_L().hg_freq_loss_workspace_bytes(H, W, levels), r.device)
-            rc = _L().hg_freq_loss(r.data_ptr(), g.data_ptr(), H, W, levels, stats.data_ptr(),
-                                   grad.data_ptr() if need else None, ws.data_ptr(), _stream())
+            if gt_state is None:
+                rc = _L().hg_freq_loss(r.data_ptr(), g.data_ptr(), H, W, levels, stats.data_ptr(),
+                                       grad.data_ptr() if need else None, ws.data_ptr(), _stream())
+            else:
+                rc = _L().hg_freq_loss_cached(r.data_ptr(), gt_state.data_ptr(), H, W, levels, stats.data_ptr(),
+                                              grad.data_ptr() if need else None, ws.data_ptr(), _stream())
         _lib.check(rc, "frequency loss")
         ctx.grad = grad
         ctx.mark_non_differentiable(stats)
@@ -37,7 +65,7 @@ class _FreqLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gs):
-        return (g * ctx.grad if ctx.needs_input_grad[0] else None), None, None
+        return (g * ctx.grad if ctx.needs_input_grad[0] else None), None, None, None
 
 
 class _ScaleReg(torch.autograd.Function):
@@ -142,7 +170,9 @@ class LazyDebugInfo(dict):
 def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, scene, viewpoint_cam,
                                            visibility_filter, iteration, lambda_freq=0.001, lambda_scale=0.005,
                                            num_levels=3, high_freq_thresh=0.2, save_results=False, save_dir=None,
-                                           warmup_iterations=1000, debug=False):
+                                           warmup_iterations=1000, debug=False, gt_cache=None):
+    """Same arguments, defaults and return triple as the reference; `gt_cache` (a GroundTruthCache of this camera's
+    image, optional, keyword only in spirit) skips the work that depends on the ground truth alone."""
     if iteration < warmup_iterations:
         return torch.tensor(0.0, device=rendered_image.device), None, {'warmup': True}
     if not 1 <= num_levels <= 3:
@@ -152,10 +182,15 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
     g = gt_image[0] if gt_image.dim() == 4 else gt_image
     total = torch.zeros((), dtype=torch.float32, device=device)
     stats = None
+    if gt_cache is not None and not gt_cache.matches(g, num_levels, high_freq_thresh):
+        raise RuntimeError("gt_cache was built for another image size / level count / threshold")
     if lambda_freq > 0:
-        freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels))
+        freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels), gt_cache.state if gt_cache is not None else None)
         total = total + lambda_freq * freq_loss
-    mask, count = detect_true_high_frequency_regions(g, high_freq_thresh)
+    if gt_cache is not None:
+        mask, count = gt_cache.mask, gt_cache.count
+    else:
+        mask, count = detect_true_high_frequency_regions(g, high_freq_thresh)
     scale_loss = None
     if lambda_scale > 0:
         if hasattr(gaussians, 'get_scaling'):

@@ -22,7 +22,7 @@ from . import gaussian_renderer as gr
 from . import loss_utils as lu
 from ._geometry_lib import lib as _G
 from . import _lib
-from .frequency_regularization import frequency_regularization_pyramid_scale
+from .frequency_regularization import GroundTruthCache, frequency_regularization_pyramid_scale
 
 GROUPS = (("xyz", 3), ("features", 48), ("opacity", 1), ("scaling", 3), ("rotation", 4))
 
@@ -200,12 +200,16 @@ class ArenaAdam:
 
 class ViewShardedTrainer:
     def __init__(self, params: GaussianParams, background, opt=OptimizationParams, pipe=PipelineParams, group=None,
-                 sparse_adam=True, densification_stats=False):
+                 sparse_adam=True, densification_stats=False, cache_ground_truth=False):
         self.params, self.bg, self.opt, self.pipe, self.group = params, background, opt, pipe, group
         self.adam = ArenaAdam(params, opt)
         # the reference steps its optimiser on the rows that were visible (`optimizer.step(relevant)`, OurAdam.py:106)
         self.sparse_adam = sparse_adam and params.param_arena.is_cuda
         self.visible = torch.zeros(params.N, dtype=torch.uint8, device=params.param_arena.device)
+        # per-camera cache of everything derived from the ground-truth image alone (frequency-loss spectra, high-frequency
+        # mask, edge-aware weight of the normal term); keyed by the camera object, built at the camera's first visit
+        self.cache_ground_truth = cache_ground_truth
+        self._gt_cache = {}
         self.densification_stats = densification_stats and params.param_arena.is_cuda
         if self.densification_stats:  # GaussianModel.training_setup (scene/gaussian_model.py:282-294)
             dev = params.param_arena.device
@@ -226,12 +230,18 @@ class ViewShardedTrainer:
             torch.cuda.current_stream().wait_event(gt_ready)
         image = pkg["render"]
         loss = (1.0 - o.lambda_dssim) * lu.l1_loss(image, gt) + o.lambda_dssim * (1.0 - lu.ssim(image, gt))
+        cache = None
+        if self.cache_ground_truth and iteration >= o.freq_warmup_iterations:
+            cache = self._gt_cache.get(id(cam))
+            if cache is None:
+                cache = self._gt_cache[id(cam)] = (cam, GroundTruthCache(gt), (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2)
         freq, _mask, _info = frequency_regularization_pyramid_scale(
             image, gt, self.params, None, cam, pkg["visibility_filter"], iteration, lambda_freq=o.lambda_freq,
-            lambda_scale=o.lambda_scale, warmup_iterations=o.freq_warmup_iterations)
+            lambda_scale=o.lambda_scale, warmup_iterations=o.freq_warmup_iterations,
+            gt_cache=cache[1] if cache is not None else None)
         loss = loss + freq
         if o.single_view_weight > 0:
-            image_weight = (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2
+            image_weight = cache[2] if cache is not None else (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2
             loss = loss + gr.normal_consistency_loss(pkg["plane_depth"], pkg["out_all_map"], cam, image_weight,
                                                      o.single_view_weight)
         return loss, pkg

@@ -87,6 +87,15 @@ HG_API size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels)
 HG_API int hg_freq_loss(const float *rendered, const float *gt, int32_t H, int32_t W, int32_t levels,
                         float *stats, float *grad_rendered, void *workspace, void *stream);
 
+/* The ground-truth side of hg_freq_loss (gray pyramid of gt, its spectra, the level-0 band sums) depends on the camera's
+ * image only.  A training loop that revisits a camera prepares it once (hg_freq_gt_prepare into a caller-owned state of
+ * hg_freq_gt_state_bytes bytes) and calls hg_freq_loss_cached, which is hg_freq_loss minus that work (3 of the 6
+ * forward FFTs); results are bit-identical to the uncached call. */
+HG_API size_t hg_freq_gt_state_bytes(int32_t H, int32_t W, int32_t levels);
+HG_API int hg_freq_gt_prepare(const float *gt, int32_t H, int32_t W, int32_t levels, void *gt_state, void *stream);
+HG_API int hg_freq_loss_cached(const float *rendered, void *gt_state, int32_t H, int32_t W, int32_t levels,
+                               float *stats, float *grad_rendered, void *workspace, void *stream);
+
 /* detect_true_high_frequency_regions on gt [3,H,W] -> mask [H,W] float (0/1); count[0] = sum(mask). */
 HG_API size_t hg_hf_mask_workspace_bytes(int32_t H, int32_t W);
 HG_API int hg_hf_mask(const float *gt, int32_t H, int32_t W, float thresh, float *mask, float *count,

@@ -152,9 +152,12 @@ def test_drop_in_signatures_match_reference():
         "viewpoint_camera", "pc", "pipe", "bg_color", "scaling_modifier", "override_color", "render_indices",
         "parent_indices", "interpolation_weights", "num_node_kids", "interp_python", "use_trained_exp"]
     assert list(inspect.signature(gr.render_normal).parameters) == ["viewpoint_cam", "depth", "offset", "normal", "scale"]
-    assert list(inspect.signature(f).parameters) == [
+    names = list(inspect.signature(f).parameters)
+    assert names[:15] == [
         "rendered_image", "gt_image", "gaussians", "scene", "viewpoint_cam", "visibility_filter", "iteration", "lambda_freq",
         "lambda_scale", "num_levels", "high_freq_thresh", "save_results", "save_dir", "warmup_iterations", "debug"]
+    # one optional trailing extension (per-camera ground-truth cache), inert by default
+    assert names[15:] == ["gt_cache"] and inspect.signature(f).parameters["gt_cache"].default is None
     sig = inspect.signature(f).parameters
     assert (sig["lambda_freq"].default, sig["lambda_scale"].default, sig["num_levels"].default,
             sig["high_freq_thresh"].default, sig["warmup_iterations"].default) == (0.001, 0.005, 3, 0.2, 1000)

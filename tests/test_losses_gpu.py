@@ -209,3 +209,27 @@ def test_warmup_bool_filter_and_lazy_debug_info(cuda_device):
     t3 = run_freq(dict(inp, visibility=torch.zeros(0, dtype=torch.int64)), dev)
     assert float(t3[4].abs().max()) == 0.0 and t3[0].item() < t1[0].item()
     assert t1[2]._fill is not None or len(t1[2]) > 0  # lazy until read
+
+
+def test_ground_truth_cache_is_bit_identical(cuda_device):
+    """GroundTruthCache: the cached call returns exactly what the plain call returns (value, mask, gradient)."""
+    import loss_utils_t as lt
+    from hidegs_b200.frequency_regularization import GroundTruthCache, frequency_regularization_pyramid_scale as f
+    dev = cuda_device
+    for name in ("near_small", "near_odd"):
+        inp = lt.make_loss_inputs(**lt.LOSS_CASES[name])
+        gt = inp["gt"].to(dev)
+        vis = inp["visibility"].to(dev)
+        outs = []
+        for cached in (False, True):
+            r = inp["render"].to(dev).requires_grad_(True)
+            sc = inp["scaling"].to(dev).requires_grad_(True)
+            cache = GroundTruthCache(gt) if cached else None
+            total, mask, info = f(r, gt, lt.GaussiansShim(sc), None, None, vis, 2000, gt_cache=cache)
+            total.backward()
+            outs.append((total.detach(), mask, r.grad, sc.grad, info["freq_band_energies"]))
+        a, b = outs
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+        assert a[4] == b[4]
+    with pytest.raises(RuntimeError, match="gt_cache was built for another"):
+        f(r, gt, lt.GaussiansShim(sc), None, None, vis, 2000, num_levels=2, gt_cache=cache)
