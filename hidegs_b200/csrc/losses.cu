@@ -99,64 +99,123 @@ int run_pixel_loss(const float* a, const float* b, int64_t n, float* out, float*
 }
 
 // ---------------------------------------------------------------- SSIM
+// Separable 11-tap Gaussian (sigma 1.5) in shared memory: 32x32 output tile per 256-thread CTA, 42x42 input tile
+// (halo 5, zero padded as F.conv2d(padding=5)).  Both passes are register blocked — a thread produces 4 consecutive
+// outputs from a 14-value sliding window — so a tap costs 0.3 shared-memory loads instead of one.
 __constant__ float c_gauss[11];
-constexpr int kTile = 16, kHalo = 5, kIn = kTile + 2 * kHalo;  // 26
+constexpr int kTile = 32, kHalo = 5, kIn = kTile + 2 * kHalo;  // 42
+constexpr int kSsimThreads = 256;
 
-__global__ void __launch_bounds__(kTile * kTile)
+// horizontal pass over NQ quantities derived from the NS staged planes; work item = (row, group of 4 columns)
+template <int NS, int NQ, typename F>
+__device__ __forceinline__ void conv_rows4(const float (*src)[kIn][kIn + 1], float (*dst)[kIn][kTile + 1], int tid, F make) {
+  for (int w = tid; w < kIn * (kTile / 4); w += kSsimThreads) {
+    const int r = w / (kTile / 4), c0 = (w - r * (kTile / 4)) * 4;
+    float acc[NQ][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      float in[NS];
+#pragma unroll
+      for (int p = 0; p < NS; ++p) in[p] = src[p][r][c0 + k];
+      float val[NQ];
+      make(in, val);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tap = k - j;  // output c0+j uses inputs c0+j .. c0+j+10
+        if (tap >= 0 && tap < 11) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) acc[q][j] += c_gauss[tap] * val[q];
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dst[q][r][c0 + j] = acc[q][j];
+  }
+}
+
+// vertical pass: thread (tx, ty) produces rows 4 ty .. 4 ty + 3 of column tx
+template <int NQ>
+__device__ __forceinline__ void conv_cols4(const float (*h)[kIn][kTile + 1], int tx, int ty, float (&out)[NQ][4]) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[q][j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 14; ++k) {
+    float v[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) v[q] = h[q][4 * ty + k][tx];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tap = k - j;
+      if (tap >= 0 && tap < 11) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) out[q][j] += c_gauss[tap] * v[q];
+      }
+    }
+  }
+}
+
+template <int NS>
+__device__ __forceinline__ void load_tile(float (*dst)[kIn][kIn + 1], const float* const (&planes)[NS], int H, int W, int x0,
+                                          int y0, int tid) {
+  for (int i = tid; i < kIn * kIn; i += kSsimThreads) {
+    const int r = i / kIn, c = i - r * kIn;
+    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;  // zero padding
+#pragma unroll
+    for (int p = 0; p < NS; ++p) dst[p][r][c] = in ? __ldg(planes[p] + (size_t)y * W + x) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kSsimThreads)
 ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W,
                 float* __restrict__ maps, size_t map_stride, double* __restrict__ partial) {
-  __shared__ float s1[kIn][kIn + 1], s2[kIn][kIn + 1];
+  __shared__ float s[2][kIn][kIn + 1];
   __shared__ float h[5][kIn][kTile + 1];
   __shared__ float red[32];
   const int plane = blockIdx.z;
   const size_t base = (size_t)plane * H * W;
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-  const int tid = threadIdx.y * kTile + threadIdx.x;
-  for (int i = tid; i < kIn * kIn; i += kTile * kTile) {
-    const int r = i / kIn, c = i % kIn;
-    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
-    const bool in = y >= 0 && y < H && x >= 0 && x < W;  // zero padding (F.conv2d padding=5)
-    s1[r][c] = in ? __ldg(img1 + base + (size_t)y * W + x) : 0.f;
-    s2[r][c] = in ? __ldg(img2 + base + (size_t)y * W + x) : 0.f;
-  }
+  const int tid = threadIdx.x;
+  const float* const planes[2] = {img1 + base, img2 + base};
+  load_tile<2>(s, planes, H, W, x0, y0, tid);
   __syncthreads();
-  for (int i = tid; i < kIn * kTile; i += kTile * kTile) {
-    const int r = i / kTile, c = i % kTile;
-    float a = 0.f, b = 0.f, aa = 0.f, bb = 0.f, ab = 0.f;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_gauss[k], x = s1[r][c + k], y = s2[r][c + k];
-      a += g * x; b += g * y; aa += g * x * x; bb += g * y * y; ab += g * x * y;
-    }
-    h[0][r][c] = a; h[1][r][c] = b; h[2][r][c] = aa; h[3][r][c] = bb; h[4][r][c] = ab;
-  }
+  conv_rows4<2, 5>(s, h, tid, [](const float (&in)[2], float (&v)[5]) {
+    v[0] = in[0]; v[1] = in[1]; v[2] = in[0] * in[0]; v[3] = in[1] * in[1]; v[4] = in[0] * in[1];
+  });
   __syncthreads();
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
-#pragma unroll
-  for (int k = 0; k < 11; ++k) {
-    const float g = c_gauss[k];
-    mu1 += g * h[0][ty + k][tx]; mu2 += g * h[1][ty + k][tx];
-    e11 += g * h[2][ty + k][tx]; e22 += g * h[3][ty + k][tx]; e12 += g * h[4][ty + k][tx];
-  }
-  const int x = x0 + tx, y = y0 + ty;
+  const int tx = tid & 31, ty = tid >> 5;
+  float o[5][4];
+  conv_cols4<5>(h, tx, ty, o);
   float val = 0.f;
-  if (x < W && y < H) {
-    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-    const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-    const float sg1 = e11 - mu1_sq, sg2 = e22 - mu2_sq, sg12 = e12 - mu12;
-    const float A = mu1_sq + mu2_sq + C1, B = sg1 + sg2 + C2, C = 2.f * mu12 + C1, D = 2.f * sg12 + C2;
-    val = (C * D) / (A * B);
-    if (maps) {
-      const size_t p = base + (size_t)y * W + x;
-      maps[p] = (mu2 * 2.f * D) / (A * B) - (mu2 * 2.f * C) / (A * B) - (mu1 * 2.f * C * D) / (A * A * B) +
-                (mu1 * 2.f * C * D) / (A * B * B);
-      maps[map_stride + p] = -(C * D) / (A * B * B);
-      maps[2 * map_stride + p] = (2.f * C) / (A * B);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + tx, y = y0 + 4 * ty + j;
+    if (x < W && y < H) {
+      const float mu1 = o[0][j], mu2 = o[1][j], e11 = o[2][j], e22 = o[3][j], e12 = o[4][j];
+      const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+      const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+      const float sg1 = e11 - mu1_sq, sg2 = e22 - mu2_sq, sg12 = e12 - mu12;
+      const float A = mu1_sq + mu2_sq + C1, B = sg1 + sg2 + C2, C = 2.f * mu12 + C1, D = 2.f * sg12 + C2;
+      val += (C * D) / (A * B);
+      if (maps) {
+        const size_t p = base + (size_t)y * W + x;
+        maps[p] = (mu2 * 2.f * D) / (A * B) - (mu2 * 2.f * C) / (A * B) - (mu1 * 2.f * C * D) / (A * A * B) +
+                  (mu1 * 2.f * C * D) / (A * B * B);
+        maps[map_stride + p] = -(C * D) / (A * B * B);
+        maps[2 * map_stride + p] = (2.f * C) / (A * B);
+      }
     }
   }
-  const float s = block_sum(val, red, tid, kTile * kTile);
-  if (tid == 0) partial[((size_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (double)s;
+  const float sum = block_sum(val, red, tid, kSsimThreads);
+  if (tid == 0) partial[((size_t)plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (double)sum;
 }
 
 __global__ void ssim_finalize_kernel(const double* __restrict__ partial, int per_item, double denom,
@@ -166,7 +225,7 @@ __global__ void ssim_finalize_kernel(const double* __restrict__ partial, int per
   if (threadIdx.x == 0) out[blockIdx.x] = (float)(s / denom);
 }
 
-__global__ void __launch_bounds__(kTile * kTile)
+__global__ void __launch_bounds__(kSsimThreads)
 ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
                 const float* __restrict__ maps, size_t map_stride, const float* __restrict__ gscale,
                 int C, int H, int W, float* __restrict__ grad) {
@@ -175,38 +234,24 @@ ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
   const int plane = blockIdx.z;
   const size_t base = (size_t)plane * H * W;
   const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
-  const int tid = threadIdx.y * kTile + threadIdx.x;
-  for (int i = tid; i < kIn * kIn; i += kTile * kTile) {
-    const int r = i / kIn, c = i % kIn;
-    const int y = y0 + r - kHalo, x = x0 + c - kHalo;
-    const bool in = y >= 0 && y < H && x >= 0 && x < W;
-    const size_t p = base + (size_t)y * W + x;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) m[q][r][c] = in ? __ldg(maps + q * map_stride + p) : 0.f;
-  }
+  const int tid = threadIdx.x;
+  const float* const planes[3] = {maps + base, maps + map_stride + base, maps + 2 * map_stride + base};
+  load_tile<3>(m, planes, H, W, x0, y0, tid);
   __syncthreads();
-  for (int i = tid; i < kIn * kTile; i += kTile * kTile) {
-    const int r = i / kTile, c = i % kTile;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  conv_rows4<3, 3>(m, h, tid, [](const float (&in)[3], float (&v)[3]) { v[0] = in[0]; v[1] = in[1]; v[2] = in[2]; });
+  __syncthreads();
+  const int tx = tid & 31, ty = tid >> 5;
+  float o[3][4];
+  conv_cols4<3>(h, tx, ty, o);
+  const float sc = __ldg(gscale + plane / C) / ((float)C * (float)H * (float)W);
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = c_gauss[k];
-      a0 += g * m[0][r][c + k]; a1 += g * m[1][r][c + k]; a2 += g * m[2][r][c + k];
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + tx, y = y0 + 4 * ty + j;
+    if (x < W && y < H) {
+      const size_t p = base + (size_t)y * W + x;
+      grad[p] = sc * (o[0][j] + 2.f * __ldg(img1 + p) * o[1][j] + __ldg(img2 + p) * o[2][j]);
     }
-    h[0][r][c] = a0; h[1][r][c] = a1; h[2][r][c] = a2;
   }
-  __syncthreads();
-  const int tx = threadIdx.x, ty = threadIdx.y, x = x0 + tx, y = y0 + ty;
-  if (x >= W || y >= H) return;
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-  for (int k = 0; k < 11; ++k) {
-    const float g = c_gauss[k];
-    c0 += g * h[0][ty + k][tx]; c1 += g * h[1][ty + k][tx]; c2 += g * h[2][ty + k][tx];
-  }
-  const size_t p = base + (size_t)y * W + x;
-  const float s = __ldg(gscale + plane / C) / ((float)C * (float)H * (float)W);
-  grad[p] = s * (c0 + 2.f * __ldg(img1 + p) * c1 + __ldg(img2 + p) * c2);
 }
 
 // ---------------------------------------------------------------- get_img_grad_weight
@@ -424,7 +469,7 @@ int hg_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t 
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)st_;
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
-  ssim_fwd_kernel<<<grid, dim3(kTile, kTile), 0, st>>>(img1, img2, H, W, maps, (size_t)B * C * H * W, (double*)ws);
+  ssim_fwd_kernel<<<grid, kSsimThreads, 0, st>>>(img1, img2, H, W, maps, (size_t)B * C * H * W, (double*)ws);
   HG_POST_LAUNCH(false, st, "ssim_fwd");
   ssim_finalize_kernel<<<B, 1024, 0, st>>>((const double*)ws, (int)(grid.x * grid.y * C), (double)C * H * W, out);
   HG_POST_LAUNCH(false, st, "ssim_finalize");
@@ -441,7 +486,7 @@ int hg_ssim_backward(const float* img1, const float* img2, const float* maps, co
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)st_;
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
-  ssim_bwd_kernel<<<grid, dim3(kTile, kTile), 0, st>>>(img1, img2, maps, (size_t)B * C * H * W, gscale, C, H, W,
+  ssim_bwd_kernel<<<grid, kSsimThreads, 0, st>>>(img1, img2, maps, (size_t)B * C * H * W, gscale, C, H, W,
                                                       grad_img1);
   HG_POST_LAUNCH(false, st, "ssim_bwd");
   return HG_OK;
