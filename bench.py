@@ -420,7 +420,9 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     from hidegs_b200 import synthetic as syn, trainer as tr, _lib
     if recipe == "uav":
         scene = syn.make_uav_scene(n_gauss, seed=0)
-        cams_all = [syn.uav_camera(i, j, width=WIDTH, height=HEIGHT).to(dev) for i in range(8) for j in range(8)]
+        # Latin-square order: views[rank::world] hands every rank one camera of every row AND every column of the
+        # survey grid, so the ranks' loads match (edge cameras see less of the slab than central ones)
+        cams_all = [syn.uav_camera(i, (j + i) % 8, width=WIDTH, height=HEIGHT).to(dev) for i in range(8) for j in range(8)]
     else:
         scene = syn.make_scene(n_gauss, seed=0)
         cams_all = [camera_for(r, s).to(dev) for r in range(8) for s in range(8)]
