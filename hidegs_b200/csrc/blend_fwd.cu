@@ -391,6 +391,201 @@ blend_fwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                           n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Variant C (experiment, HG_BLEND_FWD_VARIANT=3): as variant B, but the 64-byte splat records travel global -> shared
+// through the TMA engine: every thread issues ONE cp.async.bulk (UBLKCP) for its entry of the NEXT batch into the other
+// half of a double-buffered ring and the batch is released by an mbarrier transaction count — no register staging, no
+// STS.  The record is consumed as stored (the cull threshold is derived on the fly, the slot id sits in word 15).
+// Not used with hierarchy interpolation (two more gathered words per entry).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, int bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n"
+      " DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, int bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool GEO, bool DEPTH>
+__global__ void __launch_bounds__(kThreadsB)
+blend_fwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                  const float4* __restrict__ records, const int W, const int H, const float focal_x,
+                  const float focal_y, const float cx, const float cy,
+                  const float* __restrict__ bg_color, float* __restrict__ final_T,
+                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+                  float* __restrict__ out_invdepth, int* __restrict__ out_observe,
+                  float* __restrict__ out_all_map, float* __restrict__ out_plane_depth) {
+  __shared__ __align__(128) float4 s_ring[2][kBatchB * 4];  // raw 64-byte records
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ int s_obs[kBatchB];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
+  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 8;
+  const int pxi = wx0 + (lane & 7), pyA = wy0 + (lane >> 3), pyB = pyA + 4;
+  const bool insideA = pxi < W && pyA < H, insideB = pxi < W && pyB < H;
+  const float pixx = (float)pxi, pixyA = (float)pyA, pixyB = (float)pyB;
+  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7);
+  const float fyA0 = (float)wy0, fyA1 = (float)(wy0 + 3), fyB0 = (float)(wy0 + 4), fyB1 = (float)(wy0 + 7);
+
+  const uint2 range = ranges[tile];
+  const int n = (int)(range.y - range.x);
+  const int nb = (n + kBatchB - 1) / kBatchB;
+
+  FwdPixel A{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0u, !insideA};
+  FwdPixel B{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0u, !insideB};
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], kThreadsB);
+    mbar_init(&s_bar[1], kThreadsB);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // Every thread arrives once per batch on that batch's barrier; a thread that owns an entry also announces its 64 bytes.
+  auto issue = [&](int b, int id) {
+    uint64_t* bar = &s_bar[b & 1];
+    if (b * kBatchB + tid < n) {
+      mbar_arrive_expect_tx(bar, 64);
+      bulk_g2s(&s_ring[b & 1][4 * tid], records + 4 * (size_t)id, 64, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+  auto load_id = [&](int b) -> int {
+    const int i = b * kBatchB + tid;
+    return (b < nb && i < n) ? (int)__ldg(point_list + range.x + i) : 0;
+  };
+  int id_next = load_id(0);
+  if (nb > 0) issue(0, id_next);
+  id_next = load_id(1);
+
+  bool pending_flush = false;
+  int obs_id = 0;
+  int unconsumed = -1;  // batch whose copy was issued but never waited for (early exit)
+  for (int b = 0; b < nb; ++b) {
+    const int any_active = __syncthreads_or(!(A.done && B.done));  // also: every warp has left batch b-1 (its ring half is free)
+    if (pending_flush) {
+      const int c = s_obs[tid];
+      if (c) atomicAdd(out_observe + obs_id, c);
+      pending_flush = false;
+    }
+    if (!any_active) {
+      unconsumed = b;
+      break;
+    }
+    // reads of ring half (b+1)&1 by the generic proxy (batch b-1) are ordered before the async-proxy writes below
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (b + 1 < nb) issue(b + 1, id_next);
+    id_next = load_id(b + 2);
+    s_obs[tid] = 0;
+    mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
+    __syncthreads();  // s_obs zeroed everywhere before the first count lands
+    const float4* rec = s_ring[b & 1];
+    const int cnt = min(kBatchB, n - b * kBatchB);
+    obs_id = __float_as_int(rec[4 * tid + 3].w);
+    pending_flush = true;
+
+    uint32_t liveA = __ballot_sync(0xffffffffu, !A.done), liveB = __ballot_sync(0xffffffffu, !B.done);
+    if ((liveA | liveB) == 0) continue;
+    const uint32_t base = (uint32_t)(b * kBatchB);
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+      const int j = c0 + lane;
+      bool keepA = false, keepB = false;
+      if (j < cnt) {
+        const float4 ea = rec[4 * j];
+        const float4 eb = rec[4 * j + 1];
+        const float tau = cull_tau(ea.z, ea.w, eb.x, eb.y, false);
+        keepA = liveA != 0 && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, tau, fx0, fx1, fyA0, fyA1);
+        keepB = liveB != 0 && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, tau, fx0, fx1, fyB0, fyB1);
+      }
+      const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
+      uint32_t mask = maskA | maskB;
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int k = c0 + bit;
+        const float4* e = rec + 4 * k;
+        const float4 ea = e[0];
+        const float4 e1 = e[1];  // c o r g
+        const float4 e2 = e[2];  // b 1/z am0 am1
+        const uint32_t index1 = base + (uint32_t)k + 1u;
+        bool obsA = false, obsB = false;
+#define HG_PIX(S, PY, OBS)                                                                                   \
+  if (!S.done) {                                                                                             \
+    const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, PY);                                        \
+    const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, e1.x)));              \
+    const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));                         \
+    if (!(power > 0.0f)) {                                                                                   \
+      const float alpha = fminf(0.99f, __fmul_rn(e1.y, expf(power)));                                        \
+      if (!(alpha < 1.0f / 255.0f)) {                                                                        \
+        const float test_T = __fmul_rn(S.T, __fsub_rn(1.0f, alpha));                                         \
+        if (test_T < 0.0001f) {                                                                              \
+          S.done = true;                                                                                     \
+        } else {                                                                                             \
+          const float wgt = __fmul_rn(alpha, S.T);                                                           \
+          S.C0 = __fmaf_rn(wgt, e1.z, S.C0);                                                                 \
+          S.C1 = __fmaf_rn(wgt, e1.w, S.C1);                                                                 \
+          S.C2 = __fmaf_rn(wgt, e2.x, S.C2);                                                                 \
+          if (DEPTH) S.Dinv = __fmaf_rn(wgt, e2.y, S.Dinv);                                                  \
+          if (GEO) {                                                                                         \
+            const float4 e3 = e[3];                                                                          \
+            S.A0 = __fmaf_rn(wgt, e2.z, S.A0);                                                               \
+            S.A1 = __fmaf_rn(wgt, e2.w, S.A1);                                                               \
+            S.A2 = __fmaf_rn(wgt, e3.x, S.A2);                                                               \
+            S.A3 = __fmaf_rn(wgt, e3.y, S.A3);                                                               \
+            S.A4 = __fmaf_rn(wgt, e3.z, S.A4);                                                               \
+          }                                                                                                  \
+          OBS = S.T > 0.5f;                                                                                  \
+          S.T = test_T;                                                                                      \
+          S.last_contributor = index1;                                                                       \
+        }                                                                                                    \
+      }                                                                                                      \
+    }                                                                                                        \
+  }
+        if ((maskA >> bit) & 1u) { HG_PIX(A, pixyA, obsA) }
+        if ((maskB >> bit) & 1u) { HG_PIX(B, pixyB, obsB) }
+#undef HG_PIX
+        const uint32_t oa = __ballot_sync(0xffffffffu, obsA), ob = __ballot_sync(0xffffffffu, obsB);
+        if ((oa | ob) && lane == 0) atomicAdd(&s_obs[k], __popc(oa) + __popc(ob));
+      }
+      liveA = __ballot_sync(0xffffffffu, !A.done);
+      liveB = __ballot_sync(0xffffffffu, !B.done);
+      if ((liveA | liveB) == 0) break;
+    }
+  }
+  if (pending_flush) {
+    __syncthreads();
+    const int c = s_obs[tid];
+    if (c) atomicAdd(out_observe + obs_id, c);
+  }
+  // The bulk copy of a batch that was never consumed (early exit) may still be in flight: wait for it before the CTA's
+  // shared memory is released.
+  if (unconsumed >= 0) mbar_wait(&s_bar[unconsumed & 1], (unconsumed >> 1) & 1);
+
+  const size_t HW = (size_t)H * W;
+  write_pixel<GEO, DEPTH>(A, insideA, (size_t)pyA * W + pxi, HW, pixx, pixyA, cx, cy, focal_x, focal_y, bg_color, final_T,
+                          n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
+  write_pixel<GEO, DEPTH>(B, insideB, (size_t)pyB * W + pxi, HW, pixx, pixyB, cx, cy, focal_x, focal_y, bg_color, final_T,
+                          n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
+}
+
 template <bool GEO, bool DEPTH>
 int dispatch(bool interp, dim3 grid, cudaStream_t stream, const uint2* ranges,
              const uint32_t* point_list, const float4* records, const float* ts, const int* kids,
@@ -402,7 +597,13 @@ int dispatch(bool interp, dim3 grid, cudaStream_t stream, const uint2* ranges,
     const char* e = getenv("HG_BLEND_FWD_VARIANT");
     return e ? atoi(e) : 2;
   }();
-  if (variant == 2) {
+  if (variant == 3 && !interp) {
+    blend_fwd3_kernel<GEO, DEPTH><<<grid, kThreadsB, 0, stream>>>(ranges, point_list, records, W, H, fx, fy, cx, cy, bg,
+                                                                final_T, n_contrib, out_color, out_invdepth,
+                                                                out_observe, out_all_map, out_plane_depth);
+    return 0;
+  }
+  if (variant == 2 || variant == 3) {
     if (interp)
       blend_fwd2_kernel<GEO, DEPTH, true><<<grid, kThreadsB, 0, stream>>>(
           ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,

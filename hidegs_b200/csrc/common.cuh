@@ -12,7 +12,7 @@
 // Splat record (64 B, one per rendered slot, written by preprocess, gathered by
 // both blend kernels with four LDG.128):
 //   [0] x  [1] y  [2] conic.a  [3] conic.b | [4] conic.c  [5] opacity*AA  [6] r  [7] g
-//   [8] b  [9] 1/depth  [10] am0  [11] am1 | [12] am2  [13] am3  [14] am4  [15] depth
+//   [8] b  [9] 1/depth  [10] am0  [11] am1 | [12] am2  [13] am3  [14] am4  [15] slot id (bits)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -367,7 +367,7 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
   rec[0] = make_float4(pix_x, pix_y, conic_a, conic_b);
   rec[1] = make_float4(conic_c, opac, rgb[0], rgb[1]);
   rec[2] = make_float4(rgb[2], __frcp_rn(depth), am[0], am[1]);
-  rec[3] = make_float4(am[2], am[3], am[4], depth);
+  rec[3] = make_float4(am[2], am[3], am[4], __int_as_float(t_idx));  // the record carries its own slot id
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
