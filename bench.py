@@ -186,10 +186,20 @@ def run_gpu_arm(args, impl):
     HW = WIDTH * HEIGHT
     from hidegs_b200 import parallel
 
+    # With an NVSwitch multicast mapping the backward writes its gradients straight into symmetric memory and the
+    # exchange is ONE in-fabric kernel (hg_nvls_allreduce_f32); otherwise NCCL sums the arena in place.
+    exchange = None
+    if ddp and os.environ.get("HG_EXCHANGE", "auto") != "nccl" and parallel.nvls_available(dev):
+        exchange = parallel.SymmetricArena(N_GAUSS * 80, dev)   # 80 floats / Gaussian: the whole backward arena
+        C.set_gradient_arena_provider(lambda n, d: exchange.tensor if n <= exchange.numel else None)
+
     def pack_and_allreduce(grads):
         # (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map)
         # xyz 3 | sh 48 | opacity 1 | scale 3 | rot 4 = 59 floats per Gaussian, contiguous in the backward's arena
-        parallel.allreduce_gradients((grads[3], grads[5], grads[2], grads[6], grads[7]))
+        if exchange is not None and grads[3].data_ptr() == exchange.tensor.data_ptr():
+            exchange.all_reduce_(59 * N_GAUSS)
+        else:
+            parallel.allreduce_gradients((grads[3], grads[5], grads[2], grads[6], grads[7]))
 
     # ------------------------------------------------ device-resident leg ("value")
     def step_resident(s):
@@ -350,6 +360,8 @@ def run_gpu_arm(args, impl):
                                "REDUCED %d Gaussians %dx%d" % (N_GAUSS, WIDTH, HEIGHT),
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "visible": Nv, "num_rendered": R,
                    "outputs": "color+all_map+plane_depth+invdepth", "parallelism": "view-sharded dp%d" % world,
+                   "exchange": (None if not ddp else "nvls multimem kernel (hg_nvls_allreduce_f32), 236 MB arena"
+                                if exchange is not None else "nccl all_reduce, 236 MB arena"),
                    "l2": "inputs_exceed_l2 (SH 192 MB + records 64 MB + sort buffers > 126 MB)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),

@@ -1,1 +1,2 @@
-from hidegs_b200.gaussian_hierarchy._C import expand_to_size, get_interpolation_weights  # noqa: F401
+from hidegs_b200.gaussian_hierarchy._C import (expand_to_size, expand_to_target, get_interpolation_weights,  # noqa: F401
+                                                load_hierarchy, write_hierarchy)

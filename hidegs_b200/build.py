@@ -38,10 +38,8 @@ def _compile(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
     stamp = obj + ".sha"
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(HERE, "..", "include", "hidegs_raster.h"))
-    extra = os.path.join(HERE, "..", "include", "hidegs_losses.h")
-    if os.path.exists(extra):
-        deps.append(extra)
+    inc = os.path.join(HERE, "..", "include")
+    deps += [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
     dig = _digest(deps)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, ""

@@ -499,6 +499,336 @@ blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant C: the cross-pixel reduction as tensor-core matrix products.
+//
+// Every gradient a (pixel, entry) pair contributes is a per-pair scalar times a per-PIXEL constant:
+//   dL/d(rgb, 1/z, all_map)[entry] = sum_pix  wgt(pix, entry) * dL/dpixel[ch](pix)           wgt = alpha * T
+//   dL/d(mean2D, conic, opacity)   = polynomials in the six moments  sum_pix p(pix, entry) * {1, xi, eta, xi^2, xi eta,
+//                                    eta^2}  with p = G * dL/dalpha and (xi, eta) the pixel's offset from the sub-tile
+//                                    centre (expand dx = (x_e - cx) - xi in dG/dx, dx^2, dx dy, dy^2).
+// So for a group of 16 entries the whole reduction over the warp's 64 pixels is  D[16 x n] = A[16 x 64] * B[64 x n]:
+// the lanes park (wgt, p) of their two pixels in a per-warp shared-memory tile, and once 16 entries are collected the
+// warp runs mma.sync.m16n8k8 (TF32 inputs, FP32 accumulate) against constant B tiles built once per CTA — the nine
+// upstream-gradient channels of the warp's pixels and the six moments.  FP32 accuracy is kept by splitting A and the
+// gradient channels into TF32 hi + lo parts (three products, the lo*lo term ~2^-22 is dropped); the moment tile is
+// exact in TF32 (|xi|, |eta| <= 3.5, products <= 12.25).  This takes the 16-value shuffle butterfly (74 issue slots) and
+// the 15 per-pixel partial products (~50) of variant B off the FP32 issue port: per (warp, entry) it costs one
+// STS.128 + ~15 slots of the amortised flush.  The moments are turned into the reference's gradients per entry by the
+// lane that owns the row, and the 16-float accumulator row receives vector REDs (red.global.add.v2/v4.f32).
+// The hierarchy interpolation (INTERP) keeps variant B (its opacity term needs a third per-pair scalar).
+constexpr int kGroupC = 16;               // entries per flush (the M of the MMA)
+constexpr int kWarpsC = kThreadsB / 32;
+
+constexpr int kBatchC = 128;              // entries staged per round
+
+struct alignas(16) BwdMmaSmem {
+  float4 rec[kBatchC * kRecQuads];        // staged tile-list entries (as variant B)
+  float4 a_tile[kWarpsC][kGroupC * 32];   // (wgt_A, wgt_B, p_A, p_B) per (row, lane), XOR-swizzled (see a_slot)
+  float2 b_ch0[kWarpsC][8][32];           // channels 0..7 of the warp's pixels, fragment order: (b0, b1) per lane
+  float2 b_ch8[kWarpsC][8][4];            // channel 8 (column 0 of its n-tile: the lanes with g == 0)
+  float2 zero2;                           // what the lanes with g != 0 read instead
+  float2 b_mom[8][32];                    // the six moments, fragment order (same for every warp)
+  float4 meta[kWarpsC][kGroupC][2];       // per row: (x, y, conic a, b), (conic c, opacity, -, slot id)
+  int s_max[kWarpsC];
+};
+
+// float4 slot of pixel pair (t, s) in row `row` of an A tile.  Writers (fixed row, t; s = 0..7) and fragment readers
+// (fixed s; rows {2i, 2i+1} x t = 0..3) both touch eight distinct 16-byte bank groups per quarter-warp phase.
+__device__ __forceinline__ int a_slot(int row, int t, int s) { return row * 32 + t * 8 + (s ^ (((row & 1) << 2) | t)); }
+
+// v = hi + lo with hi the TF32 truncation of v (one LOP3; cvt.rna.tf32 is emulated with five instructions on sm_100a)
+// and lo = v - hi exact; the MMA ignores the bits of lo below TF32, so |error| <= 2^-20 |v|.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  // (opaque to the optimiser: it would otherwise feed the MMA the unmasked register through an extra MOV)
+  asm("and.b32 %0, %1, 0xffffe000;" : "=r"(hi) : "r"(__float_as_uint(v)));
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// One (pixel, entry) pair of variant C: the recurrence of pixel_pair, returning the two per-pair scalars.
+template <bool GEO, bool DEPTH>
+__device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4* __restrict__ e, const float4 ea,
+                                             const float4 eb, float pixx, float pixy, int q, float& wgt, float& p) {
+  const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
+  const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
+  const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
+  bool valid = (q < s.last_contributor) && !(power > 0.0f);
+  const float Graw = expf(power);
+  const float test_alpha = __fmul_rn(eb.y, Graw);
+  const float alpha = fminf(0.99f, test_alpha);
+  valid = valid && !(alpha < 1.0f / 255.0f);
+  const float G = valid ? Graw : 0.f;
+  const float rinv = __fdividef(1.0f, 1.0f - alpha);
+  const float Tn = s.T * rinv;
+  wgt = valid ? alpha * Tn : 0.f;
+  const float4 ec = e[2];
+  float g = ec.x * s.w[0] + ec.y * s.w[1] + ec.z * s.w[2];
+  if (DEPTH) g += ec.w * s.w[3];
+  if (GEO) {
+    const float4 ed = e[3];
+    const float ee = e[4].x;
+    g += ed.x * s.w[4] + ed.y * s.w[5] + ed.z * s.w[6] + ed.w * s.w[7] + ee * s.w[8];
+  }
+  const float acc_new = s.last_alpha * s.last_g + (1.0f - s.last_alpha) * s.acc_g;
+  float dL_dalpha = (g - acc_new) * Tn + s.bgT * rinv;
+  if (test_alpha > 0.99f || !valid) dL_dalpha = 0.f;
+  s.T = valid ? Tn : s.T;
+  s.acc_g = valid ? acc_new : s.acc_g;
+  s.last_g = valid ? g : s.last_g;
+  s.last_alpha = valid ? alpha : s.last_alpha;
+  p = G * dL_dalpha;
+  return valid;
+}
+
+template <bool GEO, bool DEPTH>
+__global__ void __launch_bounds__(kThreadsB, 4)
+blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                  const float4* __restrict__ records, const int W, const int H, const float fx, const float fy,
+                  const float* __restrict__ bg_color, const float* __restrict__ all_map_pixels,
+                  const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+                  const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dout_all_maps,
+                  const float* __restrict__ dL_dout_plane_depths, const float* __restrict__ dL_invdepths,
+                  float* __restrict__ accum) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdMmaSmem& sm = *reinterpret_cast<BwdMmaSmem*>(smem_raw);
+  float4* const s_rec = sm.rec;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
+  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
+  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 8;
+  const int pxi = wx0 + (lane & 7), pyA = wy0 + (lane >> 3), pyB = pyA + 4;
+  const bool insideA = pxi < W && pyA < H, insideB = pxi < W && pyB < H;
+  const float pixx = (float)pxi, pixyA = (float)pyA, pixyB = (float)pyB;
+  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7);
+  const float fyA0 = (float)wy0, fyA1 = (float)(wy0 + 3), fyB0 = (float)(wy0 + 4), fyB1 = (float)(wy0 + 7);
+  const float cx = (float)wx0 + 3.5f, cy = (float)wy0 + 3.5f;  // moments are taken about the sub-tile centre
+  const size_t HW = (size_t)H * W;
+
+  const uint2 range = ranges[tile];
+  const int n = (int)(range.y - range.x);
+
+  PixelState A, B;
+  load_pixel_state<GEO, DEPTH>(A, insideA, (size_t)pyA * W + pxi, HW, W, H, pixx, pixyA, fx, fy, n, bg_color,
+                               all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
+                               dL_invdepths);
+  load_pixel_state<GEO, DEPTH>(B, insideB, (size_t)pyB * W + pxi, HW, W, H, pixx, pixyB, fx, fy, n, bg_color,
+                               all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
+                               dL_invdepths);
+
+  // ---- constant B tiles.  K index of a pixel pair = (t, s) = (lane >> 3, lane & 7) of the lane that owns it; inside
+  // k-step s column j < 4 is pixel A of lane 8 j + s and column j + 4 its pixel B.
+  {
+    const int ks = lane & 7, kt = lane >> 3;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sm.b_ch0[warp][ks][c * 4 + kt] = make_float2(A.w[c], B.w[c]);
+    if (GEO) {
+      sm.b_ch8[warp][ks][kt] = make_float2(A.w[8], B.w[8]);
+      if (tid == 0) sm.zero2 = make_float2(0.f, 0.f);
+    }
+    // moments of fragment lane (g, t) at k-step s: pixel A = (xi, etaA) = (s - 3.5, t - 3.5), pixel B = (xi, t + 0.5)
+    for (int i = tid; i < 8 * 32; i += kThreadsB) {
+      const int s_ = i >> 5, l_ = i & 31, g_ = l_ >> 2, t_ = l_ & 3;
+      const float xi = (float)s_ - 3.5f, ea_ = (float)t_ - 3.5f, eb_ = (float)t_ + 0.5f;
+      float m0, m1;
+      switch (g_) {
+        case 0: m0 = 1.f; m1 = 1.f; break;
+        case 1: m0 = xi; m1 = xi; break;
+        case 2: m0 = ea_; m1 = eb_; break;
+        case 3: m0 = xi * xi; m1 = xi * xi; break;
+        case 4: m0 = xi * ea_; m1 = xi * eb_; break;
+        case 5: m0 = ea_ * ea_; m1 = eb_ * eb_; break;
+        default: m0 = 0.f; m1 = 0.f; break;
+      }
+      sm.b_mom[s_][l_] = make_float2(m0, m1);
+    }
+  }
+
+  // last contributor of each half and of the tile
+  int wmaxA = A.last_contributor, wmaxB = B.last_contributor;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmaxA = max(wmaxA, __shfl_xor_sync(0xffffffffu, wmaxA, o));
+    wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
+  }
+  const int wmax = max(wmaxA, wmaxB);
+  if (lane == 0) sm.s_max[warp] = wmax;
+  __syncthreads();
+  int n_eff = 0;
+#pragma unroll
+  for (int i = 0; i < kWarpsC; ++i) n_eff = max(n_eff, sm.s_max[i]);
+  const int nb = (n_eff + kBatchC - 1) / kBatchC;
+  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+  float4* const a_tile = sm.a_tile[warp];
+  const int fg = lane >> 2, ft = lane & 3;                      // fragment coordinates of this lane
+  const int a_even = a_slot(0, lane >> 3, lane & 7), a_odd = a_slot(1, lane >> 3, lane & 7) - 32;  // writer slots
+  const int a_swz = ((fg & 1) << 2) | ft;                       // reader swizzle (rows g and g + 8 share it)
+  const float4* const a_row0 = a_tile + fg * 32 + ft * 8;       // + (k-step ^ a_swz)
+  const float4* const a_row1 = a_row0 + 8 * 32;
+  const float2* const b8_src = fg == 0 ? &sm.b_ch8[warp][0][ft] : &sm.zero2;  // + 4 * k-step for g == 0
+  const int b8_step = fg == 0 ? 4 : 0;
+  int rows = 0;  // entries parked in the A tile
+
+  // Reduce the parked rows over the warp's 64 pixels and add them to the accumulator rows.
+  auto flush = [&]() {
+    __syncwarp();
+    // two accumulator chains per tile (hi*hi | the two cross terms) halve the depth of the dependent MMA sequence
+    float dc0[4] = {0.f, 0.f, 0.f, 0.f}, dc8[4] = {0.f, 0.f, 0.f, 0.f}, dm[4] = {0.f, 0.f, 0.f, 0.f};
+    float dc0x[4] = {0.f, 0.f, 0.f, 0.f}, dc8x[4] = {0.f, 0.f, 0.f, 0.f}, dmx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s_ = 0; s_ < 8; ++s_) {
+      const float4 r0 = a_row0[s_ ^ a_swz], r1 = a_row1[s_ ^ a_swz];
+      uint32_t w0h, w0l, w1h, w1l, w2h, w2l, w3h, w3l, p0h, p0l, p1h, p1l, p2h, p2l, p3h, p3l;
+      split_tf32(r0.x, w0h, w0l);  // a0: row g,     pixel A
+      split_tf32(r1.x, w1h, w1l);  // a1: row g + 8, pixel A
+      split_tf32(r0.y, w2h, w2l);  // a2: row g,     pixel B
+      split_tf32(r1.y, w3h, w3l);  // a3: row g + 8, pixel B
+      split_tf32(r0.z, p0h, p0l);
+      split_tf32(r1.z, p1h, p1l);
+      split_tf32(r0.w, p2h, p2l);
+      split_tf32(r1.w, p3h, p3l);
+      const float2 bq = sm.b_ch0[warp][s_][lane];
+      uint32_t b0h, b0l, b1h, b1l;
+      split_tf32(bq.x, b0h, b0l);
+      split_tf32(bq.y, b1h, b1l);
+      mma_tf32(dc0, w0h, w1h, w2h, w3h, b0h, b1h);
+      mma_tf32(dc0x, w0l, w1l, w2l, w3l, b0h, b1h);
+      mma_tf32(dc0x, w0h, w1h, w2h, w3h, b0l, b1l);
+      if (GEO) {
+        const float2 b8 = b8_src[s_ * b8_step];
+        split_tf32(b8.x, b0h, b0l);
+        split_tf32(b8.y, b1h, b1l);
+        mma_tf32(dc8, w0h, w1h, w2h, w3h, b0h, b1h);
+        mma_tf32(dc8x, w0l, w1l, w2l, w3l, b0h, b1h);
+        mma_tf32(dc8x, w0h, w1h, w2h, w3h, b0l, b1l);
+      }
+      const float2 bm = sm.b_mom[s_][lane];
+      mma_tf32(dm, p0h, p1h, p2h, p3h, __float_as_uint(bm.x), __float_as_uint(bm.y));
+      mma_tf32(dmx, p0l, p1l, p2l, p3l, __float_as_uint(bm.x), __float_as_uint(bm.y));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      dc0[i] += dc0x[i];
+      dc8[i] += dc8x[i];
+      dm[i] += dmx[i];
+    }
+    // D fragments: lane (g, t) holds columns 2t, 2t+1 of rows g (d[0], d[1]) and g + 8 (d[2], d[3]).
+    // Moment columns: 0 S1, 1 Sx, 2 Sy, 3 Sxx, 4 Sxy, 5 Syy -> collect all six in the lane with t == 0.
+    float Sy[2], Sxx[2], Sxy[2], Syy[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      Sy[h] = __shfl_down_sync(0xffffffffu, dm[2 * h], 1);
+      Sxx[h] = __shfl_down_sync(0xffffffffu, dm[2 * h + 1], 1);
+      Sxy[h] = __shfl_down_sync(0xffffffffu, dm[2 * h], 2);
+      Syy[h] = __shfl_down_sync(0xffffffffu, dm[2 * h + 1], 2);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = fg + 8 * h;
+      if (row < rows) {
+        const float4 m1 = sm.meta[warp][row][1];
+        float* const arow = accum + (size_t)__float_as_int(m1.w) * HG_ACC_FLOATS;
+        red_add_v2(arow + 2 * ft, dc0[2 * h], dc0[2 * h + 1]);
+        if (ft == 0) {
+          const float4 m0 = sm.meta[warp][row][0];
+          const float S1 = dm[2 * h], Sx = dm[2 * h + 1];
+          const float u = m0.x - cx, v = m0.y - cy, o = m1.y;
+          const float Dx = u * S1 - Sx, Dy = v * S1 - Sy[h];                 // sum p dx, sum p dy
+          const float Qxx = u * (Dx - Sx) + Sxx[h];                          // sum p dx^2
+          const float Qxy = u * Dy - v * Sx + Sxy[h];                        // sum p dx dy
+          const float Qyy = v * (Dy - Sy[h]) + Syy[h];                       // sum p dy^2
+          const float g9 = -o * ddelx_dx * (m0.z * Dx + m0.w * Dy);
+          const float g10 = -o * ddely_dy * (m1.x * Dy + m0.w * Dx);
+          const float ho = -0.5f * o;
+          red_add_v4(arow + 8, dc8[2 * h], g9, g10, ho * Qxx);
+          red_add_v2(arow + 12, ho * Qxy, ho * Qyy);
+          atomicAdd(arow + 14, S1);
+        }
+      }
+    }
+    rows = 0;
+    __syncwarp();
+  };
+
+  Prefetch pf;
+  auto prefetch = [&](int b) {
+    const int q = n_eff - 1 - (b * kBatchC + tid);
+    if (tid < kBatchC && q >= 0) gather_record<false>(pf, point_list, records, nullptr, nullptr, range.x + q);
+  };
+  if (nb > 0) prefetch(0);
+
+  for (int b = 0; b < nb; ++b) {
+    __syncthreads();
+    const int cnt = min(kBatchC, n_eff - b * kBatchC);
+    if (tid < cnt) stage_record<GEO, false>(s_rec, tid, pf);
+    __syncthreads();
+    if (b + 1 < nb) prefetch(b + 1);
+
+    const int q_first = n_eff - 1 - b * kBatchC;
+    if (q_first - (cnt - 1) >= wmax) continue;  // the whole batch lies behind this warp
+    for (int c0 = 0; c0 < cnt; c0 += 32) {
+      if (q_first - (c0 + 31) >= wmax) continue;
+      const int j = c0 + lane;
+      bool keepA = false, keepB = false;
+      if (j < cnt) {
+        const float4 ea = s_rec[kRecQuads * j];
+        const float4 eb = s_rec[kRecQuads * j + 1];
+        const int q = q_first - j;
+        keepA = q < wmaxA && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyA0, fyA1);
+        keepB = q < wmaxB && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyB0, fyB1);
+      }
+      const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
+      uint32_t mask = maskA | maskB;
+      while (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int k = c0 + bit;
+        const int q = q_first - k;
+        const float4* e = s_rec + kRecQuads * k;
+        const float4 ea = e[0];
+        const float4 eb = e[1];
+        float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f;
+        bool any;
+        const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
+        if (hasA && hasB) {  // one basic block: the two pixels' dependency chains interleave
+          any = pixel_pair_c<GEO, DEPTH>(A, e, ea, eb, pixx, pixyA, q, wA, pA);
+          any |= pixel_pair_c<GEO, DEPTH>(B, e, ea, eb, pixx, pixyB, q, wB, pB);
+        } else if (hasA) {
+          any = pixel_pair_c<GEO, DEPTH>(A, e, ea, eb, pixx, pixyA, q, wA, pA);
+        } else {
+          any = pixel_pair_c<GEO, DEPTH>(B, e, ea, eb, pixx, pixyB, q, wB, pB);
+        }
+        if (__ballot_sync(0xffffffffu, any) == 0) continue;
+        a_tile[rows * 32 + ((rows & 1) ? a_odd : a_even)] = make_float4(wA, wB, pA, pB);
+        if (lane == 0) {
+          sm.meta[warp][rows][0] = ea;
+          sm.meta[warp][rows][1] = eb;
+        }
+        if (++rows == kGroupC) flush();
+      }
+    }
+  }
+  if (rows > 0) flush();
+}
+
 }  // namespace
 
 int launch_blend_bwd(const hg_raster_inputs& in, const GeomState& g, const BinState& b,
@@ -511,9 +841,35 @@ int launch_blend_bwd(const hg_raster_inputs& in, const GeomState& g, const BinSt
   const bool depth = dL_dout_invdepth != nullptr;
   static const int variant = [] {
     const char* e = getenv("HG_BLEND_BWD_VARIANT");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 3;
   }();
-  if (variant == 2) {
+  if (variant == 3 && !interp) {
+    static const bool attr_ok = [] {
+      const int bytes = (int)sizeof(BwdMmaSmem);
+      bool ok = true;
+      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      return ok;
+    }();
+    if (!attr_ok) {
+      set_error("blend_bwd: could not reserve %zu bytes of shared memory", sizeof(BwdMmaSmem));
+      return HG_ERR_CUDA;
+    }
+#define HG_LAUNCH3(G_, D_)                                                                          \
+  blend_bwd3_kernel<G_, D_><<<grid, kThreadsB, sizeof(BwdMmaSmem), stream>>>(                       \
+      img.ranges, b.vals, g.records, in.W, in.H, focal_x, focal_y, in.background, all_map_pixels,   \
+      img.final_T, img.n_contrib, dL_dpix, dL_dout_all_map, dL_dout_plane_depth, dL_dout_invdepth, accum)
+    if (geo && depth) HG_LAUNCH3(true, true);
+    else if (geo) HG_LAUNCH3(true, false);
+    else if (depth) HG_LAUNCH3(false, true);
+    else HG_LAUNCH3(false, false);
+#undef HG_LAUNCH3
+    HG_POST_LAUNCH(in.debug, stream, "blend_bwd");
+    return HG_OK;
+  }
+  if (variant == 2 || variant == 3) {
 #define HG_LAUNCH2(G_, D_, I_)                                                                \
   blend_bwd2_kernel<G_, D_, I_><<<grid, kThreadsB, 0, stream>>>(                              \
       img.ranges, b.vals, g.records, in.ts, in.kids, in.W, in.H, focal_x, focal_y,            \

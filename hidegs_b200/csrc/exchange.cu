@@ -1,0 +1,138 @@
+// exchange.cu — the gradient exchange of view-sharded training as ONE kernel over NVSwitch multicast memory
+// (include/hidegs_exchange.h).  Replaces the ring all-reduce a library collective would run after the backward.
+//
+// Every rank owns 1/world of the flat gradient arena.  For its slice it issues `multimem.ld_reduce.add.v4.f32` on the
+// multicast address — the switch fetches the 16 bytes from every replica and returns their sum — and writes the result
+// back through the same address with `multimem.st.v4.f32`, which the switch replicates into every GPU.  Per GPU that is
+// ~1x the arena out (its replicas of all slices are read once) and ~1x in (the sums), with the additions done in the
+// fabric.  Two cross-rank barriers per CTA (flags in symmetric memory, CAS put / CAS take, system scope) bracket the
+// data phase; CTA b of one rank only ever pairs with CTA b of the others, so no co-residency is assumed.
+#include "common.cuh"
+
+#include <cstdlib>
+#include "../../include/hidegs_exchange.h"
+
+namespace hg {
+namespace {
+
+constexpr int kExThreads = 512;
+#ifndef HG_NVLS_UNROLL
+#define HG_NVLS_UNROLL 4
+#endif
+constexpr int kExDefaultBlocks = 148 * 2;
+
+__device__ __forceinline__ float4 mc_ld_reduce(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st(float4* p, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float mc_ld_reduce1(const float* p) {
+  float v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st1(float* p, const float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Barrier between the CTAs with this block index on every rank.  Slot [block][src] of rank dst's flag words is written
+// only by rank src (0 -> 1) and cleared only by rank dst (1 -> 0), so the same slots serve every barrier of every call.
+__device__ __forceinline__ void rank_barrier(const uint64_t* __restrict__ flag_ptrs, int rank, int world) {
+  __syncthreads();
+  if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+    const int peer = threadIdx.x;
+    uint32_t* remote = reinterpret_cast<uint32_t*>(flag_ptrs[peer]) + (size_t)blockIdx.x * world + rank;
+    uint32_t* mine = reinterpret_cast<uint32_t*>(flag_ptrs[rank]) + (size_t)blockIdx.x * world + peer;
+    __threadfence_system();
+    while (atomicCAS_system(remote, 0u, 1u) != 0u) {
+    }
+    while (atomicCAS_system(mine, 1u, 0u) != 1u) {
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+template <int kExUnroll>
+__global__ void __launch_bounds__(kExThreads)
+nvls_allreduce_kernel(float4* __restrict__ mc, const uint64_t* __restrict__ flag_ptrs, const int rank, const int world,
+                      const int64_t n4, const int tail) {
+  rank_barrier(flag_ptrs, rank, world);  // every replica of the arena is complete
+
+  const int64_t per = (n4 + world - 1) / world;
+  const int64_t begin = per * rank;
+  const int64_t end = begin + per < n4 ? begin + per : n4;
+  const int64_t stride = (int64_t)gridDim.x * kExThreads;
+  int64_t i = begin + (int64_t)blockIdx.x * kExThreads + threadIdx.x;
+  for (; i + (kExUnroll - 1) * stride < end; i += kExUnroll * stride) {
+    float4 v[kExUnroll];
+#pragma unroll
+    for (int u = 0; u < kExUnroll; ++u) v[u] = mc_ld_reduce(mc + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kExUnroll; ++u) mc_st(mc + i + u * stride, v[u]);
+  }
+  for (; i < end; i += stride) mc_st(mc + i, mc_ld_reduce(mc + i));
+  if (rank == 0 && blockIdx.x == 0 && (int)threadIdx.x < tail) {
+    float* p = reinterpret_cast<float*>(mc + n4) + threadIdx.x;
+    mc_st1(p, mc_ld_reduce1(p));
+  }
+  __threadfence_system();
+  rank_barrier(flag_ptrs, rank, world);  // every replica holds the sums; nobody still reads this rank's memory
+}
+
+}  // namespace
+}  // namespace hg
+
+extern "C" {
+
+size_t hg_nvls_flag_words(int32_t world, int32_t max_blocks) {
+  if (world < 1 || max_blocks < 1) return 0;
+  return (size_t)world * (size_t)max_blocks;
+}
+
+int hg_nvls_allreduce_f32(void* mc_ptr, float* local_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
+                          int64_t n_floats, int32_t blocks, void* stream) {
+  if (world < 1 || rank < 0 || rank >= world || n_floats < 0 || blocks < 0) {
+    hg::set_error("hg_nvls_allreduce_f32: bad argument (rank %d, world %d, n %lld, blocks %d)", rank, world,
+                  (long long)n_floats, blocks);
+    return HG_ERR_INVALID_ARG;
+  }
+  if (world == 1 || n_floats == 0) return HG_OK;
+  if (!mc_ptr || !local_ptr || !flag_ptrs) {
+    hg::set_error("hg_nvls_allreduce_f32: multicast pointer, local pointer and flag table are mandatory");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (((uintptr_t)mc_ptr | (uintptr_t)local_ptr) & 15) {
+    hg::set_error("hg_nvls_allreduce_f32: the arena must be 16-byte aligned");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (world > hg::kExThreads) {
+    hg::set_error("hg_nvls_allreduce_f32: world %d too large", world);
+    return HG_ERR_INVALID_ARG;
+  }
+  const int grid = blocks ? blocks : hg::kExDefaultBlocks;
+  static const int unroll = [] {
+    const char* e = getenv("HG_NVLS_UNROLL");
+    return e ? atoi(e) : HG_NVLS_UNROLL;
+  }();
+#define HG_EX_LAUNCH(U_)                                                                  \
+  hg::nvls_allreduce_kernel<U_><<<grid, hg::kExThreads, 0, (cudaStream_t)stream>>>(       \
+      (float4*)mc_ptr, flag_ptrs, rank, world, n_floats / 4, (int)(n_floats % 4))
+  if (unroll >= 8) HG_EX_LAUNCH(8);
+  else if (unroll >= 4) HG_EX_LAUNCH(4);
+  else if (unroll >= 2) HG_EX_LAUNCH(2);
+  else HG_EX_LAUNCH(1);
+#undef HG_EX_LAUNCH
+  HG_POST_LAUNCH(false, (cudaStream_t)stream, "nvls_allreduce");
+  return HG_OK;
+}
+
+}  // extern "C"

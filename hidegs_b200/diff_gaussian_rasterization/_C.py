@@ -176,6 +176,18 @@ def rasterize_gaussians(background, indices, parent_indices, ts, kids, means3D, 
             binningBuffer, imgBuffer, out_invdepth)
 
 
+_gradient_arena_provider = None
+
+
+def set_gradient_arena_provider(fn):
+    """Opt-in: `fn(numel, device) -> flat fp32 tensor or None` supplies the arena the next backward calls write their
+    gradients into (instead of a fresh allocation).  The caller owns the buffer: gradients returned by a backward are
+    views of it and are overwritten by the next backward that receives the same buffer.  Used by the view-sharded
+    data-parallel path so that the gradients are born in multicast symmetric memory (hidegs_b200/parallel.py)."""
+    global _gradient_arena_provider
+    _gradient_arena_provider = fn
+
+
 def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_indices, ts, kids, means3D, radii,
                                  colors, all_maps, opacities, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_all_map,
@@ -204,7 +216,15 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
     widths = (("means3D", 3), ("sh", 3 * M), ("opacity", 1), ("scales", 3), ("rotations", 4), ("means2D", 3),
               ("colors", 3), ("cov3D", 6), ("all_map", 5), ("invdepths", 1 if has_depth_grad else 0))
     total = fullP * sum(w for _, w in widths)
-    arena = (torch.zeros if prezero else torch.empty)((total,), dtype=torch.float32, device=dev)
+    arena = _gradient_arena_provider(total, dev) if _gradient_arena_provider is not None else None
+    if arena is None:
+        arena = (torch.zeros if prezero else torch.empty)((total,), dtype=torch.float32, device=dev)
+    else:  # caller-owned arena (e.g. multicast symmetric memory for the in-fabric gradient exchange)
+        if arena.numel() < total or arena.dtype != torch.float32 or arena.device != dev or not arena.is_contiguous():
+            raise ValueError("gradient arena provider returned an unusable buffer")
+        arena = arena[:total]
+        if prezero:
+            arena.zero_()
     g, off = {}, 0
     for name, w in widths:
         g[name] = arena[off:off + fullP * w].view(fullP, w)

@@ -7,8 +7,14 @@ rotation 4).  `flat_view()` recovers that arena from the gradient tensors so the
 place on a single buffer (NCCL over NVLink on GPUs, gloo in the CPU tests) with no pack kernel; when
 the tensors do not share storage (e.g. autograd had to clone one) they are packed first.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
+
+EXCHANGE_SYMBOLS = ("hg_nvls_flag_words", "hg_nvls_allreduce_f32")  # include/hidegs_exchange.h
+_MAX_BLOCKS = 1024
 
 
 def shard_views(views, rank=None, world=None):
@@ -61,3 +67,90 @@ def allreduce_gradients(grads, group=None, average=False, async_op=False):
             g.copy_(packed[off:off + g.numel()].view_as(g))
             off += g.numel()
     return work, nbytes
+
+
+def _exchange_lib():
+    from . import _lib
+    L = _lib.lib()
+    if not getattr(L, "_hg_exchange_ready", False):
+        L.hg_nvls_flag_words.restype, L.hg_nvls_flag_words.argtypes = ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]
+        L.hg_nvls_allreduce_f32.restype = ctypes.c_int
+        L.hg_nvls_allreduce_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                            ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]
+        L._hg_exchange_ready = True
+    return L
+
+
+def nvls_available(device=None):
+    """True when the gradient arena can live in multicast (NVLS) symmetric memory on this box."""
+    if not (torch.cuda.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    if dist.get_backend() != "nccl":
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        return bool(symm._SymmetricMemory.has_multicast_support(torch._C._autograd.DeviceType.CUDA, idx))
+    except Exception:  # noqa: BLE001 — an old torch or a box without fabric support
+        return False
+
+
+class SymmetricArena:
+    """A flat fp32 gradient arena allocated in symmetric memory with a multicast mapping, plus the flag words of the
+    in-kernel cross-rank barrier.  `all_reduce_()` sums it over the ranks in place with ONE kernel
+    (`hg_nvls_allreduce_f32`: multimem.ld_reduce + multimem.st through the NVSwitch, include/hidegs_exchange.h).
+
+    Allocation and pointer exchange are torch.distributed._symmetric_memory plumbing; every rank must construct the
+    arenas in the same order with the same sizes."""
+
+    def __init__(self, numel, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.numel = int(numel)
+        padded = (self.numel + 1023) // 1024 * 1024
+        L = _exchange_lib()
+        self._buf = symm.empty(padded, dtype=torch.float32, device=device)
+        self._buf.zero_()
+        self._h = symm.rendezvous(self._buf, group.group_name)
+        if not int(self._h.multicast_ptr):
+            raise RuntimeError("SymmetricArena: no multicast (NVLS) mapping on this box; use the NCCL exchange")
+        words = int(L.hg_nvls_flag_words(self.world, _MAX_BLOCKS))
+        self._flags = symm.empty(words, dtype=torch.int32, device=device)
+        self._flags.zero_()
+        self._hf = symm.rendezvous(self._flags, group.group_name)
+        off = int(getattr(self._hf, "offset", 0))
+        self._flag_ptrs = torch.tensor([int(p) + off for p in self._hf.buffer_ptrs], dtype=torch.int64, device=device)
+        self._mc = int(self._h.multicast_ptr) + int(getattr(self._h, "offset", 0))
+        self.blocks = int(os.environ.get("HG_NVLS_BLOCKS", 0))
+        torch.cuda.synchronize(device)
+        self._h.barrier()  # every rank's flags are zero before anyone signals
+
+    @property
+    def tensor(self):
+        """The arena as a flat tensor (this rank's replica)."""
+        return self._buf[:self.numel]
+
+    def all_reduce_(self, numel=None):
+        n = self.numel if numel is None else int(numel)
+        L = _exchange_lib()
+        from . import _lib
+        stream = torch.cuda.current_stream(self._buf.device).cuda_stream
+        _lib.check(L.hg_nvls_allreduce_f32(self._mc, self._buf.data_ptr(), self._flag_ptrs.data_ptr(), self.rank,
+                                           self.world, n, self.blocks, stream), "hg_nvls_allreduce_f32")
+        return n * 4
+
+
+def make_exchange_arena(numel, device, group=None):
+    """The gradient arena of one rank: (flat tensor, SymmetricArena or None).  With NVLS available (and
+    HG_EXCHANGE != "nccl") the arena lives in multicast memory and the exchange is the fused in-fabric kernel;
+    otherwise a plain tensor that `dist.all_reduce` (NCCL / gloo) sums."""
+    mode = os.environ.get("HG_EXCHANGE", "auto")
+    dev = torch.device(device)
+    if mode != "nccl" and dev.type == "cuda" and nvls_available(dev):
+        arena = SymmetricArena(numel, dev, group)
+        return arena.tensor, arena
+    if mode == "nvls":
+        raise RuntimeError("HG_EXCHANGE=nvls but multicast symmetric memory is not available")
+    return torch.zeros(int(numel), dtype=torch.float32, device=dev), None

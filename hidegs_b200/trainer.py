@@ -22,6 +22,7 @@ from . import gaussian_renderer as gr
 from . import loss_utils as lu
 from ._geometry_lib import lib as _G
 from . import _lib
+from . import parallel
 from .frequency_regularization import GroundTruthCache, frequency_regularization_pyramid_scale
 
 GROUPS = (("xyz", 3), ("features", 48), ("opacity", 1), ("scaling", 3), ("rotation", 4))
@@ -101,7 +102,13 @@ class GaussianParams:
         self.N = N
         width = sum(w for _, w in GROUPS)
         self.param_arena = torch.empty(N * width, dtype=torch.float32, device=dev)
-        self.grad_arena = torch.zeros(N * width, dtype=torch.float32, device=dev)
+        # the gradient arena is born where the per-step exchange wants it: multicast symmetric memory when the ranks
+        # share an NVSwitch (in-fabric all-reduce kernel), a plain tensor otherwise (NCCL / gloo all-reduce)
+        self.exchange = None
+        if dist.is_initialized() and dist.get_world_size() > 1 and dev.type == "cuda":
+            self.grad_arena, self.exchange = parallel.make_exchange_arena(N * width, dev)
+        else:
+            self.grad_arena = torch.zeros(N * width, dtype=torch.float32, device=dev)
         src = dict(xyz=xyz, features=features.reshape(N, -1), opacity=opacity_logit, scaling=scaling_log, rotation=rotation)
         self.leaves, self.slices = {}, {}
         off = 0
@@ -269,7 +276,10 @@ class ViewShardedTrainer:
             self.params.grad_arena.zero_()
         n_views = len(views)
         if self.world > 1:
-            dist.all_reduce(self.params.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
+            if self.params.exchange is not None:  # ONE kernel: multimem.ld_reduce + multimem.st through the NVSwitch
+                self.params.exchange.all_reduce_()
+            else:
+                dist.all_reduce(self.params.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
             if self.sparse_adam:  # union of the ranks' visible sets
                 dist.all_reduce(self.visible, op=dist.ReduceOp.MAX, group=self.group)
             n_views = total_views if total_views is not None else n_views * self.world

@@ -1,0 +1,48 @@
+/*
+ * hidegs_exchange.h — C-ABI of the per-step gradient exchange of view-sharded training.
+ *
+ * The reference trains on one GPU: its step ends with `loss.backward()` filling the `.grad` of the five parameter
+ * tensors (scene/gaussian_model.py:175-233 registers them with the optimiser, scene/OurAdam.py:106 consumes them).
+ * With camera views sharded over the GPUs of one NVSwitch box the only coupling between ranks is the SUM of those
+ * gradients.  They live in ONE flat fp32 arena per rank (59 floats per Gaussian); when that arena is allocated in
+ * symmetric memory with a multicast (NVLS) mapping, the sum is ONE kernel: every rank owns 1/world of the arena, pulls
+ * the switch-reduced value of its slice (`multimem.ld_reduce.add.v4.f32`: the NVSwitch reads all replicas and adds
+ * them) and broadcasts it back to every replica (`multimem.st.v4.f32`).  Each GPU moves ~1x the arena in and out
+ * over NVLink instead of the 2(world-1)/world x of a ring, and no staging buffers are involved.
+ *
+ * Plumbing (allocation of the symmetric arena, exchange of the multicast / peer pointers) is done by the caller —
+ * `torch.distributed._symmetric_memory` in hidegs_b200/parallel.py.  Conventions as in hidegs_raster.h.
+ */
+#ifndef HIDEGS_EXCHANGE_H
+#define HIDEGS_EXCHANGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "hidegs_raster.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Number of uint32 flag words every rank must provide (zero-initialised, symmetric) for `max_blocks` CTAs. */
+HG_API size_t hg_nvls_flag_words(int32_t world, int32_t max_blocks);
+
+/* In-place all-reduce (sum) of `n_floats` fp32 values that every rank holds at the same offset of a symmetric
+ * allocation.
+ *   mc_ptr      multicast (NVLS) address of the first value — stores/reductions through it reach every replica
+ *   local_ptr   this rank's own replica of the same values (used only for the < 4-float tail and checks)
+ *   flag_ptrs   DEVICE array of `world` pointers: flag_ptrs[r] = rank r's flag words as mapped in THIS process
+ *               (peer-to-peer addresses; hg_nvls_flag_words words each, all zero before the first call)
+ *   blocks      CTAs to launch (0 = default); must be identical on every rank and <= the max_blocks the flags were
+ *               sized for
+ * The kernel begins with a cross-rank barrier per CTA (every rank's arena is complete: the call is stream-ordered after
+ * the local producer) and ends with one (every replica holds the sums and nobody still reads this rank's memory), so
+ * the caller may overwrite the arena right after it on the same stream.  mc_ptr and local_ptr must be 16-byte aligned.
+ * world == 1 is a no-op. */
+HG_API int hg_nvls_allreduce_f32(void *mc_ptr, float *local_ptr, const uint64_t *flag_ptrs, int32_t rank,
+                                 int32_t world, int64_t n_floats, int32_t blocks, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
