@@ -521,11 +521,13 @@ blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 constexpr int kGroupC = 16;               // entries per flush (the M of the MMA)
 constexpr int kWarpsC = kThreadsB / 32;
 
-constexpr int kBatchC = 128;              // entries staged per round
+constexpr int kBatchC = 96;               // entries staged per round (shared memory: 4 CTAs / SM must fit)
+constexpr int kAStride = 68;              // floats per A row: 64 pixels + 4 pad (conflict-free ldmatrix rows, STS.64)
 
 struct alignas(16) BwdMmaSmem {
   float4 rec[kBatchC * kRecQuads];        // staged tile-list entries (as variant B)
-  float4 a_tile[kWarpsC][kGroupC * 32];   // (wgt_A, wgt_B, p_A, p_B) per (row, lane), XOR-swizzled (see a_slot)
+  float a_w[kWarpsC][kGroupC * kAStride]; // wgt, row-major [entry][k]; k = 2 lane + {0: pixel A, 1: pixel B}
+  float a_p[kWarpsC][kGroupC * kAStride]; // p, same layout
   float2 b_ch0[kWarpsC][8][32];           // channels 0..7 of the warp's pixels, fragment order: (b0, b1) per lane
   float2 b_ch8[kWarpsC][8][4];            // channel 8 (column 0 of its n-tile: the lanes with g == 0)
   float2 zero2;                           // what the lanes with g != 0 read instead
@@ -534,9 +536,16 @@ struct alignas(16) BwdMmaSmem {
   int s_max[kWarpsC];
 };
 
-// float4 slot of pixel pair (t, s) in row `row` of an A tile.  Writers (fixed row, t; s = 0..7) and fragment readers
-// (fixed s; rows {2i, 2i+1} x t = 0..3) both touch eight distinct 16-byte bank groups per quarter-warp phase.
-__device__ __forceinline__ int a_slot(int row, int t, int s) { return row * 32 + t * 8 + (s ^ (((row & 1) << 2) | t)); }
+// A-operand quad (a0, a1, a2, a3) of mma.m16n8k8 for one k-step straight from a row-major fp32 tile: each of the four
+// 8x8 "b16" matrices of ldmatrix is 8 rows x 16 bytes = 8 rows x 4 fp32, and lane l receives word (l / 4, l % 4) —
+// exactly the fragment layout.  Lane l supplies the row address of matrix l / 8: rows (l % 8) + 8 ((l / 8) & 1),
+// columns 4 (l / 16) .. +3 of the k-step.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const float* smem_row_ptr) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
 
 // v = hi + lo with hi the TF32 truncation of v (one LOP3; cvt.rna.tf32 is emulated with five instructions on sm_100a)
 // and lo = v - hi exact; the MMA ignores the bits of lo below TF32, so |error| <= 2^-20 |v|.
@@ -633,31 +642,43 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                                all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
                                dL_invdepths);
 
-  // ---- constant B tiles.  K index of a pixel pair = (t, s) = (lane >> 3, lane & 7) of the lane that owns it; inside
-  // k-step s column j < 4 is pixel A of lane 8 j + s and column j + 4 its pixel B.
+  // ---- constant B tiles.  K index of a pixel: k = 2 lane + {0: pixel A, 1: pixel B} of the lane that owns it; k-step
+  // s covers k = 8 s .. 8 s + 7, and fragment lane (g, t) holds b0 = B[8 s + t][g], b1 = B[8 s + t + 4][g].
   {
-    const int ks = lane & 7, kt = lane >> 3;
+    const int ks = lane >> 2, jA = 2 * (lane & 3);  // this lane's pixel A is column jA of k-step ks, pixel B column jA + 1
+    float* const ch0 = reinterpret_cast<float*>(&sm.b_ch0[warp][ks][0]);
+    float* const ch8 = reinterpret_cast<float*>(&sm.b_ch8[warp][ks][0]);
+    // column j of a k-step -> fragment lane t = j & 3, component (j >> 2): float index 2 (4 g + t) + (j >> 2)
+    const int fa = 2 * (jA & 3) + (jA >> 2), fb = 2 * ((jA + 1) & 3) + ((jA + 1) >> 2);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sm.b_ch0[warp][ks][c * 4 + kt] = make_float2(A.w[c], B.w[c]);
+    for (int c = 0; c < 8; ++c) {
+      ch0[8 * c + fa] = A.w[c];
+      ch0[8 * c + fb] = B.w[c];
+    }
     if (GEO) {
-      sm.b_ch8[warp][ks][kt] = make_float2(A.w[8], B.w[8]);
+      ch8[fa] = A.w[8];
+      ch8[fb] = B.w[8];
       if (tid == 0) sm.zero2 = make_float2(0.f, 0.f);
     }
-    // moments of fragment lane (g, t) at k-step s: pixel A = (xi, etaA) = (s - 3.5, t - 3.5), pixel B = (xi, t + 0.5)
+    // moments of fragment lane (g, t) at k-step s: the pixels at k = 8 s + t and 8 s + t + 4
     for (int i = tid; i < 8 * 32; i += kThreadsB) {
       const int s_ = i >> 5, l_ = i & 31, g_ = l_ >> 2, t_ = l_ & 3;
-      const float xi = (float)s_ - 3.5f, ea_ = (float)t_ - 3.5f, eb_ = (float)t_ + 0.5f;
-      float m0, m1;
-      switch (g_) {
-        case 0: m0 = 1.f; m1 = 1.f; break;
-        case 1: m0 = xi; m1 = xi; break;
-        case 2: m0 = ea_; m1 = eb_; break;
-        case 3: m0 = xi * xi; m1 = xi * xi; break;
-        case 4: m0 = xi * ea_; m1 = xi * eb_; break;
-        case 5: m0 = ea_ * ea_; m1 = eb_ * eb_; break;
-        default: m0 = 0.f; m1 = 0.f; break;
+      float m[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k = 8 * s_ + t_ + 4 * h, owner = k >> 1;
+        const float xi = (float)(owner & 7) - 3.5f, eta = (float)((owner >> 3) + 4 * (k & 1)) - 3.5f;
+        switch (g_) {
+          case 0: m[h] = 1.f; break;
+          case 1: m[h] = xi; break;
+          case 2: m[h] = eta; break;
+          case 3: m[h] = xi * xi; break;
+          case 4: m[h] = xi * eta; break;
+          case 5: m[h] = eta * eta; break;
+          default: m[h] = 0.f; break;
+        }
       }
-      sm.b_mom[s_][l_] = make_float2(m0, m1);
+      sm.b_mom[s_][l_] = make_float2(m[0], m[1]);
     }
   }
 
@@ -677,12 +698,11 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const int nb = (n_eff + kBatchC - 1) / kBatchC;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-  float4* const a_tile = sm.a_tile[warp];
+  float* const a_w = sm.a_w[warp];
+  float* const a_p = sm.a_p[warp];
   const int fg = lane >> 2, ft = lane & 3;                      // fragment coordinates of this lane
-  const int a_even = a_slot(0, lane >> 3, lane & 7), a_odd = a_slot(1, lane >> 3, lane & 7) - 32;  // writer slots
-  const int a_swz = ((fg & 1) << 2) | ft;                       // reader swizzle (rows g and g + 8 share it)
-  const float4* const a_row0 = a_tile + fg * 32 + ft * 8;       // + (k-step ^ a_swz)
-  const float4* const a_row1 = a_row0 + 8 * 32;
+  // ldmatrix row address this lane supplies: matrix lane / 8 -> rows (lane % 8) + 8 (matrix & 1), columns 4 (matrix >> 1)
+  const int a_ld = ((lane & 7) + 8 * ((lane >> 3) & 1)) * kAStride + 4 * (lane >> 4);  // + 8 * k-step
   const float2* const b8_src = fg == 0 ? &sm.b_ch8[warp][0][ft] : &sm.zero2;  // + 4 * k-step for g == 0
   const int b8_step = fg == 0 ? 4 : 0;
   int rows = 0;  // entries parked in the A tile
@@ -695,16 +715,18 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     float dc0x[4] = {0.f, 0.f, 0.f, 0.f}, dc8x[4] = {0.f, 0.f, 0.f, 0.f}, dmx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int s_ = 0; s_ < 8; ++s_) {
-      const float4 r0 = a_row0[s_ ^ a_swz], r1 = a_row1[s_ ^ a_swz];
+      uint32_t wq[4], pq[4];
+      ldmatrix_x4(wq, a_w + a_ld + 8 * s_);
+      ldmatrix_x4(pq, a_p + a_ld + 8 * s_);
       uint32_t w0h, w0l, w1h, w1l, w2h, w2l, w3h, w3l, p0h, p0l, p1h, p1l, p2h, p2l, p3h, p3l;
-      split_tf32(r0.x, w0h, w0l);  // a0: row g,     pixel A
-      split_tf32(r1.x, w1h, w1l);  // a1: row g + 8, pixel A
-      split_tf32(r0.y, w2h, w2l);  // a2: row g,     pixel B
-      split_tf32(r1.y, w3h, w3l);  // a3: row g + 8, pixel B
-      split_tf32(r0.z, p0h, p0l);
-      split_tf32(r1.z, p1h, p1l);
-      split_tf32(r0.w, p2h, p2l);
-      split_tf32(r1.w, p3h, p3l);
+      split_tf32(__uint_as_float(wq[0]), w0h, w0l);
+      split_tf32(__uint_as_float(wq[1]), w1h, w1l);
+      split_tf32(__uint_as_float(wq[2]), w2h, w2l);
+      split_tf32(__uint_as_float(wq[3]), w3h, w3l);
+      split_tf32(__uint_as_float(pq[0]), p0h, p0l);
+      split_tf32(__uint_as_float(pq[1]), p1h, p1l);
+      split_tf32(__uint_as_float(pq[2]), p2h, p2l);
+      split_tf32(__uint_as_float(pq[3]), p3h, p3l);
       const float2 bq = sm.b_ch0[warp][s_][lane];
       uint32_t b0h, b0l, b1h, b1l;
       split_tf32(bq.x, b0h, b0l);
@@ -817,7 +839,8 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
           any = pixel_pair_c<GEO, DEPTH>(B, e, ea, eb, pixx, pixyB, q, wB, pB);
         }
         if (__ballot_sync(0xffffffffu, any) == 0) continue;
-        a_tile[rows * 32 + ((rows & 1) ? a_odd : a_even)] = make_float4(wA, wB, pA, pB);
+        *reinterpret_cast<float2*>(a_w + rows * kAStride + 2 * lane) = make_float2(wA, wB);
+        *reinterpret_cast<float2*>(a_p + rows * kAStride + 2 * lane) = make_float2(pA, pB);
         if (lane == 0) {
           sm.meta[warp][rows][0] = ea;
           sm.meta[warp][rows][1] = eb;
