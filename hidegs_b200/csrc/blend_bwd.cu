@@ -506,7 +506,7 @@ blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 // Every gradient a (pixel, entry) pair contributes is a per-pair scalar times a per-PIXEL constant:
 //   dL/d(rgb, 1/z, all_map)[entry] = sum_pix  wgt(pix, entry) * dL/dpixel[ch](pix)           wgt = alpha * T
 //   dL/d(mean2D, conic, opacity)   = polynomials in the six moments  sum_pix p(pix, entry) * {1, xi, eta, xi^2, xi eta,
-//                                    eta^2}  with p = G * dL/dalpha and (xi, eta) the pixel's offset from the sub-tile
+//                                    eta^2}  with p = alpha * dL/dalpha and (xi, eta) the pixel's offset from the sub-tile
 //                                    centre (expand dx = (x_e - cx) - xi in dG/dx, dx^2, dx dy, dy^2).
 // So for a group of 16 entries the whole reduction over the warp's 64 pixels is  D[16 x n] = A[16 x 64] * B[64 x n]:
 // the lanes park (wgt, p) of their two pixels in a per-warp shared-memory tile, and once 16 entries are collected the
@@ -570,22 +570,23 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// One (pixel, entry) pair of variant C: the recurrence of pixel_pair, returning the two per-pair scalars.
+// One (pixel, entry) pair of variant C: the recurrence of pixel_pair, returning the two per-pair scalars
+// wgt = alpha * T_before and p = alpha * dL/dalpha (= opacity * G * dL/dalpha: the factor every geometric gradient
+// carries; the opacity gradient is sum p / opacity).  A pair that does not contribute is folded in as alpha = 0, which
+// leaves the recurrence untouched without any state select: T / (1 - 0) = T, and the next entry's
+// acc = 0 * g + 1 * acc_new re-derives the same accumulator.
 template <bool GEO, bool DEPTH>
 __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4* __restrict__ e, const float4 ea,
                                              const float4 eb, float pixx, float pixy, int q, float& wgt, float& p) {
   const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
   const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
   const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
-  bool valid = (q < s.last_contributor) && !(power > 0.0f);
-  const float Graw = expf(power);
-  const float test_alpha = __fmul_rn(eb.y, Graw);
-  const float alpha = fminf(0.99f, test_alpha);
-  valid = valid && !(alpha < 1.0f / 255.0f);
-  const float G = valid ? Graw : 0.f;
+  const float test_alpha = __fmul_rn(eb.y, expf(power));
+  const bool valid = (q < s.last_contributor) && !(power > 0.0f) && !(test_alpha < 1.0f / 255.0f);
+  const float alpha = valid ? fminf(0.99f, test_alpha) : 0.f;
   const float rinv = __fdividef(1.0f, 1.0f - alpha);
   const float Tn = s.T * rinv;
-  wgt = valid ? alpha * Tn : 0.f;
+  wgt = alpha * Tn;
   const float4 ec = e[2];
   float g = ec.x * s.w[0] + ec.y * s.w[1] + ec.z * s.w[2];
   if (DEPTH) g += ec.w * s.w[3];
@@ -595,13 +596,12 @@ __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4* __rest
     g += ed.x * s.w[4] + ed.y * s.w[5] + ed.z * s.w[6] + ed.w * s.w[7] + ee * s.w[8];
   }
   const float acc_new = s.last_alpha * s.last_g + (1.0f - s.last_alpha) * s.acc_g;
-  float dL_dalpha = (g - acc_new) * Tn + s.bgT * rinv;
-  if (test_alpha > 0.99f || !valid) dL_dalpha = 0.f;
-  s.T = valid ? Tn : s.T;
-  s.acc_g = valid ? acc_new : s.acc_g;
-  s.last_g = valid ? g : s.last_g;
-  s.last_alpha = valid ? alpha : s.last_alpha;
-  p = G * dL_dalpha;
+  const float dL_dalpha = (g - acc_new) * Tn + s.bgT * rinv;
+  s.T = Tn;
+  s.acc_g = acc_new;
+  s.last_g = g;
+  s.last_alpha = alpha;
+  p = test_alpha > 0.99f ? 0.f : alpha * dL_dalpha;  // the clamp has no gradient (backward.cu:680-682)
   return valid;
 }
 
@@ -777,12 +777,11 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
           const float Qxx = u * (Dx - Sx) + Sxx[h];                          // sum p dx^2
           const float Qxy = u * Dy - v * Sx + Sxy[h];                        // sum p dx dy
           const float Qyy = v * (Dy - Sy[h]) + Syy[h];                       // sum p dy^2
-          const float g9 = -o * ddelx_dx * (m0.z * Dx + m0.w * Dy);
-          const float g10 = -o * ddely_dy * (m1.x * Dy + m0.w * Dx);
-          const float ho = -0.5f * o;
-          red_add_v4(arow + 8, dc8[2 * h], g9, g10, ho * Qxx);
-          red_add_v2(arow + 12, ho * Qxy, ho * Qyy);
-          atomicAdd(arow + 14, S1);
+          const float g9 = -ddelx_dx * (m0.z * Dx + m0.w * Dy);
+          const float g10 = -ddely_dy * (m1.x * Dy + m0.w * Dx);
+          red_add_v4(arow + 8, dc8[2 * h], g9, g10, -0.5f * Qxx);
+          red_add_v2(arow + 12, -0.5f * Qxy, -0.5f * Qyy);
+          atomicAdd(arow + 14, __fdividef(S1, o));
         }
       }
     }
