@@ -581,6 +581,8 @@ __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4* __rest
   const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
   const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
   const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
+  // expf, not a bare ex2.approx: the pair must be classified (alpha >= 1/255, clamp at 0.99) exactly as the forward
+  // classified it.  (Measured: the one-MUFU variant is 3 % faster and flips one borderline pair in 3 M gradients.)
   const float test_alpha = __fmul_rn(eb.y, expf(power));
   const bool valid = (q < s.last_contributor) && !(power > 0.0f) && !(test_alpha < 1.0f / 255.0f);
   const float alpha = valid ? fminf(0.99f, test_alpha) : 0.f;
