@@ -210,6 +210,47 @@ struct FwdPixel {
   bool done;
 };
 
+// Select-predicated twin of fwd_pair (below): the same arithmetic in the same order — results are bit-identical, a lane
+// that does not contribute adds fma(0, feature, C) = C — but without branches, so that the evaluations of a lane's two
+// pixels sit in one basic block and their dependency chains interleave.
+template <bool GEO, bool DEPTH, bool INTERP>
+__device__ __forceinline__ bool fwd_pair_flat(FwdPixel& s, const float4* __restrict__ e, const float4 ea, const float2 eb,
+                                              float pixx, float pixy, uint32_t index1) {
+  const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
+  const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
+  const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
+  float alpha = fminf(0.99f, __fmul_rn(eb.y, expf(power)));
+  if (INTERP) {
+    const float4 e4 = e[4];
+    const float kidsqrt = __fsub_rn(1.0f, __powf(__fsub_rn(1.0f, alpha), e4.z));
+    alpha = __fmaf_rn(alpha, e4.y, __fmul_rn(__fsub_rn(1.0f, e4.y), kidsqrt));
+  }
+  const bool ok = !s.done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+  const float test_T = __fmul_rn(s.T, __fsub_rn(1.0f, alpha));
+  const bool term = ok && test_T < 0.0001f;
+  const bool contrib = ok && !term;
+  s.done = s.done || term;
+  const float wgt = contrib ? __fmul_rn(alpha, s.T) : 0.0f;
+  const float4 ec = e[2];
+  s.C0 = __fmaf_rn(wgt, ec.x, s.C0);
+  s.C1 = __fmaf_rn(wgt, ec.y, s.C1);
+  s.C2 = __fmaf_rn(wgt, ec.z, s.C2);
+  if (DEPTH) s.Dinv = __fmaf_rn(wgt, ec.w, s.Dinv);
+  if (GEO) {
+    const float4 ed = e[3];
+    const float ee = e[4].x;
+    s.A0 = __fmaf_rn(wgt, ed.x, s.A0);
+    s.A1 = __fmaf_rn(wgt, ed.y, s.A1);
+    s.A2 = __fmaf_rn(wgt, ed.z, s.A2);
+    s.A3 = __fmaf_rn(wgt, ed.w, s.A3);
+    s.A4 = __fmaf_rn(wgt, ee, s.A4);
+  }
+  const bool observed = contrib && s.T > 0.5f;
+  s.T = contrib ? test_T : s.T;
+  s.last_contributor = contrib ? index1 : s.last_contributor;
+  return observed;
+}
+
 template <bool GEO, bool DEPTH, bool INTERP>
 __device__ __forceinline__ bool fwd_pair(FwdPixel& s, const float4* __restrict__ e, const float4 ea, const float2 eb,
                                          float pixx, float pixy, uint32_t index1) {
@@ -368,8 +409,15 @@ blend_fwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         const float2 eb = *reinterpret_cast<const float2*>(e + 1);
         const uint32_t index1 = base + (uint32_t)k + 1u;
         bool obsA = false, obsB = false;
-        if ((maskA >> bit) & 1u) obsA = fwd_pair<GEO, DEPTH, INTERP>(A, e, ea, eb, pixx, pixyA, index1);
-        if ((maskB >> bit) & 1u) obsB = fwd_pair<GEO, DEPTH, INTERP>(B, e, ea, eb, pixx, pixyB, index1);
+        const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
+        if (hasA && hasB) {
+          obsA = fwd_pair_flat<GEO, DEPTH, INTERP>(A, e, ea, eb, pixx, pixyA, index1);
+          obsB = fwd_pair_flat<GEO, DEPTH, INTERP>(B, e, ea, eb, pixx, pixyB, index1);
+        } else if (hasA) {
+          obsA = fwd_pair<GEO, DEPTH, INTERP>(A, e, ea, eb, pixx, pixyA, index1);
+        } else {
+          obsB = fwd_pair<GEO, DEPTH, INTERP>(B, e, ea, eb, pixx, pixyB, index1);
+        }
         const uint32_t oa = __ballot_sync(0xffffffffu, obsA), ob = __ballot_sync(0xffffffffu, obsB);
         if ((oa | ob) && lane == 0) atomicAdd(&s_obs[k], __popc(oa) + __popc(ob));
       }
