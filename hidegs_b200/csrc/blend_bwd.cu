@@ -521,11 +521,11 @@ blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 constexpr int kGroupC = 16;               // entries per flush (the M of the MMA)
 constexpr int kWarpsC = kThreadsB / 32;
 
-constexpr int kBatchC = 96;               // entries staged per round (shared memory: 4 CTAs / SM must fit)
+constexpr int kRecQuadsC = 4;             // staged entry of variant C: 64 B (x y a b | c o am4 id | r g b 1/z | am0..3)
 constexpr int kAStride = 68;              // floats per A row: 64 pixels + 4 pad (conflict-free ldmatrix rows, STS.64)
 
 struct alignas(16) BwdMmaSmem {
-  float4 rec[kBatchC * kRecQuads];        // staged tile-list entries (as variant B)
+  float4 rec[kWarpsC][32 * kRecQuadsC];   // per-WARP staging of the 32 entries a round looks at (see the main loop)
   float a_w[kWarpsC][kGroupC * kAStride]; // wgt, row-major [entry][k]; k = 2 lane + {0: pixel A, 1: pixel B}
   float a_p[kWarpsC][kGroupC * kAStride]; // p, same layout
   float2 b_ch0[kWarpsC][8][32];           // channels 0..7 of the warp's pixels, fragment order: (b0, b1) per lane
@@ -533,7 +533,6 @@ struct alignas(16) BwdMmaSmem {
   float2 zero2;                           // what the lanes with g != 0 read instead
   float2 b_mom[8][32];                    // the six moments, fragment order (same for every warp)
   float4 meta[kWarpsC][kGroupC][2];       // per row: (x, y, conic a, b), (conic c, opacity, -, slot id)
-  int s_max[kWarpsC];
 };
 
 // A-operand quad (a0, a1, a2, a3) of mma.m16n8k8 for one k-step straight from a row-major fp32 tile: each of the four
@@ -576,8 +575,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // leaves the recurrence untouched without any state select: T / (1 - 0) = T, and the next entry's
 // acc = 0 * g + 1 * acc_new re-derives the same accumulator.
 template <bool GEO, bool DEPTH>
-__device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4* __restrict__ e, const float4 ea,
-                                             const float4 eb, float pixx, float pixy, int q, float& wgt, float& p) {
+__device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4 ea, const float4 eb, const float4 ec,
+                                             const float4 ed, float pixx, float pixy, int q, float& wgt, float& p) {
   const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
   const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
   const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
@@ -586,15 +585,14 @@ __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4* __rest
   const float test_alpha = __fmul_rn(eb.y, expf(power));
   const bool valid = (q < s.last_contributor) && !(power > 0.0f) && !(test_alpha < 1.0f / 255.0f);
   const float alpha = valid ? fminf(0.99f, test_alpha) : 0.f;
-  const float rinv = __fdividef(1.0f, 1.0f - alpha);
+  float rinv;  // 1 - alpha is in [0.01, 1]: the bare MUFU.RCP, without __fdividef's denormal-range scaling (same bits)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(1.0f - alpha));
   const float Tn = s.T * rinv;
   wgt = alpha * Tn;
-  const float4 ec = e[2];
   float g = ec.x * s.w[0] + ec.y * s.w[1] + ec.z * s.w[2];
   if (DEPTH) g += ec.w * s.w[3];
   if (GEO) {
-    const float4 ed = e[3];
-    const float ee = e[4].x;
+    const float ee = eb.z;
     g += ed.x * s.w[4] + ed.y * s.w[5] + ed.z * s.w[6] + ed.w * s.w[7] + ee * s.w[8];
   }
   const float acc_new = s.last_alpha * s.last_g + (1.0f - s.last_alpha) * s.acc_g;
@@ -618,7 +616,6 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   float* __restrict__ accum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BwdMmaSmem& sm = *reinterpret_cast<BwdMmaSmem*>(smem_raw);
-  float4* const s_rec = sm.rec;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -692,12 +689,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
   }
   const int wmax = max(wmaxA, wmaxB);
-  if (lane == 0) sm.s_max[warp] = wmax;
-  __syncthreads();
-  int n_eff = 0;
-#pragma unroll
-  for (int i = 0; i < kWarpsC; ++i) n_eff = max(n_eff, sm.s_max[i]);
-  const int nb = (n_eff + kBatchC - 1) / kBatchC;
+  __syncthreads();  // the B tiles are complete; from here on the warps of the CTA never synchronise with each other
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
   float* const a_w = sm.a_w[warp];
@@ -791,64 +783,71 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     __syncwarp();
   };
 
+  // ---- main loop, per warp and barrier-free.  Each warp walks the tile's list itself, back to front from ITS last
+  // contributor, 32 entries per round: lane j gathers entry j's 64-byte record (register double-buffered, the records
+  // are L2 resident), tests it against the warp's two 8x4 halves from registers, and only the entries that can reach
+  // the sub-tile are parked in the warp's private shared-memory slots for the broadcast reads of the blend loop.  The
+  // four warps of a tile re-read the same records from L2 (4x the gather traffic of a CTA-wide staging, ~1.9 GB per
+  // view, far from the L2 limit) and in exchange never wait for each other: no __syncthreads, no idle tail per batch.
+  float4* const w_rec = sm.rec[warp];
   Prefetch pf;
-  auto prefetch = [&](int b) {
-    const int q = n_eff - 1 - (b * kBatchC + tid);
-    if (tid < kBatchC && q >= 0) gather_record<false>(pf, point_list, records, nullptr, nullptr, range.x + q);
+  auto prefetch = [&](int base) {
+    const int q = base - lane;
+    if (q >= 0) gather_record<false>(pf, point_list, records, nullptr, nullptr, range.x + q);
   };
-  if (nb > 0) prefetch(0);
+  if (wmax > 0) prefetch(wmax - 1);
 
-  for (int b = 0; b < nb; ++b) {
-    __syncthreads();
-    const int cnt = min(kBatchC, n_eff - b * kBatchC);
-    if (tid < cnt) stage_record<GEO, false>(s_rec, tid, pf);
-    __syncthreads();
-    if (b + 1 < nb) prefetch(b + 1);
-
-    const int q_first = n_eff - 1 - b * kBatchC;
-    if (q_first - (cnt - 1) >= wmax) continue;  // the whole batch lies behind this warp
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-      if (q_first - (c0 + 31) >= wmax) continue;
-      const int j = c0 + lane;
-      bool keepA = false, keepB = false;
-      if (j < cnt) {
-        const float4 ea = s_rec[kRecQuads * j];
-        const float4 eb = s_rec[kRecQuads * j + 1];
-        const int q = q_first - j;
-        keepA = q < wmaxA && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyA0, fyA1);
-        keepB = q < wmaxB && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyB0, fyB1);
-      }
-      const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
-      uint32_t mask = maskA | maskB;
-      while (mask) {
-        const int bit = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int k = c0 + bit;
-        const int q = q_first - k;
-        const float4* e = s_rec + kRecQuads * k;
-        const float4 ea = e[0];
-        const float4 eb = e[1];
-        float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f;
-        bool any;
-        const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
-        if (hasA && hasB) {  // one basic block: the two pixels' dependency chains interleave
-          any = pixel_pair_c<GEO, DEPTH>(A, e, ea, eb, pixx, pixyA, q, wA, pA);
-          any |= pixel_pair_c<GEO, DEPTH>(B, e, ea, eb, pixx, pixyB, q, wB, pB);
-        } else if (hasA) {
-          any = pixel_pair_c<GEO, DEPTH>(A, e, ea, eb, pixx, pixyA, q, wA, pA);
-        } else {
-          any = pixel_pair_c<GEO, DEPTH>(B, e, ea, eb, pixx, pixyB, q, wB, pB);
-        }
-        if (__ballot_sync(0xffffffffu, any) == 0) continue;
-        *reinterpret_cast<float2*>(a_w + rows * kAStride + 2 * lane) = make_float2(wA, wB);
-        *reinterpret_cast<float2*>(a_p + rows * kAStride + 2 * lane) = make_float2(pA, pB);
-        if (lane == 0) {
-          sm.meta[warp][rows][0] = ea;
-          sm.meta[warp][rows][1] = eb;
-        }
-        if (++rows == kGroupC) flush();
+  for (int base = wmax - 1; base >= 0; base -= 32) {
+    const int q_mine = base - lane;
+    bool keepA = false, keepB = false;
+    if (q_mine >= 0) {
+      const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
+      const float tau = cull_tau(a, bb, c, o, false);
+      keepA = q_mine < wmaxA && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyA0, fyA1);
+      keepB = q_mine < wmaxB && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyB0, fyB1);
+      if (keepA || keepB) {
+        float4* d = w_rec + kRecQuadsC * lane;
+        d[0] = pf.r0;
+        d[1] = make_float4(c, o, pf.r3.z, __int_as_float(pf.id));
+        d[2] = make_float4(pf.r1.z, pf.r1.w, pf.r2.x, pf.r2.y);
+        if (GEO) d[3] = make_float4(pf.r2.z, pf.r2.w, pf.r3.x, pf.r3.y);
       }
     }
+    const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
+    __syncwarp();
+    if (base >= 32) prefetch(base - 32);
+    uint32_t mask = maskA | maskB;
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int q = base - bit;
+      const float4* e = w_rec + kRecQuadsC * bit;
+      const float4 ea = e[0];
+      const float4 eb = e[1];
+      const float4 ec = e[2];
+      float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (GEO) ed = e[3];
+      float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f;
+      bool any;
+      const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
+      if (hasA && hasB) {  // one basic block: the two pixels' dependency chains interleave
+        any = pixel_pair_c<GEO, DEPTH>(A, ea, eb, ec, ed, pixx, pixyA, q, wA, pA);
+        any |= pixel_pair_c<GEO, DEPTH>(B, ea, eb, ec, ed, pixx, pixyB, q, wB, pB);
+      } else if (hasA) {
+        any = pixel_pair_c<GEO, DEPTH>(A, ea, eb, ec, ed, pixx, pixyA, q, wA, pA);
+      } else {
+        any = pixel_pair_c<GEO, DEPTH>(B, ea, eb, ec, ed, pixx, pixyB, q, wB, pB);
+      }
+      if (__ballot_sync(0xffffffffu, any) == 0) continue;
+      *reinterpret_cast<float2*>(a_w + rows * kAStride + 2 * lane) = make_float2(wA, wB);
+      *reinterpret_cast<float2*>(a_p + rows * kAStride + 2 * lane) = make_float2(pA, pB);
+      if (lane == 0) {
+        sm.meta[warp][rows][0] = ea;
+        sm.meta[warp][rows][1] = eb;
+      }
+      if (++rows == kGroupC) flush();
+    }
+    __syncwarp();  // every lane is done with this round's slots
   }
   if (rows > 0) flush();
 }
