@@ -266,6 +266,11 @@ def run_gpu_arm(args, impl):
     for ev in gt_free:
         ev.record()
 
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_read = [torch.cuda.Event() for _ in range(2)]
+    for ev in loss_read:
+        ev.record()
+
     def step_e2e(s):
         cam = cams[s]
         main = torch.cuda.current_stream()
@@ -301,7 +306,13 @@ def run_gpu_arm(args, impl):
         if ddp:
             pack_and_allreduce((None, None, params["opacity"].grad, params["means3D"].grad, None, params["shs"].grad,
                                 params["scales"].grad, params["rotations"].grad))
-        return float(loss.item())  # D2H read of the step's result
+        # D2H read of the step's result: copied into pinned memory every step; the host consumes it one step later
+        # (as a training loop's logging does), so the copy never drains the launch queue.  Both arms share this harness.
+        slot = s & 1
+        prev = float(loss_host[1 - slot].item()) if loss_read[1 - slot].query() else None
+        loss_host[slot].copy_(loss.detach(), non_blocking=True)
+        loss_read[slot].record(main)
+        return prev
 
     # Untimed warm-up: at least W steps, and enough of them for torch's caching allocator to have
     # seen the step's peak working set (its first steps call cudaMalloc, 10-30 ms each).
@@ -316,7 +327,9 @@ def run_gpu_arm(args, impl):
     for s in range(Wm, Wm + K):
         step_e2e(s)
     e1.record()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize()  # every step's loss has reached the host
+    last_loss = float(loss_host[(Wm + K - 1) & 1].item())
+    assert last_loss == last_loss, "e2e loss is NaN"
     if ddp:
         dist.barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -365,7 +378,8 @@ def run_gpu_arm(args, impl):
                    "l2": "inputs_exceed_l2 (SH 192 MB + records 64 MB + sort buffers > 126 MB)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "d2h": "loss copied to pinned host memory every step (non-blocking), consumed one step later",
                 "api": "GaussianRasterizer(settings)(...) + L1 loss + autograd backward; ground-truth upload on a copy "
                        "stream, overlapped with the forward"},
     }

@@ -484,10 +484,12 @@ blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         const float4 eb = e[1];
         float v[16];
         bool any = false;
-        if ((maskA >> bit) & 1u) {
+        const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
+        if (hasA && hasB) {  // one basic block, so that the two pixels' dependency chains interleave
           any = pixel_pair<GEO, DEPTH, INTERP, true>(A, e, ea, eb, pixx, pixyA, q, ddelx_dx, ddely_dy, v);
-          if ((maskB >> bit) & 1u)
-            any |= pixel_pair<GEO, DEPTH, INTERP, false>(B, e, ea, eb, pixx, pixyB, q, ddelx_dx, ddely_dy, v);
+          any |= pixel_pair<GEO, DEPTH, INTERP, false>(B, e, ea, eb, pixx, pixyB, q, ddelx_dx, ddely_dy, v);
+        } else if (hasA) {
+          any = pixel_pair<GEO, DEPTH, INTERP, true>(A, e, ea, eb, pixx, pixyA, q, ddelx_dx, ddely_dy, v);
         } else {
           any = pixel_pair<GEO, DEPTH, INTERP, true>(B, e, ea, eb, pixx, pixyB, q, ddelx_dx, ddely_dy, v);
         }

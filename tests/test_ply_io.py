@@ -1,0 +1,123 @@
+"""point_cloud.ply / point_cloud.bin against the restated oracle (oracle/ply_oracle.py — parity
+unpinned: plyfile is not installable here) and through round trips."""
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ply_oracle as po
+from hidegs_b200 import ply_io
+
+
+def _model(n, seed=0, degree=3):
+    g = torch.Generator().manual_seed(seed)
+    k = (degree + 1) ** 2
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    return dict(xyz=r(n, 3) * 10, features_dc=r(n, 1, 3), features_rest=r(n, k - 1, 3) * 0.1, opacity=r(n, 1),
+                scaling=r(n, 3) - 3, rotation=r(n, 4))
+
+
+def _np(m):
+    return {k: v.numpy() for k, v in m.items()}
+
+
+@pytest.mark.parametrize("n", [1, 257])
+def test_save_ply_reproduces_the_oracle_bytes(tmp_path, n):
+    m = _model(n)
+    path = str(tmp_path / "pc" / "point_cloud.ply")  # the directory is created, like mkdir_p in the reference
+    ply_io.save_ply(path, **m)
+    assert open(path, "rb").read() == po.file_bytes(**_np(m))
+
+
+@pytest.mark.parametrize("degree", [0, 1, 3])
+def test_load_ply_file_matches_the_reference_reader(tmp_path, degree):
+    m = _model(100, seed=2, degree=degree)
+    path = str(tmp_path / "p.ply")
+    open(path, "wb").write(po.file_bytes(**_np(m)))
+    got, want = ply_io.load_ply_file(path, degree), po.load_ply_file(path, degree)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b)
+    assert got[1].shape == (100, 3, 1) and got[2].shape == (100, 3, (degree + 1) ** 2 - 1) and got[3].shape == (100, 1)
+
+
+def test_reader_accepts_permuted_columns_extra_fields_comments_and_ascii(tmp_path):
+    m = _model(5, seed=3)
+    names = po.attribute_names()
+    raw = po.file_bytes(**_np(m))
+    body = np.frombuffer(raw.split(b"end_header\n", 1)[1], dtype="<f4").reshape(5, len(names))
+    perm = list(reversed(range(len(names))))
+    hdr = "ply\nformat binary_little_endian 1.0\ncomment made by a test\nelement vertex 5\n"
+    hdr += "".join("property float %s\n" % names[i] for i in perm) + "property uchar flag\nelement face 0\nend_header\n"
+    rec = np.zeros(5, dtype=[(names[i], "<f4") for i in perm] + [("flag", "u1")])
+    for i in perm:
+        rec[names[i]] = body[:, i]
+    path = str(tmp_path / "perm.ply")
+    open(path, "wb").write(hdr.encode() + rec.tobytes())
+    ref_path = str(tmp_path / "ref.ply")
+    open(ref_path, "wb").write(raw)
+    for a, b in zip(ply_io.load_ply_file(path, 3), ply_io.load_ply_file(ref_path, 3)):
+        assert np.array_equal(a, b)
+    asc = str(tmp_path / "ascii.ply")
+    with open(asc, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 5\n" + "".join("property float %s\n" % n for n in names) + "end_header\n")
+        for row in body:
+            f.write(" ".join(repr(float(x)) for x in row) + "\n")
+    for a, b in zip(ply_io.load_ply_file(asc, 3), ply_io.load_ply_file(ref_path, 3)):
+        assert np.array_equal(a, b)
+
+
+def test_round_trip_to_model_layout(tmp_path):
+    m = _model(300, seed=4)
+    path = str(tmp_path / "rt.ply")
+    ply_io.save_ply(path, **m)
+    back = ply_io.load_ply(path, degree=3, device="cpu")
+    for got, key in zip(back, ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")):
+        assert got.shape == m[key].shape and torch.equal(got, m[key]), key
+
+
+def test_empty_model(tmp_path):
+    path = str(tmp_path / "empty.ply")
+    ply_io.save_ply(path, **_model(0))
+    out = ply_io.load_ply_file(path, 3)
+    assert [a.shape[0] for a in out] == [0] * 6 and out[2].shape == (0, 3, 15)
+
+
+def test_errors(tmp_path):
+    bad = str(tmp_path / "bad.ply")
+    open(bad, "wb").write(b"not a ply\n")
+    with pytest.raises(ValueError, match="not a PLY"):
+        ply_io.load_ply_file(bad, 3)
+    m = _model(4)
+    raw = po.file_bytes(**_np(m))
+    open(bad, "wb").write(raw[:-10])
+    with pytest.raises(ValueError, match="truncated"):
+        ply_io.load_ply_file(bad, 3)
+    good = str(tmp_path / "good.ply")
+    open(good, "wb").write(raw)
+    with pytest.raises(AssertionError):  # wrong SH degree for this file, as the reference asserts (gaussian_model.py:337)
+        ply_io.load_ply_file(good, 2)
+
+
+def test_point_cloud_bin(tmp_path):
+    m = _model(17, seed=5)
+    path = str(tmp_path / "point_cloud.bin")
+    ply_io.save_point_cloud_bin(path, **m)
+    raw = open(path, "rb").read()
+    assert struct.unpack("i", raw[:4])[0] == 17 and len(raw) == 4 + 17 * 59 * 4
+    f = np.frombuffer(raw[4:], dtype="<f4")
+    assert np.array_equal(f[:51], m["xyz"].numpy().reshape(-1))
+    feats = torch.cat((m["features_dc"], m["features_rest"]), 1).numpy().reshape(-1)
+    assert np.array_equal(f[51:51 + 17 * 48], feats)
+
+
+@pytest.mark.gpu
+def test_ply_from_and_to_the_device(cuda_device, tmp_path):
+    m = _model(5000, seed=6)
+    dev = {k: v.to(cuda_device) for k, v in m.items()}
+    path = str(tmp_path / "dev.ply")
+    ply_io.save_ply(path, **dev)
+    assert open(path, "rb").read() == po.file_bytes(**_np(m))
+    back = ply_io.load_ply(path, degree=3, device=cuda_device)
+    for got, key in zip(back, ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")):
+        assert got.is_cuda and torch.equal(got.cpu(), m[key]), key
