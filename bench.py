@@ -193,6 +193,15 @@ def run_gpu_arm(args, impl):
         exchange = parallel.SymmetricArena(N_GAUSS * 80, dev)   # 80 floats / Gaussian: the whole backward arena
         C.set_gradient_arena_provider(lambda n, d: exchange.tensor if n <= exchange.numel else None)
 
+    # Opt-in (HG_EXCHANGE_OVERLAP=1): overlapped with the per-Gaussian backward — preprocess_bwd is issued in slot
+    # ranges and each range's five parameter blocks travel (one in-fabric kernel on a side stream) while the next range
+    # is computed.  Measured on 2 B200 (tools/overlap_probe.py): 2.85 ms vs 2.86 ms plain with 2 ranges, slower with
+    # 4 and 8 (two cross-rank barriers per range cost what the 0.17 ms kernel could hide), so it is off by default.
+    overlap = None
+    if exchange is not None and os.environ.get("HG_EXCHANGE_OVERLAP", "0") == "1":
+        overlap = parallel.OverlappedBackwardExchange(exchange, N_GAUSS, 16,
+                                                      n_chunks=int(os.environ.get("HG_EXCHANGE_CHUNKS", 2)))
+
     def pack_and_allreduce(grads):
         # (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map)
         # xyz 3 | sh 48 | opacity 1 | scale 3 | rot 4 = 59 floats per Gaussian, contiguous in the backward's arena
@@ -206,9 +215,14 @@ def run_gpu_arm(args, impl):
         cam = cams[s]
         fa = op_tuple(C, scene, cam, all_maps[0], dev, bg)
         fwd = C.rasterize_gaussians(*fa)
-        grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
-        if ddp:
-            pack_and_allreduce(grads)
+        if overlap is not None:
+            with overlap:
+                grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
+            overlap.finish()
+        else:
+            grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
+            if ddp:
+                pack_and_allreduce(grads)
         return fwd
 
     for c in cams:
@@ -373,8 +387,11 @@ def run_gpu_arm(args, impl):
                                "REDUCED %d Gaussians %dx%d" % (N_GAUSS, WIDTH, HEIGHT),
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "visible": Nv, "num_rendered": R,
                    "outputs": "color+all_map+plane_depth+invdepth", "parallelism": "view-sharded dp%d" % world,
-                   "exchange": (None if not ddp else "nvls multimem kernel (hg_nvls_allreduce_f32), 236 MB arena"
-                                if exchange is not None else "nccl all_reduce, 236 MB arena"),
+                   "exchange": (None if not ddp else
+                                ("nvls multimem kernel, 236 MB arena, overlapped with preprocess_bwd in %d slot ranges"
+                                 % overlap.n_chunks) if overlap is not None else
+                                "nvls multimem kernel (hg_nvls_allreduce_f32), 236 MB arena" if exchange is not None
+                                else "nccl all_reduce, 236 MB arena"),
                    "l2": "inputs_exceed_l2 (SH 192 MB + records 64 MB + sort buffers > 126 MB)"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),

@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libhidegs_b200.so")
 
 c_float_p = ctypes.c_void_p  # raw device pointers travel as integers
 ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+# hg_chunk_fn(chunk_ctx, chunk, slot_begin, slot_end, stream)
+CHUNK_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p)
 
 
 class RasterInputs(ctypes.Structure):
@@ -43,6 +45,7 @@ class RasterLayout(ctypes.Structure):
 # Every symbol include/hidegs_raster.h declares (checked by the CPU test-suite).
 EXPORTED_SYMBOLS = (
     "hg_raster_layout_query", "hg_raster_forward", "hg_raster_backward_accum_bytes", "hg_raster_backward",
+    "hg_raster_backward_chunked",
     "hg_mark_visible", "hg_raster_debug_keys", "hg_launch_count", "hg_reset_launch_count", "hg_last_error", "hg_version",
     "hg_profile_enable", "hg_profile_collect",
 )
@@ -73,6 +76,8 @@ def lib():
     L.hg_raster_backward.argtypes = [ctypes.POINTER(RasterInputs), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hg_raster_backward.restype = ctypes.c_int
+    L.hg_raster_backward_chunked.argtypes = L.hg_raster_backward.argtypes[:-1] + [i32, CHUNK_FN, vp, vp]
+    L.hg_raster_backward_chunked.restype = ctypes.c_int
     L.hg_raster_debug_keys.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.hg_raster_debug_keys.restype = ctypes.c_int
     L.hg_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]

@@ -19,7 +19,7 @@ constexpr int kExThreads = 512;
 #ifndef HG_NVLS_UNROLL
 #define HG_NVLS_UNROLL 4
 #endif
-constexpr int kExDefaultBlocks = 148 * 2;
+constexpr int kExDefaultBlocks = 32;  // measured on 8 B200: 16..48 CTAs x 512 threads saturate the NVLS path, more only add barrier traffic
 
 __device__ __forceinline__ float4 mc_ld_reduce(const float4* p) {
   float4 v;
@@ -61,12 +61,16 @@ __device__ __forceinline__ void rank_barrier(const uint64_t* __restrict__ flag_p
   __syncthreads();
 }
 
-template <int kExUnroll>
-__global__ void __launch_bounds__(kExThreads)
-nvls_allreduce_kernel(float4* __restrict__ mc, const uint64_t* __restrict__ flag_ptrs, const int rank, const int world,
-                      const int64_t n4, const int tail) {
-  rank_barrier(flag_ptrs, rank, world);  // every replica of the arena is complete
+constexpr int kExMaxRanges = 8;
+struct ExRanges {  // in float4 units relative to the multicast base
+  int64_t off4[kExMaxRanges];
+  int64_t n4[kExMaxRanges];
+  int n;
+};
 
+// This rank's 1/world share of one contiguous range.
+template <int kExUnroll>
+__device__ __forceinline__ void reduce_share(float4* __restrict__ mc, const int64_t n4, const int rank, const int world) {
   const int64_t per = (n4 + world - 1) / world;
   const int64_t begin = per * rank;
   const int64_t end = begin + per < n4 ? begin + per : n4;
@@ -80,8 +84,16 @@ nvls_allreduce_kernel(float4* __restrict__ mc, const uint64_t* __restrict__ flag
     for (int u = 0; u < kExUnroll; ++u) mc_st(mc + i + u * stride, v[u]);
   }
   for (; i < end; i += stride) mc_st(mc + i, mc_ld_reduce(mc + i));
-  if (rank == 0 && blockIdx.x == 0 && (int)threadIdx.x < tail) {
-    float* p = reinterpret_cast<float*>(mc + n4) + threadIdx.x;
+}
+
+template <int kExUnroll>
+__global__ void __launch_bounds__(kExThreads)
+nvls_allreduce_kernel(float4* __restrict__ mc, const uint64_t* __restrict__ flag_ptrs, const int rank, const int world,
+                      const ExRanges ranges, const int tail) {
+  rank_barrier(flag_ptrs, rank, world);  // every replica of the ranges is complete
+  for (int r = 0; r < ranges.n; ++r) reduce_share<kExUnroll>(mc + ranges.off4[r], ranges.n4[r], rank, world);
+  if (tail && rank == 0 && blockIdx.x == 0 && (int)threadIdx.x < tail) {  // (single-range call with n % 4 floats left over)
+    float* p = reinterpret_cast<float*>(mc + ranges.off4[0] + ranges.n4[0]) + threadIdx.x;
     mc_st1(p, mc_ld_reduce1(p));
   }
   __threadfence_system();
@@ -98,26 +110,8 @@ size_t hg_nvls_flag_words(int32_t world, int32_t max_blocks) {
   return (size_t)world * (size_t)max_blocks;
 }
 
-int hg_nvls_allreduce_f32(void* mc_ptr, float* local_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
-                          int64_t n_floats, int32_t blocks, void* stream) {
-  if (world < 1 || rank < 0 || rank >= world || n_floats < 0 || blocks < 0) {
-    hg::set_error("hg_nvls_allreduce_f32: bad argument (rank %d, world %d, n %lld, blocks %d)", rank, world,
-                  (long long)n_floats, blocks);
-    return HG_ERR_INVALID_ARG;
-  }
-  if (world == 1 || n_floats == 0) return HG_OK;
-  if (!mc_ptr || !local_ptr || !flag_ptrs) {
-    hg::set_error("hg_nvls_allreduce_f32: multicast pointer, local pointer and flag table are mandatory");
-    return HG_ERR_INVALID_ARG;
-  }
-  if (((uintptr_t)mc_ptr | (uintptr_t)local_ptr) & 15) {
-    hg::set_error("hg_nvls_allreduce_f32: the arena must be 16-byte aligned");
-    return HG_ERR_INVALID_ARG;
-  }
-  if (world > hg::kExThreads) {
-    hg::set_error("hg_nvls_allreduce_f32: world %d too large", world);
-    return HG_ERR_INVALID_ARG;
-  }
+static int launch_exchange(void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
+                           const hg::ExRanges& ranges, int tail, int32_t blocks, void* stream) {
   const int grid = blocks ? blocks : hg::kExDefaultBlocks;
   static const int unroll = [] {
     const char* e = getenv("HG_NVLS_UNROLL");
@@ -125,7 +119,7 @@ int hg_nvls_allreduce_f32(void* mc_ptr, float* local_ptr, const uint64_t* flag_p
   }();
 #define HG_EX_LAUNCH(U_)                                                                  \
   hg::nvls_allreduce_kernel<U_><<<grid, hg::kExThreads, 0, (cudaStream_t)stream>>>(       \
-      (float4*)mc_ptr, flag_ptrs, rank, world, n_floats / 4, (int)(n_floats % 4))
+      (float4*)mc_ptr, flag_ptrs, rank, world, ranges, tail)
   if (unroll >= 8) HG_EX_LAUNCH(8);
   else if (unroll >= 4) HG_EX_LAUNCH(4);
   else if (unroll >= 2) HG_EX_LAUNCH(2);
@@ -133,6 +127,73 @@ int hg_nvls_allreduce_f32(void* mc_ptr, float* local_ptr, const uint64_t* flag_p
 #undef HG_EX_LAUNCH
   HG_POST_LAUNCH(false, (cudaStream_t)stream, "nvls_allreduce");
   return HG_OK;
+}
+
+static int check_exchange_args(const char* who, void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
+                               int32_t blocks) {
+  if (world < 1 || rank < 0 || rank >= world || blocks < 0 || world > hg::kExThreads) {
+    hg::set_error("%s: bad argument (rank %d, world %d, blocks %d)", who, rank, world, blocks);
+    return HG_ERR_INVALID_ARG;
+  }
+  if (world > 1 && (!mc_ptr || !flag_ptrs)) {
+    hg::set_error("%s: multicast pointer and flag table are mandatory", who);
+    return HG_ERR_INVALID_ARG;
+  }
+  if ((uintptr_t)mc_ptr & 15) {
+    hg::set_error("%s: the arena must be 16-byte aligned", who);
+    return HG_ERR_INVALID_ARG;
+  }
+  return HG_OK;
+}
+
+int hg_nvls_allreduce_f32(void* mc_ptr, float* local_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
+                          int64_t n_floats, int32_t blocks, void* stream) {
+  if (n_floats < 0) {
+    hg::set_error("hg_nvls_allreduce_f32: bad argument (n %lld)", (long long)n_floats);
+    return HG_ERR_INVALID_ARG;
+  }
+  if (world == 1 && rank == 0) return HG_OK;
+  if (world > 1 && n_floats > 0 && !local_ptr) {
+    hg::set_error("hg_nvls_allreduce_f32: multicast pointer, local pointer and flag table are mandatory");
+    return HG_ERR_INVALID_ARG;
+  }
+  if ((uintptr_t)local_ptr & 15) {
+    hg::set_error("hg_nvls_allreduce_f32: the arena must be 16-byte aligned");
+    return HG_ERR_INVALID_ARG;
+  }
+  const int rc = check_exchange_args("hg_nvls_allreduce_f32", mc_ptr, flag_ptrs, rank, world, blocks);
+  if (rc) return rc;
+  if (n_floats == 0) return HG_OK;
+  hg::ExRanges r{};
+  r.n = 1;
+  r.off4[0] = 0;
+  r.n4[0] = n_floats / 4;
+  return launch_exchange(mc_ptr, flag_ptrs, rank, world, r, (int)(n_floats % 4), blocks, stream);
+}
+
+int hg_nvls_allreduce_ranges_f32(void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world, int32_t n_ranges,
+                                 const int64_t* offsets, const int64_t* counts, int32_t blocks, void* stream) {
+  if (n_ranges < 0 || n_ranges > hg::kExMaxRanges || (n_ranges && (!offsets || !counts))) {
+    hg::set_error("hg_nvls_allreduce_ranges_f32: bad argument (%d ranges, at most %d)", n_ranges, hg::kExMaxRanges);
+    return HG_ERR_INVALID_ARG;
+  }
+  if (world == 1 && rank == 0) return HG_OK;
+  const int rc = check_exchange_args("hg_nvls_allreduce_ranges_f32", mc_ptr, flag_ptrs, rank, world, blocks);
+  if (rc) return rc;
+  hg::ExRanges r{};
+  for (int i = 0; i < n_ranges; ++i) {
+    if (offsets[i] < 0 || counts[i] < 0 || (offsets[i] & 3) || (counts[i] & 3)) {
+      hg::set_error("hg_nvls_allreduce_ranges_f32: range %d (offset %lld, count %lld) must be multiples of 4 floats", i,
+                    (long long)offsets[i], (long long)counts[i]);
+      return HG_ERR_INVALID_ARG;
+    }
+    if (counts[i] == 0) continue;
+    r.off4[r.n] = offsets[i] / 4;
+    r.n4[r.n] = counts[i] / 4;
+    ++r.n;
+  }
+  if (r.n == 0) return HG_OK;
+  return launch_exchange(mc_ptr, flag_ptrs, rank, world, r, 0, blocks, stream);
 }
 
 }  // extern "C"

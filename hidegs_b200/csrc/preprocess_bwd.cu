@@ -39,7 +39,7 @@ __device__ __forceinline__ void store_or_add3(float* dst, float a, float b, floa
 }
 
 __global__ void __launch_bounds__(kThreads)
-preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restrict__ indices,
+preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, const int* __restrict__ indices,
                       const int* __restrict__ parent_indices, const float* __restrict__ ts,
                       const float* __restrict__ means3D, const int* __restrict__ radii,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
@@ -60,7 +60,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   // per-warp shared-memory tile with coalesced 128-bit accesses when the warp's rows are contiguous (no index
   // remap); each thread then works on its own row of the tile.
   __shared__ float s_sh[kWarps][32 * kShStrideMax];
-  const int t_idx = blockIdx.x * kThreads + threadIdx.x;
+  const int t_idx = (blockIdx.x + block0) * kThreads + threadIdx.x;  // block0: first block of this chunk
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_range = t_idx < P;
   const int row = 3 * M;
@@ -69,7 +69,7 @@ preprocess_bwd_kernel(const int P, const int D, const int M, const int* __restri
   const bool staged = shs != nullptr && indices == nullptr && (row & 3) == 0 &&
                       ((reinterpret_cast<uintptr_t>(shs) | reinterpret_cast<uintptr_t>(dL_dsh)) & 15) == 0;
   float* const tile = s_sh[warp];
-  const size_t warp_base = (size_t)(blockIdx.x * kThreads + warp * 32) * row;
+  const size_t warp_base = (size_t)((blockIdx.x + block0) * kThreads + warp * 32) * row;
   const size_t sh_total = (size_t)P * row;
   // The thread's own rows are requested BEFORE the cooperative SH staging so that both are in flight together.
   float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
@@ -422,11 +422,18 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
                           float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity,
                           float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                           float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
-                          float* dL_drotations, float* dL_dall_map, cudaStream_t stream) {
+                          float* dL_drotations, float* dL_dall_map, cudaStream_t stream, int slot_begin,
+                          int slot_end) {
   const bool prezeroed = in.indices != nullptr || in.parent_indices != nullptr;
   const float* cov = in.cov3D_precomp ? in.cov3D_precomp : g.cov3D;
-  preprocess_bwd_kernel<<<(in.P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
-      in.P, in.D, in.M, in.indices, in.parent_indices, in.ts, in.means3D, radii, in.shs, g.clamped,
+  // [slot_begin, slot_end): the slots this launch covers (slot_begin a multiple of the block size; -1 = to the end)
+  if (slot_end < 0 || slot_end > in.P) slot_end = in.P;
+  if (slot_begin % kThreads != 0 || slot_begin >= slot_end) {
+    set_error("preprocess_bwd: bad slot range [%d, %d)", slot_begin, slot_end);
+    return HG_ERR_INVALID_ARG;
+  }
+  preprocess_bwd_kernel<<<(slot_end - slot_begin + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
+      slot_end, slot_begin / kThreads, in.D, in.M, in.indices, in.parent_indices, in.ts, in.means3D, radii, in.shs, g.clamped,
       in.opacities, in.scales, in.rotations, in.scale_modifier, cov, in.cov3D_precomp != nullptr,
       in.viewmatrix, in.projmatrix, in.campos, focal_x, focal_y, in.tan_fovx, in.tan_fovy, accum,
       has_invdepth, prezeroed, dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
@@ -434,5 +441,7 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
   HG_POST_LAUNCH(in.debug, stream, "preprocess_bwd");
   return HG_OK;
 }
+
+int preprocess_bwd_block_slots() { return kThreads; }
 
 }  // namespace hg

@@ -272,6 +272,22 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
                        float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                        float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
                        float* dL_dall_map, void* stream_) {
+  return hg_raster_backward_chunked(in, R, radii, geom_buffer, binning_buffer, image_buffer, all_map_pixels, dL_dpix,
+                                    dL_dout_all_map, dL_dout_plane_depth, dL_dout_invdepth, accum, dL_dmeans2D, dL_dconic,
+                                    dL_dopacity, dL_dcolors, dL_dinvdepths, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+                                    dL_drotations, dL_dall_map, 1, nullptr, nullptr, stream_);
+}
+
+int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int32_t* radii,
+                               const char* geom_buffer, const char* binning_buffer,
+                               const char* image_buffer, const float* all_map_pixels,
+                               const float* dL_dpix, const float* dL_dout_all_map,
+                               const float* dL_dout_plane_depth, const float* dL_dout_invdepth,
+                               char* accum, float* dL_dmeans2D, float* dL_dconic, float* dL_dopacity,
+                               float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
+                               float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                               float* dL_dall_map, int32_t n_chunks, hg_chunk_fn on_chunk, void* chunk_ctx,
+                               void* stream_) {
   g_err[0] = 0;
   int rc = validate(in);
   if (rc) return rc;
@@ -308,10 +324,24 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
     if (rc) return rc;
   }
   StageTimer t(HG_STAGE_PREPROCESS_BWD, stream);
-  return launch_preprocess_bwd(*in, g, radii, focal_x, focal_y, acc, dL_dout_invdepth != nullptr,
+  // The per-Gaussian backward in slot ranges: once the kernel of a range completes, the rows of those Gaussians are
+  // final in EVERY gradient array, and the caller's hook may start shipping them (gradient exchange of view-sharded
+  // training, include/hidegs_exchange.h) while the next range is still being computed.  An index remap scatters the
+  // rows, so it keeps one range.
+  if (n_chunks < 1 || in->indices || in->parent_indices) n_chunks = 1;
+  const int unit = preprocess_bwd_block_slots();
+  const int per = (int)align_up((size_t)(in->P + n_chunks - 1) / n_chunks, (size_t)unit);
+  int chunk = 0;
+  for (int p0 = 0; p0 < in->P; p0 += per, ++chunk) {
+    const int p1 = p0 + per < in->P ? p0 + per : in->P;
+    rc = launch_preprocess_bwd(*in, g, radii, focal_x, focal_y, acc, dL_dout_invdepth != nullptr,
                                dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
                                dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
-                               dL_dall_map, stream);
+                               dL_dall_map, stream, p0, p1);
+    if (rc) return rc;
+    if (on_chunk) on_chunk(chunk_ctx, chunk, p0, p1, stream_);
+  }
+  return HG_OK;
 }
 
 int hg_raster_debug_keys(int32_t P, int32_t W, int32_t H, int32_t R, const int32_t* radii, const char* geom_buffer,

@@ -188,6 +188,19 @@ def set_gradient_arena_provider(fn):
     _gradient_arena_provider = fn
 
 
+_backward_chunk_hook = None
+
+
+def set_backward_chunk_hook(n_chunks=0, fn=None):
+    """Opt-in: issue the per-Gaussian part of the next backward calls in `n_chunks` slot ranges and call
+    `fn(chunk, slot_begin, slot_end)` right after each range's kernel has been queued on the current stream
+    (hg_raster_backward_chunked).  Rows slot_begin..slot_end-1 of every gradient are final once that kernel completes:
+    the view-sharded data-parallel path starts the gradient exchange of those rows from the hook, on a side stream.
+    `set_backward_chunk_hook()` removes the hook."""
+    global _backward_chunk_hook
+    _backward_chunk_hook = (int(n_chunks), fn) if fn is not None and n_chunks > 0 else None
+
+
 def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_indices, ts, kids, means3D, radii,
                                  colors, all_maps, opacities, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_all_map,
@@ -244,13 +257,27 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
             s = _inputs(P, fullP, degree, M, W, H, tan_fovx, tan_fovy, scale_modifier, False, render_geo, debug,
                         background, viewmatrix, projmatrix, campos, indices, parent_indices, ts, kids, means3D,
                         sh, colors, all_maps, opacities, scales, rotations, cov3D_precomp)
-            rc = _lib.lib().hg_raster_backward(
-                ctypes.byref(s), int(R), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
-                _ptr(all_map_pixels), _ptr(dL_dout_color), _ptr(dL_dout_all_map), _ptr(dL_dout_plane_depth),
-                _ptr(dL_dout_invdepth) if has_depth_grad else None, accum_ptr,
-                _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
-                _ptr(dL_dinvdepths) if has_depth_grad else None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
-                _ptr(dL_dscales), _ptr(dL_drotations), _ptr(dL_dall_map), stream)
+            args = (ctypes.byref(s), int(R), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer),
+                    _ptr(all_map_pixels), _ptr(dL_dout_color), _ptr(dL_dout_all_map), _ptr(dL_dout_plane_depth),
+                    _ptr(dL_dout_invdepth) if has_depth_grad else None, accum_ptr,
+                    _ptr(dL_dmeans2D), None, _ptr(dL_dopacity), _ptr(dL_dcolors),
+                    _ptr(dL_dinvdepths) if has_depth_grad else None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
+                    _ptr(dL_dscales), _ptr(dL_drotations), _ptr(dL_dall_map))
+            hook = _backward_chunk_hook
+            if hook is not None and not prezero:
+                failure = []
+
+                def _on_chunk(_ctx, chunk, p0, p1, _stream, fn=hook[1]):
+                    try:
+                        fn(chunk, p0, p1)
+                    except BaseException as e:  # noqa: BLE001 — must not unwind through the C frame
+                        failure.append(e)
+                cb = _lib.CHUNK_FN(_on_chunk)
+                rc = _lib.lib().hg_raster_backward_chunked(*args, hook[0], cb, None, stream)
+                if failure:
+                    raise failure[0]
+            else:
+                rc = _lib.lib().hg_raster_backward(*args, stream)
         _lib.check(rc, "rasterize_gaussians_backward")
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
             dL_dall_map)

@@ -13,7 +13,7 @@ import os
 import torch
 import torch.distributed as dist
 
-EXCHANGE_SYMBOLS = ("hg_nvls_flag_words", "hg_nvls_allreduce_f32")  # include/hidegs_exchange.h
+EXCHANGE_SYMBOLS = ("hg_nvls_flag_words", "hg_nvls_allreduce_f32", "hg_nvls_allreduce_ranges_f32")  # include/hidegs_exchange.h
 _MAX_BLOCKS = 1024
 
 
@@ -77,6 +77,10 @@ def _exchange_lib():
         L.hg_nvls_allreduce_f32.restype = ctypes.c_int
         L.hg_nvls_allreduce_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                             ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]
+        L.hg_nvls_allreduce_ranges_f32.restype = ctypes.c_int
+        L.hg_nvls_allreduce_ranges_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                   ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                                   ctypes.c_void_p]
         L._hg_exchange_ready = True
     return L
 
@@ -140,6 +144,66 @@ class SymmetricArena:
         _lib.check(L.hg_nvls_allreduce_f32(self._mc, self._buf.data_ptr(), self._flag_ptrs.data_ptr(), self.rank,
                                            self.world, n, self.blocks, stream), "hg_nvls_allreduce_f32")
         return n * 4
+
+    def all_reduce_ranges_(self, offsets, counts):
+        """Sum up to 8 disjoint ranges (offsets / counts in floats, multiples of 4) over the ranks with one kernel on
+        the current stream (hg_nvls_allreduce_ranges_f32)."""
+        L = _exchange_lib()
+        from . import _lib
+        n = len(offsets)
+        off = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
+        cnt = (ctypes.c_int64 * n)(*[int(c) for c in counts])
+        stream = torch.cuda.current_stream(self._buf.device).cuda_stream
+        _lib.check(L.hg_nvls_allreduce_ranges_f32(self._mc, self._flag_ptrs.data_ptr(), self.rank, self.world, n, off, cnt,
+                                                  self.blocks, stream), "hg_nvls_allreduce_ranges_f32")
+        return 4 * sum(int(c) for c in counts)
+
+
+class OverlappedBackwardExchange:
+    """Gradient exchange overlapped with the per-Gaussian backward: the rasterizer backward writes into a
+    SymmetricArena (gradient arena provider) and issues its last kernel in `n_chunks` slot ranges; as soon as a range is
+    queued, its five parameter blocks (xyz 3 | sh 3M | opacity 1 | scale 3 | rotation 4 floats per Gaussian, SoA) are
+    summed over the ranks by ONE in-fabric kernel on a side stream while the next range is computed.
+    `finish()` makes the current stream wait for the last range.  Use as a context around the backward calls."""
+
+    def __init__(self, arena, n_gaussians, sh_coeffs=16, n_chunks=4):
+        self.arena, self.N, self.n_chunks = arena, int(n_gaussians), int(n_chunks)
+        self.widths = (3, 3 * sh_coeffs, 1, 3, 4)
+        self.stream = torch.cuda.Stream(device=arena._buf.device)
+        self._events = [torch.cuda.Event() for _ in range(2 * max(self.n_chunks, 1))]
+        self._k = 0
+        self.bytes = 0
+
+    def _on_chunk(self, chunk, p0, p1):
+        main = torch.cuda.current_stream(self.arena._buf.device)
+        ev = self._events[self._k % len(self._events)]
+        self._k += 1
+        ev.record(main)
+        self.stream.wait_event(ev)
+        offs, cnts, base = [], [], 0
+        for w in self.widths:
+            offs.append(base + w * p0)
+            cnts.append(w * (p1 - p0))
+            base += w * self.N
+        with torch.cuda.stream(self.stream):
+            self.bytes += self.arena.all_reduce_ranges_(offs, cnts)
+
+    def __enter__(self):
+        from .diff_gaussian_rasterization import _C
+        arena = self.arena
+        self._saved = (_C._gradient_arena_provider, _C._backward_chunk_hook)
+        _C.set_gradient_arena_provider(lambda n, d: arena.tensor if n <= arena.numel else None)
+        _C.set_backward_chunk_hook(self.n_chunks, self._on_chunk)
+        return self
+
+    def __exit__(self, *exc):
+        from .diff_gaussian_rasterization import _C
+        _C._gradient_arena_provider, _C._backward_chunk_hook = self._saved
+        return False
+
+    def finish(self):
+        """The current stream waits until every range of the last backward has been exchanged."""
+        torch.cuda.current_stream(self.arena._buf.device).wait_stream(self.stream)
 
 
 def make_exchange_arena(numel, device, group=None):

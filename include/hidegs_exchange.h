@@ -42,6 +42,15 @@ HG_API size_t hg_nvls_flag_words(int32_t world, int32_t max_blocks);
 HG_API int hg_nvls_allreduce_f32(void *mc_ptr, float *local_ptr, const uint64_t *flag_ptrs, int32_t rank,
                                  int32_t world, int64_t n_floats, int32_t blocks, void *stream);
 
+/* The same exchange over up to 8 disjoint ranges of the arena in ONE kernel (offsets / counts in floats relative to
+ * mc_ptr, multiples of 4; HOST arrays, read before the call returns).  This is the call a chunk hook of
+ * hg_raster_backward_chunked issues on a side stream: a slot range of the per-Gaussian backward is final in the five
+ * parameter blocks of the SoA arena (xyz | sh | opacity | scale | rotation), i.e. five ranges, and travels while the
+ * next slot range is still being computed. */
+HG_API int hg_nvls_allreduce_ranges_f32(void *mc_ptr, const uint64_t *flag_ptrs, int32_t rank, int32_t world,
+                                        int32_t n_ranges, const int64_t *offsets, const int64_t *counts, int32_t blocks,
+                                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

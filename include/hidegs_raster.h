@@ -183,6 +183,37 @@ HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
                        float *dL_dall_map,   /* [N,5] */
                        void *stream);
 
+/* hg_raster_backward with the per-Gaussian part (backward.cu:147-326, 398-496) issued in `n_chunks` slot ranges.
+ * Right after the kernel of slots [slot_begin, slot_end) has been QUEUED on `stream`, `on_chunk(chunk_ctx, chunk,
+ * slot_begin, slot_end, stream)` is called on the host: once that kernel completes, rows slot_begin..slot_end-1 of
+ * every gradient array are final, so the hook can record an event and start the gradient exchange of those rows on
+ * another stream (include/hidegs_exchange.h) while the remaining ranges are computed.  Range boundaries are multiples
+ * of 128 slots.  With render indices / parent indices (scattered rows) a single range is used. */
+typedef void (*hg_chunk_fn)(void *chunk_ctx, int32_t chunk, int32_t slot_begin, int32_t slot_end, void *stream);
+HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
+                       const int32_t *radii,
+                       const char *geom_buffer, const char *binning_buffer,
+                       const char *image_buffer,
+                       const float *all_map_pixels,     /* [5,H,W]        */
+                       const float *dL_dpix,            /* [3,H,W]        */
+                       const float *dL_dout_all_map,    /* [5,H,W]        */
+                       const float *dL_dout_plane_depth,/* [1,H,W]        */
+                       const float *dL_dout_invdepth,   /* [1,H,W] or NULL*/
+                       char *accum,
+                       float *dL_dmeans2D,   /* [N,3] */
+                       float *dL_dconic,     /* [N,2,2] or NULL */
+                       float *dL_dopacity,   /* [N,1] */
+                       float *dL_dcolors,    /* [N,3] */
+                       float *dL_dinvdepths, /* [N,1] or NULL */
+                       float *dL_dmeans3D,   /* [N,3] */
+                       float *dL_dcov3D,     /* [N,6] */
+                       float *dL_dsh,        /* [N,M,3] (may be NULL when shs is) */
+                       float *dL_dscales,    /* [N,3] */
+                       float *dL_drotations, /* [N,4] */
+                       float *dL_dall_map,   /* [N,5] */
+                       int32_t n_chunks, hg_chunk_fn on_chunk,
+                                       void *chunk_ctx, void *stream);
+
 /* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it sorts the
  * visible splats by depth once (32-bit keys, P elements), emits the tile instances in that order and then sorts
  * them stably by tile id alone (getHigherMsb(tiles) bits) -- same final order as the reference's 45..47-bit sort,
