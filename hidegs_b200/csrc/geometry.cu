@@ -566,7 +566,7 @@ int hg_activate_params_backward(const float* raw_scaling, const float* raw_rotat
                                                                      g_opacity, g_scaling, g_rotation, beta, d_xyz,
                                                                      d_opacity, d_scaling, d_rotation);
   HG_POST_LAUNCH(false, st, "activate_params_bwd");
-  if (F > 0) {
+  if (F > 0 && g_features) {  // NULL: the feature gradient already sits in d_features (rasterizer SH sink)
     axpby4_kernel<<<148 * 8, 256, 0, st>>>((const float4*)g_features, N * (int64_t)F / 4, beta, (float4*)d_features);
     HG_POST_LAUNCH(false, st, "features_grad_accumulate");
   }

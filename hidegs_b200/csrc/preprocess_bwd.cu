@@ -55,7 +55,8 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
                       float* __restrict__ dL_dcolors, float* __restrict__ dL_dinvdepths,
                       float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D,
                       float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
-                      float* __restrict__ dL_drotations, float* __restrict__ dL_dall_map) {
+                      float* __restrict__ dL_drotations, float* __restrict__ dL_dall_map,
+                      float* __restrict__ sh_sink, const float sh_beta) {
   // SH rows (read AND written, 2 x 192 B per Gaussian at degree 3: 60 % of this kernel's traffic) move through a
   // per-warp shared-memory tile with coalesced 128-bit accesses when the warp's rows are contiguous (no index
   // remap); each thread then works on its own row of the tile.
@@ -409,7 +410,12 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
     dL_drotations[4 * g + 3] = dqz;
   }
   } while (0);
-  if (staged && (alive_mask || !prezeroed)) {
+  if (staged && sh_sink) {  // accumulate straight into the caller's gradient arena (launcher guarantees `staged`)
+    if (alive_mask || sh_beta == 0.f) {
+      __syncwarp();
+      unstage_sh_rows_accum(sh_sink, warp_base, sh_total, row, lane, tile, alive_mask, sh_beta);
+    }
+  } else if (staged && (alive_mask || !prezeroed)) {
     __syncwarp();
     unstage_sh_rows(dL_dsh, warp_base, sh_total, row, lane, tile, alive_mask, !prezeroed);
   }
@@ -423,11 +429,19 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
                           float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                           float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
                           float* dL_drotations, float* dL_dall_map, cudaStream_t stream, int slot_begin,
-                          int slot_end) {
+                          int slot_end, float* sh_sink, float sh_beta) {
   const bool prezeroed = in.indices != nullptr || in.parent_indices != nullptr;
   const float* cov = in.cov3D_precomp ? in.cov3D_precomp : g.cov3D;
   // [slot_begin, slot_end): the slots this launch covers (slot_begin a multiple of the block size; -1 = to the end)
   if (slot_end < 0 || slot_end > in.P) slot_end = in.P;
+  if (sh_sink) {  // the sink is written by the staged (coalesced, contiguous-rows) path only
+    const int row = 3 * in.M;
+    if (!in.shs || in.indices || in.parent_indices || (row & 3) ||
+        ((reinterpret_cast<uintptr_t>(in.shs) | reinterpret_cast<uintptr_t>(dL_dsh) | reinterpret_cast<uintptr_t>(sh_sink)) & 15)) {
+      set_error("preprocess_bwd: an SH gradient sink needs SH input, no index remap, 3*M %% 4 == 0 and 16-byte aligned arrays");
+      return HG_ERR_INVALID_ARG;
+    }
+  }
   if (slot_begin % kThreads != 0 || slot_begin >= slot_end) {
     set_error("preprocess_bwd: bad slot range [%d, %d)", slot_begin, slot_end);
     return HG_ERR_INVALID_ARG;
@@ -437,7 +451,7 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
       in.opacities, in.scales, in.rotations, in.scale_modifier, cov, in.cov3D_precomp != nullptr,
       in.viewmatrix, in.projmatrix, in.campos, focal_x, focal_y, in.tan_fovx, in.tan_fovy, accum,
       has_invdepth, prezeroed, dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
-      dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map);
+      dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map, sh_sink, sh_beta);
   HG_POST_LAUNCH(in.debug, stream, "preprocess_bwd");
   return HG_OK;
 }

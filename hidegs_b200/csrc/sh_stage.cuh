@@ -73,4 +73,33 @@ __device__ __forceinline__ void unstage_sh_rows(float* __restrict__ dst, size_t 
   }
 }
 
+// Accumulating variant for a caller-owned gradient sink: live rows do dst = beta * dst + row (beta = 0: plain store,
+// dst is not read); rows whose bit is clear are zero-filled when beta == 0 and NOT TOUCHED otherwise — a culled
+// Gaussian costs no traffic in any view but the first of a step.
+__device__ __forceinline__ void unstage_sh_rows_accum(float* __restrict__ dst, size_t base, size_t total, int row, int lane,
+                                                      const float* src, uint32_t row_mask, float beta) {
+  const int stride = row | 1;
+  const int nfloat = 32 * row;
+  for (int i = lane * 4; i < nfloat; i += 128) {
+    const size_t gi = base + i;
+    if (gi >= total) break;
+    const int r = i / row, c = i - r * row;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((row_mask >> r) & 1u) {
+      const float* s = src + r * stride + c;
+      val = make_float4(s[0], s[1], s[2], s[3]);
+      if (beta != 0.f) {
+        const float4 old = *reinterpret_cast<const float4*>(dst + gi);
+        val.x = fmaf(beta, old.x, val.x);
+        val.y = fmaf(beta, old.y, val.y);
+        val.z = fmaf(beta, old.z, val.z);
+        val.w = fmaf(beta, old.w, val.w);
+      }
+    } else if (beta != 0.f) {
+      continue;
+    }
+    *reinterpret_cast<float4*>(dst + gi) = val;
+  }
+}
+
 }  // namespace hg

@@ -205,8 +205,12 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
                                  colors, all_maps, opacities, scales, rotations, scale_modifier, cov3D_precomp,
                                  viewmatrix, projmatrix, tan_fovx, tan_fovy, dL_dout_color, dL_dout_all_map,
                                  dL_dout_plane_depth, dL_dout_invdepth, sh, degree, campos, geomBuffer, R,
-                                 binningBuffer, imageBuffer, render_geo, debug):
-    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:149-279)."""
+                                 binningBuffer, imageBuffer, render_geo, debug, sh_sink=None):
+    """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:149-279).
+
+    `sh_sink` (extension, optional): `(tensor [N, M, 3], beta)` — the SH gradient is accumulated into that tensor
+    (`sink = beta * sink + grad`, hg_raster_backward_chunked) and the returned dL_dsh is None.  Returns False through
+    `sh_sink_supported()` for calls that cannot use it (index remap, no SH)."""
     dev = means3D.device
     background, viewmatrix, projmatrix, campos = _f32(background), _f32(viewmatrix), _f32(projmatrix), _f32(campos)
     means3D, colors, all_maps, opacities = _f32(means3D), _f32(colors), _f32(all_maps), _f32(opacities)
@@ -264,7 +268,26 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
                     _ptr(dL_dinvdepths) if has_depth_grad else None, _ptr(dL_dmeans3D), _ptr(dL_dcov3D), _ptr(dL_dsh),
                     _ptr(dL_dscales), _ptr(dL_drotations), _ptr(dL_dall_map))
             hook = _backward_chunk_hook
-            if hook is not None and not prezero:
+            if sh_sink is not None:
+                sink_t, beta = sh_sink
+                if (sink_t.dtype != torch.float32 or not sink_t.is_contiguous() or sink_t.numel() != fullP * 3 * M
+                        or sink_t.device != dev):
+                    raise ValueError("sh_sink must be a contiguous fp32 tensor of the SH gradient's shape")
+                n_chunks, cb = (hook[0], None) if (hook is not None and not prezero) else (1, None)
+                failure = []
+                if hook is not None and not prezero:
+                    def _on_chunk(_ctx, chunk, p0, p1, _stream, fn=hook[1]):
+                        try:
+                            fn(chunk, p0, p1)
+                        except BaseException as e:  # noqa: BLE001
+                            failure.append(e)
+                    cb = _lib.CHUNK_FN(_on_chunk)
+                rc = _lib.lib().hg_raster_backward_chunked(*args, n_chunks, cb if cb is not None else _lib.CHUNK_FN(),
+                                                           None, sink_t.data_ptr(), float(beta), stream)
+                if failure:
+                    raise failure[0]
+                dL_dsh = None
+            elif hook is not None and not prezero:
                 failure = []
 
                 def _on_chunk(_ctx, chunk, p0, p1, _stream, fn=hook[1]):
@@ -273,7 +296,7 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
                     except BaseException as e:  # noqa: BLE001 — must not unwind through the C frame
                         failure.append(e)
                 cb = _lib.CHUNK_FN(_on_chunk)
-                rc = _lib.lib().hg_raster_backward_chunked(*args, hook[0], cb, None, stream)
+                rc = _lib.lib().hg_raster_backward_chunked(*args, hook[0], cb, None, None, 0.0, stream)
                 if failure:
                     raise failure[0]
             else:
@@ -281,6 +304,13 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
         _lib.check(rc, "rasterize_gaussians_backward")
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
             dL_dall_map)
+
+
+def sh_sink_supported(sh, indices, parent_indices):
+    """Whether a backward over these inputs can accumulate its SH gradient into a sink (contiguous rows, 16-byte rows)."""
+    return (sh is not None and sh.numel() != 0 and (indices is None or indices.numel() == 0)
+            and (parent_indices is None or parent_indices.numel() == 0) and (3 * sh.size(1)) % 4 == 0
+            and sh.data_ptr() % 16 == 0)
 
 
 def mark_visible(positions, viewmatrix, projmatrix):

@@ -34,6 +34,11 @@ class _RasterizeGaussians(torch.autograd.Function):
          invdepths) = _C.rasterize_gaussians(*args)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
+        # extension: an SH tensor may carry `_hg_grad_sink = callable -> (tensor, beta)`; its gradient is then
+        # accumulated there by the backward kernel and autograd sees None (hidegs_b200.trainer uses it to skip the
+        # AccumulateGrad pass over the largest parameter block)
+        sink = getattr(sh, "_hg_grad_sink", None)
+        ctx.sh_sink = sink if sink is not None and _C.sh_sink_supported(sh, rs.render_indices, rs.parent_indices) else None
         ctx.save_for_backward(out_all_map, colors_precomp, all_maps, means3D, scales, rotations, cov3Ds_precomp,
                               radii, sh, opacities, geomBuffer, binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii, out_observe)
@@ -61,7 +66,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 grad_out_color, grad_out_all_map, grad_out_plane_depth, grad_out_depth, sh, rs.sh_degree, rs.campos,
                 geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.render_geo, rs.debug)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
-         grad_rotations, grad_all_map) = _C.rasterize_gaussians_backward(*args)
+         grad_rotations, grad_all_map) = _C.rasterize_gaussians_backward(
+            *args, sh_sink=ctx.sh_sink() if ctx.sh_sink is not None else None)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
                 grad_rotations, grad_cov3Ds_precomp, grad_all_map, None)
 

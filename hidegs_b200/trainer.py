@@ -68,6 +68,7 @@ class _ActivateParams(torch.autograd.Function):
                                          torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "activate_params")
         ctx.owner = owner
+        ctx.set_materialize_grads(False)  # a missing gradient stays None (the SH gradient may arrive through the sink)
         return xyz.view_as(xyz), features.view_as(features), opacity, scaling, rotation
 
     @staticmethod
@@ -77,6 +78,15 @@ class _ActivateParams(torch.autograd.Function):
 
         def ptr(t):
             return t.contiguous().data_ptr() if t is not None else None
+        if g_feat is None and not p._sink_used:  # no feature gradient at all in this view: accumulate zeros
+            g_feat = torch.zeros((N, 16, 3), dtype=torch.float32, device=p.param_arena.device) if not p._grad_dirty else None
+        missing = [i for i, t in enumerate((g_xyz, g_op, g_sc, g_rot)) if t is None]
+        if missing:  # (rare: an output that took no part in the loss)
+            z = lambda w: torch.zeros((N, w), dtype=torch.float32, device=p.param_arena.device)  # noqa: E731
+            g_xyz = z(3) if g_xyz is None else g_xyz
+            g_op = z(1) if g_op is None else g_op
+            g_sc = z(3) if g_sc is None else g_sc
+            g_rot = z(4) if g_rot is None else g_rot
         keep = [t.contiguous() if t is not None else None for t in (g_xyz, g_feat, g_op, g_sc, g_rot)]
         d = {k: p.grad_arena[p.slices[k]] for k in ("xyz", "features", "opacity", "scaling", "rotation")}
         with torch.cuda.device(p.param_arena.device):
@@ -87,6 +97,7 @@ class _ActivateParams(torch.autograd.Function):
                 d["rotation"].data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "activate_params_backward")
         p._grad_dirty = True
+        p._sink_used = False
         return None, None, None, None, None, None
 
 
@@ -129,6 +140,8 @@ class GaussianParams:
         self.fused = xyz.is_cuda
         self._act = None          # (xyz, features, opacity, scaling, rotation) of the current view
         self._grad_dirty = False  # False: the next fused backward overwrites the arena (no zero fill needed)
+        self.sh_sink = self.fused  # SH gradient accumulated by the rasterizer's own backward kernel
+        self._sink_used = False
 
     @classmethod
     def from_scene(cls, scene, device):
@@ -140,7 +153,14 @@ class GaussianParams:
     def _activated(self, i):
         if self._act is None:
             self._act = _ActivateParams.apply(self._xyz, self._features, self._opacity, self._scaling, self._rotation, self)
+            if self.sh_sink:  # the rasterizer backward accumulates dL/dSH straight into the gradient arena
+                self._act[1]._hg_grad_sink = self._sh_sink_now
         return self._act[i]
+
+    def _sh_sink_now(self):
+        """(sink tensor, beta) at the time the rasterizer backward of the current view runs."""
+        self._sink_used = True
+        return self.grad_arena[self.slices["features"]].view(self.N, 16, 3), (1.0 if self._grad_dirty else 0.0)
 
     def begin_view(self):
         """Fresh activation node for the next forward/backward (one autograd graph per view)."""

@@ -188,7 +188,11 @@ HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
  * slot_begin, slot_end, stream)` is called on the host: once that kernel completes, rows slot_begin..slot_end-1 of
  * every gradient array are final, so the hook can record an event and start the gradient exchange of those rows on
  * another stream (include/hidegs_exchange.h) while the remaining ranges are computed.  Range boundaries are multiples
- * of 128 slots.  With render indices / parent indices (scattered rows) a single range is used. */
+ * of 128 slots.  With render indices / parent indices (scattered rows) a single range is used.
+ * `sh_sink` (optional, [N, M, 3], 16-byte aligned): the SH gradient is ACCUMULATED there, sink = sh_beta * sink + grad
+ * (sh_beta 0 or 1), instead of being written to dL_dsh — the gradient arena of a multi-view training step, replacing
+ * autograd's AccumulateGrad pass over the largest parameter block; rows of culled Gaussians are zero-filled when
+ * sh_beta == 0 and not touched otherwise.  Needs SH input, no index remap and 3 M a multiple of 4. */
 typedef void (*hg_chunk_fn)(void *chunk_ctx, int32_t chunk, int32_t slot_begin, int32_t slot_end, void *stream);
 HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        const int32_t *radii,
@@ -212,7 +216,7 @@ HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        float *dL_drotations, /* [N,4] */
                        float *dL_dall_map,   /* [N,5] */
                        int32_t n_chunks, hg_chunk_fn on_chunk,
-                                       void *chunk_ctx, void *stream);
+                                       void *chunk_ctx, float *sh_sink, float sh_beta, void *stream);
 
 /* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it sorts the
  * visible splats by depth once (32-bit keys, P elements), emits the tile instances in that order and then sorts

@@ -408,3 +408,51 @@ def test_config3_uav_4k_lod_cut(cuda_device):
     v_cpu.backward()
     assert abs(v_gpu.item() - v_cpu.item()) <= 1e-5 * abs(v_cpu.item()) + 1e-12
     ru.assert_grads_close([s_gpu.grad], [s_cpu.grad], names=("scaling",), what="scale regularisation")
+
+
+def test_sh_gradient_sink_and_chunked_backward(cuda_device):
+    """Extensions of the backward: the SH gradient accumulated into a caller-owned sink (beta 0 / 1, culled rows left
+    alone) and the per-Gaussian part issued in slot ranges with a hook per range — same gradients as the plain call."""
+    from hidegs_b200 import synthetic as syn
+    dev = cuda_device
+    case = ru.build_case(9000, 176, 112, seed=21)
+    fa = ru.op_args(case, dev)
+    fwd = ru.OUR_C.rasterize_gaussians(*fa)
+    grads = syn.upstream_grads(176, 112)
+    ba = ru.bwd_args(fa, fwd, grads, dev)
+    plain = [g.clone() for g in ru.OUR_C.rasterize_gaussians_backward(*ba)]
+    dead = fwd[2] == 0
+    assert 0 < int(dead.sum()) < dead.numel()
+    # beta = 0: the sink is overwritten (culled rows zero-filled), dL_dsh comes back as None
+    sink = torch.full_like(plain[5], 7.0)
+    out = ru.OUR_C.rasterize_gaussians_backward(*ba, sh_sink=(sink, 0.0))
+    assert out[5] is None
+    ru.assert_grads_close([sink], [plain[5]], names=("dL_dsh",), what="sink beta=0")
+    assert float(sink[dead].abs().max()) == 0.0
+    for i in (0, 1, 2, 3, 4, 6, 7, 8):
+        ru.assert_grads_close([out[i]], [plain[i]], names=(ru.GRAD_NAMES[i],), what="sink other grads")
+    # beta = 1: accumulated on top; rows of culled Gaussians are not touched (bit for bit)
+    base = torch.randn_like(plain[5])
+    sink = base.clone()
+    ru.OUR_C.rasterize_gaussians_backward(*ba, sh_sink=(sink, 1.0))
+    assert torch.equal(sink[dead], base[dead])
+    ru.assert_grads_close([sink - base], [plain[5]], names=("dL_dsh",), what="sink beta=1", l2_tol=1e-3, rtol=5e-3)
+    # chunked: ranges are multiples of 128 slots, cover every slot once, and the gradients are the same
+    seen = []
+    ru.OUR_C.set_backward_chunk_hook(4, lambda c, p0, p1: seen.append((c, p0, p1)))
+    try:
+        chunked = ru.OUR_C.rasterize_gaussians_backward(*ba)
+    finally:
+        ru.OUR_C.set_backward_chunk_hook()
+    assert [c for c, _, _ in seen] == list(range(len(seen))) and 2 <= len(seen) <= 4
+    assert seen[0][1] == 0 and seen[-1][2] == 9000 and all(a[2] == b[1] for a, b in zip(seen, seen[1:]))
+    assert all(p0 % 128 == 0 for _, p0, _ in seen)
+    ru.assert_grads_close(chunked, plain, what="chunked backward")
+    # an index remap cannot feed a sink
+    with pytest.raises(RuntimeError, match="sink"):
+        hier = ru.build_case(3000, 96, 64, seed=3, with_indices=True)
+        fh = ru.op_args(hier, dev)
+        fw = ru.OUR_C.rasterize_gaussians(*fh)
+        gh = syn.upstream_grads(96, 64)
+        bh = ru.bwd_args(fh, fw, gh, dev)
+        ru.OUR_C.rasterize_gaussians_backward(*bh, sh_sink=(torch.zeros(hier["means3D"].shape[0], 16, 3, device=dev), 0.0))
