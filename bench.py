@@ -472,7 +472,9 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     total_views = views_per_rank * world
     cams = cams_all[:total_views][rank::world]
     gts = make_gt_images(views_per_rank, dev, seed=11 + rank)
-    params = tr.GaussianParams.from_scene(scene, dev)
+    # the model stores its Gaussians along a Morton curve (a one-off permutation at load time; results are invariant)
+    spatial = os.environ.get("HG_BENCH_SPATIAL_ORDER", "1") != "0"
+    params = tr.GaussianParams.from_scene(scene, dev, spatial_order=spatial)
     trainer = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev), cache_ground_truth=cache_gt)
 
     # Ground-truth images travel host -> device on a copy stream, one event per view (the losses of a view wait for
@@ -522,7 +524,7 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
             "ms_per_view": round(ms_step / views_per_rank, 3), "views_per_rank_per_step": views_per_rank,
             "views_per_step": total_views, "gaussians": n_gauss, "steps": steps, "warmup": warmup,
             "loss_last_step_rank0": round(last, 6), "gpu_launches": int(_lib.lib().hg_launch_count()),
-            "ground_truth_cache": bool(cache_gt),
+            "ground_truth_cache": bool(cache_gt), "gaussian_layout": "morton order" if spatial else "as generated",
             "allreduce_bytes_per_step": params.grad_arena.numel() * 4 if world > 1 else 0,
             "h2d_bytes_per_step": views_per_rank * 3 * HEIGHT * WIDTH * 4,
             "workload": ("configs[4]: view-sharded training, %d UAV survey cameras per step over the 2M-Gaussian slab, %dx%d, "

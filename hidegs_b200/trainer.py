@@ -101,6 +101,23 @@ class _ActivateParams(torch.autograd.Function):
         return None, None, None, None, None, None
 
 
+def morton_order(xyz):
+    """Permutation that sorts points along a 30-bit Morton (Z-order) curve: 10 bits per axis, all axes quantised with the
+    SAME scale (the largest extent), so a thin slab interleaves mostly its two long axes."""
+    xyz = xyz.detach().float().cpu()
+    lo = xyz.min(0).values
+    extent = float((xyz.max(0).values - lo).max().clamp_min(1e-30))
+    q = ((xyz - lo) / extent * 1023.0).long().clamp_(0, 1023)
+
+    def spread(v):  # insert two zero bits between the 10 bits of v
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        return (v | (v << 2)) & 0x09249249
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    return torch.argsort(code, stable=True)
+
+
 class GaussianParams:
     """Trainable Gaussians in the reference's parameterisation (scene/gaussian_model.py:60-140): raw leaves
     `_xyz`, `_features` (N,16,3), `_opacity` (logit), `_scaling` (log), `_rotation` (un-normalised quaternion) and the
@@ -144,11 +161,23 @@ class GaussianParams:
         self._sink_used = False
 
     @classmethod
-    def from_scene(cls, scene, device):
-        """From a synthetic scene dict (hidegs_b200.synthetic.make_scene): activated values -> raw leaves."""
+    def from_scene(cls, scene, device, spatial_order=False):
+        """From a synthetic scene dict (hidegs_b200.synthetic.make_scene): activated values -> raw leaves.
+
+        `spatial_order`: store the Gaussians along a Morton curve (`morton_order`).  A camera sees a compact region of
+        the scene, so with a spatially coherent layout the visible set of a view is a few contiguous index ranges:
+        whole warps of the per-Gaussian kernels are culled or live together, the sparse Adam touches whole sectors, and
+        the blend kernels' record gathers stay local in L2.  The permutation is kept in `.order` (row i of the model is
+        row order[i] of the input); rendering and training are invariant to it."""
         op = scene["opacity"].clamp(1e-6, 1 - 1e-6)
-        return cls(scene["means3D"].to(device), scene["shs"].to(device), torch.log(op / (1 - op)).to(device),
-                   torch.log(scene["scales"]).to(device), scene["rotations"].to(device))
+        t = [scene["means3D"], scene["shs"], torch.log(op / (1 - op)), torch.log(scene["scales"]), scene["rotations"]]
+        order = None
+        if spatial_order:
+            order = morton_order(scene["means3D"])
+            t = [x[order] for x in t]
+        out = cls(*[x.to(device) for x in t])
+        out.order = order
+        return out
 
     def _activated(self, i):
         if self._act is None:

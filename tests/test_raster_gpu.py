@@ -450,9 +450,34 @@ def test_sh_gradient_sink_and_chunked_backward(cuda_device):
     ru.assert_grads_close(chunked, plain, what="chunked backward")
     # an index remap cannot feed a sink
     with pytest.raises(RuntimeError, match="sink"):
-        hier = ru.build_case(3000, 96, 64, seed=3, with_indices=True)
+        hier = ru.build_case(3000, 96, 64, seed=3, with_indices=True, with_hier=True)
         fh = ru.op_args(hier, dev)
         fw = ru.OUR_C.rasterize_gaussians(*fh)
         gh = syn.upstream_grads(96, 64)
         bh = ru.bwd_args(fh, fw, gh, dev)
         ru.OUR_C.rasterize_gaussians_backward(*bh, sh_sink=(torch.zeros(hier["means3D"].shape[0], 16, 3, device=dev), 0.0))
+
+
+@pytest.mark.parametrize("degree", [3, 2])
+def test_sparse_view_zero_rows(cuda_device, degree):
+    """A view that culls most Gaussians (R < 2 P): the zero rows of culled slots come from memsets, live rows from the
+    kernel — every gradient row must be defined even when the arena starts as NaN (degree 2: per-thread SH path)."""
+    from hidegs_b200 import synthetic as syn
+    dev = cuda_device
+    case = ru.build_case(8000, 96, 64, seed=9 + degree, sh_degree=degree, eye=(4.5, 0.0, -5.0))
+    fa = ru.op_args(case, dev)
+    fwd = ru.OUR_C.rasterize_gaussians(*fa)
+    assert 0 < fwd[0] < 2 * 8000 and int((fwd[2] > 0).sum()) < 4000
+    grads = syn.upstream_grads(96, 64)
+    ru.OUR_C.set_gradient_arena_provider(lambda n, d: torch.full((n,), float("nan"), device=d))
+    try:
+        ours_b = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fa, fwd, grads, dev))
+    finally:
+        ru.OUR_C.set_gradient_arena_provider(None)
+    assert all(bool(torch.isfinite(g).all()) for g in ours_b)
+    o = ru.oracle_for_case(case)
+    o.forward()
+    og = o.backward(grads["color"].numpy(), grads["all_map"].numpy(), grads["plane_depth"].numpy(), grads["invdepth"].numpy())
+    ru.assert_grads_close([g.cpu() for g in ours_b], [torch.from_numpy(og[n]) for n in ru.GRAD_NAMES], what="sparse view")
+    dead = (fwd[2] == 0).cpu()
+    assert all(float(g.cpu()[dead].abs().max()) == 0.0 for g in ours_b)

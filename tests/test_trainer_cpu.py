@@ -92,3 +92,15 @@ def test_params_and_grads_alias_their_arenas():
     assert torch.all(p.grad_arena[:48] == 1) and torch.all(p.grad_arena[48:48 + 16 * 48] == 2)
     p.zero_grad()
     assert not p.grad_arena.any() and p.leaves["xyz"].grad.data_ptr() == p.grad_arena.data_ptr()
+
+
+def test_morton_order_is_a_locality_preserving_permutation():
+    from hidegs_b200.trainer import morton_order
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.rand(4000, 3, generator=g) * torch.tensor([400.0, 224.0, 30.0])
+    order = morton_order(xyz)
+    assert sorted(order.tolist()) == list(range(4000))
+    step_sorted = (xyz[order][1:] - xyz[order][:-1]).norm(dim=1).mean()
+    step_raw = (xyz[1:] - xyz[:-1]).norm(dim=1).mean()
+    assert float(step_sorted) < 0.25 * float(step_raw)
+    assert torch.equal(morton_order(xyz), order)  # deterministic (stable sort)

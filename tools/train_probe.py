@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--n", type=int, default=2_000_000)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--views", type=int, default=1)
+    ap.add_argument("--spatial", type=int, default=0, help="store the Gaussians in Morton order")
     a = ap.parse_args()
     from hidegs_b200 import synthetic as syn, trainer as tr, gaussian_renderer as gr, loss_utils as lu
     from hidegs_b200.frequency_regularization import frequency_regularization_pyramid_scale as freg
@@ -31,7 +32,7 @@ def main():
         scene = syn.make_scene(a.n, seed=0)
         cams = [bench.camera_for(r, 0).to(dev) for r in range(a.views)]
     gts = [g.to(dev) for g in bench.make_gt_images(a.views, dev)]
-    params = tr.GaussianParams.from_scene(scene, dev)
+    params = tr.GaussianParams.from_scene(scene, dev, spatial_order=bool(a.spatial))
     t = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev))
     o = t.opt
     names = ("zero_grad", "render_fwd", "loss_fwd", "backward", "adam")
