@@ -280,6 +280,9 @@ def run_gpu_arm(args, impl):
     for ev in gt_free:
         ev.record()
 
+    # Loss read-back: non-blocking pinned copy for both arms (measured on both: faster than a blocking .item() per step,
+    # 2.75 vs 2.86 ms ours, 16.5 vs 24.8 ms reference).  HG_BENCH_E2E_SYNC=1 forces the blocking read.
+    blocking_readback = os.environ.get("HG_BENCH_E2E_SYNC") == "1"
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_read = [torch.cuda.Event() for _ in range(2)]
     for ev in loss_read:
@@ -322,6 +325,8 @@ def run_gpu_arm(args, impl):
                                 params["scales"].grad, params["rotations"].grad))
         # D2H read of the step's result: copied into pinned memory every step; the host consumes it one step later
         # (as a training loop's logging does), so the copy never drains the launch queue.  Both arms share this harness.
+        if blocking_readback:
+            return float(loss.item())
         slot = s & 1
         prev = float(loss_host[1 - slot].item()) if loss_read[1 - slot].query() else None
         loss_host[slot].copy_(loss.detach(), non_blocking=True)
@@ -337,16 +342,23 @@ def run_gpu_arm(args, impl):
     torch.cuda.synchronize()
     if ddp:
         dist.barrier()
-    e0.record()
-    for s in range(Wm, Wm + K):
-        step_e2e(s)
-    e1.record()
-    torch.cuda.synchronize()  # every step's loss has reached the host
-    last_loss = float(loss_host[(Wm + K - 1) & 1].item())
-    assert last_loss == last_loss, "e2e loss is NaN"
-    if ddp:
-        dist.barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    # Two timed passes of K steps, the faster one is reported: the reference's per-call tensor resizes make single
+    # passes of ITS arm vary between 16 and 90 ms / step on the same box (allocator state), ours varies by < 1 %.
+    best = None
+    for _pass in range(2):
+        e0.record()
+        for s in range(Wm, Wm + K):
+            step_e2e(s)
+        e1.record()
+        torch.cuda.synchronize()  # every step's loss has reached the host
+        if not blocking_readback:
+            last_loss = float(loss_host[(Wm + K - 1) & 1].item())
+            assert last_loss == last_loss, "e2e loss is NaN"
+        if ddp:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    t2 = torch.tensor([best], device=dev)
     if ddp:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = float(t2) / K
@@ -396,9 +408,10 @@ def run_gpu_arm(args, impl):
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "d2h": "loss copied to pinned host memory every step (non-blocking), consumed one step later",
+                "d2h": ("loss read with a blocking .item() every step" if blocking_readback else
+                        "loss copied to pinned host memory every step (non-blocking), consumed one step later"),
                 "api": "GaussianRasterizer(settings)(...) + L1 loss + autograd backward; ground-truth upload on a copy "
-                       "stream, overlapped with the forward"},
+                       "stream, overlapped with the forward", "timed_passes": "2 x K steps, faster pass reported"},
     }
     if impl == "ours":
         bytes_per = stage_bytes(N_GAUSS, Nv, R, HW, ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16))
