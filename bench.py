@@ -189,7 +189,7 @@ def run_gpu_arm(args, impl):
     # With an NVSwitch multicast mapping the backward writes its gradients straight into symmetric memory and the
     # exchange is ONE in-fabric kernel (hg_nvls_allreduce_f32); otherwise NCCL sums the arena in place.
     exchange = None
-    if ddp and os.environ.get("HG_EXCHANGE", "auto") != "nccl" and parallel.nvls_available(dev):
+    if ddp and parallel.prefer_nvls(dev):
         exchange = parallel.SymmetricArena(N_GAUSS * 80, dev)   # 80 floats / Gaussian: the whole backward arena
         C.set_gradient_arena_provider(lambda n, d: exchange.tensor if n <= exchange.numel else None)
 
