@@ -193,12 +193,13 @@ def run_gpu_arm(args, impl):
         exchange = parallel.SymmetricArena(N_GAUSS * 80, dev)   # 80 floats / Gaussian: the whole backward arena
         C.set_gradient_arena_provider(lambda n, d: exchange.tensor if n <= exchange.numel else None)
 
-    # ... overlapped with the per-Gaussian backward: preprocess_bwd is issued in 2 slot ranges and the first range's five
-    # parameter blocks travel (one in-fabric kernel on a side stream) while the second range is computed.  Measured
-    # (tools/overlap_probe.py): 8 B200 2.797 ms vs 2.844 ms plain with 2 ranges (2.86 with 4, 2.99 with 8: two cross-rank
-    # barriers per range); 2 B200 2.85 vs 2.86 ms.  HG_EXCHANGE_OVERLAP=0 disables it.
+    # Opt-in (HG_EXCHANGE_OVERLAP=1): overlapped with the per-Gaussian backward — preprocess_bwd is issued in 2 slot
+    # ranges and the first range's five parameter blocks travel (one in-fabric kernel on a side stream) while the second
+    # range is computed.  Measured on 8 B200: 2.797 vs 2.844 ms per step in tools/overlap_probe.py (one camera per
+    # rank), but 2.906 vs 2.844 ms in this bench's loop (a different camera every step: the ranks' skew makes the
+    # extra cross-rank barriers cost more than the 0.08 ms they can hide), so the single call stays the default.
     overlap = None
-    if exchange is not None and os.environ.get("HG_EXCHANGE_OVERLAP", "1") != "0":
+    if exchange is not None and os.environ.get("HG_EXCHANGE_OVERLAP", "0") == "1":
         overlap = parallel.OverlappedBackwardExchange(exchange, N_GAUSS, 16,
                                                       n_chunks=int(os.environ.get("HG_EXCHANGE_CHUNKS", 2)))
 

@@ -87,6 +87,11 @@ class _ActivateParams(torch.autograd.Function):
             g_op = z(1) if g_op is None else g_op
             g_sc = z(3) if g_sc is None else g_sc
             g_rot = z(4) if g_rot is None else g_rot
+        if g_feat is not None and p._sink_used:
+            # the features were ALSO used outside the rasterizer in this view: that gradient comes on top of what the
+            # rasterizer's backward has just accumulated through the sink (never with beta = 0)
+            p.grad_arena[p.slices["features"]].add_(g_feat.reshape(-1))
+            g_feat = None
         keep = [t.contiguous() if t is not None else None for t in (g_xyz, g_feat, g_op, g_sc, g_rot)]
         d = {k: p.grad_arena[p.slices[k]] for k in ("xyz", "features", "opacity", "scaling", "rotation")}
         with torch.cuda.device(p.param_arena.device):

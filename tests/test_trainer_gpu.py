@@ -137,3 +137,26 @@ def test_sparse_arena_adam_and_densification_stats(cuda_device):
     wr = m0.clone()
     wr[f] = torch.max(m0[f], radii[f].float())
     assert torch.equal(maxr, wr)
+
+
+def test_sh_sink_matches_the_autograd_path(cuda_device):
+    """The SH gradient accumulated by the rasterizer's backward kernel (sink) equals what autograd + AccumulateGrad
+    produce, over two views, also when the features are used outside the rasterizer as well."""
+    dev = cuda_device
+    sc, cams, gts, tr = _setup(dev)
+    arenas = {}
+    for use_sink in (True, False):
+        params = tr.GaussianParams.from_scene(sc, dev)
+        params.sh_sink = use_sink
+        trainer = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev))
+        params.zero_grad()
+        for cam, gt in zip(cams, gts):
+            loss, _ = trainer.view_loss(cam, gt, 2000)
+            loss = loss + 1e-3 * (params.get_features ** 2).sum()  # a second consumer of the same features tensor
+            loss.backward()
+        arenas[use_sink] = params.grad_arena.clone()
+    a, b = arenas[True], arenas[False]
+    err = (a - b).abs().max().item()
+    assert err <= 1e-5 * b.abs().max().item() + 1e-12, err
+    sl = tr.GaussianParams.from_scene(sc, dev).slices["features"]
+    assert b[sl].abs().max().item() > 0
