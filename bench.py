@@ -271,7 +271,15 @@ def run_gpu_arm(args, impl):
     gt_host = torch.rand(3, HEIGHT, WIDTH, generator=gen).pin_memory()
     cam_host = [torch.cat([c.world_view_transform.flatten().cpu(), c.full_proj_transform.flatten().cpu(),
                            c.camera_center.cpu()]).pin_memory() for c in cams]
-    w_geo, w_pd, w_inv = g["all_map"] * 1e-3, g["plane_depth"] * 1e-3, g["invdepth"] * 1e-3
+    # linear probes: mean(x * 1e-3 g) written as one dot product each (weights pre-divided by the element count)
+    w_geo_flat = (g["all_map"] * (1e-3 / g["all_map"].numel())).reshape(-1).contiguous()
+    w_pd_flat = (g["plane_depth"] * (1e-3 / g["plane_depth"].numel())).reshape(-1).contiguous()
+    w_inv_flat = (g["invdepth"] * (1e-3 / g["invdepth"].numel())).reshape(-1).contiguous()
+    if impl == "ours":
+        from hidegs_b200.loss_utils import l1_loss as l1
+    else:
+        def l1(network_output, gt):  # utils/loss_utils.py:18-19 of the reference, verbatim
+            return torch.abs((network_output - gt)).mean()
     h2d_bytes = gt_host.numel() * 4 + cam_host[0].numel() * 4
     am_param = all_maps[0].clone().requires_grad_(True)
     # The ground-truth image (24.9 MB) is uploaded on a copy stream while the forward renders; the loss waits for it.
@@ -318,7 +326,10 @@ def run_gpu_arm(args, impl):
                                                                      params["opacity"], params["scales"],
                                                                      params["rotations"], am_param)
         main.wait_event(gt_ready)
-        loss = (color - gt).abs().mean() + (amap * w_geo).mean() + (pdepth * w_pd).mean() + (inv * w_inv).mean()
+        # L1 through each side's own loss function (the reference's utils/loss_utils.l1_loss is torch.abs(a - b).mean();
+        # ours is the fused drop-in of the same name), plus three fixed linear probes that feed the other outputs
+        loss = (l1(color, gt) + torch.dot(amap.reshape(-1), w_geo_flat) + torch.dot(pdepth.reshape(-1), w_pd_flat)
+                + torch.dot(inv.reshape(-1), w_inv_flat))
         loss.backward()
         gt_free[s & 1].record(main)
         if ddp:
@@ -411,7 +422,7 @@ def run_gpu_arm(args, impl):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "d2h": ("loss read with a blocking .item() every step" if blocking_readback else
                         "loss copied to pinned host memory every step (non-blocking), consumed one step later"),
-                "api": "GaussianRasterizer(settings)(...) + L1 loss + autograd backward; ground-truth upload on a copy "
+                "api": "GaussianRasterizer(settings)(...) + l1_loss (each side's own utils.loss_utils.l1_loss) + autograd backward; ground-truth upload on a copy "
                        "stream, overlapped with the forward", "timed_passes": "2 x K steps, faster pass reported"},
     }
     if impl == "ours":
