@@ -819,6 +819,9 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     __syncwarp();
     if (base >= 32) prefetch(base - 32);
     uint32_t mask = maskA | maskB;
+    // (Measured and dropped: software-pipelining this loop by one entry — next entry's first two quads fetched while the
+    // current one is evaluated — 1.27 vs 1.09 ms: eight more live registers at the 128-register cap cost more than the
+    // short-scoreboard stalls they remove.)
     while (mask) {
       const int bit = __ffs(mask) - 1;
       mask &= mask - 1;
@@ -826,8 +829,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       const float4* e = w_rec + kRecQuadsC * bit;
       const float4 ea = e[0];
       const float4 eb = e[1];
-      const float4 ec = e[2];
-      float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 ec = e[2];      float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
       if (GEO) ed = e[3];
       float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f;
       bool any;
@@ -869,15 +871,20 @@ int launch_blend_bwd(const hg_raster_inputs& in, const GeomState& g, const BinSt
     return e ? atoi(e) : 3;
   }();
   if (variant == 3 && !interp) {
-    static const bool attr_ok = [] {
+    // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute: set once per device
+    static bool attr_set[64] = {};
+    int device = 0;
+    HG_CUDA_TRY(cudaGetDevice(&device));
+    bool attr_ok = device >= 0 && device < 64 && attr_set[device];
+    if (!attr_ok) {
       const int bytes = (int)sizeof(BwdMmaSmem);
-      bool ok = true;
-      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      return ok;
-    }();
+      attr_ok = true;
+      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+      if (attr_ok && device >= 0 && device < 64) attr_set[device] = true;
+    }
     if (!attr_ok) {
       set_error("blend_bwd: could not reserve %zu bytes of shared memory", sizeof(BwdMmaSmem));
       return HG_ERR_CUDA;

@@ -208,9 +208,9 @@ class OverlappedBackwardExchange:
 
 def prefer_nvls(device=None, group=None):
     """Policy of HG_EXCHANGE=auto (the default): the in-fabric kernel when multicast memory is available AND the group
-    has at least 4 ranks.  Per GPU it moves (1 + 1/world) x the arena each way against the ring's 2 (world - 1) / world:
-    measured 0.55 vs 0.63 ms (NCCL) for 236 MB on 8 B200, but 0.60 vs 0.46 ms on 2, where the ring moves less.
-    HG_EXCHANGE=nvls / nccl force either."""
+    has at least 8 ranks.  Per GPU it moves (1 + 1/world) x the arena each way against the ring's 2 (world - 1) / world.
+    Measured per bench step (236 MB arena, B200): 8 ranks 2.84 ms vs 2.95 ms with NCCL; 4 ranks 2.94 vs 2.89 ms;
+    2 ranks 0.60 vs 0.46 ms for the exchange alone.  HG_EXCHANGE=nvls / nccl force either."""
     mode = os.environ.get("HG_EXCHANGE", "auto")
     if mode == "nccl" or not nvls_available(device):
         if mode == "nvls":
@@ -218,7 +218,7 @@ def prefer_nvls(device=None, group=None):
         return False
     if mode == "nvls":
         return True
-    return dist.get_world_size(group) >= 4
+    return dist.get_world_size(group) >= 8
 
 
 def make_exchange_arena(numel, device, group=None):
