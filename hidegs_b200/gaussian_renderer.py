@@ -200,8 +200,13 @@ def _exposure(rendered_image, exposure):
 
 
 def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None, indices=None,
-           use_trained_exp=False, return_plane=True, return_depth_normal=True):
-    """render() of the reference (:36-214); same arguments, same result dictionary."""
+           use_trained_exp=False, return_plane=True, return_depth_normal=True, _visibility_as_mask=False):
+    """render() of the reference (:36-214); same arguments, same result dictionary.
+
+    `_visibility_as_mask` (private, used by hidegs_b200.trainer): return `visibility_filter` as the boolean mask
+    `radii > 0` and `radii` un-compacted.  The reference's `nonzero()` / boolean indexing each block the host until the
+    forward blend has finished; a training step that only needs the SET (mask-based scale regulariser, visibility union,
+    densification statistics) keeps launching instead."""
     screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device="cuda") + 0
     try:
         screenspace_points.retain_grad()
@@ -266,7 +271,8 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
     rendered_alpha = out_all_map[3:4]
     rendered_distance = out_all_map[4:5]
     out = {"render": rendered_image, "depth": depth_image, "viewspace_points": screenspace_points,
-           "visibility_filter": vis_filter.nonzero().flatten().long(), "radii": radii[subfilter], "out_observe": out_observe,
+           "visibility_filter": vis_filter if _visibility_as_mask else vis_filter.nonzero().flatten().long(),
+           "radii": radii if _visibility_as_mask else radii[subfilter], "out_observe": out_observe,
            "rendered_normal": rendered_normal, "plane_depth": plane_depth, "rendered_distance": rendered_distance}
     if return_depth_normal:
         out["depth_normal"] = _DepthNormal.apply(plane_depth.squeeze(), rendered_alpha,

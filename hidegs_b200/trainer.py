@@ -286,7 +286,7 @@ class ViewShardedTrainer:
         the image (an upload running on a copy stream while the view renders)."""
         o = self.opt
         self.params.begin_view()
-        pkg = gr.render(cam, self.params, self.pipe, self.bg)
+        pkg = gr.render(cam, self.params, self.pipe, self.bg, _visibility_as_mask=self.params.param_arena.is_cuda)
         if gt_ready is not None:
             torch.cuda.current_stream().wait_event(gt_ready)
         image = pkg["render"]
@@ -322,7 +322,11 @@ class ViewShardedTrainer:
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             if self.sparse_adam:
-                self.visible.index_fill_(0, pkg["visibility_filter"], 1)
+                vf = pkg["visibility_filter"]
+                if vf.dtype == torch.bool:  # mask form (no host sync): union by bitwise or
+                    self.visible.bitwise_or_(vf.view(torch.uint8))
+                else:
+                    self.visible.index_fill_(0, vf, 1)
             if self.densification_stats:
                 self._add_densification_stats(pkg)
         self.params.begin_view()
@@ -345,8 +349,11 @@ class ViewShardedTrainer:
         if g is None:
             return
         N = self.params.N
-        radii_full = torch.zeros(N, dtype=torch.int32, device=g.device)
-        radii_full[pkg["visibility_filter"]] = pkg["radii"]
+        if pkg["visibility_filter"].dtype == torch.bool:  # mask form: radii is already per Gaussian (0 where culled)
+            radii_full = pkg["radii"].to(torch.int32).contiguous()
+        else:
+            radii_full = torch.zeros(N, dtype=torch.int32, device=g.device)
+            radii_full[pkg["visibility_filter"]] = pkg["radii"]
         with torch.cuda.device(g.device):
             rc = _G().hg_densification_stats(g.contiguous().data_ptr(), radii_full.data_ptr(), N,
                                              self.xyz_gradient_accum.data_ptr(), self.denom.data_ptr(),
