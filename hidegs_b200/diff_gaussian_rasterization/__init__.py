@@ -59,7 +59,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         if grad_out_plane_depth is None:
             grad_out_plane_depth = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
         if grad_out_depth is None:
-            grad_out_depth = torch.zeros((1 if rs.do_depth else 0, H, W), dtype=torch.float32, device=dev)
+            # the inverse depth took no part in the loss: "absent" (empty) instead of a zero image — the backward then
+            # runs its no-depth-gradient kernels (a zero upstream gradient contributes exactly nothing)
+            grad_out_depth = torch.empty((0, H, W), dtype=torch.float32, device=dev)
         args = (rs.bg, all_map_pixels, rs.render_indices, rs.parent_indices, rs.interpolation_weights,
                 rs.num_node_kids, means3D, radii, colors_precomp, all_maps, opacities, scales, rotations,
                 rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy,

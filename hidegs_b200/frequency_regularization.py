@@ -33,6 +33,7 @@ class GroundTruthCache:
             rc = _L().hg_freq_gt_prepare(g.data_ptr(), H, W, self.levels, self.state.data_ptr(), _stream())
         _lib.check(rc, "frequency loss ground-truth state")
         self.mask, self.count = detect_true_high_frequency_regions(g, self.thresh)
+        self.nonempty = (self.count[0] > 0).float()  # gate of the scale term (:1644), constant per image
 
     def matches(self, gt_image, num_levels, high_freq_thresh):
         g = gt_image[0] if gt_image.dim() == 4 else gt_image
@@ -180,13 +181,13 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
     device = rendered_image.device
     r = rendered_image[0] if rendered_image.dim() == 4 else rendered_image
     g = gt_image[0] if gt_image.dim() == 4 else gt_image
-    total = torch.zeros((), dtype=torch.float32, device=device)
+    total = None  # (0 + a + b of the reference, built without the zero tensor and its two extra additions)
     stats = None
     if gt_cache is not None and not gt_cache.matches(g, num_levels, high_freq_thresh):
         raise RuntimeError("gt_cache was built for another image size / level count / threshold")
     if lambda_freq > 0:
         freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels), gt_cache.state if gt_cache is not None else None)
-        total = total + lambda_freq * freq_loss
+        total = lambda_freq * freq_loss
     if gt_cache is not None:
         mask, count = gt_cache.mask, gt_cache.count
     else:
@@ -202,7 +203,11 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
         if scaling is not None:
             scale_loss = _ScaleReg.apply(scaling, visibility_filter)
             # the reference applies the term only if the mask is non-empty (:1644); same, without a host sync
-            total = total + lambda_scale * scale_loss * (count[0] > 0).float()
+            nonempty = gt_cache.nonempty if gt_cache is not None else (count[0] > 0).float()
+            term = lambda_scale * scale_loss * nonempty
+            total = term if total is None else total + term
+    if total is None:
+        total = torch.zeros((), dtype=torch.float32, device=device)
     total = torch.clamp(total, 0, 1.0)
 
     def fill():

@@ -204,7 +204,7 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
     """render() of the reference (:36-214); same arguments, same result dictionary.
 
     `_visibility_as_mask` (private, used by hidegs_b200.trainer): return `visibility_filter` as the boolean mask
-    `radii > 0` and `radii` un-compacted.  The reference's `nonzero()` / boolean indexing each block the host until the
+    `radii > 0` and `radii` un-compacted, and leave `depth_normal` out (the fused normal term recomputes it).  The reference's `nonzero()` / boolean indexing each block the host until the
     forward blend has finished; a training step that only needs the SET (mask-based scale regulariser, visibility union,
     densification statistics) keeps launching instead."""
     screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device="cuda") + 0
@@ -274,7 +274,9 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
            "visibility_filter": vis_filter if _visibility_as_mask else vis_filter.nonzero().flatten().long(),
            "radii": radii if _visibility_as_mask else radii[subfilter], "out_observe": out_observe,
            "rendered_normal": rendered_normal, "plane_depth": plane_depth, "rendered_distance": rendered_distance}
-    if return_depth_normal:
+    if _visibility_as_mask:
+        pass  # the trainer's fused normal term computes the depth normal itself (normal_consistency_loss)
+    elif return_depth_normal:
         out["depth_normal"] = _DepthNormal.apply(plane_depth.squeeze(), rendered_alpha,
                                                  camera_intrinsics(viewpoint_camera))
     else:
