@@ -23,7 +23,9 @@ from . import loss_utils as lu
 from ._geometry_lib import lib as _G
 from . import _lib
 from . import parallel
-from .frequency_regularization import GroundTruthCache, frequency_regularization_pyramid_scale
+from .frequency_regularization import (GroundTruthCache, _FreqLoss, _ScaleReg, detect_true_high_frequency_regions,
+                                       frequency_regularization_pyramid_scale)
+from .diff_gaussian_rasterization import _RasterizeGaussians
 
 GROUPS = (("xyz", 3), ("features", 48), ("opacity", 1), ("scaling", 3), ("rotation", 4))
 
@@ -278,6 +280,9 @@ class ViewShardedTrainer:
             self.denom = torch.zeros((params.N, 1), device=dev)
             self.max_radii2D = torch.zeros(params.N, device=dev)
         self.iteration = 0
+        # autograd-free executor of a view (view_step_direct); HG_TRAINER_DIRECT=0 keeps the autograd path
+        import os
+        self.direct = params.fused and os.environ.get("HG_TRAINER_DIRECT", "1") != "0"
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
@@ -307,6 +312,106 @@ class ViewShardedTrainer:
                                                      o.single_view_weight)
         return loss, pkg
 
+    # ------------------------------------------------------------------------------------------------------------------
+    # The same view without autograd.  The training step is host bound (2.2 ms of host time per view against ~1.7 ms of
+    # kernels: tools/train_cpu_profile.py), and most of that host time is autograd's — nine custom Functions applied and
+    # walked back, ~40 glue ops recorded and differentiated.  The graph of a view is FIXED, so it is executed here as a
+    # straight sequence: the forward and backward BODIES of the very same Functions (one implementation, one set of
+    # kernels) run on a hand-written tape, the loss weights are folded into the three image-gradient terms, and nothing
+    # is recorded.  tests/test_trainer_gpu.py holds it to the autograd path (same gradient arena, same loss).
+    class _Tape:
+        """What an autograd.Function body expects of `ctx`."""
+
+        def __init__(self, *needs):
+            self.needs_input_grad = needs
+            self.saved_tensors = ()
+
+        def save_for_backward(self, *tensors):
+            self.saved_tensors = tensors
+
+        def mark_non_differentiable(self, *_a):
+            pass
+
+        def set_materialize_grads(self, _v):
+            pass
+
+    def view_step_direct(self, cam, gt, iteration, gt_ready=None):
+        """Forward AND backward of one view (gradients accumulated into the arena), without autograd.  Returns
+        (loss value tensor, dict with "visibility_filter" (mask), "radii", "means2D_grad")."""
+        o, p, T = self.opt, self.params, self._Tape
+        dev = p.param_arena.device
+        with torch.no_grad():
+            # ---- forward
+            tA = T(True, True, True, True, True, False)
+            xyz, feat, opacity, scaling, rotation = _ActivateParams.forward(tA, p._xyz, p._features, p._opacity,
+                                                                            p._scaling, p._rotation, p)
+            e_i = torch.empty(0, dtype=torch.int32, device=dev)
+            e_f = torch.empty(0, dtype=torch.float32, device=dev)
+            rs = gr._raster_settings(cam, p, self.pipe, self.bg, 1.0, True, True, e_i, e_i, e_f, e_i)
+            tM = T(True, False, True, False, False)
+            all_map_in = gr._AllMap.forward(tM, xyz, scaling, rotation, rs.viewmatrix, rs.campos)
+            if p.sh_sink:
+                feat._hg_grad_sink = p._sh_sink_now
+            tR = T(True, True, True, False, True, True, True, False, True, False)
+            color, radii, _observe, out_all_map, plane_depth, _inv = _RasterizeGaussians.forward(
+                tR, xyz, xyz, feat, e_f, opacity, scaling, rotation, e_f, all_map_in, rs)
+            image = color.clamp(0, 1)
+            if gt_ready is not None:
+                torch.cuda.current_stream().wait_event(gt_ready)
+            tL, tS = T(True, False, False), T(True, False, False)
+            l1 = lu._PixelLoss.forward(tL, image, gt, False)
+            ss = lu._SSIM.forward(tS, image, gt, True)
+            visible = radii > 0
+            cache = None
+            freq_on = iteration >= o.freq_warmup_iterations
+            if self.cache_ground_truth and freq_on:
+                cache = self._gt_cache.get(id(cam))
+                if cache is None:
+                    cache = self._gt_cache[id(cam)] = (cam, GroundTruthCache(gt),
+                                                       (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2)
+            loss = (1.0 - o.lambda_dssim) * l1 + o.lambda_dssim * (1.0 - ss)
+            tF = tSc = None
+            freq_total = None
+            if freq_on:  # frequency_regularization_pyramid_scale (same arithmetic, same order)
+                if o.lambda_freq > 0:
+                    tF = T(True, False, False, False)
+                    freq_loss, _stats = _FreqLoss.forward(tF, image, gt, 3, cache[1].state if cache is not None else None)
+                    freq_total = o.lambda_freq * freq_loss
+                if o.lambda_scale > 0:
+                    nonempty = cache[1].nonempty if cache is not None else \
+                        (detect_true_high_frequency_regions(gt)[1][0] > 0).float()
+                    tSc = T(True, False)
+                    scale_loss = _ScaleReg.forward(tSc, scaling, visible)
+                    term = o.lambda_scale * scale_loss * nonempty
+                    freq_total = term if freq_total is None else freq_total + term
+                if freq_total is not None:
+                    gate = ((freq_total >= 0) & (freq_total <= 1.0)).float()  # d clamp(total, 0, 1) / d total
+                    loss = loss + torch.clamp(freq_total, 0, 1.0)
+            tN = None
+            if o.single_view_weight > 0:
+                image_weight = cache[2] if cache is not None else (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2
+                tN = T(True, True, False, False, False)
+                loss = loss + gr._NormalConsistency.forward(tN, plane_depth, out_all_map, image_weight,
+                                                            gr.camera_intrinsics(cam), o.single_view_weight)
+            # ---- backward (upstream gradient of the loss = 1)
+            g_image = tL.grad * (1.0 - o.lambda_dssim)
+            one = torch.ones((), dtype=torch.float32, device=dev)
+            g_image.add_(lu._SSIM.backward(tS, one)[0], alpha=-o.lambda_dssim)
+            if tF is not None:
+                g_image.addcmul_(tF.grad, gate * o.lambda_freq)
+            g_color = g_image * ((color >= 0) & (color <= 1))       # clamp(0, 1) passes the gradient inside [0, 1]
+            g_pd = tN.gd.reshape(plane_depth.shape) if tN is not None else None
+            g_am = tN.gam if tN is not None else None
+            (g_xyz, g_means2D, g_sh, _gc, g_op, g_sc, g_rot, _gcov, g_all_map_in, _n) = _RasterizeGaussians.backward(
+                tR, g_color, None, None, g_am, g_pd, None)
+            d_xyz, _n2, d_rot, _n3, _n4 = gr._AllMap.backward(tM, g_all_map_in)
+            g_xyz = g_xyz + d_xyz
+            g_rot = g_rot + d_rot
+            if tSc is not None:
+                g_sc = torch.addcmul(g_sc, tSc.grad, gate * nonempty * o.lambda_scale)
+            _ActivateParams.backward(tA, g_xyz, g_sh, g_op, g_sc, g_rot)
+        return loss, {"visibility_filter": visible, "radii": radii, "means2D_grad": g_means2D}
+
     def step(self, views, total_views=None):
         """One optimiser step over this rank's `views` = [(camera, gt_image[, gt_ready_event]), ...]; returns the summed
         loss tensor."""
@@ -317,9 +422,13 @@ class ViewShardedTrainer:
             self.visible.zero_()
         for view in views:
             cam, gt = view[0], view[1]
-            loss, pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations,
-                                       view[2] if len(view) > 2 else None)
-            loss.backward()
+            if getattr(self, "direct", False):
+                loss, pkg = self.view_step_direct(cam, gt, self.iteration + self.opt.freq_warmup_iterations,
+                                                  view[2] if len(view) > 2 else None)
+            else:
+                loss, pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations,
+                                           view[2] if len(view) > 2 else None)
+                loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             if self.sparse_adam:
                 vf = pkg["visibility_filter"]
@@ -345,7 +454,7 @@ class ViewShardedTrainer:
         return total
 
     def _add_densification_stats(self, pkg):
-        g = pkg["viewspace_points"].grad
+        g = pkg["means2D_grad"] if "means2D_grad" in pkg else pkg["viewspace_points"].grad
         if g is None:
             return
         N = self.params.N
