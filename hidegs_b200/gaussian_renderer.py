@@ -200,13 +200,18 @@ def _exposure(rendered_image, exposure):
 
 
 def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None, indices=None,
-           use_trained_exp=False, return_plane=True, return_depth_normal=True, _visibility_as_mask=False):
-    """render() of the reference (:36-214); same arguments, same result dictionary.
+           use_trained_exp=False, return_plane=True, return_depth_normal=True):
+    """render() of the reference (:36-214); same arguments, same result dictionary."""
+    return _render_impl(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_color, indices, use_trained_exp,
+                        return_plane, return_depth_normal, False)
 
-    `_visibility_as_mask` (private, used by hidegs_b200.trainer): return `visibility_filter` as the boolean mask
-    `radii > 0` and `radii` un-compacted, and leave `depth_normal` out (the fused normal term recomputes it).  The reference's `nonzero()` / boolean indexing each block the host until the
-    forward blend has finished; a training step that only needs the SET (mask-based scale regulariser, visibility union,
-    densification statistics) keeps launching instead."""
+
+def _render_impl(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None, indices=None,
+                 use_trained_exp=False, return_plane=True, return_depth_normal=True, _visibility_as_mask=False):
+    """Body of render().  `_visibility_as_mask` (hidegs_b200.trainer only): return `visibility_filter` as the boolean
+    mask `radii > 0` and `radii` un-compacted, and leave `depth_normal` out (the fused normal term recomputes it).  The
+    reference's `nonzero()` / boolean indexing each block the host until the forward blend has finished; a training step
+    that only needs the SET (mask-based scale regulariser, visibility union, densification statistics) keeps launching."""
     screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device="cuda") + 0
     try:
         screenspace_points.retain_grad()

@@ -291,7 +291,7 @@ class ViewShardedTrainer:
         the image (an upload running on a copy stream while the view renders)."""
         o = self.opt
         self.params.begin_view()
-        pkg = gr.render(cam, self.params, self.pipe, self.bg, _visibility_as_mask=self.params.param_arena.is_cuda)
+        pkg = gr._render_impl(cam, self.params, self.pipe, self.bg, _visibility_as_mask=self.params.param_arena.is_cuda)
         if gt_ready is not None:
             torch.cuda.current_stream().wait_event(gt_ready)
         image = pkg["render"]
