@@ -98,6 +98,23 @@ int run_pixel_loss(const float* a, const float* b, int64_t n, float* out, float*
   return HG_OK;
 }
 
+// ---------------------------------------------------------------- composed image gradient of the training loss
+__global__ void __launch_bounds__(256)
+training_image_grad_kernel(const float* __restrict__ color, const float* __restrict__ gt, const float* g_ssim,
+                           const float* g_freq, int64_t n, float w_l1_over_n, float w_ssim,
+                           const float* __restrict__ w_freq, float* out) {
+  const float wf = w_freq ? __ldg(w_freq) : 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float c = color[i];
+    const float d = fminf(fmaxf(c, 0.f), 1.f) - gt[i];
+    float g = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * w_l1_over_n;
+    if (g_ssim) g = fmaf(w_ssim, g_ssim[i], g);
+    if (g_freq) g = fmaf(wf, g_freq[i], g);
+    out[i] = (c >= 0.f && c <= 1.f) ? g : 0.f;  // d clamp(c, 0, 1) / dc
+  }
+}
+
 // ---------------------------------------------------------------- SSIM
 // Separable 11-tap Gaussian (sigma 1.5) in shared memory: 32x32 output tile per 256-thread CTA, 42x42 input tile
 // (halo 5, zero padded as F.conv2d(padding=5)).  Both passes are register blocked — a thread produces 4 consecutive
@@ -452,6 +469,21 @@ int hg_l1_loss(const float* a, const float* b, int64_t n, float* out, float* gra
 }
 int hg_l2_loss(const float* a, const float* b, int64_t n, float* out, float* grad_a, void* ws, void* st) {
   return run_pixel_loss<true>(a, b, n, out, grad_a, ws, (cudaStream_t)st);
+}
+
+int hg_training_image_grad(const float* color, const float* gt, const float* g_ssim, const float* g_freq, int64_t n,
+                           float w_l1, float w_ssim, const float* w_freq, float* out, void* st_) {
+  if (n < 0 || (n > 0 && (!color || !gt || !out))) {
+    set_error("hg_training_image_grad: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (n == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  const int64_t blocks = (n + 255) / 256;
+  training_image_grad_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
+      color, gt, g_ssim, g_freq, n, w_l1 / (float)n, w_ssim, w_freq, out);
+  HG_POST_LAUNCH(false, st, "training_image_grad");
+  return HG_OK;
 }
 
 size_t hg_ssim_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {

@@ -283,6 +283,7 @@ class ViewShardedTrainer:
         # autograd-free executor of a view (view_step_direct); HG_TRAINER_DIRECT=0 keeps the autograd path
         import os
         self.direct = params.fused and os.environ.get("HG_TRAINER_DIRECT", "1") != "0"
+        self._one = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
@@ -358,7 +359,7 @@ class ViewShardedTrainer:
             image = color.clamp(0, 1)
             if gt_ready is not None:
                 torch.cuda.current_stream().wait_event(gt_ready)
-            tL, tS = T(True, False, False), T(True, False, False)
+            tL, tS = T(False, False, False), T(True, False, False)  # (the L1 gradient is formed in the combine kernel)
             l1 = lu._PixelLoss.forward(tL, image, gt, False)
             ss = lu._SSIM.forward(tS, image, gt, True)
             visible = radii > 0
@@ -394,12 +395,17 @@ class ViewShardedTrainer:
                 loss = loss + gr._NormalConsistency.forward(tN, plane_depth, out_all_map, image_weight,
                                                             gr.camera_intrinsics(cam), o.single_view_weight)
             # ---- backward (upstream gradient of the loss = 1)
-            g_image = tL.grad * (1.0 - o.lambda_dssim)
-            one = torch.ones((), dtype=torch.float32, device=dev)
-            g_image.add_(lu._SSIM.backward(tS, one)[0], alpha=-o.lambda_dssim)
-            if tF is not None:
-                g_image.addcmul_(tF.grad, gate * o.lambda_freq)
-            g_color = g_image * ((color >= 0) & (color <= 1))       # clamp(0, 1) passes the gradient inside [0, 1]
+            # dL/dcolor = [0 <= color <= 1] ((1 - l) dL1 - l dSSIM + gate lf dfreq) in ONE pass over the image
+            if self._one is None:
+                self._one = torch.ones((), dtype=torch.float32, device=dev)
+            g_color = lu._SSIM.backward(tS, self._one)[0]
+            w_freq = (gate * o.lambda_freq) if tF is not None else None
+            with torch.cuda.device(dev):
+                rc = lu._L().hg_training_image_grad(
+                    color.data_ptr(), gt.data_ptr(), g_color.data_ptr(), tF.grad.data_ptr() if tF is not None else None,
+                    color.numel(), 1.0 - o.lambda_dssim, -o.lambda_dssim, w_freq.data_ptr() if w_freq is not None else None,
+                    g_color.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "training_image_grad")
             g_pd = tN.gd.reshape(plane_depth.shape) if tN is not None else None
             g_am = tN.gam if tN is not None else None
             (g_xyz, g_means2D, g_sh, _gc, g_op, g_sc, g_rot, _gcov, g_all_map_in, _n) = _RasterizeGaussians.backward(

@@ -39,6 +39,15 @@ HG_API int hg_l1_loss(const float *a, const float *b, int64_t n, float *out, flo
 HG_API int hg_l2_loss(const float *a, const float *b, int64_t n, float *out, float *grad_a,
                       void *workspace, void *stream);
 
+/* Image gradient of the composed training loss in one pass (used by the autograd-free executor of the training step,
+ * hidegs_b200/trainer.py; the reference composes the same terms with autograd: (1 - lambda) l1_loss + lambda (1 - ssim)
+ * + frequency term, on render().clamp(0, 1) — utils/loss_utils.py:18-64, gaussian_renderer/__init__.py:170):
+ *   out = [0 <= color <= 1] * ( w_l1 * sign(clamp(color, 0, 1) - gt) / n  +  w_ssim * g_ssim  +  w_freq[0] * g_freq )
+ * color, gt, out: n floats (out may alias g_ssim or g_freq); g_ssim / g_freq: dSSIM/dimage and dfreq/dimage for a unit
+ * upstream gradient, nullable; w_freq: DEVICE scalar (the clamp gate times lambda_freq), nullable = 0. */
+HG_API int hg_training_image_grad(const float *color, const float *gt, const float *g_ssim, const float *g_freq,
+                                  int64_t n, float w_l1, float w_ssim, const float *w_freq, float *out, void *stream);
+
 /* SSIM with the reference's 11x11 sigma=1.5 window, zero padding 5, C1=1e-4, C2=9e-4.
  * img1/img2: [B,C,H,W].  out[b] = mean over (C,H,W) of the SSIM map of batch item b (the Python
  * wrapper averages over b for size_average=True).  If `maps` != NULL (3*B*C*H*W floats) the three

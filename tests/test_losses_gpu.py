@@ -233,3 +233,34 @@ def test_ground_truth_cache_is_bit_identical(cuda_device):
         assert a[4] == b[4]
     with pytest.raises(RuntimeError, match="gt_cache was built for another"):
         f(r, gt, lt.GaussiansShim(sc), None, None, vis, 2000, num_levels=2, gt_cache=cache)
+
+
+@pytest.mark.gpu
+def test_training_image_grad_combines_the_terms(cuda_device):
+    """hg_training_image_grad: [0 <= c <= 1] ((1 - l) dL1 + w_s dSSIM + w_f dfreq) in one pass, against torch ops; `out`
+    aliasing g_ssim and the nullable frequency term."""
+    from hidegs_b200 import _lib
+    from hidegs_b200._losses_lib import lib as L
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(3)
+    n = 3 * 67 * 131 + 3  # odd size
+    color = torch.randn(n, device=dev, generator=g) * 0.6 + 0.5
+    color[:5] = torch.tensor([0.0, 1.0, -0.1, 1.1, 0.5], device=dev)
+    gt = torch.rand(n, device=dev, generator=g)
+    gt[4] = 0.5  # sign(0) = 0
+    gs, gf = torch.randn(n, device=dev, generator=g), torch.randn(n, device=dev, generator=g)
+    wf = torch.tensor(0.37, device=dev)
+    lam = 0.2
+    inside = ((color >= 0) & (color <= 1)).float()
+    l1g = torch.sign(color.clamp(0, 1) - gt) / n
+    for use_freq in (True, False):
+        want = inside * ((1 - lam) * l1g - lam * gs + (wf * gf if use_freq else 0.0))
+        out = gs.clone()  # aliases the SSIM gradient, as the trainer calls it
+        with torch.cuda.device(dev):
+            rc = L().hg_training_image_grad(color.data_ptr(), gt.data_ptr(), out.data_ptr(),
+                                            gf.data_ptr() if use_freq else None, n, 1 - lam, -lam,
+                                            wf.data_ptr() if use_freq else None, out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "training_image_grad")
+        assert torch.allclose(out, want, rtol=1e-5, atol=1e-6), float((out - want).abs().max())  # (fma vs separate rounding)
+        assert float(out[2].abs() + out[3].abs()) == 0.0 and float(out[0].abs()) > 0 and float(out[1].abs()) > 0
