@@ -46,3 +46,38 @@ def test_in_fabric_allreduce_matches_nccl(cuda_device):
         pytest.skip("no multicast (NVLS) support on this box")
     for i in range(3):  # same bits as NCCL's sum at world 2 (two addends: the order cannot matter), identical replicas
         assert out["max_abs_err_%d" % i] == 0.0 and out["replicas_identical_%d" % i]
+
+
+def test_overlap_helper_ranges_cover_the_soa_arena_once():
+    """OverlappedBackwardExchange: a slot range maps to five ranges of the SoA arena (xyz | sh | opacity | scale |
+    rotation); over all chunks every float of the 59 N arena is exchanged exactly once, in multiples of 4 floats."""
+    import numpy as np
+
+    class FakeArena:
+        class _B:
+            device = torch.device("cpu")
+        _buf = _B()
+
+        def __init__(self):
+            self.calls = []
+
+        def all_reduce_ranges_(self, offs, cnts):
+            self.calls.append((list(offs), list(cnts)))
+            return 4 * sum(cnts)
+
+    N = 1000
+    ov = parallel.OverlappedBackwardExchange.__new__(parallel.OverlappedBackwardExchange)
+    ov.arena, ov.N, ov.n_chunks, ov.widths, ov.bytes = FakeArena(), N, 4, (3, 48, 1, 3, 4), 0
+    seen = np.zeros(59 * N, np.int32)
+    for p0 in range(0, N, 256):  # chunk boundaries as hg_raster_backward_chunked makes them (multiples of 128 slots)
+        p1 = min(N, p0 + 256)
+        offs, cnts, base = [], [], 0
+        for w in ov.widths:
+            offs.append(base + w * p0)
+            cnts.append(w * (p1 - p0))
+            base += w * N
+        ov.bytes += ov.arena.all_reduce_ranges_(offs, cnts)
+        for o, c in zip(offs, cnts):
+            assert o % 4 == 0 and c % 4 == 0
+            seen[o:o + c] += 1
+    assert (seen == 1).all() and ov.bytes == 4 * 59 * N
