@@ -22,7 +22,7 @@ CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 
 
 def sources():
-    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))  # .cpp: host compiler only
 
 
 def _digest(paths):
@@ -35,7 +35,7 @@ def _digest(paths):
 
 
 def _compile(src, verbose):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
+    obj = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
     stamp = obj + ".sha"
     deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     inc = os.path.join(HERE, "..", "include")

@@ -44,55 +44,11 @@ void fill_layout(int64_t P, int64_t N, bool compressed, hg_hier_layout* L) {
   L->file_bytes = off;
 }
 
-// ---- host half conversion (IEEE binary16, round-to-nearest-even: half.hpp 2.2 with HALF_ROUND_STYLE 1) ----
-inline float half_to_float_host(uint16_t h) {
-  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
-  uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, bits;
-  if (exp == 0) {
-    if (man == 0) {
-      bits = sign;
-    } else {  // subnormal: normalise
-      int sh = 0;
-      while (!(man & 0x400u)) {
-        man <<= 1;
-        ++sh;
-      }
-      man &= 0x3ffu;
-      bits = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | (man << 13);
-    }
-  } else if (exp == 31) {
-    bits = sign | 0x7f800000u | (man << 13);
-  } else {
-    bits = sign | ((exp + 112u) << 23) | (man << 13);
-  }
-  float f;
-  memcpy(&f, &bits, 4);
-  return f;
-}
-
-inline uint16_t float_to_half_host(float f) {
-  uint32_t x;
-  memcpy(&x, &f, 4);
-  const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
-  x &= 0x7fffffffu;
-  if (x >= 0x7f800000u) return sign | (x > 0x7f800000u ? 0x7e00u : 0x7c00u);  // NaN (quiet) / inf
-  if (x >= 0x477ff000u) return sign | 0x7c00u;                                // rounds to >= 65520 -> inf
-  if (x < 0x33000001u) return sign;                                           // <= 2^-25 rounds to zero (tie to even)
-  uint32_t exp = x >> 23, man = (x & 0x7fffffu) | 0x800000u;
-  int shift;
-  uint32_t half_exp;
-  if (exp < 113) {  // subnormal half
-    shift = 13 + (113 - (int)exp);
-    half_exp = 0;
-  } else {
-    shift = 13;
-    half_exp = exp - 112;
-  }
-  const uint32_t keep = man >> shift, rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
-  uint32_t r = (half_exp ? ((half_exp << 10) | (keep & 0x3ffu)) : keep);
-  if (rem > halfway || (rem == halfway && (keep & 1u))) ++r;  // carries propagate into the exponent correctly
-  return sign | (uint16_t)r;
-}
+// host half conversion lives in hier_half.cpp (F16C when the CPU has it, scalar otherwise)
+}  // namespace
+void half_to_float_array(const uint16_t* src, float* dst, size_t n);
+void float_to_half_array(const float* src, uint16_t* dst, size_t n);
+namespace {
 
 struct File {
   FILE* f = nullptr;
@@ -239,7 +195,7 @@ int hg_hier_load(const char* filename, float* pos, float* shs, float* alphas, fl
     auto widen = [&](int64_t off, float* dst, int64_t count) {
       tmp.resize((size_t)count);
       if (!hg::read_exact(fl.f, off, tmp.data(), count * 2)) return false;
-      for (int64_t i = 0; i < count; ++i) dst[i] = hg::half_to_float_host(tmp[(size_t)i]);
+      hg::half_to_float_array(tmp.data(), dst, (size_t)count);
       return true;
     };
     ok = ok && widen(L.rot, rot, P * 4) && widen(L.scale, scales, P * 3) && widen(L.opacity, alphas, P) &&
@@ -310,7 +266,7 @@ int hg_hier_write(const char* filename, int64_t P, int64_t N, const float* pos, 
     std::vector<uint16_t> tmp;
     auto narrow = [&](const float* src, int64_t count) {
       tmp.resize((size_t)count);
-      for (int64_t i = 0; i < count; ++i) tmp[(size_t)i] = hg::float_to_half_host(src[i]);
+      hg::float_to_half_array(src, tmp.data(), (size_t)count);
       put(tmp.data(), count * 2);
     };
     narrow(rotations, P * 4);

@@ -206,3 +206,27 @@ def test_device_round_trip_large_and_rounding(cuda_device, tmp_path):
     with pytest.raises(RuntimeError, match="Would lose information!"):
         H.write_hierarchy(str(tmp_path / "bad.hier"), dev["pos"], dev["shs"], dev["alphas"], dev["scales"], dev["rot"],
                           dev["nodes"], dev["boxes"], compressed=True)
+
+
+def test_host_half_conversion_scalar_and_simd_paths_agree():
+    """hier_half.cpp: the F16C path (when the CPU has it) and the scalar fallback give the same bits, and both equal
+    numpy's IEEE round-to-nearest-even, on every finite half, every rounding tie and the overflow / underflow edges."""
+    import ctypes
+    from hidegs_b200 import _lib
+    L = _lib.lib()
+    halves = np.arange(0, 0x7c01, dtype=np.uint16)
+    f = halves.view(np.float16).astype(np.float32)
+    mids = ((f[:-2].astype(np.float64) + f[1:-1].astype(np.float64)) / 2).astype(np.float32)
+    vals = np.concatenate([f[:-1], mids, np.nextafter(mids, np.float32(np.inf)), np.nextafter(mids, np.float32(-np.inf)),
+                           np.array([65504.0, 65519.996, 65520.0, 7e4, 1e30, np.inf, 2.0 ** -25, 2.0 ** -26, 1e-30], np.float32)])
+    vals = np.ascontiguousarray(np.concatenate([vals, -vals]).astype(np.float32))
+    with np.errstate(over="ignore"):
+        want = vals.astype(np.float16).view(np.uint16)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    for scalar in (0, 1):
+        got = np.empty(len(vals), np.uint16)
+        L.hg_test_float_to_half(p(vals), p(got), ctypes.c_int64(len(vals)), scalar)
+        assert np.array_equal(got, want), ("float->half", scalar)
+        back = np.empty(len(halves), np.float32)
+        L.hg_test_half_to_float(p(halves), p(back), ctypes.c_int64(len(halves)), scalar)
+        assert np.array_equal(back.view(np.uint32), halves.view(np.float16).astype(np.float32).view(np.uint32)), scalar
