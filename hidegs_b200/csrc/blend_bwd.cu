@@ -3,21 +3,18 @@
 // Replaces renderCUDA<3,5> backward of the reference
 // (cuda_rasterizer/backward.cu:499-772, launched at :883).
 //
-// Design (B200):
-//  * same tiling as the forward (256-thread CTA per 16x16 tile, warp = 8x4
-//    sub-tile, register-double-buffered 64-byte record gathers, lane-parallel
-//    exact sub-tile culling), traversing the list from the tile's LAST
-//    contributor (block max of n_contrib) instead of the end of the range;
-//  * the nine blended channels (rgb, 5 geometry channels, inverse depth) share
-//    one recurrence: dL/dalpha only needs sum_ch (c_ch - accum_ch) * dL/dch, so
-//    each pixel carries ONE scalar accumulator of g = <features, dL/dpixel>
-//    instead of nine, which halves the FP32 work per contributing pair;
-//  * the reference issues 15 same-address float atomics per (pixel, Gaussian)
-//    pair.  Here the 15 per-lane partials are reduced across the warp with a
-//    recursive-halving butterfly (16 SHFL + 16 FADD instead of 75 + 75), and
-//    the 16 lanes that end up owning one component each issue ONE coalesced
-//    RED.ADD.F32 into the Gaussian's 64-byte accumulator row: one L2 atomic
-//    transaction per (warp, contributing entry).
+// Three generations live in this file (HG_BLEND_BWD_VARIANT selects; the default is the newest that applies):
+//  A  blend_bwd_kernel   256-thread CTA per 16x16 tile, warp = 8x4 sub-tile, one pixel per lane.
+//  B  blend_bwd2_kernel  128-thread CTA, warp = 8x8 sub-tile, two pixels per lane, ONE shuffle butterfly + ONE RED
+//                        per (warp, entry).  Still the kernel of the hierarchy-interpolation path.
+//  C  blend_bwd3_kernel  as B, but the cross-pixel reduction runs on the tensor cores (3xTF32 mma.sync against
+//                        per-pixel constant tiles), the staging is per warp and barrier free.  Default.
+// Common to all: register-double-buffered gathers of the 64-byte splat records, lane-parallel exact sub-tile
+// culling, traversal from the LAST contributor backwards, and one shared recurrence for the nine blended channels
+// (rgb, inverse depth, 5 geometry channels): dL/dalpha only needs sum_ch (c_ch - accum_ch) * dL/dch, so each pixel
+// carries ONE scalar accumulator of g = <features, dL/dpixel> instead of nine.  The reference issues 15 same-address
+// float atomics per (pixel, Gaussian) pair; here one accumulator row per Gaussian receives one (B) or a few vector
+// (C) REDs per (warp, entry).
 #include "blend_common.cuh"
 
 #include <cstdlib>
