@@ -8,6 +8,7 @@ Gaussian on the host (`list(map(tuple, attributes))`) and lets plyfile emit a bi
 CUDA tensors), crosses to the host once, and is written with one `tofile`; reading parses the header, maps the file and
 splits the columns by NAME (any property order, extra float properties ignored), exactly the fields the reference reads.
 """
+import json
 import os
 import struct
 
@@ -170,3 +171,41 @@ def save_point_cloud_bin(path, xyz, features_dc, features_rest, opacity, scaling
         f.write(struct.pack("i", t[0].size(0)))
         for x in t:
             f.write(x.numpy().tobytes())
+
+
+_PT_FILES = ("done_xyz.pt", "done_dc.pt", "done_rest.pt", "done_opacity.pt", "done_scaling.pt", "done_rotation.pt")
+
+
+def save_pt(path, xyz, features_dc, features_rest, opacity, scaling, rotation):
+    """GaussianModel.save_pt (gaussian_model.py:486-517): the six `done_*.pt` tensors (xyz / features / opacity on the
+    CPU, scaling and rotation as they are, like the reference) plus `point_cloud.bin`."""
+    os.makedirs(path, exist_ok=True)
+    torch.save(xyz.detach().cpu(), os.path.join(path, "done_xyz.pt"))
+    torch.save(features_dc.detach().cpu(), os.path.join(path, "done_dc.pt"))
+    torch.save(features_rest.detach().cpu(), os.path.join(path, "done_rest.pt"))
+    torch.save(opacity.detach().cpu(), os.path.join(path, "done_opacity.pt"))
+    torch.save(scaling.detach(), os.path.join(path, "done_scaling.pt"))
+    torch.save(rotation.detach(), os.path.join(path, "done_rotation.pt"))
+    save_point_cloud_bin(os.path.join(path, "point_cloud.bin"), xyz, features_dc, features_rest, opacity, scaling, rotation)
+
+
+def load_pt(path, device="cpu"):
+    """The inner load_pt of save_pt (gaussian_model.py:497-505) / the `done_scaling.pt`, `done_rotation.pt` reads of
+    create_from_hier (:398-399): (xyz, features_dc, features_rest, opacity, scaling, rotation)."""
+    return tuple(torch.load(os.path.join(path, f), map_location=device).detach() for f in _PT_FILES)
+
+
+def save_exposures(path, exposure, image_names):
+    """scene/__init__.py:165-170: exposure.json = {image_name: 3x4 nested list} of the per-image exposure matrices."""
+    data = {name: exposure[i].detach().cpu().numpy().tolist() for i, name in enumerate(image_names)}
+    with open(path, "w") as f:
+        json.dump(data, f, indent=2)
+
+
+def load_exposures(path, device="cuda"):
+    """create_from_hier's exposure read (gaussian_model.py:376-385): {image_name: fp32 [3,4] tensor} or None."""
+    if not os.path.exists(path):
+        return None
+    with open(path, "r") as f:
+        exposures = json.load(f)
+    return {name: torch.tensor(exposures[name], dtype=torch.float32, device=device) for name in exposures}

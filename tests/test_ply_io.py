@@ -121,3 +121,20 @@ def test_ply_from_and_to_the_device(cuda_device, tmp_path):
     back = ply_io.load_ply(path, degree=3, device=cuda_device)
     for got, key in zip(back, ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")):
         assert got.is_cuda and torch.equal(got.cpu(), m[key]), key
+
+
+def test_done_pt_and_exposure_json(tmp_path):
+    m = _model(23, seed=8)
+    d = str(tmp_path / "chunk")
+    ply_io.save_pt(d, **m)
+    import os
+    assert sorted(os.listdir(d)) == sorted(list(ply_io._PT_FILES) + ["point_cloud.bin"])
+    back = ply_io.load_pt(d)
+    for got, key in zip(back, ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")):
+        assert torch.equal(got, m[key]), key
+    exp = torch.eye(3, 4)[None].repeat(3, 1, 1) + torch.arange(3).view(3, 1, 1) * 0.01
+    path = str(tmp_path / "exposure.json")
+    ply_io.save_exposures(path, exp, ["a.jpg", "b.jpg", "c.jpg"])
+    got = ply_io.load_exposures(path, device="cpu")
+    assert list(got) == ["a.jpg", "b.jpg", "c.jpg"] and all(torch.equal(got[n], exp[i]) for i, n in enumerate(got))
+    assert ply_io.load_exposures(str(tmp_path / "missing.json"), device="cpu") is None
