@@ -18,7 +18,7 @@ def install(patch_reference_modules=True):
         get_interpolation_weights}  ->  hidegs_b200's drop-ins
         if importable and `patch_reference_modules`: the reference's own `utils.loss_utils` (l1_loss, l2_loss, ssim,
         get_img_grad_weight, lncc), `scripts.frequency_regularization.frequency_regularization_pyramid_scale`,
-        `gaussian_renderer` (render, render_post, render_normal) and `scene.OurAdam.Adam` get their hot functions
+        `gaussian_renderer` (render, render_post, render_coarse, render_normal) and `scene.OurAdam.Adam` get their hot functions
         replaced in place, so `from utils.loss_utils import ssim` etc. keep working unchanged.
 
     Returns the list of names that were redirected."""
@@ -49,7 +49,7 @@ def install(patch_reference_modules=True):
     from . import loss_utils as lu, frequency_regularization as fr, gaussian_renderer as gr, optim
     targets = (("utils.loss_utils", lu, ("l1_loss", "l2_loss", "ssim", "get_img_grad_weight", "lncc")),
                ("scripts.frequency_regularization", fr, ("frequency_regularization_pyramid_scale",)),
-               ("gaussian_renderer", gr, ("render", "render_post", "render_normal")),
+               ("gaussian_renderer", gr, ("render", "render_post", "render_coarse", "render_normal")),
                ("scene.OurAdam", optim, ("Adam",)))
     for modname, src, names in targets:
         try:

@@ -6,7 +6,7 @@ from . import _lib
 EXPORTED_SYMBOLS = (
     "hg_geometry_all_map", "hg_geometry_all_map_backward", "hg_activate_params", "hg_activate_params_backward", "hg_depth_normal", "hg_depth_normal_backward",
     "hg_normal_consistency_workspace_bytes", "hg_normal_consistency_loss", "hg_adam_step", "hg_densification_stats", "hg_expand_to_size_workspace_bytes", "hg_expand_to_size",
-    "hg_interpolation_weights",
+    "hg_interpolation_weights", "hg_hier_interpolate", "hg_hier_interpolate_backward",
     "hg_dist2_knn3_workspace_bytes", "hg_dist2_knn3",
 )
 
@@ -40,6 +40,8 @@ def lib():
         "hg_expand_to_size_workspace_bytes": (sz, [i32]),
         "hg_expand_to_size": (ci, [vp, vp, i32, f32, vp, i32, vp, vp, vp, vp, vp, ctypes.POINTER(i32), vp]),
         "hg_interpolation_weights": (ci, [vp, i32, f32, vp, vp, f32, f32, f32, vp, vp, vp]),
+        "hg_hier_interpolate": (ci, [vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp]),
+        "hg_hier_interpolate_backward": (ci, [vp, i64, i32, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "hg_dist2_knn3_workspace_bytes": (sz, [i64]),
         "hg_dist2_knn3": (ci, [vp, i64, vp, vp, vp]),
     }

@@ -119,13 +119,16 @@ training_image_grad_kernel(const float* __restrict__ color, const float* __restr
 // Separable 11-tap Gaussian (sigma 1.5) in shared memory: 32x32 output tile per 256-thread CTA, 42x42 input tile
 // (halo 5, zero padded as F.conv2d(padding=5)).  Both passes are register blocked — a thread produces 4 consecutive
 // outputs from a 14-value sliding window — so a tap costs 0.3 shared-memory loads instead of one.
-__constant__ float c_gauss[11];
+// The 11 window weights travel as a by-value kernel argument (constant bank of the launch): no per-device symbol to
+// initialise, nothing on the default stream.
+struct Gauss11 { float w[11]; };
 constexpr int kTile = 32, kHalo = 5, kIn = kTile + 2 * kHalo;  // 42
 constexpr int kSsimThreads = 256;
 
 // horizontal pass over NQ quantities derived from the NS staged planes; work item = (row, group of 4 columns)
 template <int NS, int NQ, typename F>
-__device__ __forceinline__ void conv_rows4(const float (*src)[kIn][kIn + 1], float (*dst)[kIn][kTile + 1], int tid, F make) {
+__device__ __forceinline__ void conv_rows4(const float (*src)[kIn][kIn + 1], float (*dst)[kIn][kTile + 1], int tid,
+                                           const Gauss11& gw, F make) {
   for (int w = tid; w < kIn * (kTile / 4); w += kSsimThreads) {
     const int r = w / (kTile / 4), c0 = (w - r * (kTile / 4)) * 4;
     float acc[NQ][4];
@@ -145,7 +148,7 @@ __device__ __forceinline__ void conv_rows4(const float (*src)[kIn][kIn + 1], flo
         const int tap = k - j;  // output c0+j uses inputs c0+j .. c0+j+10
         if (tap >= 0 && tap < 11) {
 #pragma unroll
-          for (int q = 0; q < NQ; ++q) acc[q][j] += c_gauss[tap] * val[q];
+          for (int q = 0; q < NQ; ++q) acc[q][j] += gw.w[tap] * val[q];
         }
       }
     }
@@ -158,7 +161,8 @@ __device__ __forceinline__ void conv_rows4(const float (*src)[kIn][kIn + 1], flo
 
 // vertical pass: thread (tx, ty) produces rows 4 ty .. 4 ty + 3 of column tx
 template <int NQ>
-__device__ __forceinline__ void conv_cols4(const float (*h)[kIn][kTile + 1], int tx, int ty, float (&out)[NQ][4]) {
+__device__ __forceinline__ void conv_cols4(const float (*h)[kIn][kTile + 1], int tx, int ty, const Gauss11& gw,
+                                           float (&out)[NQ][4]) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
@@ -173,7 +177,7 @@ __device__ __forceinline__ void conv_cols4(const float (*h)[kIn][kTile + 1], int
       const int tap = k - j;
       if (tap >= 0 && tap < 11) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) out[q][j] += c_gauss[tap] * v[q];
+        for (int q = 0; q < NQ; ++q) out[q][j] += gw.w[tap] * v[q];
       }
     }
   }
@@ -192,7 +196,7 @@ __device__ __forceinline__ void load_tile(float (*dst)[kIn][kIn + 1], const floa
 }
 
 __global__ void __launch_bounds__(kSsimThreads)
-ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W,
+ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W, const Gauss11 gw,
                 float* __restrict__ maps, size_t map_stride, double* __restrict__ partial) {
   __shared__ float s[2][kIn][kIn + 1];
   __shared__ float h[5][kIn][kTile + 1];
@@ -204,13 +208,13 @@ ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, 
   const float* const planes[2] = {img1 + base, img2 + base};
   load_tile<2>(s, planes, H, W, x0, y0, tid);
   __syncthreads();
-  conv_rows4<2, 5>(s, h, tid, [](const float (&in)[2], float (&v)[5]) {
+  conv_rows4<2, 5>(s, h, tid, gw, [](const float (&in)[2], float (&v)[5]) {
     v[0] = in[0]; v[1] = in[1]; v[2] = in[0] * in[0]; v[3] = in[1] * in[1]; v[4] = in[0] * in[1];
   });
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;
   float o[5][4];
-  conv_cols4<5>(h, tx, ty, o);
+  conv_cols4<5>(h, tx, ty, gw, o);
   float val = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -245,7 +249,7 @@ __global__ void ssim_finalize_kernel(const double* __restrict__ partial, int per
 __global__ void __launch_bounds__(kSsimThreads)
 ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
                 const float* __restrict__ maps, size_t map_stride, const float* __restrict__ gscale,
-                int C, int H, int W, float* __restrict__ grad) {
+                int C, int H, int W, const Gauss11 gw, float* __restrict__ grad) {
   __shared__ float m[3][kIn][kIn + 1];
   __shared__ float h[3][kIn][kTile + 1];
   const int plane = blockIdx.z;
@@ -255,11 +259,11 @@ ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
   const float* const planes[3] = {maps + base, maps + map_stride + base, maps + 2 * map_stride + base};
   load_tile<3>(m, planes, H, W, x0, y0, tid);
   __syncthreads();
-  conv_rows4<3, 3>(m, h, tid, [](const float (&in)[3], float (&v)[3]) { v[0] = in[0]; v[1] = in[1]; v[2] = in[2]; });
+  conv_rows4<3, 3>(m, h, tid, gw, [](const float (&in)[3], float (&v)[3]) { v[0] = in[0]; v[1] = in[1]; v[2] = in[2]; });
   __syncthreads();
   const int tx = tid & 31, ty = tid >> 5;
   float o[3][4];
-  conv_cols4<3>(h, tx, ty, o);
+  conv_cols4<3>(h, tx, ty, gw, o);
   const float sc = __ldg(gscale + plane / C) / ((float)C * (float)H * (float)W);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -440,19 +444,16 @@ scale_reg_grad_kernel(const float* __restrict__ scaling, int64_t N, const int64_
   }
 }
 
-bool g_gauss_ready = false;
-int ensure_gauss() {
-  if (g_gauss_ready) return HG_OK;
-  // gaussian(11, 1.5) of the reference (loss_utils.py:24-26): float32 values normalised by their float32 sum.
-  float g[11], sum = 0.f;
+// gaussian(11, 1.5) of the reference (loss_utils.py:24-26): float32 values normalised by their float32 sum.
+Gauss11 gauss_window() {
+  Gauss11 g;
+  float sum = 0.f;
   for (int x = 0; x < 11; ++x) {
-    g[x] = (float)std::exp(-(double)((x - 5) * (x - 5)) / (2.0 * 1.5 * 1.5));
-    sum += g[x];
+    g.w[x] = (float)std::exp(-(double)((x - 5) * (x - 5)) / (2.0 * 1.5 * 1.5));
+    sum += g.w[x];
   }
-  for (int x = 0; x < 11; ++x) g[x] = g[x] / sum;
-  HG_CUDA_TRY(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
-  g_gauss_ready = true;
-  return HG_OK;
+  for (int x = 0; x < 11; ++x) g.w[x] = g.w[x] / sum;
+  return g;
 }
 
 }  // namespace
@@ -497,11 +498,9 @@ int hg_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t 
     set_error("hg_ssim: bad argument");
     return HG_ERR_INVALID_ARG;
   }
-  int rc = ensure_gauss();
-  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)st_;
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
-  ssim_fwd_kernel<<<grid, kSsimThreads, 0, st>>>(img1, img2, H, W, maps, (size_t)B * C * H * W, (double*)ws);
+  ssim_fwd_kernel<<<grid, kSsimThreads, 0, st>>>(img1, img2, H, W, gauss_window(), maps, (size_t)B * C * H * W, (double*)ws);
   HG_POST_LAUNCH(false, st, "ssim_fwd");
   ssim_finalize_kernel<<<B, 1024, 0, st>>>((const double*)ws, (int)(grid.x * grid.y * C), (double)C * H * W, out);
   HG_POST_LAUNCH(false, st, "ssim_finalize");
@@ -514,12 +513,10 @@ int hg_ssim_backward(const float* img1, const float* img2, const float* maps, co
     set_error("hg_ssim_backward: bad argument");
     return HG_ERR_INVALID_ARG;
   }
-  int rc = ensure_gauss();
-  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)st_;
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, B * C);
   ssim_bwd_kernel<<<grid, kSsimThreads, 0, st>>>(img1, img2, maps, (size_t)B * C * H * W, gscale, C, H, W,
-                                                      grad_img1);
+                                                      gauss_window(), grad_img1);
   HG_POST_LAUNCH(false, st, "ssim_bwd");
   return HG_OK;
 }

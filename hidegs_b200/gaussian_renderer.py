@@ -7,9 +7,11 @@ on fused kernels for the per-Gaussian prologue and the per-pixel epilogue.
                   autograd graph -> one kernel forward (`hg_geometry_all_map`), one backward
       epilogue    :200-201 render_normal(plane_depth) * rendered_alpha.detach(): ~15 full-resolution PyTorch ops
                   (utils/graphics_utils.py:17-23,108-166) -> one kernel forward, one backward
-  render_post()   :217-374 (hierarchy LOD path: Python interpolation with the parent node, then the rasterizer
-                  with interpolation weights / kid counts)
-  render_normal() :21-33 (offset=None path)
+  render_post()   :217-374 (hierarchy LOD path: interpolation with the parent node in ONE gather kernel
+                  (`hg_hier_interpolate`, reference: ~25 PyTorch ops), then the rasterizer with interpolation
+                  weights / kid counts)
+  render_coarse() :376-488 (colour-only render of the coarse optimisation)
+  render_normal() :21-33
 
 `pc` is duck-typed exactly as the reference uses it: get_xyz, get_opacity, get_scaling, get_rotation,
 get_features, active_sh_degree, max_sh_degree, _xyz, skybox_points, get_covariance, get_exposure_from_name.
@@ -184,15 +186,101 @@ def _raster_settings(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, ren
         interpolation_weights=interpolation_weights, num_node_kids=num_siblings)
 
 
+_SH_C0 = 0.28209479177387814
+_SH_C1 = 0.4886025119029199
+_SH_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+_SH_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435)
+
+
+def sh_basis(deg, dirs):
+    """Real SH basis values [N, (deg+1)^2] of unit directions [N,3], in the coefficient order and with the constants
+    of utils/sh_utils.py:eval_sh (:53-112), so that eval_sh(deg, sh, dirs) == (sh[..., :K] * basis[:, None, :]).sum(-1)."""
+    x, y, z = dirs[:, 0], dirs[:, 1], dirs[:, 2]
+    cols = [torch.full_like(x, _SH_C0)]
+    if deg > 0:
+        cols += [-_SH_C1 * y, _SH_C1 * z, -_SH_C1 * x]
+    if deg > 1:
+        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+        cols += [_SH_C2[0] * xy, _SH_C2[1] * yz, _SH_C2[2] * (2.0 * zz - xx - yy), _SH_C2[3] * xz, _SH_C2[4] * (xx - yy)]
+        if deg > 2:
+            cols += [_SH_C3[0] * y * (3 * xx - yy), _SH_C3[1] * xy * z, _SH_C3[2] * y * (4 * zz - xx - yy),
+                     _SH_C3[3] * z * (2 * zz - 3 * xx - 3 * yy), _SH_C3[4] * x * (4 * zz - xx - yy),
+                     _SH_C3[5] * z * (xx - yy), _SH_C3[6] * x * (xx - 3 * yy)]
+    return torch.stack(cols, dim=1)
+
+
 def _colors(viewpoint_camera, pc, pipe, override_color):
+    """SH features or precomputed colours of a render call (gaussian_renderer/__init__.py:139-152)."""
     shs = colors_precomp = None
     if override_color is None:
         if pipe.convert_SHs_python:
-            raise NotImplementedError("convert_SHs_python: SH evaluation runs inside the rasterizer")
-        shs = pc.get_features
+            # `pipe.convert_SHs_python`: colours evaluated by differentiable torch ops and handed to the rasterizer as
+            # colors_precomp (the reference's eval_sh path); the rasterizer itself still runs on the CUDA library
+            feats = pc.get_features  # [N, K, 3]
+            dirs = pc.get_xyz - viewpoint_camera.camera_center.to(feats.device)[None, :]
+            dirs = dirs / dirs.norm(dim=1, keepdim=True)
+            basis = sh_basis(pc.active_sh_degree, dirs)  # [N, k]
+            rgb = (feats[:, :basis.size(1), :] * basis[:, :, None]).sum(1)
+            colors_precomp = torch.clamp_min(rgb + 0.5, 0.0)
+        else:
+            shs = pc.get_features
     else:
         colors_precomp = override_color
     return shs, colors_precomp
+
+
+class _HierInterp(torch.autograd.Function):
+    """Parent interpolation of a hierarchy cut (the `interp_python` branch of render_post, reference :278-318) as ONE
+    gather + lerp kernel (`hg_hier_interpolate`) and one scatter kernel backward, instead of ~25 PyTorch gathers, lerps
+    and concatenations with their autograd nodes.  Outputs hold E + skybox rows."""
+
+    @staticmethod
+    def forward(ctx, means3D, scales, rotations, opacity, shs, render_indices, parent_indices, ts, skybox):
+        _need_cuda(means3D, scales, rotations, opacity, shs, ts)
+        dev = means3D.device
+        m, sc, rot, op, sh = (t.contiguous() for t in (means3D, scales, rotations, opacity, shs))
+        N, M = m.size(0), sh.size(1)
+        E, S = int(render_indices.size(0)), int(skybox)
+        ri = render_indices.to(device=dev, dtype=torch.int32).contiguous()
+        pi = parent_indices[:E].to(device=dev, dtype=torch.int32).contiguous()
+        t = ts[:E].detach().contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        o_m, o_sc, o_rot = torch.empty((E + S, 3), **f32), torch.empty((E + S, 3), **f32), torch.empty((E + S, 4), **f32)
+        o_op, o_sh = torch.empty((E + S, 1), **f32), torch.empty((E + S, M, 3), **f32)
+        with torch.cuda.device(dev):
+            rc = _G().hg_hier_interpolate(m.data_ptr(), sc.data_ptr(), rot.data_ptr(), op.data_ptr(), sh.data_ptr(), N, M,
+                                          ri.data_ptr(), pi.data_ptr(), t.data_ptr(), E, S, o_m.data_ptr(), o_sc.data_ptr(),
+                                          o_rot.data_ptr(), o_op.data_ptr(), o_sh.data_ptr(), _stream())
+        _lib.check(rc, "hier_interpolate")
+        ctx.save_for_backward(rot, ri, pi, t)
+        ctx.dims = (N, M, E, S)
+        ctx.set_materialize_grads(False)
+        return o_m, o_sc, o_rot, o_op, o_sh
+
+    @staticmethod
+    def backward(ctx, g_m, g_sc, g_rot, g_op, g_sh):
+        rot, ri, pi, t = ctx.saved_tensors
+        N, M, E, S = ctx.dims
+        dev = rot.device
+        widths = ((3,), (3,), (4,), (1,), (M, 3))
+        gs = [g.contiguous() if g is not None else None for g in (g_m, g_sc, g_rot, g_op, g_sh)]
+        ds = [torch.zeros((N,) + w, dtype=torch.float32, device=dev) if (g is not None and need) else None
+              for g, w, need in zip(gs, widths, ctx.needs_input_grad[:5])]
+        ptr = lambda x: x.data_ptr() if x is not None else None  # noqa: E731
+        with torch.cuda.device(dev):
+            rc = _G().hg_hier_interpolate_backward(rot.data_ptr(), N, M, ri.data_ptr(), pi.data_ptr(), t.data_ptr(), E, S,
+                                                   *[ptr(g) if d is not None else None for g, d in zip(gs, ds)],
+                                                   *[ptr(d) for d in ds], _stream())
+        _lib.check(rc, "hier_interpolate_backward")
+        return ds[0], ds[1], ds[2], ds[3], ds[4], None, None, None, None
+
+
+def hierarchy_interpolate(means3D, scales, rotations, opacity, shs, render_indices, parent_indices,
+                          interpolation_weights, skybox_points=0):
+    """(means3D, scales, rotations, opacity, shs) of a hierarchy cut blended with their parent nodes; differentiable."""
+    return _HierInterp.apply(means3D, scales, rotations, opacity, shs, render_indices, parent_indices,
+                             interpolation_weights, int(skybox_points))
 
 
 def _exposure(rendered_image, exposure):
@@ -311,42 +399,25 @@ def render_post(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, over
         scales, rotations = pc.get_scaling, pc.get_rotation
     shs, colors_precomp = _colors(viewpoint_camera, pc, pipe, override_color)
 
-    if render_indices.size(0) != 0:
-        render_inds = render_indices.long()
+    E = int(render_indices.size(0))
+    if E != 0:
         if interp_python:
-            num_entries = render_indices.size(0)
-            interps = interpolation_weights[:num_entries].unsqueeze(1)
-            interps_inv = (1 - interpolation_weights[:num_entries]).unsqueeze(1)
-            parent_inds = parent_indices[:num_entries].long()
-            means3D_base = (interps * means3D[render_inds] + interps_inv * means3D[parent_inds]).contiguous()
-            scales_base = (interps * scales[render_inds] + interps_inv * scales[parent_inds]).contiguous()
-            shs_base = (interps.unsqueeze(2) * shs[render_inds] + interps_inv.unsqueeze(2) * shs[parent_inds]).contiguous()
-            parents = rotations[parent_inds]
-            rots = rotations[render_inds]
-            dots = torch.bmm(rots.unsqueeze(1), parents.unsqueeze(2)).flatten()
-            parents[dots < 0] *= -1
-            rotations_base = ((interps * rots) + interps_inv * parents).contiguous()
-            opacity_base = (interps * opacity[render_inds] + interps_inv * opacity[parent_inds]).contiguous()
-            if pc.skybox_points == 0:
-                skybox_inds = torch.empty(0, dtype=torch.long, device=dev)
-            else:
-                skybox_inds = torch.arange(pc._xyz.size(0) - pc.skybox_points, pc._xyz.size(0), device=dev).long()
-            means3D = torch.cat((means3D_base, means3D[skybox_inds])).contiguous()
-            shs = torch.cat((shs_base, shs[skybox_inds])).contiguous()
-            opacity = torch.cat((opacity_base, opacity[skybox_inds])).contiguous()
-            rotations = torch.cat((rotations_base, rotations[skybox_inds])).contiguous()
-            means2D = means2D[:(num_entries + pc.skybox_points)].contiguous()
-            scales = torch.cat((scales_base, scales[skybox_inds])).contiguous()
+            if shs is None or scales is None:
+                raise RuntimeError("render_post(interp_python=True) blends SH features, scales and rotations with the "
+                                   "parent node: it needs pc.get_features / get_scaling / get_rotation (reference :281-291)")
+            S = int(pc.skybox_points)
+            means3D, scales, rotations, opacity, shs = hierarchy_interpolate(
+                means3D, scales, rotations, opacity, shs, render_indices, parent_indices, interpolation_weights, S)
+            means2D = means2D[:E + S].contiguous()
+            # the skybox tail is rendered as-is: weight 1, one kid (reference :313-315; like the reference, the caller's
+            # num_node_kids is updated in place, the weights on a private copy)
             interpolation_weights = interpolation_weights.clone().detach()
-            interpolation_weights[num_entries:num_entries + pc.skybox_points] = 1.0
-            num_node_kids[num_entries:num_entries + pc.skybox_points] = 1
+            interpolation_weights[E:E + S] = 1.0
+            num_node_kids[E:E + S] = 1
         else:
-            means3D = means3D[render_inds].contiguous()
-            means2D = means2D[render_inds].contiguous()
-            shs = shs[render_inds].contiguous()
-            opacity = opacity[render_inds].contiguous()
-            scales = scales[render_inds].contiguous()
-            rotations = rotations[render_inds].contiguous()
+            sel = render_indices.long()
+            means3D, means2D, opacity = means3D[sel].contiguous(), means2D[sel].contiguous(), opacity[sel].contiguous()
+            shs, scales, rotations = shs[sel].contiguous(), scales[sel].contiguous(), rotations[sel].contiguous()
         render_indices = torch.empty(0, dtype=torch.int32, device=dev)
         parent_indices = torch.empty(0, dtype=torch.int32, device=dev)
 
@@ -372,3 +443,42 @@ def render_post(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, over
     vis_filter = radii > 0
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": vis_filter,
             "radii": radii[vis_filter]}
+
+
+def render_coarse(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, zfar=0.0, override_color=None, indices=None):
+    """render_coarse() of the reference (:376-488): colour-only render for the coarse optimisation (render_geo=False,
+    do_depth=False, debug=True as the reference sets it), optional row subset `indices`; returns the boolean
+    visibility mask over ALL Gaussians and the radii of the visible rendered rows."""
+    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device="cuda") + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    dev = pc.get_xyz.device
+    e_i = torch.empty(0, dtype=torch.int32, device=dev)
+    e_f = torch.empty(0, dtype=torch.float32, device=dev)
+
+    class _Debug:  # the reference hard-codes debug=True for this entry point (:412)
+        debug = True
+    rs = _raster_settings(viewpoint_camera, pc, _Debug, bg_color, scaling_modifier, False, False, e_i, e_i, e_f, e_i)
+    means3D, means2D, opacity = pc.get_xyz, screenspace_points, pc.get_opacity
+    scales = rotations = cov3D_precomp = None
+    if pipe.compute_cov3D_python:
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales, rotations = pc.get_scaling, pc.get_rotation
+    shs, colors_precomp = _colors(viewpoint_camera, pc, pipe, override_color)
+    if indices is not None:
+        means3D, means2D, opacity = means3D[indices].contiguous(), means2D[indices].contiguous(), opacity[indices].contiguous()
+        shs, scales, rotations = shs[indices].contiguous(), scales[indices].contiguous(), rotations[indices].contiguous()
+    rendered_image, radii, _, _, _, _ = GaussianRasterizer(raster_settings=rs)(
+        means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_precomp, opacities=opacity, scales=scales,
+        rotations=rotations, cov3D_precomp=cov3D_precomp)
+    subfilter = radii > 0
+    if indices is not None:
+        vis_filter = torch.zeros(pc._xyz.size(0), dtype=torch.bool, device=dev)
+        vis_filter[indices] = subfilter
+    else:
+        vis_filter = subfilter
+    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": vis_filter,
+            "radii": radii[subfilter]}

@@ -46,7 +46,11 @@ def allreduce_gradients(grads, group=None, average=False, async_op=False):
     """Sum (or average) the per-rank gradients of one step over all ranks, in place.
 
     `grads`: gradient tensors in arena order (means3D, sh, opacity, scales, rotations).  Returns
-    (work handle or None, number of bytes sent through the collective)."""
+    (work handle or None, number of bytes sent through the collective).  `average` needs the reduced values, so it
+    cannot be combined with `async_op` (the division would race with the collective): the caller scales after wait()."""
+    if average and async_op:
+        raise ValueError("allreduce_gradients: average=True needs the finished sum; wait() on the handle and scale "
+                         "yourself, or call with async_op=False")
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     flat = flat_view(grads)
     packed = None
@@ -168,6 +172,9 @@ class OverlappedBackwardExchange:
 
     def __init__(self, arena, n_gaussians, sh_coeffs=16, n_chunks=4):
         self.arena, self.N, self.n_chunks = arena, int(n_gaussians), int(n_chunks)
+        if self.N % 4 != 0:  # block starts are w * N floats into the arena; the exchange kernel works on 16-byte units
+            raise ValueError("OverlappedBackwardExchange needs a Gaussian count that is a multiple of 4 (got %d): the "
+                             "operator's gradient arena packs its SoA blocks back to back" % self.N)
         self.widths = (3, 3 * sh_coeffs, 1, 3, 4)
         self.stream = torch.cuda.Stream(device=arena._buf.device)
         self._events = [torch.cuda.Event() for _ in range(2 * max(self.n_chunks, 1))]

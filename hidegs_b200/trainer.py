@@ -62,8 +62,8 @@ class _ActivateParams(torch.autograd.Function):
     def forward(ctx, xyz, features, opacity_raw, scaling_raw, rotation_raw, owner):
         N = xyz.size(0)
         dev = xyz.device
-        act = torch.empty(N * 8, dtype=torch.float32, device=dev)
-        scaling, rotation, opacity = act[:3 * N].view(N, 3), act[3 * N:7 * N].view(N, 4), act[7 * N:].view(N, 1)
+        act = torch.empty(N * 8, dtype=torch.float32, device=dev)  # rotation first: float4 rows stay 16-byte aligned
+        rotation, scaling, opacity = act[:4 * N].view(N, 4), act[4 * N:7 * N].view(N, 3), act[7 * N:].view(N, 1)
         with torch.cuda.device(dev):
             rc = _G().hg_activate_params(scaling_raw.data_ptr(), rotation_raw.data_ptr(), opacity_raw.data_ptr(), N,
                                          scaling.data_ptr(), rotation.data_ptr(), opacity.data_ptr(),
@@ -135,19 +135,24 @@ class GaussianParams:
         dev = xyz.device
         N = xyz.size(0)
         self.N = N
-        width = sum(w for _, w in GROUPS)
-        self.param_arena = torch.empty(N * width, dtype=torch.float32, device=dev)
+        # every group starts on a multiple of 4 floats (16 bytes): the fused kernels move rotation / feature rows as
+        # float4 and the in-fabric exchange works on 16-byte units, for ANY Gaussian count (pad floats stay zero)
+        starts, total = {}, 0
+        for name, w in GROUPS:
+            starts[name] = total
+            total += (N * w + 3) // 4 * 4
+        self.param_arena = torch.zeros(total, dtype=torch.float32, device=dev)
         # the gradient arena is born where the per-step exchange wants it: multicast symmetric memory when the ranks
         # share an NVSwitch (in-fabric all-reduce kernel), a plain tensor otherwise (NCCL / gloo all-reduce)
         self.exchange = None
         if dist.is_initialized() and dist.get_world_size() > 1 and dev.type == "cuda":
-            self.grad_arena, self.exchange = parallel.make_exchange_arena(N * width, dev)
+            self.grad_arena, self.exchange = parallel.make_exchange_arena(total, dev)
         else:
-            self.grad_arena = torch.zeros(N * width, dtype=torch.float32, device=dev)
+            self.grad_arena = torch.zeros(total, dtype=torch.float32, device=dev)
         src = dict(xyz=xyz, features=features.reshape(N, -1), opacity=opacity_logit, scaling=scaling_log, rotation=rotation)
         self.leaves, self.slices = {}, {}
-        off = 0
         for name, w in GROUPS:
+            off = starts[name]
             sl = slice(off, off + N * w)
             self.slices[name] = sl
             self.param_arena[sl].view(N, w).copy_(src[name].reshape(N, w))
@@ -155,7 +160,6 @@ class GaussianParams:
             leaf = self.param_arena[sl].view(shape).requires_grad_(True)
             leaf.grad = self.grad_arena[sl].view(shape)
             self.leaves[name] = leaf
-            off += N * w
         self._xyz, self._features = self.leaves["xyz"], self.leaves["features"]
         self._opacity, self._scaling, self._rotation = self.leaves["opacity"], self.leaves["scaling"], self.leaves["rotation"]
         self.active_sh_degree = self.max_sh_degree = sh_degree
@@ -263,7 +267,7 @@ class ArenaAdam:
 
 class ViewShardedTrainer:
     def __init__(self, params: GaussianParams, background, opt=OptimizationParams, pipe=PipelineParams, group=None,
-                 sparse_adam=True, densification_stats=False, cache_ground_truth=False):
+                 sparse_adam=True, densification_stats=False, cache_ground_truth=False, start_iteration=0):
         self.params, self.bg, self.opt, self.pipe, self.group = params, background, opt, pipe, group
         self.adam = ArenaAdam(params, opt)
         # the reference steps its optimiser on the rows that were visible (`optimizer.step(relevant)`, OurAdam.py:106)
@@ -279,7 +283,9 @@ class ViewShardedTrainer:
             self.xyz_gradient_accum = torch.zeros((params.N, 1), device=dev)
             self.denom = torch.zeros((params.N, 1), device=dev)
             self.max_radii2D = torch.zeros(params.N, device=dev)
-        self.iteration = 0
+        # the frequency / scale regulariser switches on at opt.freq_warmup_iterations, as the reference's
+        # frequency_regularization_pyramid_scale(iteration, warmup_iterations=1000) does; `start_iteration` resumes a run
+        self.iteration = int(start_iteration)
         # autograd-free executor of a view (view_step_direct); HG_TRAINER_DIRECT=0 keeps the autograd path
         import os
         self.direct = params.fused and os.environ.get("HG_TRAINER_DIRECT", "1") != "0"
@@ -429,11 +435,9 @@ class ViewShardedTrainer:
         for view in views:
             cam, gt = view[0], view[1]
             if getattr(self, "direct", False):
-                loss, pkg = self.view_step_direct(cam, gt, self.iteration + self.opt.freq_warmup_iterations,
-                                                  view[2] if len(view) > 2 else None)
+                loss, pkg = self.view_step_direct(cam, gt, self.iteration, view[2] if len(view) > 2 else None)
             else:
-                loss, pkg = self.view_loss(cam, gt, self.iteration + self.opt.freq_warmup_iterations,
-                                           view[2] if len(view) > 2 else None)
+                loss, pkg = self.view_loss(cam, gt, self.iteration, view[2] if len(view) > 2 else None)
                 loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             if self.sparse_adam:
@@ -455,7 +459,12 @@ class ViewShardedTrainer:
                 dist.all_reduce(self.params.grad_arena, op=dist.ReduceOp.SUM, group=self.group)
             if self.sparse_adam:  # union of the ranks' visible sets
                 dist.all_reduce(self.visible, op=dist.ReduceOp.MAX, group=self.group)
-            n_views = total_views if total_views is not None else n_views * self.world
+            if total_views is not None:
+                n_views = total_views
+            else:  # ranks may hold uneven shards of views[rank::world]: count what was really rendered
+                cnt = torch.tensor([float(n_views)], device=self.params.grad_arena.device)
+                dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
+                n_views = int(round(float(cnt.item())))
         self.adam.step(grad_scale=1.0 / max(n_views, 1), visible_mask=self.visible if self.sparse_adam else None)
         return total
 

@@ -134,6 +134,23 @@ HG_API int hg_interpolation_weights(const int32_t *indices, int32_t n, float tar
                                     const float *boxes, float vx, float vy, float vz, float *ts, int32_t *kids,
                                     void *stream);
 
+/* Parent interpolation of a hierarchy cut — the `interp_python` branch of render_post
+ * (gaussian_renderer/__init__.py:278-318): for e < E, out[e] = ts[e] * x[render_indices[e]] + (1 - ts[e]) *
+ * x[parent_indices[e]] for means3D [N,3], scales [N,3], rotations [N,4] (the parent's quaternion negated when its dot
+ * product with the child's is negative), opacity [N,1] and shs [N,M,3]; rows E..E+S-1 are the model's last S rows
+ * (skybox).  Negative indices wrap like torch indexing.  Outputs hold E+S rows.  The backward ACCUMULATES (atomics)
+ * into d_* [N,...], which the caller zero-fills; any g_x / d_x pair may be NULL. */
+HG_API int hg_hier_interpolate(const float *means3D, const float *scales, const float *rotations, const float *opacity,
+                               const float *shs, int64_t N, int32_t M, const int32_t *render_indices,
+                               const int32_t *parent_indices, const float *ts, int64_t E, int64_t S,
+                               float *out_means3D, float *out_scales, float *out_rotations, float *out_opacity,
+                               float *out_shs, void *stream);
+HG_API int hg_hier_interpolate_backward(const float *rotations, int64_t N, int32_t M, const int32_t *render_indices,
+                                        const int32_t *parent_indices, const float *ts, int64_t E, int64_t S,
+                                        const float *g_means3D, const float *g_scales, const float *g_rotations,
+                                        const float *g_opacity, const float *g_shs, float *d_means3D, float *d_scales,
+                                        float *d_rotations, float *d_opacity, float *d_shs, void *stream);
+
 /* Mean squared distance of every point to its 3 nearest neighbours (exact).  points [N,3] -> out [N].
  * workspace: hg_dist2_knn3_workspace_bytes(N) bytes.  No host synchronisation. */
 HG_API size_t hg_dist2_knn3_workspace_bytes(int64_t N);

@@ -36,16 +36,21 @@ def test_nvls_is_not_claimed_without_a_process_group():
 def test_in_fabric_allreduce_matches_nccl(cuda_device):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs behind an NVSwitch")
+    world = torch.cuda.device_count()  # every GPU of the box (2, 4 or 8 ranks)
     env = dict(os.environ, PYTHONPATH=ROOT)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "exchange_probe.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     out = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
     if not out["nvls"]:
         pytest.skip("no multicast (NVLS) support on this box")
-    for i in range(3):  # same bits as NCCL's sum at world 2 (two addends: the order cannot matter), identical replicas
-        assert out["max_abs_err_%d" % i] == 0.0 and out["replicas_identical_%d" % i]
+    assert out["world"] == world
+    for i in range(3):
+        # identical replicas at any world size; same bits as NCCL's sum at world 2 (two addends: the order cannot
+        # matter), within fp32 summation-order noise of it (59M standard-normal values, |sum| <~ 6 sqrt(world)) beyond
+        assert out["replicas_identical_%d" % i]
+        assert out["max_abs_err_%d" % i] <= (0.0 if world == 2 else 1e-5), out
 
 
 def test_overlap_helper_ranges_cover_the_soa_arena_once():

@@ -79,6 +79,11 @@ def measure(dev, iters=20, warmup=5, cpu=True, noise=0.002, cpu_iters=2):
         return run
 
     out["gpu_ms"] = round(_events(full, iters, warmup), 4)
+    from hidegs_b200 import _lib
+    torch.cuda.synchronize()
+    _lib.lib().hg_reset_launch_count()
+    full()
+    out["gpu_launches"] = int(_lib.lib().hg_launch_count())  # this library's kernels in one forward + backward
     out["gpu_loss_value"] = float(full().item())
     out["gpu_ms_parts"] = {
         "l1": round(_events(only(lambda: lu.l1_loss(render, gt)), iters, 2), 4),

@@ -19,7 +19,7 @@ def main():
     cams = [syn.uav_camera(i, (j + i) % 8, width=W, height=H).to(dev) for i in range(8) for j in range(8)][:8]
     gts = [g.to(dev) for g in bench.make_gt_images(8, dev)]
     params = tr.GaussianParams.from_scene(scene, dev, spatial_order=True)
-    t = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev), cache_ground_truth=True)
+    t = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev), cache_ground_truth=True, start_iteration=1000)
     views = list(zip(cams, gts))
     for _ in range(3):
         t.step(views)

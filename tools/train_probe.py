@@ -33,7 +33,7 @@ def main():
         cams = [bench.camera_for(r, 0).to(dev) for r in range(a.views)]
     gts = [g.to(dev) for g in bench.make_gt_images(a.views, dev)]
     params = tr.GaussianParams.from_scene(scene, dev, spatial_order=bool(a.spatial))
-    t = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev))
+    t = tr.ViewShardedTrainer(params, torch.zeros(3, device=dev), start_iteration=1000)
     o = t.opt
     names = ("zero_grad", "render_fwd", "loss_fwd", "backward", "adam")
     acc = {k: 0.0 for k in names}
