@@ -232,7 +232,9 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
     # view-sharded trainer can all-reduce `arena[:59 N]` in place without a pack kernel.
     widths = (("means3D", 3), ("sh", 3 * M), ("opacity", 1), ("scales", 3), ("rotations", 4), ("means2D", 3),
               ("colors", 3), ("cov3D", 6), ("all_map", 5), ("invdepths", 1 if has_depth_grad else 0))
-    total = fullP * sum(w for _, w in widths)
+    # (every block starts on a multiple of 4 floats, so that the float4 paths of the backward — SH staging, the SH sink —
+    # see 16-byte aligned rows for any Gaussian count; with fullP % 4 == 0 the blocks are back to back)
+    total = sum(_up(fullP * w, 4) for _, w in widths)
     arena = _gradient_arena_provider(total, dev) if _gradient_arena_provider is not None else None
     if arena is None:
         arena = (torch.zeros if prezero else torch.empty)((total,), dtype=torch.float32, device=dev)
@@ -245,7 +247,7 @@ def rasterize_gaussians_backward(background, all_map_pixels, indices, parent_ind
     g, off = {}, 0
     for name, w in widths:
         g[name] = arena[off:off + fullP * w].view(fullP, w)
-        off += fullP * w
+        off += _up(fullP * w, 4)
     dL_dmeans3D, dL_dmeans2D, dL_dcolors, dL_dall_map = g["means3D"], g["means2D"], g["colors"], g["all_map"]
     dL_dopacity, dL_dcov3D, dL_dscales, dL_drotations = g["opacity"], g["cov3D"], g["scales"], g["rotations"]
     dL_dsh = g["sh"].view(fullP, M, 3)
