@@ -7,7 +7,7 @@ EXPORTED_SYMBOLS = (
     "hg_reduce_workspace_bytes", "hg_l1_loss", "hg_l2_loss", "hg_training_image_grad", "hg_ssim_workspace_bytes", "hg_ssim", "hg_ssim_backward",
     "hg_img_grad_weight_workspace_bytes", "hg_img_grad_weight", "hg_lncc", "hg_lncc_backward",
     "hg_scale_reg_workspace_bytes", "hg_scale_reg", "hg_fft2_workspace_bytes", "hg_fft2_r2c", "hg_fft2_c2r",
-    "hg_freq_loss_workspace_bytes", "hg_freq_loss", "hg_freq_gt_state_bytes", "hg_freq_gt_prepare", "hg_freq_loss_cached", "hg_hf_mask_workspace_bytes", "hg_hf_mask",
+    "hg_freq_loss_workspace_bytes", "hg_freq_loss", "hg_freq_forward", "hg_freq_backward", "hg_freq_gt_state_bytes", "hg_freq_gt_prepare", "hg_freq_loss_cached", "hg_hf_mask_workspace_bytes", "hg_hf_mask",
 )
 FREQ_STATS = 24
 _ready = False
@@ -38,6 +38,8 @@ def lib():
         "hg_fft2_c2r": (ctypes.c_int, [vp, i32, i32, vp, ctypes.c_int, vp, vp]),
         "hg_freq_loss_workspace_bytes": (sz, [i32, i32, i32]),
         "hg_freq_loss": (ctypes.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+        "hg_freq_forward": (ctypes.c_int, [vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, vp, vp]),
+        "hg_freq_backward": (ctypes.c_int, [vp, i32, i32, i32, i32, vp, vp, vp, vp]),
         "hg_freq_gt_state_bytes": (sz, [i32, i32, i32]),
         "hg_freq_gt_prepare": (ctypes.c_int, [vp, i32, i32, i32, vp, vp]),
         "hg_freq_loss_cached": (ctypes.c_int, [vp, vp, i32, i32, i32, vp, vp, vp, vp]),

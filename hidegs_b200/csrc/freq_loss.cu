@@ -9,6 +9,8 @@
 // (torch.clamp passes gradient only inside [min, max]; torch.min(a, b) splits it on ties; angle/abs
 // have zero gradient at 0).
 //
+// (Pipeline: see "fused frequency-regulariser pipeline" below — six launches forward + backward.)
+//
 // FFT: Stockham autosort in shared memory, radix 4/2/3/5 butterflies (1080 x 1920 and its pyramid
 // factor as 2^a 3^b 5^c) plus a generic O(R^2) butterfly for other prime factors, twiddles from a per-length
 // table (host double precision, L1-resident).  Rows: one CTA per PAIR of image rows (two real rows ride one
@@ -383,36 +385,30 @@ int fft2_c2r(float2* spec, int H, int W, float scale, float* img, cudaStream_t s
   return HG_OK;
 }
 
-// =============================================================== pyramid / spatial terms
-__global__ void gray_kernel(const float* __restrict__ img, int64_t hw, float* __restrict__ gray) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < hw) gray[i] = (__ldg(img + i) + __ldg(img + hw + i) + __ldg(img + 2 * hw + i)) / 3.0f;
-}
+// =============================================================== fused frequency-regulariser pipeline
+//
+// The whole regulariser is six launches (nine with the ground-truth-only high-frequency mask), every intermediate is
+// produced by the kernel that has its inputs on chip:
+//
+//   forward   pyramid_kernel        RGB -> gray pyramid of both images (3 levels from one 40x40 tile in shared memory),
+//                                   Sobel / Laplacian sums of all levels, the ground truth's edge score (hf mask)
+//             fft_rows_jobs_kernel  row transforms of every level and image in ONE launch (clamp on load, equal work per
+//                                   CTA: 1 / 2 / 4 row pairs at levels 0 / 1 / 2)
+//             fft_cols_jobs_kernel  column transforms of the rendered AND the ground-truth spectrum of the same columns
+//                                   in one CTA -> the spectral sums come out of shared memory (no spectrum is re-read);
+//                                   the hf job does forward columns -> high-pass -> inverse columns without leaving the
+//                                   SM; the last CTA to finish reduces all partials (fixed order, double) and runs the
+//                                   scalar epilogue (no reduce / finalize launches)
+//   backward  spectral_grad_cols_kernel   spectral gradient formed on load + inverse columns
+//             fft_rows_c2r_jobs_kernel    inverse rows of all levels, clamp gate on store
+//             spatial_grad_rgb_kernel     Sobel / Laplacian gradient of all levels + un-pooling down the pyramid +
+//                                         gray -> RGB + the upstream scalar, one pass over the image
+//   hf mask   fft_rows_c2r_jobs_kernel (|.| + max), hf_combine_kernel (score + min / max), hf_threshold_kernel (mask + count)
+constexpr int kMaxLevels = 3;
+constexpr int kT0 = 32;   // level-0 tile edge of the image-space kernels
+constexpr int kImgThreads = 256;
 
-__global__ void pool_kernel(const float* __restrict__ src, int Ws, int Hd, int Wd, float* __restrict__ dst) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= Wd || y >= Hd) return;
-  const float* p = src + (size_t)(2 * y) * Ws + 2 * x;
-  dst[(size_t)y * Wd + x] = (p[0] + p[1] + p[Ws] + p[Ws + 1]) * 0.25f;
-}
-
-__device__ __forceinline__ float block_sum(float v, float* smem, int tid, int nthreads) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int lane = tid & 31, warp = tid >> 5;
-  if (lane == 0) smem[warp] = v;
-  __syncthreads();
-  const int nw = (nthreads + 31) >> 5;
-  v = (tid < nw) ? smem[tid] : 0.f;
-  if (warp == 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  }
-  __syncthreads();
-  return v;
-}
-
-// Per-level control block written by the finalize kernel and read by the gradient kernels.
+// Per-level control block written by the epilogue and read by the gradient kernels.
 struct LevelCtl {
   float c_sobel, c_lap;      // coefficients of d(loss)/d(response) = c * response
   float c_mag, c_phase;      // spectral coefficients
@@ -420,69 +416,221 @@ struct LevelCtl {
   float band_count[4];
 };
 
-constexpr int kSpTile = 16;
-// d = gray_r - gray_g (zero outside), responses of Sobel-x / Sobel-y / Laplacian (cross-correlation, zero pad 1)
-__device__ __forceinline__ void responses(const float (*d)[kSpTile + 4 + 1], int r, int c, float& sx, float& sy,
-                                          float& lp) {
-  // d[r][c] is the centre; neighbours at +-1
-  const float a00 = d[r - 1][c - 1], a01 = d[r - 1][c], a02 = d[r - 1][c + 1];
-  const float a10 = d[r][c - 1], a11 = d[r][c], a12 = d[r][c + 1];
-  const float a20 = d[r + 1][c - 1], a21 = d[r + 1][c], a22 = d[r + 1][c + 1];
+// responses of Sobel-x / Sobel-y / Laplacian (cross-correlation, zero pad 1) around d[0]; rows `stride` floats apart
+__device__ __forceinline__ void responses_at(const float* d, int stride, float& sx, float& sy, float& lp) {
+  const float a00 = d[-stride - 1], a01 = d[-stride], a02 = d[-stride + 1];
+  const float a10 = d[-1], a11 = d[0], a12 = d[1];
+  const float a20 = d[stride - 1], a21 = d[stride], a22 = d[stride + 1];
   sx = -a00 + a02 - 2.f * a10 + 2.f * a12 - a20 + a22;
   sy = -a00 - 2.f * a01 - a02 + a20 + 2.f * a21 + a22;
   lp = -a01 - a10 + 4.f * a11 - a12 - a21;
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(kSpTile * kSpTile)
-spatial_kernel(const float* __restrict__ gr, const float* __restrict__ gg, int H, int W,
-               double* __restrict__ partial, const LevelCtl* __restrict__ ctl, float* __restrict__ dgray) {
-  __shared__ float d[kSpTile + 4][kSpTile + 4 + 1];
-  __shared__ float rx[kSpTile + 2][kSpTile + 2 + 1], ry[kSpTile + 2][kSpTile + 2 + 1], rl[kSpTile + 2][kSpTile + 2 + 1];
-  __shared__ float red[32];
-  const int x0 = blockIdx.x * kSpTile, y0 = blockIdx.y * kSpTile;
-  const int tid = threadIdx.y * kSpTile + threadIdx.x;
-  for (int i = tid; i < (kSpTile + 4) * (kSpTile + 4); i += kSpTile * kSpTile) {
-    const int r = i / (kSpTile + 4), c = i % (kSpTile + 4);
-    const int y = y0 + r - 2, x = x0 + c - 2;
-    const bool in = y >= 0 && y < H && x >= 0 && x < W;
-    d[r][c] = in ? (__ldg(gr + (size_t)y * W + x) - __ldg(gg + (size_t)y * W + x)) : 0.f;
-  }
-  __syncthreads();
-  if (!GRAD) {
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    float sx = 0.f, sy = 0.f, lp = 0.f;
-    if (x < W && y < H) responses(d, threadIdx.y + 2, threadIdx.x + 2, sx, sy, lp);
-    const float s0 = block_sum(sx * sx, red, tid, kSpTile * kSpTile);
-    const float s1 = block_sum(sy * sy, red, tid, kSpTile * kSpTile);
-    const float s2 = block_sum(lp * lp, red, tid, kSpTile * kSpTile);
-    if (tid == 0) {
-      double* p = partial + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
-      p[0] = s0; p[1] = s1; p[2] = s2;
-    }
-    return;
-  }
-  // responses on the tile + halo 1, scaled by their loss coefficients, zero outside the image
-  const float cs = ctl->c_sobel, cl = ctl->c_lap;
-  for (int i = tid; i < (kSpTile + 2) * (kSpTile + 2); i += kSpTile * kSpTile) {
-    const int r = i / (kSpTile + 2), c = i % (kSpTile + 2);
-    const int y = y0 + r - 1, x = x0 + c - 1;
-    float sx = 0.f, sy = 0.f, lp = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) responses(d, r + 1, c + 1, sx, sy, lp);
-    rx[r][c] = cs * sx; ry[r][c] = cs * sy; rl[r][c] = cl * lp;
-  }
-  __syncthreads();
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= W || y >= H) return;
-  // dL/dd(p) = sum_{u,v} K[u][v] * R(p - (u-1, v-1))
-  const int r = threadIdx.y + 1, c = threadIdx.x + 1;
-  const float gx = -rx[r + 1][c + 1] + rx[r + 1][c - 1] - 2.f * rx[r][c + 1] + 2.f * rx[r][c - 1] - rx[r - 1][c + 1] + rx[r - 1][c - 1];
-  const float gy = -ry[r + 1][c + 1] - 2.f * ry[r + 1][c] - ry[r + 1][c - 1] + ry[r - 1][c + 1] + 2.f * ry[r - 1][c] + ry[r - 1][c - 1];
-  const float gl = -rl[r + 1][c] - rl[r][c + 1] + 4.f * rl[r][c] - rl[r][c - 1] - rl[r - 1][c];
-  dgray[(size_t)y * W + x] += gx + gy + gl;
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-// =============================================================== spectral terms
+// ---------------------------------------------------------------- image space, forward
+struct PyrArgs {
+  const float* rgb[2];            // [0] rendered (or the only image), [1] ground truth; NULL: gray[i][0] is read instead
+  float* gray[2][kMaxLevels];     // gray pyramid per image (written for images that have an rgb source)
+  int n_images, levels;
+  int H[kMaxLevels], W[kMaxLevels];
+  double* partial;                // [tiles][9] Sobel-x / Sobel-y / Laplacian sums of squares per level, or NULL
+  float* hf_score;                // [H][W] 0.6 |grad| + 0.4 |lap| of image `hf_src`, or NULL
+  int hf_src;
+  unsigned* counters;             // 8 words zeroed by CTA 0 (tickets of the later last-block reductions)
+};
+
+__global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
+  __shared__ float g0[2][kT0 + 8][kT0 + 9];
+  __shared__ float g1[2][kT0 / 2 + 4][kT0 / 2 + 5];
+  __shared__ float g2[2][kT0 / 4 + 2][kT0 / 4 + 3];
+  __shared__ float red[kImgThreads / 32][9];
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid < 8 && a.counters) a.counters[tid] = 0u;
+  const int x0 = blockIdx.x * kT0, y0 = blockIdx.y * kT0;
+  const int H0 = a.H[0], W0 = a.W[0];
+  const size_t hw0 = (size_t)H0 * W0;
+  constexpr int E0 = kT0 + 8;
+  for (int i = tid; i < E0 * E0; i += kImgThreads) {
+    const int r = i / E0, c = i - r * E0;
+    const int y = y0 + r - 4, x = x0 + c - 4;
+    const bool in = y >= 0 && y < H0 && x >= 0 && x < W0;
+    for (int im = 0; im < a.n_images; ++im) {
+      float v = 0.f;
+      if (in) {
+        const size_t p = (size_t)y * W0 + x;
+        if (a.rgb[im]) v = (__ldg(a.rgb[im] + p) + __ldg(a.rgb[im] + hw0 + p) + __ldg(a.rgb[im] + 2 * hw0 + p)) / 3.0f;
+        else v = __ldg(a.gray[im][0] + p);
+      }
+      g0[im][r][c] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kT0 * kT0; i += kImgThreads) {
+    const int r = i / kT0, c = i - r * kT0;
+    const int y = y0 + r, x = x0 + c;
+    if (y < H0 && x < W0)
+      for (int im = 0; im < a.n_images; ++im)
+        if (a.rgb[im]) a.gray[im][0][(size_t)y * W0 + x] = g0[im][r + 4][c + 4];
+  }
+  const int H1 = a.levels > 1 ? a.H[1] : 0, W1 = a.levels > 1 ? a.W[1] : 0;
+  const int H2 = a.levels > 2 ? a.H[2] : 0, W2 = a.levels > 2 ? a.W[2] : 0;
+  if (a.levels > 1) {  // 2x2 average pooling (F.avg_pool2d(kernel 2, stride 2)), halo 2
+    constexpr int E1 = kT0 / 2 + 4;
+    for (int i = tid; i < E1 * E1; i += kImgThreads) {
+      const int r = i / E1, c = i - r * E1;
+      const int Y = (y0 >> 1) + r - 2, X = (x0 >> 1) + c - 2;
+      const bool ok = Y >= 0 && Y < H1 && X >= 0 && X < W1;
+      for (int im = 0; im < a.n_images; ++im)
+        g1[im][r][c] = ok ? (g0[im][2 * r][2 * c] + g0[im][2 * r][2 * c + 1] + g0[im][2 * r + 1][2 * c] +
+                             g0[im][2 * r + 1][2 * c + 1]) * 0.25f : 0.f;
+    }
+    __syncthreads();
+    {
+      const int r = tid >> 4, c = tid & 15;
+      const int Y = (y0 >> 1) + r, X = (x0 >> 1) + c;
+      if (Y < H1 && X < W1)
+        for (int im = 0; im < a.n_images; ++im)
+          if (a.rgb[im]) a.gray[im][1][(size_t)Y * W1 + X] = g1[im][r + 2][c + 2];
+    }
+  }
+  if (a.levels > 2) {
+    constexpr int E2 = kT0 / 4 + 2;
+    for (int i = tid; i < E2 * E2; i += kImgThreads) {
+      const int r = i / E2, c = i - r * E2;
+      const int Y = (y0 >> 2) + r - 1, X = (x0 >> 2) + c - 1;
+      const bool ok = Y >= 0 && Y < H2 && X >= 0 && X < W2;
+      for (int im = 0; im < a.n_images; ++im)
+        g2[im][r][c] = ok ? (g1[im][2 * r][2 * c] + g1[im][2 * r][2 * c + 1] + g1[im][2 * r + 1][2 * c] +
+                             g1[im][2 * r + 1][2 * c + 1]) * 0.25f : 0.f;
+    }
+    __syncthreads();
+    if (tid < 64) {
+      const int r = tid >> 3, c = tid & 7;
+      const int Y = (y0 >> 2) + r, X = (x0 >> 2) + c;
+      if (Y < H2 && X < W2)
+        for (int im = 0; im < a.n_images; ++im)
+          if (a.rgb[im]) a.gray[im][2][(size_t)Y * W2 + X] = g2[im][r + 1][c + 1];
+    }
+  }
+  // ---- ground-truth edge score of detect_true_high_frequency_regions (:1180-1207)
+  if (a.hf_score) {
+    const int s = a.hf_src;
+    for (int i = tid; i < kT0 * kT0; i += kImgThreads) {
+      const int r = i / kT0, c = i - r * kT0;
+      const int y = y0 + r, x = x0 + c;
+      if (y < H0 && x < W0) {
+        float sx, sy, lp;
+        responses_at(&g0[s][r + 4][c + 4], kT0 + 9, sx, sy, lp);
+        a.hf_score[(size_t)y * W0 + x] = 0.6f * sqrtf(sx * sx + sy * sy + 1e-8f) + 0.4f * fabsf(lp);
+      }
+    }
+  }
+  if (!a.partial || a.n_images < 2) return;
+  // ---- Sobel / Laplacian of d = gray_rendered - gray_gt at every level (d = 0 outside the image)
+  __syncthreads();
+  for (int i = tid; i < E0 * E0; i += kImgThreads) {
+    const int r = i / E0, c = i - r * E0;
+    g0[0][r][c] -= g0[1][r][c];
+  }
+  if (a.levels > 1)
+    for (int i = tid; i < (kT0 / 2 + 4) * (kT0 / 2 + 4); i += kImgThreads) {
+      const int r = i / (kT0 / 2 + 4), c = i - r * (kT0 / 2 + 4);
+      g1[0][r][c] -= g1[1][r][c];
+    }
+  if (a.levels > 2)
+    for (int i = tid; i < (kT0 / 4 + 2) * (kT0 / 4 + 2); i += kImgThreads) {
+      const int r = i / (kT0 / 4 + 2), c = i - r * (kT0 / 4 + 2);
+      g2[0][r][c] -= g2[1][r][c];
+    }
+  __syncthreads();
+  float acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.f;
+  for (int i = tid; i < kT0 * kT0; i += kImgThreads) {
+    const int r = i / kT0, c = i - r * kT0;
+    if (y0 + r < H0 && x0 + c < W0) {
+      float sx, sy, lp;
+      responses_at(&g0[0][r + 4][c + 4], kT0 + 9, sx, sy, lp);
+      acc[0] += sx * sx; acc[1] += sy * sy; acc[2] += lp * lp;
+    }
+  }
+  if (a.levels > 1) {
+    const int r = tid >> 4, c = tid & 15;
+    if ((y0 >> 1) + r < H1 && (x0 >> 1) + c < W1) {
+      float sx, sy, lp;
+      responses_at(&g1[0][r + 2][c + 2], kT0 / 2 + 5, sx, sy, lp);
+      acc[3] = sx * sx; acc[4] = sy * sy; acc[5] = lp * lp;
+    }
+  }
+  if (a.levels > 2 && tid < 64) {
+    const int r = tid >> 3, c = tid & 7;
+    if ((y0 >> 2) + r < H2 && (x0 >> 2) + c < W2) {
+      float sx, sy, lp;
+      responses_at(&g2[0][r + 1][c + 1], kT0 / 4 + 3, sx, sy, lp);
+      acc[6] = sx * sx; acc[7] = sy * sy; acc[8] = lp * lp;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) {
+    const float v = warp_sum(acc[q]);
+    if ((tid & 31) == 0) red[tid >> 5][q] = v;
+  }
+  __syncthreads();
+  if (tid < 9) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kImgThreads / 32; ++w) v += red[w][tid];
+    a.partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 9 + tid] = (double)v;
+  }
+}
+
+// ---------------------------------------------------------------- rows, forward (all levels / images in one launch)
+constexpr int kMaxRowJobs = 7;
+struct RowJob {
+  const float* src;   // [H][W] real
+  float2* dst;        // [H][W/2+1]
+  int H, W, clamp01, pairs, cta_begin;
+  Plan plan;
+};
+struct RowArgs { int n_jobs; RowJob job[kMaxRowJobs]; };
+
+__global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const RowArgs a) {
+  extern __shared__ float2 sm[];
+  int j = 0;
+  for (int k = 1; k < a.n_jobs; ++k)
+    if ((int)blockIdx.x >= a.job[k].cta_begin) j = k;
+  const RowJob& J = a.job[j];
+  const int W = J.W, H = J.H, pairs = J.pairs;
+  const int p0 = ((int)blockIdx.x - J.cta_begin) * pairs;
+  float2 *bufa = sm, *bufb = sm + pairs * W;
+  for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
+    const int pr = i / W, x = i - pr * W;
+    const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
+    float v0 = r0 < H ? __ldg(J.src + (size_t)r0 * W + x) : 0.f;
+    float v1 = r1 < H ? __ldg(J.src + (size_t)r1 * W + x) : 0.f;
+    if (J.clamp01) { v0 = fminf(fmaxf(v0, 0.f), 1.f); v1 = fminf(fmaxf(v1, 0.f), 1.f); }
+    bufa[i] = make_float2(v0, v1);
+  }
+  __syncthreads();
+  const float2* z = fft_smem(bufa, bufb, J.plan, pairs);
+  const int Wh = W / 2 + 1;
+  for (int i = threadIdx.x; i < pairs * Wh; i += blockDim.x) {
+    const int pr = i / Wh, k = i - pr * Wh;
+    const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
+    if (r0 >= H) continue;
+    const float2* zz = z + pr * W;
+    const float2 p = zz[k], q = zz[k == 0 ? 0 : W - k];
+    J.dst[(size_t)r0 * Wh + k] = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));
+    if (r1 < H) J.dst[(size_t)r1 * Wh + k] = make_float2(0.5f * (p.y + q.y), -0.5f * (p.x - q.x));
+  }
+}
+
+// ---------------------------------------------------------------- spectral terms
 __device__ __forceinline__ int signed_freq(int k, int n) { return (k < (n + 1) / 2) ? k : k - n; }
 
 __device__ __forceinline__ int band_of(int ky, int kx, int H, int W) {
@@ -495,112 +643,69 @@ __device__ __forceinline__ int band_of(int ky, int kx, int H, int W) {
   return -1;
 }
 
-constexpr int kSpecVals = 14;  // mag, phase, band_r[4], band_r - band_g [4], count[4]
-__global__ void __launch_bounds__(256)
-spectral_sums_kernel(const float2* __restrict__ fr, const float2* __restrict__ fg, int H, int W,
-                     double* __restrict__ partial) {
-  __shared__ float red[32];
-  const int Wh = W / 2 + 1;
-  float acc[kSpecVals];
-#pragma unroll
-  for (int i = 0; i < kSpecVals; ++i) acc[i] = 0.f;
-  const int64_t n = (int64_t)H * Wh;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
-    const float w = (kx == 0 || (2 * kx == W)) ? 1.f : 2.f;  // Hermitian twin outside the half spectrum
-    const float2 a = fr[i], b = fg[i];
-    const float ma = hypotf(a.x, a.y), mb = hypotf(b.x, b.y);
-    const float dl = logf(ma + 1e-6f) - logf(mb + 1e-6f);
-    acc[0] += w * dl * dl;
-    const float pa = atan2f(a.y, a.x), pb = atan2f(b.y, b.x);
-    const float ad = fabsf(pa - pb);
-    acc[1] += w * fminf(ad, 2.f * kPi - ad);
-    const int band = band_of(ky, kx, H, W);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (band == q) { acc[2 + q] += w * ma; acc[6 + q] += w * (ma - mb); acc[10 + q] += w; }  // difference summed directly: Er - Eg cancels
-  }
-#pragma unroll
-  for (int q = 0; q < kSpecVals; ++q) {
-    const float s = block_sum(acc[q], red, threadIdx.x, 256);
-    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * kSpecVals + q] = (double)s;
-  }
-}
-
-// band energies of a single spectrum (debug_info['freq_band_energies'] of the level-0 GT)
-__global__ void __launch_bounds__(256)
-band_energy_kernel(const float2* __restrict__ f, int H, int W, double* __restrict__ partial) {
-  __shared__ float red[32];
-  const int Wh = W / 2 + 1;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int64_t n = (int64_t)H * Wh;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
-    const float w = (kx == 0 || (2 * kx == W)) ? 1.f : 2.f;
-    const int band = band_of(ky, kx, H, W);
-    if (band >= 0) {
-      const float2 a = f[i];
-      const float m = hypotf(a.x, a.y);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (band == q) { acc[q] += w * m; acc[4 + q] += w; }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float s = block_sum(acc[q], red, threadIdx.x, 256);
-    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * 8 + q] = (double)s;
-  }
-}
-
-constexpr int kSumBlocks = 148 * 2;
-
-struct LevelDims { int H, W; };
-struct FreqFinalizeArgs {
-  int levels;
-  LevelDims dim[3];
-  const double* spatial_partial[3];
-  int spatial_blocks[3];
-  const double* spectral_partial[3];
-  const double* band0_partial;  // level-0 GT band energies
-  LevelCtl* ctl;
-  float* stats;
-  double* sums;  // [kFreqSums] second-stage sums
-};
-
 __device__ __forceinline__ bool within(float v, float lo, float hi) { return v >= lo && v <= hi; }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
-// Second reduction stage: block b sums one of the 3*17 per-level quantities (3 spatial + 14 spectral) or one of
-// the 8 level-0 ground-truth band sums into a.sums[b] (fixed order, double).
-constexpr int kPerLevelSums = 3 + kSpecVals;
-constexpr int kFreqSums = 3 * kPerLevelSums + 8;
-__global__ void __launch_bounds__(256) freq_reduce_kernel(FreqFinalizeArgs a) {
-  __shared__ double sm[32];
-  const int b = blockIdx.x;
-  double v = 0.0;
-  if (b < 3 * kPerLevelSums) {
-    const int l = b / kPerLevelSums, q = b - l * kPerLevelSums;
-    if (l >= a.levels) return;
-    if (q < 3) v = cta_sum_strided(a.spatial_partial[l], a.spatial_blocks[l], 3, q, sm);
-    else v = cta_sum_strided(a.spectral_partial[l], kSumBlocks, kSpecVals, q - 3, sm);
-  } else {
-    v = cta_sum_strided(a.band0_partial, kSumBlocks, 8, b - 3 * kPerLevelSums, sm);
-  }
-  if (threadIdx.x == 0) a.sums[b] = v;
-}
+// per-CTA partial sums of the column kernel: mag, phase, band_r[4], band_r - band_g [4], count[4] (the loss), then the
+// band sums [4] and counts [4] of the level-0 ground-truth spectrum (debug_info['freq_band_energies'])
+constexpr int kSpecVals = 14;
+constexpr int kColVals = kSpecVals + 8;
 
-// Scalar epilogue of compute_true_frequency_loss, and the coefficients its backward needs.
-__global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
+struct FinalizeArgs {
+  int mode;                        // 0 none, 1 loss epilogue, 2 ground-truth state (band sums only)
+  int levels;
+  int H[kMaxLevels], W[kMaxLevels];
+  const double* spatial_partial;   // [spatial_tiles][9]
+  int spatial_tiles;
+  int col_begin[kMaxLevels], col_end[kMaxLevels];  // CTAs of the column launch that hold level l's sums
+  const double* band0_in;          // cached ground truth: the 8 final band sums; NULL: reduced from the level-0 partials
+  double* band0_out;               // mode 2: the 8 final band sums
+  LevelCtl* ctl;
+  float* stats;
+  unsigned* counter;
+};
+
+// Scalar epilogue of compute_true_frequency_loss (:1293-1325, :1362-1401) and the coefficients its backward needs.
+// Runs in the last CTA of the column launch; every sum is formed in a fixed order in double.
+__device__ void freq_epilogue(const FinalizeArgs& a, const double* __restrict__ col_partial) {
+  __shared__ double sums[kMaxLevels * (3 + kSpecVals) + 8];
+  __shared__ double sm[32];
+  constexpr int kPer = 3 + kSpecVals;
+  for (int l = 0; l < a.levels; ++l) {
+    if (a.mode == 1) {
+      for (int q = 0; q < 3; ++q) {
+        const double v = cta_sum_strided(a.spatial_partial, a.spatial_tiles, 9, 3 * l + q, sm);
+        if (threadIdx.x == 0) sums[l * kPer + q] = v;
+      }
+      for (int q = 0; q < kSpecVals; ++q) {
+        const double v = cta_sum_strided(col_partial + (size_t)a.col_begin[l] * kColVals, a.col_end[l] - a.col_begin[l],
+                                         kColVals, q, sm);
+        if (threadIdx.x == 0) sums[l * kPer + 3 + q] = v;
+      }
+    }
+    if (l == 0)
+      for (int q = 0; q < 8; ++q) {
+        double v;
+        if (a.band0_in) v = a.band0_in[q];
+        else v = cta_sum_strided(col_partial + (size_t)a.col_begin[0] * kColVals, a.col_end[0] - a.col_begin[0], kColVals,
+                                 kSpecVals + q, sm);
+        if (threadIdx.x == 0) sums[kMaxLevels * kPer + q] = v;
+      }
+  }
+  __syncthreads();
   if (threadIdx.x != 0) return;
+  const double* e = sums + kMaxLevels * kPer;
+  if (a.band0_out)
+    for (int q = 0; q < 8; ++q) a.band0_out[q] = e[q];
+  if (a.mode != 1) return;
   const float w_lvl[3] = {0.1f, 0.05f, 0.025f};
   float total = 0.f;
   float lvl_raw[3] = {0, 0, 0};
   float sp_raw[3], fft_raw[3], mag_raw[3], ph_raw[3], band_raw[3];
   float ediff[3][4], cnt[3][4];
   for (int l = 0; l < a.levels; ++l) {
-    const double n = (double)a.dim[l].H * a.dim[l].W;
-    const double* s = a.sums + l * kPerLevelSums;
+    const double n = (double)a.H[l] * a.W[l];
+    const double* s = sums + l * kPer;
     const float gx = (float)(s[0] / n), gy = (float)(s[1] / n), lap = (float)(s[2] / n);
     sp_raw[l] = 0.7f * (gx + gy) + 0.3f * lap;
     const double* v = s + 3;
@@ -625,7 +730,7 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
   a.stats[0] = clampf(total, 0.f, 0.1f);
   const float g_total = within(total, 0.f, 0.1f) ? 1.f : 0.f;
   for (int l = 0; l < a.levels; ++l) {
-    const float n = (float)a.dim[l].H * (float)a.dim[l].W;
+    const float n = (float)a.H[l] * (float)a.W[l];
     const float g_level = g_total * w_lvl[l] * (within(lvl_raw[l], 0.f, 0.1f) ? 1.f : 0.f);
     const float g_sp = g_level * 0.7f * (within(sp_raw[l], 0.f, 1.f) ? 1.f : 0.f);
     const float g_fft = g_level * 0.3f * (within(fft_raw[l], 0.f, 10.f) ? 1.f : 0.f);
@@ -641,114 +746,410 @@ __global__ void freq_finalize_kernel(FreqFinalizeArgs a) {
     }
   }
   // band energies of the level-0 ground truth (debug_info)
-  const double* e = a.sums + 3 * kPerLevelSums;
   for (int q = 0; q < 4; ++q) a.stats[19 + q] = e[4 + q] > 0.0 ? (float)(e[q] / (e[4 + q] + 1e-8)) : 0.f;
 }
 
-// Gradient of the spectral loss w.r.t. the rendered spectrum, written in place over `fr`.
-__global__ void __launch_bounds__(256)
-spectral_grad_kernel(float2* __restrict__ fr, const float2* __restrict__ fg, int H, int W,
-                     const LevelCtl* __restrict__ ctl) {
-  const int Wh = W / 2 + 1;
-  const int64_t n = (int64_t)H * Wh;
-  const float c_mag = ctl->c_mag, c_phase = ctl->c_phase;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
-    const float2 a = fr[i], b = fg[i];
-    const float ma = hypotf(a.x, a.y), mb = hypotf(b.x, b.y);
-    float gre = 0.f, gim = 0.f;
-    if (ma > 0.f) {
-      float dmag = c_mag * (logf(ma + 1e-6f) - logf(mb + 1e-6f)) / (ma + 1e-6f);
-      const int band = band_of(ky, kx, H, W);
-      if (band >= 0) dmag += ctl->c_band[band];
-      gre = dmag * a.x / ma;
-      gim = dmag * a.y / ma;
-      const float pa = atan2f(a.y, a.x), pb = atan2f(b.y, b.x);
-      const float dlt = pa - pb, ad = fabsf(dlt);
-      const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
-      const float other = 2.f * kPi - ad;
-      // d min(|D|, 2pi - |D|) / dD, with torch.min's even split on ties
-      const float dw = ad < other ? sgn : (ad > other ? -sgn : 0.f);
-      const float gp = c_phase * dw / (ma * ma);
-      gre += gp * (-a.y);
-      gim += gp * a.x;
+// ---------------------------------------------------------------- columns, forward
+enum ColKind { kColPair = 0, kColPairCached = 1, kColHighpassInverse = 2, kColSingle = 3 };
+constexpr int kMaxColJobs = 5;
+struct ColJob {
+  float2* A;          // spectrum transformed in place
+  float2* B;          // second spectrum of the same level: transformed too (pair) or final (pair-cached); else NULL
+  int H, W, kind, tc, cta_begin, level;
+  Plan plan;
+};
+struct ColArgs {
+  int n_jobs;
+  ColJob job[kMaxColJobs];
+  double* partial;    // [CTAs][kColVals]
+  FinalizeArgs fin;
+};
+
+__global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const ColArgs a) {
+  extern __shared__ float2 sm[];
+  __shared__ float red[kFftThreads / 32][kColVals];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  int j = 0;
+  for (int k = 1; k < a.n_jobs; ++k)
+    if ((int)blockIdx.x >= a.job[k].cta_begin) j = k;
+  const ColJob& J = a.job[j];
+  const int H = J.H, W = J.W, Wh = W / 2 + 1, tc = J.tc, kind = J.kind;
+  const int c0 = ((int)blockIdx.x - J.cta_begin) * tc;
+  const int nc = min(tc, Wh - c0);
+  const int nseq = kind == kColPair ? 2 * tc : tc;
+  float2 *bufa = sm, *bufb = sm + (size_t)nseq * H;
+  for (int i = tid; i < H * tc; i += kFftThreads) {
+    const int y = i / tc, c = i - y * tc;
+    float2 v = make_float2(0.f, 0.f), w = v;
+    if (c < nc) {
+      v = J.A[(size_t)y * Wh + c0 + c];
+      if (kind == kColPair) w = J.B[(size_t)y * Wh + c0 + c];
     }
-    fr[i] = make_float2(gre, gim);
-  }
-}
-
-// dgray (from the inverse FFT, w.r.t. the CLAMPED gray) -> gate by the clamp and overwrite
-__global__ void clamp_gate_kernel(const float* __restrict__ gray, int64_t n, float* __restrict__ dgray) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const float g = gray[i];
-    if (!(g >= 0.f && g <= 1.f)) dgray[i] = 0.f;
-  }
-}
-
-// dgray_fine += 0.25 * dgray_coarse (avg_pool2d backward)
-__global__ void unpool_add_kernel(const float* __restrict__ dcoarse, int Hc, int Wc, int Wf, float* __restrict__ dfine) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= 2 * Wc || y >= 2 * Hc) return;
-  dfine[(size_t)y * Wf + x] += 0.25f * dcoarse[(size_t)(y >> 1) * Wc + (x >> 1)];
-}
-
-__global__ void gray_to_rgb_grad_kernel(const float* __restrict__ dgray, int64_t hw, float* __restrict__ dimg) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < hw) {
-    const float g = dgray[i] / 3.0f;
-    dimg[i] = g; dimg[hw + i] = g; dimg[2 * hw + i] = g;
-  }
-}
-
-// =============================================================== high-frequency mask
-__global__ void __launch_bounds__(kSpTile * kSpTile)
-hf_spatial_kernel(const float* __restrict__ gray, int H, int W, float* __restrict__ score) {
-  __shared__ float d[kSpTile + 4][kSpTile + 4 + 1];
-  const int x0 = blockIdx.x * kSpTile, y0 = blockIdx.y * kSpTile;
-  const int tid = threadIdx.y * kSpTile + threadIdx.x;
-  for (int i = tid; i < (kSpTile + 4) * (kSpTile + 4); i += kSpTile * kSpTile) {
-    const int r = i / (kSpTile + 4), c = i % (kSpTile + 4);
-    const int y = y0 + r - 2, x = x0 + c - 2;
-    d[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(gray + (size_t)y * W + x) : 0.f;
+    bufa[c * H + y] = v;
+    if (kind == kColPair) bufa[(tc + c) * H + y] = w;
   }
   __syncthreads();
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= W || y >= H) return;
-  float sx, sy, lp;
-  responses(d, threadIdx.y + 2, threadIdx.x + 2, sx, sy, lp);
-  score[(size_t)y * W + x] = 0.6f * sqrtf(sx * sx + sy * sy + 1e-8f) + 0.4f * fabsf(lp);
-}
-
-__global__ void highpass_kernel(float2* __restrict__ spec, int H, int W) {
-  const int Wh = W / 2 + 1;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)H * Wh) return;
-  const int ky = (int)(i / Wh), kx = (int)(i - (int64_t)ky * Wh);
-  const int fy = signed_freq(ky, H), fx = signed_freq(kx, W);
-  const float dist = sqrtf((float)(fy * fy + fx * fx));
-  const float radius = (float)((double)min(H / 2, W / 2) * 0.3);
-  if (!(dist > radius)) spec[i] = make_float2(0.f, 0.f);
-}
-
-// op 0: v = |x| -> max;  op 1: combined score -> min/max;  partial: [blocks][2]
-__global__ void __launch_bounds__(256)
-hf_reduce_kernel(float* __restrict__ hs, const float* __restrict__ spatial, const float* __restrict__ mm_in, int64_t n,
-                 int op, float* __restrict__ pmin, float* __restrict__ pmax) {
-  __shared__ float smin[8], smax[8];
-  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v;
-    if (op == 0) {
-      v = fabsf(hs[i]);
-      hs[i] = v;
-    } else {
-      float h = hs[i];
-      const float mx = mm_in[1];
-      if (mx > 1e-8f) h = h / mx;
-      v = fminf(fmaxf(0.7f * spatial[i] + 0.3f * h, 0.f), 5.0f);
-      hs[i] = v;
+  float2* r = fft_smem(bufa, bufb, J.plan, nseq);
+  if (kind == kColHighpassInverse) {
+    // high-pass of detect_true_high_frequency_regions (:1229-1243: keep dist > 0.3 * min(h//2, w//2)), then the inverse
+    // column transform (conj -> FFT -> conj) of the same columns
+    const float radius = (float)((double)min(H / 2, W / 2) * 0.3);
+    for (int i = tid; i < H * tc; i += kFftThreads) {
+      const int y = i / tc, c = i - y * tc;
+      const int fy = signed_freq(y, H), fx = signed_freq(c0 + c, W);
+      const float dist = sqrtf((float)(fy * fy + fx * fx));
+      float2 v = r[c * H + y];
+      if (!(dist > radius)) v = make_float2(0.f, 0.f);
+      v.y = -v.y;
+      r[c * H + y] = v;
     }
+    __syncthreads();
+    float2* r2 = fft_smem(r, r == bufa ? bufb : bufa, J.plan, tc);
+    for (int i = tid; i < H * tc; i += kFftThreads) {
+      const int y = i / tc, c = i - y * tc;
+      if (c < nc) {
+        float2 v = r2[c * H + y];
+        v.y = -v.y;
+        J.A[(size_t)y * Wh + c0 + c] = v;
+      }
+    }
+  } else {
+    float acc[kColVals];
+#pragma unroll
+    for (int q = 0; q < kColVals; ++q) acc[q] = 0.f;
+    const bool sums = kind != kColSingle;
+    const bool band0 = J.level == 0;
+    for (int i = tid; i < H * tc; i += kFftThreads) {
+      const int y = i / tc, c = i - y * tc;
+      if (c >= nc) continue;
+      const int kx = c0 + c;
+      const size_t p = (size_t)y * Wh + kx;
+      const float2 fa = r[c * H + y];
+      J.A[p] = fa;
+      float2 fb = make_float2(0.f, 0.f);
+      if (kind == kColPair) {
+        fb = r[(tc + c) * H + y];
+        J.B[p] = fb;
+      } else if (kind == kColPairCached) {
+        fb = J.B[p];
+      }
+      const float w = (kx == 0 || (2 * kx == W)) ? 1.f : 2.f;  // Hermitian twin outside the half spectrum
+      const int band = (sums || band0) ? band_of(y, kx, H, W) : -1;
+      if (sums) {
+        const float ma = hypotf(fa.x, fa.y), mb = hypotf(fb.x, fb.y);
+        const float dl = logf(ma + 1e-6f) - logf(mb + 1e-6f);
+        acc[0] += w * dl * dl;
+        const float pa = atan2f(fa.y, fa.x), pb = atan2f(fb.y, fb.x);
+        const float ad = fabsf(pa - pb);
+        acc[1] += w * fminf(ad, 2.f * kPi - ad);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (band == q) {
+            acc[2 + q] += w * ma;
+            acc[6 + q] += w * (ma - mb);  // difference summed directly: E_r - E_g cancels
+            acc[10 + q] += w;
+            if (band0) { acc[kSpecVals + q] += w * mb; acc[kSpecVals + 4 + q] += w; }
+          }
+      } else if (band0 && band >= 0) {  // ground-truth state: band sums of this (ground-truth) spectrum
+        const float m = hypotf(fa.x, fa.y);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (band == q) { acc[kSpecVals + q] += w * m; acc[kSpecVals + 4 + q] += w; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kColVals; ++q) {
+      const float v = warp_sum(acc[q]);
+      if ((tid & 31) == 0) red[tid >> 5][q] = v;
+    }
+    __syncthreads();
+    if (tid < kColVals) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFftThreads / 32; ++w) v += red[w][tid];
+      a.partial[(size_t)blockIdx.x * kColVals + tid] = (double)v;
+    }
+  }
+  if (a.fin.mode == 0) return;
+  // ---- the last CTA to arrive reduces every partial and runs the scalar epilogue
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(a.fin.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  freq_epilogue(a.fin, a.partial);
+}
+
+// ---------------------------------------------------------------- backward: spectral gradient + inverse columns
+struct GradJob {
+  float2* A;          // rendered spectrum in, inverse-column-transformed gradient out
+  const float2* B;    // ground-truth spectrum
+  int H, W, tc, cta_begin, level;
+  Plan plan;
+};
+struct GradArgs { int n_jobs; GradJob job[kMaxLevels]; const LevelCtl* ctl; };
+
+__global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const GradArgs a) {
+  extern __shared__ float2 sm[];
+  const int tid = threadIdx.x;
+  int j = 0;
+  for (int k = 1; k < a.n_jobs; ++k)
+    if ((int)blockIdx.x >= a.job[k].cta_begin) j = k;
+  const GradJob& J = a.job[j];
+  const int H = J.H, W = J.W, Wh = W / 2 + 1, tc = J.tc;
+  const int c0 = ((int)blockIdx.x - J.cta_begin) * tc;
+  const int nc = min(tc, Wh - c0);
+  const LevelCtl* ctl = a.ctl + J.level;
+  const float c_mag = ctl->c_mag, c_phase = ctl->c_phase;
+  float2 *bufa = sm, *bufb = sm + (size_t)tc * H;
+  for (int i = tid; i < H * tc; i += kFftThreads) {
+    const int ky = i / tc, c = i - ky * tc;
+    float gre = 0.f, gim = 0.f;
+    if (c < nc) {
+      const int kx = c0 + c;
+      const float2 fa = J.A[(size_t)ky * Wh + kx], fb = J.B[(size_t)ky * Wh + kx];
+      const float ma = hypotf(fa.x, fa.y), mb = hypotf(fb.x, fb.y);
+      if (ma > 0.f) {
+        float dmag = c_mag * (logf(ma + 1e-6f) - logf(mb + 1e-6f)) / (ma + 1e-6f);
+        const int band = band_of(ky, kx, H, W);
+        if (band >= 0) dmag += ctl->c_band[band];
+        gre = dmag * fa.x / ma;
+        gim = dmag * fa.y / ma;
+        const float pa = atan2f(fa.y, fa.x), pb = atan2f(fb.y, fb.x);
+        const float dlt = pa - pb, ad = fabsf(dlt);
+        const float sgn = dlt > 0.f ? 1.f : (dlt < 0.f ? -1.f : 0.f);
+        const float other = 2.f * kPi - ad;
+        // d min(|D|, 2pi - |D|) / dD, with torch.min's even split on ties
+        const float dw = ad < other ? sgn : (ad > other ? -sgn : 0.f);
+        const float gp = c_phase * dw / (ma * ma);
+        gre += gp * (-fa.y);
+        gim += gp * fa.x;
+      }
+    }
+    bufa[c * H + ky] = make_float2(gre, -gim);  // conj: the inverse is conj -> FFT -> conj
+  }
+  __syncthreads();
+  const float2* r = fft_smem(bufa, bufb, J.plan, tc);
+  for (int i = tid; i < H * tc; i += kFftThreads) {
+    const int y = i / tc, c = i - y * tc;
+    if (c < nc) {
+      float2 v = r[c * H + y];
+      v.y = -v.y;
+      J.A[(size_t)y * Wh + c0 + c] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- rows, inverse (all levels in one launch)
+struct InvJob {
+  const float2* spec;  // [H][W/2+1], columns already inverse-transformed
+  float* dst;          // [H][W]
+  const float* gate;   // mode 0: gray image whose clamp(0, 1) gates the gradient (NULL: no gate)
+  int H, W, pairs, cta_begin, mode;  // mode 0: dst = x * scale (gated); mode 1: dst = |x * scale| and the maximum of it
+  float scale;
+  Plan plan;
+};
+struct InvArgs {
+  int n_jobs;
+  InvJob job[kMaxLevels];
+  float* pmax;         // mode 1: per-CTA maxima, then mm[1] = the global maximum (last CTA)
+  float* mm;
+  unsigned* counter;
+};
+
+__global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const InvArgs a) {
+  extern __shared__ float2 sm[];
+  __shared__ float smax[kFftThreads / 32];
+  __shared__ int s_last;
+  int j = 0;
+  for (int k = 1; k < a.n_jobs; ++k)
+    if ((int)blockIdx.x >= a.job[k].cta_begin) j = k;
+  const InvJob& J = a.job[j];
+  const int W = J.W, H = J.H, Wh = W / 2 + 1, pairs = J.pairs;
+  const int p0 = ((int)blockIdx.x - J.cta_begin) * pairs;
+  float2 *bufa = sm, *bufb = sm + pairs * W;
+  for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
+    const int pr = i / W, x = i - pr * W;
+    const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
+    const bool upper = x >= Wh;
+    const int k = upper ? W - x : x;
+    float2 A = r0 < H ? J.spec[(size_t)r0 * Wh + k] : make_float2(0.f, 0.f);
+    float2 B = r1 < H ? J.spec[(size_t)r1 * Wh + k] : make_float2(0.f, 0.f);
+    if (k == 0 || 2 * k == W) { A.y = 0.f; B.y = 0.f; }
+    if (upper) { A.y = -A.y; B.y = -B.y; }  // conj(S[N-k])
+    bufa[i] = make_float2(A.x - B.y, -(A.y + B.x));  // conj(A + i B)
+  }
+  __syncthreads();
+  const float2* r = fft_smem(bufa, bufb, J.plan, pairs);
+  float vmax = 0.f;
+  for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
+    const int pr = i / W, x = i - pr * W;
+    const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
+    if (r0 >= H) continue;
+    const float2 v = r[i];
+    float o0 = v.x * J.scale, o1 = -v.y * J.scale;
+    const size_t q0 = (size_t)r0 * W + x, q1 = (size_t)r1 * W + x;
+    if (J.mode == 1) {
+      o0 = fabsf(o0);
+      o1 = fabsf(o1);
+      vmax = fmaxf(vmax, o0);
+      if (r1 < H) vmax = fmaxf(vmax, o1);
+    } else if (J.gate) {  // d clamp(gray, 0, 1) / d gray
+      const float g0 = __ldg(J.gate + q0);
+      if (!(g0 >= 0.f && g0 <= 1.f)) o0 = 0.f;
+      if (r1 < H) {
+        const float g1 = __ldg(J.gate + q1);
+        if (!(g1 >= 0.f && g1 <= 1.f)) o1 = 0.f;
+      }
+    }
+    J.dst[q0] = o0;
+    if (r1 < H) J.dst[q1] = o1;
+  }
+  if (J.mode != 1) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kFftThreads / 32; ++w) vmax = fmaxf(vmax, smax[w]);
+    a.pmax[blockIdx.x] = vmax;
+    __threadfence();
+    s_last = atomicAdd(a.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float m = 0.f;  // |.| >= 0; the maximum is order independent
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) m = fmaxf(m, a.pmax[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kFftThreads / 32; ++w) m = fmaxf(m, smax[w]);
+    a.mm[1] = m;
+  }
+}
+
+// ---------------------------------------------------------------- image space, backward
+struct BwdArgs {
+  int levels;
+  int H[kMaxLevels], W[kMaxLevels];
+  const float* gr[kMaxLevels];   // gray pyramids
+  const float* gg[kMaxLevels];
+  const float* dg[kMaxLevels];   // gradient w.r.t. the gray level from the spectral terms (clamp-gated)
+  const LevelCtl* ctl;
+  const float* gscale;           // device scalar multiplied into the result (NULL: 1)
+  float* out;                    // [3][H0][W0]
+};
+
+// scaled responses c * R on tile + halo 1 from d on tile + halo 2 (zero where the centre is outside the image)
+template <int T>
+__device__ __forceinline__ void scaled_responses(const float (*d)[T + 5], float (*rx)[T + 3], float (*ry)[T + 3],
+                                                 float (*rl)[T + 3], int y0, int x0, int H, int W, float cs, float cl,
+                                                 int tid) {
+  for (int i = tid; i < (T + 2) * (T + 2); i += kImgThreads) {
+    const int r = i / (T + 2), c = i - r * (T + 2);
+    const int y = y0 + r - 1, x = x0 + c - 1;
+    float sx = 0.f, sy = 0.f, lp = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) responses_at(&d[r + 1][c + 1], T + 5, sx, sy, lp);
+    rx[r][c] = cs * sx; ry[r][c] = cs * sy; rl[r][c] = cl * lp;
+  }
+}
+
+// dL/dd(p) = sum_{u,v} K[u][v] * R(p - (u-1, v-1)); (r, c) index the response arrays (tile + halo 1)
+template <int T>
+__device__ __forceinline__ float stencil_adjoint(const float (*rx)[T + 3], const float (*ry)[T + 3],
+                                                 const float (*rl)[T + 3], int r, int c) {
+  const float gx = -rx[r + 1][c + 1] + rx[r + 1][c - 1] - 2.f * rx[r][c + 1] + 2.f * rx[r][c - 1] - rx[r - 1][c + 1] + rx[r - 1][c - 1];
+  const float gy = -ry[r + 1][c + 1] - 2.f * ry[r + 1][c] - ry[r + 1][c - 1] + ry[r - 1][c + 1] + 2.f * ry[r - 1][c] + ry[r - 1][c - 1];
+  const float gl = -rl[r + 1][c] - rl[r][c + 1] + 4.f * rl[r][c] - rl[r][c - 1] - rl[r - 1][c];
+  return gx + gy + gl;
+}
+
+template <int T>
+__device__ __forceinline__ void load_diff(float (*d)[T + 5], const float* __restrict__ gr, const float* __restrict__ gg,
+                                          int y0, int x0, int H, int W, int tid) {
+  for (int i = tid; i < (T + 4) * (T + 4); i += kImgThreads) {
+    const int r = i / (T + 4), c = i - r * (T + 4);
+    const int y = y0 + r - 2, x = x0 + c - 2;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    d[r][c] = in ? (__ldg(gr + (size_t)y * W + x) - __ldg(gg + (size_t)y * W + x)) : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kImgThreads) spatial_grad_rgb_kernel(const BwdArgs a) {
+  constexpr int T0 = kT0, T1 = kT0 / 2, T2 = kT0 / 4;
+  __shared__ float d0[T0 + 4][T0 + 5], d1[T1 + 4][T1 + 5], d2[T2 + 4][T2 + 5];
+  __shared__ float rx0[T0 + 2][T0 + 3], ry0[T0 + 2][T0 + 3], rl0[T0 + 2][T0 + 3];
+  __shared__ float rx1[T1 + 2][T1 + 3], ry1[T1 + 2][T1 + 3], rl1[T1 + 2][T1 + 3];
+  __shared__ float rx2[T2 + 2][T2 + 3], ry2[T2 + 2][T2 + 3], rl2[T2 + 2][T2 + 3];
+  __shared__ float t1[T1][T1 + 1], t2[T2][T2 + 1];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * T0, y0 = blockIdx.y * T0;
+  const int H0 = a.H[0], W0 = a.W[0];
+  const int H1 = a.levels > 1 ? a.H[1] : 0, W1 = a.levels > 1 ? a.W[1] : 0;
+  const int H2 = a.levels > 2 ? a.H[2] : 0, W2 = a.levels > 2 ? a.W[2] : 0;
+  load_diff<T0>(d0, a.gr[0], a.gg[0], y0, x0, H0, W0, tid);
+  if (a.levels > 1) load_diff<T1>(d1, a.gr[1], a.gg[1], y0 >> 1, x0 >> 1, H1, W1, tid);
+  if (a.levels > 2) load_diff<T2>(d2, a.gr[2], a.gg[2], y0 >> 2, x0 >> 2, H2, W2, tid);
+  __syncthreads();
+  scaled_responses<T0>(d0, rx0, ry0, rl0, y0, x0, H0, W0, a.ctl[0].c_sobel, a.ctl[0].c_lap, tid);
+  if (a.levels > 1) scaled_responses<T1>(d1, rx1, ry1, rl1, y0 >> 1, x0 >> 1, H1, W1, a.ctl[1].c_sobel, a.ctl[1].c_lap, tid);
+  if (a.levels > 2) scaled_responses<T2>(d2, rx2, ry2, rl2, y0 >> 2, x0 >> 2, H2, W2, a.ctl[2].c_sobel, a.ctl[2].c_lap, tid);
+  __syncthreads();
+  if (a.levels > 2 && tid < T2 * T2) {
+    const int r = tid / T2, c = tid - r * T2;
+    const int Y = (y0 >> 2) + r, X = (x0 >> 2) + c;
+    float t = 0.f;
+    if (Y < H2 && X < W2) t = __ldg(a.dg[2] + (size_t)Y * W2 + X) + stencil_adjoint<T2>(rx2, ry2, rl2, r + 1, c + 1);
+    t2[r][c] = t;
+  }
+  __syncthreads();
+  if (a.levels > 1) {
+    const int r = tid / T1, c = tid - r * T1;
+    const int Y = (y0 >> 1) + r, X = (x0 >> 1) + c;
+    float t = 0.f;
+    if (Y < H1 && X < W1) {
+      t = __ldg(a.dg[1] + (size_t)Y * W1 + X) + stencil_adjoint<T1>(rx1, ry1, rl1, r + 1, c + 1);
+      if (a.levels > 2 && (Y >> 1) < H2 && (X >> 1) < W2) t += 0.25f * t2[r >> 1][c >> 1];  // avg_pool2d backward
+    }
+    t1[r][c] = t;
+  }
+  __syncthreads();
+  const float gs = a.gscale ? __ldg(a.gscale) : 1.0f;
+  const size_t hw0 = (size_t)H0 * W0;
+  for (int i = tid; i < T0 * T0; i += kImgThreads) {
+    const int r = i / T0, c = i - r * T0;
+    const int y = y0 + r, x = x0 + c;
+    if (y >= H0 || x >= W0) continue;
+    const size_t p = (size_t)y * W0 + x;
+    float t = __ldg(a.dg[0] + p) + stencil_adjoint<T0>(rx0, ry0, rl0, r + 1, c + 1);
+    if (a.levels > 1 && (y >> 1) < H1 && (x >> 1) < W1) t += 0.25f * t1[r >> 1][c >> 1];
+    const float g = (t / 3.0f) * gs;
+    a.out[p] = g; a.out[hw0 + p] = g; a.out[2 * hw0 + p] = g;
+  }
+}
+
+// ---------------------------------------------------------------- high-frequency mask tail
+constexpr int kSumBlocks = 148 * 2;
+
+// score = clamp(0.7 spatial + 0.3 hs / max(hs), 0, 5) in place over hs; min / max of it -> mm2[0..1] (last CTA)
+__global__ void __launch_bounds__(256)
+hf_combine_kernel(float* __restrict__ hs, const float* __restrict__ spatial, const float* __restrict__ mm, int64_t n,
+                  float* __restrict__ pmin, float* __restrict__ pmax, float* __restrict__ mm2, unsigned* counter) {
+  __shared__ float smin[8], smax[8];
+  __shared__ int s_last;
+  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+  const float mx = mm[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float h = hs[i];
+    if (mx > 1e-8f) h = h / mx;
+    const float v = fminf(fmaxf(0.7f * spatial[i] + 0.3f * h, 0.f), 5.0f);
+    hs[i] = v;
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);
   }
@@ -763,26 +1164,38 @@ hf_reduce_kernel(float* __restrict__ hs, const float* __restrict__ spatial, cons
     for (int i = 1; i < 8; ++i) { lo = fminf(lo, smin[i]); hi = fmaxf(hi, smax[i]); }
     pmin[blockIdx.x] = lo;
     pmax[blockIdx.x] = hi;
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
   }
-}
-
-// one warp; min/max are order independent
-__global__ void hf_minmax_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax, int n,
-                                 float* __restrict__ mm) {
-  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
-  for (int i = threadIdx.x; i < n; i += 32) { lo = fminf(lo, pmin[i]); hi = fmaxf(hi, pmax[i]); }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  lo = __int_as_float(0x7f800000);
+  hi = -__int_as_float(0x7f800000);
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { lo = fminf(lo, pmin[i]); hi = fmaxf(hi, pmax[i]); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if (threadIdx.x == 0) { mm[0] = lo; mm[1] = hi; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) { lo = fminf(lo, smin[i]); hi = fmaxf(hi, smax[i]); }
+    mm2[0] = lo;
+    mm2[1] = hi;
+  }
 }
 
+// mask = (score - min) / (max - min) > thresh; count = sum(mask) (0 / 1 values: the float sum is exact below 2^24 per
+// CTA, the cross-CTA sum runs in double)
 __global__ void __launch_bounds__(256)
 hf_threshold_kernel(const float* __restrict__ score, const float* __restrict__ mm, int64_t n, float thresh,
-                    float* __restrict__ mask, double* __restrict__ partial) {
-  __shared__ float red[32];
+                    float* __restrict__ mask, double* __restrict__ partial, float* __restrict__ count, unsigned* counter) {
+  __shared__ float red[8];
+  __shared__ double sm[32];
+  __shared__ int s_last;
   float cnt = 0.f;
   const float lo = mm[0], range = mm[1] - mm[0];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -791,16 +1204,24 @@ hf_threshold_kernel(const float* __restrict__ score, const float* __restrict__ m
     mask[i] = m;
     cnt += m;
   }
-  const float s = block_sum(cnt, red, threadIdx.x, 256);
-  if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
-}
-
-__global__ void __launch_bounds__(256) hf_count_kernel(const double* __restrict__ partial, int n, float* __restrict__ count) {
-  __shared__ double sm[32];
-  const double s = cta_sum_strided(partial, n, 1, 0, sm);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    partial[blockIdx.x] = (double)s;
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double s = cta_sum_strided(partial, (int)gridDim.x, 1, 0, sm);
   if (threadIdx.x == 0) count[0] = (float)s;
 }
 
+// ---------------------------------------------------------------- host side: workspace, job tables, launches
 struct Carver {
   char* p;
   explicit Carver(void* base) : p((char*)(((uintptr_t)base + 255) / 256 * 256)) {}
@@ -812,10 +1233,307 @@ struct Carver {
   }
 };
 
-size_t level_bytes(int H, int W) {
-  const size_t hw = (size_t)H * W, sp = (size_t)H * (W / 2 + 1);
-  const size_t tiles = (size_t)((W + kSpTile - 1) / kSpTile) * ((H + kSpTile - 1) / kSpTile);
-  return 3 * (hw * 4 + 256) + 2 * (sp * 8 + 256) + (tiles * 3 * 8 + 256) + ((size_t)kSumBlocks * kSpecVals * 8 + 256);
+static inline size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
+
+// columns per CTA of the column kernels: the pair job keeps 2 * tc columns twice (ping-pong) in shared memory
+static int cols_per_cta(int H) {
+  int tc = (int)((72 * 1024) / (32 * (size_t)H));
+  return tc > 4 ? 4 : (tc < 1 ? 1 : tc);
+}
+// row pairs per CTA of the row kernels: about 2048 points per CTA (1 / 2 / 4 pairs at 1920 / 960 / 480 columns)
+static int pairs_per_cta(int W) {
+  int p = 2048 / W;
+  return p > 8 ? 8 : (p < 1 ? 1 : p);
+}
+
+struct Dims {
+  int levels;
+  int H[kMaxLevels], W[kMaxLevels];
+  Plan row[kMaxLevels], col[kMaxLevels];
+};
+
+static int make_dims(int32_t H, int32_t W, int32_t levels, Dims* d) {
+  if (levels < 1 || levels > kMaxLevels || H < 4 || W < 4) {
+    set_error("frequency loss: bad size / level count");
+    return HG_ERR_INVALID_ARG;
+  }
+  d->levels = levels;
+  d->H[0] = H; d->W[0] = W;
+  for (int l = 1; l < levels; ++l) { d->H[l] = d->H[l - 1] / 2; d->W[l] = d->W[l - 1] / 2; }
+  for (int l = 0; l < levels; ++l) {
+    if (d->H[l] <= 0 || d->W[l] <= 1 || d->H[l] > 4096 || d->W[l] > 4096 || !make_plan(d->W[l], &d->row[l]) ||
+        !make_plan(d->H[l], &d->col[l])) {
+      set_error("FFT size %dx%d unsupported (each side must be in [1, 4096])", d->H[l], d->W[l]);
+      return HG_ERR_INVALID_ARG;
+    }
+  }
+  return HG_OK;
+}
+
+static int set_fused_attrs() {
+  static thread_local bool done[64] = {};
+  int dev = 0;
+  HG_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return HG_OK;
+  const int maxb = 200 * 1024;
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_rows_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_cols_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  HG_CUDA_TRY(cudaFuncSetAttribute(spectral_grad_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  HG_CUDA_TRY(cudaFuncSetAttribute(fft_rows_c2r_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxb));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return HG_OK;
+}
+
+// Ground-truth side of the regulariser for one image: gray pyramid, its spectra, the 8 level-0 band sums.
+struct GtState {
+  float* gg[kMaxLevels];
+  float2* fg[kMaxLevels];
+  double* band0;   // 8 final sums
+};
+
+static void carve_gt_state(void* base, const Dims& d, GtState* g) {
+  Carver cv(base);
+  for (int l = 0; l < d.levels; ++l) {
+    g->gg[l] = cv.take<float>((size_t)d.H[l] * d.W[l]);
+    g->fg[l] = cv.take<float2>((size_t)d.H[l] * (d.W[l] / 2 + 1));
+  }
+  g->band0 = cv.take<double>(8);
+}
+
+static size_t gt_state_bytes(const Dims& d) {
+  size_t total = 512 + pad256(8 * sizeof(double));
+  for (int l = 0; l < d.levels; ++l)
+    total += pad256((size_t)d.H[l] * d.W[l] * 4) + pad256((size_t)d.H[l] * (d.W[l] / 2 + 1) * 8);
+  return total;
+}
+
+// The workspace of one call (forward state kept for the backward).
+struct Work {
+  LevelCtl* ctl;
+  unsigned* counters;  // [0] column epilogue, [1] hf maximum, [2] hf min / max, [3] hf count
+  float* mm;           // [0..1] hf maximum, [2..3] score min / max
+  float *gr[kMaxLevels], *dg[kMaxLevels];
+  float2* fr[kMaxLevels];
+  double* spatial_partial;
+  double* col_partial;
+  int tiles, col_ctas_max;
+  // high-frequency mask (uncached ground truth)
+  float *hf_score, *hf_hs, *hf_pmin, *hf_pmax;
+  float2* hf_spec;
+  double* hf_part;
+  GtState gt;          // uncached: carved behind everything else
+  char* end;
+};
+
+static int col_ctas(const Dims& d, int l) { return (d.W[l] / 2 + 1 + cols_per_cta(d.H[l]) - 1) / cols_per_cta(d.H[l]); }
+
+static void carve_work(void* ws, const Dims& d, bool with_gt, bool with_hf, Work* w) {
+  Carver cv(ws);
+  w->ctl = cv.take<LevelCtl>(kMaxLevels);
+  w->counters = cv.take<unsigned>(8);
+  w->mm = cv.take<float>(8);
+  w->tiles = ((d.W[0] + kT0 - 1) / kT0) * ((d.H[0] + kT0 - 1) / kT0);
+  int ctas = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    const size_t hw = (size_t)d.H[l] * d.W[l];
+    w->gr[l] = cv.take<float>(hw);
+    w->dg[l] = cv.take<float>(hw);
+    w->fr[l] = cv.take<float2>((size_t)d.H[l] * (d.W[l] / 2 + 1));
+    ctas += col_ctas(d, l);
+  }
+  const int hf_ctas = (d.W[0] / 2 + 1 + 3) / 4 + 8;
+  w->col_ctas_max = ctas + hf_ctas;
+  w->spatial_partial = cv.take<double>((size_t)w->tiles * 9);
+  w->col_partial = cv.take<double>((size_t)w->col_ctas_max * kColVals);
+  w->hf_score = w->hf_hs = w->hf_pmin = w->hf_pmax = nullptr;
+  w->hf_spec = nullptr;
+  w->hf_part = nullptr;
+  if (with_hf) {
+    const size_t hw = (size_t)d.H[0] * d.W[0];
+    w->hf_score = cv.take<float>(hw);
+    w->hf_hs = cv.take<float>(hw);
+    w->hf_spec = cv.take<float2>((size_t)d.H[0] * (d.W[0] / 2 + 1));
+    w->hf_pmin = cv.take<float>(2048);
+    w->hf_pmax = cv.take<float>(2048);
+    w->hf_part = cv.take<double>(kSumBlocks);
+  }
+  if (with_gt) {
+    carve_gt_state(cv.p, d, &w->gt);
+    cv.p += gt_state_bytes(d);
+  }
+  w->end = cv.p;
+}
+
+static size_t work_bytes(const Dims& d, bool with_gt, bool with_hf) {
+  Work w;
+  carve_work((void*)(uintptr_t)4096, d, with_gt, with_hf, &w);
+  return (size_t)(w.end - (char*)(uintptr_t)4096) + 512;
+}
+
+static RowJob row_job(const float* src, float2* dst, const Dims& d, int l, int clamp01, int* cta) {
+  RowJob j;
+  j.src = src; j.dst = dst; j.H = d.H[l]; j.W = d.W[l]; j.clamp01 = clamp01;
+  j.pairs = pairs_per_cta(d.W[l]);
+  j.cta_begin = *cta;
+  j.plan = d.row[l];
+  *cta += ((d.H[l] + 1) / 2 + j.pairs - 1) / j.pairs;
+  return j;
+}
+
+static size_t row_smem(const Dims& d, int l) { return 2 * (size_t)pairs_per_cta(d.W[l]) * d.W[l] * sizeof(float2); }
+
+static int launch_rows(const RowArgs& ra, int ctas, size_t smem, cudaStream_t st) {
+  fft_rows_jobs_kernel<<<ctas, kFftThreads, smem, st>>>(ra);
+  HG_POST_LAUNCH(false, st, "fft_rows_jobs");
+  return HG_OK;
+}
+
+// the tail of the high-frequency mask: inverse rows (|.|, max) -> score, min / max -> mask, count
+static int launch_hf_tail(const Dims& d, const Work& w, float thresh, float* mask, float* count, cudaStream_t st) {
+  InvArgs ia{};
+  ia.n_jobs = 1;
+  InvJob& j = ia.job[0];
+  j.spec = w.hf_spec; j.dst = w.hf_hs; j.gate = nullptr; j.H = d.H[0]; j.W = d.W[0];
+  j.pairs = pairs_per_cta(d.W[0]); j.cta_begin = 0; j.mode = 1;
+  j.scale = 1.0f / ((float)d.H[0] * (float)d.W[0]);
+  j.plan = d.row[0];
+  ia.pmax = w.hf_pmax; ia.mm = w.mm; ia.counter = w.counters + 1;
+  const int ctas = ((d.H[0] + 1) / 2 + j.pairs - 1) / j.pairs;
+  if (ctas > 2048) { set_error("hf mask: image too tall"); return HG_ERR_INVALID_ARG; }
+  fft_rows_c2r_jobs_kernel<<<ctas, kFftThreads, row_smem(d, 0), st>>>(ia);
+  HG_POST_LAUNCH(false, st, "ifft_rows_hf");
+  const int64_t hw = (int64_t)d.H[0] * d.W[0];
+  hf_combine_kernel<<<kSumBlocks, 256, 0, st>>>(w.hf_hs, w.hf_score, w.mm, hw, w.hf_pmin, w.hf_pmax, w.mm + 2, w.counters + 2);
+  HG_POST_LAUNCH(false, st, "hf_combine");
+  hf_threshold_kernel<<<kSumBlocks, 256, 0, st>>>(w.hf_hs, w.mm + 2, hw, thresh, mask, w.hf_part, count, w.counters + 3);
+  HG_POST_LAUNCH(false, st, "hf_threshold");
+  return HG_OK;
+}
+
+static void fill_pyr_dims(PyrArgs* pa, const Dims& d) {
+  pa->levels = d.levels;
+  for (int l = 0; l < kMaxLevels; ++l) { pa->H[l] = l < d.levels ? d.H[l] : 0; pa->W[l] = l < d.levels ? d.W[l] : 0; }
+}
+
+// Forward of the regulariser (+ optionally the high-frequency mask of the same ground truth).
+static int freq_forward(const float* rendered, const float* gt, void* gt_state, const Dims& d, float hf_thresh,
+                        float* hf_mask, float* hf_count, float* stats, void* ws, cudaStream_t st) {
+  const bool cached = gt_state != nullptr;
+  const bool hf = hf_mask != nullptr;
+  int rc = set_fused_attrs();
+  if (rc) return rc;
+  Work w;
+  carve_work(ws, d, !cached, hf, &w);
+  GtState G;
+  if (cached) carve_gt_state(gt_state, d, &G); else G = w.gt;
+  // ---- image space
+  PyrArgs pa{};
+  pa.rgb[0] = rendered; pa.rgb[1] = cached ? nullptr : gt;
+  for (int l = 0; l < d.levels; ++l) { pa.gray[0][l] = w.gr[l]; pa.gray[1][l] = G.gg[l]; }
+  pa.n_images = 2;
+  fill_pyr_dims(&pa, d);
+  pa.partial = w.spatial_partial;
+  pa.hf_score = hf ? w.hf_score : nullptr;
+  pa.hf_src = 1;
+  pa.counters = w.counters;
+  const dim3 tiles((d.W[0] + kT0 - 1) / kT0, (d.H[0] + kT0 - 1) / kT0);
+  pyramid_kernel<<<tiles, kImgThreads, 0, st>>>(pa);
+  HG_POST_LAUNCH(false, st, "pyramid");
+  // ---- rows
+  RowArgs ra{};
+  int cta = 0;
+  size_t smem = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    ra.job[ra.n_jobs++] = row_job(w.gr[l], w.fr[l], d, l, 1, &cta);
+    if (!cached) ra.job[ra.n_jobs++] = row_job(G.gg[l], G.fg[l], d, l, 1, &cta);
+    if (row_smem(d, l) > smem) smem = row_smem(d, l);
+  }
+  if (hf) ra.job[ra.n_jobs++] = row_job(G.gg[0], w.hf_spec, d, 0, 0, &cta);  // unclamped here (:1221)
+  rc = launch_rows(ra, cta, smem, st);
+  if (rc) return rc;
+  // ---- columns + sums + epilogue
+  ColArgs ca{};
+  cta = 0;
+  smem = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    ColJob& j = ca.job[ca.n_jobs++];
+    j.A = w.fr[l]; j.B = G.fg[l]; j.H = d.H[l]; j.W = d.W[l];
+    j.kind = cached ? kColPairCached : kColPair;
+    j.tc = cols_per_cta(d.H[l]); j.cta_begin = cta; j.level = l; j.plan = d.col[l];
+    ca.fin.col_begin[l] = cta;
+    cta += col_ctas(d, l);
+    ca.fin.col_end[l] = cta;
+    const size_t b = 2 * (size_t)(cached ? 1 : 2) * j.tc * d.H[l] * sizeof(float2);
+    if (b > smem) smem = b;
+  }
+  if (hf) {
+    ColJob& j = ca.job[ca.n_jobs++];
+    j.A = w.hf_spec; j.B = nullptr; j.H = d.H[0]; j.W = d.W[0]; j.kind = kColHighpassInverse;
+    j.tc = 2 * cols_per_cta(d.H[0]) > 4 ? 4 : 2 * cols_per_cta(d.H[0]);
+    j.cta_begin = cta; j.level = -1; j.plan = d.col[0];
+    cta += (d.W[0] / 2 + 1 + j.tc - 1) / j.tc;
+    const size_t b = 2 * (size_t)j.tc * d.H[0] * sizeof(float2);
+    if (b > smem) smem = b;
+  }
+  ca.partial = w.col_partial;
+  FinalizeArgs& f = ca.fin;
+  f.mode = 1; f.levels = d.levels;
+  for (int l = 0; l < d.levels; ++l) { f.H[l] = d.H[l]; f.W[l] = d.W[l]; }
+  f.spatial_partial = w.spatial_partial; f.spatial_tiles = w.tiles;
+  f.band0_in = cached ? G.band0 : nullptr; f.band0_out = nullptr;
+  f.ctl = w.ctl; f.stats = stats; f.counter = w.counters;
+  fft_cols_jobs_kernel<<<cta, kFftThreads, smem, st>>>(ca);
+  HG_POST_LAUNCH(false, st, "fft_cols_jobs");
+  if (hf) return launch_hf_tail(d, w, hf_thresh, hf_mask, hf_count, st);
+  return HG_OK;
+}
+
+// Backward of the regulariser on the state the forward left in the workspace: grad = gscale * d freq_loss / d rendered.
+static int freq_backward(void* gt_state, const Dims& d, bool forward_had_hf, const float* gscale, float* grad, void* ws,
+                         cudaStream_t st) {
+  const bool cached = gt_state != nullptr;
+  Work w;
+  carve_work(ws, d, !cached, forward_had_hf, &w);
+  GtState G;
+  if (cached) carve_gt_state(gt_state, d, &G); else G = w.gt;
+  GradArgs ga{};
+  int cta = 0;
+  size_t smem = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    GradJob& j = ga.job[ga.n_jobs++];
+    j.A = w.fr[l]; j.B = G.fg[l]; j.H = d.H[l]; j.W = d.W[l];
+    j.tc = 2 * cols_per_cta(d.H[l]) > 4 ? 4 : 2 * cols_per_cta(d.H[l]);
+    j.cta_begin = cta; j.level = l; j.plan = d.col[l];
+    cta += (d.W[l] / 2 + 1 + j.tc - 1) / j.tc;
+    const size_t b = 2 * (size_t)j.tc * d.H[l] * sizeof(float2);
+    if (b > smem) smem = b;
+  }
+  ga.ctl = w.ctl;
+  spectral_grad_cols_kernel<<<cta, kFftThreads, smem, st>>>(ga);
+  HG_POST_LAUNCH(false, st, "spectral_grad_cols");
+  InvArgs ia{};
+  cta = 0;
+  smem = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    InvJob& j = ia.job[ia.n_jobs++];
+    j.spec = w.fr[l]; j.dst = w.dg[l]; j.gate = w.gr[l]; j.H = d.H[l]; j.W = d.W[l];
+    j.pairs = pairs_per_cta(d.W[l]); j.cta_begin = cta; j.mode = 0; j.scale = 1.0f; j.plan = d.row[l];
+    cta += ((d.H[l] + 1) / 2 + j.pairs - 1) / j.pairs;
+    if (row_smem(d, l) > smem) smem = row_smem(d, l);
+  }
+  fft_rows_c2r_jobs_kernel<<<cta, kFftThreads, smem, st>>>(ia);
+  HG_POST_LAUNCH(false, st, "ifft_rows_jobs");
+  BwdArgs ba{};
+  ba.levels = d.levels;
+  for (int l = 0; l < d.levels; ++l) {
+    ba.H[l] = d.H[l]; ba.W[l] = d.W[l];
+    ba.gr[l] = w.gr[l]; ba.gg[l] = G.gg[l]; ba.dg[l] = w.dg[l];
+  }
+  ba.ctl = w.ctl; ba.gscale = gscale; ba.out = grad;
+  const dim3 tiles((d.W[0] + kT0 - 1) / kT0, (d.H[0] + kT0 - 1) / kT0);
+  spatial_grad_rgb_kernel<<<tiles, kImgThreads, 0, st>>>(ba);
+  HG_POST_LAUNCH(false, st, "spatial_grad_rgb");
+  return HG_OK;
 }
 
 }  // namespace
@@ -844,74 +1562,22 @@ int hg_fft2_c2r(const float* spec, int32_t H, int32_t W, float* img, int scale_i
 }
 
 size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels) {
-  size_t total = 4096 + (size_t)kSumBlocks * 8 * 8 + 1024 + hg_freq_gt_state_bytes(H, W, levels);
-  int h = H, w = W;
-  for (int l = 0; l < levels; ++l) {
-    total += level_bytes(h, w);
-    h /= 2;
-    w /= 2;
-  }
-  return total;
-}
-
-// Ground-truth side of the frequency loss for one image: gray pyramid, its spectra and the level-0 band sums.
-struct GtState {
-  float* gg[3];
-  float2* fg[3];
-  double* band0;
-};
-
-static void carve_gt_state(void* base, int levels, const int* hs, const int* wsz, GtState* g) {
-  Carver cv(base);
-  for (int l = 0; l < levels; ++l) {
-    g->gg[l] = cv.take<float>((size_t)hs[l] * wsz[l]);
-    g->fg[l] = cv.take<float2>((size_t)hs[l] * (wsz[l] / 2 + 1));
-  }
-  g->band0 = cv.take<double>((size_t)kSumBlocks * 8);
-}
-
-static int level_sizes(int32_t H, int32_t W, int32_t levels, int* hs, int* wsz) {
-  if (levels < 1 || levels > 3 || H < 4 || W < 4) {
-    set_error("frequency loss: bad size / level count");
-    return HG_ERR_INVALID_ARG;
-  }
-  hs[0] = H; wsz[0] = W;
-  for (int l = 1; l < levels; ++l) { hs[l] = hs[l - 1] / 2; wsz[l] = wsz[l - 1] / 2; }
-  for (int l = 0; l < levels; ++l) {
-    FftCfg c;
-    int rc = make_cfg(hs[l], wsz[l], &c);
-    if (rc) return rc;
-  }
-  return HG_OK;
-}
-
-static int prepare_gt(const float* gt, int levels, const int* hs, const int* wsz, const GtState& g, cudaStream_t st) {
-  const int64_t hw0 = (int64_t)hs[0] * wsz[0];
-  gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(gt, hw0, g.gg[0]);
-  HG_POST_LAUNCH(false, st, "gray");
-  for (int l = 1; l < levels; ++l) {
-    const dim3 grid((wsz[l] + 127) / 128, hs[l]);
-    pool_kernel<<<grid, 128, 0, st>>>(g.gg[l - 1], wsz[l - 1], hs[l], wsz[l], g.gg[l]);
-    HG_POST_LAUNCH(false, st, "pool");
-  }
-  for (int l = 0; l < levels; ++l) {
-    int rc = fft2_r2c(g.gg[l], g.fg[l], nullptr, nullptr, hs[l], wsz[l], 1, st);
-    if (rc) return rc;
-  }
-  band_energy_kernel<<<kSumBlocks, 256, 0, st>>>(g.fg[0], hs[0], wsz[0], g.band0);
-  HG_POST_LAUNCH(false, st, "band_energy");
-  return HG_OK;
+  Dims d;
+  d.levels = levels < 1 ? 1 : (levels > kMaxLevels ? kMaxLevels : levels);
+  d.H[0] = H < 4 ? 4 : H; d.W[0] = W < 4 ? 4 : W;
+  for (int l = 1; l < d.levels; ++l) { d.H[l] = d.H[l - 1] / 2; d.W[l] = d.W[l - 1] / 2; }
+  return work_bytes(d, true, true);
 }
 
 size_t hg_freq_gt_state_bytes(int32_t H, int32_t W, int32_t levels) {
-  size_t total = 1024 + (size_t)kSumBlocks * 8 * 8 + 256;
-  int h = H, w = W;
-  for (int l = 0; l < levels; ++l) {
-    total += ((size_t)h * w * 4 + 256) + ((size_t)h * (w / 2 + 1) * 8 + 256);
-    h /= 2;
-    w /= 2;
-  }
-  return total;
+  Dims d;
+  d.levels = levels < 1 ? 1 : (levels > kMaxLevels ? kMaxLevels : levels);
+  d.H[0] = H < 4 ? 4 : H; d.W[0] = W < 4 ? 4 : W;
+  for (int l = 1; l < d.levels; ++l) { d.H[l] = d.H[l - 1] / 2; d.W[l] = d.W[l - 1] / 2; }
+  // (+ the scratch of the preparation itself: per-CTA partial sums and a ticket)
+  int ctas = 8;
+  for (int l = 0; l < d.levels; ++l) ctas += col_ctas(d, l);
+  return gt_state_bytes(d) + pad256((size_t)ctas * kColVals * 8) + 1024;
 }
 
 int hg_freq_gt_prepare(const float* gt, int32_t H, int32_t W, int32_t levels, void* gt_state, void* st_) {
@@ -919,115 +1585,80 @@ int hg_freq_gt_prepare(const float* gt, int32_t H, int32_t W, int32_t levels, vo
     set_error("hg_freq_gt_prepare: NULL pointer");
     return HG_ERR_INVALID_ARG;
   }
-  int hs[3], wsz[3];
-  int rc = level_sizes(H, W, levels, hs, wsz);
+  Dims d;
+  int rc = make_dims(H, W, levels, &d);
   if (rc) return rc;
-  GtState g;
-  carve_gt_state(gt_state, levels, hs, wsz, &g);
-  return prepare_gt(gt, levels, hs, wsz, g, (cudaStream_t)st_);
+  rc = set_fused_attrs();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)st_;
+  GtState G;
+  carve_gt_state(gt_state, d, &G);
+  Carver scratch((char*)gt_state + gt_state_bytes(d));
+  unsigned* counters = scratch.take<unsigned>(8);
+  int n_ctas = 8;
+  for (int l = 0; l < d.levels; ++l) n_ctas += col_ctas(d, l);
+  double* partial = scratch.take<double>((size_t)n_ctas * kColVals);
+  PyrArgs pa{};
+  pa.rgb[0] = gt; pa.rgb[1] = nullptr;
+  for (int l = 0; l < d.levels; ++l) pa.gray[0][l] = G.gg[l];
+  pa.n_images = 1;
+  fill_pyr_dims(&pa, d);
+  pa.counters = counters;
+  const dim3 tiles((d.W[0] + kT0 - 1) / kT0, (d.H[0] + kT0 - 1) / kT0);
+  pyramid_kernel<<<tiles, kImgThreads, 0, st>>>(pa);
+  HG_POST_LAUNCH(false, st, "pyramid");
+  RowArgs ra{};
+  int cta = 0;
+  size_t smem = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    ra.job[ra.n_jobs++] = row_job(G.gg[l], G.fg[l], d, l, 1, &cta);
+    if (row_smem(d, l) > smem) smem = row_smem(d, l);
+  }
+  rc = launch_rows(ra, cta, smem, st);
+  if (rc) return rc;
+  ColArgs ca{};
+  cta = 0;
+  smem = 0;
+  for (int l = 0; l < d.levels; ++l) {
+    ColJob& j = ca.job[ca.n_jobs++];
+    j.A = G.fg[l]; j.B = nullptr; j.H = d.H[l]; j.W = d.W[l]; j.kind = kColSingle;
+    j.tc = cols_per_cta(d.H[l]); j.cta_begin = cta; j.level = l; j.plan = d.col[l];
+    if (l == 0) { ca.fin.col_begin[0] = cta; ca.fin.col_end[0] = cta + col_ctas(d, 0); }
+    cta += col_ctas(d, l);
+    const size_t b = 2 * (size_t)j.tc * d.H[l] * sizeof(float2);
+    if (b > smem) smem = b;
+  }
+  ca.partial = partial;
+  ca.fin.mode = 2; ca.fin.levels = 1;  // the last CTA reduces the level-0 band sums into the state
+  ca.fin.band0_in = nullptr; ca.fin.band0_out = G.band0; ca.fin.counter = counters;
+  fft_cols_jobs_kernel<<<cta, kFftThreads, smem, st>>>(ca);
+  HG_POST_LAUNCH(false, st, "fft_cols_jobs");
+  return HG_OK;
 }
 
-// gt != NULL: the ground-truth side is computed into the workspace; gt_state != NULL: it is read from a state
-// prepared by hg_freq_gt_prepare (the ground truth of a camera does not change between its visits).
-static int freq_loss_impl(const float* rendered, const float* gt, void* gt_state, int32_t H, int32_t W, int32_t levels,
-                          float* stats, float* grad_rendered, void* ws, cudaStream_t st) {
-  if (!rendered || (!gt && !gt_state) || !stats || !ws) {
-    set_error("hg_freq_loss: NULL pointer");
+int hg_freq_forward(const float* rendered, const float* gt, void* gt_state, int32_t H, int32_t W, int32_t levels,
+                    float hf_thresh, float* hf_mask, float* hf_count, float* stats, void* ws, void* st_) {
+  if (!rendered || (!gt && !gt_state) || !stats || !ws || (hf_mask && !hf_count)) {
+    set_error("hg_freq_forward: NULL pointer");
     return HG_ERR_INVALID_ARG;
   }
-  int hs[3], wsz[3];
-  int rc0 = level_sizes(H, W, levels, hs, wsz);
-  if (rc0) return rc0;
-  Carver cv(ws);
-  LevelCtl* ctl = cv.take<LevelCtl>(3);
-  double* sums = cv.take<double>(kFreqSums);
-  float *gr[3], *dg[3];
-  float2* fr[3];
-  double *sp_part[3], *spec_part[3];
-  int sp_blocks[3];
-  for (int l = 0; l < levels; ++l) {
-    const size_t hw = (size_t)hs[l] * wsz[l], sp = (size_t)hs[l] * (wsz[l] / 2 + 1);
-    gr[l] = cv.take<float>(hw);
-    dg[l] = cv.take<float>(hw);
-    fr[l] = cv.take<float2>(sp);
-    sp_blocks[l] = ((wsz[l] + kSpTile - 1) / kSpTile) * ((hs[l] + kSpTile - 1) / kSpTile);
-    sp_part[l] = cv.take<double>((size_t)sp_blocks[l] * 3);
-    spec_part[l] = cv.take<double>((size_t)kSumBlocks * kSpecVals);
+  Dims d;
+  int rc = make_dims(H, W, levels, &d);
+  if (rc) return rc;
+  return freq_forward(rendered, gt_state ? nullptr : gt, gt_state, d, hf_thresh, hf_mask, hf_count, stats, ws,
+                      (cudaStream_t)st_);
+}
+
+int hg_freq_backward(void* gt_state, int32_t H, int32_t W, int32_t levels, int32_t forward_had_hf_mask,
+                     const float* gscale, float* grad_rendered, void* ws, void* st_) {
+  if (!grad_rendered || !ws) {
+    set_error("hg_freq_backward: NULL pointer");
+    return HG_ERR_INVALID_ARG;
   }
-  GtState G;
-  const bool cached = gt_state != nullptr;
-  carve_gt_state(cached ? gt_state : (void*)cv.p, levels, hs, wsz, &G);
-  float** gg = G.gg;
-  float2** fg = G.fg;
-  double* band0 = G.band0;
-  // ---- forward
-  const int64_t hw0 = (int64_t)H * W;
-  gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(rendered, hw0, gr[0]);
-  HG_POST_LAUNCH(false, st, "gray");
-  if (!cached) {
-    gray_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(gt, hw0, gg[0]);
-    HG_POST_LAUNCH(false, st, "gray");
-  }
-  for (int l = 1; l < levels; ++l) {
-    const dim3 grid((wsz[l] + 127) / 128, hs[l]);
-    pool_kernel<<<grid, 128, 0, st>>>(gr[l - 1], wsz[l - 1], hs[l], wsz[l], gr[l]);
-    HG_POST_LAUNCH(false, st, "pool");
-    if (!cached) {
-      pool_kernel<<<grid, 128, 0, st>>>(gg[l - 1], wsz[l - 1], hs[l], wsz[l], gg[l]);
-      HG_POST_LAUNCH(false, st, "pool");
-    }
-  }
-  FreqFinalizeArgs fa{};
-  fa.levels = levels;
-  for (int l = 0; l < levels; ++l) {
-    const dim3 grid((wsz[l] + kSpTile - 1) / kSpTile, (hs[l] + kSpTile - 1) / kSpTile);
-    spatial_kernel<false><<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gr[l], gg[l], hs[l], wsz[l], sp_part[l], nullptr, nullptr);
-    HG_POST_LAUNCH(false, st, "spatial");
-    // rendered + ground truth in one launch pair (rendered alone when the ground-truth spectra are cached)
-    int rc = cached ? fft2_r2c(gr[l], fr[l], nullptr, nullptr, hs[l], wsz[l], 1, st)
-                    : fft2_r2c(gr[l], fr[l], gg[l], fg[l], hs[l], wsz[l], 1, st);
-    if (rc) return rc;
-    spectral_sums_kernel<<<kSumBlocks, 256, 0, st>>>(fr[l], fg[l], hs[l], wsz[l], spec_part[l]);
-    HG_POST_LAUNCH(false, st, "spectral_sums");
-    fa.dim[l] = {hs[l], wsz[l]};
-    fa.spatial_partial[l] = sp_part[l];
-    fa.spatial_blocks[l] = sp_blocks[l];
-    fa.spectral_partial[l] = spec_part[l];
-  }
-  if (!cached) {
-    band_energy_kernel<<<kSumBlocks, 256, 0, st>>>(fg[0], hs[0], wsz[0], band0);
-    HG_POST_LAUNCH(false, st, "band_energy");
-  }
-  fa.band0_partial = band0;
-  fa.ctl = ctl;
-  fa.stats = stats;
-  fa.sums = sums;
-  freq_reduce_kernel<<<kFreqSums, 256, 0, st>>>(fa);
-  HG_POST_LAUNCH(false, st, "freq_reduce");
-  freq_finalize_kernel<<<1, 32, 0, st>>>(fa);
-  HG_POST_LAUNCH(false, st, "freq_finalize");
-  if (!grad_rendered) return HG_OK;
-  // ---- backward (unit upstream gradient on freq_loss)
-  for (int l = 0; l < levels; ++l) {
-    spectral_grad_kernel<<<kSumBlocks, 256, 0, st>>>(fr[l], fg[l], hs[l], wsz[l], ctl + l);
-    HG_POST_LAUNCH(false, st, "spectral_grad");
-    int rc = fft2_c2r(fr[l], hs[l], wsz[l], 1.0f, dg[l], st);
-    if (rc) return rc;
-    const int64_t hw = (int64_t)hs[l] * wsz[l];
-    clamp_gate_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, st>>>(gr[l], hw, dg[l]);
-    HG_POST_LAUNCH(false, st, "clamp_gate");
-    const dim3 grid((wsz[l] + kSpTile - 1) / kSpTile, (hs[l] + kSpTile - 1) / kSpTile);
-    spatial_kernel<true><<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gr[l], gg[l], hs[l], wsz[l], nullptr, ctl + l, dg[l]);
-    HG_POST_LAUNCH(false, st, "spatial_grad");
-  }
-  for (int l = levels - 1; l >= 1; --l) {
-    const dim3 grid((2 * wsz[l] + 127) / 128, 2 * hs[l]);
-    unpool_add_kernel<<<grid, 128, 0, st>>>(dg[l], hs[l], wsz[l], wsz[l - 1], dg[l - 1]);
-    HG_POST_LAUNCH(false, st, "unpool_add");
-  }
-  gray_to_rgb_grad_kernel<<<(unsigned)((hw0 + 255) / 256), 256, 0, st>>>(dg[0], hw0, grad_rendered);
-  HG_POST_LAUNCH(false, st, "gray_to_rgb_grad");
-  return HG_OK;
+  Dims d;
+  int rc = make_dims(H, W, levels, &d);
+  if (rc) return rc;
+  return freq_backward(gt_state, d, forward_had_hf_mask != 0, gscale, grad_rendered, ws, (cudaStream_t)st_);
 }
 
 int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, int32_t levels, float* stats,
@@ -1036,7 +1667,9 @@ int hg_freq_loss(const float* rendered, const float* gt, int32_t H, int32_t W, i
     set_error("hg_freq_loss: NULL pointer");
     return HG_ERR_INVALID_ARG;
   }
-  return freq_loss_impl(rendered, gt, nullptr, H, W, levels, stats, grad_rendered, ws, (cudaStream_t)st_);
+  int rc = hg_freq_forward(rendered, gt, nullptr, H, W, levels, 0.f, nullptr, nullptr, stats, ws, st_);
+  if (rc || !grad_rendered) return rc;
+  return hg_freq_backward(nullptr, H, W, levels, 0, nullptr, grad_rendered, ws, st_);
 }
 
 int hg_freq_loss_cached(const float* rendered, void* gt_state, int32_t H, int32_t W, int32_t levels, float* stats,
@@ -1045,12 +1678,16 @@ int hg_freq_loss_cached(const float* rendered, void* gt_state, int32_t H, int32_
     set_error("hg_freq_loss_cached: NULL ground-truth state");
     return HG_ERR_INVALID_ARG;
   }
-  return freq_loss_impl(rendered, nullptr, gt_state, H, W, levels, stats, grad_rendered, ws, (cudaStream_t)st_);
+  int rc = hg_freq_forward(rendered, nullptr, gt_state, H, W, levels, 0.f, nullptr, nullptr, stats, ws, st_);
+  if (rc || !grad_rendered) return rc;
+  return hg_freq_backward(gt_state, H, W, levels, 0, nullptr, grad_rendered, ws, st_);
 }
 
 size_t hg_hf_mask_workspace_bytes(int32_t H, int32_t W) {
-  const size_t hw = (size_t)H * W;
-  return 3 * (hw * 4 + 256) + (size_t)H * (W / 2 + 1) * 8 + 256 + 4 * (kSumBlocks * 8 + 256) + 1024;
+  Dims d;
+  d.levels = 1;
+  d.H[0] = H < 4 ? 4 : H; d.W[0] = W < 4 ? 4 : W;
+  return work_bytes(d, true, true);
 }
 
 int hg_hf_mask(const float* gt, int32_t H, int32_t W, float thresh, float* mask, float* count, void* ws, void* st_) {
@@ -1058,37 +1695,40 @@ int hg_hf_mask(const float* gt, int32_t H, int32_t W, float thresh, float* mask,
     set_error("hg_hf_mask: bad argument");
     return HG_ERR_INVALID_ARG;
   }
+  Dims d;
+  int rc = make_dims(H, W, 1, &d);
+  if (rc) return rc;
+  rc = set_fused_attrs();
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)st_;
-  Carver cv(ws);
-  const int64_t hw = (int64_t)H * W;
-  float* gray = cv.take<float>(hw);
-  float* spatial = cv.take<float>(hw);
-  float* hsp = cv.take<float>(hw);
-  float2* spec = cv.take<float2>((size_t)H * (W / 2 + 1));
-  float* pmin = cv.take<float>(kSumBlocks);
-  float* pmax = cv.take<float>(kSumBlocks);
-  float* mm = cv.take<float>(4);
-  double* part = cv.take<double>(kSumBlocks);
-  gray_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, st>>>(gt, hw, gray);
-  HG_POST_LAUNCH(false, st, "gray");
-  const dim3 grid((W + kSpTile - 1) / kSpTile, (H + kSpTile - 1) / kSpTile);
-  hf_spatial_kernel<<<grid, dim3(kSpTile, kSpTile), 0, st>>>(gray, H, W, spatial);
-  HG_POST_LAUNCH(false, st, "hf_spatial");
-  int rc = fft2_r2c(gray, spec, nullptr, nullptr, H, W, 0, st);  // unclamped here (frequency_regularization.py:1221)
+  Work w;
+  carve_work(ws, d, true, true, &w);
+  PyrArgs pa{};
+  pa.rgb[0] = gt; pa.rgb[1] = nullptr;
+  pa.gray[0][0] = w.gt.gg[0];
+  pa.n_images = 1;
+  fill_pyr_dims(&pa, d);
+  pa.hf_score = w.hf_score;
+  pa.hf_src = 0;
+  pa.counters = w.counters;
+  const dim3 tiles((W + kT0 - 1) / kT0, (H + kT0 - 1) / kT0);
+  pyramid_kernel<<<tiles, kImgThreads, 0, st>>>(pa);
+  HG_POST_LAUNCH(false, st, "pyramid");
+  RowArgs ra{};
+  int cta = 0;
+  ra.job[ra.n_jobs++] = row_job(w.gt.gg[0], w.hf_spec, d, 0, 0, &cta);  // unclamped (:1221)
+  rc = launch_rows(ra, cta, row_smem(d, 0), st);
   if (rc) return rc;
-  const int64_t nsp = (int64_t)H * (W / 2 + 1);
-  highpass_kernel<<<(unsigned)((nsp + 255) / 256), 256, 0, st>>>(spec, H, W);
-  HG_POST_LAUNCH(false, st, "highpass");
-  rc = fft2_c2r(spec, H, W, 1.0f / ((float)H * (float)W), hsp, st);
-  if (rc) return rc;
-  hf_reduce_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, spatial, mm, hw, 0, pmin, pmax);
-  hf_minmax_kernel<<<1, 32, 0, st>>>(pmin, pmax, kSumBlocks, mm);
-  hf_reduce_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, spatial, mm, hw, 1, pmin, pmax);
-  hf_minmax_kernel<<<1, 32, 0, st>>>(pmin, pmax, kSumBlocks, mm + 2);
-  hf_threshold_kernel<<<kSumBlocks, 256, 0, st>>>(hsp, mm + 2, hw, thresh, mask, part);
-  hf_count_kernel<<<1, 256, 0, st>>>(part, kSumBlocks, count);
-  HG_POST_LAUNCH(false, st, "hf_mask");
-  return HG_OK;
+  ColArgs ca{};
+  ColJob& j = ca.job[ca.n_jobs++];
+  j.A = w.hf_spec; j.B = nullptr; j.H = H; j.W = W; j.kind = kColHighpassInverse;
+  j.tc = 2 * cols_per_cta(H) > 4 ? 4 : 2 * cols_per_cta(H);
+  j.cta_begin = 0; j.level = -1; j.plan = d.col[0];
+  ca.partial = w.col_partial;
+  ca.fin.mode = 0;
+  fft_cols_jobs_kernel<<<(W / 2 + 1 + j.tc - 1) / j.tc, kFftThreads, 2 * (size_t)j.tc * H * sizeof(float2), st>>>(ca);
+  HG_POST_LAUNCH(false, st, "fft_cols_jobs");
+  return launch_hf_tail(d, w, thresh, mask, count, st);
 }
 
 }  // extern "C"

@@ -41,32 +41,48 @@ class GroundTruthCache:
 
 
 class _FreqLoss(torch.autograd.Function):
-    """compute_true_frequency_loss(build_pyramid(rendered), build_pyramid(gt))  (:1293-1325)."""
+    """compute_true_frequency_loss(build_pyramid(rendered), build_pyramid(gt))  (:1293-1325).
+
+    forward: hg_freq_forward (3 launches; with `hf_thresh` the high-frequency mask of the same ground truth rides the
+    same row / column kernels and comes back as the 3rd / 4th output); the workspace keeps the pyramids and spectra.
+    backward: hg_freq_backward (3 launches), the upstream scalar is folded into its last kernel."""
 
     @staticmethod
-    def forward(ctx, rendered, gt, levels, gt_state=None):
+    def forward(ctx, rendered, gt, levels, gt_state=None, hf_thresh=None):
         _check_cuda(rendered, gt)
         r, g = rendered.contiguous(), gt.contiguous()
         _, H, W = r.shape
-        stats = torch.empty(FREQ_STATS, dtype=torch.float32, device=r.device)
-        need = ctx.needs_input_grad[0]
-        grad = torch.empty_like(r) if need else None
-        with torch.cuda.device(r.device):
-            ws = _ws(_L().hg_freq_loss_workspace_bytes(H, W, levels), r.device)
-            if gt_state is None:
-                rc = _L().hg_freq_loss(r.data_ptr(), g.data_ptr(), H, W, levels, stats.data_ptr(),
-                                       grad.data_ptr() if need else None, ws.data_ptr(), _stream())
-            else:
-                rc = _L().hg_freq_loss_cached(r.data_ptr(), gt_state.data_ptr(), H, W, levels, stats.data_ptr(),
-                                              grad.data_ptr() if need else None, ws.data_ptr(), _stream())
+        dev = r.device
+        stats = torch.empty(FREQ_STATS, dtype=torch.float32, device=dev)
+        want_hf = hf_thresh is not None
+        mask = torch.empty((H, W), dtype=torch.float32, device=dev) if want_hf else None
+        count = torch.empty(1, dtype=torch.float32, device=dev) if want_hf else None
+        with torch.cuda.device(dev):
+            ws = _ws(_L().hg_freq_loss_workspace_bytes(H, W, levels), dev)
+            rc = _L().hg_freq_forward(r.data_ptr(), g.data_ptr(), gt_state.data_ptr() if gt_state is not None else None,
+                                      H, W, levels, float(hf_thresh) if want_hf else 0.0,
+                                      mask.data_ptr() if want_hf else None, count.data_ptr() if want_hf else None,
+                                      stats.data_ptr(), ws.data_ptr(), _stream())
         _lib.check(rc, "frequency loss")
-        ctx.grad = grad
+        ctx.state = (ws, gt_state, H, W, int(levels), want_hf, dev) if ctx.needs_input_grad[0] else None
         ctx.mark_non_differentiable(stats)
+        if want_hf:
+            ctx.mark_non_differentiable(mask, count)
+            return stats[0].clone(), stats, mask, count
         return stats[0].clone(), stats
 
     @staticmethod
-    def backward(ctx, g, _gs):
-        return (g * ctx.grad if ctx.needs_input_grad[0] else None), None, None, None
+    def backward(ctx, g, *_unused):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        ws, gt_state, H, W, levels, had_hf, dev = ctx.state
+        grad = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        gs = g.detach().reshape(1).to(dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            rc = _L().hg_freq_backward(gt_state.data_ptr() if gt_state is not None else None, H, W, levels, int(had_hf),
+                                       gs.data_ptr(), grad.data_ptr(), ws.data_ptr(), _stream())
+        _lib.check(rc, "frequency loss backward")
+        return grad, None, None, None, None
 
 
 class _ScaleReg(torch.autograd.Function):
@@ -185,12 +201,16 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
     stats = None
     if gt_cache is not None and not gt_cache.matches(g, num_levels, high_freq_thresh):
         raise RuntimeError("gt_cache was built for another image size / level count / threshold")
-    if lambda_freq > 0:
-        freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels), gt_cache.state if gt_cache is not None else None)
-        total = lambda_freq * freq_loss
+    mask = count = None
     if gt_cache is not None:
         mask, count = gt_cache.mask, gt_cache.count
-    else:
+    if lambda_freq > 0:
+        if mask is None:  # the mask of this ground truth comes out of the regulariser's own launches
+            freq_loss, stats, mask, count = _FreqLoss.apply(r, g.detach(), int(num_levels), None, float(high_freq_thresh))
+        else:
+            freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels), gt_cache.state)
+        total = lambda_freq * freq_loss
+    elif mask is None:
         mask, count = detect_true_high_frequency_regions(g, high_freq_thresh)
     scale_loss = None
     if lambda_scale > 0:

@@ -381,12 +381,19 @@ class ViewShardedTrainer:
             freq_total = None
             if freq_on:  # frequency_regularization_pyramid_scale (same arithmetic, same order)
                 if o.lambda_freq > 0:
-                    tF = T(True, False, False, False)
-                    freq_loss, _stats = _FreqLoss.forward(tF, image, gt, 3, cache[1].state if cache is not None else None)
+                    tF = T(True, False, False, False, False)
+                    if cache is not None:
+                        freq_loss, _stats = _FreqLoss.forward(tF, image, gt, 3, cache[1].state)
+                    else:  # the high-frequency mask of this ground truth rides the same launches
+                        freq_loss, _stats, _mask, hf_count = _FreqLoss.forward(tF, image, gt, 3, None, 0.2)
                     freq_total = o.lambda_freq * freq_loss
                 if o.lambda_scale > 0:
-                    nonempty = cache[1].nonempty if cache is not None else \
-                        (detect_true_high_frequency_regions(gt)[1][0] > 0).float()
+                    if cache is not None:
+                        nonempty = cache[1].nonempty
+                    elif tF is not None:
+                        nonempty = (hf_count[0] > 0).float()
+                    else:
+                        nonempty = (detect_true_high_frequency_regions(gt)[1][0] > 0).float()
                     tSc = T(True, False)
                     scale_loss = _ScaleReg.forward(tSc, scaling, visible)
                     term = o.lambda_scale * scale_loss * nonempty
@@ -405,11 +412,12 @@ class ViewShardedTrainer:
             if self._one is None:
                 self._one = torch.ones((), dtype=torch.float32, device=dev)
             g_color = lu._SSIM.backward(tS, self._one)[0]
-            w_freq = (gate * o.lambda_freq) if tF is not None else None
+            # d(lambda_freq * clamp gate * freq_loss) / d image: the scalar rides the regulariser's last backward kernel
+            g_freq = _FreqLoss.backward(tF, gate * o.lambda_freq)[0] if tF is not None else None
             with torch.cuda.device(dev):
                 rc = lu._L().hg_training_image_grad(
-                    color.data_ptr(), gt.data_ptr(), g_color.data_ptr(), tF.grad.data_ptr() if tF is not None else None,
-                    color.numel(), 1.0 - o.lambda_dssim, -o.lambda_dssim, w_freq.data_ptr() if w_freq is not None else None,
+                    color.data_ptr(), gt.data_ptr(), g_color.data_ptr(), g_freq.data_ptr() if g_freq is not None else None,
+                    color.numel(), 1.0 - o.lambda_dssim, -o.lambda_dssim, self._one.data_ptr() if g_freq is not None else None,
                     g_color.data_ptr(), torch.cuda.current_stream().cuda_stream)
             _lib.check(rc, "training_image_grad")
             g_pd = tN.gd.reshape(plane_depth.shape) if tN is not None else None

@@ -96,6 +96,21 @@ HG_API size_t hg_freq_loss_workspace_bytes(int32_t H, int32_t W, int32_t levels)
 HG_API int hg_freq_loss(const float *rendered, const float *gt, int32_t H, int32_t W, int32_t levels,
                         float *stats, float *grad_rendered, void *workspace, void *stream);
 
+/* The same regulariser as two calls, for callers that keep the forward state until a backward arrives (autograd):
+ *   hg_freq_forward   value + stats (as hg_freq_loss); the ground truth comes either as the image `gt` or as a state
+ *                     prepared by hg_freq_gt_prepare (`gt_state`, then `gt` may be NULL).  If hf_mask != NULL the
+ *                     high-frequency mask of the same ground truth (hg_hf_mask: mask [H,W], hf_count[0] = sum) is produced
+ *                     by the same launches (its row / column transforms ride the regulariser's kernels).
+ *   hg_freq_backward  grad_rendered [3,H,W] = gscale[0] * d freq_loss / d rendered (gscale: DEVICE scalar, NULL = 1) from
+ *                     the state hg_freq_forward left in `workspace` (same H, W, levels, gt_state; forward_had_hf_mask
+ *                     tells whether that forward call produced the mask, which fixes the workspace layout).
+ * Six launches in total (nine with the mask); the scalar epilogue runs in the last CTA of the column kernel. */
+HG_API int hg_freq_forward(const float *rendered, const float *gt, void *gt_state, int32_t H, int32_t W, int32_t levels,
+                           float hf_thresh, float *hf_mask, float *hf_count, float *stats, void *workspace,
+                           void *stream);
+HG_API int hg_freq_backward(void *gt_state, int32_t H, int32_t W, int32_t levels, int32_t forward_had_hf_mask,
+                            const float *gscale, float *grad_rendered, void *workspace, void *stream);
+
 /* The ground-truth side of hg_freq_loss (gray pyramid of gt, its spectra, the level-0 band sums) depends on the camera's
  * image only.  A training loop that revisits a camera prepares it once (hg_freq_gt_prepare into a caller-owned state of
  * hg_freq_gt_state_bytes bytes) and calls hg_freq_loss_cached, which is hg_freq_loss minus that work (3 of the 6
