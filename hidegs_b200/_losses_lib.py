@@ -4,7 +4,7 @@ import ctypes
 from . import _lib
 
 EXPORTED_SYMBOLS = (
-    "hg_reduce_workspace_bytes", "hg_l1_loss", "hg_l2_loss", "hg_training_image_grad", "hg_ssim_workspace_bytes", "hg_ssim", "hg_ssim_backward",
+    "hg_reduce_workspace_bytes", "hg_l1_loss", "hg_l2_loss", "hg_pixel_loss_backward", "hg_freq_total", "hg_training_image_grad", "hg_ssim_workspace_bytes", "hg_ssim", "hg_ssim_backward",
     "hg_img_grad_weight_workspace_bytes", "hg_img_grad_weight", "hg_lncc", "hg_lncc_backward",
     "hg_scale_reg_workspace_bytes", "hg_scale_reg", "hg_fft2_workspace_bytes", "hg_fft2_r2c", "hg_fft2_c2r",
     "hg_freq_loss_workspace_bytes", "hg_freq_loss", "hg_freq_forward", "hg_freq_backward", "hg_freq_gt_state_bytes", "hg_freq_gt_prepare", "hg_freq_loss_cached", "hg_hf_mask_workspace_bytes", "hg_hf_mask",
@@ -23,6 +23,8 @@ def lib():
         "hg_reduce_workspace_bytes": (sz, [i64]),
         "hg_l1_loss": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
         "hg_l2_loss": (ctypes.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+        "hg_pixel_loss_backward": (ctypes.c_int, [vp, vp, i64, i32, vp, vp, vp, vp]),
+        "hg_freq_total": (ctypes.c_int, [vp, vp, vp, f32, f32, vp, vp]),
         "hg_training_image_grad": (ctypes.c_int, [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp]),
         "hg_ssim_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "hg_ssim": (ctypes.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),

@@ -74,14 +74,56 @@ const float2* twiddle_table(int n) {
   return d;
 }
 
+// fewest passes over the radices {10, 9, 8, 6, 5, 4, 3, 2} for m = 2^a 3^b 5^c (0: m has another prime factor)
+static int fewest_passes(int m, int* out) {
+  static const int kRadices[] = {10, 9, 8, 6, 5, 4, 3, 2};
+  if (m == 1) return 0;
+  int best = 0, tmp[kMaxRadices], keep[kMaxRadices];
+  for (int r : kRadices) {
+    if (m % r) continue;
+    const int sub = fewest_passes(m / r, tmp + 1);
+    if (m / r != 1 && sub == 0) continue;
+    if (best == 0 || sub + 1 < best) {
+      best = sub + 1;
+      keep[0] = r;
+      for (int i = 0; i < sub; ++i) keep[1 + i] = tmp[1 + i];
+    }
+  }
+  for (int i = 0; i < best && i < kMaxRadices; ++i) out[i] = keep[i];
+  return best;
+}
+
+static bool build_plan(int n, Plan* p);
+
+// plans are built once per (device, length) and kept (the pass search and the twiddle upload run once)
 bool make_plan(int n, Plan* p) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, Plan> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({dev, n});
+    if (it != cache.end()) { *p = it->second; return true; }
+  }
+  if (!build_plan(n, p)) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  cache[{dev, n}] = *p;
+  return true;
+}
+
+static bool build_plan(int n, Plan* p) {
   p->n = n;
   p->nr = 0;
-  int m = n;
-  while (m % 4 == 0) { p->radix[p->nr++] = 4; m /= 4; }
-  while (m % 2 == 0) { p->radix[p->nr++] = 2; m /= 2; }
-  while (m % 3 == 0) { p->radix[p->nr++] = 3; m /= 3; }
-  while (m % 5 == 0) { p->radix[p->nr++] = 5; m /= 5; }
+  int m = n, smooth = 1;
+  for (int f : {2, 3, 5})
+    while (m % f == 0) { m /= f; smooth *= f; }
+  if (smooth > 1) {
+    int r[kMaxRadices];
+    const int k = fewest_passes(smooth, r);
+    if (k <= 0 || k > kMaxRadices) return false;
+    for (int i = 0; i < k; ++i) p->radix[p->nr++] = r[i];
+  }
   // any other prime factor runs through the generic O(R^2) butterfly (a prime length is one pass of
   // radix n, i.e. the plain DFT): every size works, sizes of the form 2^a 3^b 5^c are the fast path
   for (int f = 7; m > 1 && p->nr < kMaxRadices; f += 2) {
@@ -148,6 +190,108 @@ __device__ __forceinline__ void dft<5>(float2* v) {
   v[3] = csub(m2, n2);
 }
 
+// ---- composite butterflies (Cooley-Tukey inside the registers of one thread): radix R1 * R2 from dft<R1>, dft<R2>
+// and the constant twiddles W_N^m = exp(-2 pi i m / N).  Radices 6, 8, 9, 10 bring 1080 / 1920-point transforms (and
+// their pyramid halves) down to 3-4 shared-memory passes instead of 5-6.
+template <int N>
+__device__ __forceinline__ float2 twc(int m);
+template <>
+__device__ __forceinline__ float2 twc<6>(int m) {
+  switch (m) {
+    case 1: return make_float2(0.5f, -0.866025404f);
+    case 2: return make_float2(-0.5f, -0.866025404f);
+    case 3: return make_float2(-1.f, 0.f);
+    case 4: return make_float2(-0.5f, 0.866025404f);
+    case 5: return make_float2(0.5f, 0.866025404f);
+    default: return make_float2(1.f, 0.f);
+  }
+}
+template <>
+__device__ __forceinline__ float2 twc<8>(int m) {
+  switch (m) {
+    case 1: return make_float2(0.707106781f, -0.707106781f);
+    case 2: return make_float2(0.f, -1.f);
+    case 3: return make_float2(-0.707106781f, -0.707106781f);
+    case 4: return make_float2(-1.f, 0.f);
+    case 5: return make_float2(-0.707106781f, 0.707106781f);
+    case 6: return make_float2(0.f, 1.f);
+    case 7: return make_float2(0.707106781f, 0.707106781f);
+    default: return make_float2(1.f, 0.f);
+  }
+}
+template <>
+__device__ __forceinline__ float2 twc<9>(int m) {
+  switch (m) {
+    case 1: return make_float2(0.766044443f, -0.64278761f);
+    case 2: return make_float2(0.173648178f, -0.984807753f);
+    case 3: return make_float2(-0.5f, -0.866025404f);
+    case 4: return make_float2(-0.939692621f, -0.342020143f);
+    case 5: return make_float2(-0.939692621f, 0.342020143f);
+    case 6: return make_float2(-0.5f, 0.866025404f);
+    case 7: return make_float2(0.173648178f, 0.984807753f);
+    case 8: return make_float2(0.766044443f, 0.64278761f);
+    default: return make_float2(1.f, 0.f);
+  }
+}
+template <>
+__device__ __forceinline__ float2 twc<10>(int m) {
+  switch (m) {
+    case 1: return make_float2(0.809016994f, -0.587785252f);
+    case 2: return make_float2(0.309016994f, -0.951056516f);
+    case 3: return make_float2(-0.309016994f, -0.951056516f);
+    case 4: return make_float2(-0.809016994f, -0.587785252f);
+    case 5: return make_float2(-1.f, 0.f);
+    case 6: return make_float2(-0.809016994f, 0.587785252f);
+    case 7: return make_float2(-0.309016994f, 0.951056516f);
+    case 8: return make_float2(0.309016994f, 0.951056516f);
+    case 9: return make_float2(0.809016994f, 0.587785252f);
+    default: return make_float2(1.f, 0.f);
+  }
+}
+
+template <int R1, int R2>
+__device__ __forceinline__ void dft_ct(float2* v) {
+  constexpr int N = R1 * R2;
+  float2 y[N];  // y[k1 * R2 + i2]
+#pragma unroll
+  for (int i2 = 0; i2 < R2; ++i2) {
+    float2 t[R1];
+#pragma unroll
+    for (int i1 = 0; i1 < R1; ++i1) t[i1] = v[i1 * R2 + i2];
+    dft<R1>(t);
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+      const int m = (i2 * k1) % N;
+      y[k1 * R2 + i2] = (m == 0) ? t[k1] : cmul(t[k1], twc<N>(m));
+    }
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < R1; ++k1) {
+    float2 t[R2];
+#pragma unroll
+    for (int i2 = 0; i2 < R2; ++i2) t[i2] = y[k1 * R2 + i2];
+    dft<R2>(t);
+#pragma unroll
+    for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = t[k2];
+  }
+}
+template <>
+__device__ __forceinline__ void dft<6>(float2* v) { dft_ct<2, 3>(v); }
+template <>
+__device__ __forceinline__ void dft<8>(float2* v) { dft_ct<2, 4>(v); }
+template <>
+__device__ __forceinline__ void dft<9>(float2* v) { dft_ct<3, 3>(v); }
+template <>
+__device__ __forceinline__ void dft<10>(float2* v) { dft_ct<2, 5>(v); }
+
+// w / d and w % d for 0 <= w < 2^24, 1 <= d <= 2^16 without an integer division (float reciprocal + one correction)
+__device__ __forceinline__ void fast_divmod(int w, int d, float inv_d, int& q, int& r) {
+  q = (int)((float)w * inv_d);
+  r = w - q * d;
+  if (r < 0) { r += d; --q; }
+  else if (r >= d) { r -= d; ++q; }
+}
+
 // One Stockham pass of radix R over `batch` independent length-n sequences stored back to back.
 // Twiddle of butterfly input r at position k of a sub-transform of length ns*R:  tw[(k r) * n / (ns R)].
 template <int R>
@@ -155,11 +299,14 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, fl
                                               int ns, int batch, const float2* __restrict__ tw) {
   const int per = n / R;
   const int tstep = n / (ns * R);
+  const float inv_per = 1.0f / (float)per, inv_ns = 1.0f / (float)ns;
   for (int w = threadIdx.x; w < per * batch; w += blockDim.x) {
-    const int b = w / per, j = w - b * per;
+    int b = 0, j = w;
+    if (batch > 1) fast_divmod(w, per, inv_per, b, j);
     const float2* s = src + b * n;
     float2* d = dst + b * n;
-    const int k = j % ns;
+    int q = 0, k = 0;
+    if (ns > 1) fast_divmod(j, ns, inv_ns, q, k);
     float2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = s[j + r * per];
@@ -205,7 +352,11 @@ __device__ float2* fft_smem(float2* a, float2* b, const Plan& p, int batch) {
   float2 *src = a, *dst = b;
   for (int i = 0; i < p.nr; ++i) {
     const int R = p.radix[i];
-    if (R == 4) stockham_pass<4>(src, dst, p.n, ns, batch, p.tw);
+    if (R == 8) stockham_pass<8>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 10) stockham_pass<10>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 9) stockham_pass<9>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 6) stockham_pass<6>(src, dst, p.n, ns, batch, p.tw);
+    else if (R == 4) stockham_pass<4>(src, dst, p.n, ns, batch, p.tw);
     else if (R == 2) stockham_pass<2>(src, dst, p.n, ns, batch, p.tw);
     else if (R == 3) stockham_pass<3>(src, dst, p.n, ns, batch, p.tw);
     else if (R == 5) stockham_pass<5>(src, dst, p.n, ns, batch, p.tw);
@@ -444,7 +595,8 @@ struct PyrArgs {
   unsigned* counters;             // 8 words zeroed by CTA 0 (tickets of the later last-block reductions)
 };
 
-__global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
+template <int NI>
+__global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const __grid_constant__ PyrArgs a) {
   __shared__ float g0[2][kT0 + 8][kT0 + 9];
   __shared__ float g1[2][kT0 / 2 + 4][kT0 / 2 + 5];
   __shared__ float g2[2][kT0 / 4 + 2][kT0 / 4 + 3];
@@ -459,7 +611,7 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
     const int r = i / E0, c = i - r * E0;
     const int y = y0 + r - 4, x = x0 + c - 4;
     const bool in = y >= 0 && y < H0 && x >= 0 && x < W0;
-    for (int im = 0; im < a.n_images; ++im) {
+    _Pragma("unroll") for (int im = 0; im < NI; ++im) {
       float v = 0.f;
       if (in) {
         const size_t p = (size_t)y * W0 + x;
@@ -474,7 +626,7 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
     const int r = i / kT0, c = i - r * kT0;
     const int y = y0 + r, x = x0 + c;
     if (y < H0 && x < W0)
-      for (int im = 0; im < a.n_images; ++im)
+      _Pragma("unroll") for (int im = 0; im < NI; ++im)
         if (a.rgb[im]) a.gray[im][0][(size_t)y * W0 + x] = g0[im][r + 4][c + 4];
   }
   const int H1 = a.levels > 1 ? a.H[1] : 0, W1 = a.levels > 1 ? a.W[1] : 0;
@@ -485,7 +637,7 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
       const int r = i / E1, c = i - r * E1;
       const int Y = (y0 >> 1) + r - 2, X = (x0 >> 1) + c - 2;
       const bool ok = Y >= 0 && Y < H1 && X >= 0 && X < W1;
-      for (int im = 0; im < a.n_images; ++im)
+      _Pragma("unroll") for (int im = 0; im < NI; ++im)
         g1[im][r][c] = ok ? (g0[im][2 * r][2 * c] + g0[im][2 * r][2 * c + 1] + g0[im][2 * r + 1][2 * c] +
                              g0[im][2 * r + 1][2 * c + 1]) * 0.25f : 0.f;
     }
@@ -494,7 +646,7 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
       const int r = tid >> 4, c = tid & 15;
       const int Y = (y0 >> 1) + r, X = (x0 >> 1) + c;
       if (Y < H1 && X < W1)
-        for (int im = 0; im < a.n_images; ++im)
+        _Pragma("unroll") for (int im = 0; im < NI; ++im)
           if (a.rgb[im]) a.gray[im][1][(size_t)Y * W1 + X] = g1[im][r + 2][c + 2];
     }
   }
@@ -504,7 +656,7 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
       const int r = i / E2, c = i - r * E2;
       const int Y = (y0 >> 2) + r - 1, X = (x0 >> 2) + c - 1;
       const bool ok = Y >= 0 && Y < H2 && X >= 0 && X < W2;
-      for (int im = 0; im < a.n_images; ++im)
+      _Pragma("unroll") for (int im = 0; im < NI; ++im)
         g2[im][r][c] = ok ? (g1[im][2 * r][2 * c] + g1[im][2 * r][2 * c + 1] + g1[im][2 * r + 1][2 * c] +
                              g1[im][2 * r + 1][2 * c + 1]) * 0.25f : 0.f;
     }
@@ -513,7 +665,7 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
       const int r = tid >> 3, c = tid & 7;
       const int Y = (y0 >> 2) + r, X = (x0 >> 2) + c;
       if (Y < H2 && X < W2)
-        for (int im = 0; im < a.n_images; ++im)
+        _Pragma("unroll") for (int im = 0; im < NI; ++im)
           if (a.rgb[im]) a.gray[im][2][(size_t)Y * W2 + X] = g2[im][r + 1][c + 1];
     }
   }
@@ -530,22 +682,22 @@ __global__ void __launch_bounds__(kImgThreads) pyramid_kernel(const PyrArgs a) {
       }
     }
   }
-  if (!a.partial || a.n_images < 2) return;
+  if (!a.partial || NI < 2) return;
   // ---- Sobel / Laplacian of d = gray_rendered - gray_gt at every level (d = 0 outside the image)
   __syncthreads();
   for (int i = tid; i < E0 * E0; i += kImgThreads) {
     const int r = i / E0, c = i - r * E0;
-    g0[0][r][c] -= g0[1][r][c];
+    g0[0][r][c] -= g0[NI - 1][r][c];
   }
   if (a.levels > 1)
     for (int i = tid; i < (kT0 / 2 + 4) * (kT0 / 2 + 4); i += kImgThreads) {
       const int r = i / (kT0 / 2 + 4), c = i - r * (kT0 / 2 + 4);
-      g1[0][r][c] -= g1[1][r][c];
+      g1[0][r][c] -= g1[NI - 1][r][c];
     }
   if (a.levels > 2)
     for (int i = tid; i < (kT0 / 4 + 2) * (kT0 / 4 + 2); i += kImgThreads) {
       const int r = i / (kT0 / 4 + 2), c = i - r * (kT0 / 4 + 2);
-      g2[0][r][c] -= g2[1][r][c];
+      g2[0][r][c] -= g2[NI - 1][r][c];
     }
   __syncthreads();
   float acc[9];
@@ -599,7 +751,7 @@ struct RowJob {
 };
 struct RowArgs { int n_jobs; RowJob job[kMaxRowJobs]; };
 
-__global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const RowArgs a) {
+__global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ float2 sm[];
   int j = 0;
   for (int k = 1; k < a.n_jobs; ++k)
@@ -608,8 +760,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const RowArg
   const int W = J.W, H = J.H, pairs = J.pairs;
   const int p0 = ((int)blockIdx.x - J.cta_begin) * pairs;
   float2 *bufa = sm, *bufb = sm + pairs * W;
+  const float inv_w = 1.0f / (float)W;
   for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
-    const int pr = i / W, x = i - pr * W;
+    int pr = 0, x = i;
+    if (pairs > 1) fast_divmod(i, W, inv_w, pr, x);
     const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
     float v0 = r0 < H ? __ldg(J.src + (size_t)r0 * W + x) : 0.f;
     float v1 = r1 < H ? __ldg(J.src + (size_t)r1 * W + x) : 0.f;
@@ -619,8 +773,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const RowArg
   __syncthreads();
   const float2* z = fft_smem(bufa, bufb, J.plan, pairs);
   const int Wh = W / 2 + 1;
+  const float inv_wh = 1.0f / (float)Wh;
   for (int i = threadIdx.x; i < pairs * Wh; i += blockDim.x) {
-    const int pr = i / Wh, k = i - pr * Wh;
+    int pr = 0, k = i;
+    if (pairs > 1) fast_divmod(i, Wh, inv_wh, pr, k);
     const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
     if (r0 >= H) continue;
     const float2* zz = z + pr * W;
@@ -765,7 +921,7 @@ struct ColArgs {
   FinalizeArgs fin;
 };
 
-__global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const ColArgs a) {
+__global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const __grid_constant__ ColArgs a) {
   extern __shared__ float2 sm[];
   __shared__ float red[kFftThreads / 32][kColVals];
   __shared__ int s_last;
@@ -778,9 +934,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const ColArg
   const int c0 = ((int)blockIdx.x - J.cta_begin) * tc;
   const int nc = min(tc, Wh - c0);
   const int nseq = kind == kColPair ? 2 * tc : tc;
+  const int tsh = tc == 4 ? 2 : (tc == 2 ? 1 : 0);  // tc is 1, 2 or 4
   float2 *bufa = sm, *bufb = sm + (size_t)nseq * H;
   for (int i = tid; i < H * tc; i += kFftThreads) {
-    const int y = i / tc, c = i - y * tc;
+    const int y = i >> tsh, c = i - (y << tsh);
     float2 v = make_float2(0.f, 0.f), w = v;
     if (c < nc) {
       v = J.A[(size_t)y * Wh + c0 + c];
@@ -796,7 +953,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const ColArg
     // column transform (conj -> FFT -> conj) of the same columns
     const float radius = (float)((double)min(H / 2, W / 2) * 0.3);
     for (int i = tid; i < H * tc; i += kFftThreads) {
-      const int y = i / tc, c = i - y * tc;
+      const int y = i >> tsh, c = i - (y << tsh);
       const int fy = signed_freq(y, H), fx = signed_freq(c0 + c, W);
       const float dist = sqrtf((float)(fy * fy + fx * fx));
       float2 v = r[c * H + y];
@@ -807,7 +964,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const ColArg
     __syncthreads();
     float2* r2 = fft_smem(r, r == bufa ? bufb : bufa, J.plan, tc);
     for (int i = tid; i < H * tc; i += kFftThreads) {
-      const int y = i / tc, c = i - y * tc;
+      const int y = i >> tsh, c = i - (y << tsh);
       if (c < nc) {
         float2 v = r2[c * H + y];
         v.y = -v.y;
@@ -821,7 +978,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const ColArg
     const bool sums = kind != kColSingle;
     const bool band0 = J.level == 0;
     for (int i = tid; i < H * tc; i += kFftThreads) {
-      const int y = i / tc, c = i - y * tc;
+      const int y = i >> tsh, c = i - (y << tsh);
       if (c >= nc) continue;
       const int kx = c0 + c;
       const size_t p = (size_t)y * Wh + kx;
@@ -891,7 +1048,7 @@ struct GradJob {
 };
 struct GradArgs { int n_jobs; GradJob job[kMaxLevels]; const LevelCtl* ctl; };
 
-__global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const GradArgs a) {
+__global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const __grid_constant__ GradArgs a) {
   extern __shared__ float2 sm[];
   const int tid = threadIdx.x;
   int j = 0;
@@ -903,9 +1060,10 @@ __global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const G
   const int nc = min(tc, Wh - c0);
   const LevelCtl* ctl = a.ctl + J.level;
   const float c_mag = ctl->c_mag, c_phase = ctl->c_phase;
+  const int tsh = tc == 4 ? 2 : (tc == 2 ? 1 : 0);  // tc is 1, 2 or 4
   float2 *bufa = sm, *bufb = sm + (size_t)tc * H;
   for (int i = tid; i < H * tc; i += kFftThreads) {
-    const int ky = i / tc, c = i - ky * tc;
+    const int ky = i >> tsh, c = i - (ky << tsh);
     float gre = 0.f, gim = 0.f;
     if (c < nc) {
       const int kx = c0 + c;
@@ -933,7 +1091,7 @@ __global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const G
   __syncthreads();
   const float2* r = fft_smem(bufa, bufb, J.plan, tc);
   for (int i = tid; i < H * tc; i += kFftThreads) {
-    const int y = i / tc, c = i - y * tc;
+    const int y = i >> tsh, c = i - (y << tsh);
     if (c < nc) {
       float2 v = r[c * H + y];
       v.y = -v.y;
@@ -959,7 +1117,7 @@ struct InvArgs {
   unsigned* counter;
 };
 
-__global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const InvArgs a) {
+__global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const __grid_constant__ InvArgs a) {
   extern __shared__ float2 sm[];
   __shared__ float smax[kFftThreads / 32];
   __shared__ int s_last;
@@ -970,8 +1128,10 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const In
   const int W = J.W, H = J.H, Wh = W / 2 + 1, pairs = J.pairs;
   const int p0 = ((int)blockIdx.x - J.cta_begin) * pairs;
   float2 *bufa = sm, *bufb = sm + pairs * W;
+  const float inv_w = 1.0f / (float)W;
   for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
-    const int pr = i / W, x = i - pr * W;
+    int pr = 0, x = i;
+    if (pairs > 1) fast_divmod(i, W, inv_w, pr, x);
     const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
     const bool upper = x >= Wh;
     const int k = upper ? W - x : x;
@@ -985,7 +1145,8 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const In
   const float2* r = fft_smem(bufa, bufb, J.plan, pairs);
   float vmax = 0.f;
   for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
-    const int pr = i / W, x = i - pr * W;
+    int pr = 0, x = i;
+    if (pairs > 1) fast_divmod(i, W, inv_w, pr, x);
     const int r0 = 2 * (p0 + pr), r1 = r0 + 1;
     if (r0 >= H) continue;
     const float2 v = r[i];
@@ -1081,7 +1242,7 @@ __device__ __forceinline__ void load_diff(float (*d)[T + 5], const float* __rest
   }
 }
 
-__global__ void __launch_bounds__(kImgThreads) spatial_grad_rgb_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kImgThreads) spatial_grad_rgb_kernel(const __grid_constant__ BwdArgs a) {
   constexpr int T0 = kT0, T1 = kT0 / 2, T2 = kT0 / 4;
   __shared__ float d0[T0 + 4][T0 + 5], d1[T1 + 4][T1 + 5], d2[T2 + 4][T2 + 5];
   __shared__ float rx0[T0 + 2][T0 + 3], ry0[T0 + 2][T0 + 3], rl0[T0 + 2][T0 + 3];
@@ -1236,9 +1397,9 @@ struct Carver {
 static inline size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 
 // columns per CTA of the column kernels: the pair job keeps 2 * tc columns twice (ping-pong) in shared memory
-static int cols_per_cta(int H) {
-  int tc = (int)((72 * 1024) / (32 * (size_t)H));
-  return tc > 4 ? 4 : (tc < 1 ? 1 : tc);
+static int cols_per_cta(int H) {  // 1, 2 or 4 (a power of two: the kernels index with shifts)
+  const int tc = (int)((72 * 1024) / (32 * (size_t)H));
+  return tc >= 4 ? 4 : (tc >= 2 ? 2 : 1);
 }
 // row pairs per CTA of the row kernels: about 2048 points per CTA (1 / 2 / 4 pairs at 1920 / 960 / 480 columns)
 static int pairs_per_cta(int W) {
@@ -1437,7 +1598,7 @@ static int freq_forward(const float* rendered, const float* gt, void* gt_state, 
   pa.hf_src = 1;
   pa.counters = w.counters;
   const dim3 tiles((d.W[0] + kT0 - 1) / kT0, (d.H[0] + kT0 - 1) / kT0);
-  pyramid_kernel<<<tiles, kImgThreads, 0, st>>>(pa);
+  pyramid_kernel<2><<<tiles, kImgThreads, 0, st>>>(pa);
   HG_POST_LAUNCH(false, st, "pyramid");
   // ---- rows
   RowArgs ra{};
@@ -1605,7 +1766,7 @@ int hg_freq_gt_prepare(const float* gt, int32_t H, int32_t W, int32_t levels, vo
   fill_pyr_dims(&pa, d);
   pa.counters = counters;
   const dim3 tiles((d.W[0] + kT0 - 1) / kT0, (d.H[0] + kT0 - 1) / kT0);
-  pyramid_kernel<<<tiles, kImgThreads, 0, st>>>(pa);
+  pyramid_kernel<1><<<tiles, kImgThreads, 0, st>>>(pa);
   HG_POST_LAUNCH(false, st, "pyramid");
   RowArgs ra{};
   int cta = 0;
@@ -1712,7 +1873,7 @@ int hg_hf_mask(const float* gt, int32_t H, int32_t W, float thresh, float* mask,
   pa.hf_src = 0;
   pa.counters = w.counters;
   const dim3 tiles((W + kT0 - 1) / kT0, (H + kT0 - 1) / kT0);
-  pyramid_kernel<<<tiles, kImgThreads, 0, st>>>(pa);
+  pyramid_kernel<1><<<tiles, kImgThreads, 0, st>>>(pa);
   HG_POST_LAUNCH(false, st, "pyramid");
   RowArgs ra{};
   int cta = 0;

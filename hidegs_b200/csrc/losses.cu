@@ -98,6 +98,40 @@ int run_pixel_loss(const float* a, const float* b, int64_t n, float* out, float*
   return HG_OK;
 }
 
+// d (g * mean |a - b|) / da  (or the squared difference); grad_b = -grad_a.  The upstream scalar is read from the device.
+template <bool L2>
+__global__ void __launch_bounds__(256)
+pixel_loss_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, const float* __restrict__ gscale,
+                      float* __restrict__ grad_a, float* __restrict__ grad_b) {
+  const float s = (gscale ? __ldg(gscale) : 1.0f) / (float)n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    const float g = L2 ? 2.0f * d * s : (d > 0.f ? s : (d < 0.f ? -s : 0.f));
+    if (grad_a) grad_a[i] = g;
+    if (grad_b) grad_b[i] = -g;
+  }
+}
+
+// total = clamp(lambda_freq * freq + lambda_scale * scale * [count > 0], 0, 1) of frequency_regularization_pyramid_scale
+// (:1636-1660) and its two partial derivatives, in one launch: out = [total, d total / d freq, d total / d scale]
+__global__ void freq_total_kernel(const float* __restrict__ freq, const float* __restrict__ scale,
+                                  const float* __restrict__ count, float lambda_freq, float lambda_scale,
+                                  float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float nonempty = (count && count[0] > 0.f) ? 1.f : 0.f;
+  float t = 0.f;
+  if (freq) t = lambda_freq * freq[0];
+  if (scale) {
+    const float term = lambda_scale * scale[0] * nonempty;
+    t = freq ? t + term : term;
+  }
+  const float gate = (t >= 0.f && t <= 1.0f) ? 1.f : 0.f;  // d clamp(t, 0, 1) / dt
+  out[0] = fminf(fmaxf(t, 0.f), 1.0f);
+  out[1] = freq ? gate * lambda_freq : 0.f;
+  out[2] = scale ? gate * lambda_scale * nonempty : 0.f;
+}
+
 // ---------------------------------------------------------------- composed image gradient of the training loss
 __global__ void __launch_bounds__(256)
 training_image_grad_kernel(const float* __restrict__ color, const float* __restrict__ gt, const float* g_ssim,
@@ -225,13 +259,17 @@ ssim_fwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2, 
       const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
       const float sg1 = e11 - mu1_sq, sg2 = e22 - mu2_sq, sg12 = e12 - mu12;
       const float A = mu1_sq + mu2_sq + C1, B = sg1 + sg2 + C2, C = 2.f * mu12 + C1, D = 2.f * sg12 + C2;
-      val += (C * D) / (A * B);
+      // two reciprocals instead of seven divisions (A >= C1 > 0; B >= C2 up to rounding of the variances)
+      const float iA = 1.0f / A, iB = 1.0f / B;
+      const float iAB = iA * iB;
+      const float ssim = (C * D) * iAB;
+      val += ssim;
       if (maps) {
         const size_t p = base + (size_t)y * W + x;
-        maps[p] = (mu2 * 2.f * D) / (A * B) - (mu2 * 2.f * C) / (A * B) - (mu1 * 2.f * C * D) / (A * A * B) +
-                  (mu1 * 2.f * C * D) / (A * B * B);
-        maps[map_stride + p] = -(C * D) / (A * B * B);
-        maps[2 * map_stride + p] = (2.f * C) / (A * B);
+        // d ssim / d mu1 (through mu1, mu1^2 and mu1 mu2), d ssim / d E[x^2], d ssim / d E[xy]
+        maps[p] = 2.f * mu2 * (D - C) * iAB - 2.f * mu1 * ssim * (iA - iB);
+        maps[map_stride + p] = -ssim * iB;
+        maps[2 * map_stride + p] = (2.f * C) * iAB;
       }
     }
   }
@@ -470,6 +508,34 @@ int hg_l1_loss(const float* a, const float* b, int64_t n, float* out, float* gra
 }
 int hg_l2_loss(const float* a, const float* b, int64_t n, float* out, float* grad_a, void* ws, void* st) {
   return run_pixel_loss<true>(a, b, n, out, grad_a, ws, (cudaStream_t)st);
+}
+
+int hg_pixel_loss_backward(const float* a, const float* b, int64_t n, int32_t squared, const float* gscale, float* grad_a,
+                           float* grad_b, void* st_) {
+  if (n < 0 || (n > 0 && (!a || !b || (!grad_a && !grad_b)))) {
+    set_error("hg_pixel_loss_backward: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (n == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  const int64_t blocks = (n + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+  if (squared) pixel_loss_bwd_kernel<true><<<grid, 256, 0, st>>>(a, b, n, gscale, grad_a, grad_b);
+  else pixel_loss_bwd_kernel<false><<<grid, 256, 0, st>>>(a, b, n, gscale, grad_a, grad_b);
+  HG_POST_LAUNCH(false, st, "pixel_loss_bwd");
+  return HG_OK;
+}
+
+int hg_freq_total(const float* freq_loss, const float* scale_loss, const float* hf_count, float lambda_freq,
+                  float lambda_scale, float* out3, void* st_) {
+  if (!out3 || (scale_loss && !hf_count)) {
+    set_error("hg_freq_total: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  freq_total_kernel<<<1, 32, 0, st>>>(freq_loss, scale_loss, hf_count, lambda_freq, lambda_scale, out3);
+  HG_POST_LAUNCH(false, st, "freq_total");
+  return HG_OK;
 }
 
 int hg_training_image_grad(const float* color, const float* gt, const float* g_ssim, const float* g_freq, int64_t n,

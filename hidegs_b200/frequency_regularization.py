@@ -117,6 +117,30 @@ class _ScaleReg(torch.autograd.Function):
         return (g * ctx.grad if ctx.needs_input_grad[0] else None), None
 
 
+class _FreqTotal(torch.autograd.Function):
+    """clamp(lambda_freq * freq_loss + lambda_scale * scale_loss * [mask non-empty], 0, 1) — the scalar tail of the
+    reference function (:1636-1660) — and its two partial derivatives in ONE launch (hg_freq_total) instead of ~8
+    scalar torch kernels forward and as many backward.  `freq_loss` / `scale_loss` may be None (term switched off)."""
+
+    @staticmethod
+    def forward(ctx, freq_loss, scale_loss, count, lambda_freq, lambda_scale):
+        ref = freq_loss if freq_loss is not None else scale_loss
+        out = torch.empty(3, dtype=torch.float32, device=ref.device)
+        ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        with torch.cuda.device(ref.device):
+            rc = _L().hg_freq_total(ptr(freq_loss), ptr(scale_loss), ptr(count), float(lambda_freq), float(lambda_scale),
+                                    out.data_ptr(), _stream())
+        _lib.check(rc, "frequency regulariser total")
+        ctx.partials = out
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        p = ctx.partials
+        return (g * p[1] if ctx.needs_input_grad[0] else None, g * p[2] if ctx.needs_input_grad[1] else None,
+                None, None, None)
+
+
 def detect_true_high_frequency_regions(gt_image, high_freq_thresh=0.2):
     """detect_true_high_frequency_regions (:1166-1271): (mask [H,W] float 0/1, count tensor [1])."""
     _check_cuda(gt_image)
@@ -197,19 +221,18 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
     device = rendered_image.device
     r = rendered_image[0] if rendered_image.dim() == 4 else rendered_image
     g = gt_image[0] if gt_image.dim() == 4 else gt_image
-    total = None  # (0 + a + b of the reference, built without the zero tensor and its two extra additions)
     stats = None
     if gt_cache is not None and not gt_cache.matches(g, num_levels, high_freq_thresh):
         raise RuntimeError("gt_cache was built for another image size / level count / threshold")
     mask = count = None
     if gt_cache is not None:
         mask, count = gt_cache.mask, gt_cache.count
+    freq_loss = None
     if lambda_freq > 0:
         if mask is None:  # the mask of this ground truth comes out of the regulariser's own launches
             freq_loss, stats, mask, count = _FreqLoss.apply(r, g.detach(), int(num_levels), None, float(high_freq_thresh))
         else:
             freq_loss, stats = _FreqLoss.apply(r, g.detach(), int(num_levels), gt_cache.state)
-        total = lambda_freq * freq_loss
     elif mask is None:
         mask, count = detect_true_high_frequency_regions(g, high_freq_thresh)
     scale_loss = None
@@ -222,13 +245,12 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
             scaling = None
         if scaling is not None:
             scale_loss = _ScaleReg.apply(scaling, visibility_filter)
-            # the reference applies the term only if the mask is non-empty (:1644); same, without a host sync
-            nonempty = gt_cache.nonempty if gt_cache is not None else (count[0] > 0).float()
-            term = lambda_scale * scale_loss * nonempty
-            total = term if total is None else total + term
-    if total is None:
+    if freq_loss is None and scale_loss is None:
         total = torch.zeros((), dtype=torch.float32, device=device)
-    total = torch.clamp(total, 0, 1.0)
+    else:
+        # 0 + lambda_freq * freq + lambda_scale * scale (the scale term only if the mask is non-empty, :1644), clamped
+        # to [0, 1] (:1660): one launch, no host sync
+        total = _FreqTotal.apply(freq_loss, scale_loss, count, lambda_freq, lambda_scale)
 
     def fill():
         info = {'pyramid_levels': int(num_levels)}

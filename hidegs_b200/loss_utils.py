@@ -33,28 +33,37 @@ def _stream():
 
 
 class _PixelLoss(torch.autograd.Function):
+    """forward: value only (both images read once); backward: one kernel, the upstream scalar read on the device."""
+
     @staticmethod
     def forward(ctx, a, b, l2):
         _check_cuda(a, b)
         if a.shape != b.shape:
             raise RuntimeError("l1/l2 loss: shapes differ %s vs %s" % (tuple(a.shape), tuple(b.shape)))
         a_c, b_c = a.contiguous(), b.contiguous()
-        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         out = torch.empty(1, dtype=torch.float32, device=a.device)
-        grad = torch.empty_like(a_c) if need else None
         with torch.cuda.device(a.device):
             ws = _ws(_L().hg_reduce_workspace_bytes(a_c.numel()), a.device)
             fn = _L().hg_l2_loss if l2 else _L().hg_l1_loss
-            rc = fn(a_c.data_ptr(), b_c.data_ptr(), a_c.numel(), out.data_ptr(), grad.data_ptr() if need else None,
-                    ws.data_ptr(), _stream())
+            rc = fn(a_c.data_ptr(), b_c.data_ptr(), a_c.numel(), out.data_ptr(), None, ws.data_ptr(), _stream())
         _lib.check(rc, "l2_loss" if l2 else "l1_loss")
-        ctx.grad = grad
+        ctx.save_for_backward(a_c, b_c)
+        ctx.l2 = bool(l2)
         return out.reshape(())
 
     @staticmethod
     def backward(ctx, g):
-        ga = g * ctx.grad if ctx.needs_input_grad[0] else None
-        gb = -(g * ctx.grad) if ctx.needs_input_grad[1] else None
+        a, b = ctx.saved_tensors
+        need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_a or need_b):
+            return None, None, None
+        ga = torch.empty_like(a) if need_a else None
+        gb = torch.empty_like(b) if need_b else None
+        gs = g.detach().reshape(1).to(dtype=torch.float32).contiguous()
+        with torch.cuda.device(a.device):
+            rc = _L().hg_pixel_loss_backward(a.data_ptr(), b.data_ptr(), a.numel(), int(ctx.l2), gs.data_ptr(),
+                                             ga.data_ptr() if need_a else None, gb.data_ptr() if need_b else None, _stream())
+        _lib.check(rc, "pixel_loss_backward")
         return ga, gb, None
 
 
@@ -95,7 +104,11 @@ class _SSIM(torch.autograd.Function):
     def backward(ctx, g):
         x, y = ctx.saved_tensors
         B, C, H, W = ctx.dims
-        gs = (g.reshape(1).expand(B) / B if ctx.size_average else g).contiguous().float()
+        if ctx.size_average:  # mean over the batch: every item receives g / B (no kernel for the usual B == 1)
+            gs = g.detach().reshape(1) if B == 1 else (g.detach().reshape(1) / B).expand(B)
+        else:
+            gs = g.detach()
+        gs = gs.contiguous().float()
         g1 = g2 = None
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:

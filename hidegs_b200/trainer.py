@@ -23,7 +23,7 @@ from . import loss_utils as lu
 from ._geometry_lib import lib as _G
 from . import _lib
 from . import parallel
-from .frequency_regularization import (GroundTruthCache, _FreqLoss, _ScaleReg, detect_true_high_frequency_regions,
+from .frequency_regularization import (GroundTruthCache, _FreqLoss, _FreqTotal, _ScaleReg, detect_true_high_frequency_regions,
                                        frequency_regularization_pyramid_scale)
 from .diff_gaussian_rasterization import _RasterizeGaussians
 
@@ -377,30 +377,24 @@ class ViewShardedTrainer:
                     cache = self._gt_cache[id(cam)] = (cam, GroundTruthCache(gt),
                                                        (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2)
             loss = (1.0 - o.lambda_dssim) * l1 + o.lambda_dssim * (1.0 - ss)
-            tF = tSc = None
-            freq_total = None
+            tF = tSc = tT = None
             if freq_on:  # frequency_regularization_pyramid_scale (same arithmetic, same order)
+                freq_loss = scale_loss = None
+                count = cache[1].count if cache is not None else None
                 if o.lambda_freq > 0:
                     tF = T(True, False, False, False, False)
                     if cache is not None:
                         freq_loss, _stats = _FreqLoss.forward(tF, image, gt, 3, cache[1].state)
                     else:  # the high-frequency mask of this ground truth rides the same launches
-                        freq_loss, _stats, _mask, hf_count = _FreqLoss.forward(tF, image, gt, 3, None, 0.2)
-                    freq_total = o.lambda_freq * freq_loss
+                        freq_loss, _stats, _mask, count = _FreqLoss.forward(tF, image, gt, 3, None, 0.2)
                 if o.lambda_scale > 0:
-                    if cache is not None:
-                        nonempty = cache[1].nonempty
-                    elif tF is not None:
-                        nonempty = (hf_count[0] > 0).float()
-                    else:
-                        nonempty = (detect_true_high_frequency_regions(gt)[1][0] > 0).float()
+                    if count is None:
+                        count = detect_true_high_frequency_regions(gt)[1]
                     tSc = T(True, False)
                     scale_loss = _ScaleReg.forward(tSc, scaling, visible)
-                    term = o.lambda_scale * scale_loss * nonempty
-                    freq_total = term if freq_total is None else freq_total + term
-                if freq_total is not None:
-                    gate = ((freq_total >= 0) & (freq_total <= 1.0)).float()  # d clamp(total, 0, 1) / d total
-                    loss = loss + torch.clamp(freq_total, 0, 1.0)
+                if freq_loss is not None or scale_loss is not None:
+                    tT = T(freq_loss is not None, scale_loss is not None, False, False, False)
+                    loss = loss + _FreqTotal.forward(tT, freq_loss, scale_loss, count, o.lambda_freq, o.lambda_scale)
             tN = None
             if o.single_view_weight > 0:
                 image_weight = cache[2] if cache is not None else (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2
@@ -413,7 +407,7 @@ class ViewShardedTrainer:
                 self._one = torch.ones((), dtype=torch.float32, device=dev)
             g_color = lu._SSIM.backward(tS, self._one)[0]
             # d(lambda_freq * clamp gate * freq_loss) / d image: the scalar rides the regulariser's last backward kernel
-            g_freq = _FreqLoss.backward(tF, gate * o.lambda_freq)[0] if tF is not None else None
+            g_freq = _FreqLoss.backward(tF, tT.partials[1])[0] if tF is not None else None
             with torch.cuda.device(dev):
                 rc = lu._L().hg_training_image_grad(
                     color.data_ptr(), gt.data_ptr(), g_color.data_ptr(), g_freq.data_ptr() if g_freq is not None else None,
@@ -428,7 +422,7 @@ class ViewShardedTrainer:
             g_xyz = g_xyz + d_xyz
             g_rot = g_rot + d_rot
             if tSc is not None:
-                g_sc = torch.addcmul(g_sc, tSc.grad, gate * nonempty * o.lambda_scale)
+                g_sc = torch.addcmul(g_sc, tSc.grad, tT.partials[2])
             _ActivateParams.backward(tA, g_xyz, g_sh, g_op, g_sc, g_rot)
         return loss, {"visibility_filter": visible, "radii": radii, "means2D_grad": g_means2D}
 

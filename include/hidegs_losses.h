@@ -39,6 +39,18 @@ HG_API int hg_l1_loss(const float *a, const float *b, int64_t n, float *out, flo
 HG_API int hg_l2_loss(const float *a, const float *b, int64_t n, float *out, float *grad_a,
                       void *workspace, void *stream);
 
+/* Backward of hg_l1_loss (squared = 0) / hg_l2_loss (squared = 1): grad_a = gscale[0] * d loss / d a, grad_b = -grad_a
+ * (either may be NULL); gscale: DEVICE scalar (NULL = 1). */
+HG_API int hg_pixel_loss_backward(const float *a, const float *b, int64_t n, int32_t squared, const float *gscale,
+                                  float *grad_a, float *grad_b, void *stream);
+
+/* Scalar tail of frequency_regularization_pyramid_scale (scripts/frequency_regularization.py:1636-1660) in one launch:
+ *   out3[0] = clamp(lambda_freq * freq_loss[0] + lambda_scale * scale_loss[0] * [hf_count[0] > 0], 0, 1)
+ *   out3[1] = d out3[0] / d freq_loss, out3[2] = d out3[0] / d scale_loss   (zero where the clamp saturates)
+ * freq_loss / scale_loss: device scalars, either may be NULL (term absent); hf_count: pixel count of the mask. */
+HG_API int hg_freq_total(const float *freq_loss, const float *scale_loss, const float *hf_count, float lambda_freq,
+                         float lambda_scale, float *out3, void *stream);
+
 /* Image gradient of the composed training loss in one pass (used by the autograd-free executor of the training step,
  * hidegs_b200/trainer.py; the reference composes the same terms with autograd: (1 - lambda) l1_loss + lambda (1 - ssim)
  * + frequency term, on render().clamp(0, 1) — utils/loss_utils.py:18-64, gaussian_renderer/__init__.py:170):
