@@ -751,7 +751,7 @@ struct RowJob {
 };
 struct RowArgs { int n_jobs; RowJob job[kMaxRowJobs]; };
 
-__global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const __grid_constant__ RowArgs a) {
+__global__ void __launch_bounds__(kFftThreads, 5) fft_rows_jobs_kernel(const __grid_constant__ RowArgs a) {
   extern __shared__ float2 sm[];
   int j = 0;
   for (int k = 1; k < a.n_jobs; ++k)
@@ -761,6 +761,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_jobs_kernel(const __grid
   const int p0 = ((int)blockIdx.x - J.cta_begin) * pairs;
   float2 *bufa = sm, *bufb = sm + pairs * W;
   const float inv_w = 1.0f / (float)W;
+#pragma unroll 4
   for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
     int pr = 0, x = i;
     if (pairs > 1) fast_divmod(i, W, inv_w, pr, x);
@@ -821,32 +822,59 @@ struct FinalizeArgs {
   unsigned* counter;
 };
 
+// Sums of ALL columns of a row-major [rows][NC] matrix of per-CTA partials at once, by the whole CTA (256 threads),
+// in a fixed order: warp g, lane l adds the rows  g * RPW + l / NC + 8 RPW k  of column l % NC (RPW = 32 / NC rows per
+// warp load, eight loads in flight per thread), then the 8 RPW row-slot sums of a column are added in index order.
+// The last-CTA epilogue is a serial tail of the launch: its dependent L2 round trips are what has to be short.
+template <int NC>
+__device__ __forceinline__ void cta_column_sums(const double* __restrict__ p, int rows, double* __restrict__ out,
+                                                double* __restrict__ scratch /* [8 * (32 / NC)][NC] */) {
+  constexpr int RPW = 32 / NC;
+  constexpr int SLOTS = (kFftThreads / 32) * RPW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / NC, col = lane - sub * NC;
+  double acc = 0.0;
+  if (sub < RPW) {
+    double a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] = 0.0;
+    int r = warp * RPW + sub;
+    for (; r + 7 * SLOTS < rows; r += 8 * SLOTS) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += p[(size_t)(r + u * SLOTS) * NC + col];
+    }
+    for (int u = 0; r < rows; r += SLOTS, ++u) a[u & 7] += p[(size_t)r * NC + col];
+    acc = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    scratch[(warp * RPW + sub) * NC + col] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < NC) {
+    double v = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) v += scratch[sl * NC + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
+
 // Scalar epilogue of compute_true_frequency_loss (:1293-1325, :1362-1401) and the coefficients its backward needs.
 // Runs in the last CTA of the column launch; every sum is formed in a fixed order in double.
 __device__ void freq_epilogue(const FinalizeArgs& a, const double* __restrict__ col_partial) {
   __shared__ double sums[kMaxLevels * (3 + kSpecVals) + 8];
-  __shared__ double sm[32];
+  __shared__ double scratch[8 * 32];
+  __shared__ double colv[kColVals], spv[9];
   constexpr int kPer = 3 + kSpecVals;
+  if (a.mode == 1) {
+    cta_column_sums<9>(a.spatial_partial, a.spatial_tiles, spv, scratch);
+    if (threadIdx.x < 9) sums[(threadIdx.x / 3) * kPer + threadIdx.x % 3] = spv[threadIdx.x];
+  }
   for (int l = 0; l < a.levels; ++l) {
-    if (a.mode == 1) {
-      for (int q = 0; q < 3; ++q) {
-        const double v = cta_sum_strided(a.spatial_partial, a.spatial_tiles, 9, 3 * l + q, sm);
-        if (threadIdx.x == 0) sums[l * kPer + q] = v;
-      }
-      for (int q = 0; q < kSpecVals; ++q) {
-        const double v = cta_sum_strided(col_partial + (size_t)a.col_begin[l] * kColVals, a.col_end[l] - a.col_begin[l],
-                                         kColVals, q, sm);
-        if (threadIdx.x == 0) sums[l * kPer + 3 + q] = v;
-      }
-    }
-    if (l == 0)
-      for (int q = 0; q < 8; ++q) {
-        double v;
-        if (a.band0_in) v = a.band0_in[q];
-        else v = cta_sum_strided(col_partial + (size_t)a.col_begin[0] * kColVals, a.col_end[0] - a.col_begin[0], kColVals,
-                                 kSpecVals + q, sm);
-        if (threadIdx.x == 0) sums[kMaxLevels * kPer + q] = v;
-      }
+    if (a.mode != 1 && l > 0) break;
+    cta_column_sums<kColVals>(col_partial + (size_t)a.col_begin[l] * kColVals, a.col_end[l] - a.col_begin[l], colv, scratch);
+    if (a.mode == 1 && threadIdx.x < kSpecVals) sums[l * kPer + 3 + threadIdx.x] = colv[threadIdx.x];
+    if (l == 0 && threadIdx.x < 8)
+      sums[kMaxLevels * kPer + threadIdx.x] = a.band0_in ? a.band0_in[threadIdx.x] : colv[kSpecVals + threadIdx.x];
+    __syncthreads();
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -921,7 +949,7 @@ struct ColArgs {
   FinalizeArgs fin;
 };
 
-__global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const __grid_constant__ ColArgs a) {
+__global__ void __launch_bounds__(kFftThreads, 4) fft_cols_jobs_kernel(const __grid_constant__ ColArgs a) {
   extern __shared__ float2 sm[];
   __shared__ float red[kFftThreads / 32][kColVals];
   __shared__ int s_last;
@@ -936,6 +964,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_cols_jobs_kernel(const __grid
   const int nseq = kind == kColPair ? 2 * tc : tc;
   const int tsh = tc == 4 ? 2 : (tc == 2 ? 1 : 0);  // tc is 1, 2 or 4
   float2 *bufa = sm, *bufb = sm + (size_t)nseq * H;
+#pragma unroll 4
   for (int i = tid; i < H * tc; i += kFftThreads) {
     const int y = i >> tsh, c = i - (y << tsh);
     float2 v = make_float2(0.f, 0.f), w = v;
@@ -1048,7 +1077,7 @@ struct GradJob {
 };
 struct GradArgs { int n_jobs; GradJob job[kMaxLevels]; const LevelCtl* ctl; };
 
-__global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const __grid_constant__ GradArgs a) {
+__global__ void __launch_bounds__(kFftThreads, 4) spectral_grad_cols_kernel(const __grid_constant__ GradArgs a) {
   extern __shared__ float2 sm[];
   const int tid = threadIdx.x;
   int j = 0;
@@ -1062,6 +1091,7 @@ __global__ void __launch_bounds__(kFftThreads) spectral_grad_cols_kernel(const _
   const float c_mag = ctl->c_mag, c_phase = ctl->c_phase;
   const int tsh = tc == 4 ? 2 : (tc == 2 ? 1 : 0);  // tc is 1, 2 or 4
   float2 *bufa = sm, *bufb = sm + (size_t)tc * H;
+#pragma unroll 2
   for (int i = tid; i < H * tc; i += kFftThreads) {
     const int ky = i >> tsh, c = i - (ky << tsh);
     float gre = 0.f, gim = 0.f;
@@ -1117,7 +1147,7 @@ struct InvArgs {
   unsigned* counter;
 };
 
-__global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const __grid_constant__ InvArgs a) {
+__global__ void __launch_bounds__(kFftThreads, 5) fft_rows_c2r_jobs_kernel(const __grid_constant__ InvArgs a) {
   extern __shared__ float2 sm[];
   __shared__ float smax[kFftThreads / 32];
   __shared__ int s_last;
@@ -1129,6 +1159,7 @@ __global__ void __launch_bounds__(kFftThreads) fft_rows_c2r_jobs_kernel(const __
   const int p0 = ((int)blockIdx.x - J.cta_begin) * pairs;
   float2 *bufa = sm, *bufb = sm + pairs * W;
   const float inv_w = 1.0f / (float)W;
+#pragma unroll 4
   for (int i = threadIdx.x; i < pairs * W; i += blockDim.x) {
     int pr = 0, x = i;
     if (pairs > 1) fast_divmod(i, W, inv_w, pr, x);
@@ -1296,7 +1327,7 @@ __global__ void __launch_bounds__(kImgThreads) spatial_grad_rgb_kernel(const __g
 }
 
 // ---------------------------------------------------------------- high-frequency mask tail
-constexpr int kSumBlocks = 148 * 2;
+constexpr int kSumBlocks = 148 * 8;
 
 // score = clamp(0.7 spatial + 0.3 hs / max(hs), 0, 5) in place over hs; min / max of it -> mm2[0..1] (last CTA)
 __global__ void __launch_bounds__(256)
@@ -1306,6 +1337,7 @@ hf_combine_kernel(float* __restrict__ hs, const float* __restrict__ spatial, con
   __shared__ int s_last;
   float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
   const float mx = mm[1];
+#pragma unroll 4
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float h = hs[i];
     if (mx > 1e-8f) h = h / mx;
@@ -1359,6 +1391,7 @@ hf_threshold_kernel(const float* __restrict__ score, const float* __restrict__ m
   __shared__ int s_last;
   float cnt = 0.f;
   const float lo = mm[0], range = mm[1] - mm[0];
+#pragma unroll 4
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float s = range > 1e-6f ? (score[i] - lo) / range : 0.f;
     const float m = s > thresh ? 1.f : 0.f;
@@ -1514,8 +1547,8 @@ static void carve_work(void* ws, const Dims& d, bool with_gt, bool with_hf, Work
     w->hf_score = cv.take<float>(hw);
     w->hf_hs = cv.take<float>(hw);
     w->hf_spec = cv.take<float2>((size_t)d.H[0] * (d.W[0] / 2 + 1));
-    w->hf_pmin = cv.take<float>(2048);
-    w->hf_pmax = cv.take<float>(2048);
+    w->hf_pmin = cv.take<float>(2048 > kSumBlocks ? 2048 : kSumBlocks);
+    w->hf_pmax = cv.take<float>(2048 > kSumBlocks ? 2048 : kSumBlocks);
     w->hf_part = cv.take<double>(kSumBlocks);
   }
   if (with_gt) {
@@ -1612,10 +1645,20 @@ static int freq_forward(const float* rendered, const float* gt, void* gt_state, 
   if (hf) ra.job[ra.n_jobs++] = row_job(G.gg[0], w.hf_spec, d, 0, 0, &cta);  // unclamped here (:1221)
   rc = launch_rows(ra, cta, smem, st);
   if (rc) return rc;
-  // ---- columns + sums + epilogue
+  // ---- columns + sums + epilogue (heaviest CTAs first: the hf job runs two transforms per column group; the
+  // scheduler hands out CTAs in index order, so the light level-2 CTAs fill the tail of the launch)
   ColArgs ca{};
   cta = 0;
   smem = 0;
+  if (hf) {
+    ColJob& j = ca.job[ca.n_jobs++];
+    j.A = w.hf_spec; j.B = nullptr; j.H = d.H[0]; j.W = d.W[0]; j.kind = kColHighpassInverse;
+    j.tc = 2 * cols_per_cta(d.H[0]) > 4 ? 4 : 2 * cols_per_cta(d.H[0]);
+    j.cta_begin = cta; j.level = -1; j.plan = d.col[0];
+    cta += (d.W[0] / 2 + 1 + j.tc - 1) / j.tc;
+    const size_t b = 2 * (size_t)j.tc * d.H[0] * sizeof(float2);
+    if (b > smem) smem = b;
+  }
   for (int l = 0; l < d.levels; ++l) {
     ColJob& j = ca.job[ca.n_jobs++];
     j.A = w.fr[l]; j.B = G.fg[l]; j.H = d.H[l]; j.W = d.W[l];
@@ -1625,15 +1668,6 @@ static int freq_forward(const float* rendered, const float* gt, void* gt_state, 
     cta += col_ctas(d, l);
     ca.fin.col_end[l] = cta;
     const size_t b = 2 * (size_t)(cached ? 1 : 2) * j.tc * d.H[l] * sizeof(float2);
-    if (b > smem) smem = b;
-  }
-  if (hf) {
-    ColJob& j = ca.job[ca.n_jobs++];
-    j.A = w.hf_spec; j.B = nullptr; j.H = d.H[0]; j.W = d.W[0]; j.kind = kColHighpassInverse;
-    j.tc = 2 * cols_per_cta(d.H[0]) > 4 ? 4 : 2 * cols_per_cta(d.H[0]);
-    j.cta_begin = cta; j.level = -1; j.plan = d.col[0];
-    cta += (d.W[0] / 2 + 1 + j.tc - 1) / j.tc;
-    const size_t b = 2 * (size_t)j.tc * d.H[0] * sizeof(float2);
     if (b > smem) smem = b;
   }
   ca.partial = w.col_partial;
