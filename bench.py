@@ -191,7 +191,6 @@ def run_gpu_arm(args, impl):
     exchange = None
     if ddp and parallel.prefer_nvls(dev):
         exchange = parallel.SymmetricArena(N_GAUSS * 80, dev)   # 80 floats / Gaussian: the whole backward arena
-        C.set_gradient_arena_provider(lambda n, d: exchange.tensor if n <= exchange.numel else None)
 
     # Opt-in (HG_EXCHANGE_OVERLAP=1): overlapped with the per-Gaussian backward — preprocess_bwd is issued in 2 slot
     # ranges and the first range's five parameter blocks travel (one in-fabric kernel on a side stream) while the second
@@ -249,11 +248,11 @@ def run_gpu_arm(args, impl):
         fa = op_tuple(C, scene, cam, all_maps[0], dev, bg)
         fwd = C.rasterize_gaussians(*fa)
         if overlap is not None:
-            with overlap:
-                grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
+            grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g), **overlap.backward_kwargs())
             overlap.finish()
         else:
-            grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
+            kw = dict(grad_arena=exchange.tensor) if exchange is not None else {}
+            grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g), **kw)
             if ddp:
                 pack_and_allreduce(grads)
         return fwd
@@ -299,6 +298,8 @@ def run_gpu_arm(args, impl):
     if impl == "ours":
         from hidegs_b200.diff_gaussian_rasterization import GaussianRasterizer
     params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacity", "scales", "rotations")}
+    if exchange is not None:  # the autograd backward of every e2e step writes its gradients into the symmetric arena
+        params["means3D"]._hg_grad_arena = exchange.tensor
     gen = torch.Generator().manual_seed(7)
     gt_host = torch.rand(3, HEIGHT, WIDTH, generator=gen).pin_memory()
     cam_host = [torch.cat([c.world_view_transform.flatten().cpu(), c.full_proj_transform.flatten().cpu(),

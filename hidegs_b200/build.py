@@ -52,6 +52,48 @@ def _compile(src, verbose):
     return obj, res.stderr if verbose else ""
 
 
+EXT_SRC = os.path.join(HERE, "csrc_ext", "raster_ext.cpp")
+EXT_NAME = "_hgC"
+
+
+def ext_path():
+    import sysconfig
+    return os.path.join(HERE, "diff_gaussian_rasterization", EXT_NAME + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_extension(verbose=False, force=False):
+    """The thin torch C++ extension of the rasterizer operators (csrc_ext/raster_ext.cpp -> diff_gaussian_rasterization/
+    _hgC*.so): host code only (g++), linked against libhidegs_b200.so next to it (rpath $ORIGIN/..) and torch's libraries
+    (already loaded when the module is imported)."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    out = ext_path()
+    inc = os.path.join(HERE, "..", "include")
+    deps = [EXT_SRC, LIB] + [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
+    stamp = out + ".sha"
+    dig = _digest(deps[:1] + deps[2:]) + torch.__version__
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return out
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-DTORCH_EXTENSION_NAME=" + EXT_NAME, "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    cmd += ["-I" + p for p in ce.include_paths()] + ["-I" + sysconfig.get_paths()["include"], "-I" + cuda_home + "/include"]
+    cmd += [EXT_SRC, "-o", out]
+    cmd += ["-L" + p for p in ce.library_paths()] + ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+                                                     "-ltorch_python"]
+    cmd += ["-L" + HERE, "-l:libhidegs_b200.so", "-Wl,-rpath,$ORIGIN/.."]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building the torch extension failed:\n%s\n%s" % (res.stdout, res.stderr))
+    with open(stamp, "w") as f:
+        f.write(dig)
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return out
+
+
 def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     if force:
@@ -70,6 +112,7 @@ def build(verbose=False, force=False):
             raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
     if verbose and log:
         sys.stderr.write(log)
+    build_extension(verbose=verbose, force=force)
     return LIB
 
 

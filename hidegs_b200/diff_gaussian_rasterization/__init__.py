@@ -39,6 +39,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         # AccumulateGrad pass over the largest parameter block)
         sink = getattr(sh, "_hg_grad_sink", None)
         ctx.sh_sink = sink if sink is not None and _C.sh_sink_supported(sh, rs.render_indices, rs.parent_indices) else None
+        # extension: `means3D._hg_grad_arena = flat fp32 tensor` makes the backward of THIS call write its gradients
+        # into that caller-owned arena (e.g. multicast symmetric memory of the data-parallel exchange)
+        ctx.grad_arena = getattr(means3D, "_hg_grad_arena", None)
         ctx.save_for_backward(out_all_map, colors_precomp, all_maps, means3D, scales, rotations, cov3Ds_precomp,
                               radii, sh, opacities, geomBuffer, binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii, out_observe)
@@ -69,7 +72,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.render_geo, rs.debug)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations, grad_all_map) = _C.rasterize_gaussians_backward(
-            *args, sh_sink=ctx.sh_sink() if ctx.sh_sink is not None else None)
+            *args, sh_sink=ctx.sh_sink() if ctx.sh_sink is not None else None, grad_arena=ctx.grad_arena)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
                 grad_rotations, grad_cov3Ds_precomp, grad_all_map, None)
 

@@ -168,7 +168,7 @@ class OverlappedBackwardExchange:
     SymmetricArena (gradient arena provider) and issues its last kernel in `n_chunks` slot ranges; as soon as a range is
     queued, its five parameter blocks (xyz 3 | sh 3M | opacity 1 | scale 3 | rotation 4 floats per Gaussian, SoA) are
     summed over the ranks by ONE in-fabric kernel on a side stream while the next range is computed.
-    `finish()` makes the current stream wait for the last range.  Use as a context around the backward calls."""
+    `finish()` makes the current stream wait for the last range.  Pass `backward_kwargs()` to the backward call."""
 
     def __init__(self, arena, n_gaussians, sh_coeffs=16, n_chunks=4):
         self.arena, self.N, self.n_chunks = arena, int(n_gaussians), int(n_chunks)
@@ -195,18 +195,10 @@ class OverlappedBackwardExchange:
         with torch.cuda.stream(self.stream):
             self.bytes += self.arena.all_reduce_ranges_(offs, cnts)
 
-    def __enter__(self):
-        from .diff_gaussian_rasterization import _C
-        arena = self.arena
-        self._saved = (_C._gradient_arena_provider, _C._backward_chunk_hook)
-        _C.set_gradient_arena_provider(lambda n, d: arena.tensor if n <= arena.numel else None)
-        _C.set_backward_chunk_hook(self.n_chunks, self._on_chunk)
-        return self
-
-    def __exit__(self, *exc):
-        from .diff_gaussian_rasterization import _C
-        _C._gradient_arena_provider, _C._backward_chunk_hook = self._saved
-        return False
+    def backward_kwargs(self):
+        """Keyword arguments for `_C.rasterize_gaussians_backward` (per call, nothing global): the gradients are born in
+        the symmetric arena and every queued slot range starts its exchange."""
+        return dict(grad_arena=self.arena.tensor, chunk_hook=(self.n_chunks, self._on_chunk))
 
     def finish(self):
         """The current stream waits until every range of the last backward has been exchanged."""

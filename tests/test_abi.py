@@ -164,3 +164,28 @@ def test_drop_in_signatures_match_reference():
     assert list(inspect.signature(lu.ssim).parameters) == ["img1", "img2", "window_size", "size_average"]
     assert list(inspect.signature(lu.get_img_grad_weight).parameters) == ["img", "beta"]
     assert list(inspect.signature(lu.lncc).parameters) == ["ref", "nea"]
+
+
+def test_torch_extension_surface_and_no_cpu_path():
+    """The rasterizer's `_C` is the thin torch C++ extension (csrc_ext/raster_ext.cpp) over the C-ABI: same operator
+    names as the reference's pybind module (ext.cpp:15-18) + mark_visible, no module-level mutable state in the Python
+    shim, CPU tensors rejected (no fallback)."""
+    import inspect
+    import pytest
+    import torch
+    from hidegs_b200.diff_gaussian_rasterization import _C
+    for name in ("rasterize_gaussians", "rasterize_gaussians_backward", "mark_visible", "sh_sink_supported"):
+        assert callable(getattr(_C, name)), name
+    assert type(_C.rasterize_gaussians).__name__ == "builtin_function_or_method"  # bound straight from the extension
+    assert _C._hgC.__file__.endswith(".so") and "hidegs_b200" in _C._hgC.__file__
+    src = inspect.getsource(_C)
+    assert "global " not in src and "ctypes" not in src
+    e_i, e_f = torch.empty(0, dtype=torch.int32), torch.empty(0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        _C.rasterize_gaussians(torch.zeros(3), e_i, e_i, e_f, e_i, torch.zeros(4, 3), e_f, e_f, torch.zeros(4, 1),
+                               torch.ones(4, 3), torch.ones(4, 4), 1.0, e_f, torch.eye(4), torch.eye(4), 1.0, 1.0, 16, 16,
+                               torch.zeros(4, 16, 3), 3, torch.zeros(3), False, True, False, True)
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        _C.rasterize_gaussians(torch.zeros(3), e_i, e_i, e_f, e_i, torch.zeros(4, 2), e_f, e_f, torch.zeros(4, 1),
+                               torch.ones(4, 3), torch.ones(4, 4), 1.0, e_f, torch.eye(4), torch.eye(4), 1.0, 1.0, 16, 16,
+                               torch.zeros(4, 16, 3), 3, torch.zeros(3), False, True, False, True)

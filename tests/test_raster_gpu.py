@@ -439,11 +439,9 @@ def test_sh_gradient_sink_and_chunked_backward(cuda_device):
     ru.assert_grads_close([sink - base], [plain[5]], names=("dL_dsh",), what="sink beta=1", l2_tol=1e-3, rtol=5e-3)
     # chunked: ranges are multiples of 128 slots, cover every slot once, and the gradients are the same
     seen = []
-    ru.OUR_C.set_backward_chunk_hook(4, lambda c, p0, p1: seen.append((c, p0, p1)))
-    try:
-        chunked = ru.OUR_C.rasterize_gaussians_backward(*ba)
-    finally:
-        ru.OUR_C.set_backward_chunk_hook()
+    chunked = ru.OUR_C.rasterize_gaussians_backward(*ba, chunk_hook=(4, lambda c, p0, p1: seen.append((c, p0, p1))))
+    with pytest.raises(ZeroDivisionError):  # an exception raised inside the hook surfaces after the C frame returns
+        ru.OUR_C.rasterize_gaussians_backward(*ba, chunk_hook=(2, lambda c, p0, p1: 1 // 0))
     assert [c for c, _, _ in seen] == list(range(len(seen))) and 2 <= len(seen) <= 4
     assert seen[0][1] == 0 and seen[-1][2] == 9000 and all(a[2] == b[1] for a, b in zip(seen, seen[1:]))
     assert all(p0 % 128 == 0 for _, p0, _ in seen)
@@ -469,11 +467,9 @@ def test_sparse_view_zero_rows(cuda_device, degree):
     fwd = ru.OUR_C.rasterize_gaussians(*fa)
     assert 0 < fwd[0] < 2 * 8000 and int((fwd[2] > 0).sum()) < 4000
     grads = syn.upstream_grads(96, 64)
-    ru.OUR_C.set_gradient_arena_provider(lambda n, d: torch.full((n,), float("nan"), device=d))
-    try:
-        ours_b = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fa, fwd, grads, dev))
-    finally:
-        ru.OUR_C.set_gradient_arena_provider(None)
+    poisoned = torch.full((8000 * 84,), float("nan"), device=dev)  # caller-owned arena (>= 80 floats per Gaussian)
+    ours_b = ru.OUR_C.rasterize_gaussians_backward(*ru.bwd_args(fa, fwd, grads, dev), grad_arena=poisoned)
+    assert ours_b[3].data_ptr() == poisoned.data_ptr()  # the gradients are views of the arena
     assert all(bool(torch.isfinite(g).all()) for g in ours_b)
     o = ru.oracle_for_case(case)
     o.forward()

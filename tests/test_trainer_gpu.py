@@ -407,5 +407,6 @@ def test_gaussian_count_not_multiple_of_four(cuda_device):
         trainer.step(list(zip(cams, gts)))
         arenas[direct] = (params.grad_arena.clone(), params.param_arena.clone())
     err = (arenas[True][0] - arenas[False][0]).abs().max().item()
-    assert err <= 1e-5 * arenas[False][0].abs().max().item() + 1e-12, err
+    # (two evaluations of the SAME path differ by ~1.6e-5 of the largest entry here: float-atomic order of the blend)
+    assert err <= 1e-4 * arenas[False][0].abs().max().item() + 1e-12, err
     assert torch.isfinite(arenas[True][1]).all()

@@ -33,11 +33,10 @@ def main():
     out = {"world": world, "N": N}
 
     arena = parallel.SymmetricArena(N * 80, dev)
-    C.set_gradient_arena_provider(lambda n, d: arena.tensor if n <= arena.numel else None)
 
     def plain():
         fwd = C.rasterize_gaussians(*fa)
-        C.rasterize_gaussians_backward(*bench.bwd_tuple(fa, fwd, g))
+        C.rasterize_gaussians_backward(*bench.bwd_tuple(fa, fwd, g), grad_arena=arena.tensor)
         arena.all_reduce_(59 * N)
 
     results = {}
@@ -49,8 +48,7 @@ def main():
                 plain()
             else:
                 fwd = C.rasterize_gaussians(*fa)
-                with ov:
-                    C.rasterize_gaussians_backward(*bench.bwd_tuple(fa, fwd, g))
+                C.rasterize_gaussians_backward(*bench.bwd_tuple(fa, fwd, g), **ov.backward_kwargs())
                 ov.finish()
         for _ in range(4):
             step()
