@@ -36,10 +36,9 @@ class RasterLayout(ctypes.Structure):
     """struct hg_raster_layout (include/hidegs_raster.h)."""
     _fields_ = [(n, ctypes.c_size_t) for n in (
         "geom_bytes", "depths", "tiles_touched", "point_offsets", "rects", "cov3D", "clamped", "records",
-        "scan_temp", "scan_temp_bytes", "slot_ids", "depth_sorted", "depth_order", "offsets_sorted", "depth_sort_temp",
-        "depth_sort_temp_bytes",
+        "tiles", "ctr_stride", "tile_ctr", "tile_lists", "bin_header",
         "image_bytes", "final_T", "n_contrib", "ranges",
-        "binning_bytes", "keys_unsorted", "keys", "vals_unsorted", "vals", "sort_temp", "sort_temp_bytes")]
+        "binning_bytes", "vals", "pairs")]
 
 
 # Every symbol include/hidegs_raster.h declares (checked by the CPU test-suite).

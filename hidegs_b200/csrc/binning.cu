@@ -1,44 +1,500 @@
-// binning.cu — tile-instance generation, sort and per-tile ranges.
+// binning.cu — tile-instance generation, per-tile depth sort and tile ranges.  All kernels here are hand-written for
+// sm_100a; no library sort or scan runs on the forward path.
 //
 // Replaces, in order, cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:321), duplicateWithKeys (:70-115),
 // cub::DeviceRadixSort::SortPairs on the 64-bit tile|depth key (:357-362, bits [0, 32+getHigherMsb(tiles))) and
 // identifyTileRanges (:120-142) with its memset (:364).
 //
-// The reference sorts R tile instances (R ~ 5.4 M at config 2) on 45..47-bit keys: six 8-bit radix passes over
-// 12-byte pairs.  The same order is produced here with far less traffic by sorting in two stages:
-//   1. the P slots are sorted ONCE by depth (32-bit keys, stable; culled slots carry 0xFFFFFFFF and end up last);
-//      this runs while the host waits for num_rendered;
-//   2. tile instances are emitted in that depth order (y-major / x-minor inside a splat, as duplicateWithKeys does)
-//      with the tile id as their only key and sorted STABLY on getHigherMsb(tiles) bits (13 at 1080p: two passes
-//      over 8-byte pairs).
-// A stable LSD radix sort orders by (tile, depth, emission order); emission order among equal (tile, depth) is the
-// ascending slot index in both schemes (stage 1 is stable over the slot index; a splat appears at most once per
-// tile), so point_list and the tile ranges are bit-identical to the reference's, ties included.  The 64-bit keys
-// themselves are only reconstructed on request (hg_raster_debug_keys) for the parity tests.
+// The reference sorts R tile instances (R ~ 5.4 M at config 2) GLOBALLY on 45..47-bit keys: six 8-bit radix passes
+// over 12-byte pairs in HBM.  The sorted order it produces is "by tile, then by depth, ties by ascending slot" — and
+// the tile part of that key is known before anything is sorted.  So the instances are BUCKETED by tile first and
+// each tile's list is sorted on chip:
+//   1. preprocess_fwd counts the instances of every tile while it computes the rectangles (one RED per instance);
+//   2. tile_scan_kernel (ONE CTA) turns the counts into list offsets = the tile ranges, the total R, and four work
+//      lists by list length; R and the list lengths travel to the host in one 32-byte copy (R is part of the API);
+//   3. scatter_instances_kernel appends (depth bits, slot) to its tile's list through a per-tile cursor
+//      (arrival order is arbitrary: 32 atomics in flight per warp, the instances of a warp's 32 splats are spread
+//      evenly over its lanes whatever the splat sizes);
+//   4. tile_sort kernels sort every list in SHARED MEMORY with a stable LSD radix sort over only the depth bits in
+//      which the list's keys differ (min/max first; typically 3-4 eight-bit passes), ranks by warp match instead of
+//      atomics, a warp per short list (<= 512), a CTA per medium list, a 512-thread CTA with 214 KB of shared memory
+//      per long list, a global-memory version of the same routine for lists beyond that.  Ties in depth are put in
+//      ascending slot order afterwards (short runs in place; a list with a long run is re-sorted slot-first, which
+//      the stable depth passes then preserve), so point_list is bit-identical to the reference's, ties included.
+// HBM traffic: 8 R written + 8 R read + 4 R written (the reference: 12 R written, then 6 x 24 R through the sort).
+// The 64-bit keys themselves are only reconstructed on request (hg_raster_debug_keys) for the parity tests.
 #include "common.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include "tile_instances.cuh"
+
+#include <cstdlib>
 
 namespace hg {
 
 namespace {
 
-// getHigherMsb (rasterizer_impl.cu:35-50): note getHigherMsb(16) == 5.
-inline uint32_t higher_msb(uint32_t n) {
-  uint32_t msb = sizeof(n) * 4;
-  uint32_t step = msb;
-  while (step > 1) {
-    step /= 2;
-    if (n >> msb) msb += step;
-    else msb -= step;
-  }
-  if (n >> msb) msb++;
-  return msb;
+constexpr uint32_t kFull = 0xffffffffu;
+
+// ---- list-length classes ------------------------------------------------------------------------------------------
+constexpr int kSortWarpsA = 4;                      // tile_sort_kernel A: CTA of 4 warps
+constexpr int kCapS = 1024;                         // short list: one warp
+constexpr int kCapM = kCapS * kSortWarpsA;          // medium list: the CTA
+constexpr int kSortWarpsB = 16;                     // kernel B: 512 threads, one CTA per SM
+constexpr int kCapL = 12288;                        // 12288 * 16 B + 32 KB of counters = 224 KB
+constexpr int kSortWarpsC = 32;                     // kernel C: lists beyond shared memory, sorted in HBM scratch
+
+// keys + slots, twice (ping-pong), and 32 digits x threads 16-bit counters
+__host__ __device__ constexpr size_t sort_smem_bytes(int warps, int cap) {
+  return (size_t)cap * 16 + (size_t)warps * 32 * 32 * 2;
 }
 
-// Reference emission (duplicateWithKeys, rasterizer_impl.cu:70-115): 64-bit keys in ascending slot order.  Used
-// only by hg_raster_debug_keys.
+// ---- 2. counts -> offsets, ranges, work lists ------------------------------------------------------------------------
+// header: [0] R  [1] #short  [2] #medium  [3] #long  [4] #beyond  [5] pairs in "beyond" lists  [6] longest list  [7] -
+//         [8..11] work counters of the sort kernels (zeroed here)
+// One CTA; rounds of 4096 tiles, four consecutive tiles per thread.  `host_header` is mapped pinned host memory: the
+// kernel stores the eight header words straight into it (no separate copy operation behind the kernel).
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32_t* __restrict__ ctr,
+                 uint2* __restrict__ ranges, uint32_t* __restrict__ list_a, uint32_t* __restrict__ list_b,
+                 uint32_t* __restrict__ xl_off, uint32_t* __restrict__ header, volatile uint32_t* host_header) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_cnt[8];
+  __shared__ uint32_t s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  if (tid < 8) s_cnt[tid] = 0;
+  // total first (ranges of a view with a single instance stay (0, 0), see below)
+  uint32_t part = 0;
+  for (int t = tid; t < T; t += 1024) part += ctr[(size_t)t * stride];
+  part = __reduce_add_sync(kFull, part);
+  if (lane == 0) s_warp[warp] = part;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = __reduce_add_sync(kFull, s_warp[lane]);
+    if (lane == 0) s_total = v;
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  uint32_t carry = 0, longest = 0;
+  for (int base = 0; base < T; base += 4096) {
+    const int t0 = base + tid * 4;
+    uint32_t n[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) n[k] = t0 + k < T ? ctr[(size_t)(t0 + k) * stride] : 0u;
+    const uint32_t sum = n[0] + n[1] + n[2] + n[3];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    __syncthreads();  // s_warp of the previous round has been read
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t wsum = s_warp[lane];
+    uint32_t wincl = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, wincl, o);
+      if (lane >= o) wincl += v;
+    }
+    const uint32_t before = __shfl_sync(kFull, wincl - wsum, warp);
+    const uint32_t round_total = __shfl_sync(kFull, wincl, 31);
+    uint32_t run = carry + before + incl - sum;
+    carry += round_total;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = t0 + k;
+      const uint32_t nk = n[k];
+      if (t < T) {
+        ctr[(size_t)t * stride + 1] = run;
+        // identifyTileRanges: empty tiles keep the memset's (0, 0); with a single instance in the whole view the end
+        // marker is never written (rasterizer_impl.cu:133-141), so that tile reads (0, 0) as well.
+        ranges[t] = (nk && total != 1u) ? make_uint2(run, run + nk) : make_uint2(0u, 0u);
+      }
+      longest = max(longest, nk);
+      const int cls = nk == 0 ? 0 : nk <= cap_short ? 1 : nk <= (uint32_t)kCapM ? 2 : nk <= (uint32_t)kCapL ? 3 : 4;
+#pragma unroll
+      for (int c = 1; c <= 4; ++c) {  // warp-aggregated appends
+        const uint32_t m = __ballot_sync(kFull, cls == c);
+        if (m) {
+          uint32_t at = 0;
+          if (lane == __ffs(m) - 1) at = atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
+          at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & lt);
+          if (cls == c) {
+            if (c == 1) list_a[at] = (uint32_t)t;
+            else if (c == 2) list_a[T - 1 - at] = (uint32_t)t;
+            else if (c == 3) list_b[at] = (uint32_t)t;
+            else {
+              list_b[T - 1 - at] = (uint32_t)t;
+              xl_off[at] = atomicAdd(&s_cnt[5], nk);
+            }
+          }
+        }
+      }
+      run += nk;
+    }
+  }
+  longest = __reduce_max_sync(kFull, longest);
+  if (lane == 0) atomicMax(&s_cnt[6], longest);
+  __syncthreads();
+  if (tid < 8) {
+    const uint32_t v = tid == 0 ? total : s_cnt[tid];
+    header[tid] = v;
+    host_header[tid] = v;
+  } else if (tid < 12) {
+    header[tid] = 0;
+  }
+}
+
+// ---- 3. scatter ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scatter_instances_kernel(const int P, const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
+                         const float* __restrict__ depths, const uint32_t grid_x, const int stride,
+                         uint32_t* __restrict__ ctr, uint2* __restrict__ pairs) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cnt = idx < P ? tiles_touched[idx] : 0u;
+  if (__ballot_sync(kFull, cnt != 0) == 0) return;
+  uint2 r = make_uint2(0u, 0u);
+  uint32_t dbits = 0;
+  if (cnt) {
+    r = rects[idx];
+    dbits = __float_as_uint(depths[idx]);
+  }
+  const uint32_t first = (uint32_t)(idx - lane);
+  WarpInstances wi(cnt, r.x, (r.y & 0xffffu) - (r.x & 0xffffu), lane);
+  for (uint32_t j0 = 0; j0 < wi.total; j0 += 64) {  // two instances per lane: two atomics in flight
+    int owner0, owner1;
+    uint32_t tile0, tile1;
+    const bool on0 = wi.at(j0, grid_x, owner0, tile0);
+    const bool on1 = wi.at(j0 + 32, grid_x, owner1, tile1);
+    const uint32_t d0 = __shfl_sync(kFull, dbits, owner0);
+    const uint32_t d1 = __shfl_sync(kFull, dbits, owner1);
+    uint32_t pos0 = 0, pos1 = 0;
+    if (on0) pos0 = atomicAdd(ctr + (size_t)tile0 * stride + 1, 1u);
+    if (on1) pos1 = atomicAdd(ctr + (size_t)tile1 * stride + 1, 1u);
+    if (on0) pairs[pos0] = make_uint2(d0, first + owner0);
+    if (on1) pairs[pos1] = make_uint2(d1, first + owner1);
+  }
+}
+
+// ---- 4. per-list stable LSD radix sort ------------------------------------------------------------------------------
+// NW warps cooperate on one list held in K0/V0 (keys / slots); K1/V1 is the other half of the ping-pong.  A pass
+// ranks 5-bit digits WITHOUT warp collectives or atomics: thread t owns the m consecutive elements [t m, (t+1) m)
+// (m odd: the strided shared-memory reads are conflict-free) and a private counter per digit, cnt[digit][t]; the
+// flat array cnt[32][NT] read front to back IS the stable order (digit, owner thread, position), so one exclusive scan
+// of it — 32 counters per thread, serial, then one warp scan of the per-thread totals — turns counts into
+// destinations, which the owner hands out in a second walk over its elements.  (The warp-match ranking of 8-bit
+// digits this replaced spent 3x the instructions: MATCH / eight ballots per 32 elements and a dependent
+// shared-memory update chain.)
+template <int NW>
+__device__ __forceinline__ void group_sync() {
+  if (NW == 1) __syncwarp();
+  else __syncthreads();
+}
+
+constexpr int kDigitBits = 5;
+constexpr uint32_t kDigits = 1u << kDigitBits;
+
+template <typename CntT> struct CntPack;
+template <> struct CntPack<uint16_t> { static constexpr int kWords = 16; };  // 32 counters in 16 words
+template <> struct CntPack<uint32_t> { static constexpr int kWords = 32; };
+
+template <int NW, bool BY_SLOT, typename CntT>
+__device__ __forceinline__ void radix_pass(const uint32_t* __restrict__ K0, const uint32_t* __restrict__ V0,
+                                           uint32_t* __restrict__ K1, uint32_t* __restrict__ V1,
+                                           CntT* __restrict__ cnt, uint32_t* __restrict__ red, const int n,
+                                           const int m, const uint32_t kmin, const int shift, const int w,
+                                           const int lane) {
+  constexpr int NT = NW * 32;
+  constexpr int kWords = CntPack<CntT>::kWords;
+  const int tid = w * 32 + lane;
+  const int b = min(n, tid * m), e = min(n, b + m);
+  {
+    uint4* z = reinterpret_cast<uint4*>(cnt);
+#pragma unroll
+    for (int i = 0; i < kWords / 4; ++i) z[i * NT + tid] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  group_sync<NW>();
+  CntT* mine = cnt + tid;
+#pragma unroll 4
+  for (int i = b; i < e; ++i) {
+    const uint32_t key = BY_SLOT ? V0[i] : K0[i] - kmin;
+    const uint32_t d = (key >> shift) & (kDigits - 1u);
+    mine[d * NT] += 1;
+  }
+  group_sync<NW>();
+  // exclusive scan of the flat counter array: this thread's 32 consecutive counters, then across threads
+  {
+    uint4* row = reinterpret_cast<uint4*>(cnt) + tid * (kWords / 4);
+    uint32_t c[kWords];
+#pragma unroll
+    for (int i = 0; i < kWords / 4; ++i) {
+      const uint4 q = row[i];
+      c[4 * i] = q.x; c[4 * i + 1] = q.y; c[4 * i + 2] = q.z; c[4 * i + 3] = q.w;
+    }
+    uint32_t total = 0;
+    if (sizeof(CntT) == 2) {
+      uint32_t acc = 0;  // two 16-bit lanes; neither overflows (n < 65536 in this variant)
+#pragma unroll
+      for (int i = 0; i < kWords; ++i) acc += c[i];
+      total = (acc & 0xffffu) + (acc >> 16);
+    } else {
+#pragma unroll
+      for (int i = 0; i < kWords; ++i) total += c[i];
+    }
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t run = incl - total;
+    if (NW > 1) {
+      if (lane == 31) red[w] = incl;
+      __syncthreads();
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) run += ww < w ? red[ww] : 0u;
+    }
+    if (sizeof(CntT) == 2) {
+#pragma unroll
+      for (int i = 0; i < kWords; ++i) {
+        const uint32_t lo = c[i] & 0xffffu, hi = c[i] >> 16;
+        c[i] = run | ((run + lo) << 16);
+        run += lo + hi;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kWords; ++i) {
+        const uint32_t v = c[i];
+        c[i] = run;
+        run += v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kWords / 4; ++i) row[i] = make_uint4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
+  }
+  group_sync<NW>();
+#pragma unroll 4
+  for (int i = b; i < e; ++i) {
+    const uint32_t k = K0[i], v = V0[i];
+    const uint32_t key = BY_SLOT ? v : k - kmin;
+    const uint32_t d = (key >> shift) & (kDigits - 1u);
+    const uint32_t pos = mine[d * NT];
+    mine[d * NT] = (CntT)(pos + 1u);
+    K1[pos] = k;
+    V1[pos] = v;
+  }
+  group_sync<NW>();
+}
+
+// Sorts list `src[0..n)` of (depth bits, slot) by (depth, slot) and writes the slots to dst[0..n).
+template <int NW, typename CntT>
+__device__ __forceinline__ void sort_list(uint32_t* K0, uint32_t* V0, uint32_t* K1, uint32_t* V1, CntT* cnt,
+                                          uint32_t* red, const uint2* __restrict__ src,
+                                          uint32_t* __restrict__ dst, const int n, const int slot_bits,
+                                          const int w, const int lane) {
+  constexpr int NT = NW * 32;
+  const int tid = w * 32 + lane;
+  const int m = ((n + NT - 1) / NT) | 1;
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  for (int i = tid; i < n; i += NT) {
+    const uint2 p = src[i];
+    K0[i] = p.x;
+    V0[i] = p.y;
+    kmin = min(kmin, p.x);
+    kmax = max(kmax, p.x);
+  }
+  kmin = __reduce_min_sync(kFull, kmin);
+  kmax = __reduce_max_sync(kFull, kmax);
+  if (NW > 1) {
+    if (lane == 0) {
+      red[32 + w] = kmin;
+      red[64 + w] = kmax;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) {
+      kmin = min(kmin, red[32 + ww]);
+      kmax = max(kmax, red[64 + ww]);
+    }
+  } else {
+    __syncwarp();
+  }
+  const int bits = 32 - __clz(kmax - kmin);  // __clz(0) == 32
+  bool by_slot_done = false;
+  for (;;) {
+    for (int shift = 0; shift < bits; shift += kDigitBits) {
+      radix_pass<NW, false, CntT>(K0, V0, K1, V1, cnt, red, n, m, kmin, shift, w, lane);
+      uint32_t* t = K0; K0 = K1; K1 = t;
+      t = V0; V0 = V1; V1 = t;
+    }
+    if (by_slot_done) break;
+    // equal depths: ascending slot (the reference's stable sort over its ascending-slot emission order)
+    uint32_t long_run = 0;
+    for (int i = tid; i < n - 1; i += NT) {
+      const uint32_t k = K0[i];
+      if (K0[i + 1] == k && (i == 0 || K0[i - 1] != k)) {
+        int e = i + 2;
+        while (e < n && e < i + 17 && K0[e] == k) ++e;
+        if (e == i + 17) { long_run = 1; continue; }
+        for (int a = i + 1; a < e; ++a) {  // insertion sort of a short run, owned by this thread alone
+          const uint32_t v = V0[a];
+          int c = a - 1;
+          while (c >= i && V0[c] > v) { V0[c + 1] = V0[c]; --c; }
+          V0[c + 1] = v;
+        }
+      }
+    }
+    long_run = __any_sync(kFull, long_run);
+    if (NW > 1) {
+      if (tid == 0) red[96] = 0;
+      __syncthreads();
+      if (long_run && lane == 0) red[96] = 1;
+      __syncthreads();
+      long_run = red[96];
+    } else {
+      __syncwarp();
+    }
+    if (!long_run) break;
+    // a long run of equal depths: order the whole list by slot first; the depth passes keep that order among equals
+    for (int shift = 0; shift < slot_bits; shift += kDigitBits) {
+      radix_pass<NW, true, CntT>(K0, V0, K1, V1, cnt, red, n, m, 0u, shift, w, lane);
+      uint32_t* t = K0; K0 = K1; K1 = t;
+      t = V0; V0 = V1; V1 = t;
+    }
+    by_slot_done = true;
+  }
+  group_sync<NW>();
+  for (int i = tid; i < n; i += NT) dst[i] = V0[i];
+  group_sync<NW>();
+}
+
+// Kernel A: CTA of kSortWarpsA warps; the CTA first takes medium lists (all warps on one list), then every warp takes
+// short lists on its own.  Work is handed out through two device counters (header[8], header[9]).
+__global__ void __launch_bounds__(kSortWarpsA * 32)
+tile_sort_small_kernel(const int T, const int stride, const uint32_t* __restrict__ ctr,
+                       const uint32_t* __restrict__ list_a, uint32_t* __restrict__ header,
+                       const uint2* __restrict__ pairs, uint32_t* __restrict__ vals, const int slot_bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_red[128];
+  __shared__ uint32_t s_item;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n_short = header[1], n_medium = header[2];
+  uint32_t* const words = reinterpret_cast<uint32_t*>(smem_raw);
+  uint16_t* const counters = reinterpret_cast<uint16_t*>(words + 4 * kCapM);  // [32][128] for the CTA, [32][32] per warp
+  {
+    uint32_t* K0 = words;
+    uint32_t* V0 = K0 + kCapM;
+    uint32_t* K1 = V0 + kCapM;
+    uint32_t* V1 = K1 + kCapM;
+    for (;;) {
+      if (threadIdx.x == 0) s_item = atomicAdd(header + 9, 1u);
+      __syncthreads();
+      const uint32_t item = s_item;
+      __syncthreads();
+      if (item >= n_medium) break;
+      const uint32_t t = list_a[T - 1 - item];
+      const uint2 ce = *reinterpret_cast<const uint2*>(ctr + (size_t)t * stride);  // (count, end of list)
+      const uint32_t n = ce.x, start = ce.y - ce.x;
+      sort_list<kSortWarpsA, uint16_t>(K0, V0, K1, V1, counters, s_red, pairs + start, vals + start, (int)n, slot_bits,
+                                       w, lane);
+    }
+  }
+  {
+    uint32_t* K0 = words + w * (4 * kCapS);
+    uint32_t* V0 = K0 + kCapS;
+    uint32_t* K1 = V0 + kCapS;
+    uint32_t* V1 = K1 + kCapS;
+    uint16_t* cnt = counters + w * (kDigits * 32);
+    for (;;) {
+      uint32_t item = 0;
+      if (lane == 0) item = atomicAdd(header + 8, 1u);
+      item = __shfl_sync(kFull, item, 0);
+      if (item >= n_short) break;
+      const uint32_t t = list_a[item];
+      const uint2 ce = *reinterpret_cast<const uint2*>(ctr + (size_t)t * stride);
+      const uint32_t n = ce.x, start = ce.y - ce.x;
+      sort_list<1, uint16_t>(K0, V0, K1, V1, cnt, s_red, pairs + start, vals + start, (int)n, slot_bits, 0, lane);
+    }
+  }
+}
+
+// Kernel B: long lists, one 512-thread CTA per list, ~225 KB of shared memory.
+__global__ void __launch_bounds__(kSortWarpsB * 32)
+tile_sort_long_kernel(const int stride, const uint32_t* __restrict__ ctr, const uint32_t* __restrict__ list_b,
+                      const uint32_t* __restrict__ header, const uint2* __restrict__ pairs,
+                      uint32_t* __restrict__ vals, const int slot_bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_red[128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t* K0 = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* V0 = K0 + kCapL;
+  uint32_t* K1 = V0 + kCapL;
+  uint32_t* V1 = K1 + kCapL;
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(V1 + kCapL);
+  const uint32_t n_long = header[3];
+  for (uint32_t item = blockIdx.x; item < n_long; item += gridDim.x) {
+    const uint32_t t = list_b[item];
+    const uint2 ce = *reinterpret_cast<const uint2*>(ctr + (size_t)t * stride);
+    const uint32_t n = ce.x, start = ce.y - ce.x;
+    sort_list<kSortWarpsB, uint16_t>(K0, V0, K1, V1, cnt, s_red, pairs + start, vals + start, (int)n, slot_bits, w,
+                                     lane);
+  }
+}
+
+// Kernel C: lists that do not fit shared memory; the same routine with keys / slots in 16 n bytes of HBM scratch per
+// list and 32-bit counters in shared memory (128 KB).
+__global__ void __launch_bounds__(kSortWarpsC * 32)
+tile_sort_beyond_kernel(const int T, const int stride, const uint32_t* __restrict__ ctr,
+                        const uint32_t* __restrict__ list_b, const uint32_t* __restrict__ xl_off,
+                        const uint32_t* __restrict__ header, const uint2* __restrict__ pairs,
+                        uint32_t* __restrict__ vals, uint32_t* __restrict__ scratch, const int slot_bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_red[128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n_beyond = header[4];
+  for (uint32_t item = blockIdx.x; item < n_beyond; item += gridDim.x) {
+    const uint32_t t = list_b[T - 1 - item];
+    const uint2 ce = *reinterpret_cast<const uint2*>(ctr + (size_t)t * stride);
+    const uint32_t n = ce.x, start = ce.y - ce.x;
+    uint32_t* base = scratch + 4 * (size_t)xl_off[item];
+    sort_list<kSortWarpsC, uint32_t>(base, base + n, base + 2 * (size_t)n, base + 3 * (size_t)n,
+                                     reinterpret_cast<uint32_t*>(smem_raw), s_red, pairs + start, vals + start, (int)n,
+                                     slot_bits, w, lane);
+  }
+}
+
+// ---- diagnostics (hg_raster_debug_keys) ------------------------------------------------------------------------------
+// Inclusive sum of tiles_touched in slot order (the reference's point_offsets), one CTA.
+__global__ void __launch_bounds__(1024)
+debug_slot_offsets_kernel(const int P, const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < P; base += 1024) {
+    const int i = base + tid;
+    const uint32_t v = i < P ? tiles_touched[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t add = s_carry;
+    for (int ww = 0; ww < warp; ++ww) add += s_warp[ww];
+    if (i < P) offsets[i] = incl + add;
+    __syncthreads();
+    if (tid == 1023) s_carry = incl + add;
+    __syncthreads();
+  }
+}
+
+// Reference emission (duplicateWithKeys, rasterizer_impl.cu:70-115): 64-bit keys in ascending slot order.
 __global__ void __launch_bounds__(256)
 emit_keys_reference_kernel(const int P, const float* __restrict__ depths,
                            const uint32_t* __restrict__ offsets, const uint2* __restrict__ rects,
@@ -61,136 +517,96 @@ emit_keys_reference_kernel(const int P, const float* __restrict__ depths,
   }
 }
 
-__global__ void __launch_bounds__(256)
-rebuild_sorted_keys_kernel(const int R, const uint32_t* __restrict__ tiles_sorted,
+__global__ void __launch_bounds__(128)
+rebuild_sorted_keys_kernel(const int stride, const uint32_t* __restrict__ ctr,
                            const uint32_t* __restrict__ point_list, const float* __restrict__ depths,
                            uint64_t* __restrict__ keys) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R) return;
-  keys[i] = ((uint64_t)tiles_sorted[i] << 32) | (uint64_t)__float_as_uint(depths[point_list[i]]);
-}
-
-// tiles_touched in depth order (input of the second scan)
-struct TilesInDepthOrder {
-  const uint32_t* tiles_touched;
-  __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& slot) const { return tiles_touched[slot]; }
-};
-
-// Stage 2 emission: the i-th nearest splat writes its tile ids and its slot index behind those of all nearer
-// splats.  Culled slots have no tiles and sit at the end of the order.
-__global__ void __launch_bounds__(256)
-emit_instances_kernel(const int P, const uint32_t* __restrict__ depth_order,
-                      const uint32_t* __restrict__ offsets_sorted, const uint32_t* __restrict__ tiles_touched,
-                      const uint2* __restrict__ rects, const uint32_t grid_x, uint32_t* __restrict__ tile_ids,
-                      uint32_t* __restrict__ vals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const uint32_t idx = depth_order[i];
-  if (tiles_touched[idx] == 0) return;
-  uint32_t off = (i == 0) ? 0u : offsets_sorted[i - 1];
-  const uint2 r = rects[idx];
-  const uint32_t minx = r.x & 0xffffu, miny = r.x >> 16;
-  const uint32_t maxx = r.y & 0xffffu, maxy = r.y >> 16;
-  for (uint32_t y = miny; y < maxy; ++y) {
-    for (uint32_t x = minx; x < maxx; ++x) {
-      tile_ids[off] = y * grid_x + x;
-      vals[off] = idx;
-      ++off;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(const int L, const uint32_t* __restrict__ tiles, uint2* __restrict__ ranges) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L) return;
-  const uint32_t cur = tiles[idx];
-  if (idx == 0) {
-    ranges[cur].x = 0;
-  } else {
-    const uint32_t prev = tiles[idx - 1];
-    if (cur != prev) {
-      ranges[prev].y = idx;
-      ranges[cur].x = idx;
-    }
-    // As in the reference the end marker sits inside the else branch: a list
-    // with a single instance (L == 1) leaves its tile range at (0, 0).
-    if (idx == L - 1) ranges[cur].y = L;
-  }
+  const uint32_t t = blockIdx.x;
+  const uint32_t n = ctr[(size_t)t * stride], start = ctr[(size_t)t * stride + 1] - n;
+  for (uint32_t i = threadIdx.x; i < n; i += 128)
+    keys[start + i] = ((uint64_t)t << 32) | (uint64_t)__float_as_uint(depths[point_list[start + i]]);
 }
 
 }  // namespace
 
-size_t scan_temp_bytes(int P) {
-  size_t bytes = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, P);
-  return bytes;
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
 }
 
-size_t sort_temp_bytes(int64_t R) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (uint32_t*)nullptr, (int)R);
-  return bytes;
-}
-
-size_t depth_sort_temp_bytes(int P) {
-  size_t a = 0, b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, a, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, P);
-  cub::TransformInputIterator<uint32_t, TilesInDepthOrder, const uint32_t*> it(nullptr, TilesInDepthOrder{nullptr});
-  cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, P);
-  return a > b ? a : b;  // the depth-order scan reuses the depth sort's temp storage
-}
-
-int launch_scan(const GeomState& g, int P, size_t temp_bytes, cudaStream_t stream, bool debug) {
-  HG_CUDA_TRY(cub::DeviceScan::InclusiveSum(g.scan_temp, temp_bytes, g.tiles_touched,
-                                            g.point_offsets, P, stream));
-  HG_POST_LAUNCH(debug, stream, "scan");
+int launch_tile_scan(const GeomState& g, const ImageState& img, int T, uint32_t* host_header, cudaStream_t stream,
+                     bool debug) {
+  static const int cap_short = env_int("HG_SORT_SCAP", kCapS);
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(T, g.ctr_stride, (uint32_t)(cap_short < kCapS ? cap_short : kCapS),
+                                           g.tile_ctr, img.ranges, g.list_a, g.list_b, g.xl_off, g.bin_header,
+                                           host_header);
+  HG_POST_LAUNCH(debug, stream, "tile_scan");
   return HG_OK;
 }
 
-int launch_depth_sort(const GeomState& g, int P, size_t temp_bytes, cudaStream_t stream, bool debug) {
-  HG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(g.depth_sort_temp, temp_bytes, reinterpret_cast<const uint32_t*>(g.depths),
-                                              g.depth_sorted, g.slot_ids, g.depth_order, P, 0, 32, stream));
-  count_launch(4);
-  HG_POST_LAUNCH(debug, stream, "depth_sort");
+size_t binning_scratch_bytes(uint32_t beyond_pairs) { return beyond_pairs ? 16 * (size_t)beyond_pairs + 256 : 0; }
+
+int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinState& b, int T, dim3 grid,
+                   const uint32_t* header_host, cudaStream_t stream) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  HG_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sort_smem_bytes(kSortWarpsA, kCapM)));
+    HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_beyond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(kSortWarpsC * 32 * 32 * 4)));
+    HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sort_smem_bytes(kSortWarpsB, kCapL)));
+    attr_done[dev] = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool debug = in.debug != 0;
+  scatter_instances_kernel<<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths, grid.x,
+                                                                   g.ctr_stride, g.tile_ctr, b.pairs);
+  HG_POST_LAUNCH(debug, stream, "scatter_instances");
+  uint32_t slot_bits = 1;
+  while (slot_bits < 32 && ((uint32_t)(in.P - 1) >> slot_bits)) ++slot_bits;
+  const uint32_t n_short = header_host[1], n_medium = header_host[2], n_long = header_host[3], n_beyond = header_host[4];
+  if (n_long) {  // heaviest first
+    const int blocks = (int)(n_long < (uint32_t)sms ? n_long : (uint32_t)sms);
+    tile_sort_long_kernel<<<blocks, kSortWarpsB * 32, sort_smem_bytes(kSortWarpsB, kCapL), stream>>>(
+        g.ctr_stride, g.tile_ctr, g.list_b, g.bin_header, b.pairs, b.vals, (int)slot_bits);
+    HG_POST_LAUNCH(debug, stream, "tile_sort_long");
+  }
+  if (n_beyond) {
+    const int blocks = (int)(n_beyond < (uint32_t)sms ? n_beyond : (uint32_t)sms);
+    tile_sort_beyond_kernel<<<blocks, kSortWarpsC * 32, kSortWarpsC * 32 * 32 * 4, stream>>>(T, g.ctr_stride, g.tile_ctr, g.list_b, g.xl_off,
+                                                                      g.bin_header, b.pairs, b.vals, b.scratch,
+                                                                      (int)slot_bits);
+    HG_POST_LAUNCH(debug, stream, "tile_sort_beyond");
+  }
+  if (n_short + n_medium) {
+    const size_t smem = sort_smem_bytes(kSortWarpsA, kCapM);
+    const int per_sm = (int)((227 * 1024) / (smem + 1024));
+    const uint32_t want = n_medium + (n_short + kSortWarpsA - 1) / kSortWarpsA;
+    const uint32_t cap = (uint32_t)(sms * (per_sm > 0 ? per_sm : 1));
+    const int blocks = (int)(want < cap ? want : cap);
+    tile_sort_small_kernel<<<blocks, kSortWarpsA * 32, smem, stream>>>(T, g.ctr_stride, g.tile_ctr, g.list_a,
+                                                                        g.bin_header, b.pairs, b.vals, (int)slot_bits);
+    HG_POST_LAUNCH(debug, stream, "tile_sort_small");
+  }
   return HG_OK;
 }
 
-int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinState& b,
-                   const ImageState& img, const int* radii, int R, dim3 grid, size_t sort_bytes,
-                   size_t dtemp, cudaStream_t stream) {
-  (void)radii;
-  cub::TransformInputIterator<uint32_t, TilesInDepthOrder, const uint32_t*> tiles_sorted(g.depth_order,
-                                                                                        TilesInDepthOrder{g.tiles_touched});
-  HG_CUDA_TRY(cub::DeviceScan::InclusiveSum(g.depth_sort_temp, dtemp, tiles_sorted, g.offsets_sorted, in.P, stream));
-  HG_POST_LAUNCH(in.debug, stream, "scan_depth_order");
-  emit_instances_kernel<<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.depth_order, g.offsets_sorted, g.tiles_touched,
-                                                                g.rects, grid.x, b.keys_unsorted, b.vals_unsorted);
-  HG_POST_LAUNCH(in.debug, stream, "emit_instances");
-
-  const int bit = (int)higher_msb(grid.x * grid.y);
-  HG_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b.sort_temp, sort_bytes, b.keys_unsorted, b.keys,
-                                              b.vals_unsorted, b.vals, R, 0, bit, stream));
-  count_launch(1 + (bit + 7) / 8);
-
-  HG_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, (size_t)grid.x * grid.y * sizeof(uint2), stream));
-  tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, b.keys, img.ranges);
-  HG_POST_LAUNCH(in.debug, stream, "tile_ranges");
-  return HG_OK;
-}
-
-int launch_debug_keys(int P, const GeomState& g, const BinState& b, const int* radii, int R,
-                      dim3 grid, uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys_sorted,
-                      cudaStream_t stream) {
+int launch_debug_keys(int P, int T, const GeomState& g, const BinState& b, const int* radii, int R, dim3 grid,
+                      uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys_sorted, cudaStream_t stream) {
+  (void)R;
   if (keys_unsorted || vals_unsorted) {
+    debug_slot_offsets_kernel<<<1, 1024, 0, stream>>>(P, g.tiles_touched, g.point_offsets);
+    HG_POST_LAUNCH(true, stream, "debug_slot_offsets");
     emit_keys_reference_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.depths, g.point_offsets, g.rects, radii,
                                                                        grid.x, keys_unsorted, vals_unsorted);
     HG_POST_LAUNCH(true, stream, "emit_keys_reference");
   }
   if (keys_sorted) {
-    rebuild_sorted_keys_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, b.keys, b.vals, g.depths, keys_sorted);
+    rebuild_sorted_keys_kernel<<<T, 128, 0, stream>>>(g.ctr_stride, g.tile_ctr, b.vals, g.depths, keys_sorted);
     HG_POST_LAUNCH(true, stream, "rebuild_sorted_keys");
   }
   return HG_OK;

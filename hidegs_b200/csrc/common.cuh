@@ -1,13 +1,14 @@
 // common.cuh — shared definitions of the B200-native HiDeGS rasterizer.
 //
 // State layout (our own; opaque to callers, see hg_raster_layout):
-//   geometry buffer : depths f32[P] | tiles_touched u32[P] | point_offsets u32[P]
+//   geometry buffer : depths f32[P] | tiles_touched u32[P] | point_offsets u32[P] (diagnostics only)
 //                     | rects u32[P,2] (packed tile bounds) | cov3D f32[P,6]
-//                     | clamped u8[P] | records f32[P,16] | scan temp | slot_ids u32[P]
-//                     | depth_sorted u32[P] | depth_order u32[P] | offsets_sorted u32[P] | depth-sort temp
+//                     | clamped u8[P] | records f32[P,16]
+//                     | tile_ctr u32[T, stride] (count, cursor) | list_a u32[T] | list_b u32[T] | xl_off u32[T]
+//                     | binning header u32[16]
 //   image buffer    : final_T f32[HW] | n_contrib u32[HW] | ranges u32[T,2]
-//   binning buffer  : tile ids u32[R] (depth order) | tile ids u32[R] (sorted) | vals_unsorted u32[R]
-//                     | vals u32[R] | sort temp
+//   binning buffer  : vals u32[R] (= point_list) | pairs u32[R,2] (depth bits, slot; bucketed by tile)
+//                     | scratch for lists beyond shared memory (binning.cu)
 //
 // Splat record (64 B, one per rendered slot, written by preprocess, gathered by
 // both blend kernels with four LDG.128):
@@ -62,12 +63,13 @@ struct GeomState {
   float* cov3D;
   uint8_t* clamped;
   float4* records;
-  char* scan_temp;
-  uint32_t* slot_ids;
-  uint32_t* depth_sorted;
-  uint32_t* depth_order;
-  uint32_t* offsets_sorted;
-  char* depth_sort_temp;
+  uint32_t* tile_ctr;     // per tile, `ctr_stride` words apart: [0] instances (REDs of preprocess_fwd), [1] list offset,
+                          // after the scatter the END of its list
+  int ctr_stride;
+  uint32_t* list_a;       // short lists from the front, medium lists from the back
+  uint32_t* list_b;       // long lists from the front, lists beyond shared memory from the back
+  uint32_t* xl_off;       // scratch offset (in pairs) of the k-th list beyond shared memory
+  uint32_t* bin_header;   // see tile_scan_kernel
 };
 struct ImageState {
   float* final_T;
@@ -75,16 +77,12 @@ struct ImageState {
   uint2* ranges;
 };
 struct BinState {
-  uint32_t* keys_unsorted;  // tile ids, depth order
-  uint32_t* keys;           // tile ids, sorted
-  uint32_t* vals_unsorted;
-  uint32_t* vals;
-  char* sort_temp;
+  uint32_t* vals;     // point_list
+  uint2* pairs;       // (depth bits, slot) of every instance, bucketed by tile
+  uint32_t* scratch;  // only for lists beyond shared memory
 };
 
-size_t scan_temp_bytes(int P);
-size_t sort_temp_bytes(int64_t R);
-size_t depth_sort_temp_bytes(int P);
+size_t binning_scratch_bytes(uint32_t beyond_pairs);
 
 static inline GeomState geom_from(char* base, const hg_raster_layout& L) {
   GeomState g;
@@ -95,12 +93,12 @@ static inline GeomState geom_from(char* base, const hg_raster_layout& L) {
   g.cov3D = (float*)(base + L.cov3D);
   g.clamped = (uint8_t*)(base + L.clamped);
   g.records = (float4*)(base + L.records);
-  g.scan_temp = base + L.scan_temp;
-  g.slot_ids = (uint32_t*)(base + L.slot_ids);
-  g.depth_sorted = (uint32_t*)(base + L.depth_sorted);
-  g.depth_order = (uint32_t*)(base + L.depth_order);
-  g.offsets_sorted = (uint32_t*)(base + L.offsets_sorted);
-  g.depth_sort_temp = base + L.depth_sort_temp;
+  g.tile_ctr = (uint32_t*)(base + L.tile_ctr);
+  g.ctr_stride = (int)L.ctr_stride;
+  g.list_a = (uint32_t*)(base + L.tile_lists);
+  g.list_b = g.list_a + L.tiles;
+  g.xl_off = g.list_b + L.tiles;
+  g.bin_header = (uint32_t*)(base + L.bin_header);
   return g;
 }
 static inline ImageState image_from(char* base, const hg_raster_layout& L) {
@@ -112,11 +110,9 @@ static inline ImageState image_from(char* base, const hg_raster_layout& L) {
 }
 static inline BinState bin_from(char* base, const hg_raster_layout& L) {
   BinState b;
-  b.keys_unsorted = (uint32_t*)(base + L.keys_unsorted);
-  b.keys = (uint32_t*)(base + L.keys);
-  b.vals_unsorted = (uint32_t*)(base + L.vals_unsorted);
   b.vals = (uint32_t*)(base + L.vals);
-  b.sort_temp = base + L.sort_temp;
+  b.pairs = (uint2*)(base + L.pairs);
+  b.scratch = (uint32_t*)(base + L.binning_bytes);
   return b;
 }
 
@@ -136,14 +132,13 @@ static inline char* align_ptr(char* p, size_t a) {
 int launch_preprocess_fwd(const hg_raster_inputs& in, const GeomState& g, int* radii,
                           int* out_observe, dim3 grid, float focal_x, float focal_y,
                           cudaStream_t stream);
-int launch_scan(const GeomState& g, int P, size_t temp_bytes, cudaStream_t stream, bool debug);
-int launch_depth_sort(const GeomState& g, int P, size_t temp_bytes, cudaStream_t stream, bool debug);
-int launch_debug_keys(int P, const GeomState& g, const BinState& b, const int* radii, int R,
+int launch_tile_scan(const GeomState& g, const ImageState& img, int T, uint32_t* host_header, cudaStream_t stream,
+                     bool debug);
+int launch_debug_keys(int P, int T, const GeomState& g, const BinState& b, const int* radii, int R,
                       dim3 grid, uint64_t* keys_unsorted, uint32_t* vals_unsorted, uint64_t* keys_sorted,
                       cudaStream_t stream);
-int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinState& b,
-                   const ImageState& img, const int* radii, int R, dim3 grid, size_t sort_bytes,
-                   size_t depth_temp_bytes, cudaStream_t stream);
+int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinState& b, int T, dim3 grid,
+                   const uint32_t* header_host, cudaStream_t stream);
 int launch_blend_fwd(const hg_raster_inputs& in, const GeomState& g, const BinState& b,
                      const ImageState& img, dim3 grid, float focal_x, float focal_y,
                      float* out_color, float* out_invdepth, int* out_observe, float* out_all_map,

@@ -16,6 +16,7 @@
 // into shared memory and read back transposed; results go out as one 64-byte
 // splat record per slot plus the SoA arrays the binning stage reads.
 #include "common.cuh"
+#include "tile_instances.cuh"
 #include "sh_stage.cuh"
 
 namespace hg {
@@ -166,7 +167,8 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
                       int* __restrict__ out_observe, float* __restrict__ depths,
                       uint32_t* __restrict__ tiles_touched, uint2* __restrict__ rects,
                       float* __restrict__ cov3Ds, uint8_t* __restrict__ clamped,
-                      float4* __restrict__ records, uint32_t* __restrict__ slot_ids) {
+                      float4* __restrict__ records, uint32_t* __restrict__ tile_ctr,
+                      const int ctr_stride) {
   __shared__ float s_sh[kWarps][32 * kShStrideMax];
 
   const int t_idx = blockIdx.x * kThreads + threadIdx.x;
@@ -191,9 +193,6 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
     radii[t_idx] = 0;
     tiles_touched[t_idx] = 0;
     out_observe[t_idx] = 0;
-    // depth doubles as the key of the slot sort: culled slots sort behind every visible one
-    reinterpret_cast<uint32_t*>(depths)[t_idx] = 0xFFFFFFFFu;
-    slot_ids[t_idx] = (uint32_t)t_idx;
 
     px = __ldg(means3D + 3 * (size_t)r_idx);
     py = __ldg(means3D + 3 * (size_t)r_idx + 1);
@@ -352,6 +351,17 @@ preprocess_fwd_kernel(const int P, const int N, const int D, const int M,
     for (int c = 0; c < 3; ++c) rgb[c] = __ldg(colors_precomp + 3 * (size_t)t_idx + c);
   }
 
+  // Instances per tile (the bucket sizes of binning.cu): one RED per (splat, tile), the warp's instances spread evenly
+  // over its lanes whatever the rectangle sizes.
+  {
+    const uint32_t width = maxx - minx;
+    const WarpInstances wi(alive ? width * (maxy - miny) : 0u, minx | (miny << 16), width, lane);
+    for (uint32_t j0 = 0; j0 < wi.total; j0 += 32) {
+      int owner;
+      uint32_t tile;
+      if (wi.at(j0, grid_x, owner, tile)) atomicAdd(tile_ctr + (size_t)tile * ctr_stride, 1u);
+    }
+  }
   if (!alive) return;
 
   const float* am = pre_am;
@@ -394,7 +404,7 @@ int launch_preprocess_fwd(const hg_raster_inputs& in, const GeomState& g, int* r
       in.scale_modifier, in.rotations, in.opacities, in.shs, in.cov3D_precomp, in.colors_precomp,
       in.all_map, in.viewmatrix, in.projmatrix, in.campos, in.W, in.H, in.tan_fovx, in.tan_fovy,
       focal_x, focal_y, grid.x, grid.y, radii, out_observe, g.depths, g.tiles_touched, g.rects,
-      g.cov3D, g.clamped, g.records, g.slot_ids);
+      g.cov3D, g.clamped, g.records, g.tile_ctr, g.ctr_stride);
   HG_POST_LAUNCH(in.debug, stream, "preprocess_fwd");
   return HG_OK;
 }

@@ -53,15 +53,16 @@ struct StageTimer {
   }
 };
 
-// Pinned 4-byte landing slot for num_rendered and the event that signals its arrival (one per host thread and device).
-struct HostSlot { uint32_t* value = nullptr; cudaEvent_t ready = nullptr; int device = -1; };
+// Pinned landing slot for the binning header (num_rendered + list counts) and the event that signals its arrival (one per host thread and device).
+struct HostSlot { uint32_t* value = nullptr; uint32_t* device_value = nullptr; cudaEvent_t ready = nullptr; int device = -1; };
 static HostSlot* host_slot() {
   static thread_local HostSlot slots[16];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { set_error("cudaGetDevice failed"); return nullptr; }
   HostSlot& s = slots[dev];
   if (s.device != dev) {
-    if (cudaHostAlloc((void**)&s.value, 64, cudaHostAllocDefault) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&s.value, 64, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&s.device_value, s.value, 0) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming) != cudaSuccess) {
       set_error("allocating the pinned num_rendered slot failed: %s", cudaGetErrorString(cudaGetLastError()));
       return nullptr;
@@ -91,14 +92,13 @@ static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_la
   L->cov3D = take(p * 24);
   L->clamped = take(p);
   L->records = take(p * HG_REC_FLOATS * 4);
-  L->scan_temp_bytes = p ? scan_temp_bytes((int)p) : 0;
-  L->scan_temp = take(L->scan_temp_bytes);
-  L->slot_ids = take(p * 4);
-  L->depth_sorted = take(p * 4);
-  L->depth_order = take(p * 4);
-  L->offsets_sorted = take(p * 4);
-  L->depth_sort_temp_bytes = p ? depth_sort_temp_bytes((int)p) : 0;
-  L->depth_sort_temp = take(L->depth_sort_temp_bytes);
+  L->tiles = tiles;
+  // one 128-byte line per tile: the REDs / atomics of neighbouring tiles do not serialise in one L2 line
+  static const size_t stride = [] { const char* v = getenv("HG_CTR_STRIDE"); return (size_t)(v && *v ? atoi(v) : 32); }();
+  L->ctr_stride = stride < 2 ? 2 : stride;
+  L->tile_ctr = take(tiles * L->ctr_stride * 4);
+  L->tile_lists = take(tiles * 12);
+  L->bin_header = take(64);
   L->geom_bytes = off + kAlign;
   // image
   off = 0;
@@ -108,12 +108,8 @@ static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_la
   L->image_bytes = off + kAlign;
   // binning
   off = 0;
-  L->keys_unsorted = take(r * 4);
-  L->keys = take(r * 4);
-  L->vals_unsorted = take(r * 4);
-  L->vals = take(r * 4);
-  L->sort_temp_bytes = r ? sort_temp_bytes((int64_t)r) : 0;
-  L->sort_temp = take(L->sort_temp_bytes);
+  L->vals = take(r * 4);  // first: the backward only needs the sorted list
+  L->pairs = take(r * 8);
   L->binning_bytes = off + kAlign;
 }
 
@@ -219,36 +215,40 @@ int hg_raster_forward(const hg_raster_inputs* in, hg_alloc_fn geom_alloc, void* 
   const float focal_x = in->W / (2.0f * in->tan_fovx);
   const dim3 grid((in->W + HG_BLOCK_X - 1) / HG_BLOCK_X, (in->H + HG_BLOCK_Y - 1) / HG_BLOCK_Y, 1);
 
+  const int T = (int)(grid.x * grid.y);
   {
     StageTimer t(HG_STAGE_PREPROCESS_FWD, stream);
+    HG_CUDA_TRY(cudaMemsetAsync(g.tile_ctr, 0, (size_t)T * g.ctr_stride * sizeof(uint32_t), stream));
     rc = launch_preprocess_fwd(*in, g, radii, out_observe, grid, focal_x, focal_y, stream);
   }
   if (rc) return rc;
   // R is part of the API contract (returned to Python as an int,
-  // diff_gaussian_rasterization/__init__.py:89-93), so one sync is unavoidable.  The depth sort of the slots does
-  // not depend on R: it is queued behind the copy and runs while the host waits / allocates the binning buffer.
-  // (pinned landing slot + event per host thread and device: a pageable destination would make the "async" copy block)
+  // diff_gaussian_rasterization/__init__.py:89-93), so one sync is unavoidable.  The scan kernel stores R and the
+  // counts of the sort's work lists straight into mapped pinned host memory (one slot + event per host thread and
+  // device): no copy operation behind the kernel, the host wakes on the kernel's own completion event.
   HostSlot* slot = host_slot();
   if (!slot) return HG_ERR_CUDA;
   {
     StageTimer t(HG_STAGE_SCAN, stream);
-    rc = launch_scan(g, in->P, L.scan_temp_bytes, stream, in->debug != 0);
+    rc = launch_tile_scan(g, img, T, slot->device_value, stream, in->debug != 0);
     if (rc) return rc;
-    HG_CUDA_TRY(cudaMemcpyAsync(slot->value, g.point_offsets + in->P - 1, sizeof(uint32_t),
-                                cudaMemcpyDeviceToHost, stream));
     HG_CUDA_TRY(cudaEventRecord(slot->ready, stream));
-    rc = launch_depth_sort(g, in->P, L.depth_sort_temp_bytes, stream, in->debug != 0);
   }
   HG_CUDA_TRY(cudaEventSynchronize(slot->ready));
-  if (rc) return rc;
-  const uint32_t R = *slot->value;
+  uint32_t header[8];
+  memcpy(header, slot->value, sizeof(header));
+  const uint32_t R = header[0];
+  if (R > 0x7fffffffu) {
+    set_error("%u tile instances exceed the 31-bit num_rendered of the API", R);
+    return HG_ERR_INVALID_ARG;
+  }
   *num_rendered = (int)R;
 
   BinState b{};
   if (R > 0) {
     hg_raster_layout LB;
     fill_layout(in->P, in->W, in->H, (int64_t)R, &LB);
-    char* bin_raw = binning_alloc(binning_ctx, LB.binning_bytes);
+    char* bin_raw = binning_alloc(binning_ctx, LB.binning_bytes + binning_scratch_bytes(header[5]));
     if (!bin_raw) {
       set_error("binning allocator returned NULL");
       return HG_ERR_ALLOC;
@@ -256,7 +256,7 @@ int hg_raster_forward(const hg_raster_inputs* in, hg_alloc_fn geom_alloc, void* 
     b = bin_from(align_ptr(bin_raw, kAlign), LB);
     {
       StageTimer t(HG_STAGE_BINNING, stream);
-      rc = launch_binning(*in, g, b, img, radii, (int)R, grid, LB.sort_temp_bytes, L.depth_sort_temp_bytes, stream);
+      rc = launch_binning(*in, g, b, T, grid, header, stream);
     }
     if (rc) return rc;
   }
@@ -367,7 +367,8 @@ int hg_raster_debug_keys(int32_t P, int32_t W, int32_t H, int32_t R, const int32
   GeomState g = geom_from(align_ptr(const_cast<char*>(geom_buffer), kAlign), L);
   BinState b = bin_from(align_ptr(const_cast<char*>(binning_buffer), kAlign), L);
   const dim3 grid((W + HG_BLOCK_X - 1) / HG_BLOCK_X, (H + HG_BLOCK_Y - 1) / HG_BLOCK_Y, 1);
-  return launch_debug_keys(P, g, b, radii, R, grid, keys_unsorted, vals_unsorted, keys_sorted, (cudaStream_t)stream_);
+  return launch_debug_keys(P, (int)(grid.x * grid.y), g, b, radii, R, grid, keys_unsorted, vals_unsorted, keys_sorted,
+                           (cudaStream_t)stream_);
 }
 
 void hg_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }

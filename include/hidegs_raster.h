@@ -102,36 +102,29 @@ typedef struct hg_raster_inputs {
 /* Byte offsets of the arrays inside the three opaque scratch buffers
  * (test/diagnostic accessor). */
 typedef struct hg_raster_layout {
-  /* geometry buffer */
+  /* geometry buffer (depends on P and on the tile grid of W x H) */
   size_t geom_bytes;
-  size_t depths;        /* f32[P]; culled slots hold the bit pattern 0xFFFFFFFF (they sort last) */
-  size_t tiles_touched; /* u32[P]                                         */
-  size_t point_offsets; /* u32[P] inclusive prefix sum                    */
+  size_t depths;        /* f32[P] view depth of visible slots (culled slots: undefined) */
+  size_t tiles_touched; /* u32[P]; 0 for culled slots                     */
+  size_t point_offsets; /* u32[P] inclusive prefix sum; only filled by hg_raster_debug_keys */
   size_t rects;         /* u32[P,2] tile bounds: minx|miny<<16, maxx|maxy<<16 */
   size_t cov3D;         /* f32[P,6]                                       */
   size_t clamped;       /* u8[P] bit0..2 = r,g,b clamped                  */
   size_t records;       /* f32[P,16] splat record, see DESIGN.md          */
-  size_t scan_temp;
-  size_t scan_temp_bytes;
-  size_t slot_ids;       /* u32[P] 0..P-1                                  */
-  size_t depth_sorted;   /* u32[P] depth bits ascending (stable)           */
-  size_t depth_order;    /* u32[P] slot of the i-th nearest splat          */
-  size_t offsets_sorted; /* u32[P] inclusive sum of tiles_touched in depth order */
-  size_t depth_sort_temp;
-  size_t depth_sort_temp_bytes;
+  size_t tiles;         /* T = number of 16x16 tiles (a count, not an offset) */
+  size_t ctr_stride;    /* words between the counters of consecutive tiles (a count, not an offset) */
+  size_t tile_ctr;      /* u32[T, ctr_stride]: [t][0] instances of tile t, [t][1] end of its list in pairs / vals */
+  size_t tile_lists;    /* u32[3,T] work lists of the per-tile sort, by list length */
+  size_t bin_header;    /* u32[16]: R, list counts, work counters         */
   /* image buffer */
   size_t image_bytes;
   size_t final_T;   /* f32[H*W]                                           */
   size_t n_contrib; /* u32[H*W]                                           */
   size_t ranges;    /* u32[T,2]                                           */
-  /* binning buffer (sized for R instances) */
+  /* binning buffer (sized for R instances; lists too long for shared memory add sort scratch behind it) */
   size_t binning_bytes;
-  size_t keys_unsorted; /* u32[R] tile id of every instance, emitted in depth order */
-  size_t keys;          /* u32[R] tile ids after the stable sort          */
-  size_t vals_unsorted; /* u32[R] slot of every instance, depth order     */
-  size_t vals;          /* u32[R] == reference point_list                 */
-  size_t sort_temp;
-  size_t sort_temp_bytes;
+  size_t vals;      /* u32[R] == reference point_list                     */
+  size_t pairs;     /* u32[R,2] (depth bits, slot) of every instance, bucketed by tile, arrival order */
 } hg_raster_layout;
 
 HG_API int hg_raster_layout_query(int32_t P, int32_t W, int32_t H, int64_t R,
@@ -218,10 +211,10 @@ HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        int32_t n_chunks, hg_chunk_fn on_chunk,
                                        void *chunk_ctx, float *sh_sink, float sh_beta, void *stream);
 
-/* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it sorts the
- * visible splats by depth once (32-bit keys, P elements), emits the tile instances in that order and then sorts
- * them stably by tile id alone (getHigherMsb(tiles) bits) -- same final order as the reference's 45..47-bit sort,
- * ~5x less sort traffic.  This call reconstructs, from the buffers of a finished forward, what the reference holds:
+/* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it buckets the
+ * tile instances by tile (counts from the preprocess pass, one scan, one scatter) and sorts every tile's list by
+ * (depth, slot) in shared memory -- same final order as the reference's global 45..47-bit sort, one pass over the
+ * instances in HBM instead of six.  This call reconstructs, from the buffers of a finished forward, what the reference holds:
  *   keys_unsorted [R] u64, vals_unsorted [R] u32   duplicateWithKeys output (ascending slot, y-major / x-minor)
  *   keys_sorted   [R] u64                          binningState.point_list_keys after the sort
  * (any of the three may be NULL).  `radii` as returned by the forward. */
@@ -247,8 +240,8 @@ HG_API void hg_reset_launch_count(void);
  * record.  Used by bench.py for the live roofline numbers. */
 enum hg_stage {
   HG_STAGE_PREPROCESS_FWD = 0,
-  HG_STAGE_SCAN = 1,    /* tile-count scan + depth sort of the slots (overlaps the host's read of R) */
-  HG_STAGE_BINNING = 2, /* depth-order scan + instance emit + tile sort + tile ranges */
+  HG_STAGE_SCAN = 1,    /* tile counts -> list offsets, tile ranges, R, work lists (one CTA) */
+  HG_STAGE_BINNING = 2, /* instance scatter + per-tile sorts */
   HG_STAGE_BLEND_FWD = 3,
   HG_STAGE_ACCUM_ZERO = 4,
   HG_STAGE_BLEND_BWD = 5,

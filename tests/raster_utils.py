@@ -96,7 +96,6 @@ def our_state(fwd_out, P, W, H):
     st = dict(R=R)
     st["depths"] = view(geom, L.depths, 4 * P, torch.float32)
     st["tiles_touched"] = view(geom, L.tiles_touched, 4 * P, torch.int32)
-    st["point_offsets"] = view(geom, L.point_offsets, 4 * P, torch.int32)
     st["rects"] = view(geom, L.rects, 8 * P, torch.int32).view(P, 2)
     st["cov3D"] = view(geom, L.cov3D, 24 * P, torch.float32).view(P, 6)
     st["clamped"] = view(geom, L.clamped, P, torch.uint8)
@@ -106,9 +105,8 @@ def our_state(fwd_out, P, W, H):
     st["ranges"] = view(img, L.ranges, 8 * T, torch.int32).view(T, 2)
     if R > 0:
         st["point_list"] = view(binning, L.vals, 4 * R, torch.int32)
-        st["tile_ids_sorted"] = view(binning, L.keys, 4 * R, torch.int32)
-        # The library sorts (depth, then tile) in two stages and never holds the reference's 64-bit tile|depth keys;
-        # hg_raster_debug_keys rebuilds them from its buffers (see include/hidegs_raster.h).
+        # The library buckets the instances by tile and sorts each list on chip; it never holds the reference's 64-bit
+        # tile|depth keys.  hg_raster_debug_keys rebuilds them from its buffers (see include/hidegs_raster.h).
         dev = geom.device
         st["keys_unsorted"] = torch.empty(R, dtype=torch.int64, device=dev)
         st["vals_unsorted"] = torch.empty(R, dtype=torch.int32, device=dev)

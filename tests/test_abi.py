@@ -34,17 +34,18 @@ def test_library_exports_every_declared_symbol():
 
 def test_layout_query_is_consistent():
     L = _lib.layout(1000, 1920, 1080, 5000)
-    offs = [L.depths, L.tiles_touched, L.point_offsets, L.rects, L.cov3D, L.clamped, L.records, L.scan_temp, L.slot_ids,
-            L.depth_sorted, L.depth_order, L.offsets_sorted, L.depth_sort_temp]
+    offs = [L.depths, L.tiles_touched, L.point_offsets, L.rects, L.cov3D, L.clamped, L.records, L.tile_ctr, L.tile_lists,
+            L.bin_header]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs)
-    assert L.records - L.clamped >= 1000 and L.geom_bytes >= L.records + 64 * 1000
+    assert L.records - L.clamped >= 1000 and L.tile_ctr >= L.records + 64 * 1000
+    assert L.tiles == 120 * 68 and L.tile_lists - L.tile_ctr >= 4 * L.ctr_stride * L.tiles
+    assert L.bin_header - L.tile_lists >= 12 * L.tiles and L.geom_bytes >= L.bin_header + 64
     assert L.ranges + 8 * 120 * 68 <= L.image_bytes
-    assert L.keys - L.keys_unsorted >= 4 * 5000 and L.vals - L.vals_unsorted >= 4 * 5000
-    # (the CUB temp-size query needs a device, so sort_temp_bytes is 0 on a CPU-only box)
-    assert L.binning_bytes >= L.sort_temp + L.sort_temp_bytes
-    # binning layout only depends on R, geometry layout only on P
+    # the sorted list comes first in the binning block (all the backward reads), the bucketed pairs behind it
+    assert L.vals == 0 and L.pairs >= 4 * 5000 and L.binning_bytes >= L.pairs + 8 * 5000
+    # binning layout only depends on R, geometry layout on P and the tile grid
     L2 = _lib.layout(1000, 1920, 1080, 0)
-    assert L2.records == L.records and L2.keys_unsorted == 0
+    assert L2.records == L.records and L2.pairs == 0
 
 
 def test_layout_query_rejects_bad_sizes():
