@@ -37,7 +37,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 // ---- list-length classes ------------------------------------------------------------------------------------------
 constexpr int kSortWarpsA = 4;                      // tile_sort_kernel A: CTA of 4 warps
 constexpr int kCapS = 1024;                         // short list: one warp
-constexpr int kCapM = kCapS * kSortWarpsA;          // medium list: the CTA
+constexpr int kCapM = kCapS * kSortWarpsA / 2;      // medium list: the CTA (the short-list path holds 8 bytes per element)
 constexpr int kSortWarpsB = 16;                     // kernel B: 512 threads, one CTA per SM
 constexpr int kCapL = 12288;                        // 12288 * 16 B + 32 KB of counters = 224 KB
 constexpr int kSortWarpsC = 32;                     // kernel C: lists beyond shared memory, sorted in HBM scratch
@@ -101,10 +101,13 @@ tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32
     const uint32_t round_total = __shfl_sync(kFull, wincl, 31);
     uint32_t run = carry + before + incl - sum;
     carry += round_total;
+    int cls[4];
+    uint32_t starts[4], seen = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int t = t0 + k;
       const uint32_t nk = n[k];
+      starts[k] = run;
       if (t < T) {
         ctr[(size_t)t * stride + 1] = run;
         // identifyTileRanges: empty tiles keep the memset's (0, 0); with a single instance in the whole view the end
@@ -112,26 +115,32 @@ tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32
         ranges[t] = (nk && total != 1u) ? make_uint2(run, run + nk) : make_uint2(0u, 0u);
       }
       longest = max(longest, nk);
-      const int cls = nk == 0 ? 0 : nk <= cap_short ? 1 : nk <= (uint32_t)kCapM ? 2 : nk <= (uint32_t)kCapL ? 3 : 4;
+      cls[k] = nk == 0 ? 0 : nk <= cap_short ? 1 : nk <= (uint32_t)kCapM ? 2 : nk <= (uint32_t)kCapL ? 3 : 4;
+      seen |= 1u << cls[k];
+      run += nk;
+    }
+    seen = __reduce_or_sync(kFull, seen) & ~1u;
+    while (seen) {  // warp-aggregated appends, only for the classes this warp holds
+      const int c = __ffs(seen) - 1;
+      seen &= seen - 1;
 #pragma unroll
-      for (int c = 1; c <= 4; ++c) {  // warp-aggregated appends
-        const uint32_t m = __ballot_sync(kFull, cls == c);
-        if (m) {
-          uint32_t at = 0;
-          if (lane == __ffs(m) - 1) at = atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
-          at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & lt);
-          if (cls == c) {
-            if (c == 1) list_a[at] = (uint32_t)t;
-            else if (c == 2) list_a[T - 1 - at] = (uint32_t)t;
-            else if (c == 3) list_b[at] = (uint32_t)t;
-            else {
-              list_b[T - 1 - at] = (uint32_t)t;
-              xl_off[at] = atomicAdd(&s_cnt[5], nk);
-            }
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t m = __ballot_sync(kFull, cls[k] == c);
+        if (m == 0) continue;
+        uint32_t at = 0;
+        if (lane == __ffs(m) - 1) at = atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
+        at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & lt);
+        if (cls[k] == c) {
+          const uint32_t t = (uint32_t)(t0 + k);
+          if (c == 1) list_a[at] = t;
+          else if (c == 2) list_a[T - 1 - at] = t;
+          else if (c == 3) list_b[at] = t;
+          else {
+            list_b[T - 1 - at] = t;
+            xl_off[at] = atomicAdd(&s_cnt[5], n[k]);
           }
         }
       }
-      run += nk;
     }
   }
   longest = __reduce_max_sync(kFull, longest);
@@ -147,6 +156,7 @@ tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32
 }
 
 // ---- 3. scatter ---------------------------------------------------------------------------------------------------
+template <int PER>
 __global__ void __launch_bounds__(256)
 scatter_instances_kernel(const int P, const uint32_t* __restrict__ tiles_touched, const uint2* __restrict__ rects,
                          const float* __restrict__ depths, const uint32_t grid_x, const int stride,
@@ -163,18 +173,20 @@ scatter_instances_kernel(const int P, const uint32_t* __restrict__ tiles_touched
   }
   const uint32_t first = (uint32_t)(idx - lane);
   WarpInstances wi(cnt, r.x, (r.y & 0xffffu) - (r.x & 0xffffu), lane);
-  for (uint32_t j0 = 0; j0 < wi.total; j0 += 64) {  // two instances per lane: two atomics in flight
-    int owner0, owner1;
-    uint32_t tile0, tile1;
-    const bool on0 = wi.at(j0, grid_x, owner0, tile0);
-    const bool on1 = wi.at(j0 + 32, grid_x, owner1, tile1);
-    const uint32_t d0 = __shfl_sync(kFull, dbits, owner0);
-    const uint32_t d1 = __shfl_sync(kFull, dbits, owner1);
-    uint32_t pos0 = 0, pos1 = 0;
-    if (on0) pos0 = atomicAdd(ctr + (size_t)tile0 * stride + 1, 1u);
-    if (on1) pos1 = atomicAdd(ctr + (size_t)tile1 * stride + 1, 1u);
-    if (on0) pairs[pos0] = make_uint2(d0, first + owner0);
-    if (on1) pairs[pos1] = make_uint2(d1, first + owner1);
+  for (uint32_t j0 = 0; j0 < wi.total; j0 += 32 * PER) {  // PER instances per lane: PER atomics in flight
+    int owner[PER];
+    uint32_t tile[PER], d[PER], pos[PER];
+    bool on[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      on[q] = wi.at(j0 + 32 * q, grid_x, owner[q], tile[q]);
+      d[q] = __shfl_sync(kFull, dbits, owner[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) pos[q] = on[q] ? atomicAdd(ctr + (size_t)tile[q] * stride + 1, 1u) : 0u;
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+      if (on[q]) pairs[pos[q]] = make_uint2(d[q], first + owner[q]);
   }
 }
 
@@ -200,12 +212,13 @@ template <typename CntT> struct CntPack;
 template <> struct CntPack<uint16_t> { static constexpr int kWords = 16; };  // 32 counters in 16 words
 template <> struct CntPack<uint32_t> { static constexpr int kWords = 32; };
 
-template <int NW, bool BY_SLOT, typename CntT>
-__device__ __forceinline__ void radix_pass(const uint32_t* __restrict__ K0, const uint32_t* __restrict__ V0,
-                                           uint32_t* __restrict__ K1, uint32_t* __restrict__ V1,
-                                           CntT* __restrict__ cnt, uint32_t* __restrict__ red, const int n,
-                                           const int m, const uint32_t kmin, const int shift, const int w,
-                                           const int lane) {
+// One counting pass over the list.  `ops` supplies the element type and three operations:
+//   E load(int i)              the element at position i of the source buffer
+//   uint32_t digit(const E&)   its 5-bit digit in this pass
+//   void store(uint32_t pos, const E&)   put it at position pos of the destination buffer
+template <int NW, typename CntT, typename Ops>
+__device__ __forceinline__ void counting_pass(CntT* __restrict__ cnt, uint32_t* __restrict__ red, const int n,
+                                              const int m, const int w, const int lane, const Ops ops) {
   constexpr int NT = NW * 32;
   constexpr int kWords = CntPack<CntT>::kWords;
   const int tid = w * 32 + lane;
@@ -217,11 +230,23 @@ __device__ __forceinline__ void radix_pass(const uint32_t* __restrict__ K0, cons
   }
   group_sync<NW>();
   CntT* mine = cnt + tid;
-#pragma unroll 4
-  for (int i = b; i < e; ++i) {
-    const uint32_t key = BY_SLOT ? V0[i] : K0[i] - kmin;
-    const uint32_t d = (key >> shift) & (kDigits - 1u);
-    mine[d * NT] += 1;
+  // Four elements per step: their counters are read together and written back in order, equal digits inside the
+  // group folded into the increments — one shared-memory round trip per four elements instead of a read-modify-write
+  // chain per element.
+  for (int i = b; i < e; i += 4) {
+    uint32_t d[4], c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      d[j] = i + j < e ? ops.digit(ops.load(min(i + j, e - 1))) : kDigits + j;  // out of range: matches nothing
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = i + j < e ? (uint32_t)mine[d[j] * NT] : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t inc = 1;
+#pragma unroll
+      for (int q = 0; q < j; ++q) inc += d[q] == d[j];
+      if (i + j < e) mine[d[j] * NT] = (CntT)(c[j] + inc);
+    }
   }
   group_sync<NW>();
   // exclusive scan of the flat counter array: this thread's 32 consecutive counters, then across threads
@@ -275,17 +300,78 @@ __device__ __forceinline__ void radix_pass(const uint32_t* __restrict__ K0, cons
     for (int i = 0; i < kWords / 4; ++i) row[i] = make_uint4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
   }
   group_sync<NW>();
-#pragma unroll 4
-  for (int i = b; i < e; ++i) {
-    const uint32_t k = K0[i], v = V0[i];
-    const uint32_t key = BY_SLOT ? v : k - kmin;
-    const uint32_t d = (key >> shift) & (kDigits - 1u);
-    const uint32_t pos = mine[d * NT];
-    mine[d * NT] = (CntT)(pos + 1u);
-    K1[pos] = k;
-    V1[pos] = v;
+  for (int i = b; i < e; i += 4) {
+    uint32_t d[4], c[4];
+    typename Ops::E el[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      el[j] = ops.load(min(i + j, e - 1));
+      d[j] = i + j < e ? ops.digit(el[j]) : kDigits + j;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] = i + j < e ? (uint32_t)mine[d[j] * NT] : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t inc = 0;
+#pragma unroll
+      for (int q = 0; q < j; ++q) inc += d[q] == d[j];
+      if (i + j < e) {
+        const uint32_t pos = c[j] + inc;
+        mine[d[j] * NT] = (CntT)(pos + 1u);
+        ops.store(pos, el[j]);
+      }
+    }
   }
   group_sync<NW>();
+}
+
+// (key, slot) pairs in two arrays each way; the digit comes from the key (depth bits above kmin) or from the slot
+template <bool BY_SLOT>
+struct PairOps {
+  struct E { uint32_t k, v; };
+  const uint32_t* __restrict__ K0;
+  const uint32_t* __restrict__ V0;
+  uint32_t* __restrict__ K1;
+  uint32_t* __restrict__ V1;
+  uint32_t kmin;
+  int shift;
+  __device__ __forceinline__ E load(int i) const { return E{K0[i], V0[i]}; }
+  __device__ __forceinline__ uint32_t digit(const E& x) const {
+    return ((BY_SLOT ? x.v : x.k - kmin) >> shift) & (kDigits - 1u);
+  }
+  __device__ __forceinline__ void store(uint32_t pos, const E& x) const {
+    K1[pos] = x.k;
+    V1[pos] = x.v;
+  }
+};
+
+template <int NW, bool BY_SLOT, typename CntT>
+__device__ __forceinline__ void radix_pass(const uint32_t* K0, const uint32_t* V0, uint32_t* K1, uint32_t* V1,
+                                           CntT* cnt, uint32_t* red, const int n, const int m, const uint32_t kmin,
+                                           const int shift, const int w, const int lane) {
+  counting_pass<NW, CntT>(cnt, red, n, m, w, lane, PairOps<BY_SLOT>{K0, V0, K1, V1, kmin, shift});
+}
+
+// Equal depths: ascending slot (the reference's stable sort over its ascending-slot emission order).  Runs of up to 16
+// equal keys are insertion-sorted by the thread that owns their head; returns whether a longer run exists.
+template <int NT>
+__device__ __forceinline__ uint32_t order_short_runs(const uint32_t* K, uint32_t* V, const int n, const int tid) {
+  uint32_t long_run = 0;
+  for (int i = tid; i < n - 1; i += NT) {
+    const uint32_t k = K[i];
+    if (K[i + 1] == k && (i == 0 || K[i - 1] != k)) {
+      int e = i + 2;
+      while (e < n && e < i + 17 && K[e] == k) ++e;
+      if (e == i + 17) { long_run = 1; continue; }
+      for (int a = i + 1; a < e; ++a) {
+        const uint32_t v = V[a];
+        int c = a - 1;
+        while (c >= i && V[c] > v) { V[c + 1] = V[c]; --c; }
+        V[c + 1] = v;
+      }
+    }
+  }
+  return long_run;
 }
 
 // Sorts list `src[0..n)` of (depth bits, slot) by (depth, slot) and writes the slots to dst[0..n).
@@ -298,6 +384,7 @@ __device__ __forceinline__ void sort_list(uint32_t* K0, uint32_t* V0, uint32_t* 
   const int tid = w * 32 + lane;
   const int m = ((n + NT - 1) / NT) | 1;
   uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll 4
   for (int i = tid; i < n; i += NT) {
     const uint2 p = src[i];
     K0[i] = p.x;
@@ -330,22 +417,7 @@ __device__ __forceinline__ void sort_list(uint32_t* K0, uint32_t* V0, uint32_t* 
       t = V0; V0 = V1; V1 = t;
     }
     if (by_slot_done) break;
-    // equal depths: ascending slot (the reference's stable sort over its ascending-slot emission order)
-    uint32_t long_run = 0;
-    for (int i = tid; i < n - 1; i += NT) {
-      const uint32_t k = K0[i];
-      if (K0[i + 1] == k && (i == 0 || K0[i - 1] != k)) {
-        int e = i + 2;
-        while (e < n && e < i + 17 && K0[e] == k) ++e;
-        if (e == i + 17) { long_run = 1; continue; }
-        for (int a = i + 1; a < e; ++a) {  // insertion sort of a short run, owned by this thread alone
-          const uint32_t v = V0[a];
-          int c = a - 1;
-          while (c >= i && V0[c] > v) { V0[c + 1] = V0[c]; --c; }
-          V0[c + 1] = v;
-        }
-      }
-    }
+    uint32_t long_run = order_short_runs<NT>(K0, V0, n, tid);
     long_run = __any_sync(kFull, long_run);
     if (NW > 1) {
       if (tid == 0) red[96] = 0;
@@ -370,12 +442,85 @@ __device__ __forceinline__ void sort_list(uint32_t* K0, uint32_t* V0, uint32_t* 
   group_sync<NW>();
 }
 
+// Short lists, one warp, 8 bytes of shared memory per element instead of 16: once the first digit has been consumed
+// an element is ONE word — its remaining key bits above its arrival position (key' >> 5) << idx_bits | position — so the
+// later passes move 4 bytes per element, and twice as many warps fit an SM.  After the last pass the position part
+// gathers (depth bits, slot) back from the list's own segment in HBM (L2 hits).  Needs bits - 5 + idx_bits <= 32, i.e.
+// for a list of 1024 a depth spread below 2^27 ulps (a factor 65536 in depth); returns false, with nothing written, when
+// the list does not qualify or holds a run of more than 16 equal depths — the caller then takes the general routine.
+struct PackFirstOps {
+  struct E { uint32_t a; int i; };
+  const uint32_t* __restrict__ A;
+  uint32_t* __restrict__ B;
+  uint32_t kmin;
+  int idx_bits;
+  __device__ __forceinline__ E load(int i) const { return E{A[i] - kmin, i}; }
+  __device__ __forceinline__ uint32_t digit(const E& x) const { return x.a & (kDigits - 1u); }
+  __device__ __forceinline__ void store(uint32_t pos, const E& x) const {
+    B[pos] = ((x.a >> kDigitBits) << idx_bits) | (uint32_t)x.i;
+  }
+};
+struct PackNextOps {
+  struct E { uint32_t a; };
+  const uint32_t* __restrict__ X;
+  uint32_t* __restrict__ Y;
+  int shift;
+  __device__ __forceinline__ E load(int i) const { return E{X[i]}; }
+  __device__ __forceinline__ uint32_t digit(const E& x) const { return (x.a >> shift) & (kDigits - 1u); }
+  __device__ __forceinline__ void store(uint32_t pos, const E& x) const { Y[pos] = x.a; }
+};
+
+__device__ __forceinline__ bool sort_short_packed(uint32_t* A, uint32_t* B, uint16_t* cnt, const uint2* __restrict__ src,
+                                                  uint32_t* __restrict__ dst, const int n, const int lane) {
+  const int m = ((n + 31) >> 5) | 1;
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll 4
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t k = src[i].x;
+    A[i] = k;
+    kmin = min(kmin, k);
+    kmax = max(kmax, k);
+  }
+  kmin = __reduce_min_sync(kFull, kmin);
+  kmax = __reduce_max_sync(kFull, kmax);
+  __syncwarp();
+  const int bits = 32 - __clz(kmax - kmin);
+  const int idx_bits = n > 1 ? 32 - __clz(n - 1) : 1;  // positions < n fit
+  if (bits - kDigitBits + idx_bits > 32 || (bits == 0 && n > 16)) return false;
+  uint32_t* X = A;  // buffer that holds the current order
+  uint32_t* Y = B;
+  if (bits > 0) {
+    counting_pass<1, uint16_t>(cnt, nullptr, n, m, 0, lane, PackFirstOps{A, B, kmin, idx_bits});
+    X = B;
+    Y = A;
+    for (int done = kDigitBits; done < bits; done += kDigitBits) {
+      counting_pass<1, uint16_t>(cnt, nullptr, n, m, 0, lane, PackNextOps{X, Y, idx_bits + done - kDigitBits});
+      uint32_t* t = X; X = Y; Y = t;
+    }
+  }
+  // positions -> (depth bits, slot): keys into Y, slots over the packed words
+  const uint32_t mask = (1u << idx_bits) - 1u;
+#pragma unroll 4
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t at = bits > 0 ? (X[i] & mask) : (uint32_t)i;
+    const uint2 p = src[at];
+    Y[i] = p.x;
+    X[i] = p.y;
+  }
+  __syncwarp();
+  if (__any_sync(kFull, order_short_runs<32>(Y, X, n, lane))) return false;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) dst[i] = X[i];
+  __syncwarp();
+  return true;
+}
+
 // Kernel A: CTA of kSortWarpsA warps; the CTA first takes medium lists (all warps on one list), then every warp takes
 // short lists on its own.  Work is handed out through two device counters (header[8], header[9]).
 __global__ void __launch_bounds__(kSortWarpsA * 32)
 tile_sort_small_kernel(const int T, const int stride, const uint32_t* __restrict__ ctr,
-                       const uint32_t* __restrict__ list_a, uint32_t* __restrict__ header,
-                       const uint2* __restrict__ pairs, uint32_t* __restrict__ vals, const int slot_bits) {
+                       const uint32_t* __restrict__ list_a, uint32_t* __restrict__ header, uint2* pairs,
+                       uint32_t* __restrict__ vals, const int slot_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_red[128];
   __shared__ uint32_t s_item;
@@ -402,10 +547,8 @@ tile_sort_small_kernel(const int T, const int stride, const uint32_t* __restrict
     }
   }
   {
-    uint32_t* K0 = words + w * (4 * kCapS);
-    uint32_t* V0 = K0 + kCapS;
-    uint32_t* K1 = V0 + kCapS;
-    uint32_t* V1 = K1 + kCapS;
+    uint32_t* A = words + w * (2 * kCapS);
+    uint32_t* B = A + kCapS;
     uint16_t* cnt = counters + w * (kDigits * 32);
     for (;;) {
       uint32_t item = 0;
@@ -415,7 +558,13 @@ tile_sort_small_kernel(const int T, const int stride, const uint32_t* __restrict
       const uint32_t t = list_a[item];
       const uint2 ce = *reinterpret_cast<const uint2*>(ctr + (size_t)t * stride);
       const uint32_t n = ce.x, start = ce.y - ce.x;
-      sort_list<1, uint16_t>(K0, V0, K1, V1, cnt, s_red, pairs + start, vals + start, (int)n, slot_bits, 0, lane);
+      if (!sort_short_packed(A, B, cnt, pairs + start, vals + start, (int)n, lane)) {
+        // general routine: keys / slots in the warp's two buffers, the other half of the ping-pong in the list's own
+        // (already consumed) segment of `pairs`
+        uint32_t* spill = reinterpret_cast<uint32_t*>(pairs + start);
+        sort_list<1, uint16_t>(A, B, spill, spill + n, cnt, s_red, pairs + start, vals + start, (int)n, slot_bits, 0,
+                               lane);
+      }
     }
   }
 }
@@ -563,8 +712,16 @@ int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinStat
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool debug = in.debug != 0;
-  scatter_instances_kernel<<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths, grid.x,
-                                                                   g.ctr_stride, g.tile_ctr, b.pairs);
+  static const int per = env_int("HG_SCATTER_PER", 2);
+  if (per == 4)
+    scatter_instances_kernel<4><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths,
+                                                                        grid.x, g.ctr_stride, g.tile_ctr, b.pairs);
+  else if (per == 1)
+    scatter_instances_kernel<1><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths,
+                                                                        grid.x, g.ctr_stride, g.tile_ctr, b.pairs);
+  else
+    scatter_instances_kernel<2><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths,
+                                                                        grid.x, g.ctr_stride, g.tile_ctr, b.pairs);
   HG_POST_LAUNCH(debug, stream, "scatter_instances");
   uint32_t slot_bits = 1;
   while (slot_bits < 32 && ((uint32_t)(in.P - 1) >> slot_bits)) ++slot_bits;

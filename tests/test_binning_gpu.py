@@ -3,7 +3,8 @@ shared-memory radix sort against the reference's global 64-bit key sort (rasteri
 
 Bit-exact bar: num_rendered, the sorted 64-bit keys, point_list and the tile ranges — including equal depths
 (the reference's stable sort leaves them in ascending slot order) and lists of every length class the sort
-dispatches on (one warp <= 1024, one CTA <= 4096, 512-thread CTA <= 12288, HBM scratch beyond)."""
+dispatches on (one warp <= 1024 — packed one-word elements, with the general routine as its fallback —, one CTA <= 2048,
+512-thread CTA <= 12288, HBM scratch beyond)."""
 import numpy as np
 import pytest
 import torch
@@ -85,7 +86,7 @@ def test_all_depths_equal(cuda_device):
 
 
 @pytest.mark.parametrize("what,n,scale,lo,hi", [
-    ("medium lists (CTA)", 6000, 0.35, 1025, 4096),          # lists of 1892 .. 3720
+    ("medium and long lists", 6000, 0.35, 1025, 4096),       # lists of 1892 .. 3720: CTA (<= 2048) and 512-thread CTA
     ("long lists (512-thread CTA)", 12000, 0.6, 4097, 12288),  # 6368 .. 10061
     ("lists beyond shared memory", 30000, 1.2, 12289, None),   # 25850 .. 29432
 ])
@@ -93,6 +94,21 @@ def test_list_length_classes(cuda_device, what, n, scale, lo, hi):
     import math
     case = ru.build_case(n, 64, 48, seed=41, log_scale_mean=math.log(scale))
     _check(case, cuda_device, what, min_longest=lo, max_longest=hi)
+
+
+def test_wide_depth_range_short_lists(cuda_device):
+    """Depths from 0.3 to 2e5 inside one tile: more than 27 significant key bits, so lists of 513..1024 entries do not
+    fit the one-word packing of the short-list path and take its fallback (67 such lists in this scene)."""
+    import math
+    n = 3000
+    case = ru.build_case(n, 208, 120, seed=51, log_scale_mean=math.log(0.06))
+    g = torch.Generator().manual_seed(3)
+    z = torch.exp(torch.rand(n, generator=g) * (math.log(2e5) - math.log(0.3)) + math.log(0.3))
+    xy = (torch.rand(n, 2, generator=g) * 2 - 1) * torch.tensor([0.55, 0.3])
+    case["means3D"] = torch.cat([xy * z[:, None], (z - 5.0)[:, None]], 1).contiguous()
+    case["scales"] = (case["scales"] * z[:, None]).contiguous()
+    case["all_map"] = ru.syn.geometry_all_map(case["means3D"], case["scales"], case["rotations"], case["cam"])
+    _check(case, cuda_device, "wide depth range", min_longest=513)
 
 
 def test_mixed_classes_with_ties(cuda_device):

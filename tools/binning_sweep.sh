@@ -15,5 +15,5 @@ except Exception as e:
 PY
 }
 run base HG_CTR_STRIDE=2
-run scap512 HG_CTR_STRIDE=2 HG_SORT_SCAP=512
-run scap256 HG_CTR_STRIDE=2 HG_SORT_SCAP=256
+run per4 HG_CTR_STRIDE=2 HG_SCATTER_PER=4
+run per1 HG_CTR_STRIDE=2 HG_SCATTER_PER=1
