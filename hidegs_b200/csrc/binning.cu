@@ -15,18 +15,18 @@
 //   3. scatter_instances_kernel appends (depth bits, slot) to its tile's list through a per-tile cursor
 //      (arrival order is arbitrary: 32 atomics in flight per warp, the instances of a warp's 32 splats are spread
 //      evenly over its lanes whatever the splat sizes);
-//   4. tile_sort kernels sort every list in SHARED MEMORY with a stable LSD radix sort over only the depth bits in
-//      which the list's keys differ (min/max first; typically 3-4 eight-bit passes), ranks by warp match instead of
-//      atomics, a warp per short list (<= 512), a CTA per medium list, a 512-thread CTA with 214 KB of shared memory
-//      per long list, a global-memory version of the same routine for lists beyond that.  Ties in depth are put in
-//      ascending slot order afterwards (short runs in place; a list with a long run is re-sorted slot-first, which
-//      the stable depth passes then preserve), so point_list is bit-identical to the reference's, ties included.
+//   4. tile_sort kernels sort every list in SHARED MEMORY with a stable LSD radix sort (5-bit digits) over only the
+//      depth bits in which the list's keys differ (min/max first: 24 bits = 5 passes at config 2).  Ranks come from
+//      thread-private digit counters and one scan per pass — no atomics, no warp collectives in the element loops.  A
+//      warp per short list (<= 1024, elements packed into one word after the first pass), a CTA per medium list
+//      (<= 2048), a 512-thread CTA with 224 KB of shared memory per long list (<= 12288), the same routine over HBM
+//      scratch for lists beyond that.  Ties in depth are put in ascending slot order afterwards (short runs in place;
+//      a list with a long run is re-sorted slot-first, which the stable depth passes then preserve), so point_list is
+//      bit-identical to the reference's, ties included.
 // HBM traffic: 8 R written + 8 R read + 4 R written (the reference: 12 R written, then 6 x 24 R through the sort).
 // The 64-bit keys themselves are only reconstructed on request (hg_raster_debug_keys) for the parity tests.
 #include "common.cuh"
 #include "tile_instances.cuh"
-
-#include <cstdlib>
 
 namespace hg {
 
@@ -50,13 +50,15 @@ __host__ __device__ constexpr size_t sort_smem_bytes(int warps, int cap) {
 // ---- 2. counts -> offsets, ranges, work lists ------------------------------------------------------------------------
 // header: [0] R  [1] #short  [2] #medium  [3] #long  [4] #beyond  [5] pairs in "beyond" lists  [6] longest list  [7] -
 //         [8..11] work counters of the sort kernels (zeroed here)
-// One CTA; rounds of 4096 tiles, four consecutive tiles per thread.  `host_header` is mapped pinned host memory: the
-// kernel stores the eight header words straight into it (no separate copy operation behind the kernel).
+// One CTA; rounds of 1024 consecutive tiles, one per thread, so that every global access of a warp is contiguous
+// (a single SM issues all of this kernel's memory traffic: with four tiles per thread the 32-byte lane stride made it
+// 40 k sector transactions and 18 us; now ~7 k).  `host_header` is mapped pinned host memory: the kernel stores the
+// eight header words straight into it (no separate copy operation behind the kernel).
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32_t* __restrict__ ctr,
                  uint2* __restrict__ ranges, uint32_t* __restrict__ list_a, uint32_t* __restrict__ list_b,
                  uint32_t* __restrict__ xl_off, uint32_t* __restrict__ header, volatile uint32_t* host_header) {
-  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_warp[2][32];
   __shared__ uint32_t s_cnt[8];
   __shared__ uint32_t s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -66,79 +68,59 @@ tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32
   uint32_t part = 0;
   for (int t = tid; t < T; t += 1024) part += ctr[(size_t)t * stride];
   part = __reduce_add_sync(kFull, part);
-  if (lane == 0) s_warp[warp] = part;
+  if (lane == 0) s_warp[1][warp] = part;
   __syncthreads();
   if (warp == 0) {
-    const uint32_t v = __reduce_add_sync(kFull, s_warp[lane]);
+    const uint32_t v = __reduce_add_sync(kFull, s_warp[1][lane]);
     if (lane == 0) s_total = v;
   }
   __syncthreads();
   const uint32_t total = s_total;
   uint32_t carry = 0, longest = 0;
-  for (int base = 0; base < T; base += 4096) {
-    const int t0 = base + tid * 4;
-    uint32_t n[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) n[k] = t0 + k < T ? ctr[(size_t)(t0 + k) * stride] : 0u;
-    const uint32_t sum = n[0] + n[1] + n[2] + n[3];
-    uint32_t incl = sum;
+  int round = 0;
+  for (int base = 0; base < T; base += 1024, round ^= 1) {
+    const int t = base + tid;
+    const uint32_t n = t < T ? ctr[(size_t)t * stride] : 0u;
+    uint32_t incl = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t v = __shfl_up_sync(kFull, incl, o);
       if (lane >= o) incl += v;
     }
-    __syncthreads();  // s_warp of the previous round has been read
-    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 31) s_warp[round][warp] = incl;  // double-buffered: one barrier per round
     __syncthreads();
-    uint32_t wsum = s_warp[lane];
+    const uint32_t wsum = s_warp[round][lane];
     uint32_t wincl = wsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t v = __shfl_up_sync(kFull, wincl, o);
       if (lane >= o) wincl += v;
     }
-    const uint32_t before = __shfl_sync(kFull, wincl - wsum, warp);
-    const uint32_t round_total = __shfl_sync(kFull, wincl, 31);
-    uint32_t run = carry + before + incl - sum;
-    carry += round_total;
-    int cls[4];
-    uint32_t starts[4], seen = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int t = t0 + k;
-      const uint32_t nk = n[k];
-      starts[k] = run;
-      if (t < T) {
-        ctr[(size_t)t * stride + 1] = run;
-        // identifyTileRanges: empty tiles keep the memset's (0, 0); with a single instance in the whole view the end
-        // marker is never written (rasterizer_impl.cu:133-141), so that tile reads (0, 0) as well.
-        ranges[t] = (nk && total != 1u) ? make_uint2(run, run + nk) : make_uint2(0u, 0u);
-      }
-      longest = max(longest, nk);
-      cls[k] = nk == 0 ? 0 : nk <= cap_short ? 1 : nk <= (uint32_t)kCapM ? 2 : nk <= (uint32_t)kCapL ? 3 : 4;
-      seen |= 1u << cls[k];
-      run += nk;
+    const uint32_t start = carry + __shfl_sync(kFull, wincl - wsum, warp) + incl - n;
+    carry += __shfl_sync(kFull, wincl, 31);
+    if (t < T) {
+      ctr[(size_t)t * stride + 1] = start;
+      // identifyTileRanges: empty tiles keep the memset's (0, 0); with a single instance in the whole view the end
+      // marker is never written (rasterizer_impl.cu:133-141), so that tile reads (0, 0) as well.
+      ranges[t] = (n && total != 1u) ? make_uint2(start, start + n) : make_uint2(0u, 0u);
     }
-    seen = __reduce_or_sync(kFull, seen) & ~1u;
+    longest = max(longest, n);
+    const int cls = n == 0 ? 0 : n <= cap_short ? 1 : n <= (uint32_t)kCapM ? 2 : n <= (uint32_t)kCapL ? 3 : 4;
+    uint32_t seen = __reduce_or_sync(kFull, 1u << cls) & ~1u;
     while (seen) {  // warp-aggregated appends, only for the classes this warp holds
       const int c = __ffs(seen) - 1;
       seen &= seen - 1;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t m = __ballot_sync(kFull, cls[k] == c);
-        if (m == 0) continue;
-        uint32_t at = 0;
-        if (lane == __ffs(m) - 1) at = atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
-        at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & lt);
-        if (cls[k] == c) {
-          const uint32_t t = (uint32_t)(t0 + k);
-          if (c == 1) list_a[at] = t;
-          else if (c == 2) list_a[T - 1 - at] = t;
-          else if (c == 3) list_b[at] = t;
-          else {
-            list_b[T - 1 - at] = t;
-            xl_off[at] = atomicAdd(&s_cnt[5], n[k]);
-          }
+      const uint32_t m = __ballot_sync(kFull, cls == c);
+      uint32_t at = 0;
+      if (lane == __ffs(m) - 1) at = atomicAdd(&s_cnt[c], (uint32_t)__popc(m));
+      at = __shfl_sync(kFull, at, __ffs(m) - 1) + __popc(m & lt);
+      if (cls == c) {
+        if (c == 1) list_a[at] = (uint32_t)t;
+        else if (c == 2) list_a[T - 1 - at] = (uint32_t)t;
+        else if (c == 3) list_b[at] = (uint32_t)t;
+        else {
+          list_b[T - 1 - at] = (uint32_t)t;
+          xl_off[at] = atomicAdd(&s_cnt[5], n);
         }
       }
     }
@@ -149,7 +131,7 @@ tile_scan_kernel(const int T, const int stride, const uint32_t cap_short, uint32
   if (tid < 8) {
     const uint32_t v = tid == 0 ? total : s_cnt[tid];
     header[tid] = v;
-    host_header[tid] = v;
+    if (host_header) host_header[tid] = v;
   } else if (tid < 12) {
     header[tid] = 0;
   }
@@ -233,21 +215,22 @@ __device__ __forceinline__ void counting_pass(CntT* __restrict__ cnt, uint32_t* 
   // Four elements per step: their counters are read together and written back in order, equal digits inside the
   // group folded into the increments — one shared-memory round trip per four elements instead of a read-modify-write
   // chain per element.
-  for (int i = b; i < e; i += 4) {
+  int i = b;
+  for (; i + 4 <= e; i += 4) {
     uint32_t d[4], c[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      d[j] = i + j < e ? ops.digit(ops.load(min(i + j, e - 1))) : kDigits + j;  // out of range: matches nothing
+    for (int j = 0; j < 4; ++j) d[j] = ops.digit(ops.load(i + j));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = i + j < e ? (uint32_t)mine[d[j] * NT] : 0u;
+    for (int j = 0; j < 4; ++j) c[j] = (uint32_t)mine[d[j] * NT];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t inc = 1;
 #pragma unroll
       for (int q = 0; q < j; ++q) inc += d[q] == d[j];
-      if (i + j < e) mine[d[j] * NT] = (CntT)(c[j] + inc);
+      mine[d[j] * NT] = (CntT)(c[j] + inc);
     }
   }
+  for (; i < e; ++i) mine[ops.digit(ops.load(i)) * NT] += 1;
   group_sync<NW>();
   // exclusive scan of the flat counter array: this thread's 32 consecutive counters, then across threads
   {
@@ -300,27 +283,32 @@ __device__ __forceinline__ void counting_pass(CntT* __restrict__ cnt, uint32_t* 
     for (int i = 0; i < kWords / 4; ++i) row[i] = make_uint4(c[4 * i], c[4 * i + 1], c[4 * i + 2], c[4 * i + 3]);
   }
   group_sync<NW>();
-  for (int i = b; i < e; i += 4) {
+  i = b;
+  for (; i + 4 <= e; i += 4) {
     uint32_t d[4], c[4];
     typename Ops::E el[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      el[j] = ops.load(min(i + j, e - 1));
-      d[j] = i + j < e ? ops.digit(el[j]) : kDigits + j;
+      el[j] = ops.load(i + j);
+      d[j] = ops.digit(el[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) c[j] = i + j < e ? (uint32_t)mine[d[j] * NT] : 0u;
+    for (int j = 0; j < 4; ++j) c[j] = (uint32_t)mine[d[j] * NT];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t inc = 0;
+      uint32_t pos = c[j];
 #pragma unroll
-      for (int q = 0; q < j; ++q) inc += d[q] == d[j];
-      if (i + j < e) {
-        const uint32_t pos = c[j] + inc;
-        mine[d[j] * NT] = (CntT)(pos + 1u);
-        ops.store(pos, el[j]);
-      }
+      for (int q = 0; q < j; ++q) pos += d[q] == d[j];
+      mine[d[j] * NT] = (CntT)(pos + 1u);
+      ops.store(pos, el[j]);
     }
+  }
+  for (; i < e; ++i) {
+    const typename Ops::E el = ops.load(i);
+    const uint32_t d = ops.digit(el);
+    const uint32_t pos = mine[d * NT];
+    mine[d * NT] = (CntT)(pos + 1u);
+    ops.store(pos, el);
   }
   group_sync<NW>();
 }
@@ -550,13 +538,20 @@ tile_sort_small_kernel(const int T, const int stride, const uint32_t* __restrict
     uint32_t* A = words + w * (2 * kCapS);
     uint32_t* B = A + kCapS;
     uint16_t* cnt = counters + w * (kDigits * 32);
-    for (;;) {
+    // the next list is claimed, and its counters fetched, before the current one is sorted: the three dependent
+    // global round trips of a hand-out (counter, list entry, tile counters) overlap the sort
+    auto claim = [&](uint2& ce) -> bool {
       uint32_t item = 0;
       if (lane == 0) item = atomicAdd(header + 8, 1u);
       item = __shfl_sync(kFull, item, 0);
-      if (item >= n_short) break;
-      const uint32_t t = list_a[item];
-      const uint2 ce = *reinterpret_cast<const uint2*>(ctr + (size_t)t * stride);
+      if (item >= n_short) return false;
+      ce = *reinterpret_cast<const uint2*>(ctr + (size_t)list_a[item] * stride);  // (count, end of list)
+      return true;
+    };
+    uint2 ce = make_uint2(0u, 0u), ce_next = make_uint2(0u, 0u);
+    bool have = claim(ce);
+    while (have) {
+      const bool have_next = claim(ce_next);
       const uint32_t n = ce.x, start = ce.y - ce.x;
       if (!sort_short_packed(A, B, cnt, pairs + start, vals + start, (int)n, lane)) {
         // general routine: keys / slots in the warp's two buffers, the other half of the ping-pong in the list's own
@@ -565,6 +560,8 @@ tile_sort_small_kernel(const int T, const int stride, const uint32_t* __restrict
         sort_list<1, uint16_t>(A, B, spill, spill + n, cnt, s_red, pairs + start, vals + start, (int)n, slot_bits, 0,
                                lane);
       }
+      ce = ce_next;
+      have = have_next;
     }
   }
 }
@@ -678,17 +675,10 @@ rebuild_sorted_keys_kernel(const int stride, const uint32_t* __restrict__ ctr,
 
 }  // namespace
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
 int launch_tile_scan(const GeomState& g, const ImageState& img, int T, uint32_t* host_header, cudaStream_t stream,
                      bool debug) {
-  static const int cap_short = env_int("HG_SORT_SCAP", kCapS);
-  tile_scan_kernel<<<1, 1024, 0, stream>>>(T, g.ctr_stride, (uint32_t)(cap_short < kCapS ? cap_short : kCapS),
-                                           g.tile_ctr, img.ranges, g.list_a, g.list_b, g.xl_off, g.bin_header,
-                                           host_header);
+  tile_scan_kernel<<<1, 1024, 0, stream>>>(T, g.ctr_stride, (uint32_t)kCapS, g.tile_ctr, img.ranges, g.list_a, g.list_b,
+                                           g.xl_off, g.bin_header, host_header);
   HG_POST_LAUNCH(debug, stream, "tile_scan");
   return HG_OK;
 }
@@ -712,16 +702,10 @@ int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinStat
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool debug = in.debug != 0;
-  static const int per = env_int("HG_SCATTER_PER", 2);
-  if (per == 4)
-    scatter_instances_kernel<4><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths,
-                                                                        grid.x, g.ctr_stride, g.tile_ctr, b.pairs);
-  else if (per == 1)
-    scatter_instances_kernel<1><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths,
-                                                                        grid.x, g.ctr_stride, g.tile_ctr, b.pairs);
-  else
-    scatter_instances_kernel<2><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths,
-                                                                        grid.x, g.ctr_stride, g.tile_ctr, b.pairs);
+  // (one, two or four instances per lane measure the same 63 us at config 2: the kernel runs at the rate the L2
+  // serves 5.4 M atomics with return plus as many scattered 8-byte stores)
+  scatter_instances_kernel<2><<<(in.P + 255) / 256, 256, 0, stream>>>(in.P, g.tiles_touched, g.rects, g.depths, grid.x,
+                                                                      g.ctr_stride, g.tile_ctr, b.pairs);
   HG_POST_LAUNCH(debug, stream, "scatter_instances");
   uint32_t slot_bits = 1;
   while (slot_bits < 32 && ((uint32_t)(in.P - 1) >> slot_bits)) ++slot_bits;

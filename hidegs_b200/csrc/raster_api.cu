@@ -93,9 +93,9 @@ static void fill_layout(int32_t P, int32_t W, int32_t H, int64_t R, hg_raster_la
   L->clamped = take(p);
   L->records = take(p * HG_REC_FLOATS * 4);
   L->tiles = tiles;
-  // one 128-byte line per tile: the REDs / atomics of neighbouring tiles do not serialise in one L2 line
-  static const size_t stride = [] { const char* v = getenv("HG_CTR_STRIDE"); return (size_t)(v && *v ? atoi(v) : 32); }();
-  L->ctr_stride = stride < 2 ? 2 : stride;
+  // (count, cursor) interleaved.  Measured and dropped: one 128-byte line per tile — the REDs / atomics do not run
+  // faster, and zero-filling and scanning 1 MB instead of 64 KB cost 15 us.
+  L->ctr_stride = 2;
   L->tile_ctr = take(tiles * L->ctr_stride * 4);
   L->tile_lists = take(tiles * 12);
   L->bin_header = take(64);
