@@ -28,6 +28,8 @@
 #include "common.cuh"
 #include "tile_instances.cuh"
 
+#include <mutex>
+
 namespace hg {
 
 namespace {
@@ -687,17 +689,25 @@ size_t binning_scratch_bytes(uint32_t beyond_pairs) { return beyond_pairs ? 16 *
 
 int launch_binning(const hg_raster_inputs& in, const GeomState& g, const BinState& b, int T, dim3 grid,
                    const uint32_t* header_host, cudaStream_t stream) {
+  static std::mutex attr_mu;
   static bool attr_done[64] = {};
   int dev = 0;
   HG_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sort_smem_bytes(kSortWarpsA, kCapM)));
-    HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_beyond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(kSortWarpsC * 32 * 32 * 4)));
-    HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sort_smem_bytes(kSortWarpsB, kCapL)));
-    attr_done[dev] = true;
+  if (dev < 0 || dev >= 64) {
+    set_error("binning: device index %d out of range", dev);
+    return HG_ERR_CUDA;
+  }
+  {  // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (!attr_done[dev]) {
+      HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sort_smem_bytes(kSortWarpsA, kCapM)));
+      HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_beyond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kSortWarpsC * 32 * 32 * 4)));
+      HG_CUDA_TRY(cudaFuncSetAttribute(tile_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sort_smem_bytes(kSortWarpsB, kCapL)));
+      attr_done[dev] = true;
+    }
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

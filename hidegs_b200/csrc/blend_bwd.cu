@@ -18,6 +18,7 @@
 #include "blend_common.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace hg {
 
@@ -523,15 +524,19 @@ constexpr int kWarpsC = kThreadsB / 32;
 constexpr int kRecQuadsC = 4;             // staged entry of variant C: 64 B (x y a b | c o am4 id | r g b 1/z | am0..3)
 constexpr int kAStride = 68;              // floats per A row: 64 pixels + 4 pad (conflict-free ldmatrix rows, STS.64)
 
+template <bool INTERP>
 struct alignas(16) BwdMmaSmem {
   float4 rec[kWarpsC][32 * kRecQuadsC];   // per-WARP staging of the 32 entries a round looks at (see the main loop)
-  float a_w[kWarpsC][kGroupC * kAStride]; // wgt, row-major [entry][k]; k = 2 lane + {0: pixel A, 1: pixel B}
+  alignas(16) float a_w[kWarpsC][kGroupC * kAStride]; // wgt, row-major [entry][k]; k = 2 lane + {0: pixel A, 1: pixel B}
   float a_p[kWarpsC][kGroupC * kAStride]; // p, same layout
   float2 b_ch0[kWarpsC][8][32];           // channels 0..7 of the warp's pixels, fragment order: (b0, b1) per lane
   float2 b_ch8[kWarpsC][8][4];            // channel 8 (column 0 of its n-tile: the lanes with g == 0)
   float2 zero2;                           // what the lanes with g != 0 read instead
   float2 b_mom[8][32];                    // the six moments, fragment order (same for every warp)
   float4 meta[kWarpsC][kGroupC][2];       // per row: (x, y, conic a, b), (conic c, opacity, -, slot id)
+  // hierarchy interpolation only (last, so that the layout above is the same in both variants):
+  float2 tf[INTERP ? kWarpsC : 1][INTERP ? 32 : 1];        // (t, 1 / kids) of the staged entries
+  float p3[INTERP ? kWarpsC : 1][INTERP ? kGroupC : 1];   // per-row sum of the third per-pair scalar
 };
 
 // A-operand quad (a0, a1, a2, a3) of mma.m16n8k8 for one k-step straight from a row-major fp32 tile: each of the four
@@ -573,17 +578,42 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // carries; the opacity gradient is sum p / opacity).  A pair that does not contribute is folded in as alpha = 0, which
 // leaves the recurrence untouched without any state select: T / (1 - 0) = T, and the next entry's
 // acc = 0 * g + 1 * acc_new re-derives the same accumulator.
-template <bool GEO, bool DEPTH>
+// With the hierarchy interpolation (INTERP; backward.cu:659-672, 757-765) the blended alpha is
+// t a + (1 - t) (1 - (1 - a)^(1/kids)) of a = min(0.99, opacity G); the geometric gradients keep the factor
+// opacity * G * dL/dalpha (the reference does not chain them through the interpolation), and the opacity gradient needs
+// a THIRD per-pair scalar p3 = opac_mult(a) * p, returned through `p3` and summed over the warp's pixels outside.
+// ACC selects how (1 - a)^(1/kids) is evaluated: false = ex2(y lg2 x) as the FORWARD does (forward.cu:550 uses __powf),
+// true = the accurate pow of the reference's backward (~35 instructions each, twice per pair).  The fast evaluation
+// reports through `near` when the interpolated alpha lies within 2e-6 of the 1/255 cut — ten times its error — so that
+// the caller can redo the rare pair whose classification could differ from the reference's.
+template <bool GEO, bool DEPTH, bool INTERP, bool ACC>
 __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4 ea, const float4 eb, const float4 ec,
-                                             const float4 ed, float pixx, float pixy, int q, float& wgt, float& p) {
+                                             const float4 ed, const float2 tf, float pixx, float pixy, int q,
+                                             float& wgt, float& p, float& p3, bool& near) {
   const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
   const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
   const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
   // expf, not a bare ex2.approx: the pair must be classified (alpha >= 1/255, clamp at 0.99) exactly as the forward
   // classified it.  (Measured: the one-MUFU variant is 3 % faster and flips one borderline pair in 3 M gradients.)
   const float test_alpha = __fmul_rn(eb.y, expf(power));
-  const bool valid = (q < s.last_contributor) && !(power > 0.0f) && !(test_alpha < 1.0f / 255.0f);
-  const float alpha = valid ? fminf(0.99f, test_alpha) : 0.f;
+  float blend_alpha = fminf(0.99f, test_alpha);
+  float opac_mult = 1.0f;
+  if (INTERP) {
+    const float my_alpha = blend_alpha;
+    if (ACC) {
+      const float kidsqrt = 1.0f - powf(1.0f - my_alpha, tf.y);
+      blend_alpha = tf.x * my_alpha + (1.0f - tf.x) * kidsqrt;
+      opac_mult = tf.x - powf(1.0f - my_alpha, tf.y - 1.0f) * (tf.x - 1.0f) * tf.y;
+    } else {
+      const float lg = __log2f(1.0f - my_alpha);  // both powers from one logarithm
+      const float kidsqrt = 1.0f - exp2f(tf.y * lg);
+      blend_alpha = tf.x * my_alpha + (1.0f - tf.x) * kidsqrt;
+      opac_mult = tf.x - exp2f((tf.y - 1.0f) * lg) * (tf.x - 1.0f) * tf.y;
+      near = near || fabsf(blend_alpha - 1.0f / 255.0f) < 2e-6f;
+    }
+  }
+  const bool valid = (q < s.last_contributor) && !(power > 0.0f) && !(blend_alpha < 1.0f / 255.0f);
+  const float alpha = valid ? blend_alpha : 0.f;
   float rinv;  // 1 - alpha is in [0.01, 1]: the bare MUFU.RCP, without __fdividef's denormal-range scaling (same bits)
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(1.0f - alpha));
   const float Tn = s.T * rinv;
@@ -600,21 +630,24 @@ __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4 ea, con
   s.acc_g = acc_new;
   s.last_g = g;
   s.last_alpha = alpha;
-  p = test_alpha > 0.99f ? 0.f : alpha * dL_dalpha;  // the clamp has no gradient (backward.cu:680-682)
+  // the clamp has no gradient (backward.cu:680-682).  Without interpolation alpha == opacity * G here.
+  p = test_alpha > 0.99f ? 0.f : (INTERP ? (valid ? test_alpha : 0.f) : alpha) * dL_dalpha;
+  p3 = INTERP ? opac_mult * p : 0.f;
   return valid;
 }
 
-template <bool GEO, bool DEPTH>
-__global__ void __launch_bounds__(kThreadsB, 4)
+template <bool GEO, bool DEPTH, bool INTERP>
+__global__ void __launch_bounds__(kThreadsB, INTERP ? 3 : 4)
 blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                  const float4* __restrict__ records, const int W, const int H, const float fx, const float fy,
+                  const float4* __restrict__ records, const float* __restrict__ ts, const int* __restrict__ kids,
+                  const int W, const int H, const float fx, const float fy,
                   const float* __restrict__ bg_color, const float* __restrict__ all_map_pixels,
                   const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
                   const float* __restrict__ dL_dpixels, const float* __restrict__ dL_dout_all_maps,
                   const float* __restrict__ dL_dout_plane_depths, const float* __restrict__ dL_invdepths,
                   float* __restrict__ accum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  BwdMmaSmem& sm = *reinterpret_cast<BwdMmaSmem*>(smem_raw);
+  BwdMmaSmem<INTERP>& sm = *reinterpret_cast<BwdMmaSmem<INTERP>*>(smem_raw);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -774,7 +807,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
           const float g10 = -ddely_dy * (m1.x * Dy + m0.w * Dx);
           red_add_v4(arow + 8, dc8[2 * h], g9, g10, -0.5f * Qxx);
           red_add_v2(arow + 12, -0.5f * Qxy, -0.5f * Qyy);
-          atomicAdd(arow + 14, __fdividef(S1, o));
+          atomicAdd(arow + 14, __fdividef(INTERP ? sm.p3[warp][row] : S1, o));
         }
       }
     }
@@ -792,7 +825,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   Prefetch pf;
   auto prefetch = [&](int base) {
     const int q = base - lane;
-    if (q >= 0) gather_record<false>(pf, point_list, records, nullptr, nullptr, range.x + q);
+    if (q >= 0) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + q);
   };
   if (wmax > 0) prefetch(wmax - 1);
 
@@ -801,7 +834,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     bool keepA = false, keepB = false;
     if (q_mine >= 0) {
       const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
-      const float tau = cull_tau(a, bb, c, o, false);
+      const float tau = cull_tau(a, bb, c, o, INTERP);
       keepA = q_mine < wmaxA && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyA0, fyA1);
       keepB = q_mine < wmaxB && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyB0, fyB1);
       if (keepA || keepB) {
@@ -810,6 +843,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         d[1] = make_float4(c, o, pf.r3.z, __int_as_float(pf.id));
         d[2] = make_float4(pf.r1.z, pf.r1.w, pf.r2.x, pf.r2.y);
         if (GEO) d[3] = make_float4(pf.r2.z, pf.r2.w, pf.r3.x, pf.r3.y);
+        if (INTERP) sm.tf[warp][lane] = make_float2(pf.it, pf.ifrac);
       }
     }
     const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
@@ -828,18 +862,39 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       const float4 eb = e[1];
       const float4 ec = e[2];      float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
       if (GEO) ed = e[3];
-      float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f;
-      bool any;
+      float2 tf = make_float2(1.f, 1.f);
+      if (INTERP) tf = sm.tf[warp][bit];
+      float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f, p3A = 0.f, p3B = 0.f;
+      bool any, near = false;
       const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
+      // state before this entry (only read again on the rare redo below)
+      const float A_T = A.T, A_acc = A.acc_g, A_lg = A.last_g, A_la = A.last_alpha;
+      const float B_T = B.T, B_acc = B.acc_g, B_lg = B.last_g, B_la = B.last_alpha;
       if (hasA && hasB) {  // one basic block: the two pixels' dependency chains interleave
-        any = pixel_pair_c<GEO, DEPTH>(A, ea, eb, ec, ed, pixx, pixyA, q, wA, pA);
-        any |= pixel_pair_c<GEO, DEPTH>(B, ea, eb, ec, ed, pixx, pixyB, q, wB, pB);
+        any = pixel_pair_c<GEO, DEPTH, INTERP, false>(A, ea, eb, ec, ed, tf, pixx, pixyA, q, wA, pA, p3A, near);
+        any |= pixel_pair_c<GEO, DEPTH, INTERP, false>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
       } else if (hasA) {
-        any = pixel_pair_c<GEO, DEPTH>(A, ea, eb, ec, ed, pixx, pixyA, q, wA, pA);
+        any = pixel_pair_c<GEO, DEPTH, INTERP, false>(A, ea, eb, ec, ed, tf, pixx, pixyA, q, wA, pA, p3A, near);
       } else {
-        any = pixel_pair_c<GEO, DEPTH>(B, ea, eb, ec, ed, pixx, pixyB, q, wB, pB);
+        any = pixel_pair_c<GEO, DEPTH, INTERP, false>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
+      }
+      if (INTERP && __any_sync(0xffffffffu, near)) {
+        // a pair within the error of the fast pow of the 1/255 cut: evaluate this entry again, for the whole warp, the
+        // way the reference's backward does
+        A.T = A_T; A.acc_g = A_acc; A.last_g = A_lg; A.last_alpha = A_la;
+        B.T = B_T; B.acc_g = B_acc; B.last_g = B_lg; B.last_alpha = B_la;
+        wA = pA = wB = pB = p3A = p3B = 0.f;
+        any = false;
+        if (hasA) any = pixel_pair_c<GEO, DEPTH, INTERP, true>(A, ea, eb, ec, ed, tf, pixx, pixyA, q, wA, pA, p3A, near);
+        if (hasB) any |= pixel_pair_c<GEO, DEPTH, INTERP, true>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
       }
       if (__ballot_sync(0xffffffffu, any) == 0) continue;
+      if (INTERP) {  // the third scalar only needs its plain sum over the 64 pixels: one butterfly, no third A tile
+        float s3 = p3A + p3B;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        if (lane == 0) sm.p3[warp][rows] = s3;
+      }
       *reinterpret_cast<float2*>(a_w + rows * kAStride + 2 * lane) = make_float2(wA, wB);
       *reinterpret_cast<float2*>(a_p + rows * kAStride + 2 * lane) = make_float2(pA, pB);
       if (lane == 0) {
@@ -867,38 +922,59 @@ int launch_blend_bwd(const hg_raster_inputs& in, const GeomState& g, const BinSt
     const char* e = getenv("HG_BLEND_BWD_VARIANT");
     return e ? atoi(e) : 3;
   }();
-  if (variant == 3 && !interp) {
+  if (variant == 3) {
     // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute: set once per device
-    static bool attr_set[64] = {};
+    static std::mutex attr_mu;
+    static bool attr_done[64] = {}, attr_ok[64] = {};
     int device = 0;
     HG_CUDA_TRY(cudaGetDevice(&device));
-    bool attr_ok = device >= 0 && device < 64 && attr_set[device];
-    if (!attr_ok) {
-      const int bytes = (int)sizeof(BwdMmaSmem);
-      attr_ok = true;
-      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      attr_ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
-      if (attr_ok && device >= 0 && device < 64) attr_set[device] = true;
-    }
-    if (!attr_ok) {
-      set_error("blend_bwd: could not reserve %zu bytes of shared memory", sizeof(BwdMmaSmem));
+    if (device < 0 || device >= 64) {
+      set_error("blend_bwd: device index %d out of range", device);
       return HG_ERR_CUDA;
     }
-#define HG_LAUNCH3(G_, D_)                                                                          \
-  blend_bwd3_kernel<G_, D_><<<grid, kThreadsB, sizeof(BwdMmaSmem), stream>>>(                       \
-      img.ranges, b.vals, g.records, in.W, in.H, focal_x, focal_y, in.background, all_map_pixels,   \
-      img.final_T, img.n_contrib, dL_dpix, dL_dout_all_map, dL_dout_plane_depth, dL_dout_invdepth, accum)
-    if (geo && depth) HG_LAUNCH3(true, true);
-    else if (geo) HG_LAUNCH3(true, false);
-    else if (depth) HG_LAUNCH3(false, true);
-    else HG_LAUNCH3(false, false);
+    {
+      std::lock_guard<std::mutex> lk(attr_mu);
+      if (!attr_done[device]) {
+        bool ok = true;
+        const int b0 = (int)sizeof(BwdMmaSmem<false>), b1 = (int)sizeof(BwdMmaSmem<true>);
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, true, false>, attr, b0) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, false, false>, attr, b0) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, true, false>, attr, b0) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, false, false>, attr, b0) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, true, true>, attr, b1) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<true, false, true>, attr, b1) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, true, true>, attr, b1) == cudaSuccess;
+        ok &= cudaFuncSetAttribute(blend_bwd3_kernel<false, false, true>, attr, b1) == cudaSuccess;
+        attr_ok[device] = ok;
+        attr_done[device] = true;
+      }
+    }
+    if (!attr_ok[device]) {
+      set_error("blend_bwd: could not reserve %zu bytes of shared memory", sizeof(BwdMmaSmem<true>));
+      return HG_ERR_CUDA;
+    }
+#define HG_LAUNCH3(G_, D_, I_)                                                                            \
+  blend_bwd3_kernel<G_, D_, I_><<<grid, kThreadsB, sizeof(BwdMmaSmem<I_>), stream>>>(                     \
+      img.ranges, b.vals, g.records, in.ts, in.kids, in.W, in.H, focal_x, focal_y, in.background,         \
+      all_map_pixels, img.final_T, img.n_contrib, dL_dpix, dL_dout_all_map, dL_dout_plane_depth,          \
+      dL_dout_invdepth, accum)
+    if (interp) {
+      if (geo && depth) HG_LAUNCH3(true, true, true);
+      else if (geo) HG_LAUNCH3(true, false, true);
+      else if (depth) HG_LAUNCH3(false, true, true);
+      else HG_LAUNCH3(false, false, true);
+    } else {
+      if (geo && depth) HG_LAUNCH3(true, true, false);
+      else if (geo) HG_LAUNCH3(true, false, false);
+      else if (depth) HG_LAUNCH3(false, true, false);
+      else HG_LAUNCH3(false, false, false);
+    }
 #undef HG_LAUNCH3
     HG_POST_LAUNCH(in.debug, stream, "blend_bwd");
     return HG_OK;
   }
-  if (variant == 2 || variant == 3) {
+  if (variant == 2) {
 #define HG_LAUNCH2(G_, D_, I_)                                                                \
   blend_bwd2_kernel<G_, D_, I_><<<grid, kThreadsB, 0, stream>>>(                              \
       img.ranges, b.vals, g.records, in.ts, in.kids, in.W, in.H, focal_x, focal_y,            \
