@@ -3,18 +3,17 @@
 // Replaces renderCUDA<3,5> backward of the reference
 // (cuda_rasterizer/backward.cu:499-772, launched at :883).
 //
-// Three generations live in this file (HG_BLEND_BWD_VARIANT selects; the default is the newest that applies):
-//  A  blend_bwd_kernel   256-thread CTA per 16x16 tile, warp = 8x4 sub-tile, one pixel per lane.
-//  B  blend_bwd2_kernel  128-thread CTA, warp = 8x8 sub-tile, two pixels per lane, ONE shuffle butterfly + ONE RED
-//                        per (warp, entry).  Still the kernel of the hierarchy-interpolation path.
-//  C  blend_bwd3_kernel  as B, but the cross-pixel reduction runs on the tensor cores (3xTF32 mma.sync against
-//                        per-pixel constant tiles), the staging is per warp and barrier free.  Default.
-// Common to all: register-double-buffered gathers of the 64-byte splat records, lane-parallel exact sub-tile
-// culling, traversal from the LAST contributor backwards, and one shared recurrence for the nine blended channels
-// (rgb, inverse depth, 5 geometry channels): dL/dalpha only needs sum_ch (c_ch - accum_ch) * dL/dch, so each pixel
-// carries ONE scalar accumulator of g = <features, dL/dpixel> instead of nine.  The reference issues 15 same-address
-// float atomics per (pixel, Gaussian) pair; here one accumulator row per Gaussian receives one (B) or a few vector
-// (C) REDs per (warp, entry).
+// One kernel, blend_bwd3_kernel: 128-thread CTA per 16x16 tile, a warp per 8x8 sub-tile, two pixels per lane; every
+// warp walks the tile's list on its own (no CTA barrier in the loop) back to front from ITS last contributor, with
+// register-double-buffered gathers of the 64-byte splat records and a lane-parallel exact sub-tile cull.  The nine
+// blended channels (rgb, inverse depth, 5 geometry channels) share ONE scalar recurrence: dL/dalpha only needs
+// sum_ch (c_ch - accum_ch) * dL/dch, so each pixel carries one accumulator of g = <features, dL/dpixel> instead of
+// nine.  The reduction of the per-pair gradients over the warp's 64 pixels runs on the tensor cores (3xTF32 mma.sync
+// against per-pixel constant tiles, see below).  The reference issues 15 same-address float atomics per (pixel,
+// Gaussian) pair; here one 64-byte accumulator row per Gaussian receives a few vector REDs per (warp, 16 entries).
+// (Rounds 1-2 also carried a one-pixel-per-lane kernel and a two-pixel kernel with a 16-value shuffle butterfly per
+// entry, 1.6 and 1.34 ms at config 2 against 1.09 ms; both were removed once this kernel covered the hierarchy
+// interpolation as well.)
 #include "blend_common.cuh"
 
 #include <cstdlib>
@@ -24,244 +23,9 @@ namespace hg {
 
 namespace {
 
-// Sum v[0..15] over the 32 lanes.  On return lane L holds in v[0] the total of
-// component comp(L) = 8*b4 + 4*b3 + 2*b2 + b1 (b_i = bit i of L); lanes with
-// bit 0 clear are the owners.
-__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float send = hi ? v[i] : v[i + 8];
-      const float keep = hi ? v[i + 8] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = hi ? v[i] : v[i + 4];
-      const float keep = hi ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = hi ? v[i] : v[i + 2];
-      const float keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool hi = lane & 2;
-    const float send = hi ? v[0] : v[1];
-    const float keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-template <bool GEO, bool DEPTH, bool INTERP>
-__global__ void __launch_bounds__(HG_BLOCK_SIZE)
-blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                 const float4* __restrict__ records, const float* __restrict__ ts,
-                 const int* __restrict__ kids, const int W, const int H, const float fx,
-                 const float fy, const float* __restrict__ bg_color,
-                 const float* __restrict__ all_map_pixels, const float* __restrict__ final_Ts,
-                 const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-                 const float* __restrict__ dL_dout_all_maps,
-                 const float* __restrict__ dL_dout_plane_depths,
-                 const float* __restrict__ dL_invdepths, float* __restrict__ accum) {
-  __shared__ float4 s_rec[kBatch * kRecQuads];
-  __shared__ int s_max[HG_BLOCK_SIZE / 32];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
-  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 4;
-  const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
-  const bool inside = pxi < W && pyi < H;
-  const float pixx = (float)pxi, pixy = (float)pyi;
-  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7), fy0 = (float)wy0, fy1 = (float)(wy0 + 3);
-  const size_t HW = (size_t)H * W;
-  const size_t pix = (size_t)pyi * W + pxi;
-
-  const uint2 range = ranges[tile];
-  const int n = (int)(range.y - range.x);
-
-  const float T_final = inside ? final_Ts[pix] : 0.f;
-  const int last_contributor = inside ? min((int)n_contrib[pix], n) : 0;
-
-  // Per-pixel upstream gradients w[0..2]=rgb, w[3]=invdepth, w[4..8]=all_map.
-  float w[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) w[i] = 0.f;
-  float bg_dot = 0.f;
-  if (inside) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      w[c] = dL_dpixels[c * HW + pix];
-      bg_dot += __ldg(bg_color + c) * w[c];
-    }
-    if (DEPTH) w[3] = dL_invdepths[pix];
-    if (GEO) {
-#pragma unroll
-      for (int c = 0; c < 5; ++c) w[4 + c] = dL_dout_all_maps[c * HW + pix];
-      // Fold dL/dplane_depth into the geometry channels (backward.cu:583-592).
-      const float rayx = (float)(((double)pixx - W * 0.5) / (double)fx);
-      const float rayy = (float)(((double)pixy - H * 0.5) / (double)fy);
-      const float nx = all_map_pixels[pix], ny = all_map_pixels[HW + pix],
-                  nz = all_map_pixels[2 * HW + pix];
-      const float dist = all_map_pixels[4 * HW + pix];
-      const float tmp = (float)((double)(nx * rayx + ny * rayy + nz) + 1.0e-8);
-      const float dpd = dL_dout_plane_depths[pix];
-      w[8] += (-dpd / tmp);
-      w[4] += dpd * (dist / (tmp * tmp) * rayx);
-      w[5] += dpd * (dist / (tmp * tmp) * rayy);
-      w[6] += dpd * (dist / (tmp * tmp));
-    }
-  }
-  const float bgT = -T_final * bg_dot;  // background term of dL/dalpha, times 1/(1-alpha) per entry
-
-  // Tile-wide last contributor: nothing behind it received any weight.
-  int wmax = last_contributor;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  if (lane == 0) s_max[warp] = wmax;
-  __syncthreads();
-  int n_eff = 0;
-#pragma unroll
-  for (int i = 0; i < HG_BLOCK_SIZE / 32; ++i) n_eff = max(n_eff, s_max[i]);
-  const int nb = (n_eff + kBatch - 1) / kBatch;
-
-  float T = T_final;
-  float acc_g = 0.f, last_g = 0.f, last_alpha = 0.f;
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-
-  Prefetch pf;
-  auto prefetch = [&](int b) {
-    const int q = n_eff - 1 - (b * kBatch + tid);  // position in the tile's list
-    if (q >= 0) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + q);
-  };
-  if (nb > 0) prefetch(0);
-
-  for (int b = 0; b < nb; ++b) {
-    __syncthreads();
-    const int cnt = min(kBatch, n_eff - b * kBatch);
-    if (tid < cnt) stage_record<GEO, INTERP>(s_rec, tid, pf);
-    __syncthreads();
-    if (b + 1 < nb) prefetch(b + 1);
-
-    // Position of slot k of this batch: q = n_eff - 1 - (b*kBatch + k).
-    const int q_first = n_eff - 1 - b * kBatch;
-    if (q_first - (cnt - 1) >= wmax) continue;  // the whole batch lies behind this warp
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-      if (q_first - (c0 + 31) >= wmax) continue;
-      const int j = c0 + lane;
-      bool keep = false;
-      if (j < cnt && q_first - j < wmax) {
-        const float4 ea = s_rec[kRecQuads * j];
-        const float4 eb = s_rec[kRecQuads * j + 1];
-        keep = may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fy0, fy1);
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, keep);
-      while (mask) {
-        const int k = c0 + __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float4* e = s_rec + kRecQuads * k;
-        const float4 ea = e[0];
-        const float4 eb = e[1];
-        // Straight-line, select-predicated evaluation: a lane that does not contribute carries zeros into the
-        // warp reduction instead of branching around the arithmetic (the warp issues it anyway).
-        const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
-        const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
-        const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
-        bool valid = (q_first - k < last_contributor) && !(power > 0.0f);
-        const float Graw = expf(power);
-        const float test_alpha = __fmul_rn(eb.y, Graw);
-        const float my_alpha = fminf(0.99f, test_alpha);
-        float alpha = my_alpha;
-        float opac_mult = 1.0f;
-        if (INTERP) {
-          const float4 e4 = e[4];
-          const float kidsqrt = 1.0f - powf(1.0f - my_alpha, e4.z);
-          alpha = e4.y * my_alpha + (1.0f - e4.y) * kidsqrt;
-          opac_mult = e4.y - powf(1.0f - my_alpha, e4.z - 1.0f) * (e4.y - 1.0f) * e4.z;
-        }
-        valid = valid && !(alpha < 1.0f / 255.0f);
-        if (__ballot_sync(0xffffffffu, valid) == 0) continue;
-        const float G = valid ? Graw : 0.f;  // also keeps inf / NaN of skipped lanes out of the products below
-        const float rinv = __fdividef(1.0f, 1.0f - alpha);
-        const float Tn = T * rinv;
-        const float weight = valid ? alpha * Tn : 0.f;
-        const float4 ec = e[2];
-        float g = ec.x * w[0] + ec.y * w[1] + ec.z * w[2];
-        float v[16];
-        v[0] = weight * w[0];
-        v[1] = weight * w[1];
-        v[2] = weight * w[2];
-        v[3] = 0.f;
-        if (DEPTH) {
-          g += ec.w * w[3];
-          v[3] = weight * w[3];
-        }
-#pragma unroll
-        for (int i = 4; i < 9; ++i) v[i] = 0.f;
-        if (GEO) {
-          const float4 ed = e[3];
-          const float ee = e[4].x;
-          g += ed.x * w[4] + ed.y * w[5] + ed.z * w[6] + ed.w * w[7] + ee * w[8];
-          v[4] = weight * w[4];
-          v[5] = weight * w[5];
-          v[6] = weight * w[6];
-          v[7] = weight * w[7];
-          v[8] = weight * w[8];
-        }
-        const float acc_new = last_alpha * last_g + (1.0f - last_alpha) * acc_g;
-        float dL_dalpha = (g - acc_new) * Tn + bgT * rinv;
-        if (test_alpha > 0.99f || !valid) dL_dalpha = 0.f;
-        T = valid ? Tn : T;
-        acc_g = valid ? acc_new : acc_g;
-        last_g = valid ? g : last_g;
-        last_alpha = valid ? alpha : last_alpha;
-        const float dL_dG = eb.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * ea.z - gdy * ea.w;
-        const float dG_ddely = -gdy * eb.x - gdx * ea.w;
-        v[9] = dL_dG * dG_ddelx * ddelx_dx;
-        v[10] = dL_dG * dG_ddely * ddely_dy;
-        const float hG = -0.5f * dL_dG;
-        v[11] = hG * gdx * dx;
-        v[12] = hG * gdx * dy;
-        v[13] = hG * gdy * dy;
-        v[14] = opac_mult * G * dL_dalpha;
-        v[15] = 0.f;
-        warp_reduce16(v, lane);
-        if ((lane & 1) == 0) {
-          const int comp = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                           ((lane >> 1) & 1);
-          if (comp < 15) atomicAdd(accum + (size_t)__float_as_int(eb.w) * HG_ACC_FLOATS + comp, v[0]);
-        }
-      }
-    }
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------------
-// Variant B: warp per 8x8 sub-tile, TWO pixels per lane (rows r and r+4), 128-thread CTA per tile.  The per-pixel math
-// is unchanged; the 15 partials of both pixels are summed in registers before ONE butterfly and ONE RED per (warp,
-// entry), which amortises the reduction (~45 % of the issued instructions of variant A) over up to 64 pixels.  Each
-// half of the sub-tile has its own exact cull test, so a half that an entry cannot reach costs nothing.
-#ifndef HG_BWD2_MINB
-#define HG_BWD2_MINB 4
-#endif
+// Two pixels per lane (rows r and r + 4 of the warp's 8x8 sub-tile), 128-thread CTA per 16x16 tile.
 constexpr int kThreadsB = 128;
-constexpr int kBatchB = kThreadsB;
+
 
 struct PixelState {
   float w[9];
@@ -313,195 +77,8 @@ __device__ __forceinline__ void load_pixel_state(PixelState& s, bool inside, siz
   s.acc_g = s.last_g = s.last_alpha = 0.f;
 }
 
-// One (pixel, entry) pair: select-predicated, accumulates its 15 partials into v.  Returns whether it contributed.
-#define MUL2(a, b) ((a) * (b))
-template <bool GEO, bool DEPTH, bool INTERP, bool FIRST>
-__device__ __forceinline__ bool pixel_pair(PixelState& s, const float4* __restrict__ e, const float4 ea, const float4 eb,
-                                           float pixx, float pixy, int q, float ddelx_dx, float ddely_dy,
-                                           float (&v)[16]) {
-  const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
-  const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
-  const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
-  bool valid = (q < s.last_contributor) && !(power > 0.0f);
-  const float Graw = expf(power);
-  const float test_alpha = __fmul_rn(eb.y, Graw);
-  const float my_alpha = fminf(0.99f, test_alpha);
-  float alpha = my_alpha;
-  float opac_mult = 1.0f;
-  if (INTERP) {
-    const float4 e4 = e[4];
-    const float kidsqrt = 1.0f - powf(1.0f - my_alpha, e4.z);
-    alpha = e4.y * my_alpha + (1.0f - e4.y) * kidsqrt;
-    opac_mult = e4.y - powf(1.0f - my_alpha, e4.z - 1.0f) * (e4.y - 1.0f) * e4.z;
-  }
-  valid = valid && !(alpha < 1.0f / 255.0f);
-  const float G = valid ? Graw : 0.f;
-  const float rinv = __fdividef(1.0f, 1.0f - alpha);
-  const float Tn = s.T * rinv;
-  const float weight = valid ? alpha * Tn : 0.f;
-  if (FIRST) {
-    if (!DEPTH) v[3] = 0.f;
-    if (!GEO) v[4] = v[5] = v[6] = v[7] = v[8] = 0.f;
-    v[15] = 0.f;
-  }
-  const float4 ec = e[2];
-  float g = ec.x * s.w[0] + ec.y * s.w[1] + ec.z * s.w[2];
-  v[0] = FIRST ? (MUL2(weight, s.w[0])) : __fmaf_rn(weight, s.w[0], v[0]);
-  v[1] = FIRST ? (MUL2(weight, s.w[1])) : __fmaf_rn(weight, s.w[1], v[1]);
-  v[2] = FIRST ? (MUL2(weight, s.w[2])) : __fmaf_rn(weight, s.w[2], v[2]);
-  if (DEPTH) {
-    g += ec.w * s.w[3];
-    v[3] = FIRST ? (MUL2(weight, s.w[3])) : __fmaf_rn(weight, s.w[3], v[3]);
-  }
-  if (GEO) {
-    const float4 ed = e[3];
-    const float ee = e[4].x;
-    g += ed.x * s.w[4] + ed.y * s.w[5] + ed.z * s.w[6] + ed.w * s.w[7] + ee * s.w[8];
-    v[4] = FIRST ? (MUL2(weight, s.w[4])) : __fmaf_rn(weight, s.w[4], v[4]);
-    v[5] = FIRST ? (MUL2(weight, s.w[5])) : __fmaf_rn(weight, s.w[5], v[5]);
-    v[6] = FIRST ? (MUL2(weight, s.w[6])) : __fmaf_rn(weight, s.w[6], v[6]);
-    v[7] = FIRST ? (MUL2(weight, s.w[7])) : __fmaf_rn(weight, s.w[7], v[7]);
-    v[8] = FIRST ? (MUL2(weight, s.w[8])) : __fmaf_rn(weight, s.w[8], v[8]);
-  }
-  const float acc_new = s.last_alpha * s.last_g + (1.0f - s.last_alpha) * s.acc_g;
-  float dL_dalpha = (g - acc_new) * Tn + s.bgT * rinv;
-  if (test_alpha > 0.99f || !valid) dL_dalpha = 0.f;
-  s.T = valid ? Tn : s.T;
-  s.acc_g = valid ? acc_new : s.acc_g;
-  s.last_g = valid ? g : s.last_g;
-  s.last_alpha = valid ? alpha : s.last_alpha;
-  const float dL_dG = eb.y * dL_dalpha;
-  const float gdx = G * dx, gdy = G * dy;
-  const float dG_ddelx = -gdx * ea.z - gdy * ea.w;
-  const float dG_ddely = -gdy * eb.x - gdx * ea.w;
-  v[9] = FIRST ? (MUL2(dL_dG * dG_ddelx, ddelx_dx)) : __fmaf_rn(dL_dG * dG_ddelx, ddelx_dx, v[9]);
-  v[10] = FIRST ? (MUL2(dL_dG * dG_ddely, ddely_dy)) : __fmaf_rn(dL_dG * dG_ddely, ddely_dy, v[10]);
-  const float hG = -0.5f * dL_dG;
-  v[11] = FIRST ? (MUL2(hG * gdx, dx)) : __fmaf_rn(hG * gdx, dx, v[11]);
-  v[12] = FIRST ? (MUL2(hG * gdx, dy)) : __fmaf_rn(hG * gdx, dy, v[12]);
-  v[13] = FIRST ? (MUL2(hG * gdy, dy)) : __fmaf_rn(hG * gdy, dy, v[13]);
-  v[14] = FIRST ? (MUL2(opac_mult * G, dL_dalpha)) : __fmaf_rn(opac_mult * G, dL_dalpha, v[14]);
-  return valid;
-}
-
-#undef MUL2
-
-template <bool GEO, bool DEPTH, bool INTERP>
-__global__ void __launch_bounds__(kThreadsB, HG_BWD2_MINB)
-blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                  const float4* __restrict__ records, const float* __restrict__ ts,
-                  const int* __restrict__ kids, const int W, const int H, const float fx,
-                  const float fy, const float* __restrict__ bg_color,
-                  const float* __restrict__ all_map_pixels, const float* __restrict__ final_Ts,
-                  const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpixels,
-                  const float* __restrict__ dL_dout_all_maps,
-                  const float* __restrict__ dL_dout_plane_depths,
-                  const float* __restrict__ dL_invdepths, float* __restrict__ accum) {
-  __shared__ float4 s_rec[kBatchB * kRecQuads];
-  __shared__ int s_max[kThreadsB / 32];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
-  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 8;
-  const int pxi = wx0 + (lane & 7), pyA = wy0 + (lane >> 3), pyB = pyA + 4;
-  const bool insideA = pxi < W && pyA < H, insideB = pxi < W && pyB < H;
-  const float pixx = (float)pxi, pixyA = (float)pyA, pixyB = (float)pyB;
-  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7);
-  const float fyA0 = (float)wy0, fyA1 = (float)(wy0 + 3), fyB0 = (float)(wy0 + 4), fyB1 = (float)(wy0 + 7);
-  const size_t HW = (size_t)H * W;
-
-  const uint2 range = ranges[tile];
-  const int n = (int)(range.y - range.x);
-
-  PixelState A, B;
-  load_pixel_state<GEO, DEPTH>(A, insideA, (size_t)pyA * W + pxi, HW, W, H, pixx, pixyA, fx, fy, n, bg_color,
-                               all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
-                               dL_invdepths);
-  load_pixel_state<GEO, DEPTH>(B, insideB, (size_t)pyB * W + pxi, HW, W, H, pixx, pixyB, fx, fy, n, bg_color,
-                               all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
-                               dL_invdepths);
-
-  // last contributor of each half and of the tile
-  int wmaxA = A.last_contributor, wmaxB = B.last_contributor;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    wmaxA = max(wmaxA, __shfl_xor_sync(0xffffffffu, wmaxA, o));
-    wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
-  }
-  const int wmax = max(wmaxA, wmaxB);
-  if (lane == 0) s_max[warp] = wmax;
-  __syncthreads();
-  int n_eff = 0;
-#pragma unroll
-  for (int i = 0; i < kThreadsB / 32; ++i) n_eff = max(n_eff, s_max[i]);
-  const int nb = (n_eff + kBatchB - 1) / kBatchB;
-  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-  // lane -> component it owns after the butterfly (lanes with bit 0 clear; component 15 is padding)
-  const int comp = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-  const bool owner = (lane & 1) == 0 && comp < 15;
-  float* const acc_lane = accum + comp;
-
-  Prefetch pf;
-  auto prefetch = [&](int b) {
-    const int q = n_eff - 1 - (b * kBatchB + tid);
-    if (q >= 0) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + q);
-  };
-  if (nb > 0) prefetch(0);
-
-  for (int b = 0; b < nb; ++b) {
-    __syncthreads();
-    const int cnt = min(kBatchB, n_eff - b * kBatchB);
-    if (tid < cnt) stage_record<GEO, INTERP>(s_rec, tid, pf);
-    __syncthreads();
-    if (b + 1 < nb) prefetch(b + 1);
-
-    const int q_first = n_eff - 1 - b * kBatchB;
-    if (q_first - (cnt - 1) >= wmax) continue;  // the whole batch lies behind this warp
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-      if (q_first - (c0 + 31) >= wmax) continue;
-      const int j = c0 + lane;
-      bool keepA = false, keepB = false;
-      if (j < cnt) {
-        const float4 ea = s_rec[kRecQuads * j];
-        const float4 eb = s_rec[kRecQuads * j + 1];
-        const int q = q_first - j;
-        keepA = q < wmaxA && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyA0, fyA1);
-        keepB = q < wmaxB && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fyB0, fyB1);
-      }
-      const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
-      uint32_t mask = maskA | maskB;
-      while (mask) {
-        const int bit = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int k = c0 + bit;
-        const int q = q_first - k;
-        const float4* e = s_rec + kRecQuads * k;
-        const float4 ea = e[0];
-        const float4 eb = e[1];
-        float v[16];
-        bool any = false;
-        const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
-        if (hasA && hasB) {  // one basic block, so that the two pixels' dependency chains interleave
-          any = pixel_pair<GEO, DEPTH, INTERP, true>(A, e, ea, eb, pixx, pixyA, q, ddelx_dx, ddely_dy, v);
-          any |= pixel_pair<GEO, DEPTH, INTERP, false>(B, e, ea, eb, pixx, pixyB, q, ddelx_dx, ddely_dy, v);
-        } else if (hasA) {
-          any = pixel_pair<GEO, DEPTH, INTERP, true>(A, e, ea, eb, pixx, pixyA, q, ddelx_dx, ddely_dy, v);
-        } else {
-          any = pixel_pair<GEO, DEPTH, INTERP, true>(B, e, ea, eb, pixx, pixyB, q, ddelx_dx, ddely_dy, v);
-        }
-        if (__ballot_sync(0xffffffffu, any) == 0) continue;
-        warp_reduce16(v, lane);
-        if (owner) atomicAdd(acc_lane + (size_t)__float_as_int(eb.w) * HG_ACC_FLOATS, v[0]);
-      }
-    }
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
-// Variant C: the cross-pixel reduction as tensor-core matrix products.
+// The cross-pixel reduction as tensor-core matrix products.
 //
 // Every gradient a (pixel, entry) pair contributes is a per-pair scalar times a per-PIXEL constant:
 //   dL/d(rgb, 1/z, all_map)[entry] = sum_pix  wgt(pix, entry) * dL/dpixel[ch](pix)           wgt = alpha * T
@@ -514,14 +91,15 @@ blend_bwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 // upstream-gradient channels of the warp's pixels and the six moments.  FP32 accuracy is kept by splitting A and the
 // gradient channels into TF32 hi + lo parts (three products, the lo*lo term ~2^-22 is dropped); the moment tile is
 // exact in TF32 (|xi|, |eta| <= 3.5, products <= 12.25).  This takes the 16-value shuffle butterfly (74 issue slots) and
-// the 15 per-pixel partial products (~50) of variant B off the FP32 issue port: per (warp, entry) it costs one
+// the 15 per-pixel partial products (~50) of a shuffle-based reduction off the FP32 issue port: per (warp, entry) it costs one
 // STS.128 + ~15 slots of the amortised flush.  The moments are turned into the reference's gradients per entry by the
 // lane that owns the row, and the 16-float accumulator row receives vector REDs (red.global.add.v2/v4.f32).
-// The hierarchy interpolation (INTERP) keeps variant B (its opacity term needs a third per-pair scalar).
+// With the hierarchy interpolation (INTERP) the opacity gradient needs a third per-pair scalar; only its plain sum is
+// needed, so it takes one shuffle butterfly per (warp, entry) instead of a third A tile.
 constexpr int kGroupC = 16;               // entries per flush (the M of the MMA)
 constexpr int kWarpsC = kThreadsB / 32;
 
-constexpr int kRecQuadsC = 4;             // staged entry of variant C: 64 B (x y a b | c o am4 id | r g b 1/z | am0..3)
+constexpr int kRecQuadsC = 4;             // staged entry: 64 B (x y a b | c o am4 id | r g b 1/z | am0..3)
 constexpr int kAStride = 68;              // floats per A row: 64 pixels + 4 pad (conflict-free ldmatrix rows, STS.64)
 
 template <bool INTERP>
@@ -573,7 +151,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// One (pixel, entry) pair of variant C: the recurrence of pixel_pair, returning the two per-pair scalars
+// One (pixel, entry) pair: the recurrence, returning the two per-pair scalars
 // wgt = alpha * T_before and p = alpha * dL/dalpha (= opacity * G * dL/dalpha: the factor every geometric gradient
 // carries; the opacity gradient is sum p / opacity).  A pair that does not contribute is folded in as alpha = 0, which
 // leaves the recurrence untouched without any state select: T / (1 - 0) = T, and the next entry's
@@ -918,12 +496,7 @@ int launch_blend_bwd(const hg_raster_inputs& in, const GeomState& g, const BinSt
   const bool interp = in.ts != nullptr && in.kids != nullptr;
   const bool geo = in.render_geo != 0;
   const bool depth = dL_dout_invdepth != nullptr;
-  static const int variant = [] {
-    const char* e = getenv("HG_BLEND_BWD_VARIANT");
-    return e ? atoi(e) : 3;
-  }();
-  if (variant == 3) {
-    // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute: set once per device
+  // the opt-in for > 48 KB of dynamic shared memory is a per-device function attribute: set once per device
     static std::mutex attr_mu;
     static bool attr_done[64] = {}, attr_ok[64] = {};
     int device = 0;
@@ -971,47 +544,6 @@ int launch_blend_bwd(const hg_raster_inputs& in, const GeomState& g, const BinSt
       else HG_LAUNCH3(false, false, false);
     }
 #undef HG_LAUNCH3
-    HG_POST_LAUNCH(in.debug, stream, "blend_bwd");
-    return HG_OK;
-  }
-  if (variant == 2) {
-#define HG_LAUNCH2(G_, D_, I_)                                                                \
-  blend_bwd2_kernel<G_, D_, I_><<<grid, kThreadsB, 0, stream>>>(                              \
-      img.ranges, b.vals, g.records, in.ts, in.kids, in.W, in.H, focal_x, focal_y,            \
-      in.background, all_map_pixels, img.final_T, img.n_contrib, dL_dpix, dL_dout_all_map,    \
-      dL_dout_plane_depth, dL_dout_invdepth, accum)
-    if (interp) {
-      if (geo && depth) HG_LAUNCH2(true, true, true);
-      else if (geo) HG_LAUNCH2(true, false, true);
-      else if (depth) HG_LAUNCH2(false, true, true);
-      else HG_LAUNCH2(false, false, true);
-    } else {
-      if (geo && depth) HG_LAUNCH2(true, true, false);
-      else if (geo) HG_LAUNCH2(true, false, false);
-      else if (depth) HG_LAUNCH2(false, true, false);
-      else HG_LAUNCH2(false, false, false);
-    }
-#undef HG_LAUNCH2
-    HG_POST_LAUNCH(in.debug, stream, "blend_bwd");
-    return HG_OK;
-  }
-#define HG_LAUNCH(G_, D_, I_)                                                                 \
-  blend_bwd_kernel<G_, D_, I_><<<grid, HG_BLOCK_SIZE, 0, stream>>>(                           \
-      img.ranges, b.vals, g.records, in.ts, in.kids, in.W, in.H, focal_x, focal_y,            \
-      in.background, all_map_pixels, img.final_T, img.n_contrib, dL_dpix, dL_dout_all_map,    \
-      dL_dout_plane_depth, dL_dout_invdepth, accum)
-  if (interp) {
-    if (geo && depth) HG_LAUNCH(true, true, true);
-    else if (geo) HG_LAUNCH(true, false, true);
-    else if (depth) HG_LAUNCH(false, true, true);
-    else HG_LAUNCH(false, false, true);
-  } else {
-    if (geo && depth) HG_LAUNCH(true, true, false);
-    else if (geo) HG_LAUNCH(true, false, false);
-    else if (depth) HG_LAUNCH(false, true, false);
-    else HG_LAUNCH(false, false, false);
-  }
-#undef HG_LAUNCH
   HG_POST_LAUNCH(in.debug, stream, "blend_bwd");
   return HG_OK;
 }

@@ -3,29 +3,28 @@
 // Replaces renderCUDA<3,5> forward of the reference
 // (cuda_rasterizer/forward.cu:440-610, launched at :639).
 //
-// Design (B200):
-//  * one 256-thread CTA per 16x16 tile; each WARP owns an 8x4 pixel sub-tile so
-//    that all decisions that let the reference skip work per pixel can be taken
-//    per warp here;
-//  * the tile's sorted list is consumed in batches of 256 entries.  Each thread
-//    gathers ONE 64-byte splat record (4 x LDG.128, L2-resident: 64 MB at 1M
-//    Gaussians) into registers while the previous batch is being blended
-//    (register double buffering), then publishes it to shared memory as one
-//    80-byte staging record (blend_common.cuh): one address per entry in the
-//    blend loop, every field at an immediate offset;
-//  * per warp, 32 entries at a time are tested lane-parallel against the warp's
-//    sub-tile with an EXACT conservative bound (minimum of the Gaussian's
-//    quadratic form over the 8x4 rectangle vs ln(255*opacity)); only entries
-//    that can reach alpha >= 1/255 somewhere in the sub-tile are evaluated.
-//    Skipped entries are exactly those the reference would `continue` on for
-//    every pixel of the sub-tile, so results are unchanged;
-//  * the per-pixel arithmetic of kept entries (power, exp, alpha, T) uses
-//    explicit round-to-nearest intrinsics in the reference's compiled order so
-//    that alpha thresholds, early termination, n_contrib and out_observe are
-//    bit-identical;
-//  * out_observe is counted with one warp ballot per entry into a shared
-//    counter and flushed with one global atomic per (tile, entry);
+// Design (B200), blend_fwd2_kernel:
+//  * one 128-thread CTA per 16x16 tile; each WARP owns an 8x8 pixel sub-tile, two pixels per lane (rows r, r+4), so
+//    that all decisions that let the reference skip work per pixel can be taken per warp and half here;
+//  * the tile's sorted list is consumed in batches of 128 entries.  Each thread gathers ONE 64-byte splat record
+//    (4 x LDG.128, L2-resident: 64 MB at 1M Gaussians) into registers while the previous batch is being blended
+//    (register double buffering), then publishes it to shared memory as one 80-byte staging record
+//    (blend_common.cuh): one address per entry in the blend loop, every field at an immediate offset;
+//  * per warp and half, 32 entries at a time are tested lane-parallel against the 8x4 rectangle with an EXACT
+//    conservative bound (minimum of the Gaussian's quadratic form over the rectangle vs ln(255*opacity)); only entries
+//    that can reach alpha >= 1/255 somewhere in it are evaluated.  Skipped entries are exactly those the reference
+//    would `continue` on for every pixel of the rectangle, so results are unchanged;
+//  * the per-pixel arithmetic of kept entries (power, exp, alpha, T) uses explicit round-to-nearest intrinsics in the
+//    reference's compiled order so that alpha thresholds, early termination, n_contrib and out_observe are
+//    bit-identical; when an entry reaches both halves the two pixels of a lane run through a select-predicated,
+//    branch-free twin of the per-pixel code in ONE basic block (their dependency chains interleave);
+//  * out_observe is counted with one warp ballot per entry into a shared counter and flushed with one global atomic
+//    per (tile, entry);
 //  * early termination: lane (pixel) -> warp (ballot) -> CTA (__syncthreads_or).
+// Removed after measurement: the one-pixel-per-lane first version (0.66 vs 0.55 ms at config 2) and a variant that
+// staged every batch with one cp.async.bulk per thread into an mbarrier-released ring (SASS UBLKCP.S.G +
+// SYNCS.ARRIVE.TRANS64, dump kept in profiles/r02_sass_excerpts.md): 0.674 vs 0.661 ms for the register-double-buffered
+// gather of the same build — the gathers hit L2 and are hidden already.
 #include "blend_common.cuh"
 
 #include <cstdlib>
@@ -34,173 +33,9 @@ namespace hg {
 
 namespace {
 
-template <bool GEO, bool DEPTH, bool INTERP>
-__global__ void __launch_bounds__(HG_BLOCK_SIZE)
-blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                 const float4* __restrict__ records, const float* __restrict__ ts,
-                 const int* __restrict__ kids, const int W, const int H, const float focal_x,
-                 const float focal_y, const float cx, const float cy,
-                 const float* __restrict__ bg_color, float* __restrict__ final_T,
-                 uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-                 float* __restrict__ out_invdepth, int* __restrict__ out_observe,
-                 float* __restrict__ out_all_map, float* __restrict__ out_plane_depth) {
-  __shared__ float4 s_rec[kBatch * kRecQuads];
-  __shared__ int s_obs[kBatch];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
-  // Warp -> 8x4 sub-tile, lane -> pixel.
-  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
-  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 4;
-  const int pxi = wx0 + (lane & 7), pyi = wy0 + (lane >> 3);
-  const bool inside = pxi < W && pyi < H;
-  const float pixx = (float)pxi, pixy = (float)pyi;
-  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7), fy0 = (float)wy0, fy1 = (float)(wy0 + 3);
-
-  const uint2 range = ranges[tile];
-  const int n = (int)(range.y - range.x);
-  const int nb = (n + kBatch - 1) / kBatch;
-
-  bool done = !inside;
-  float T = 1.0f;
-  uint32_t last_contributor = 0;
-  float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dinv = 0.f;
-  float A0 = 0.f, A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f;
-
-  Prefetch pf;
-  auto prefetch = [&](int b) {
-    const int i = b * kBatch + tid;
-    if (i < n) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + i);
-  };
-  if (nb > 0) prefetch(0);
-
-  bool pending_flush = false;
-  for (int b = 0; b < nb; ++b) {
-    const int any_active = __syncthreads_or(!done);
-    if (pending_flush) {
-      const int c = s_obs[tid];
-      if (c) atomicAdd(out_observe + __float_as_int(s_rec[kRecQuads * tid + 1].w), c);
-      pending_flush = false;
-    }
-    if (!any_active) break;
-    // (thread `tid` is the only one that rewrites slot `tid`, whose id it has just read: no barrier needed here)
-
-    const int cnt = min(kBatch, n - b * kBatch);
-    if (tid < cnt) stage_record<GEO, INTERP>(s_rec, tid, pf);
-    s_obs[tid] = 0;
-    __syncthreads();
-    if (b + 1 < nb) prefetch(b + 1);
-    pending_flush = true;
-
-    if (__ballot_sync(0xffffffffu, !done) == 0) continue;  // whole warp finished
-    const uint32_t base = (uint32_t)(b * kBatch);
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-      const int j = c0 + lane;
-      bool keep = false;
-      if (j < cnt) {
-        const float4 ea = s_rec[kRecQuads * j];
-        const float4 eb = s_rec[kRecQuads * j + 1];
-        keep = may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, eb.z, fx0, fx1, fy0, fy1);
-      }
-      uint32_t mask = __ballot_sync(0xffffffffu, keep);
-      while (mask) {
-        const int k = c0 + __ffs(mask) - 1;
-        mask &= mask - 1;
-        const float4* e = s_rec + kRecQuads * k;
-        bool observed = false;
-        if (!done) {
-          const float4 ea = e[0];
-          const float2 eb = *reinterpret_cast<const float2*>(e + 1);
-          const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
-          // power = -0.5f*(a dx dx + c dy dy) - b dx dy, as compiled (forward.cu:536).
-          const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
-          const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
-          if (!(power > 0.0f)) {
-            float alpha = fminf(0.99f, __fmul_rn(eb.y, expf(power)));
-            if (INTERP) {
-              const float4 e4 = e[4];
-              const float kidsqrt = __fsub_rn(1.0f, __powf(__fsub_rn(1.0f, alpha), e4.z));
-              alpha = __fmaf_rn(alpha, e4.y, __fmul_rn(__fsub_rn(1.0f, e4.y), kidsqrt));
-            }
-            if (!(alpha < 1.0f / 255.0f)) {
-              const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-              if (test_T < 0.0001f) {
-                done = true;
-              } else {
-                // Blend weight alpha*T once, then one FMA per channel.  (The reference forms (c*alpha)*T per
-                // channel; the weights differ by one rounding, images agree to ~1e-7, far inside the 1e-4 bound.
-                // T itself, the thresholds and hence n_contrib / final_T / out_observe stay bit-identical.)
-                const float wgt = __fmul_rn(alpha, T);
-                const float4 ec = e[2];
-                C0 = __fmaf_rn(wgt, ec.x, C0);
-                C1 = __fmaf_rn(wgt, ec.y, C1);
-                C2 = __fmaf_rn(wgt, ec.z, C2);
-                if (DEPTH) Dinv = __fmaf_rn(wgt, ec.w, Dinv);
-                if (GEO) {
-                  const float4 ed = e[3];
-                  const float ee = e[4].x;
-                  A0 = __fmaf_rn(wgt, ed.x, A0);
-                  A1 = __fmaf_rn(wgt, ed.y, A1);
-                  A2 = __fmaf_rn(wgt, ed.z, A2);
-                  A3 = __fmaf_rn(wgt, ed.w, A3);
-                  A4 = __fmaf_rn(wgt, ee, A4);
-                }
-                observed = T > 0.5f;
-                T = test_T;
-                last_contributor = base + (uint32_t)k + 1u;
-              }
-            }
-          }
-        }
-        const uint32_t om = __ballot_sync(0xffffffffu, observed);
-        if (om && lane == 0) atomicAdd(&s_obs[k], __popc(om));
-      }
-      if (__ballot_sync(0xffffffffu, !done) == 0) break;
-    }
-  }
-  if (pending_flush) {
-    __syncthreads();
-    const int c = s_obs[tid];
-    if (c) atomicAdd(out_observe + __float_as_int(s_rec[kRecQuads * tid + 1].w), c);
-  }
-
-  if (inside) {
-    const size_t HW = (size_t)H * W;
-    const size_t pix = (size_t)pyi * W + pxi;
-    final_T[pix] = T;
-    n_contrib[pix] = last_contributor;
-    out_color[pix] = __fmaf_rn(T, __ldg(bg_color), C0);
-    out_color[HW + pix] = __fmaf_rn(T, __ldg(bg_color + 1), C1);
-    out_color[2 * HW + pix] = __fmaf_rn(T, __ldg(bg_color + 2), C2);
-    if (DEPTH) out_invdepth[pix] = Dinv;
-    if (GEO) {
-      out_all_map[pix] = A0;
-      out_all_map[HW + pix] = A1;
-      out_all_map[2 * HW + pix] = A2;
-      out_all_map[3 * HW + pix] = A3;
-      out_all_map[4 * HW + pix] = A4;
-      // plane depth (forward.cu:474,607): float ray, double add/div.
-      const float rayx = __fdiv_rn(__fsub_rn(pixx, cx), focal_x);
-      const float rayy = __fdiv_rn(__fsub_rn(pixy, cy), focal_y);
-      const float den = __fadd_rn(A2, __fmaf_rn(rayx, A0, __fmul_rn(rayy, A1)));
-      out_plane_depth[pix] = (float)__ddiv_rn((double)A4, -__dadd_rn((double)den, 1.0e-8));
-    } else {
-      out_all_map[pix] = 0.f;
-      out_all_map[HW + pix] = 0.f;
-      out_all_map[2 * HW + pix] = 0.f;
-      out_all_map[3 * HW + pix] = 0.f;
-      out_all_map[4 * HW + pix] = 0.f;
-      out_plane_depth[pix] = 0.f;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Variant B: warp per 8x8 sub-tile, TWO pixels per lane (rows r and r+4), 128-thread CTA per tile.  The loop control,
-// the broadcast reads of the staged entry and the observe bookkeeping are shared by the two pixels; each half of the
-// sub-tile has its own exact cull test.  Per-pixel arithmetic and decisions are those of variant A (bit-identical
-// n_contrib / final_T / out_observe).
+// Warp per 8x8 sub-tile, TWO pixels per lane (rows r and r+4), 128-thread CTA per tile.  The loop control, the broadcast
+// reads of the staged entry and the observe bookkeeping are shared by the two pixels; each half of the sub-tile has its
+// own exact cull test.
 constexpr int kThreadsB = 128;
 constexpr int kBatchB = kThreadsB;
 
@@ -439,201 +274,6 @@ blend_fwd2_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                           n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Variant C (experiment, HG_BLEND_FWD_VARIANT=3): as variant B, but the 64-byte splat records travel global -> shared
-// through the TMA engine: every thread issues ONE cp.async.bulk (UBLKCP) for its entry of the NEXT batch into the other
-// half of a double-buffered ring and the batch is released by an mbarrier transaction count — no register staging, no
-// STS.  The record is consumed as stored (the cull threshold is derived on the fly, the slot id sits in word 15).
-// Not used with hierarchy interpolation (two more gathered words per entry).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, int bytes) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n"
-      " DONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, int bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <bool GEO, bool DEPTH>
-__global__ void __launch_bounds__(kThreadsB)
-blend_fwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                  const float4* __restrict__ records, const int W, const int H, const float focal_x,
-                  const float focal_y, const float cx, const float cy,
-                  const float* __restrict__ bg_color, float* __restrict__ final_T,
-                  uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
-                  float* __restrict__ out_invdepth, int* __restrict__ out_observe,
-                  float* __restrict__ out_all_map, float* __restrict__ out_plane_depth) {
-  __shared__ __align__(128) float4 s_ring[2][kBatchB * 4];  // raw 64-byte records
-  __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ int s_obs[kBatchB];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile = blockIdx.y * gridDim.x + blockIdx.x;
-  const int wx0 = blockIdx.x * HG_BLOCK_X + (warp & 1) * 8;
-  const int wy0 = blockIdx.y * HG_BLOCK_Y + (warp >> 1) * 8;
-  const int pxi = wx0 + (lane & 7), pyA = wy0 + (lane >> 3), pyB = pyA + 4;
-  const bool insideA = pxi < W && pyA < H, insideB = pxi < W && pyB < H;
-  const float pixx = (float)pxi, pixyA = (float)pyA, pixyB = (float)pyB;
-  const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7);
-  const float fyA0 = (float)wy0, fyA1 = (float)(wy0 + 3), fyB0 = (float)(wy0 + 4), fyB1 = (float)(wy0 + 7);
-
-  const uint2 range = ranges[tile];
-  const int n = (int)(range.y - range.x);
-  const int nb = (n + kBatchB - 1) / kBatchB;
-
-  FwdPixel A{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0u, !insideA};
-  FwdPixel B{1.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0u, !insideB};
-
-  if (tid == 0) {
-    mbar_init(&s_bar[0], kThreadsB);
-    mbar_init(&s_bar[1], kThreadsB);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // Every thread arrives once per batch on that batch's barrier; a thread that owns an entry also announces its 64 bytes.
-  auto issue = [&](int b, int id) {
-    uint64_t* bar = &s_bar[b & 1];
-    if (b * kBatchB + tid < n) {
-      mbar_arrive_expect_tx(bar, 64);
-      bulk_g2s(&s_ring[b & 1][4 * tid], records + 4 * (size_t)id, 64, bar);
-    } else {
-      mbar_arrive(bar);
-    }
-  };
-  auto load_id = [&](int b) -> int {
-    const int i = b * kBatchB + tid;
-    return (b < nb && i < n) ? (int)__ldg(point_list + range.x + i) : 0;
-  };
-  int id_next = load_id(0);
-  if (nb > 0) issue(0, id_next);
-  id_next = load_id(1);
-
-  bool pending_flush = false;
-  int obs_id = 0;
-  int unconsumed = -1;  // batch whose copy was issued but never waited for (early exit)
-  for (int b = 0; b < nb; ++b) {
-    const int any_active = __syncthreads_or(!(A.done && B.done));  // also: every warp has left batch b-1 (its ring half is free)
-    if (pending_flush) {
-      const int c = s_obs[tid];
-      if (c) atomicAdd(out_observe + obs_id, c);
-      pending_flush = false;
-    }
-    if (!any_active) {
-      unconsumed = b;
-      break;
-    }
-    // reads of ring half (b+1)&1 by the generic proxy (batch b-1) are ordered before the async-proxy writes below
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    if (b + 1 < nb) issue(b + 1, id_next);
-    id_next = load_id(b + 2);
-    s_obs[tid] = 0;
-    mbar_wait(&s_bar[b & 1], (b >> 1) & 1);
-    __syncthreads();  // s_obs zeroed everywhere before the first count lands
-    const float4* rec = s_ring[b & 1];
-    const int cnt = min(kBatchB, n - b * kBatchB);
-    obs_id = __float_as_int(rec[4 * tid + 3].w);
-    pending_flush = true;
-
-    uint32_t liveA = __ballot_sync(0xffffffffu, !A.done), liveB = __ballot_sync(0xffffffffu, !B.done);
-    if ((liveA | liveB) == 0) continue;
-    const uint32_t base = (uint32_t)(b * kBatchB);
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
-      const int j = c0 + lane;
-      bool keepA = false, keepB = false;
-      if (j < cnt) {
-        const float4 ea = rec[4 * j];
-        const float4 eb = rec[4 * j + 1];
-        const float tau = cull_tau(ea.z, ea.w, eb.x, eb.y, false);
-        keepA = liveA != 0 && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, tau, fx0, fx1, fyA0, fyA1);
-        keepB = liveB != 0 && may_touch(ea.x, ea.y, ea.z, ea.w, eb.x, tau, fx0, fx1, fyB0, fyB1);
-      }
-      const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
-      uint32_t mask = maskA | maskB;
-      while (mask) {
-        const int bit = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int k = c0 + bit;
-        const float4* e = rec + 4 * k;
-        const float4 ea = e[0];
-        const float4 e1 = e[1];  // c o r g
-        const float4 e2 = e[2];  // b 1/z am0 am1
-        const uint32_t index1 = base + (uint32_t)k + 1u;
-        bool obsA = false, obsB = false;
-#define HG_PIX(S, PY, OBS)                                                                                   \
-  if (!S.done) {                                                                                             \
-    const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, PY);                                        \
-    const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, e1.x)));              \
-    const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));                         \
-    if (!(power > 0.0f)) {                                                                                   \
-      const float alpha = fminf(0.99f, __fmul_rn(e1.y, expf(power)));                                        \
-      if (!(alpha < 1.0f / 255.0f)) {                                                                        \
-        const float test_T = __fmul_rn(S.T, __fsub_rn(1.0f, alpha));                                         \
-        if (test_T < 0.0001f) {                                                                              \
-          S.done = true;                                                                                     \
-        } else {                                                                                             \
-          const float wgt = __fmul_rn(alpha, S.T);                                                           \
-          S.C0 = __fmaf_rn(wgt, e1.z, S.C0);                                                                 \
-          S.C1 = __fmaf_rn(wgt, e1.w, S.C1);                                                                 \
-          S.C2 = __fmaf_rn(wgt, e2.x, S.C2);                                                                 \
-          if (DEPTH) S.Dinv = __fmaf_rn(wgt, e2.y, S.Dinv);                                                  \
-          if (GEO) {                                                                                         \
-            const float4 e3 = e[3];                                                                          \
-            S.A0 = __fmaf_rn(wgt, e2.z, S.A0);                                                               \
-            S.A1 = __fmaf_rn(wgt, e2.w, S.A1);                                                               \
-            S.A2 = __fmaf_rn(wgt, e3.x, S.A2);                                                               \
-            S.A3 = __fmaf_rn(wgt, e3.y, S.A3);                                                               \
-            S.A4 = __fmaf_rn(wgt, e3.z, S.A4);                                                               \
-          }                                                                                                  \
-          OBS = S.T > 0.5f;                                                                                  \
-          S.T = test_T;                                                                                      \
-          S.last_contributor = index1;                                                                       \
-        }                                                                                                    \
-      }                                                                                                      \
-    }                                                                                                        \
-  }
-        if ((maskA >> bit) & 1u) { HG_PIX(A, pixyA, obsA) }
-        if ((maskB >> bit) & 1u) { HG_PIX(B, pixyB, obsB) }
-#undef HG_PIX
-        const uint32_t oa = __ballot_sync(0xffffffffu, obsA), ob = __ballot_sync(0xffffffffu, obsB);
-        if ((oa | ob) && lane == 0) atomicAdd(&s_obs[k], __popc(oa) + __popc(ob));
-      }
-      liveA = __ballot_sync(0xffffffffu, !A.done);
-      liveB = __ballot_sync(0xffffffffu, !B.done);
-      if ((liveA | liveB) == 0) break;
-    }
-  }
-  if (pending_flush) {
-    __syncthreads();
-    const int c = s_obs[tid];
-    if (c) atomicAdd(out_observe + obs_id, c);
-  }
-  // The bulk copy of a batch that was never consumed (early exit) may still be in flight: wait for it before the CTA's
-  // shared memory is released.
-  if (unconsumed >= 0) mbar_wait(&s_bar[unconsumed & 1], (unconsumed >> 1) & 1);
-
-  const size_t HW = (size_t)H * W;
-  write_pixel<GEO, DEPTH>(A, insideA, (size_t)pyA * W + pxi, HW, pixx, pixyA, cx, cy, focal_x, focal_y, bg_color, final_T,
-                          n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
-  write_pixel<GEO, DEPTH>(B, insideB, (size_t)pyB * W + pxi, HW, pixx, pixyB, cx, cy, focal_x, focal_y, bg_color, final_T,
-                          n_contrib, out_color, out_invdepth, out_all_map, out_plane_depth);
-}
-
 template <bool GEO, bool DEPTH>
 int dispatch(bool interp, dim3 grid, cudaStream_t stream, const uint2* ranges,
              const uint32_t* point_list, const float4* records, const float* ts, const int* kids,
@@ -641,33 +281,12 @@ int dispatch(bool interp, dim3 grid, cudaStream_t stream, const uint2* ranges,
              uint32_t* n_contrib, float* out_color, float* out_invdepth, int* out_observe,
              float* out_all_map, float* out_plane_depth) {
   const float cx = float(W * 0.5f), cy = float(H * 0.5f);
-  static const int variant = [] {
-    const char* e = getenv("HG_BLEND_FWD_VARIANT");
-    return e ? atoi(e) : 2;
-  }();
-  if (variant == 3 && !interp) {
-    blend_fwd3_kernel<GEO, DEPTH><<<grid, kThreadsB, 0, stream>>>(ranges, point_list, records, W, H, fx, fy, cx, cy, bg,
-                                                                final_T, n_contrib, out_color, out_invdepth,
-                                                                out_observe, out_all_map, out_plane_depth);
-    return 0;
-  }
-  if (variant == 2 || variant == 3) {
-    if (interp)
-      blend_fwd2_kernel<GEO, DEPTH, true><<<grid, kThreadsB, 0, stream>>>(
-          ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
-          out_color, out_invdepth, out_observe, out_all_map, out_plane_depth);
-    else
-      blend_fwd2_kernel<GEO, DEPTH, false><<<grid, kThreadsB, 0, stream>>>(
-          ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
-          out_color, out_invdepth, out_observe, out_all_map, out_plane_depth);
-    return 0;
-  }
   if (interp)
-    blend_fwd_kernel<GEO, DEPTH, true><<<grid, HG_BLOCK_SIZE, 0, stream>>>(
+    blend_fwd2_kernel<GEO, DEPTH, true><<<grid, kThreadsB, 0, stream>>>(
         ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
         out_color, out_invdepth, out_observe, out_all_map, out_plane_depth);
   else
-    blend_fwd_kernel<GEO, DEPTH, false><<<grid, HG_BLOCK_SIZE, 0, stream>>>(
+    blend_fwd2_kernel<GEO, DEPTH, false><<<grid, kThreadsB, 0, stream>>>(
         ranges, point_list, records, ts, kids, W, H, fx, fy, cx, cy, bg, final_T, n_contrib,
         out_color, out_invdepth, out_observe, out_all_map, out_plane_depth);
   return 0;

@@ -78,7 +78,7 @@ def main():
         return dict(fwd_ms=round(f_ms[len(f_ms) // 2], 3), bwd_ms=round(b_ms[len(b_ms) // 2], 3), num_rendered=R)
 
     out = dict(workload="configs[2]: %d-Gaussian UAV slab, hierarchy cut of %d nodes with interpolation weights, %dx%d, SH 3, "
-               "colour only" % (n, P, W, H), bwd_variant=os.environ.get("HG_BLEND_BWD_VARIANT", "3"))
+               "colour only" % (n, P, W, H))
     from hidegs_b200 import _lib
     _lib.profile_enable(True)
     _lib.profile_collect()
