@@ -5,6 +5,7 @@ from . import _lib
 
 EXPORTED_SYMBOLS = (
     "hg_reduce_workspace_bytes", "hg_l1_loss", "hg_l2_loss", "hg_pixel_loss_backward", "hg_freq_total", "hg_training_image_grad", "hg_ssim_workspace_bytes", "hg_ssim", "hg_ssim_backward",
+    "hg_ssim_window_workspace_bytes", "hg_ssim_window", "hg_ssim_window_backward",
     "hg_img_grad_weight_workspace_bytes", "hg_img_grad_weight", "hg_lncc", "hg_lncc_backward",
     "hg_scale_reg_workspace_bytes", "hg_scale_reg", "hg_fft2_workspace_bytes", "hg_fft2_r2c", "hg_fft2_c2r",
     "hg_freq_loss_workspace_bytes", "hg_freq_loss", "hg_freq_forward", "hg_freq_backward", "hg_freq_gt_state_bytes", "hg_freq_gt_prepare", "hg_freq_loss_cached", "hg_hf_mask_workspace_bytes", "hg_hf_mask",
@@ -29,6 +30,9 @@ def lib():
         "hg_ssim_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "hg_ssim": (ctypes.c_int, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
         "hg_ssim_backward": (ctypes.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]),
+        "hg_ssim_window_workspace_bytes": (sz, [i32, i32, i32, i32]),
+        "hg_ssim_window": (ctypes.c_int, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "hg_ssim_window_backward": (ctypes.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
         "hg_img_grad_weight_workspace_bytes": (sz, [i32, i32]),
         "hg_img_grad_weight": (ctypes.c_int, [vp, i32, i32, i32, vp, vp, vp]),
         "hg_lncc": (ctypes.c_int, [vp, vp, i32, i32, vp, vp, vp]),

@@ -313,6 +313,100 @@ ssim_bwd_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
   }
 }
 
+// ---------------------------------------------------------------- SSIM, any odd window
+// The tiled kernels above are specialised for the reference's default window (11 taps, the one every call site uses).
+// ssim(img1, img2, window_size) with another odd size takes these two-pass kernels: a horizontal pass into a scratch
+// of five (forward) or three (backward) planes, a vertical pass that finishes the map.  Same separable Gaussian
+// (gaussian(window_size, 1.5), loss_utils.py:24-26), same zero padding of window_size / 2, same derivative maps.
+constexpr int kMaxWindow = 63;
+struct GaussN { float w[kMaxWindow]; int n; };
+
+template <int NQ, bool SSIM_IN>
+__global__ void __launch_bounds__(256)
+window_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                   size_t in_stride, int H, int W, const GaussN gw, float* __restrict__ tmp, size_t plane_elems) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const size_t base = (size_t)blockIdx.z * H * W + (size_t)y * W;
+  const int R = gw.n / 2;
+  float acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+  for (int k = 0; k < gw.n; ++k) {
+    const int xx = x + k - R;
+    if (xx < 0 || xx >= W) continue;  // zero padding
+    const float w = gw.w[k];
+    if (SSIM_IN) {
+      const float p = __ldg(a + base + xx), q = __ldg(b + base + xx);
+      acc[0] += w * p; acc[1] += w * q; acc[2] += w * (p * p); acc[3] += w * (q * q); acc[4] += w * (p * q);
+    } else {
+      acc[0] += w * __ldg(a + base + xx);
+      acc[1] += w * __ldg(b + base + xx);
+      acc[2] += w * __ldg(c + base + xx);
+    }
+  }
+  (void)in_stride;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) tmp[q * plane_elems + base + x] = acc[q];
+}
+
+__global__ void __launch_bounds__(256)
+window_cols_ssim_kernel(const float* __restrict__ tmp, size_t plane_elems, int H, int W, const GaussN gw,
+                        float* __restrict__ maps, size_t map_stride, double* __restrict__ partial) {
+  __shared__ float red[32];
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const size_t base = (size_t)blockIdx.z * H * W;
+  float val = 0.f;
+  if (x < W && y < H) {
+    const int R = gw.n / 2;
+    float o[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < gw.n; ++k) {
+      const int yy = y + k - R;
+      if (yy < 0 || yy >= H) continue;
+      const float w = gw.w[k];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) o[q] += w * __ldg(tmp + q * plane_elems + base + (size_t)yy * W + x);
+    }
+    const float mu1 = o[0], mu2 = o[1], e11 = o[2], e22 = o[3], e12 = o[4];
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+    const float sg1 = e11 - mu1_sq, sg2 = e22 - mu2_sq, sg12 = e12 - mu12;
+    const float A = mu1_sq + mu2_sq + C1, B = sg1 + sg2 + C2, C = 2.f * mu12 + C1, D = 2.f * sg12 + C2;
+    const float iA = 1.0f / A, iB = 1.0f / B, iAB = iA * iB;
+    const float ssim = (C * D) * iAB;
+    val = ssim;
+    if (maps) {
+      const size_t p = base + (size_t)y * W + x;
+      maps[p] = 2.f * mu2 * (D - C) * iAB - 2.f * mu1 * ssim * (iA - iB);
+      maps[map_stride + p] = -ssim * iB;
+      maps[2 * map_stride + p] = (2.f * C) * iAB;
+    }
+  }
+  const float sum = block_sum(val, red, threadIdx.x, 256);
+  if (threadIdx.x == 0) partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = (double)sum;
+}
+
+__global__ void __launch_bounds__(256)
+window_cols_grad_kernel(const float* __restrict__ tmp, size_t plane_elems, const float* __restrict__ img1,
+                        const float* __restrict__ img2, const float* __restrict__ gscale, int C, int H, int W,
+                        const GaussN gw, float* __restrict__ grad) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const size_t base = (size_t)blockIdx.z * H * W;
+  const int R = gw.n / 2;
+  float o[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < gw.n; ++k) {
+    const int yy = y + k - R;
+    if (yy < 0 || yy >= H) continue;
+    const float w = gw.w[k];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) o[q] += w * __ldg(tmp + q * plane_elems + base + (size_t)yy * W + x);
+  }
+  const size_t p = base + (size_t)y * W + x;
+  const float sc = __ldg(gscale + blockIdx.z / C) / ((float)C * (float)H * (float)W);
+  grad[p] = sc * (o[0] + 2.f * __ldg(img1 + p) * o[1] + __ldg(img2 + p) * o[2]);
+}
+
 // ---------------------------------------------------------------- get_img_grad_weight
 __global__ void __launch_bounds__(256)
 grad_weight_raw_kernel(const float* __restrict__ img, int C, int H, int W, float* __restrict__ out,
@@ -494,6 +588,20 @@ Gauss11 gauss_window() {
   return g;
 }
 
+// gaussian(n, 1.5), same evaluation order
+bool gauss_window_n(int n, GaussN* g) {
+  if (n < 1 || n > kMaxWindow || (n & 1) == 0) return false;
+  g->n = n;
+  float sum = 0.f;
+  for (int x = 0; x < n; ++x) {
+    g->w[x] = (float)std::exp(-(double)((x - n / 2) * (x - n / 2)) / (2.0 * 1.5 * 1.5));
+    sum += g->w[x];
+  }
+  for (int x = 0; x < n; ++x) g->w[x] = g->w[x] / sum;
+  for (int x = n; x < kMaxWindow; ++x) g->w[x] = 0.f;
+  return true;
+}
+
 }  // namespace
 }  // namespace hg
 
@@ -584,6 +692,52 @@ int hg_ssim_backward(const float* img1, const float* img2, const float* maps, co
   ssim_bwd_kernel<<<grid, kSsimThreads, 0, st>>>(img1, img2, maps, (size_t)B * C * H * W, gscale, C, H, W,
                                                       gauss_window(), grad_img1);
   HG_POST_LAUNCH(false, st, "ssim_bwd");
+  return HG_OK;
+}
+
+size_t hg_ssim_window_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W) {
+  const size_t blocks = (size_t)((W + 31) / 32) * ((H + 7) / 8);
+  return sizeof(double) * blocks * (size_t)B * C + 256 + sizeof(float) * 5 * (size_t)B * C * H * W;
+}
+
+int hg_ssim_window(const float* img1, const float* img2, int32_t B, int32_t C, int32_t H, int32_t W, int32_t window_size,
+                   float* out, float* maps, void* ws, void* st_) {
+  GaussN gw;
+  if (!img1 || !img2 || !out || !ws || B <= 0 || C <= 0 || H <= 0 || W <= 0 || (size_t)B * C > 65535 ||
+      !gauss_window_n(window_size, &gw)) {
+    set_error("hg_ssim_window: bad argument (window_size must be odd, 1..%d)", kMaxWindow);
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, B * C);
+  const size_t n = (size_t)B * C * H * W;
+  double* partial = (double*)ws;
+  float* tmp = (float*)((char*)ws + align_up(sizeof(double) * grid.x * grid.y * grid.z, 256));
+  window_rows_kernel<5, true><<<grid, 256, 0, st>>>(img1, img2, nullptr, 0, H, W, gw, tmp, n);
+  HG_POST_LAUNCH(false, st, "ssim_window_rows");
+  window_cols_ssim_kernel<<<grid, 256, 0, st>>>(tmp, n, H, W, gw, maps, n, partial);
+  HG_POST_LAUNCH(false, st, "ssim_window_cols");
+  ssim_finalize_kernel<<<B, 1024, 0, st>>>(partial, (int)(grid.x * grid.y * C), (double)C * H * W, out);
+  HG_POST_LAUNCH(false, st, "ssim_finalize");
+  return HG_OK;
+}
+
+int hg_ssim_window_backward(const float* img1, const float* img2, const float* maps, const float* gscale, int32_t B,
+                            int32_t C, int32_t H, int32_t W, int32_t window_size, float* grad_img1, void* ws, void* st_) {
+  GaussN gw;
+  if (!img1 || !img2 || !maps || !gscale || !grad_img1 || !ws || B <= 0 || C <= 0 || H <= 0 || W <= 0 ||
+      !gauss_window_n(window_size, &gw)) {
+    set_error("hg_ssim_window_backward: bad argument");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, B * C);
+  const size_t n = (size_t)B * C * H * W;
+  float* tmp = (float*)((char*)ws + align_up(sizeof(double) * grid.x * grid.y * grid.z, 256));
+  window_rows_kernel<3, false><<<grid, 256, 0, st>>>(maps, maps + n, maps + 2 * n, n, H, W, gw, tmp, n);
+  HG_POST_LAUNCH(false, st, "ssim_window_bwd_rows");
+  window_cols_grad_kernel<<<grid, 256, 0, st>>>(tmp, n, img1, img2, gscale, C, H, W, gw, grad_img1);
+  HG_POST_LAUNCH(false, st, "ssim_window_bwd_cols");
   return HG_OK;
 }
 

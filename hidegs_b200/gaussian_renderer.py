@@ -122,13 +122,40 @@ class _DepthNormal(torch.autograd.Function):
         return gd, None, None
 
 
+def _normal_from_offset_samples(depth, offset, K):
+    """The offset branch of depth_pcd2normal (utils/graphics_utils.py:130-150): the four neighbours of every interior
+    pixel are displaced by per-pixel 2-D offsets and read from the unprojected point map by bilinear interpolation
+    (grid_sample's default align_corners=False over coordinates normalised with (size - 1), as the reference does).
+    No call site of the reference passes an offset (render() never does), so this branch is a composition of device
+    tensor operations with autograd, not a fused kernel."""
+    H, W = depth.shape
+    dev = depth.device
+    u = torch.arange(W, dtype=torch.float32, device=dev) / (W - 1)
+    v = torch.arange(H, dtype=torch.float32, device=dev) / (H - 1)
+    scale = torch.tensor([W - 1, H - 1], dtype=torch.float32, device=dev)
+    uv = torch.stack(torch.broadcast_tensors(u[None, :], v[:, None]), -1)                      # (H, W, 2) in [0, 1]
+    Kmat = torch.tensor([[K.fx, 0.0, K.cx], [0.0, K.fy, K.cy], [0.0, 0.0, 1.0]], dtype=torch.float32, device=dev)
+    pts = torch.cat([uv * scale * depth[..., None], depth[..., None]], -1) @ torch.inverse(Kmat.t())   # camera points
+    step = torch.tensor([[0.0, 1.0], [0.0, -1.0], [1.0, 0.0], [-1.0, 0.0]], device=dev)      # bottom, top, right, left
+    ij = torch.stack(torch.meshgrid(torch.arange(W, device=dev), torch.arange(H, device=dev), indexing="xy"), -1)
+    at = ij[1:-1, 1:-1, None, :] + step + offset.reshape(H, W, 4, 2)[1:-1, 1:-1]
+    at = torch.stack([2 * at[..., 0] / (W - 1) - 1.0, 2 * at[..., 1] / (H - 1) - 1.0], -1)
+    smp = torch.nn.functional.grid_sample(pts.permute(2, 0, 1)[None], at.reshape(1, -1, 1, 2), align_corners=False)
+    smp = smp.permute(0, 2, 3, 1).reshape(H - 2, W - 2, 4, 3)
+    n = torch.cross(smp[:, :, 2] - smp[:, :, 3], smp[:, :, 1] - smp[:, :, 0], dim=-1)
+    n = torch.nn.functional.normalize(n, p=2, dim=-1)
+    return torch.nn.functional.pad(n.permute(2, 0, 1), (1, 1, 1, 1))
+
+
 def render_normal(viewpoint_cam, depth, offset=None, normal=None, scale=1):
     """render_normal (:21-33): (3, H, W) normals of the unprojected depth map."""
-    if offset is not None:
-        raise NotImplementedError("hidegs_b200.render_normal implements the offset=None path the reference's render() uses")
     st = max(int(scale / 2) - 1, 0)
     d = depth[st::scale, st::scale] if scale != 1 else depth
-    return _DepthNormal.apply(d, None, camera_intrinsics(viewpoint_cam, scale))
+    K = camera_intrinsics(viewpoint_cam, scale)
+    if offset is not None:
+        _need_cuda(depth, offset)
+        return _normal_from_offset_samples(d, offset[st::scale, st::scale], K)
+    return _DepthNormal.apply(d, None, K)
 
 
 class _NormalConsistency(torch.autograd.Function):

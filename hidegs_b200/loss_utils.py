@@ -76,8 +76,34 @@ def l2_loss(network_output, gt):
 
 
 class _SSIM(torch.autograd.Function):
+    """ssim (loss_utils.py:24-64).  window 11 (every call site of the reference): the tiled shared-memory kernels;
+    any other odd window: the two-pass kernels of hg_ssim_window."""
+
     @staticmethod
-    def forward(ctx, img1, img2, size_average):
+    def _fwd(x, y, B, C, H, W, window, out, maps):
+        if window == 11:
+            ws = _ws(_L().hg_ssim_workspace_bytes(B, C, H, W), x.device)
+            rc = _L().hg_ssim(x.data_ptr(), y.data_ptr(), B, C, H, W, out.data_ptr(), maps.data_ptr() if maps is not None else None,
+                              ws.data_ptr(), _stream())
+        else:
+            ws = _ws(_L().hg_ssim_window_workspace_bytes(B, C, H, W), x.device)
+            rc = _L().hg_ssim_window(x.data_ptr(), y.data_ptr(), B, C, H, W, window, out.data_ptr(),
+                                     maps.data_ptr() if maps is not None else None, ws.data_ptr(), _stream())
+        _lib.check(rc, "ssim")
+
+    @staticmethod
+    def _bwd(x, y, maps, gs, B, C, H, W, window, grad):
+        if window == 11:
+            rc = _L().hg_ssim_backward(x.data_ptr(), y.data_ptr(), maps.data_ptr(), gs.data_ptr(), B, C, H, W, grad.data_ptr(),
+                                       _stream())
+        else:
+            ws = _ws(_L().hg_ssim_window_workspace_bytes(B, C, H, W), x.device)
+            rc = _L().hg_ssim_window_backward(x.data_ptr(), y.data_ptr(), maps.data_ptr(), gs.data_ptr(), B, C, H, W, window,
+                                              grad.data_ptr(), ws.data_ptr(), _stream())
+        _lib.check(rc, "ssim_backward")
+
+    @staticmethod
+    def forward(ctx, img1, img2, size_average, window):
         _check_cuda(img1, img2)
         if img1.shape != img2.shape or img1.dim() not in (3, 4):
             raise RuntimeError("ssim: expected two (C,H,W) or (B,C,H,W) tensors of the same shape")
@@ -88,12 +114,9 @@ class _SSIM(torch.autograd.Function):
         out = torch.empty(B, dtype=torch.float32, device=x.device)
         maps = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=x.device) if need1 else None
         with torch.cuda.device(x.device):
-            ws = _ws(_L().hg_ssim_workspace_bytes(B, C, H, W), x.device)
-            rc = _L().hg_ssim(x.data_ptr(), y.data_ptr(), B, C, H, W, out.data_ptr(), maps.data_ptr() if need1 else None,
-                              ws.data_ptr(), _stream())
-        _lib.check(rc, "ssim")
+            _SSIM._fwd(x, y, B, C, H, W, window, out, maps)
         ctx.save_for_backward(x, y)
-        ctx.maps, ctx.dims, ctx.size_average, ctx.need2 = maps, (B, C, H, W), size_average, need2
+        ctx.maps, ctx.dims, ctx.size_average, ctx.need2, ctx.window = maps, (B, C, H, W), size_average, need2, window
         if size_average:
             return out.mean() if B > 1 else out.reshape(())
         if x.dim() != 4:
@@ -113,26 +136,23 @@ class _SSIM(torch.autograd.Function):
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:
                 g1 = torch.empty_like(x)
-                rc = _L().hg_ssim_backward(x.data_ptr(), y.data_ptr(), ctx.maps.data_ptr(), gs.data_ptr(), B, C, H, W,
-                                           g1.data_ptr(), _stream())
-                _lib.check(rc, "ssim_backward")
+                _SSIM._bwd(x, y, ctx.maps, gs, B, C, H, W, ctx.window, g1)
             if ctx.need2:  # SSIM is symmetric in its arguments: swap roles for d/d img2
                 out = torch.empty(B, dtype=torch.float32, device=x.device)
                 maps = torch.empty((3,) + tuple(x.shape), dtype=torch.float32, device=x.device)
-                ws = _ws(_L().hg_ssim_workspace_bytes(B, C, H, W), x.device)
-                rc = _L().hg_ssim(y.data_ptr(), x.data_ptr(), B, C, H, W, out.data_ptr(), maps.data_ptr(), ws.data_ptr(), _stream())
-                _lib.check(rc, "ssim")
+                _SSIM._fwd(y, x, B, C, H, W, ctx.window, out, maps)
                 g2 = torch.empty_like(x)
-                rc = _L().hg_ssim_backward(y.data_ptr(), x.data_ptr(), maps.data_ptr(), gs.data_ptr(), B, C, H, W,
-                                           g2.data_ptr(), _stream())
-                _lib.check(rc, "ssim_backward")
-        return g1, g2, None
+                _SSIM._bwd(y, x, maps, gs, B, C, H, W, ctx.window, g2)
+        return g1, g2, None, None
 
 
 def ssim(img1, img2, window_size=11, size_average=True):
-    if window_size != 11:
-        raise NotImplementedError("hidegs_b200.ssim implements the reference's default 11x11 window only")
-    return _SSIM.apply(img1, img2, size_average)
+    window_size = int(window_size)
+    if window_size < 1 or window_size > 63 or window_size % 2 == 0:
+        # an even window makes the reference's conv2d(padding=window_size // 2) return maps one pixel larger than the
+        # images; no call site uses one
+        raise ValueError("hidegs_b200.ssim: window_size must be odd and in 1..63 (got %d)" % window_size)
+    return _SSIM.apply(img1, img2, size_average, window_size)
 
 
 def get_img_grad_weight(img, beta=2.0):

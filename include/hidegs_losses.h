@@ -71,6 +71,16 @@ HG_API int hg_ssim(const float *img1, const float *img2, int32_t B, int32_t C, i
 HG_API int hg_ssim_backward(const float *img1, const float *img2, const float *maps, const float *gscale,
                             int32_t B, int32_t C, int32_t H, int32_t W, float *grad_img1, void *stream);
 
+/* ssim(img1, img2, window_size) for any odd window_size in 1..63 (loss_utils.py:24-64 with a non-default window;
+ * hg_ssim / hg_ssim_backward are the tiled kernels of the default 11).  Same outputs and derivative maps; `workspace` of
+ * hg_ssim_window_workspace_bytes() bytes is needed by both calls (its contents need not survive between them). */
+HG_API size_t hg_ssim_window_workspace_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+HG_API int hg_ssim_window(const float *img1, const float *img2, int32_t B, int32_t C, int32_t H, int32_t W,
+                          int32_t window_size, float *out, float *maps, void *workspace, void *stream);
+HG_API int hg_ssim_window_backward(const float *img1, const float *img2, const float *maps, const float *gscale,
+                                   int32_t B, int32_t C, int32_t H, int32_t W, int32_t window_size, float *grad_img1,
+                                   void *workspace, void *stream);
+
 /* get_img_grad_weight: img [C,H,W] -> out [H,W] (border = 1.0). */
 HG_API size_t hg_img_grad_weight_workspace_bytes(int32_t H, int32_t W);
 HG_API int hg_img_grad_weight(const float *img, int32_t C, int32_t H, int32_t W, float *out,

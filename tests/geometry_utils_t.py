@@ -48,3 +48,9 @@ def make_geometry_inputs(n, H, W, seed):
     return dict(xyz=xyz, scaling=scaling, rotation=rotation, view=view, campos=campos, g_all_map=g_all_map, depth=depth,
                 alpha=alpha, g_normal=g_normal, K=K, out_all_map=out_all_map, image_weight=image_weight, adam_p=adam_p,
                 adam_g=adam_g, adam_rel=adam_rel)
+
+
+def sample_offsets(H, W, seed):
+    """Per-pixel sampling offsets for render_normal(offset=...): four 2-D displacements of up to +-0.8 pixel."""
+    g = torch.Generator().manual_seed(seed + 77)
+    return (torch.rand(H, W, 8, generator=g) - 0.5) * 1.6

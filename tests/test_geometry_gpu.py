@@ -65,6 +65,27 @@ def test_depth_normal_epilogue(cuda_device, name):
     assert rel(depth.grad.cpu().numpy(), ref["depth_normal_grad"]) <= 1e-3
 
 
+@pytest.mark.parametrize("name", sorted(gt.GEOMETRY_CASES))
+def test_render_normal_with_offsets_vs_reference_golden(cuda_device, name):
+    """render_normal(offset=...) (gaussian_renderer/__init__.py:21-33, graphics_utils.py:130-150): normals and both
+    gradients against the reference's own normal_from_depth_image (tests/golden/api_extras_ref.npz)."""
+    from hidegs_b200 import gaussian_renderer as gr
+    p = gt.GEOMETRY_CASES[name]
+    c = gt.make_geometry_inputs(**p)
+    ref = np.load(os.path.join(GOLD, "api_extras_ref.npz"))
+    dev = cuda_device
+    depth = c["depth"].to(dev).requires_grad_(True)
+    off = gt.sample_offsets(p["H"], p["W"], p["seed"]).to(dev).requires_grad_(True)
+    n = gr.render_normal(Cam(c["K"], p["W"], p["H"]), depth, offset=off)
+    # 3e-4: the normals are normalised cross products of DIFFERENCES of interpolated points (|p| ~ 5, |dp| ~ 0.01), so one
+    # ulp of a point is ~1e-4 of a normal component; the same expression evaluated on the CPU agrees to 5e-6, the GPU's
+    # fused multiply-adds in grid_sample move 18 of 14 k components by 1e-4 .. 1.5e-4
+    assert np.abs(n.detach().cpu().numpy() - ref["normal_offset_%s" % name]).max() <= 3e-4
+    (n * c["g_normal"].to(dev)).sum().backward()
+    assert rel(depth.grad.cpu().numpy(), ref["normal_offset_%s_grad_depth" % name]) <= 1e-3
+    assert rel(off.grad.cpu().numpy(), ref["normal_offset_%s_grad_offset" % name]) <= 1e-3
+
+
 def test_depth_normal_full_size_vs_oracle(cuda_device):
     from hidegs_b200 import gaussian_renderer as gr
     H, W = 1080, 1920

@@ -108,8 +108,26 @@ def test_ssim_gradient_wrt_second_image_and_batch(cuda_device):
     v.backward()
     assert abs(v.item() - lo.ssim(x, y).item()) < 1e-5
     assert grad_ok(xd.grad.cpu().numpy(), xo.grad.numpy()) and grad_ok(yd.grad.cpu().numpy(), yo.grad.numpy())
-    with pytest.raises(NotImplementedError):
-        hlu.ssim(xd, yd, window_size=7)
+    with pytest.raises(ValueError):  # an even window changes the map size in the reference; none is used
+        hlu.ssim(xd, yd, window_size=8)
+
+
+@pytest.mark.parametrize("window", [3, 7, 15])
+def test_ssim_other_window_sizes_vs_reference_golden(cuda_device, window):
+    """ssim(window_size != 11): values and gradients of the reference's own ssim (tests/golden/api_extras_ref.npz,
+    generated by make_api_extras_golden.py) and symmetry of the gradient w.r.t. the second image vs the oracle."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "api_extras_ref.npz"))
+    inp = lt.make_loss_inputs(**lt.LOSS_CASES["near_odd"])
+    dev = cuda_device
+    r = inp["render"].to(dev).requires_grad_(True)
+    gt_d = inp["gt"].to(dev).requires_grad_(True)
+    v = hlu.ssim(r, gt_d, window_size=window)
+    v.backward()
+    assert abs(v.item() - float(gold["ssim_w%d" % window])) < 1e-5
+    assert rel(r.grad.cpu().numpy(), gold["ssim_w%d_grad" % window]) < 1e-3
+    ro, go_ = inp["render"].clone().requires_grad_(True), inp["gt"].clone().requires_grad_(True)
+    lo.ssim(ro, go_, window_size=window).backward()
+    assert rel(gt_d.grad.cpu().numpy(), go_.grad.numpy()) < 1e-3
 
 
 def test_losses_reject_cpu_tensors():
