@@ -559,7 +559,8 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
         scene = syn.make_scene(n_gauss, seed=0)
         cams_all = [camera_for(r, s).to(dev) for r in range(8) for s in range(8)]
     total_views = views_per_rank * world
-    cams = cams_all[:total_views][rank::world]
+    my_views = list(range(total_views))[rank::world]
+    cams = [cams_all[i] for i in my_views]
     gts = make_gt_images(views_per_rank, dev, seed=11 + rank)
     # the model stores its Gaussians along a Morton curve (a one-off permutation at load time; results are invariant)
     spatial = os.environ.get("HG_BENCH_SPATIAL_ORDER", "1") != "0"
@@ -596,9 +597,31 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    balance = None
+    if ddp and os.environ.get("HG_BENCH_BALANCE", "1") != "0":
+        # Re-shard the step's views by the cost the warm-up measured (num_rendered per view): the ranks meet at the
+        # gradient exchange, so the step runs at the pace of the rank with the heaviest views.
+        mine = list(zip(my_views, trainer.last_view_costs))
+        table = [None] * world
+        dist.all_gather_object(table, mine)
+        cost = [0] * total_views
+        for part in table:
+            for i, c in part:
+                cost[i] = c
+        before = [sum(cost[i] for i in list(range(total_views))[r::world]) for r in range(world)]
+        shards = tr.balance_views(cost, world)
+        after = [sum(cost[i] for i in sh) for sh in shards]
+        balance = {"num_rendered_per_rank_before": before, "num_rendered_per_rank_after": after}
+        my_views = shards[rank]
+        cams[:] = [cams_all[i] for i in my_views]
+        trainer._gt_cache.clear()
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
     if ddp:
         dist.barrier()
     _lib.lib().hg_reset_launch_count()
+    trainer.timing = []
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
     for _ in range(steps):
@@ -608,19 +631,30 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     if ddp:
         dist.barrier()
     last = float(loss.item())
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    # where the step goes on this rank: its views (render + losses + backward), then exchange + union + Adam
+    t_views = sum(e[0].elapsed_time(e[1]) for e in trainer.timing) / steps
+    t_tail = sum(e[1].elapsed_time(e[2]) for e in trainer.timing) / steps
+    trainer.timing = None
+    t = torch.tensor([e0.elapsed_time(e1), t_views, -t_views, t_tail, -t_tail], device=dev)
     if ddp:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t) / steps
+    ms_step = float(t[0]) / steps
+    phases = {"views_ms_max_over_ranks": round(float(t[1]), 3), "views_ms_min_over_ranks": round(-float(t[2]), 3),
+              "exchange_union_adam_ms_max": round(float(t[3]), 3), "exchange_union_adam_ms_min": round(-float(t[4]), 3),
+              "note": "per rank, CUDA events: start -> last view's backward queued work done -> Adam done; the tail of a "
+                      "rank that finishes its views early includes its wait for the slowest rank at the exchange"}
+    if balance is not None:
+        phases["balance"] = balance
     return {"views_per_s": round(total_views / (ms_step * 1e-3), 2), "ms_per_step": round(ms_step, 3),
             "ms_per_view": round(ms_step / views_per_rank, 3), "views_per_rank_per_step": views_per_rank,
             "views_per_step": total_views, "gaussians": n_gauss, "steps": steps, "warmup": warmup,
             "loss_last_step_rank0": round(last, 6), "gpu_launches": int(_lib.lib().hg_launch_count()),
             "ground_truth_cache": bool(cache_gt), "gaussian_layout": "morton order" if spatial else "as generated",
-            "allreduce_bytes_per_step": params.grad_arena.numel() * 4 if world > 1 else 0,
+            "allreduce_bytes_per_step": params.grad_arena.numel() * 4 if world > 1 else 0, "phases": phases,
             "h2d_bytes_per_step": views_per_rank * 3 * HEIGHT * WIDTH * 4,
             "workload": ("configs[4]: view-sharded training, %d UAV survey cameras per step over the 2M-Gaussian slab, %dx%d, "
-                         "views[rank::world], one fp32 gradient all-reduce + fused Adam per step" % (total_views, WIDTH, HEIGHT))
+                         "views sharded over the ranks (views[rank::world], then re-sharded by measured num_rendered), one fp32 gradient "
+                         "all-reduce + fused Adam per step" % (total_views, WIDTH, HEIGHT))
             if recipe == "uav" else
             ("configs[3]: full HiDeGS training step (L1 + SSIM + frequency + scale reg + single-view normal term) on the "
              "config-2 scene with %d Gaussians, %d view(s) per step" % (n_gauss, total_views))}

@@ -103,7 +103,7 @@ class _SSIM(torch.autograd.Function):
         _lib.check(rc, "ssim_backward")
 
     @staticmethod
-    def forward(ctx, img1, img2, size_average, window):
+    def forward(ctx, img1, img2, size_average, window=11):
         _check_cuda(img1, img2)
         if img1.shape != img2.shape or img1.dim() not in (3, 4):
             raise RuntimeError("ssim: expected two (C,H,W) or (B,C,H,W) tensors of the same shape")

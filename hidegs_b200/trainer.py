@@ -265,6 +265,49 @@ class ArenaAdam:
                                  mask, None, 0, lr, 0.9, 0.999, self.eps, self.step_count, grad_scale, head_cols, head_lr, st)
 
 
+def balance_views(costs, world):
+    """Shard `len(costs)` views over `world` ranks with equal counts and near-equal summed cost.  `costs[i]`: predicted
+    cost of view i, e.g. its num_rendered from an earlier visit — the blend kernels' time is proportional to it.
+    Start: the better of views[rank::world] and longest-processing-time-first with a per-rank capacity; then pairwise
+    swaps between the heaviest rank and the others while they lower the larger of the two loads.  Returns one sorted
+    index list per rank; every rank computes the same assignment from the same table."""
+    n = len(costs)
+    c = [float(x) for x in costs]
+    room = [n // world + (1 if r < n % world else 0) for r in range(world)]
+    lpt = [[] for _ in range(world)]
+    load = [0.0] * world
+    for i in sorted(range(n), key=lambda k: (-c[k], k)):
+        r = min((q for q in range(world) if len(lpt[q]) < room[q]), key=lambda q: (load[q], q))
+        lpt[r].append(i)
+        load[r] += c[i]
+    strided = [list(range(n))[r::world] for r in range(world)]
+    total = lambda sh: [sum(c[i] for i in s) for s in sh]  # noqa: E731
+    out = lpt if max(total(lpt)) <= max(total(strided)) else strided
+    load = total(out)
+    for _ in range(4 * n):
+        h = max(range(world), key=lambda q: (load[q], -q))
+        best = None
+        for r in range(world):
+            if r == h:
+                continue
+            for a in out[h]:
+                for b in out[r]:
+                    d = c[a] - c[b]
+                    if d <= 0:
+                        continue
+                    worst = max(load[h] - d, load[r] + d)
+                    if worst < load[h] and (best is None or worst < best[0]):
+                        best = (worst, r, a, b)
+        if best is None:
+            break
+        _w, r, a, b = best
+        out[h][out[h].index(a)] = b
+        out[r][out[r].index(b)] = a
+        load[h] -= c[a] - c[b]
+        load[r] += c[a] - c[b]
+    return [sorted(x) for x in out]
+
+
 class ViewShardedTrainer:
     def __init__(self, params: GaussianParams, background, opt=OptimizationParams, pipe=PipelineParams, group=None,
                  sparse_adam=True, densification_stats=False, cache_ground_truth=False, start_iteration=0):
@@ -424,14 +467,20 @@ class ViewShardedTrainer:
             if tSc is not None:
                 g_sc = torch.addcmul(g_sc, tSc.grad, tT.partials[2])
             _ActivateParams.backward(tA, g_xyz, g_sh, g_op, g_sc, g_rot)
-        return loss, {"visibility_filter": visible, "radii": radii, "means2D_grad": g_means2D}
+        return loss, {"visibility_filter": visible, "radii": radii, "means2D_grad": g_means2D,
+                      "num_rendered": int(tR.num_rendered)}
 
     def step(self, views, total_views=None):
         """One optimiser step over this rank's `views` = [(camera, gt_image[, gt_ready_event]), ...]; returns the summed
         loss tensor."""
         self.iteration += 1
+        timing = getattr(self, "timing", None)  # optional list: (start, views done, step done) CUDA events per step
+        if timing is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         self.params.zero_grad()
         total = None
+        self.last_view_costs = []
         if self.sparse_adam:
             self.visible.zero_()
         for view in views:
@@ -450,6 +499,9 @@ class ViewShardedTrainer:
                     self.visible.index_fill_(0, vf, 1)
             if self.densification_stats:
                 self._add_densification_stats(pkg)
+            self.last_view_costs.append(pkg.get("num_rendered", 0) if isinstance(pkg, dict) else 0)
+        if timing is not None:
+            ev[1].record()
         self.params.begin_view()
         if self.params.fused and not self.params._grad_dirty:  # no view produced a gradient
             self.params.grad_arena.zero_()
@@ -468,6 +520,9 @@ class ViewShardedTrainer:
                 dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
                 n_views = int(round(float(cnt.item())))
         self.adam.step(grad_scale=1.0 / max(n_views, 1), visible_mask=self.visible if self.sparse_adam else None)
+        if timing is not None:
+            ev[2].record()
+            timing.append(ev)
         return total
 
     def _add_densification_stats(self, pkg):

@@ -104,3 +104,19 @@ def test_morton_order_is_a_locality_preserving_permutation():
     step_raw = (xyz[1:] - xyz[:-1]).norm(dim=1).mean()
     assert float(step_sorted) < 0.25 * float(step_raw)
     assert torch.equal(morton_order(xyz), order)  # deterministic (stable sort)
+
+
+def test_balance_views_equal_counts_and_near_equal_cost():
+    from hidegs_b200.trainer import balance_views
+    import random
+    rnd = random.Random(0)
+    for world, n in ((2, 8), (8, 64), (4, 10), (3, 9)):
+        costs = [rnd.randint(1, 1000) for _ in range(n)]
+        shards = balance_views(costs, world)
+        assert sorted(i for s in shards for i in s) == list(range(n))
+        sizes = [len(s) for s in shards]
+        assert max(sizes) - min(sizes) <= 1
+        loads = [sum(costs[i] for i in s) for s in shards]
+        naive = [sum(costs[i] for i in range(n)[r::world]) for r in range(world)]
+        assert max(loads) <= max(naive)
+        assert balance_views(costs, world) == shards  # deterministic: every rank computes the same table
