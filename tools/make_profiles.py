@@ -11,7 +11,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
+ROUND = "Round %d" % int(TAG[1:])
 
 
 def agg(path):
@@ -45,13 +46,13 @@ def copy(src, dst):
 
 
 def launches():
-    if not copy("launches_r1b.csv", "%s_launches.csv" % TAG):
+    if not copy("%s_launches.csv" % TAG, "%s_launches.csv" % TAG):
         return
     a = agg(os.path.join(P, "%s_launches.csv" % TAG))
     tot = sum(v[1] for v in a.values())
     d = json.load(open(os.path.join(P, "%s_bench_ours.json" % TAG)))
-    L = ["# Round 1 — ncu launch list of `HG_BENCH_SKIP_TRAIN=1 python bench.py --steps 2 --warmup 3` (B200, 1M Gaussians, 1080p)\n",
-         "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv`",
+    L = ["# %s — ncu launch list of `HG_BENCH_SKIP_TRAIN=1 python bench.py --steps 2 --warmup 3` (B200, 1M Gaussians, 1080p)\n" % ROUND,
+         "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv`",
          "(cold-cache, serialised: compare SHARES).  The capture covers the resident-leg steps and the first steps of the e2e leg",
          "(with torch's elementwise kernels of its L1 loss).\n",
          "| kernel | launches | total us | avg us | share | DRAM read MB/launch | DRAM write MB/launch |", "|---|---:|---:|---:|---:|---:|---:|"]
@@ -65,10 +66,12 @@ def launches():
              ", ".join("%s %.3f ms (%.1f %%)" % (k, v, 100 * v / ssum) for k, v in st.items()) + ".")
     rast = sum(v[1] for k, v in a.items() if "hg::" in k or "cub" in k.lower())
     sh = lambda sub: sum(v[1] for k, v in a.items() if sub in k) / rast  # noqa: E731
-    L.append("Shares inside the rasterizer's own kernels (ncu): blend_bwd %.3f, blend_fwd %.3f, radix sorts %.3f, preprocess_bwd "
-             "%.3f, preprocess_fwd %.3f — they agree with the live stage shares above (blend_bwd %.3f, blend_fwd %.3f)." %
-             (sh("blend_bwd"), sh("blend_fwd"), sh("RadixSort"), sh("preprocess_bwd"), sh("preprocess_fwd"),
-              st["blend_bwd"] / ssum, st["blend_fwd"] / ssum))
+    L.append("Shares inside the rasterizer's own kernels (ncu): blend_bwd %.3f, blend_fwd %.3f, tile_sort %.3f, scatter %.3f, "
+             "tile_scan %.3f, preprocess_bwd %.3f, preprocess_fwd %.3f — they agree with the live stage shares above (blend_bwd "
+             "%.3f, blend_fwd %.3f).  Library kernels among the rasterizer's launches: %s." %
+             (sh("blend_bwd"), sh("blend_fwd"), sh("tile_sort"), sh("scatter_instances"), sh("tile_scan"), sh("preprocess_bwd"),
+              sh("preprocess_fwd"), st["blend_bwd"] / ssum, st["blend_fwd"] / ssum,
+              ", ".join(sorted(set(short(k)[:40] for k in a if "cub" in k.lower()))) or "none (no cub:: symbol)"))
     open(os.path.join(P, "%s_launches_summary.md" % TAG), "w").write("\n".join(L) + "\n")
     tr = {}
     tp = os.path.join(P, "ncu_traffic.json")
@@ -93,7 +96,7 @@ def table(src, dst, title, note, n_iter):
     open(os.path.join(P, dst + "_summary.md"), "w").write("\n".join(L) + "\n")
 
 
-def blend_full(rep):
+def full_capture(rep, dst, what, cmd, traffic_keys=False):
     path = os.path.join(G, rep)
     if not os.path.exists(path):
         return
@@ -107,7 +110,9 @@ def blend_full(rep):
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
             "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_global_red.sum", "lts__t_sector_hit_rate.pct",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "smsp__inst_executed_op_global_red.sum", "lts__t_sector_hit_rate.pct",
             "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
             "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -117,10 +122,9 @@ def blend_full(rep):
             "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio"]
     kn = hdr.index("Kernel Name")
     kern = rows[2:]
-    names = [r[kn].split("(")[0].split("::")[-1] for r in kern]
-    L = ["# Round 1 — `ncu --set full --clock-control none --import-source on -k regex:blend_` (B200)\n",
-         "Source: gpurun_out/%s (not tracked), one launch of each blend kernel inside `HG_BENCH_SKIP_TRAIN=1 python bench.py --steps 2" % rep,
-         "--warmup 3` (1M Gaussians, 1920x1080, R = 5.42 M tile instances, geometry + depth outputs on).\n",
+    names = [r[kn].split("(")[0].split("::")[-1].replace("void ", "")[:28] for r in kern]
+    L = ["# %s — `ncu --set full --clock-control none --import-source on` (B200): %s\n" % (ROUND, what),
+         "Source: gpurun_out/%s (not tracked), one launch of each kernel inside `%s`.\n" % (rep, cmd),
          "| metric | " + " | ".join(names) + " | unit |", "|---|" + "---:|" * len(names) + "---|"]
     vals = {}
     for w in want:
@@ -128,31 +132,45 @@ def blend_full(rep):
             i = hdr.index(w)
             L.append("| %s | %s | %s |" % (w, " | ".join(r[i] for r in kern), units[i]))
             vals[w] = [r[i] for r in kern]
-    open(os.path.join(P, "%s_ncu_blend_full.md" % TAG), "w").write("\n".join(L) + "\n\n" + open(os.path.join(P, "%s_ncu_blend_reading.md" % TAG)).read()
-                                                                  if os.path.exists(os.path.join(P, "%s_ncu_blend_reading.md" % TAG)) else "\n".join(L) + "\n")
+    extra = os.path.join(P, dst.replace(".md", "_reading.md"))
+    body = "\n".join(L) + "\n"
+    if os.path.exists(extra):
+        body += "\n" + open(extra).read()
+    open(os.path.join(P, dst), "w").write(body)
+    if not traffic_keys:
+        return
     tp = os.path.join(P, "ncu_traffic.json")
     tr = json.load(open(tp)) if os.path.exists(tp) else {}
-    key = lambda n: "blend_fwd" if "fwd" in n else "blend_bwd"  # noqa: E731
-    tr["_issue_active_pct"] = {key(n): float(v) for n, v in zip(names, vals["smsp__issue_active.avg.pct_of_peak_sustained_active"])}
-    tr["_warp_instructions"] = {key(n): float(v) for n, v in zip(names, vals["smsp__inst_executed.sum"])}
+    ia, wi = tr.get("_issue_active_pct", {}), tr.get("_warp_instructions", {})
+    for n, a_, w_ in zip(names, vals["smsp__issue_active.avg.pct_of_peak_sustained_active"], vals["smsp__inst_executed.sum"]):
+        for key in ("blend_fwd", "blend_bwd"):
+            if key in n:
+                ia[key], wi[key] = float(a_), float(w_.replace(",", ""))
+    tr["_issue_active_pct"], tr["_warp_instructions"] = ia, wi
     json.dump(tr, open(tp, "w"), indent=1)
 
 
 def main():
     os.makedirs(P, exist_ok=True)
-    copy("bench_r1_final.json", "%s_bench_ours.json" % TAG)
-    copy("bench_r1_final_ref.json", "%s_bench_reference.json" % TAG)
-    copy("bench_n2b.json", "%s_bench_ours_n2.json" % TAG)
+    copy("%s_bench.json" % TAG, "%s_bench_ours.json" % TAG)
+    copy("%s_bench_ref.json" % TAG, "%s_bench_reference.json" % TAG)
+    copy("%s_hier_probe.json" % TAG, "%s_hier_probe.json" % TAG)
+    for n in (2, 4, 8):
+        copy("%s_n%d.json" % (TAG, n), "%s_bench_ours_n%d.json" % (TAG, n))
     launches()
-    table("loss_launches2.csv", "%s_loss_launches" % TAG,
-          "# Round 1 — ncu launch list of the loss path: `python tools/loss_bench.py --no-cpu --iters 3 --warmup 2` (B200)",
+    table("%s_loss_launches.csv" % TAG, "%s_loss_launches" % TAG,
+          "# %s — ncu launch list of the loss path: `python tools/loss_bench.py --no-cpu --iters 3 --warmup 2` (B200)" % ROUND,
           "One iteration = L1 + SSIM + frequency_regularization_pyramid_scale forward + backward on a 3x1080x1920 pair (BASELINE "
-          "configs[0]); the capture holds 11 iterations.", 11)
-    table("train_launches2.csv", "%s_train_launches" % TAG,
-          "# Round 1 — ncu launch list of the training step: `python tools/train_probe.py --recipe c2 --steps 2` (B200)",
+          "configs[0]); the capture holds 11 iterations (full path 5 + per-function passes).", 11)
+    table("%s_train_launches.csv" % TAG, "%s_train_launches" % TAG,
+          "# %s — ncu launch list of the training step: `python tools/train_probe.py --recipe c2 --steps 2` (B200)" % ROUND,
           "Config 3 (config-2 scene at 2M Gaussians, 1080p, one view per step: render + all losses + backward + Adam); the capture "
-          "starts after 400 launches and holds about 2.5 steps.", 2.5)
-    blend_full("prof_blend_r1c.ncu-rep")
+          "starts after 300 launches and holds 400 launches.", 1.0)
+    full_capture("%s_prof_raster.ncu-rep" % TAG, "%s_ncu_raster_full.md" % TAG, "the rasterizer's kernels",
+                 "HG_BENCH_SKIP_TRAIN=1 python bench.py --steps 2 --warmup 3` (1M Gaussians, 1920x1080, R = 5.42 M tile instances, "
+                 "geometry + depth outputs on", traffic_keys=True)
+    full_capture("%s_prof_loss.ncu-rep" % TAG, "%s_ncu_loss_full.md" % TAG, "the loss path's heaviest kernels",
+                 "python tools/loss_bench.py --no-cpu --iters 2 --warmup 1` (3x1080x1920")
 
 
 if __name__ == "__main__":
