@@ -304,10 +304,11 @@ def run_gpu_arm(args, impl):
     gt_host = torch.rand(3, HEIGHT, WIDTH, generator=gen).pin_memory()
     cam_host = [torch.cat([c.world_view_transform.flatten().cpu(), c.full_proj_transform.flatten().cpu(),
                            c.camera_center.cpu()]).pin_memory() for c in cams]
-    # linear probes: mean(x * 1e-3 g) written as one dot product each (weights pre-divided by the element count)
-    w_geo_flat = (g["all_map"] * (1e-3 / g["all_map"].numel())).reshape(-1).contiguous()
-    w_pd_flat = (g["plane_depth"] * (1e-3 / g["plane_depth"].numel())).reshape(-1).contiguous()
-    w_inv_flat = (g["invdepth"] * (1e-3 / g["invdepth"].numel())).reshape(-1).contiguous()
+    # the other outputs receive FIXED upstream gradients (d/dx of mean(x * 1e-3 g)) through torch.autograd.backward's
+    # grad_tensors: every output of the rasterizer carries a gradient, without probe kernels in the timed region
+    w_geo = (g["all_map"] * (1e-3 / g["all_map"].numel())).contiguous()
+    w_pd = (g["plane_depth"] * (1e-3 / g["plane_depth"].numel())).contiguous()
+    w_inv = (g["invdepth"] * (1e-3 / g["invdepth"].numel())).contiguous()
     if impl == "ours":
         from hidegs_b200.loss_utils import l1_loss as l1
     else:
@@ -360,10 +361,10 @@ def run_gpu_arm(args, impl):
                                                                      params["rotations"], am_param)
         main.wait_event(gt_ready)
         # L1 through each side's own loss function (the reference's utils/loss_utils.l1_loss is torch.abs(a - b).mean();
-        # ours is the fused drop-in of the same name), plus three fixed linear probes that feed the other outputs
-        loss = (l1(color, gt) + torch.dot(amap.reshape(-1), w_geo_flat) + torch.dot(pdepth.reshape(-1), w_pd_flat)
-                + torch.dot(inv.reshape(-1), w_inv_flat))
-        loss.backward()
+        # ours is the fused drop-in of the same name); the geometry / depth outputs get their fixed upstream gradients
+        loss = l1(color, gt)
+        torch.autograd.backward([loss, amap, pdepth, inv], [None, w_geo.view_as(amap), w_pd.view_as(pdepth),
+                                                            w_inv.view_as(inv)])
         gt_free[s & 1].record(main)
         if ddp:
             pack_and_allreduce((None, None, params["opacity"].grad, params["means3D"].grad, None, params["shs"].grad,
@@ -461,7 +462,7 @@ def run_gpu_arm(args, impl):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "d2h": ("loss read with a blocking .item() every step" if blocking_readback else
                         "loss copied to pinned host memory every step (non-blocking), consumed one step later"),
-                "api": "GaussianRasterizer(settings)(...) + l1_loss (each side's own utils.loss_utils.l1_loss) + autograd backward; ground-truth upload on a copy "
+                "api": "GaussianRasterizer(settings)(...) + l1_loss (each side's own utils.loss_utils.l1_loss) + torch.autograd.backward (fixed upstream gradients for all_map / plane_depth / invdepth); ground-truth upload on a copy "
                        "stream, overlapped with the forward",
                 "timed_passes": "5 x K steps, median pass reported",
                 "ms_per_step_min_median_max": [round(min(passes) / K, 4), round(float(np.median(passes)) / K, 4),

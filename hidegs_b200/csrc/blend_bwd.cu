@@ -105,17 +105,31 @@ constexpr int kAStride = 68;              // floats per A row: 64 pixels + 4 pad
 template <bool INTERP>
 struct alignas(16) BwdMmaSmem {
   float4 rec[kWarpsC][32 * kRecQuadsC];   // per-WARP staging of the 32 entries a round looks at (see the main loop)
-  alignas(16) float a_w[kWarpsC][kGroupC * kAStride]; // wgt, row-major [entry][k]; k = 2 lane + {0: pixel A, 1: pixel B}
-  float a_p[kWarpsC][kGroupC * kAStride]; // p, same layout
+  // wgt, row-major [entry][k]; k = 2 lane + {0: pixel A, 1: pixel B}.  The four pad floats of a row (columns 64..67, never
+  // read by ldmatrix) hold the row's first meta quad (x, y, conic a, b):
+  alignas(16) float a_w[kWarpsC][kGroupC * kAStride];
+  // p, same layout; pad = the second meta quad (conic c, opacity, sum of the third per-pair scalar [INTERP], slot id).
+  // One address per parked row reaches all four stores with immediate offsets.
+  float a_p[kWarpsC][kGroupC * kAStride];
   float2 b_ch0[kWarpsC][8][32];           // channels 0..7 of the warp's pixels, fragment order: (b0, b1) per lane
   float2 b_ch8[kWarpsC][8][4];            // channel 8 (column 0 of its n-tile: the lanes with g == 0)
   float2 zero2;                           // what the lanes with g != 0 read instead
   float2 b_mom[8][32];                    // the six moments, fragment order (same for every warp)
-  float4 meta[kWarpsC][kGroupC][2];       // per row: (x, y, conic a, b), (conic c, opacity, -, slot id)
   // hierarchy interpolation only (last, so that the layout above is the same in both variants):
   float2 tf[INTERP ? kWarpsC : 1][INTERP ? 32 : 1];        // (t, 1 / kids) of the staged entries
-  float p3[INTERP ? kWarpsC : 1][INTERP ? kGroupC : 1];   // per-row sum of the third per-pair scalar
+  uint32_t info[kWarpsC][32];             // per staged entry: list position | kHasA | kHasB (which halves it can reach)
 };
+constexpr uint32_t kHasA = 1u << 30, kHasB = 1u << 31;
+constexpr uint32_t kARowBytes = kAStride * 4;
+constexpr uint32_t kAPOffset = kWarpsC * kGroupC * kAStride * 4;  // from a row of a_w to the same row of a_p
+constexpr uint32_t kMetaOffset = 64 * 4;                          // from a row's start to its pad quad
+
+__device__ __forceinline__ void sts_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // A-operand quad (a0, a1, a2, a3) of mma.m16n8k8 for one k-step straight from a row-major fp32 tile: each of the four
 // 8x8 "b16" matrices of ldmatrix is 8 rows x 16 bytes = 8 rows x 4 fp32, and lane l receives word (l / 4, l % 4) —
@@ -310,6 +324,10 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const float2* const b8_src = fg == 0 ? &sm.b_ch8[warp][0][ft] : &sm.zero2;  // + 4 * k-step for g == 0
   const int b8_step = fg == 0 ? 4 : 0;
   int rows = 0;  // entries parked in the A tile
+  // shared-space address of this lane's (pixel A, pixel B) pair in row 0 of a_w.  Opaque to the optimiser: under the
+  // 128-register cap it otherwise re-derives the address from S2R (thread id, shared window) for every parked entry.
+  uint32_t park_base;
+  asm volatile("mov.u32 %0, %1;" : "=r"(park_base) : "r"((uint32_t)__cvta_generic_to_shared(a_w + 2 * lane)));
 
   // Reduce the parked rows over the warp's 64 pixels and add them to the accumulator rows.
   auto flush = [&]() {
@@ -370,11 +388,11 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     for (int h = 0; h < 2; ++h) {
       const int row = fg + 8 * h;
       if (row < rows) {
-        const float4 m1 = sm.meta[warp][row][1];
+        const float4 m1 = *reinterpret_cast<const float4*>(a_p + row * kAStride + 64);
         float* const arow = accum + (size_t)__float_as_int(m1.w) * HG_ACC_FLOATS;
         red_add_v2(arow + 2 * ft, dc0[2 * h], dc0[2 * h + 1]);
         if (ft == 0) {
-          const float4 m0 = sm.meta[warp][row][0];
+          const float4 m0 = *reinterpret_cast<const float4*>(a_w + row * kAStride + 64);
           const float S1 = dm[2 * h], Sx = dm[2 * h + 1];
           const float u = m0.x - cx, v = m0.y - cy, o = m1.y;
           const float Dx = u * S1 - Sx, Dy = v * S1 - Sy[h];                 // sum p dx, sum p dy
@@ -385,7 +403,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
           const float g10 = -ddely_dy * (m1.x * Dy + m0.w * Dx);
           red_add_v4(arow + 8, dc8[2 * h], g9, g10, -0.5f * Qxx);
           red_add_v2(arow + 12, -0.5f * Qxy, -0.5f * Qyy);
-          atomicAdd(arow + 14, __fdividef(INTERP ? sm.p3[warp][row] : S1, o));
+          atomicAdd(arow + 14, __fdividef(INTERP ? m1.z : S1, o));
         }
       }
     }
@@ -400,51 +418,57 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   // four warps of a tile re-read the same records from L2 (4x the gather traffic of a CTA-wide staging, ~1.9 GB per
   // view, far from the L2 limit) and in exchange never wait for each other: no __syncthreads, no idle tail per batch.
   float4* const w_rec = sm.rec[warp];
+  uint32_t* const w_info = sm.info[warp];
+  const uint32_t lanes_below = (1u << lane) - 1u;
   Prefetch pf;
   auto prefetch = [&](int base) {
     const int q = base - lane;
     if (q >= 0) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + q);
   };
   if (wmax > 0) prefetch(wmax - 1);
+  // (Measured and dropped: fetching the list's slot ids one round further ahead than the records, so that the record
+  // loads never wait for the list read — 1.036 vs 1.022 ms, one more live register.)
 
   for (int base = wmax - 1; base >= 0; base -= 32) {
     const int q_mine = base - lane;
     bool keepA = false, keepB = false;
+    const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
     if (q_mine >= 0) {
-      const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
       const float tau = cull_tau(a, bb, c, o, INTERP);
       keepA = q_mine < wmaxA && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyA0, fyA1);
       keepB = q_mine < wmaxB && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyB0, fyB1);
-      if (keepA || keepB) {
-        float4* d = w_rec + kRecQuadsC * lane;
-        d[0] = pf.r0;
-        d[1] = make_float4(c, o, pf.r3.z, __int_as_float(pf.id));
-        d[2] = make_float4(pf.r1.z, pf.r1.w, pf.r2.x, pf.r2.y);
-        if (GEO) d[3] = make_float4(pf.r2.z, pf.r2.w, pf.r3.x, pf.r3.y);
-        if (INTERP) sm.tf[warp][lane] = make_float2(pf.it, pf.ifrac);
-      }
     }
     const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
+    const uint32_t mask = maskA | maskB;
+    if (keepA || keepB) {  // survivors are parked densely, in list order: the blend loop below is a plain counted loop
+      const int slot = __popc(mask & lanes_below);
+      float4* d = w_rec + kRecQuadsC * slot;
+      d[0] = pf.r0;
+      d[1] = make_float4(c, o, pf.r3.z, __int_as_float(pf.id));
+      d[2] = make_float4(pf.r1.z, pf.r1.w, pf.r2.x, pf.r2.y);
+      if (GEO) d[3] = make_float4(pf.r2.z, pf.r2.w, pf.r3.x, pf.r3.y);
+      if (INTERP) sm.tf[warp][slot] = make_float2(pf.it, pf.ifrac);
+      w_info[slot] = (uint32_t)q_mine | (keepA ? kHasA : 0u) | (keepB ? kHasB : 0u);
+    }
     __syncwarp();
     if (base >= 32) prefetch(base - 32);
-    uint32_t mask = maskA | maskB;
     // (Measured and dropped: software-pipelining this loop by one entry — next entry's first two quads fetched while the
     // current one is evaluated — 1.27 vs 1.09 ms: eight more live registers at the 128-register cap cost more than the
     // short-scoreboard stalls they remove.)
-    while (mask) {
-      const int bit = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int q = base - bit;
-      const float4* e = w_rec + kRecQuadsC * bit;
+    const int cnt = __popc(mask);
+    for (int i = 0; i < cnt; ++i) {
+      const float4* e = w_rec + kRecQuadsC * i;
+      const uint32_t info = w_info[i];
       const float4 ea = e[0];
       const float4 eb = e[1];
       const float4 ec = e[2];      float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
       if (GEO) ed = e[3];
       float2 tf = make_float2(1.f, 1.f);
-      if (INTERP) tf = sm.tf[warp][bit];
+      if (INTERP) tf = sm.tf[warp][i];
+      const int q = (int)(info & (kHasA - 1u));
+      const bool hasA = (info & kHasA) != 0u, hasB = (info & kHasB) != 0u;
       float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f, p3A = 0.f, p3B = 0.f;
       bool any, near = false;
-      const bool hasA = (maskA >> bit) & 1u, hasB = (maskB >> bit) & 1u;
       // state before this entry (only read again on the rare redo below)
       const float A_T = A.T, A_acc = A.acc_g, A_lg = A.last_g, A_la = A.last_alpha;
       const float B_T = B.T, B_acc = B.acc_g, B_lg = B.last_g, B_la = B.last_alpha;
@@ -467,17 +491,18 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
         if (hasB) any |= pixel_pair_c<GEO, DEPTH, INTERP, true>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
       }
       if (__ballot_sync(0xffffffffu, any) == 0) continue;
+      float s3 = eb.z;
       if (INTERP) {  // the third scalar only needs its plain sum over the 64 pixels: one butterfly, no third A tile
-        float s3 = p3A + p3B;
+        s3 = p3A + p3B;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-        if (lane == 0) sm.p3[warp][rows] = s3;
       }
-      *reinterpret_cast<float2*>(a_w + rows * kAStride + 2 * lane) = make_float2(wA, wB);
-      *reinterpret_cast<float2*>(a_p + rows * kAStride + 2 * lane) = make_float2(pA, pB);
+      const uint32_t row_addr = park_base + rows * kARowBytes;
+      sts_v2(row_addr, wA, wB);
+      sts_v2(row_addr + kAPOffset, pA, pB);
       if (lane == 0) {
-        sm.meta[warp][rows][0] = ea;
-        sm.meta[warp][rows][1] = eb;
+        sts_v4(row_addr + kMetaOffset, ea.x, ea.y, ea.z, ea.w);
+        sts_v4(row_addr + kAPOffset + kMetaOffset, eb.x, eb.y, s3, eb.w);
       }
       if (++rows == kGroupC) flush();
     }
