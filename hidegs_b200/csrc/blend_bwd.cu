@@ -265,6 +265,18 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                                all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
                                dL_invdepths);
 
+  // last contributor of each half and of the tile; the slot id of this lane's first list entry is requested right away
+  // so that the list read (and, behind it, the record gather) overlaps the construction of the B tiles
+  int wmaxA = A.last_contributor, wmaxB = B.last_contributor;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wmaxA = max(wmaxA, __shfl_xor_sync(0xffffffffu, wmaxA, o));
+    wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
+  }
+  const int wmax = max(wmaxA, wmaxB);
+  int first_id = 0;
+  if (wmax - 1 - lane >= 0) first_id = (int)__ldg(point_list + range.x + (wmax - 1 - lane));
+
   // ---- constant B tiles.  K index of a pixel: k = 2 lane + {0: pixel A, 1: pixel B} of the lane that owns it; k-step
   // s covers k = 8 s .. 8 s + 7, and fragment lane (g, t) holds b0 = B[8 s + t][g], b1 = B[8 s + t + 4][g].
   {
@@ -305,14 +317,6 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     }
   }
 
-  // last contributor of each half and of the tile
-  int wmaxA = A.last_contributor, wmaxB = B.last_contributor;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    wmaxA = max(wmaxA, __shfl_xor_sync(0xffffffffu, wmaxA, o));
-    wmaxB = max(wmaxB, __shfl_xor_sync(0xffffffffu, wmaxB, o));
-  }
-  const int wmax = max(wmaxA, wmaxB);
   __syncthreads();  // the B tiles are complete; from here on the warps of the CTA never synchronise with each other
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
@@ -425,7 +429,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     const int q = base - lane;
     if (q >= 0) gather_record<INTERP>(pf, point_list, records, ts, kids, range.x + q);
   };
-  if (wmax > 0) prefetch(wmax - 1);
+  if (wmax - 1 - lane >= 0) gather_record_id<INTERP>(pf, first_id, records, ts, kids);
   // (Measured and dropped: fetching the list's slot ids one round further ahead than the records, so that the record
   // loads never wait for the list read — 1.036 vs 1.022 ms, one more live register.)
 
