@@ -188,8 +188,15 @@ def run_gpu_arm(args, impl):
 
     # With an NVSwitch multicast mapping the backward writes its gradients straight into symmetric memory and the
     # exchange is ONE in-fabric kernel (hg_nvls_allreduce_f32); otherwise NCCL sums the arena in place.
-    exchange = None
-    if ddp and parallel.prefer_nvls(dev):
+    # Default (HG_EXCHANGE_FACTORED=0 restores the whole-arena sum): the SH block does not travel.  dL/dSH of a view is
+    # the outer product of the SH basis at the view direction with three clamp-masked colour gradients, so the backward
+    # writes those three factors, the ranks all-gather them (12 B per Gaussian and rank) and all-reduce only the 11
+    # non-SH floats, and every rank rebuilds the summed SH rows locally (parallel.FactoredExchange): (44 + 12 world) B
+    # per Gaussian through the fabric instead of 236 B.
+    exchange = factored = None
+    if ddp and os.environ.get("HG_EXCHANGE_FACTORED", "1") == "1":
+        factored = parallel.FactoredExchange(N_GAUSS, dev, 16, arena_numel=N_GAUSS * 80)
+    elif ddp and parallel.prefer_nvls(dev):
         exchange = parallel.SymmetricArena(N_GAUSS * 80, dev)   # 80 floats / Gaussian: the whole backward arena
 
     # Opt-in (HG_EXCHANGE_OVERLAP=1): overlapped with the per-Gaussian backward — preprocess_bwd is issued in 2 slot
@@ -238,16 +245,56 @@ def run_gpu_arm(args, impl):
                 "vs": "torch.distributed.all_reduce (NCCL) of the same seeded per-rank pattern, %d floats" % n,
                 "kernel": "hg_nvls_allreduce_f32" if exchange is not None else "ncclAllReduce"}
 
-    xcheck = exchange_check() if ddp else None
-    if xcheck is not None and not (xcheck["replicas_identical"] and xcheck["max_abs_err"] <= 1e-5 * xcheck["max_abs_value"]):
-        raise SystemExit("gradient exchange check failed: %s" % json.dumps(xcheck))
+    def factored_check():
+        """The same check for the factored exchange, end to end on this rank's first view: plain backward + NCCL
+        all_reduce of the 59-float arena against factor backward + FactoredExchange.finish."""
+        n = 59 * N_GAUSS
+        cams[0].to(dev)
+        fa = op_tuple(C, scene, cams[0], all_maps[0], dev, bg)
+        fwd = C.rasterize_gaussians(*fa)
+        p = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g))
+        want = torch.cat([p[3].reshape(-1), p[5].reshape(-1), p[2].reshape(-1), p[6].reshape(-1), p[7].reshape(-1)])
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g), **factored.backward_kwargs())
+        got = factored.finish(scene["means3D"], 3)[:n]
+        torch.cuda.synchronize()
+        err = (got - want).abs().max().reshape(1)
+        scale = want.abs().max().reshape(1)
+        rel_l2 = ((got - want).double().norm() / want.double().norm()).float().reshape(1)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rel_l2, op=dist.ReduceOp.MAX)
+        first = got.clone()
+        dist.broadcast(first, src=0)
+        same = torch.tensor([1.0 if torch.equal(first, got) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        # two runs of the backward differ by the order of their atomic adds (~1e-7 relative per element, more on the few
+        # largest ones), so the gate is the relative L2 error of the whole arena plus a loose bound on the worst element
+        return {"max_abs_err": float(err), "max_abs_value": float(scale), "rel_l2_err": float(rel_l2),
+                "replicas_identical": bool(same.item() == 1.0), "tolerance": {"rel_l2_err": 1e-5, "max_abs_err_over_max": 1e-4},
+                "vs": "plain backward + torch.distributed.all_reduce (NCCL) of the 59-float arena, %d floats, each rank "
+                      "its own view" % n,
+                "kernel": ("hg_nvls_exchange_f32" if factored.symmetric is not None else
+                           "ncclAllReduce x2 + ncclAllGather") + " + hg_sh_gradient_from_factors"}
+
+    xcheck = (factored_check() if factored is not None else exchange_check()) if ddp else None
+    if xcheck is not None:
+        ok = xcheck["replicas_identical"]
+        if "rel_l2_err" in xcheck:
+            ok = ok and xcheck["rel_l2_err"] <= 1e-5 and xcheck["max_abs_err"] <= 1e-4 * xcheck["max_abs_value"]
+        else:
+            ok = ok and xcheck["max_abs_err"] <= 1e-5 * xcheck["max_abs_value"]
+        if not ok:
+            raise SystemExit("gradient exchange check failed: %s" % json.dumps(xcheck))
 
     # ------------------------------------------------ device-resident leg ("value")
     def step_resident(s):
         cam = cams[s]
         fa = op_tuple(C, scene, cam, all_maps[0], dev, bg)
         fwd = C.rasterize_gaussians(*fa)
-        if overlap is not None:
+        if factored is not None:
+            grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g), **factored.backward_kwargs())
+            factored.finish(scene["means3D"], 3)
+        elif overlap is not None:
             grads = C.rasterize_gaussians_backward(*bwd_tuple(fa, fwd, g), **overlap.backward_kwargs())
             overlap.finish()
         else:
@@ -298,7 +345,10 @@ def run_gpu_arm(args, impl):
     if impl == "ours":
         from hidegs_b200.diff_gaussian_rasterization import GaussianRasterizer
     params = {k: scene[k].clone().requires_grad_(True) for k in ("means3D", "shs", "opacity", "scales", "rotations")}
-    if exchange is not None:  # the autograd backward of every e2e step writes its gradients into the symmetric arena
+    if factored is not None:  # the autograd backward writes into the exchange's arena, the SH block as factors
+        params["means3D"]._hg_grad_arena = factored.tensor
+        params["shs"]._hg_grad_factor = factored.my_factors
+    elif exchange is not None:  # the autograd backward of every e2e step writes its gradients into the symmetric arena
         params["means3D"]._hg_grad_arena = exchange.tensor
     gen = torch.Generator().manual_seed(7)
     gt_host = torch.rand(3, HEIGHT, WIDTH, generator=gen).pin_memory()
@@ -366,7 +416,9 @@ def run_gpu_arm(args, impl):
         torch.autograd.backward([loss, amap, pdepth, inv], [None, w_geo.view_as(amap), w_pd.view_as(pdepth),
                                                             w_inv.view_as(inv)])
         gt_free[s & 1].record(main)
-        if ddp:
+        if factored is not None:
+            factored.finish(params["means3D"].detach(), 3)
+        elif ddp:
             pack_and_allreduce((None, None, params["opacity"].grad, params["means3D"].grad, None, params["shs"].grad,
                                 params["scales"].grad, params["rotations"].grad))
         # D2H read of the step's result: copied into pinned memory every step; the host consumes it one step later
@@ -452,6 +504,13 @@ def run_gpu_arm(args, impl):
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "visible": Nv, "num_rendered": R,
                    "outputs": "color+all_map+plane_depth+invdepth", "parallelism": "view-sharded dp%d" % world,
                    "exchange": (None if not ddp else
+                                ("factored: %s; %d B per Gaussian through the fabric instead of 236"
+                                 % ("ONE in-fabric kernel (hg_nvls_exchange_f32: 11 non-SH floats summed with "
+                                    "multimem.ld_reduce, 3 colour-gradient factors per rank gathered with multimem.st)"
+                                    if factored.symmetric is not None else
+                                    "nccl all_reduce of the 11 non-SH floats + all_gather of 3 colour-gradient factors "
+                                    "per rank", 44 + 12 * world)
+                                 + ", SH rows rebuilt locally (hg_sh_gradient_from_factors)") if factored is not None else
                                 ("nvls multimem kernel, 236 MB arena, overlapped with preprocess_bwd in %d slot ranges"
                                  % overlap.n_chunks) if overlap is not None else
                                 "nvls multimem kernel (hg_nvls_allreduce_f32), 236 MB arena" if exchange is not None

@@ -66,6 +66,10 @@ struct ExRanges {  // in float4 units relative to the multicast base
   int64_t off4[kExMaxRanges];
   int64_t n4[kExMaxRanges];
   int n;
+  // all-gather part: every rank owns `gather_n4` float4 at gather_off4 + rank * gather_n4 of its replica and
+  // replicates them into every GPU (0 = none)
+  int64_t gather_off4;
+  int64_t gather_n4;
 };
 
 // This rank's 1/world share of one contiguous range.
@@ -86,11 +90,30 @@ __device__ __forceinline__ void reduce_share(float4* __restrict__ mc, const int6
   for (; i < end; i += stride) mc_st(mc + i, mc_ld_reduce(mc + i));
 }
 
+// This rank's slice of the gather range: plain loads from the local replica, multimem.st into every replica.
+template <int kExUnroll>
+__device__ __forceinline__ void gather_share(float4* __restrict__ mc, const float4* __restrict__ local, const int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * kExThreads;
+  int64_t i = (int64_t)blockIdx.x * kExThreads + threadIdx.x;
+  for (; i + (kExUnroll - 1) * stride < n4; i += kExUnroll * stride) {
+    float4 v[kExUnroll];
+#pragma unroll
+    for (int u = 0; u < kExUnroll; ++u) v[u] = local[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < kExUnroll; ++u) mc_st(mc + i + u * stride, v[u]);
+  }
+  for (; i < n4; i += stride) mc_st(mc + i, local[i]);
+}
+
 template <int kExUnroll>
 __global__ void __launch_bounds__(kExThreads)
-nvls_allreduce_kernel(float4* __restrict__ mc, const uint64_t* __restrict__ flag_ptrs, const int rank, const int world,
-                      const ExRanges ranges, const int tail) {
+nvls_allreduce_kernel(float4* __restrict__ mc, const float4* __restrict__ local, const uint64_t* __restrict__ flag_ptrs,
+                      const int rank, const int world, const ExRanges ranges, const int tail) {
   rank_barrier(flag_ptrs, rank, world);  // every replica of the ranges is complete
+  if (ranges.gather_n4) {
+    const int64_t o = ranges.gather_off4 + ranges.gather_n4 * rank;
+    gather_share<kExUnroll>(mc + o, local + o, ranges.gather_n4);
+  }
   for (int r = 0; r < ranges.n; ++r) reduce_share<kExUnroll>(mc + ranges.off4[r], ranges.n4[r], rank, world);
   if (tail && rank == 0 && blockIdx.x == 0 && (int)threadIdx.x < tail) {  // (single-range call with n % 4 floats left over)
     float* p = reinterpret_cast<float*>(mc + ranges.off4[0] + ranges.n4[0]) + threadIdx.x;
@@ -110,7 +133,7 @@ size_t hg_nvls_flag_words(int32_t world, int32_t max_blocks) {
   return (size_t)world * (size_t)max_blocks;
 }
 
-static int launch_exchange(void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
+static int launch_exchange(void* mc_ptr, const void* local_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
                            const hg::ExRanges& ranges, int tail, int32_t blocks, void* stream) {
   const int grid = blocks ? blocks : hg::kExDefaultBlocks;
   static const int unroll = [] {
@@ -119,7 +142,7 @@ static int launch_exchange(void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank
   }();
 #define HG_EX_LAUNCH(U_)                                                                  \
   hg::nvls_allreduce_kernel<U_><<<grid, hg::kExThreads, 0, (cudaStream_t)stream>>>(       \
-      (float4*)mc_ptr, flag_ptrs, rank, world, ranges, tail)
+      (float4*)mc_ptr, (const float4*)local_ptr, flag_ptrs, rank, world, ranges, tail)
   if (unroll >= 8) HG_EX_LAUNCH(8);
   else if (unroll >= 4) HG_EX_LAUNCH(4);
   else if (unroll >= 2) HG_EX_LAUNCH(2);
@@ -168,22 +191,29 @@ int hg_nvls_allreduce_f32(void* mc_ptr, float* local_ptr, const uint64_t* flag_p
   r.n = 1;
   r.off4[0] = 0;
   r.n4[0] = n_floats / 4;
-  return launch_exchange(mc_ptr, flag_ptrs, rank, world, r, (int)(n_floats % 4), blocks, stream);
+  return launch_exchange(mc_ptr, local_ptr, flag_ptrs, rank, world, r, (int)(n_floats % 4), blocks, stream);
 }
 
-int hg_nvls_allreduce_ranges_f32(void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world, int32_t n_ranges,
-                                 const int64_t* offsets, const int64_t* counts, int32_t blocks, void* stream) {
+static int exchange_ranges(const char* who, void* mc_ptr, const float* local_ptr, const uint64_t* flag_ptrs, int32_t rank,
+                           int32_t world, int32_t n_ranges, const int64_t* offsets, const int64_t* counts,
+                           int64_t gather_offset, int64_t gather_count, int32_t blocks, void* stream) {
   if (n_ranges < 0 || n_ranges > hg::kExMaxRanges || (n_ranges && (!offsets || !counts))) {
-    hg::set_error("hg_nvls_allreduce_ranges_f32: bad argument (%d ranges, at most %d)", n_ranges, hg::kExMaxRanges);
+    hg::set_error("%s: bad argument (%d ranges, at most %d)", who, n_ranges, hg::kExMaxRanges);
+    return HG_ERR_INVALID_ARG;
+  }
+  if (gather_offset < 0 || gather_count < 0 || (gather_offset & 3) || (gather_count & 3) ||
+      (gather_count && (!local_ptr || ((uintptr_t)local_ptr & 15)))) {
+    hg::set_error("%s: gather range (offset %lld, %lld floats per rank) must be multiples of 4 floats of a 16-byte "
+                  "aligned replica", who, (long long)gather_offset, (long long)gather_count);
     return HG_ERR_INVALID_ARG;
   }
   if (world == 1 && rank == 0) return HG_OK;
-  const int rc = check_exchange_args("hg_nvls_allreduce_ranges_f32", mc_ptr, flag_ptrs, rank, world, blocks);
+  const int rc = check_exchange_args(who, mc_ptr, flag_ptrs, rank, world, blocks);
   if (rc) return rc;
   hg::ExRanges r{};
   for (int i = 0; i < n_ranges; ++i) {
     if (offsets[i] < 0 || counts[i] < 0 || (offsets[i] & 3) || (counts[i] & 3)) {
-      hg::set_error("hg_nvls_allreduce_ranges_f32: range %d (offset %lld, count %lld) must be multiples of 4 floats", i,
+      hg::set_error("%s: range %d (offset %lld, count %lld) must be multiples of 4 floats", who, i,
                     (long long)offsets[i], (long long)counts[i]);
       return HG_ERR_INVALID_ARG;
     }
@@ -192,8 +222,23 @@ int hg_nvls_allreduce_ranges_f32(void* mc_ptr, const uint64_t* flag_ptrs, int32_
     r.n4[r.n] = counts[i] / 4;
     ++r.n;
   }
-  if (r.n == 0) return HG_OK;
-  return launch_exchange(mc_ptr, flag_ptrs, rank, world, r, 0, blocks, stream);
+  r.gather_off4 = gather_offset / 4;
+  r.gather_n4 = gather_count / 4;
+  if (r.n == 0 && r.gather_n4 == 0) return HG_OK;
+  return launch_exchange(mc_ptr, local_ptr, flag_ptrs, rank, world, r, 0, blocks, stream);
+}
+
+int hg_nvls_allreduce_ranges_f32(void* mc_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world, int32_t n_ranges,
+                                 const int64_t* offsets, const int64_t* counts, int32_t blocks, void* stream) {
+  return exchange_ranges("hg_nvls_allreduce_ranges_f32", mc_ptr, nullptr, flag_ptrs, rank, world, n_ranges, offsets,
+                         counts, 0, 0, blocks, stream);
+}
+
+int hg_nvls_exchange_f32(void* mc_ptr, const float* local_ptr, const uint64_t* flag_ptrs, int32_t rank, int32_t world,
+                         int32_t n_ranges, const int64_t* offsets, const int64_t* counts, int64_t gather_offset,
+                         int64_t gather_count, int32_t blocks, void* stream) {
+  return exchange_ranges("hg_nvls_exchange_f32", mc_ptr, local_ptr, flag_ptrs, rank, world, n_ranges, offsets, counts,
+                         gather_offset, gather_count, blocks, stream);
 }
 
 }  // extern "C"

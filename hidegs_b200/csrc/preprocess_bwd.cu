@@ -56,7 +56,7 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
                       float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D,
                       float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                       float* __restrict__ dL_drotations, float* __restrict__ dL_dall_map,
-                      float* __restrict__ sh_sink, const float sh_beta) {
+                      float* __restrict__ sh_sink, const float sh_beta, float* __restrict__ sh_factor) {
   // SH rows (read AND written, 2 x 192 B per Gaussian at degree 3: 60 % of this kernel's traffic) move through a
   // per-warp shared-memory tile with coalesced 128-bit accesses when the warp's rows are contiguous (no index
   // remap); each thread then works on its own row of the tile.
@@ -114,7 +114,8 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
     dL_dmeans3D[3 * g] = dL_dmeans3D[3 * g + 1] = dL_dmeans3D[3 * g + 2] = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) dL_dcov3D[6 * g + i] = 0.f;
-    if (!staged)
+    if (sh_factor) sh_factor[3 * g] = sh_factor[3 * g + 1] = sh_factor[3 * g + 2] = 0.f;
+    else if (!staged)
       for (int i = 0; i < row; ++i) dL_dsh[g * row + i] = 0.f;
     dL_dscales[3 * g] = dL_dscales[3 * g + 1] = dL_dscales[3 * g + 2] = 0.f;
     dL_drotations[4 * g] = dL_drotations[4 * g + 1] = dL_drotations[4 * g + 2] = dL_drotations[4 * g + 3] = 0.f;
@@ -328,12 +329,20 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
     if (nb > M) nb = M;
     // With a parent the reference zeroes the (48-float) SH gradient row again.
     const float keep = has_parent ? 0.f : 1.f;
-    for (int k = 0; k < M; ++k) {
-      const float bk = (k < nb) ? basis[k] * keep : 0.f;
-      if (k < nb || !prezeroed || staged) {
-        out[3 * k] = bk * dr;
-        out[3 * k + 1] = bk * dg;
-        out[3 * k + 2] = bk * db;
+    if (sh_factor) {
+      // factored exchange (include/hidegs_exchange.h): dL/dSH is the outer product basis(view direction) x dL/dRGB, so
+      // only the three clamp-masked colour gradients leave this kernel; hg_sh_gradient_from_factors rebuilds the rows
+      sh_factor[3 * g] = keep * dr;
+      sh_factor[3 * g + 1] = keep * dg;
+      sh_factor[3 * g + 2] = keep * db;
+    } else {
+      for (int k = 0; k < M; ++k) {
+        const float bk = (k < nb) ? basis[k] * keep : 0.f;
+        if (k < nb || !prezeroed || staged) {
+          out[3 * k] = bk * dr;
+          out[3 * k + 1] = bk * dg;
+          out[3 * k + 2] = bk * db;
+        }
       }
     }
     // d(normalised dir)/d(mean)  (auxiliary.h:132-142)
@@ -410,7 +419,9 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
     dL_drotations[4 * g + 3] = dqz;
   }
   } while (0);
-  if (staged && sh_sink) {  // accumulate straight into the caller's gradient arena (launcher guarantees `staged`)
+  if (sh_factor) {  // the view's camera centre rides behind the factors: [3 P .. 3 P + 2]
+    if (blockIdx.x == 0 && block0 == 0 && threadIdx.x < 3) sh_factor[3 * (size_t)P + threadIdx.x] = __ldg(campos + threadIdx.x);
+  } else if (staged && sh_sink) {  // accumulate straight into the caller's gradient arena (launcher guarantees `staged`)
     if (alive_mask || sh_beta == 0.f) {
       __syncwarp();
       unstage_sh_rows_accum(sh_sink, warp_base, sh_total, row, lane, tile, alive_mask, sh_beta);
@@ -421,7 +432,96 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
   }
 }
 
+// dL/dSH rows rebuilt from the factors of `n_views` views (factored gradient exchange, include/hidegs_exchange.h):
+//   dL_dsh[g][k][c] = beta * dL_dsh[g][k][c] + sum_v basis_k(normalize(mean_g - campos_v)) * factor_v[g][c]
+// with the basis expressions of the SH backward above, summed in view order (every rank forms the same bits).  Thread
+// per Gaussian, 3 M accumulators in registers, rows leave through the per-warp tile as coalesced 128-bit stores.
+__global__ void __launch_bounds__(kThreads)
+sh_from_factors_kernel(const int N, const int D, const int M, const int n_views, const float* __restrict__ means3D,
+                       const float* __restrict__ factors, const size_t view_stride, float* __restrict__ dL_dsh,
+                       const float beta, const bool vector_rows) {
+  __shared__ float s_sh[kWarps][32 * kShStrideMax];
+  const int g = blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = 3 * M;
+  float acc[48];
+#pragma unroll
+  for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+  if (g < N) {
+    const float mx = __ldg(means3D + 3 * (size_t)g), my = __ldg(means3D + 3 * (size_t)g + 1),
+                mz = __ldg(means3D + 3 * (size_t)g + 2);
+    for (int v = 0; v < n_views; ++v) {
+      const float* fv = factors + (size_t)v * view_stride;
+      const float dr = __ldg(fv + 3 * (size_t)g), dg = __ldg(fv + 3 * (size_t)g + 1), db = __ldg(fv + 3 * (size_t)g + 2);
+      if (dr == 0.f && dg == 0.f && db == 0.f) continue;  // culled (or fully clamped) in that view
+      const float ox = mx - __ldg(fv + 3 * (size_t)N), oy = my - __ldg(fv + 3 * (size_t)N + 1),
+                  oz = mz - __ldg(fv + 3 * (size_t)N + 2);
+      const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+      const float x = ox / len, y = oy / len, z = oz / len;
+      float basis[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) basis[k] = 0.f;
+      basis[0] = SH_C0;
+      if (D > 0) {
+        basis[1] = -SH_C1 * y;
+        basis[2] = SH_C1 * z;
+        basis[3] = -SH_C1 * x;
+        if (D > 1) {
+          const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+          basis[4] = SH_C2_0 * xy;
+          basis[5] = SH_C2_1 * yz;
+          basis[6] = SH_C2_2 * (2.f * zz - xx - yy);
+          basis[7] = SH_C2_3 * xz;
+          basis[8] = SH_C2_4 * (xx - yy);
+          if (D > 2) {
+            basis[9] = SH_C3_0 * y * (3.f * xx - yy);
+            basis[10] = SH_C3_1 * xy * z;
+            basis[11] = SH_C3_2 * y * (4.f * zz - xx - yy);
+            basis[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+            basis[13] = SH_C3_4 * x * (4.f * zz - xx - yy);
+            basis[14] = SH_C3_5 * z * (xx - yy);
+            basis[15] = SH_C3_6 * x * (xx - 3.f * yy);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        acc[3 * k] += basis[k] * dr;
+        acc[3 * k + 1] += basis[k] * dg;
+        acc[3 * k + 2] += basis[k] * db;
+      }
+    }
+  }
+  if (vector_rows) {
+    float* const tile = s_sh[warp];
+    float* const mine = tile + lane * (row | 1);
+#pragma unroll
+    for (int i = 0; i < 48; ++i)
+      if (i < row) mine[i] = acc[i];
+    __syncwarp();
+    const size_t warp_base = (size_t)(blockIdx.x * kThreads + warp * 32) * row;
+    if (warp_base < (size_t)N * row)
+      unstage_sh_rows_accum(dL_dsh, warp_base, (size_t)N * row, row, lane, tile, 0xffffffffu, beta);
+  } else if (g < N) {
+#pragma unroll
+    for (int i = 0; i < 48; ++i)
+      if (i < row) {
+        float* d = dL_dsh + (size_t)g * row + i;
+        *d = beta != 0.f ? fmaf(beta, *d, acc[i]) : acc[i];
+      }
+  }
+}
+
 }  // namespace
+
+int launch_sh_from_factors(int N, int D, int M, int n_views, const float* means3D, const float* factors,
+                           size_t view_stride, float* dL_dsh, float beta, cudaStream_t stream) {
+  const bool vector_rows = ((3 * M) & 3) == 0 && (reinterpret_cast<uintptr_t>(dL_dsh) & 15) == 0;
+  sh_from_factors_kernel<<<(N + kThreads - 1) / kThreads, kThreads, 0, stream>>>(N, D, M, n_views, means3D, factors,
+                                                                                view_stride, dL_dsh, beta, vector_rows);
+  HG_POST_LAUNCH(false, stream, "sh_from_factors");
+  return HG_OK;
+}
 
 int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const int* radii,
                           float focal_x, float focal_y, const float* accum, bool has_invdepth,
@@ -429,7 +529,7 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
                           float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                           float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
                           float* dL_drotations, float* dL_dall_map, cudaStream_t stream, int slot_begin,
-                          int slot_end, float* sh_sink, float sh_beta) {
+                          int slot_end, float* sh_sink, float sh_beta, float* sh_factor) {
   const bool prezeroed = in.indices != nullptr || in.parent_indices != nullptr;
   const float* cov = in.cov3D_precomp ? in.cov3D_precomp : g.cov3D;
   // [slot_begin, slot_end): the slots this launch covers (slot_begin a multiple of the block size; -1 = to the end)
@@ -442,6 +542,10 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
       return HG_ERR_INVALID_ARG;
     }
   }
+  if (sh_factor && (!in.shs || in.indices || in.parent_indices || sh_sink)) {
+    set_error("preprocess_bwd: SH gradient factors need SH input, no index remap and no SH sink");
+    return HG_ERR_INVALID_ARG;
+  }
   if (slot_begin % kThreads != 0 || slot_begin >= slot_end) {
     set_error("preprocess_bwd: bad slot range [%d, %d)", slot_begin, slot_end);
     return HG_ERR_INVALID_ARG;
@@ -451,7 +555,7 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
       in.opacities, in.scales, in.rotations, in.scale_modifier, cov, in.cov3D_precomp != nullptr,
       in.viewmatrix, in.projmatrix, in.campos, focal_x, focal_y, in.tan_fovx, in.tan_fovy, accum,
       has_invdepth, prezeroed, dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
-      dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map, sh_sink, sh_beta);
+      dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dall_map, sh_sink, sh_beta, sh_factor);
   HG_POST_LAUNCH(in.debug, stream, "preprocess_bwd");
   return HG_OK;
 }

@@ -3,6 +3,7 @@
 // Host-side orchestration that replaces CudaRasterizer::Rasterizer::forward /
 // backward (cuda_rasterizer/rasterizer_impl.cu:203-405, 409-535).
 #include "common.cuh"
+#include "../../include/hidegs_exchange.h"
 
 #include <cstdlib>
 
@@ -277,7 +278,7 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
   return hg_raster_backward_chunked(in, R, radii, geom_buffer, binning_buffer, image_buffer, all_map_pixels, dL_dpix,
                                     dL_dout_all_map, dL_dout_plane_depth, dL_dout_invdepth, accum, dL_dmeans2D, dL_dconic,
                                     dL_dopacity, dL_dcolors, dL_dinvdepths, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
-                                    dL_drotations, dL_dall_map, 1, nullptr, nullptr, nullptr, 0.f, stream_);
+                                    dL_drotations, dL_dall_map, 1, nullptr, nullptr, nullptr, 0.f, nullptr, stream_);
 }
 
 int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int32_t* radii,
@@ -289,7 +290,7 @@ int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int3
                                float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                                float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
                                float* dL_dall_map, int32_t n_chunks, hg_chunk_fn on_chunk, void* chunk_ctx,
-                               float* sh_sink, float sh_beta, void* stream_) {
+                               float* sh_sink, float sh_beta, float* sh_factor, void* stream_) {
   g_err[0] = 0;
   int rc = validate(in);
   if (rc) return rc;
@@ -342,7 +343,7 @@ int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int3
     rc = launch_preprocess_bwd(*in, g, radii, focal_x, focal_y, acc, dL_dout_invdepth != nullptr,
                                dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
                                dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
-                               dL_dall_map, stream, p0, p1, sh_sink, sh_beta);
+                               dL_dall_map, stream, p0, p1, sh_sink, sh_beta, sh_factor);
     if (rc) return rc;
     if (on_chunk) on_chunk(chunk_ctx, chunk, p0, p1, stream_);
   }
@@ -369,6 +370,20 @@ int hg_raster_debug_keys(int32_t P, int32_t W, int32_t H, int32_t R, const int32
   const dim3 grid((W + HG_BLOCK_X - 1) / HG_BLOCK_X, (H + HG_BLOCK_Y - 1) / HG_BLOCK_Y, 1);
   return launch_debug_keys(P, (int)(grid.x * grid.y), g, b, radii, R, grid, keys_unsorted, vals_unsorted, keys_sorted,
                            (cudaStream_t)stream_);
+}
+
+int hg_sh_gradient_from_factors(int32_t N, int32_t D, int32_t M, int32_t n_views, const float* means3D,
+                                const float* factors, int64_t view_stride, float* dL_dsh, float beta, void* stream_) {
+  g_err[0] = 0;
+  if (N < 0 || n_views < 0 || M <= 0 || M > 16 || D < 0 || (D + 1) * (D + 1) > M || view_stride < 3 * (int64_t)N + 3 ||
+      (N > 0 && (!means3D || !dL_dsh || (n_views > 0 && !factors)))) {
+    set_error("hg_sh_gradient_from_factors: bad argument (N %d, D %d, M %d, views %d, stride %lld)", N, D, M, n_views,
+              (long long)view_stride);
+    return HG_ERR_INVALID_ARG;
+  }
+  if (N == 0) return HG_OK;
+  return launch_sh_from_factors(N, D, M, n_views, means3D, factors, (size_t)view_stride, dL_dsh, beta,
+                                (cudaStream_t)stream_);
 }
 
 void hg_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }

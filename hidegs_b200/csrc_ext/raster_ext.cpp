@@ -12,6 +12,7 @@
 //   * ONE flat gradient arena per backward whose first 59 floats / Gaussian are xyz | sh | opacity | scale | rotation.
 // Per-call extensions (keyword arguments of rasterize_gaussians_backward; no module state):
 //   sh_sink / sh_beta   accumulate dL/dSH into a caller tensor (hg_raster_backward_chunked)
+//   sh_factor           write the three colour-gradient factors per Gaussian instead of the SH rows (factored exchange)
 //   grad_arena          caller-owned flat fp32 tensor the gradients are written into (e.g. multicast symmetric memory)
 //   n_chunks/chunk_hook issue the per-Gaussian backward in slot ranges and call hook(chunk, slot_begin, slot_end)
 #include <torch/extension.h>
@@ -247,7 +248,8 @@ py::tuple rasterize_gaussians_backward(torch::Tensor background, torch::Tensor a
                                        int64_t degree, torch::Tensor campos, torch::Tensor geomBuffer, int64_t R,
                                        torch::Tensor binningBuffer, torch::Tensor imageBuffer, bool render_geo, bool debug,
                                        c10::optional<torch::Tensor> sh_sink, double sh_beta,
-                                       c10::optional<torch::Tensor> grad_arena, int64_t n_chunks, py::object chunk_hook) {
+                                       c10::optional<torch::Tensor> grad_arena, int64_t n_chunks, py::object chunk_hook,
+                                       c10::optional<torch::Tensor> sh_factor) {
   const auto dev = means3D.device();
   background = f32(background, "bg"); viewmatrix = f32(viewmatrix, "viewmatrix"); projmatrix = f32(projmatrix, "projmatrix");
   campos = f32(campos, "campos"); means3D = f32(means3D, "means3D"); colors = f32(colors, "colors_precomp");
@@ -323,10 +325,20 @@ py::tuple rasterize_gaussians_backward(torch::Tensor background, torch::Tensor a
       sink_ptr = sh_sink->data_ptr<float>();
       sink_used = true;
     }
+    float* factor_ptr = nullptr;
+    if (sh_factor.has_value() && sh_factor->defined()) {
+      TORCH_CHECK(sh_factor->scalar_type() == torch::kFloat32 && sh_factor->is_contiguous() &&
+                      sh_factor->numel() >= 3 * fullP + 3 && sh_factor->device() == dev,
+                  "sh_factor must be a contiguous fp32 tensor of at least 3 N + 3 elements");
+      TORCH_CHECK(sh.numel() != 0 && indices.numel() == 0 && parent_indices.numel() == 0 && !sink_used,
+                  "SH gradient factors need SH input, no index remap and no SH sink");
+      factor_ptr = sh_factor->data_ptr<float>();
+      sink_used = true;  // the SH rows are not written: no dL_dsh is returned
+    }
     const bool hooked = !chunk_hook.is_none() && n_chunks > 0 && !prezero;
     ChunkCtx cctx{hooked ? chunk_hook : py::none(), nullptr};
     int rc;
-    if (sink_ptr || hooked) {
+    if (sink_ptr || factor_ptr || hooked) {
       rc = hg_raster_backward_chunked(
           &in, (int32_t)R, ptr<int32_t>(radii), reinterpret_cast<const char*>(geomBuffer.data_ptr()),
           reinterpret_cast<const char*>(binningBuffer.data_ptr()), reinterpret_cast<const char*>(imageBuffer.data_ptr()),
@@ -335,7 +347,7 @@ py::tuple rasterize_gaussians_backward(torch::Tensor background, torch::Tensor a
           mptr<float>(dL_dmeans2D), nullptr, mptr<float>(dL_dopacity), mptr<float>(dL_dcolors),
           has_depth_grad ? mptr<float>(dL_dinvdepths) : nullptr, mptr<float>(dL_dmeans3D), mptr<float>(dL_dcov3D),
           mptr<float>(dL_dsh), mptr<float>(dL_dscales), mptr<float>(dL_drotations), mptr<float>(dL_dall_map),
-          hooked ? (int32_t)n_chunks : 1, hooked ? on_chunk : nullptr, &cctx, sink_ptr, (float)sh_beta, stream);
+          hooked ? (int32_t)n_chunks : 1, hooked ? on_chunk : nullptr, &cctx, sink_ptr, (float)sh_beta, factor_ptr, stream);
       if (cctx.error) std::rethrow_exception(cctx.error);
     } else {
       rc = hg_raster_backward(
@@ -392,7 +404,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("dL_dout_plane_depth"), py::arg("dL_dout_invdepth"), py::arg("sh"), py::arg("degree"), py::arg("campos"),
         py::arg("geomBuffer"), py::arg("R"), py::arg("binningBuffer"), py::arg("imageBuffer"), py::arg("render_geo"),
         py::arg("debug"), py::arg("sh_sink") = py::none(), py::arg("sh_beta") = 0.0, py::arg("grad_arena") = py::none(),
-        py::arg("n_chunks") = 0, py::arg("chunk_hook") = py::none());
+        py::arg("n_chunks") = 0, py::arg("chunk_hook") = py::none(), py::arg("sh_factor") = py::none());
   m.def("mark_visible", &mark_visible);
   m.def("sh_sink_supported", &sh_sink_supported, py::arg("sh"), py::arg("indices") = py::none(),
         py::arg("parent_indices") = py::none());

@@ -42,6 +42,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         # extension: `means3D._hg_grad_arena = flat fp32 tensor` makes the backward of THIS call write its gradients
         # into that caller-owned arena (e.g. multicast symmetric memory of the data-parallel exchange)
         ctx.grad_arena = getattr(means3D, "_hg_grad_arena", None)
+        # extension: `sh._hg_grad_factor = flat fp32 tensor (>= 3 N + 3)` makes the backward of THIS call write the
+        # three colour-gradient factors per Gaussian there instead of the SH rows (parallel.FactoredExchange); autograd
+        # sees None for the SH gradient
+        factor = getattr(sh, "_hg_grad_factor", None)
+        ctx.sh_factor = (factor if factor is not None and ctx.sh_sink is None
+                         and _C.sh_sink_supported(sh, rs.render_indices, rs.parent_indices) else None)
         ctx.save_for_backward(out_all_map, colors_precomp, all_maps, means3D, scales, rotations, cov3Ds_precomp,
                               radii, sh, opacities, geomBuffer, binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii, out_observe)
@@ -72,7 +78,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.render_geo, rs.debug)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations, grad_all_map) = _C.rasterize_gaussians_backward(
-            *args, sh_sink=ctx.sh_sink() if ctx.sh_sink is not None else None, grad_arena=ctx.grad_arena)
+            *args, sh_sink=ctx.sh_sink() if ctx.sh_sink is not None else None, grad_arena=ctx.grad_arena,
+            sh_factor=ctx.sh_factor)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales,
                 grad_rotations, grad_cov3Ds_precomp, grad_all_map, None)
 

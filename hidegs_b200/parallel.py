@@ -13,7 +13,8 @@ import os
 import torch
 import torch.distributed as dist
 
-EXCHANGE_SYMBOLS = ("hg_nvls_flag_words", "hg_nvls_allreduce_f32", "hg_nvls_allreduce_ranges_f32")  # include/hidegs_exchange.h
+EXCHANGE_SYMBOLS = ("hg_nvls_flag_words", "hg_nvls_allreduce_f32", "hg_nvls_allreduce_ranges_f32", "hg_nvls_exchange_f32",
+                    "hg_sh_gradient_from_factors")  # include/hidegs_exchange.h
 _MAX_BLOCKS = 1024
 
 
@@ -85,6 +86,14 @@ def _exchange_lib():
         L.hg_nvls_allreduce_ranges_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                                    ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                                    ctypes.c_void_p]
+        L.hg_nvls_exchange_f32.restype = ctypes.c_int
+        L.hg_nvls_exchange_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]
+        L.hg_sh_gradient_from_factors.restype = ctypes.c_int
+        L.hg_sh_gradient_from_factors.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                  ctypes.c_float, ctypes.c_void_p]
         L._hg_exchange_ready = True
     return L
 
@@ -161,6 +170,104 @@ class SymmetricArena:
         _lib.check(L.hg_nvls_allreduce_ranges_f32(self._mc, self._flag_ptrs.data_ptr(), self.rank, self.world, n, off, cnt,
                                                   self.blocks, stream), "hg_nvls_allreduce_ranges_f32")
         return 4 * sum(int(c) for c in counts)
+
+
+    def exchange_(self, offsets, counts, gather_offset, gather_count):
+        """Sum the ranges AND all-gather one range (rank r owns `gather_count` floats at gather_offset + r * gather_count)
+        with one kernel on the current stream (hg_nvls_exchange_f32).  Returns the bytes this rank contributes."""
+        L = _exchange_lib()
+        from . import _lib
+        n = len(offsets)
+        off = (ctypes.c_int64 * max(n, 1))(*[int(o) for o in offsets])
+        cnt = (ctypes.c_int64 * max(n, 1))(*[int(c) for c in counts])
+        stream = torch.cuda.current_stream(self._buf.device).cuda_stream
+        _lib.check(L.hg_nvls_exchange_f32(self._mc, self._buf.data_ptr(), self._flag_ptrs.data_ptr(), self.rank,
+                                          self.world, n, off, cnt, int(gather_offset), int(gather_count), self.blocks,
+                                          stream), "hg_nvls_exchange_f32")
+        return 4 * (sum(int(c) for c in counts) + int(gather_count))
+
+
+def sh_gradient_from_factors(means3D, factors, n_views, view_stride, degree, dL_dsh, beta=0.0):
+    """dL_dsh[N, M, 3] = beta * dL_dsh + sum over the `n_views` factor blocks of basis(view direction) x factor
+    (hg_sh_gradient_from_factors, include/hidegs_exchange.h).  `factors`: flat fp32 tensor, block v at v * view_stride =
+    [N, 3] factors then the view's camera centre, as `rasterize_gaussians_backward(..., sh_factor=...)` writes them."""
+    L = _exchange_lib()
+    from . import _lib
+    if not (means3D.is_cuda and factors.is_cuda and dL_dsh.is_cuda):
+        raise RuntimeError("sh_gradient_from_factors needs CUDA tensors (there is no CPU path)")
+    N, M = int(dL_dsh.shape[0]), int(dL_dsh.shape[1])
+    assert means3D.is_contiguous() and factors.is_contiguous() and dL_dsh.is_contiguous()
+    assert factors.numel() >= (n_views - 1) * view_stride + 3 * N + 3
+    stream = torch.cuda.current_stream(means3D.device).cuda_stream
+    _lib.check(L.hg_sh_gradient_from_factors(N, int(degree), M, int(n_views), means3D.data_ptr(), factors.data_ptr(),
+                                             int(view_stride), dL_dsh.data_ptr(), float(beta), stream),
+               "hg_sh_gradient_from_factors")
+    return dL_dsh
+
+
+class FactoredExchange:
+    """Gradient exchange of a data-parallel step with ONE view per rank, with the SH block factored.
+
+    dL/dSH of one view is the outer product of the SH basis at the view direction (16 numbers that every rank can
+    compute from the Gaussian's mean and the view's camera centre) with three clamp-masked colour gradients, so the 48
+    SH floats per Gaussian need not travel: the backward writes the three factors (`sh_factor`), the ranks all-GATHER
+    them (12 bytes per Gaussian and rank) and all-REDUCE only the 11 non-SH floats (xyz 3 | opacity 1 | scale 3 |
+    rotation 4), and every rank rebuilds the summed SH rows locally (`hg_sh_gradient_from_factors`, views added in rank
+    order: identical bits on every rank).  (44 + 12 world) bytes per Gaussian through the fabric instead of 236.
+
+    Layout: one flat fp32 buffer [arena 59 N | factor blocks world x (3 N + 4)], in multicast symmetric memory where
+    `prefer_nvls` says so (the whole exchange is then ONE in-fabric kernel, hg_nvls_exchange_f32), otherwise a plain
+    tensor with two `all_reduce` and one `all_gather_into_tensor` (NCCL / gloo)."""
+
+    def __init__(self, n_gaussians, device, sh_coeffs=16, group=None, arena_numel=None):
+        """`arena_numel`: size of the gradient arena handed to the backward (default: the 59 trainable floats per
+        Gaussian; the raw operator wants its whole 80-float arena)."""
+        self.N, self.M = int(n_gaussians), int(sh_coeffs)
+        if self.N % 4 != 0:
+            raise ValueError("FactoredExchange needs a Gaussian count that is a multiple of 4 (got %d)" % self.N)
+        self.group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        N, M = self.N, self.M
+        self.param_numel = (3 + 3 * M + 1 + 3 + 4) * N
+        self.arena_numel = max(self.param_numel, int(arena_numel or 0))
+        self.block = 3 * N + 4                       # factors + camera centre + pad (a multiple of 4 floats)
+        self.factor_offset = (self.arena_numel + 1023) // 1024 * 1024
+        total = self.factor_offset + self.world * self.block
+        self.buffer, self.symmetric = make_exchange_arena(total, device, self.group)
+        self.tensor = self.buffer[:self.arena_numel]  # the gradient arena the backward writes (grad_arena=...)
+        self.factors = self.buffer[self.factor_offset:self.factor_offset + self.world * self.block]
+        self.my_factors = self.factors[self.rank * self.block:(self.rank + 1) * self.block]
+        # the two summed pieces of the SoA arena: xyz, and opacity | scale | rotation (contiguous)
+        self.reduce_offsets = (0, (3 + 3 * M) * N)
+        self.reduce_counts = (3 * N, 8 * N)
+        self.bytes = 0
+
+    def backward_kwargs(self):
+        """Keyword arguments for `_C.rasterize_gaussians_backward` of this rank's view."""
+        return dict(grad_arena=self.tensor, sh_factor=self.my_factors)
+
+    def finish(self, means3D, degree):
+        """Exchange + rebuild: afterwards `self.tensor` holds the summed gradients of all ranks' views."""
+        self.exchange()
+        return self.rebuild(means3D, degree)
+
+    def exchange(self):
+        """The communication half: non-SH blocks summed, factor blocks gathered."""
+        if self.symmetric is not None:
+            self.bytes += self.symmetric.exchange_(self.reduce_offsets, self.reduce_counts,
+                                                   self.factor_offset, self.block)
+        else:
+            for o, c in zip(self.reduce_offsets, self.reduce_counts):
+                dist.all_reduce(self.buffer[o:o + c], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_gather_into_tensor(self.factors, self.my_factors, group=self.group)
+            self.bytes += 4 * (sum(self.reduce_counts) + self.block)
+
+    def rebuild(self, means3D, degree):
+        """The local half: the summed SH rows from every rank's factors (one kernel)."""
+        N, M = self.N, self.M
+        sh = self.tensor[3 * N:(3 + 3 * M) * N].view(N, M, 3)
+        sh_gradient_from_factors(means3D, self.factors, self.world, self.block, degree, sh, beta=0.0)
+        return self.tensor
 
 
 class OverlappedBackwardExchange:

@@ -51,6 +51,25 @@ HG_API int hg_nvls_allreduce_ranges_f32(void *mc_ptr, const uint64_t *flag_ptrs,
                                         int32_t n_ranges, const int64_t *offsets, const int64_t *counts, int32_t blocks,
                                         void *stream);
 
+/* Factored exchange: all-reduce ranges AND one all-gather range in the same kernel (same barriers).  Rank r owns
+ * `gather_count` floats at gather_offset + r * gather_count of its replica (`local_ptr` = this rank's replica of
+ * mc_ptr[0]) and replicates them into every GPU with multimem.st; the ranges are summed as above.  Used for the step
+ * whose SH gradient travels as factors (hg_raster_backward_chunked's `sh_factor`): the 11 non-SH floats per Gaussian
+ * are summed, the 3 N + 4 factor floats of every rank's view are gathered, and every rank rebuilds the summed SH rows
+ * locally with hg_sh_gradient_from_factors — (44 + 12 world) bytes per Gaussian through the fabric instead of 236. */
+HG_API int hg_nvls_exchange_f32(void *mc_ptr, const float *local_ptr, const uint64_t *flag_ptrs, int32_t rank,
+                                int32_t world, int32_t n_ranges, const int64_t *offsets, const int64_t *counts,
+                                int64_t gather_offset, int64_t gather_count, int32_t blocks, void *stream);
+
+/* dL_dsh[g][k][c] = beta * dL_dsh[g][k][c] + sum_v basis_k(normalize(means3D[g] - campos_v)) * factor_v[g][c] over
+ * `n_views` factor blocks laid out `view_stride` floats apart: block v = [N, 3] factors followed by campos_v (3 floats),
+ * exactly what hg_raster_backward_chunked's `sh_factor` writes.  The basis is that of the reference's SH backward
+ * (cuda_rasterizer/backward.cu:23-142 with auxiliary.h:34-51), views are added in index order, so every rank that
+ * holds the same factor blocks forms the same bits.  beta: 0 (overwrite) or 1 (accumulate). */
+HG_API int hg_sh_gradient_from_factors(int32_t N, int32_t D, int32_t M, int32_t n_views, const float *means3D,
+                                       const float *factors, int64_t view_stride, float *dL_dsh, float beta,
+                                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,7 +185,12 @@ HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
  * `sh_sink` (optional, [N, M, 3], 16-byte aligned): the SH gradient is ACCUMULATED there, sink = sh_beta * sink + grad
  * (sh_beta 0 or 1), instead of being written to dL_dsh — the gradient arena of a multi-view training step, replacing
  * autograd's AccumulateGrad pass over the largest parameter block; rows of culled Gaussians are zero-filled when
- * sh_beta == 0 and not touched otherwise.  Needs SH input, no index remap and 3 M a multiple of 4. */
+ * sh_beta == 0 and not touched otherwise.  Needs SH input, no index remap and 3 M a multiple of 4.
+ * `sh_factor` (optional, [3 N + 4] floats; excludes sh_sink): the SH gradient rows are NOT written at all; instead the
+ * three clamp-masked colour gradients of every Gaussian go to sh_factor[3 g .. 3 g + 2] (zeros for culled slots) and
+ * the view's camera centre to sh_factor[3 N .. 3 N + 2].  dL/dSH is the outer product of the SH basis at the view
+ * direction with exactly these three numbers, so a data-parallel step ships 12 bytes per Gaussian and view instead of
+ * 192 and rebuilds the summed rows with hg_sh_gradient_from_factors (include/hidegs_exchange.h). */
 typedef void (*hg_chunk_fn)(void *chunk_ctx, int32_t chunk, int32_t slot_begin, int32_t slot_end, void *stream);
 HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        const int32_t *radii,
@@ -209,7 +214,8 @@ HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        float *dL_drotations, /* [N,4] */
                        float *dL_dall_map,   /* [N,5] */
                        int32_t n_chunks, hg_chunk_fn on_chunk,
-                                       void *chunk_ctx, float *sh_sink, float sh_beta, void *stream);
+                                       void *chunk_ctx, float *sh_sink, float sh_beta, float *sh_factor,
+                                       void *stream);
 
 /* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it buckets the
  * tile instances by tile (counts from the preprocess pass, one scan, one scatter) and sorts every tile's list by

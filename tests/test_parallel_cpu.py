@@ -88,3 +88,50 @@ def test_flat_view_detects_gaps_and_single_process_path():
     before = [g.clone() for g in grads]
     work, nbytes = parallel.allreduce_gradients(grads)  # no process group: a no-op
     assert work is None and nbytes == 59 * 16 * 4 and all(torch.equal(a, b) for a, b in zip(grads, before))
+
+
+def _factored_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N = 64
+        fx = parallel.FactoredExchange(N, "cpu")
+        assert fx.symmetric is None and fx.tensor.numel() == 59 * N and fx.block == 3 * N + 4
+        assert fx.factor_offset % 4 == 0 and fx.factors.numel() == world * fx.block
+        kw = fx.backward_kwargs()
+        assert kw["grad_arena"].data_ptr() == fx.buffer.data_ptr() and kw["sh_factor"].data_ptr() == fx.my_factors.data_ptr()
+
+        def fill(r):
+            g = torch.Generator().manual_seed(300 + r)
+            return torch.randn(59 * N, generator=g), torch.randn(fx.block, generator=g)
+        a, f = fill(rank)
+        fx.tensor.copy_(a)
+        fx.my_factors.copy_(f)
+        sh_before = fx.tensor[3 * N:51 * N].clone()
+        fx.exchange()
+        every = [fill(r) for r in range(world)]
+        total = sum(e[0] for e in every)
+        assert torch.allclose(fx.tensor[:3 * N], total[:3 * N], atol=1e-6)            # xyz summed
+        assert torch.allclose(fx.tensor[51 * N:], total[51 * N:], atol=1e-6)          # opacity | scale | rotation summed
+        assert torch.equal(fx.tensor[3 * N:51 * N], sh_before)                        # the SH block did not travel
+        for r in range(world):                                                        # every rank's factors gathered
+            assert torch.equal(fx.factors[r * fx.block:(r + 1) * fx.block], every[r][1])
+        assert fx.bytes == 4 * (11 * N + fx.block)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_factored_exchange_moves_only_the_non_sh_blocks_and_the_factors():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_factored_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

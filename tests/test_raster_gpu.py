@@ -456,6 +456,57 @@ def test_sh_gradient_sink_and_chunked_backward(cuda_device):
         ru.OUR_C.rasterize_gaussians_backward(*bh, sh_sink=(torch.zeros(hier["means3D"].shape[0], 16, 3, device=dev), 0.0))
 
 
+@pytest.mark.parametrize("degree", [3, 1])
+def test_sh_gradient_factors_rebuild_the_summed_rows(cuda_device, degree):
+    """Factored exchange (include/hidegs_exchange.h): with `sh_factor` the backward writes three colour-gradient factors
+    per Gaussian + the camera centre instead of the SH rows; hg_sh_gradient_from_factors over the blocks of several
+    views rebuilds exactly the sum of the rows the plain backward writes for those views; every other gradient is
+    untouched."""
+    from hidegs_b200 import parallel, synthetic as syn
+    dev = cuda_device
+    N, W, H = 9000, 176, 112
+    eyes = [(0.0, 0.0, -5.0), (1.5, 0.4, -4.5), (-2.0, -0.6, -4.0)]
+    block = 3 * N + 4
+    factors = torch.full((len(eyes) * block,), 3.0, device=dev)
+    want = None
+    some_dead = False
+    for v, eye in enumerate(eyes):
+        case = ru.build_case(N, W, H, seed=21, sh_degree=degree, eye=eye)
+        fa = ru.op_args(case, dev)
+        fwd = ru.OUR_C.rasterize_gaussians(*fa)
+        ba = ru.bwd_args(fa, fwd, syn.upstream_grads(W, H, seed=v), dev)
+        plain = [g.clone() for g in ru.OUR_C.rasterize_gaussians_backward(*ba)]
+        mine = factors[v * block:(v + 1) * block]
+        out = ru.OUR_C.rasterize_gaussians_backward(*ba, sh_factor=mine)
+        assert out[5] is None
+        for i in (0, 1, 2, 3, 4, 6, 7, 8):
+            ru.assert_grads_close([out[i]], [plain[i]], names=(ru.GRAD_NAMES[i],), what="factor mode, other grads")
+        dead = fwd[2] == 0
+        some_dead |= bool(dead.any())
+        assert float(mine[:3 * N].view(N, 3)[dead].abs().max()) == 0.0          # culled slots: zero factors
+        assert torch.equal(mine[3 * N:3 * N + 3], fa[21])                       # the view's camera centre rides along
+        # one view alone: the rebuilt rows are the plain rows (up to the FMA contraction of the basis polynomials)
+        single = torch.full_like(plain[5], 9.0)
+        parallel.sh_gradient_from_factors(fa[5], mine, 1, block, degree, single, beta=0.0)
+        ru.assert_grads_close([single], [plain[5]], names=("dL_dsh",), what="rebuilt rows, one view", l2_tol=1e-6, rtol=1e-5)
+        assert float(single[dead].abs().max()) == 0.0
+        want = plain[5].double() if want is None else want + plain[5].double()
+        means3D = fa[5]
+    assert some_dead
+    got = torch.full_like(plain[5], -1.0)
+    parallel.sh_gradient_from_factors(means3D, factors, len(eyes), block, degree, got, beta=0.0)
+    ru.assert_grads_close([got], [want.float()], names=("dL_dsh",), what="rebuilt sum", l2_tol=1e-6, rtol=1e-5)
+    acc = got.clone()
+    parallel.sh_gradient_from_factors(means3D, factors, len(eyes), block, degree, acc, beta=1.0)
+    ru.assert_grads_close([acc], [(2 * want).float()], names=("dL_dsh",), what="rebuilt sum, beta=1", l2_tol=1e-6, rtol=1e-5)
+    with pytest.raises(RuntimeError, match="factors"):  # an index remap cannot be factored
+        hier = ru.build_case(3000, 96, 64, seed=3, with_indices=True, with_hier=True)
+        fh = ru.op_args(hier, dev)
+        fw = ru.OUR_C.rasterize_gaussians(*fh)
+        bh = ru.bwd_args(fh, fw, syn.upstream_grads(96, 64), dev)
+        ru.OUR_C.rasterize_gaussians_backward(*bh, sh_factor=torch.zeros(3 * hier["means3D"].shape[0] + 4, device=dev))
+
+
 @pytest.mark.parametrize("degree", [3, 2])
 def test_sparse_view_zero_rows(cuda_device, degree):
     """A view that culls most Gaussians (R < 2 P): the zero rows of culled slots come from memsets, live rows from the
