@@ -659,9 +659,13 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     torch.cuda.synchronize()
     balance = None
     if ddp and os.environ.get("HG_BENCH_BALANCE", "1") != "0":
-        # Re-shard the step's views by the cost the warm-up measured (num_rendered per view): the ranks meet at the
-        # gradient exchange, so the step runs at the pace of the rank with the heaviest views.
-        mine = list(zip(my_views, trainer.last_view_costs))
+        # Re-shard the step's views by the cost one more warm-up step measures (device ms per view, CUDA events around
+        # every view): the ranks meet at the gradient exchange, so the step runs at the pace of the rank with the
+        # heaviest views.  (num_rendered alone left 13.2 - 14.4 ms across 8 ranks: the per-view cost is not only blend.)
+        trainer.time_views = True
+        step()
+        trainer.time_views = False
+        mine = list(zip(my_views, trainer.last_view_ms()))
         table = [None] * world
         dist.all_gather_object(table, mine)
         cost = [0] * total_views
@@ -671,7 +675,8 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
         before = [sum(cost[i] for i in list(range(total_views))[r::world]) for r in range(world)]
         shards = tr.balance_views(cost, world)
         after = [sum(cost[i] for i in sh) for sh in shards]
-        balance = {"num_rendered_per_rank_before": before, "num_rendered_per_rank_after": after}
+        balance = {"view_ms_per_rank_before": [round(x, 3) for x in before],
+                   "view_ms_per_rank_after": [round(x, 3) for x in after]}
         my_views = shards[rank]
         cams[:] = [cams_all[i] for i in my_views]
         trainer._gt_cache.clear()
@@ -713,7 +718,7 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
             "allreduce_bytes_per_step": params.grad_arena.numel() * 4 if world > 1 else 0, "phases": phases,
             "h2d_bytes_per_step": views_per_rank * 3 * HEIGHT * WIDTH * 4,
             "workload": ("configs[4]: view-sharded training, %d UAV survey cameras per step over the 2M-Gaussian slab, %dx%d, "
-                         "views sharded over the ranks (views[rank::world], then re-sharded by measured num_rendered), one fp32 gradient "
+                         "views sharded over the ranks (views[rank::world], then re-sharded by the measured device time per view), one fp32 gradient "
                          "all-reduce + fused Adam per step" % (total_views, WIDTH, HEIGHT))
             if recipe == "uav" else
             ("configs[3]: full HiDeGS training step (L1 + SSIM + frequency + scale reg + single-view normal term) on the "

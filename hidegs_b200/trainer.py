@@ -470,6 +470,16 @@ class ViewShardedTrainer:
         return loss, {"visibility_filter": visible, "radii": radii, "means2D_grad": g_means2D,
                       "num_rendered": int(tR.num_rendered)}
 
+    def last_view_ms(self):
+        """Device time of every view of the last step (needs `self.time_views = True` during that step; synchronises).
+        The cost table for `balance_views` when the same views come round again: time is not exactly proportional to
+        num_rendered (losses and per-Gaussian kernels are per view, list lengths matter)."""
+        marks = getattr(self, "_view_marks", None)
+        if not marks:
+            return []
+        marks[-1].synchronize()
+        return [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - 1)]
+
     def step(self, views, total_views=None):
         """One optimiser step over this rank's `views` = [(camera, gt_image[, gt_ready_event]), ...]; returns the summed
         loss tensor."""
@@ -481,6 +491,10 @@ class ViewShardedTrainer:
         self.params.zero_grad()
         total = None
         self.last_view_costs = []
+        # optional (`self.time_views = True`): one CUDA event per view boundary, read back by last_view_ms()
+        marks = [torch.cuda.Event(enable_timing=True)] if getattr(self, "time_views", False) else None
+        if marks is not None:
+            marks[0].record()
         if self.sparse_adam:
             self.visible.zero_()
         for view in views:
@@ -500,6 +514,10 @@ class ViewShardedTrainer:
             if self.densification_stats:
                 self._add_densification_stats(pkg)
             self.last_view_costs.append(pkg.get("num_rendered", 0) if isinstance(pkg, dict) else 0)
+            if marks is not None:
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
+        self._view_marks = marks
         if timing is not None:
             ev[1].record()
         self.params.begin_view()
