@@ -4,7 +4,7 @@ import ctypes
 from . import _lib
 
 EXPORTED_SYMBOLS = (
-    "hg_geometry_all_map", "hg_geometry_all_map_backward", "hg_activate_params", "hg_activate_params_backward", "hg_depth_normal", "hg_depth_normal_backward",
+    "hg_geometry_all_map", "hg_geometry_all_map_backward", "hg_activate_params", "hg_activate_params_backward", "hg_prologue_backward", "hg_depth_normal", "hg_depth_normal_backward",
     "hg_normal_consistency_workspace_bytes", "hg_normal_consistency_loss", "hg_adam_step", "hg_densification_stats", "hg_expand_to_size_workspace_bytes", "hg_expand_to_size",
     "hg_interpolation_weights", "hg_hier_interpolate", "hg_hier_interpolate_backward",
     "hg_dist2_knn3_workspace_bytes", "hg_dist2_knn3",
@@ -31,6 +31,8 @@ def lib():
         "hg_geometry_all_map_backward": (ci, [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
         "hg_activate_params": (ci, [vp, vp, vp, i64, vp, vp, vp, vp]),
         "hg_activate_params_backward": (ci, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]),
+        "hg_prologue_backward": (ci, [vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp,
+                                      vp, vp]),
         "hg_depth_normal": (ci, [vp, vp, i32, i32, Intrinsics, vp, vp]),
         "hg_depth_normal_backward": (ci, [vp, vp, vp, i32, i32, Intrinsics, vp, vp]),
         "hg_normal_consistency_workspace_bytes": (sz, [i32, i32]),

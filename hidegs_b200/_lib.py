@@ -75,7 +75,7 @@ def lib():
     L.hg_raster_backward.argtypes = [ctypes.POINTER(RasterInputs), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hg_raster_backward.restype = ctypes.c_int
-    L.hg_raster_backward_chunked.argtypes = L.hg_raster_backward.argtypes[:-1] + [i32, CHUNK_FN, vp, vp, ctypes.c_float, vp, vp]
+    L.hg_raster_backward_chunked.argtypes = L.hg_raster_backward.argtypes[:-1] + [i32, CHUNK_FN, vp, vp, ctypes.c_float, vp, i32, vp]
     L.hg_raster_backward_chunked.restype = ctypes.c_int
     L.hg_raster_debug_keys.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.hg_raster_debug_keys.restype = ctypes.c_int

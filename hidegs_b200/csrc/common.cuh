@@ -155,7 +155,7 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
                           float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
                           float* dL_drotations, float* dL_dall_map, cudaStream_t stream, int slot_begin = 0,
                           int slot_end = -1, float* sh_sink = nullptr, float sh_beta = 0.f,
-                          float* sh_factor = nullptr);
+                          float* sh_factor = nullptr, bool skip_culled_rows = false);
 int launch_sh_from_factors(int N, int D, int M, int n_views, const float* means3D, const float* factors,
                            size_t view_stride, float* dL_dsh, float beta, cudaStream_t stream);
 int preprocess_bwd_block_slots();

@@ -44,23 +44,12 @@ __device__ __forceinline__ int argmin3(float a, float b, float c) {
   return m;
 }
 
+// One row of input_all_map and (BACKWARD) of its gradient: `m` = index of the smallest scaling axis, `q` the rotation as
+// the renderer sees it (activated).  out5 / g5 point at the row's five floats.
 template <bool BACKWARD>
-__global__ void __launch_bounds__(256)
-all_map_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling, const float* __restrict__ rotation,
-               const float* __restrict__ viewmatrix, const float* __restrict__ campos, const int64_t N,
-               float* __restrict__ out, const float* __restrict__ dL_dall_map, float* __restrict__ dL_dxyz,
-               float* __restrict__ dL_drot) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  // the 19 camera floats are read through the pointers (uniform, L1-resident): no host round trip
-  View V;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) V.v[i] = __ldg(viewmatrix + i);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) V.cam[i] = __ldg(campos + i);
-  const float px = xyz[3 * n], py = xyz[3 * n + 1], pz = xyz[3 * n + 2];
-  const int m = argmin3(scaling[3 * n], scaling[3 * n + 1], scaling[3 * n + 2]);
-  const float4 q = __ldg(reinterpret_cast<const float4*>(rotation) + n);
+__device__ __forceinline__ void all_map_row(const View& V, const float px, const float py, const float pz, const int m,
+                                            const float4 q, float* __restrict__ out5, const float* __restrict__ g5,
+                                            float (&dxyz)[3], float4& drot) {
   const float qq = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
   const float s = 2.0f / qq;
   float col[3];
@@ -76,26 +65,23 @@ all_map_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling,
   }
   const float d = ln[0] * pc[0] + ln[1] * pc[1] + ln[2] * pc[2];
   if (!BACKWARD) {
-    float* o = out + 5 * n;
-    o[0] = ln[0]; o[1] = ln[1]; o[2] = ln[2]; o[3] = 1.0f; o[4] = fabsf(d);
+    out5[0] = ln[0]; out5[1] = ln[1]; out5[2] = ln[2]; out5[3] = 1.0f; out5[4] = fabsf(d);
     return;
   }
-  const float* g = dL_dall_map + 5 * n;
   const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);  // d|d|/dd, 0 at 0 as torch.abs
-  const float g4 = g[4] * sg;
+  const float g4 = g5[4] * sg;
   float dln[3], dpc[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    dln[j] = g[j] + g4 * pc[j];
+    dln[j] = g5[j] + g4 * pc[j];
     dpc[j] = g4 * ln[j];
   }
-  float dn[3], dp[3];
+  float dn[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     dn[i] = dln[0] * V.v[4 * i] + dln[1] * V.v[4 * i + 1] + dln[2] * V.v[4 * i + 2];
-    dp[i] = dpc[0] * V.v[4 * i] + dpc[1] * V.v[4 * i + 1] + dpc[2] * V.v[4 * i + 2];
+    dxyz[i] = dpc[0] * V.v[4 * i] + dpc[1] * V.v[4 * i + 1] + dpc[2] * V.v[4 * i + 2];
   }
-  dL_dxyz[3 * n] = dp[0]; dL_dxyz[3 * n + 1] = dp[1]; dL_dxyz[3 * n + 2] = dp[2];
   // column = e_m + s * A_m(q):  dL/dq = s * J_A^T G + (G . A_m) ds/dq,  ds/dq = -s^2 q
   const float G0 = flip * dn[0], G1 = flip * dn[1], G2 = flip * dn[2];
   const float r = q.x, i = q.y, j = q.z, k = q.w;
@@ -123,7 +109,34 @@ all_map_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling,
     dk = G0 * i + G1 * j;
   }
   const float c = -s * s * GA;
-  reinterpret_cast<float4*>(dL_drot)[n] = make_float4(s * dr + c * r, s * di + c * i, s * dj + c * j, s * dk + c * k);
+  drot = make_float4(s * dr + c * r, s * di + c * i, s * dj + c * j, s * dk + c * k);
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256)
+all_map_kernel(const float* __restrict__ xyz, const float* __restrict__ scaling, const float* __restrict__ rotation,
+               const float* __restrict__ viewmatrix, const float* __restrict__ campos, const int64_t N,
+               float* __restrict__ out, const float* __restrict__ dL_dall_map, float* __restrict__ dL_dxyz,
+               float* __restrict__ dL_drot) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  // the 19 camera floats are read through the pointers (uniform, L1-resident): no host round trip
+  View V;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) V.v[i] = __ldg(viewmatrix + i);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) V.cam[i] = __ldg(campos + i);
+  const float px = xyz[3 * n], py = xyz[3 * n + 1], pz = xyz[3 * n + 2];
+  const int m = argmin3(scaling[3 * n], scaling[3 * n + 1], scaling[3 * n + 2]);
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rotation) + n);
+  float dxyz[3];
+  float4 drot;
+  all_map_row<BACKWARD>(V, px, py, pz, m, q, BACKWARD ? nullptr : out + 5 * n, BACKWARD ? dL_dall_map + 5 * n : nullptr,
+                        dxyz, drot);
+  if (BACKWARD) {
+    dL_dxyz[3 * n] = dxyz[0]; dL_dxyz[3 * n + 1] = dxyz[1]; dL_dxyz[3 * n + 2] = dxyz[2];
+    reinterpret_cast<float4*>(dL_drot)[n] = drot;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -183,6 +196,88 @@ activate_bwd_kernel(const float* __restrict__ rs, const float* __restrict__ rr, 
       d = make_float4(p.x + d.x, p.y + d.y, p.z + d.z, p.w + d.w);
     }
     *dst = d;
+  }
+}
+
+// Everything between the rasterizer's backward and the raw-parameter gradient arena of a training view, in ONE pass over
+// the rows the view rendered: all_map backward (its xyz / rotation gradients join the rasterizer's), the scale
+// regulariser's gradient (g_s_extra * *extra_scale), the activation chain rule (exp / sigmoid / normalize) and the
+// accumulation dst = beta * dst + grad.  Rows with radii <= 0 carry no gradient in any of these terms: they are
+// skipped (beta = 1) or zero-filled (beta = 0) without reading their gradient rows — which the rasterizer's backward
+// therefore need not write (HG_BWD_SKIP_CULLED_ROWS).  Replaces all_map_kernel<true>, two adds, one addcmul and
+// activate_bwd_kernel (five passes over N rows) of the executor.
+__global__ void __launch_bounds__(256)
+prologue_bwd_kernel(const float* __restrict__ rs, const float* __restrict__ rr, const float* __restrict__ ro,
+                    const float* __restrict__ xyz, const int64_t N, const int* __restrict__ radii,
+                    const float* __restrict__ viewmatrix, const float* __restrict__ campos,
+                    const float* __restrict__ g_xyz, const float* __restrict__ g_o, const float* __restrict__ g_s,
+                    const float* __restrict__ g_r, const float* __restrict__ g_all_map,
+                    const float* __restrict__ g_s_extra, const float* __restrict__ extra_scale, const float beta,
+                    float* __restrict__ d_xyz, float* __restrict__ d_o, float* __restrict__ d_s,
+                    float* __restrict__ d_r) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const bool acc = beta != 0.0f;
+  float4* const dst_r = reinterpret_cast<float4*>(d_r) + n;
+  if (radii && radii[n] <= 0) {
+    if (!acc) {
+      d_xyz[3 * n] = d_xyz[3 * n + 1] = d_xyz[3 * n + 2] = 0.f;
+      d_s[3 * n] = d_s[3 * n + 1] = d_s[3 * n + 2] = 0.f;
+      d_o[n] = 0.f;
+      *dst_r = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  const float4 q = __ldg(reinterpret_cast<const float4*>(rr) + n);
+  const float len = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  const float inv = 1.0f / fmaxf(len, 1e-12f);
+  const float4 y = make_float4(q.x * inv, q.y * inv, q.z * inv, q.w * inv);  // the activated rotation
+  const float r0 = rs[3 * n], r1 = rs[3 * n + 1], r2 = rs[3 * n + 2];
+  const float e[3] = {expf(r0), expf(r1), expf(r2)};                         // the activated scaling
+  float gx[3] = {0.f, 0.f, 0.f};
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g_xyz) { gx[0] = g_xyz[3 * n]; gx[1] = g_xyz[3 * n + 1]; gx[2] = g_xyz[3 * n + 2]; }
+  if (g_r) g = __ldg(reinterpret_cast<const float4*>(g_r) + n);
+  if (g_all_map) {
+    View V;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) V.v[i] = __ldg(viewmatrix + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) V.cam[i] = __ldg(campos + i);
+    float dxyz[3];
+    float4 drot;
+    all_map_row<true>(V, xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2], argmin3(e[0], e[1], e[2]), y, nullptr,
+                      g_all_map + 5 * n, dxyz, drot);
+    gx[0] += dxyz[0]; gx[1] += dxyz[1]; gx[2] += dxyz[2];
+    g = make_float4(g.x + drot.x, g.y + drot.y, g.z + drot.z, g.w + drot.w);
+  }
+  const float xs = (g_s_extra && extra_scale) ? __ldg(extra_scale) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d_xyz[3 * n + i] = acc ? d_xyz[3 * n + i] + gx[i] : gx[i];
+    float gs = g_s ? g_s[3 * n + i] : 0.f;
+    if (g_s_extra) gs = fmaf(g_s_extra[3 * n + i], xs, gs);  // torch.addcmul(g_s, extra, scale)
+    gs *= e[i];
+    d_s[3 * n + i] = acc ? d_s[3 * n + i] + gs : gs;
+  }
+  {
+    const float sg = 1.0f / (1.0f + expf(-ro[n]));
+    const float go = g_o ? g_o[n] * sg * (1.0f - sg) : 0.f;
+    d_o[n] = acc ? d_o[n] + go : go;
+  }
+  {
+    float4 d;
+    if (len > 1e-12f) {
+      const float t = y.x * g.x + y.y * g.y + y.z * g.z + y.w * g.w;
+      d = make_float4((g.x - y.x * t) * inv, (g.y - y.y * t) * inv, (g.z - y.z * t) * inv, (g.w - y.w * t) * inv);
+    } else {  // clamp_min saturated: the denominator is the constant eps
+      d = make_float4(g.x * 1e12f, g.y * 1e12f, g.z * 1e12f, g.w * 1e12f);
+    }
+    if (acc) {
+      const float4 p = *dst_r;
+      d = make_float4(p.x + d.x, p.y + d.y, p.z + d.z, p.w + d.w);
+    }
+    *dst_r = d;
   }
 }
 
@@ -566,6 +661,34 @@ int hg_activate_params_backward(const float* raw_scaling, const float* raw_rotat
                                                                      g_opacity, g_scaling, g_rotation, beta, d_xyz,
                                                                      d_opacity, d_scaling, d_rotation);
   HG_POST_LAUNCH(false, st, "activate_params_bwd");
+  if (F > 0 && g_features) {  // NULL: the feature gradient already sits in d_features (rasterizer SH sink)
+    axpby4_kernel<<<148 * 8, 256, 0, st>>>((const float4*)g_features, N * (int64_t)F / 4, beta, (float4*)d_features);
+    HG_POST_LAUNCH(false, st, "features_grad_accumulate");
+  }
+  return HG_OK;
+}
+
+int hg_prologue_backward(const float* raw_scaling, const float* raw_rotation, const float* raw_opacity, const float* xyz,
+                         int64_t N, int32_t F, const int32_t* radii, const float* viewmatrix, const float* campos,
+                         const float* g_xyz, const float* g_features, const float* g_opacity, const float* g_scaling,
+                         const float* g_rotation, const float* g_all_map, const float* g_scaling_extra,
+                         const float* extra_scale, float beta, float* d_xyz, float* d_features, float* d_opacity,
+                         float* d_scaling, float* d_rotation, void* st_) {
+  if (N < 0 || F < 0 || !(beta == 0.0f || beta == 1.0f) ||
+      (N > 0 && (!raw_scaling || !raw_rotation || !raw_opacity || !d_xyz || !d_opacity || !d_scaling || !d_rotation ||
+                 (g_all_map && (!xyz || !viewmatrix || !campos)) || (F > 0 && g_features && !d_features))) ||
+      (((uintptr_t)raw_rotation | (uintptr_t)g_rotation | (uintptr_t)d_rotation | (uintptr_t)g_features |
+        (uintptr_t)d_features) & 15) != 0 || (g_features && ((N * (int64_t)F) & 3) != 0)) {
+    set_error("hg_prologue_backward: bad argument (rotation / feature arrays must be 16-byte aligned, N*F % 4 == 0)");
+    return HG_ERR_INVALID_ARG;
+  }
+  if (N == 0) return HG_OK;
+  cudaStream_t st = (cudaStream_t)st_;
+  prologue_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(raw_scaling, raw_rotation, raw_opacity, xyz, N, radii,
+                                                                     viewmatrix, campos, g_xyz, g_opacity, g_scaling,
+                                                                     g_rotation, g_all_map, g_scaling_extra, extra_scale,
+                                                                     beta, d_xyz, d_opacity, d_scaling, d_rotation);
+  HG_POST_LAUNCH(false, st, "prologue_bwd");
   if (F > 0 && g_features) {  // NULL: the feature gradient already sits in d_features (rasterizer SH sink)
     axpby4_kernel<<<148 * 8, 256, 0, st>>>((const float4*)g_features, N * (int64_t)F / 4, beta, (float4*)d_features);
     HG_POST_LAUNCH(false, st, "features_grad_accumulate");

@@ -104,6 +104,7 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
   const size_t g = (size_t)idx;
 
   if (!alive) {
+    if (sh_factor) sh_factor[3 * g] = sh_factor[3 * g + 1] = sh_factor[3 * g + 2] = 0.f;
     if (prezeroed) break;
     // Culled slot: its gradient rows are all zero.
     dL_dmeans2D[3 * g] = dL_dmeans2D[3 * g + 1] = dL_dmeans2D[3 * g + 2] = 0.f;
@@ -114,8 +115,7 @@ preprocess_bwd_kernel(const int P, const int block0, const int D, const int M, c
     dL_dmeans3D[3 * g] = dL_dmeans3D[3 * g + 1] = dL_dmeans3D[3 * g + 2] = 0.f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) dL_dcov3D[6 * g + i] = 0.f;
-    if (sh_factor) sh_factor[3 * g] = sh_factor[3 * g + 1] = sh_factor[3 * g + 2] = 0.f;
-    else if (!staged)
+    if (!sh_factor && !staged)
       for (int i = 0; i < row; ++i) dL_dsh[g * row + i] = 0.f;
     dL_dscales[3 * g] = dL_dscales[3 * g + 1] = dL_dscales[3 * g + 2] = 0.f;
     dL_drotations[4 * g] = dL_drotations[4 * g + 1] = dL_drotations[4 * g + 2] = dL_drotations[4 * g + 3] = 0.f;
@@ -529,8 +529,10 @@ int launch_preprocess_bwd(const hg_raster_inputs& in, const GeomState& g, const 
                           float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                           float* dL_dcov3D, float* dL_dsh, float* dL_dscales,
                           float* dL_drotations, float* dL_dall_map, cudaStream_t stream, int slot_begin,
-                          int slot_end, float* sh_sink, float sh_beta, float* sh_factor) {
-  const bool prezeroed = in.indices != nullptr || in.parent_indices != nullptr;
+                          int slot_end, float* sh_sink, float sh_beta, float* sh_factor, bool skip_culled_rows) {
+  // "prezeroed": the kernel leaves the rows of culled slots alone — because the caller zero-filled the arrays (index
+  // remap / parents: rows are scattered and accumulated), or because it never reads them (HG_BWD_SKIP_CULLED_ROWS)
+  const bool prezeroed = in.indices != nullptr || in.parent_indices != nullptr || skip_culled_rows;
   const float* cov = in.cov3D_precomp ? in.cov3D_precomp : g.cov3D;
   // [slot_begin, slot_end): the slots this launch covers (slot_begin a multiple of the block size; -1 = to the end)
   if (slot_end < 0 || slot_end > in.P) slot_end = in.P;

@@ -278,7 +278,7 @@ int hg_raster_backward(const hg_raster_inputs* in, int32_t R, const int32_t* rad
   return hg_raster_backward_chunked(in, R, radii, geom_buffer, binning_buffer, image_buffer, all_map_pixels, dL_dpix,
                                     dL_dout_all_map, dL_dout_plane_depth, dL_dout_invdepth, accum, dL_dmeans2D, dL_dconic,
                                     dL_dopacity, dL_dcolors, dL_dinvdepths, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
-                                    dL_drotations, dL_dall_map, 1, nullptr, nullptr, nullptr, 0.f, nullptr, stream_);
+                                    dL_drotations, dL_dall_map, 1, nullptr, nullptr, nullptr, 0.f, nullptr, 0, stream_);
 }
 
 int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int32_t* radii,
@@ -290,7 +290,7 @@ int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int3
                                float* dL_dcolors, float* dL_dinvdepths, float* dL_dmeans3D,
                                float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
                                float* dL_dall_map, int32_t n_chunks, hg_chunk_fn on_chunk, void* chunk_ctx,
-                               float* sh_sink, float sh_beta, float* sh_factor, void* stream_) {
+                               float* sh_sink, float sh_beta, float* sh_factor, int32_t flags, void* stream_) {
   g_err[0] = 0;
   int rc = validate(in);
   if (rc) return rc;
@@ -343,7 +343,8 @@ int hg_raster_backward_chunked(const hg_raster_inputs* in, int32_t R, const int3
     rc = launch_preprocess_bwd(*in, g, radii, focal_x, focal_y, acc, dL_dout_invdepth != nullptr,
                                dL_dmeans2D, dL_dconic, dL_dopacity, dL_dcolors, dL_dinvdepths,
                                dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
-                               dL_dall_map, stream, p0, p1, sh_sink, sh_beta, sh_factor);
+                               dL_dall_map, stream, p0, p1, sh_sink, sh_beta, sh_factor,
+                               (flags & HG_BWD_SKIP_CULLED_ROWS) != 0);
     if (rc) return rc;
     if (on_chunk) on_chunk(chunk_ctx, chunk, p0, p1, stream_);
   }

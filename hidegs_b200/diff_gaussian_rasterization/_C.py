@@ -24,7 +24,8 @@ mark_visible = _hgC.mark_visible
 sh_sink_supported = _hgC.sh_sink_supported
 
 
-def rasterize_gaussians_backward(*args, sh_sink=None, grad_arena=None, chunk_hook=None, sh_factor=None):
+def rasterize_gaussians_backward(*args, sh_sink=None, grad_arena=None, chunk_hook=None, sh_factor=None,
+                                 skip_culled_rows=False):
     """RasterizeGaussiansBackwardCUDA (rasterize_points.cu:149-279), positional arguments as in the reference.
 
     Per-call extensions (keyword only; nothing is remembered between calls):
@@ -38,8 +39,11 @@ def rasterize_gaussians_backward(*args, sh_sink=None, grad_arena=None, chunk_hoo
       sh_factor  flat fp32 tensor of >= 3 N + 3 elements: instead of the [N, M, 3] SH gradient rows the call writes the
                  three clamp-masked colour gradients per Gaussian (the rows are their outer product with the SH basis
                  at the view direction) followed by the camera centre; dL_dsh is returned as None
-                 (parallel.FactoredExchange ships these 12 bytes per Gaussian instead of 192)."""
+                 (parallel.FactoredExchange ships these 12 bytes per Gaussian instead of 192)
+      skip_culled_rows  the gradient rows of culled Gaussians (radii <= 0) are left UNWRITTEN instead of zero-filled:
+                 only for a consumer that masks by `radii` (the trainer's fused prologue backward)."""
     sink, beta = sh_sink if sh_sink is not None else (None, 0.0)
     n_chunks, fn = chunk_hook if chunk_hook is not None else (0, None)
     return _hgC.rasterize_gaussians_backward(*args, sh_sink=sink, sh_beta=float(beta), grad_arena=grad_arena,
-                                             n_chunks=int(n_chunks), chunk_hook=fn, sh_factor=sh_factor)
+                                             n_chunks=int(n_chunks), chunk_hook=fn, sh_factor=sh_factor,
+                                             skip_culled_rows=bool(skip_culled_rows))

@@ -387,7 +387,8 @@ class ViewShardedTrainer:
 
     def view_step_direct(self, cam, gt, iteration, gt_ready=None):
         """Forward AND backward of one view (gradients accumulated into the arena), without autograd.  Returns
-        (loss value tensor, dict with "visibility_filter" (mask), "radii", "means2D_grad")."""
+        (loss value tensor, dict with "visibility_filter" (mask), "radii", "means2D_grad" — defined on the rendered rows
+        only: the rasterizer's backward does not write the rows of culled Gaussians here)."""
         o, p, T = self.opt, self.params, self._Tape
         dev = p.param_arena.device
         with torch.no_grad():
@@ -459,16 +460,41 @@ class ViewShardedTrainer:
             _lib.check(rc, "training_image_grad")
             g_pd = tN.gd.reshape(plane_depth.shape) if tN is not None else None
             g_am = tN.gam if tN is not None else None
+            # the rasterizer's backward leaves the gradient rows of culled Gaussians unwritten: the fused prologue
+            # backward below looks at `radii` first (a UAV view culls ~80 % of the slab)
+            tR.skip_culled_rows = True
             (g_xyz, g_means2D, g_sh, _gc, g_op, g_sc, g_rot, _gcov, g_all_map_in, _n) = _RasterizeGaussians.backward(
                 tR, g_color, None, None, g_am, g_pd, None)
-            d_xyz, _n2, d_rot, _n3, _n4 = gr._AllMap.backward(tM, g_all_map_in)
-            g_xyz = g_xyz + d_xyz
-            g_rot = g_rot + d_rot
-            if tSc is not None:
-                g_sc = torch.addcmul(g_sc, tSc.grad, tT.partials[2])
-            _ActivateParams.backward(tA, g_xyz, g_sh, g_op, g_sc, g_rot)
+            # all_map backward + scale-regulariser gradient + activation chain rule + accumulation into the arena: one
+            # kernel over the rendered rows (hg_prologue_backward)
+            self._prologue_backward(p, radii, rs, g_xyz, g_sh, g_op, g_sc, g_rot, g_all_map_in,
+                                    tSc.grad if tSc is not None else None, tT.partials[2] if tSc is not None else None)
         return loss, {"visibility_filter": visible, "radii": radii, "means2D_grad": g_means2D,
                       "num_rendered": int(tR.num_rendered)}
+
+    @staticmethod
+    def _prologue_backward(p, radii, rs, g_xyz, g_feat, g_op, g_sc, g_rot, g_all_map, g_sc_extra, extra_scale):
+        """Gradients w.r.t. the activated parameters (+ dL/dall_map, + the scale regulariser's gradient) -> the raw
+        parameters' rows of the gradient arena, dst = beta * dst + grad, rows with radii <= 0 skipped."""
+        N = p.N
+        if g_feat is not None and p._sink_used:  # (features also used outside the rasterizer: on top of the sink)
+            p.grad_arena[p.slices["features"]].add_(g_feat.reshape(-1))
+            g_feat = None
+        if g_feat is None and not p._sink_used and not p._grad_dirty:  # no feature gradient at all in the first view
+            g_feat = torch.zeros((N, 16, 3), dtype=torch.float32, device=p.param_arena.device)
+        ptr = lambda t: t.contiguous().data_ptr() if t is not None else None  # noqa: E731
+        d = {k: p.grad_arena[p.slices[k]] for k in ("xyz", "features", "opacity", "scaling", "rotation")}
+        with torch.cuda.device(p.param_arena.device):
+            rc = _G().hg_prologue_backward(
+                p._scaling.data_ptr(), p._rotation.data_ptr(), p._opacity.data_ptr(), p._xyz.data_ptr(), N, 48,
+                radii.data_ptr(), rs.viewmatrix.contiguous().data_ptr(), rs.campos.contiguous().data_ptr(),
+                ptr(g_xyz), ptr(g_feat), ptr(g_op), ptr(g_sc), ptr(g_rot), ptr(g_all_map), ptr(g_sc_extra),
+                ptr(extra_scale), 1.0 if p._grad_dirty else 0.0, d["xyz"].data_ptr(), d["features"].data_ptr(),
+                d["opacity"].data_ptr(), d["scaling"].data_ptr(), d["rotation"].data_ptr(),
+                torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "prologue_backward")
+        p._grad_dirty = True
+        p._sink_used = False
 
     def last_view_ms(self):
         """Device time of every view of the last step (needs `self.time_views = True` during that step; synchronises).

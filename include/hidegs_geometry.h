@@ -69,6 +69,21 @@ HG_API int hg_activate_params_backward(const float *raw_scaling, const float *ra
                                        float beta, float *d_xyz, float *d_features, float *d_opacity,
                                        float *d_scaling, float *d_rotation, void *stream);
 
+/* The executor's fused prologue backward of a training view: all_map backward (gaussian_renderer/__init__.py:161-169
+ * and its autograd) + the gradient of the scale regulariser (g_scaling_extra * *extra_scale, a DEVICE scalar; both may
+ * be NULL) + hg_activate_params_backward, in one pass over the rows the view rendered.  `radii` (int32 [N], the
+ * rasterizer's output; may be NULL = every row): rows with radii <= 0 are zero-filled (beta = 0) or left alone
+ * (beta = 1) WITHOUT reading their gradient rows, so the rasterizer's backward may leave them unwritten
+ * (HG_BWD_SKIP_CULLED_ROWS of hg_raster_backward_chunked).  g_* are the rasterizer's gradients w.r.t. the ACTIVATED
+ * parameters, g_all_map its dL/dall_map [N,5]; xyz / viewmatrix / campos as in hg_geometry_all_map. */
+HG_API int hg_prologue_backward(const float *raw_scaling, const float *raw_rotation, const float *raw_opacity,
+                                const float *xyz, int64_t N, int32_t F, const int32_t *radii, const float *viewmatrix,
+                                const float *campos, const float *g_xyz, const float *g_features,
+                                const float *g_opacity, const float *g_scaling, const float *g_rotation,
+                                const float *g_all_map, const float *g_scaling_extra, const float *extra_scale,
+                                float beta, float *d_xyz, float *d_features, float *d_opacity, float *d_scaling,
+                                float *d_rotation, void *stream);
+
 /* Camera intrinsics as Camera.get_calib_matrix_nerf builds them (scene/cameras.py:93-96,135-138). */
 typedef struct hg_intrinsics {
   float fx, fy, cx, cy;

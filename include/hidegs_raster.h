@@ -190,7 +190,12 @@ HG_API int hg_raster_backward(const hg_raster_inputs *in, int32_t R,
  * three clamp-masked colour gradients of every Gaussian go to sh_factor[3 g .. 3 g + 2] (zeros for culled slots) and
  * the view's camera centre to sh_factor[3 N .. 3 N + 2].  dL/dSH is the outer product of the SH basis at the view
  * direction with exactly these three numbers, so a data-parallel step ships 12 bytes per Gaussian and view instead of
- * 192 and rebuilds the summed rows with hg_sh_gradient_from_factors (include/hidegs_exchange.h). */
+ * 192 and rebuilds the summed rows with hg_sh_gradient_from_factors (include/hidegs_exchange.h).
+ * `flags`: HG_BWD_SKIP_CULLED_ROWS = the gradient rows of culled slots (radii <= 0) are NOT written (they are zeros by
+ * definition; the reference zero-fills 324 B per Gaussian for them): for a consumer that looks at `radii` first, such
+ * as hg_prologue_backward (include/hidegs_geometry.h) — a sparse view then costs no gradient traffic for the
+ * Gaussians it does not see.  The SH sink keeps its own rule (sh_beta). */
+#define HG_BWD_SKIP_CULLED_ROWS 1
 typedef void (*hg_chunk_fn)(void *chunk_ctx, int32_t chunk, int32_t slot_begin, int32_t slot_end, void *stream);
 HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        const int32_t *radii,
@@ -215,7 +220,7 @@ HG_API int hg_raster_backward_chunked(const hg_raster_inputs *in, int32_t R,
                        float *dL_dall_map,   /* [N,5] */
                        int32_t n_chunks, hg_chunk_fn on_chunk,
                                        void *chunk_ctx, float *sh_sink, float sh_beta, float *sh_factor,
-                                       void *stream);
+                                       int32_t flags, void *stream);
 
 /* Test / diagnostic accessor.  The library never materialises the reference's 64-bit tile|depth keys: it buckets the
  * tile instances by tile (counts from the preprocess pass, one scan, one scatter) and sorts every tile's list by

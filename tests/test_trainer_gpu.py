@@ -193,8 +193,11 @@ def test_direct_view_executor_matches_autograd(cuda_device, cache_gt):
     err = (a[0] - b[0]).abs().max().item()
     assert err <= 1e-5 * b[0].abs().max().item() + 1e-12, err
     assert all(torch.equal(x, y) for x, y in zip(a[2], b[2]))
-    for x, y in zip(a[3], b[3]):
-        assert (x - y).abs().max().item() <= 1e-5 * y.abs().max().item() + 1e-12
+    for x, y, v in zip(a[3], b[3], a[2]):
+        # (the executor's rasterizer backward leaves the rows of culled Gaussians unwritten — HG_BWD_SKIP_CULLED_ROWS:
+        # every consumer masks by radii — so only the rendered rows are defined; the autograd path holds zeros there)
+        assert float(y[~v].abs().max()) == 0.0
+        assert (x[v] - y[v]).abs().max().item() <= 1e-5 * y.abs().max().item() + 1e-12
     # three full steps (Adam included): parameters stay together
     arenas = {}
     for direct in (True, False):
