@@ -393,9 +393,14 @@ class ViewShardedTrainer:
         dev = p.param_arena.device
         with torch.no_grad():
             # ---- forward
-            tA = T(True, True, True, True, True, False)
-            xyz, feat, opacity, scaling, rotation = _ActivateParams.forward(tA, p._xyz, p._features, p._opacity,
-                                                                            p._scaling, p._rotation, p)
+            # the activated parameters are the same for every view of one optimiser step: step() keeps them
+            act = getattr(self, "_step_activations", None)
+            if act is None:
+                tA = T(True, True, True, True, True, False)
+                act = _ActivateParams.forward(tA, p._xyz, p._features, p._opacity, p._scaling, p._rotation, p)
+                if getattr(self, "_in_step", False):
+                    self._step_activations = act
+            xyz, feat, opacity, scaling, rotation = act
             e_i = torch.empty(0, dtype=torch.int32, device=dev)
             e_f = torch.empty(0, dtype=torch.float32, device=dev)
             rs = gr._raster_settings(cam, p, self.pipe, self.bg, 1.0, True, True, e_i, e_i, e_f, e_i)
@@ -523,6 +528,7 @@ class ViewShardedTrainer:
             marks[0].record()
         if self.sparse_adam:
             self.visible.zero_()
+        self._in_step, self._step_activations = True, None
         for view in views:
             cam, gt = view[0], view[1]
             if getattr(self, "direct", False):
@@ -544,6 +550,7 @@ class ViewShardedTrainer:
                 marks.append(torch.cuda.Event(enable_timing=True))
                 marks[-1].record()
         self._view_marks = marks
+        self._in_step, self._step_activations = False, None  # the optimiser is about to change the parameters
         if timing is not None:
             ev[1].record()
         self.params.begin_view()

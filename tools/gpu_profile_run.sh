@@ -16,9 +16,9 @@ HG_BENCH_SKIP_TRAIN=1 HG_BENCH_SKIP_CPU=1 timeout 600 ncu --metrics $M --clock-c
 timeout 300 python tools/loss_bench.py --no-cpu --iters 3 --warmup 2 > $O/${TAG}_lb_plain.log 2>&1 \
   && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_loss_launches.csv \
     python tools/loss_bench.py --no-cpu --iters 3 --warmup 2 > $O/${TAG}_lb_ncu.log 2>&1 || echo "loss list failed"
-timeout 300 python tools/train_probe.py --recipe c2 --steps 2 > $O/${TAG}_tp_plain.log 2>&1 \
-  && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file $O/${TAG}_train_launches.csv \
-    python tools/train_probe.py --recipe c2 --steps 2 > $O/${TAG}_tp_ncu.log 2>&1 || echo "train list failed"
+timeout 300 python tools/train_leg_probe.py --steps 3 > $O/${TAG}_tp_plain.log 2>&1 \
+  && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $O/${TAG}_train_launches.csv \
+    python tools/train_leg_probe.py --steps 2 > $O/${TAG}_tp_ncu.log 2>&1 || echo "train list failed"
 # full-section captures: one launch of each kernel of interest from the second resident step
 HG_BENCH_SKIP_TRAIN=1 HG_BENCH_SKIP_CPU=1 timeout 900 ncu $FULL -k regex:"blend_|tile_sort|scatter_inst|tile_scan|preprocess_" -s 8 -c 8 \
     -f -o $O/${TAG}_prof_raster python bench.py --steps 2 --warmup 3 > $O/${TAG}_ncu_f.log 2>&1 || echo "raster capture failed"

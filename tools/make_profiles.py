@@ -96,6 +96,44 @@ def table(src, dst, title, note, n_iter):
     open(os.path.join(P, dst + "_summary.md"), "w").write("\n".join(L) + "\n")
 
 
+def train_table(src, dst, title, note, views):
+    """The LAST optimiser step of the capture (between the two last groups of Adam launches), per view."""
+    if not copy(src, dst + ".csv"):
+        return
+    rows = list(csv.reader(open(os.path.join(P, dst + ".csv"))))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    kn, mv, mn = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    L_ = [(r[kn], float(r[mv].replace(",", ""))) for r in rows[hi + 1:] if len(r) > mv and r[mn] == "gpu__time_duration.sum"]
+    idx = [i for i, (n, _) in enumerate(L_) if "adam_masked4" in n]
+    groups = []
+    for i in idx:
+        if groups and i - groups[-1][-1] < 12:
+            groups[-1].append(i)
+        else:
+            groups.append([i])
+    if len(groups) < 2:
+        return
+    a, b = groups[-2][-1] + 1, groups[-1][-1] + 1
+    while a < len(L_) and "adam" in L_[a][0]:
+        a += 1
+    while b < len(L_) and "adam" in L_[b][0]:
+        b += 1
+    seg = L_[a:b]
+    acc = {}
+    for n, t in seg:
+        e = acc.setdefault(n, [0, 0.0])
+        e[0] += 1
+        e[1] += t
+    tot = sum(v[1] for v in acc.values())
+    out = [title + "\n", note + "\n", "| kernel | launches / step | us / step | us / view | share |", "|---|---:|---:|---:|---:|"]
+    for k, v in sorted(acc.items(), key=lambda x: -x[1][1])[:40]:
+        out.append("| `%s` | %d | %.1f | %.1f | %.3f |" % (short(k), v[0], v[1] / 1e3, v[1] / 1e3 / views, v[1] / tot))
+    out.append("\nTotal: %.1f us per step = %.1f us per view under ncu (cold, serialised), %d launches per step." %
+               (tot / 1e3, tot / 1e3 / views, len(seg)))
+    open(os.path.join(P, dst + "_summary.md"), "w").write("\n".join(out) + "\n")
+
+
 def full_capture(rep, dst, what, cmd, traffic_keys=False):
     path = os.path.join(G, rep)
     if not os.path.exists(path):
@@ -162,10 +200,11 @@ def main():
           "# %s — ncu launch list of the loss path: `python tools/loss_bench.py --no-cpu --iters 3 --warmup 2` (B200)" % ROUND,
           "One iteration = L1 + SSIM + frequency_regularization_pyramid_scale forward + backward on a 3x1080x1920 pair (BASELINE "
           "configs[0]); the capture holds 11 iterations (full path 5 + per-function passes).", 11)
-    table("%s_train_launches.csv" % TAG, "%s_train_launches" % TAG,
-          "# %s — ncu launch list of the training step: `python tools/train_probe.py --recipe c2 --steps 2` (B200)" % ROUND,
-          "Config 3 (config-2 scene at 2M Gaussians, 1080p, one view per step: render + all losses + backward + Adam); the capture "
-          "starts after 300 launches and holds 400 launches.", 1.0)
+    train_table("%s_train_launches.csv" % TAG, "%s_train_launches" % TAG,
+                "# %s — ncu launch list of the training leg: `python tools/train_leg_probe.py --steps 2` (B200)" % ROUND,
+                "bench.py's `train` leg alone (configs[4] recipe: 2M-Gaussian UAV slab in Morton order, 8 views per step, "
+                "1920x1080, render + L1 + SSIM + frequency / scale regulariser + normal term + backward per view, then the "
+                "sparse Adam); the table is the LAST optimiser step of the capture.", 8)
     full_capture("%s_prof_raster.ncu-rep" % TAG, "%s_ncu_raster_full.md" % TAG, "the rasterizer's kernels",
                  "HG_BENCH_SKIP_TRAIN=1 python bench.py --steps 2 --warmup 3` (1M Gaussians, 1920x1080, R = 5.42 M tile instances, "
                  "geometry + depth outputs on", traffic_keys=True)
