@@ -14,8 +14,10 @@ WANT = [  # (object, kernel regex, mnemonic regex, what it shows)
     ("blend_bwd", r"blend_bwd3_kernelILb1ELb1ELb0", r"HMMA|LDSM|REDG?\.|RED\.|MUFU", "3xTF32 mma.sync reduction, ldmatrix A quads, vector REDs"),
     ("blend_bwd", r"blend_bwd3_kernelILb0ELb0ELb1", r"HMMA|LDSM|MUFU\.(LG2|EX2)|CALL", "hierarchy interpolation on the MMA kernel: lg2 / ex2 pow, out-of-line accurate redo"),
     ("blend_fwd", r"blend_fwd2_kernelILb1ELb1ELb0", r"LDG\.E\.128|STS\.128|LDS\.128|MUFU|VOTE|ATOM|RED", "register-double-buffered gather, 128-bit staging, ballots"),
-    ("blend_fwd", r"blend_fwd3_kernel", r"UBLKCP|SYNCS", "TMA bulk-copy staging experiment (cp.async.bulk + mbarrier)"),
-    ("exchange", r"nvls_allreduce", r"LDGMC|STG.*MC|MULTIMEM|ST\.E.*MMIO|RED|ATOM|CAS", "multimem.ld_reduce / multimem.st through NVSwitch"),
+    ("blend_fwd", r"blend_fwd3_kernel", r"UBLKCP|SYNCS", "TMA bulk-copy staging experiment (cp.async.bulk + mbarrier; removed from the tree)"),
+    ("exchange", r"nvls_allreduce_kernelILi4", r"LDGMC|STG.*MC|MULTIMEM|ST\.E.*MMIO|RED|ATOM|CAS|LDG\.E\.128", "multimem.ld_reduce / multimem.st through NVSwitch; the gather range = plain LDG.128 + multimem.st"),
+    ("preprocess_bwd", r"sh_from_factors", r"STS|LDS|STG\.E\.128|LDG", "SH rows rebuilt from the factors: rows leave through the shared-memory tile as STG.128"),
+    ("geometry", r"prologue_bwd_kernel", r"MUFU|LDG\.E\.128|STG\.E\.128|EXIT", "fused prologue backward: early exit on radii, one pass"),
     ("binning", r"tile_sort_small", r"MATCH|ATOMS|ATOMG|LDS|STS|SHFL|REDUX|LDG|STG", "per-list radix sort: shared-memory loads/stores only in the element loops"),
     ("binning", r"scatter_instances", r"ATOMG|STG|SHFL", "scatter: one ATOMG + one STG.64 per instance"),
     ("preprocess", r"preprocess_fwd_kernel", r"REDG?\.|RED\.|LDG\.E\.128|STG\.E\.128", "tile counters by RED, 128-bit record stores"),
