@@ -7,6 +7,10 @@
 // ~1x the arena out (its replicas of all slices are read once) and ~1x in (the sums), with the additions done in the
 // fabric.  Two cross-rank barriers per CTA (flags in symmetric memory, CAS put / CAS take, system scope) bracket the
 // data phase; CTA b of one rank only ever pairs with CTA b of the others, so no co-residency is assumed.
+//
+// hg_nvls_exchange_f32 adds an all-GATHER range to the same launch: rank r owns a slice of that range in its replica and
+// replicates it into every GPU (plain 128-bit loads + multimem.st) — the SH gradient factors of the factored exchange
+// (DESIGN.md §6), which every rank then turns into the summed SH rows locally (sh_from_factors_kernel).
 #include "common.cuh"
 
 #include <cstdlib>

@@ -6,6 +6,12 @@ first 59 floats per Gaussian are the trainable parameters (xyz 3 | sh 48 | opaci
 rotation 4).  `flat_view()` recovers that arena from the gradient tensors so the collective runs in
 place on a single buffer (NCCL over NVLink on GPUs, gloo in the CPU tests) with no pack kernel; when
 the tensors do not share storage (e.g. autograd had to clone one) they are packed first.
+
+Three exchanges (include/hidegs_exchange.h): `SymmetricArena.all_reduce_` (the whole arena, one in-fabric
+multimem kernel where the ranks share an NVSwitch with multicast support and the group has >= 8 ranks; NCCL otherwise),
+`OverlappedBackwardExchange` (slot ranges of the arena while the per-Gaussian backward still runs; opt-in) and
+`FactoredExchange` (one view per rank: the SH block travels as three colour-gradient factors per Gaussian and rank and
+is rebuilt locally).
 """
 import ctypes
 import os

@@ -12,6 +12,12 @@ Data parallelism: Gaussians are replicated, the views of a step are split `views
 the gradients of its views in ONE flat fp32 arena (59 floats per Gaussian: xyz 3 | features 48 | opacity 1 | scaling 3 |
 rotation 4, SoA by group), the arena is all-reduced once per step (NCCL over NVLink) and the fused Adam kernel consumes
 it with grad_scale = 1 / views.  Parameters live in a matching flat arena, so the optimiser is 6 launches per step.
+
+A view runs without autograd (`ViewShardedTrainer.view_step_direct`: the forward / backward bodies of the same Functions
+on a hand-written tape).  Everything per Gaussian is sparse in the view: the rasterizer's backward leaves the gradient rows
+of culled Gaussians unwritten (HG_BWD_SKIP_CULLED_ROWS) and ONE kernel (`hg_prologue_backward`) takes the rendered rows
+from the rasterizer's gradients to the raw-parameter arena (all_map backward, scale-regulariser gradient, activation
+chain rule, accumulation); the activations themselves are computed once per optimiser step.
 """
 import math
 
