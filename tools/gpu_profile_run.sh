@@ -24,4 +24,6 @@ HG_BENCH_SKIP_TRAIN=1 HG_BENCH_SKIP_CPU=1 timeout 900 ncu $FULL -k regex:"blend_
     -f -o $O/${TAG}_prof_raster python bench.py --steps 2 --warmup 3 > $O/${TAG}_ncu_f.log 2>&1 || echo "raster capture failed"
 timeout 900 ncu $FULL -k regex:"fft_cols|fft_rows_jobs|ssim_fwd|ssim_bwd|pyramid_kernel" -s 10 -c 5 \
     -f -o $O/${TAG}_prof_loss python tools/loss_bench.py --no-cpu --iters 2 --warmup 1 > $O/${TAG}_ncu_fl.log 2>&1 || echo "loss capture failed"
+timeout 900 ncu $FULL -k regex:"blend_|preprocess_|tile_sort|scatter" -s 60 -c 7 \
+    -f -o $O/${TAG}_prof_uav python tools/train_leg_probe.py --steps 1 > $O/${TAG}_ncu_fu.log 2>&1 || echo "uav capture failed"
 tail -c 300 $O/${TAG}_bench.json; echo; tail -c 300 $O/${TAG}_bench_ref.json; echo; ls -la $O/${TAG}_*

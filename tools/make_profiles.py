@@ -210,6 +210,10 @@ def main():
                  "geometry + depth outputs on", traffic_keys=True)
     full_capture("%s_prof_loss.ncu-rep" % TAG, "%s_ncu_loss_full.md" % TAG, "the loss path's heaviest kernels",
                  "python tools/loss_bench.py --no-cpu --iters 2 --warmup 1` (3x1080x1920")
+    full_capture("%s_prof_uav.ncu-rep" % TAG, "%s_ncu_uav_view_full.md" % TAG,
+                 "the rasterizer's kernels on one UAV training view (configs[4] recipe: 2M-Gaussian slab in Morton order, "
+                 "~20 % of it rendered, R ~ 0.76 M tile instances)",
+                 "python tools/train_leg_probe.py --steps 1` (`-k regex:blend_|preprocess_|tile_sort|scatter -s 60 -c 7")
 
 
 if __name__ == "__main__":
