@@ -659,24 +659,40 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
     torch.cuda.synchronize()
     balance = None
     if ddp and os.environ.get("HG_BENCH_BALANCE", "1") != "0":
-        # Re-shard the step's views by the cost one more warm-up step measures (device ms per view, CUDA events around
-        # every view): the ranks meet at the gradient exchange, so the step runs at the pace of the rank with the
-        # heaviest views.  (num_rendered alone left 13.2 - 14.4 ms across 8 ranks: the per-view cost is not only blend.)
-        trainer.time_views = True
-        step()
-        trainer.time_views = False
-        mine = list(zip(my_views, trainer.last_view_ms()))
+        # Re-shard the step's views by measured device time: the ranks meet at the gradient exchange, so the step runs at
+        # the pace of the slowest rank.  A view's time is (cost of the view) x (pace of the GPU it ran on) — the GPUs of
+        # one box do not run at exactly the same pace (measured: +-6 % between the halves of an 8-GPU box) — so every
+        # view is timed on TWO ranks (its own shard, then the next rank's shard) and the two factors are separated by
+        # alternating least squares before the assignment.  (num_rendered alone left 13.2 - 14.4 ms across 8 ranks.)
+        def timed_shard(view_ids):
+            cams[:] = [cams_all[i] for i in view_ids]
+            trainer._gt_cache.clear()
+            step()                     # (builds the per-camera ground-truth caches)
+            trainer.time_views = True
+            step()
+            trainer.time_views = False
+            return [(i, rank, t_) for i, t_ in zip(view_ids, trainer.last_view_ms())]
+        every = list(range(total_views))
+        mine = timed_shard(my_views) + timed_shard(every[(rank + 1) % world::world])
         table = [None] * world
         dist.all_gather_object(table, mine)
-        cost = [0] * total_views
-        for part in table:
-            for i, c in part:
-                cost[i] = c
-        before = [sum(cost[i] for i in list(range(total_views))[r::world]) for r in range(world)]
-        shards = tr.balance_views(cost, world)
-        after = [sum(cost[i] for i in sh) for sh in shards]
+        meas = [m for part in table for m in part]
+        cost, speeds = [1.0] * total_views, [1.0] * world
+        for _ in range(20):            # t = cost[i] * pace[r]
+            for i in range(total_views):
+                v = [t_ / speeds[r_] for j, r_, t_ in meas if j == i]
+                cost[i] = sum(v) / len(v)
+            for r_ in range(world):
+                v = [t_ / cost[j] for j, q, t_ in meas if q == r_]
+                speeds[r_] = sum(v) / len(v)
+            norm = sum(speeds) / world
+            speeds = [x / norm for x in speeds]
+        before = [speeds[r] * sum(cost[i] for i in every[r::world]) for r in range(world)]
+        shards = tr.balance_views(cost, world, speeds)
+        after = [speeds[r] * sum(cost[i] for i in sh) for r, sh in enumerate(shards)]
         balance = {"view_ms_per_rank_before": [round(x, 3) for x in before],
-                   "view_ms_per_rank_after": [round(x, 3) for x in after]}
+                   "view_ms_per_rank_after_predicted": [round(x, 3) for x in after],
+                   "rank_pace": [round(x, 3) for x in speeds]}
         my_views = shards[rank]
         cams[:] = [cams_all[i] for i in my_views]
         trainer._gt_cache.clear()

@@ -271,23 +271,26 @@ class ArenaAdam:
                                  mask, None, 0, lr, 0.9, 0.999, self.eps, self.step_count, grad_scale, head_cols, head_lr, st)
 
 
-def balance_views(costs, world):
-    """Shard `len(costs)` views over `world` ranks with equal counts and near-equal summed cost.  `costs[i]`: predicted
-    cost of view i, e.g. its num_rendered from an earlier visit — the blend kernels' time is proportional to it.
+def balance_views(costs, world, speeds=None):
+    """Shard `len(costs)` views over `world` ranks with equal counts and near-equal time.  `costs[i]`: predicted cost
+    of view i (its device time or num_rendered from an earlier visit).  `speeds[r]` (optional): time multiplier of rank
+    r — the GPUs of one box do not run at exactly the same pace (power / thermal headroom, host placement) — so that the
+    time of a rank is speeds[r] * (sum of its views' costs) and a slower rank is handed lighter views.
     Start: the better of views[rank::world] and longest-processing-time-first with a per-rank capacity; then pairwise
-    swaps between the heaviest rank and the others while they lower the larger of the two loads.  Returns one sorted
+    swaps between the slowest rank and the others while they lower the larger of the two times.  Returns one sorted
     index list per rank; every rank computes the same assignment from the same table."""
     n = len(costs)
     c = [float(x) for x in costs]
+    s = [1.0] * world if speeds is None else [float(x) for x in speeds]
     room = [n // world + (1 if r < n % world else 0) for r in range(world)]
     lpt = [[] for _ in range(world)]
     load = [0.0] * world
     for i in sorted(range(n), key=lambda k: (-c[k], k)):
-        r = min((q for q in range(world) if len(lpt[q]) < room[q]), key=lambda q: (load[q], q))
+        r = min((q for q in range(world) if len(lpt[q]) < room[q]), key=lambda q: (load[q] + s[q] * c[i], q))
         lpt[r].append(i)
-        load[r] += c[i]
+        load[r] += s[r] * c[i]
     strided = [list(range(n))[r::world] for r in range(world)]
-    total = lambda sh: [sum(c[i] for i in s) for s in sh]  # noqa: E731
+    total = lambda sh: [s[r] * sum(c[i] for i in x) for r, x in enumerate(sh)]  # noqa: E731
     out = lpt if max(total(lpt)) <= max(total(strided)) else strided
     load = total(out)
     for _ in range(4 * n):
@@ -296,21 +299,21 @@ def balance_views(costs, world):
         for r in range(world):
             if r == h:
                 continue
-            for a in out[h]:
-                for b in out[r]:
-                    d = c[a] - c[b]
+            for a_ in out[h]:
+                for b_ in out[r]:
+                    d = c[a_] - c[b_]
                     if d <= 0:
                         continue
-                    worst = max(load[h] - d, load[r] + d)
+                    worst = max(load[h] - s[h] * d, load[r] + s[r] * d)
                     if worst < load[h] and (best is None or worst < best[0]):
-                        best = (worst, r, a, b)
+                        best = (worst, r, a_, b_)
         if best is None:
             break
-        _w, r, a, b = best
-        out[h][out[h].index(a)] = b
-        out[r][out[r].index(b)] = a
-        load[h] -= c[a] - c[b]
-        load[r] += c[a] - c[b]
+        _w, r, a_, b_ = best
+        out[h][out[h].index(a_)] = b_
+        out[r][out[r].index(b_)] = a_
+        load[h] -= s[h] * (c[a_] - c[b_])
+        load[r] += s[r] * (c[a_] - c[b_])
     return [sorted(x) for x in out]
 
 

@@ -120,3 +120,10 @@ def test_balance_views_equal_counts_and_near_equal_cost():
         naive = [sum(costs[i] for i in range(n)[r::world]) for r in range(world)]
         assert max(loads) <= max(naive)
         assert balance_views(costs, world) == shards  # deterministic: every rank computes the same table
+        # ranks that run at different paces: the slowest rank's TIME (speed x cost) is what gets levelled
+        speeds = [1.0 + 0.15 * (r % 2) for r in range(world)]
+        sh2 = balance_views(costs, world, speeds)
+        assert sorted(i for s in sh2 for i in s) == list(range(n)) and max(map(len, sh2)) - min(map(len, sh2)) <= 1
+        t_aware = max(speeds[r] * sum(costs[i] for i in s) for r, s in enumerate(sh2))
+        t_blind = max(speeds[r] * sum(costs[i] for i in s) for r, s in enumerate(shards))
+        assert t_aware <= t_blind
