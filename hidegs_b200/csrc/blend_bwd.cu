@@ -33,6 +33,19 @@ struct PixelState {
   int last_contributor;
 };
 
+// The recurrence state of a lane's two pixels as register PAIRS (.x: pixel A, .y: pixel B four rows below), so that an
+// entry that reaches both halves is evaluated with the packed FP32 instructions (blend_common.cuh).
+struct PairState {
+  float2 w[9];
+  float2 bgT, T, acc_g, last_g, last_alpha;
+  int lastA, lastB;
+};
+
+template <int HALF>
+__device__ __forceinline__ float& half_of(float2& v) { return HALF ? v.y : v.x; }
+template <int HALF>
+__device__ __forceinline__ float half_of(const float2& v) { return HALF ? v.y : v.x; }
+
 template <bool GEO, bool DEPTH>
 __device__ __forceinline__ void load_pixel_state(PixelState& s, bool inside, size_t pix, size_t HW, int W, int H,
                                                  float pixx, float pixy, float fx, float fy, int n,
@@ -178,11 +191,21 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // true = the accurate pow of the reference's backward (~35 instructions each, twice per pair).  The fast evaluation
 // reports through `near` when the interpolated alpha lies within 2e-6 of the 1/255 cut — ten times its error — so that
 // the caller can redo the rare pair whose classification could differ from the reference's.
-template <bool GEO, bool DEPTH, bool INTERP, bool ACC>
-__device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4 ea, const float4 eb, const float4 ec,
-                                             const float4 ed, const float2 tf, float pixx, float pixy, int q,
+template <bool GEO, bool DEPTH, bool INTERP, bool ACC, int HALF>
+__device__ __forceinline__ bool pixel_pair_c(PairState& ps, const float4 ea, const float4 eb, const float4 ec,
+                                             const float4 ed, const float2 tf, float pixx, float2 neg_pixy, int q,
                                              float& wgt, float& p, float& p3, bool& near) {
-  const float dx = __fsub_rn(ea.x, pixx), dy = __fsub_rn(ea.y, pixy);
+  struct {  // this half's view of the pair state
+    float &T, &acc_g, &last_g, &last_alpha;
+    const float bgT;
+    const int last_contributor;
+    float w[9];
+  } s{half_of<HALF>(ps.T), half_of<HALF>(ps.acc_g), half_of<HALF>(ps.last_g), half_of<HALF>(ps.last_alpha),
+      half_of<HALF>(ps.bgT), HALF ? ps.lastB : ps.lastA,
+      {half_of<HALF>(ps.w[0]), half_of<HALF>(ps.w[1]), half_of<HALF>(ps.w[2]), half_of<HALF>(ps.w[3]),
+       half_of<HALF>(ps.w[4]), half_of<HALF>(ps.w[5]), half_of<HALF>(ps.w[6]), half_of<HALF>(ps.w[7]),
+       half_of<HALF>(ps.w[8])}};
+  const float dx = __fsub_rn(ea.x, pixx), dy = __fadd_rn(ea.y, half_of<HALF>(neg_pixy));  // y - pixy
   const float quad = __fmaf_rn(dx, __fmul_rn(dx, ea.z), __fmul_rn(dy, __fmul_rn(dy, eb.x)));
   const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, ea.w)));
   // expf, not a bare ex2.approx: the pair must be classified (alpha >= 1/255, clamp at 0.99) exactly as the forward
@@ -228,6 +251,54 @@ __device__ __forceinline__ bool pixel_pair_c(PixelState& s, const float4 ea, con
   return valid;
 }
 
+// Both pixels of the lane at once (an entry that reaches both halves; no hierarchy interpolation): the code above on
+// FADD2 / FMUL2 / FFMA2.  The classification (power, expf, the 0.99 clamp and the 1/255 cut) keeps the forward's
+// operations, order and roundings per half (see fwd_pair_flat2 in blend_fwd.cu); the gradient arithmetic behind it is
+// the same expressions with explicit contractions.
+template <bool GEO, bool DEPTH>
+__device__ __forceinline__ bool pixel_pair_c2(PairState& s, const float4 ea, const float4 eb, const float4 ec,
+                                              const float4 ed, float pixx, float2 neg_pixy, int q, float2& wgt,
+                                              float2& p) {
+  const float dx = __fsub_rn(ea.x, pixx);
+  const float dxa = __fmul_rn(dx, ea.z);
+  const float ndxb = __fmul_rn(dx, -ea.w);
+  const float2 dy = __fadd2_rn(bc2(ea.y), neg_pixy);
+  const float2 quad = __ffma2_rn(bc2(dx), bc2(dxa), __fmul2_rn(dy, __fmul2_rn(dy, bc2(eb.x))));
+  const float2 power = __ffma2_rn(quad, bc2(-0.5f), __fmul2_rn(dy, bc2(ndxb)));
+  const float2 test_alpha = __fmul2_rn(bc2(eb.y), expf_pair(power));
+  const float bA = fminf(0.99f, test_alpha.x), bB = fminf(0.99f, test_alpha.y);
+  const bool validA = (q < s.lastA) && !(power.x > 0.0f) && !(bA < 1.0f / 255.0f);
+  const bool validB = (q < s.lastB) && !(power.y > 0.0f) && !(bB < 1.0f / 255.0f);
+  const float2 alpha = make_float2(validA ? bA : 0.f, validB ? bB : 0.f);
+  const float2 om = __ffma2_rn(alpha, bc2(-1.0f), bc2(1.0f));
+  float2 rinv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv.x) : "f"(om.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv.y) : "f"(om.y));
+  const float2 Tn = __fmul2_rn(s.T, rinv);
+  wgt = __fmul2_rn(alpha, Tn);
+  float2 g = __ffma2_rn(bc2(ec.z), s.w[2], __ffma2_rn(bc2(ec.y), s.w[1], __fmul2_rn(bc2(ec.x), s.w[0])));
+  if (DEPTH) g = __ffma2_rn(bc2(ec.w), s.w[3], g);
+  if (GEO) {
+    g = __ffma2_rn(bc2(ed.x), s.w[4], g);
+    g = __ffma2_rn(bc2(ed.y), s.w[5], g);
+    g = __ffma2_rn(bc2(ed.z), s.w[6], g);
+    g = __ffma2_rn(bc2(ed.w), s.w[7], g);
+    g = __ffma2_rn(bc2(eb.z), s.w[8], g);
+  }
+  const float2 om_last = __ffma2_rn(s.last_alpha, bc2(-1.0f), bc2(1.0f));
+  const float2 acc_new = __ffma2_rn(s.last_alpha, s.last_g, __fmul2_rn(om_last, s.acc_g));
+  const float2 diff = __fadd2_rn(g, make_float2(-acc_new.x, -acc_new.y));
+  const float2 dL_dalpha = __ffma2_rn(diff, Tn, __fmul2_rn(s.bgT, rinv));
+  s.T = Tn;
+  s.acc_g = acc_new;
+  s.last_g = g;
+  s.last_alpha = alpha;
+  p = __fmul2_rn(alpha, dL_dalpha);
+  p.x = test_alpha.x > 0.99f ? 0.f : p.x;
+  p.y = test_alpha.y > 0.99f ? 0.f : p.y;
+  return validA || validB;
+}
+
 template <bool GEO, bool DEPTH, bool INTERP>
 // (Measured: 3 CTAs / SM with 148 registers — no rematerialisation pressure, 12 warps — 1.123 ms against 1.014 ms at
 // 4 CTAs / 125 registers: the kernel wants warps more than registers.)
@@ -259,6 +330,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const uint2 range = ranges[tile];
   const int n = (int)(range.y - range.x);
 
+  PairState S;
   PixelState A, B;
   load_pixel_state<GEO, DEPTH>(A, insideA, (size_t)pyA * W + pxi, HW, W, H, pixx, pixyA, fx, fy, n, bg_color,
                                all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
@@ -267,6 +339,14 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                                all_map_pixels, final_Ts, n_contrib, dL_dpixels, dL_dout_all_maps, dL_dout_plane_depths,
                                dL_invdepths);
 
+#pragma unroll
+  for (int c = 0; c < 9; ++c) S.w[c] = make_float2(A.w[c], B.w[c]);
+  S.bgT = make_float2(A.bgT, B.bgT);
+  S.T = make_float2(A.T, B.T);
+  S.acc_g = S.last_g = S.last_alpha = make_float2(0.f, 0.f);
+  S.lastA = A.last_contributor;
+  S.lastB = B.last_contributor;
+  const float2 neg_pixy = make_float2(-pixyA, -pixyB);
   // last contributor of each half and of the tile; the slot id of this lane's first list entry is requested right away
   // so that the list read (and, behind it, the record gather) overlaps the construction of the B tiles
   int wmaxA = A.last_contributor, wmaxB = B.last_contributor;
@@ -476,25 +556,29 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       float wA = 0.f, pA = 0.f, wB = 0.f, pB = 0.f, p3A = 0.f, p3B = 0.f;
       bool any, near = false;
       // state before this entry (only read again on the rare redo below)
-      const float A_T = A.T, A_acc = A.acc_g, A_lg = A.last_g, A_la = A.last_alpha;
-      const float B_T = B.T, B_acc = B.acc_g, B_lg = B.last_g, B_la = B.last_alpha;
+      const float2 S_T = S.T, S_acc = S.acc_g, S_lg = S.last_g, S_la = S.last_alpha;
       if (hasA && hasB) {  // one basic block: the two pixels' dependency chains interleave
-        any = pixel_pair_c<GEO, DEPTH, INTERP, false>(A, ea, eb, ec, ed, tf, pixx, pixyA, q, wA, pA, p3A, near);
-        any |= pixel_pair_c<GEO, DEPTH, INTERP, false>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
+        if (!INTERP) {
+          float2 w2, p2;
+          any = pixel_pair_c2<GEO, DEPTH>(S, ea, eb, ec, ed, pixx, neg_pixy, q, w2, p2);
+          wA = w2.x; wB = w2.y; pA = p2.x; pB = p2.y;
+        } else {
+          any = pixel_pair_c<GEO, DEPTH, INTERP, false, 0>(S, ea, eb, ec, ed, tf, pixx, neg_pixy, q, wA, pA, p3A, near);
+          any |= pixel_pair_c<GEO, DEPTH, INTERP, false, 1>(S, ea, eb, ec, ed, tf, pixx, neg_pixy, q, wB, pB, p3B, near);
+        }
       } else if (hasA) {
-        any = pixel_pair_c<GEO, DEPTH, INTERP, false>(A, ea, eb, ec, ed, tf, pixx, pixyA, q, wA, pA, p3A, near);
+        any = pixel_pair_c<GEO, DEPTH, INTERP, false, 0>(S, ea, eb, ec, ed, tf, pixx, neg_pixy, q, wA, pA, p3A, near);
       } else {
-        any = pixel_pair_c<GEO, DEPTH, INTERP, false>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
+        any = pixel_pair_c<GEO, DEPTH, INTERP, false, 1>(S, ea, eb, ec, ed, tf, pixx, neg_pixy, q, wB, pB, p3B, near);
       }
       if (INTERP && __any_sync(0xffffffffu, near)) {
         // a pair within the error of the fast pow of the 1/255 cut: evaluate this entry again, for the whole warp, the
         // way the reference's backward does
-        A.T = A_T; A.acc_g = A_acc; A.last_g = A_lg; A.last_alpha = A_la;
-        B.T = B_T; B.acc_g = B_acc; B.last_g = B_lg; B.last_alpha = B_la;
+        S.T = S_T; S.acc_g = S_acc; S.last_g = S_lg; S.last_alpha = S_la;
         wA = pA = wB = pB = p3A = p3B = 0.f;
         any = false;
-        if (hasA) any = pixel_pair_c<GEO, DEPTH, INTERP, true>(A, ea, eb, ec, ed, tf, pixx, pixyA, q, wA, pA, p3A, near);
-        if (hasB) any |= pixel_pair_c<GEO, DEPTH, INTERP, true>(B, ea, eb, ec, ed, tf, pixx, pixyB, q, wB, pB, p3B, near);
+        if (hasA) any = pixel_pair_c<GEO, DEPTH, INTERP, true, 0>(S, ea, eb, ec, ed, tf, pixx, neg_pixy, q, wA, pA, p3A, near);
+        if (hasB) any |= pixel_pair_c<GEO, DEPTH, INTERP, true, 1>(S, ea, eb, ec, ed, tf, pixx, neg_pixy, q, wB, pB, p3B, near);
       }
       if (__ballot_sync(0xffffffffu, any) == 0) continue;
       float s3 = eb.z;
