@@ -163,6 +163,16 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// The same for two values at once: the two truncations are LOP3s, the two exact remainders ONE packed FADD2.
+__device__ __forceinline__ void split_tf32_pair(float v0, float v1, uint32_t& hi0, uint32_t& lo0, uint32_t& hi1,
+                                                uint32_t& lo1) {
+  asm("and.b32 %0, %1, 0xffffe000;" : "=r"(hi0) : "r"(__float_as_uint(v0)));
+  asm("and.b32 %0, %1, 0xffffe000;" : "=r"(hi1) : "r"(__float_as_uint(v1)));
+  const float2 lo = __fadd2_rn(make_float2(v0, v1), make_float2(-__uint_as_float(hi0), -__uint_as_float(hi1)));
+  lo0 = __float_as_uint(lo.x);
+  lo1 = __float_as_uint(lo.y);
+}
+
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
   asm volatile(
@@ -427,25 +437,19 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
       ldmatrix_x4(wq, a_w + a_ld + 8 * s_);
       ldmatrix_x4(pq, a_p + a_ld + 8 * s_);
       uint32_t w0h, w0l, w1h, w1l, w2h, w2l, w3h, w3l, p0h, p0l, p1h, p1l, p2h, p2l, p3h, p3l;
-      split_tf32(__uint_as_float(wq[0]), w0h, w0l);
-      split_tf32(__uint_as_float(wq[1]), w1h, w1l);
-      split_tf32(__uint_as_float(wq[2]), w2h, w2l);
-      split_tf32(__uint_as_float(wq[3]), w3h, w3l);
-      split_tf32(__uint_as_float(pq[0]), p0h, p0l);
-      split_tf32(__uint_as_float(pq[1]), p1h, p1l);
-      split_tf32(__uint_as_float(pq[2]), p2h, p2l);
-      split_tf32(__uint_as_float(pq[3]), p3h, p3l);
+      split_tf32_pair(__uint_as_float(wq[0]), __uint_as_float(wq[1]), w0h, w0l, w1h, w1l);
+      split_tf32_pair(__uint_as_float(wq[2]), __uint_as_float(wq[3]), w2h, w2l, w3h, w3l);
+      split_tf32_pair(__uint_as_float(pq[0]), __uint_as_float(pq[1]), p0h, p0l, p1h, p1l);
+      split_tf32_pair(__uint_as_float(pq[2]), __uint_as_float(pq[3]), p2h, p2l, p3h, p3l);
       const float2 bq = sm.b_ch0[warp][s_][lane];
       uint32_t b0h, b0l, b1h, b1l;
-      split_tf32(bq.x, b0h, b0l);
-      split_tf32(bq.y, b1h, b1l);
+      split_tf32_pair(bq.x, bq.y, b0h, b0l, b1h, b1l);
       mma_tf32(dc0, w0h, w1h, w2h, w3h, b0h, b1h);
       mma_tf32(dc0x, w0l, w1l, w2l, w3l, b0h, b1h);
       mma_tf32(dc0x, w0h, w1h, w2h, w3h, b0l, b1l);
       if (GEO) {
         const float2 b8 = b8_src[s_ * b8_step];
-        split_tf32(b8.x, b0h, b0l);
-        split_tf32(b8.y, b1h, b1l);
+        split_tf32_pair(b8.x, b8.y, b0h, b0l, b1h, b1l);
         mma_tf32(dc8, w0h, w1h, w2h, w3h, b0h, b1h);
         mma_tf32(dc8x, w0l, w1l, w2l, w3l, b0h, b1h);
         mma_tf32(dc8x, w0h, w1h, w2h, w3h, b0l, b1l);
