@@ -544,9 +544,10 @@ def run_gpu_arm(args, impl):
                "algorithmic_bytes": bytes_per[dom], "peak_source": how}
         sm_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
         issue_peak = 148 * 4 * sm_ghz  # G warp-instructions / s: 148 SMs x 4 schedulers x 1 issue / clock
-        warp_inst = None
+        warp_inst = packed = None
         if os.path.exists(tp):
             warp_inst = json.load(open(tp)).get("_warp_instructions", {}).get(dom)
+            packed = json.load(open(tp)).get("_packed_fp32_instructions", {}).get(dom)
         if dom.startswith("blend") and warp_inst:
             # the blend kernels gather L2-resident records and are bound by instruction issue: the
             # fraction is quoted against THAT roof, the HBM figure is kept beside it
@@ -556,6 +557,12 @@ def run_gpu_arm(args, impl):
                                 "warp_instructions_per_launch_ncu": warp_inst,
                                 "peak_source": "148 SM x 4 schedulers x median SM clock under load (%.0f MHz)" % (sm_ghz * 1e3),
                                 "issue_active_pct_ncu": issue_pct, "frac_hbm": hbm["frac"], "hbm": hbm}
+            if packed:
+                # FADD2 / FMUL2 / FFMA2 retire two FP32 operations per issue slot at the same 128 FMA / clk / SM: `frac`
+                # counts them once (= how busy the issue port is), this figure counts them twice (= the scalar-
+                # equivalent instruction rate, the unit SURVEY.md 8(d) quotes the blend loops in)
+                line["roofline"]["packed_fp32_instructions_per_launch_ncu"] = packed
+                line["roofline"]["frac_scalar_equivalent"] = round((warp_inst + packed) / (dom_ms * 1e-3) / 1e9 / issue_peak, 4)
         else:
             line["roofline"] = dict(kernel=dom, bound="hbm", traffic=traffic, **hbm)
         line["roofline"].update({"kernel_ms": round(dom_ms, 4), "stage_ms": per_stage,

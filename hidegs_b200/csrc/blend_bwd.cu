@@ -542,6 +542,9 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     }
     __syncwarp();
     if (base >= 32) prefetch(base - 32);
+    // (Measured and dropped after the packed-FP32 rewrite: every survivor through the packed pair path — a half it cannot
+    // reach entering with alpha = 0 — with test_alpha of entry i + 1 computed next to the recurrence of entry i: 1.012 vs
+    // 0.976 ms; the entries that reach one half only are too many to pay a pair evaluation each.)
     // (Measured and dropped: software-pipelining this loop by one entry — next entry's first two quads fetched while the
     // current one is evaluated — 1.27 vs 1.09 ms: eight more live registers at the 128-register cap cost more than the
     // short-scoreboard stalls they remove.)

@@ -3,6 +3,7 @@
 reports) into the tracked summaries under profiles/.  Usage: python tools/make_profiles.py [round-tag, default r01]"""
 import collections
 import csv
+import io
 import json
 import os
 import shutil
@@ -185,6 +186,22 @@ def full_capture(rep, dst, what, cmd, traffic_keys=False):
             if key in n:
                 ia[key], wi[key] = float(a_), float(w_.replace(",", ""))
     tr["_issue_active_pct"], tr["_warp_instructions"] = ia, wi
+    # packed FP32 (FADD2 / FMUL2 / FFMA2) instructions executed, from the report's SASS page: each retires two FP32
+    # operations in one issue slot, so executed + packed = the scalar-equivalent instruction count of the kernel
+    pk = tr.get("_packed_fp32_instructions", {})
+    for key, rx in (("blend_fwd", "blend_fwd2"), ("blend_bwd", "blend_bwd3")):
+        out = subprocess.run(["ncu", "-i", os.path.join(G, rep), "--page", "source", "--csv", "--kernel-name", "regex:" + rx],
+                             capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+        if not hi:
+            continue
+        hdr = rows[hi[0]]
+        end = hi[1] - 1 if len(hi) > 1 else len(rows)
+        si, ie = hdr.index("Source"), hdr.index("Instructions Executed")
+        pk[key] = float(sum(int(r[ie]) for r in rows[hi[0] + 1:end]
+                            if len(r) == len(hdr) and any(m in r[si] for m in ("FFMA2", "FMUL2", "FADD2"))))
+    tr["_packed_fp32_instructions"] = pk
     json.dump(tr, open(tp, "w"), indent=1)
 
 

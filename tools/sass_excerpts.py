@@ -13,6 +13,8 @@ OBJ = os.path.join(ROOT, "hidegs_b200", "csrc", "build")
 WANT = [  # (object, kernel regex, mnemonic regex, what it shows)
     ("blend_bwd", r"blend_bwd3_kernelILb1ELb1ELb0", r"HMMA|LDSM|REDG?\.|RED\.|MUFU", "3xTF32 mma.sync reduction, ldmatrix A quads, vector REDs"),
     ("blend_bwd", r"blend_bwd3_kernelILb0ELb0ELb1", r"HMMA|LDSM|MUFU\.(LG2|EX2)|CALL", "hierarchy interpolation on the MMA kernel: lg2 / ex2 pow, out-of-line accurate redo"),
+    ("blend_fwd", r"blend_fwd2_kernelILb1ELb1ELb0", r"FFMA2|FMUL2|FADD2", "packed FP32 (fma/mul/add.f32x2): the lane's two pixels per instruction, scalar-broadcast (.F32) and pair (.F32x2.HI_LO) operands, FFMA2.RM of the paired expf"),
+    ("blend_bwd", r"blend_bwd3_kernelILb1ELb1ELb0", r"FFMA2|FMUL2|FADD2", "packed FP32 in the backward: pair recurrence, g = <features, dL/dpixel> as 9 packed FMAs, TF32 remainders of the flush"),
     ("blend_fwd", r"blend_fwd2_kernelILb1ELb1ELb0", r"LDG\.E\.128|STS\.128|LDS\.128|MUFU|VOTE|ATOM|RED", "register-double-buffered gather, 128-bit staging, ballots"),
     ("blend_fwd", r"blend_fwd3_kernel", r"UBLKCP|SYNCS", "TMA bulk-copy staging experiment (cp.async.bulk + mbarrier; removed from the tree)"),
     ("exchange", r"nvls_allreduce_kernelILi4", r"LDGMC|STG.*MC|MULTIMEM|ST\.E.*MMIO|RED|ATOM|CAS|LDG\.E\.128", "multimem.ld_reduce / multimem.st through NVSwitch; the gather range = plain LDG.128 + multimem.st"),
