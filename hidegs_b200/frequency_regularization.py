@@ -216,19 +216,29 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
     image, optional, keyword only in spirit) skips the work that depends on the ground truth alone."""
     if iteration < warmup_iterations:
         return torch.tensor(0.0, device=rendered_image.device), None, {'warmup': True}
-    if not 1 <= num_levels <= 3:
-        raise NotImplementedError("hidegs_b200 frequency regularisation supports 1..3 pyramid levels")
+    # Level counts outside 1..3, as the reference treats them: build_pyramid's range(1, num_levels) adds nothing below two
+    # levels (:1073-1084), and above three `pyramid_weights = [0.1, 0.05, 0.025][:len(pyramid)]` has no entry for level 3 —
+    # the IndexError lands in compute_true_frequency_loss's own try block, which prints and returns tensor(0.0)
+    # (:1301-1325): the frequency term is a gradient-free zero, mask and scale term are computed as usual.
+    requested_levels = int(num_levels)
+    num_levels = max(1, requested_levels)
+    freq_fails = num_levels > 3
     device = rendered_image.device
     r = rendered_image[0] if rendered_image.dim() == 4 else rendered_image
     g = gt_image[0] if gt_image.dim() == 4 else gt_image
     stats = None
-    if gt_cache is not None and not gt_cache.matches(g, num_levels, high_freq_thresh):
+    if gt_cache is not None and not gt_cache.matches(g, min(num_levels, 3), high_freq_thresh):
         raise RuntimeError("gt_cache was built for another image size / level count / threshold")
     mask = count = None
     if gt_cache is not None:
         mask, count = gt_cache.mask, gt_cache.count
     freq_loss = None
-    if lambda_freq > 0:
+    if lambda_freq > 0 and freq_fails:
+        print("frequency loss failed: list index out of range")  # the reference's message, same place
+        freq_loss = torch.zeros((), dtype=torch.float32, device=device)
+        if mask is None:
+            mask, count = detect_true_high_frequency_regions(g, high_freq_thresh)
+    elif lambda_freq > 0:
         if mask is None:  # the mask of this ground truth comes out of the regulariser's own launches
             freq_loss, stats, mask, count = _FreqLoss.apply(r, g.detach(), int(num_levels), None, float(high_freq_thresh))
         else:
@@ -254,6 +264,8 @@ def frequency_regularization_pyramid_scale(rendered_image, gt_image, gaussians, 
 
     def fill():
         info = {'pyramid_levels': int(num_levels)}
+        if freq_fails and lambda_freq > 0:
+            info['freq_loss'] = 0.0
         vals = [total.detach().reshape(1), count]
         if stats is not None:
             vals.append(stats)

@@ -178,6 +178,33 @@ def test_frequency_regularization_vs_reference_golden(cuda_device, path):
     assert info["pyramid_levels"] == 3 and info["fft_valid"] is True and "total_loss" in info
 
 
+@pytest.mark.parametrize("levels", [0, 1, 2, 4])
+def test_frequency_regularization_other_level_counts_vs_reference_golden(cuda_device, levels):
+    """num_levels other than 3 against the reference's own function (tests/golden/api_extras_ref.npz): below two levels the
+    pyramid is the image alone; above three the reference's level-weight table runs out and its try block turns the
+    frequency term into a gradient-free zero (scale term and mask as usual)."""
+    from hidegs_b200.frequency_regularization import frequency_regularization_pyramid_scale as f
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "api_extras_ref.npz"))
+    inp = lt.make_loss_inputs(**lt.LOSS_CASES["near_small"])
+    dev = cuda_device
+    r = inp["render"].to(dev).requires_grad_(True)
+    sc = inp["scaling"].to(dev).requires_grad_(True)
+    total, mask, info = f(r, inp["gt"].to(dev), lt.GaussiansShim(sc), None, None, inp["visibility"].to(dev), 2000,
+                          num_levels=levels)
+    total.backward()
+    k = "freq_lv%d_" % levels
+    assert abs(total.item() - float(gold[k + "total"])) <= 1e-3 * float(gold[k + "total"])
+    assert info["pyramid_levels"] == int(gold[k + "pyramid_levels"])
+    assert abs(info["freq_loss"] - float(gold[k + "freq_loss"])) <= 1e-3 * float(gold[k + "freq_loss"])
+    assert abs(int(mask.sum().item()) - int(gold[k + "mask_pixels"])) <= 2  # threshold ties
+    assert grad_ok(sc.grad.cpu().numpy(), gold[k + "grad_scaling"])
+    if levels > 3:
+        assert r.grad is None or float(r.grad.abs().max()) == 0.0  # no gradient reaches the image
+    else:
+        want = gold[k + "grad_render"]
+        assert rel(r.grad.cpu().numpy(), want) < 2e-3  # the reference's own float32 gradient is ~6e-4 off float64
+
+
 @pytest.mark.parametrize("noise", [0.05, 0.002])
 def test_frequency_regularization_full_size_vs_oracle(cuda_device, noise):
     """Config 1 (3x1080x1920): far variant saturates the level-0/1 clamps, near variant does not."""
