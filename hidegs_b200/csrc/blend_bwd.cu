@@ -333,7 +333,7 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
   const bool insideA = pxi < W && pyA < H, insideB = pxi < W && pyB < H;
   const float pixx = (float)pxi, pixyA = (float)pyA, pixyB = (float)pyB;
   const float fx0 = (float)wx0, fx1 = (float)(wx0 + 7);
-  const float fyA0 = (float)wy0, fyA1 = (float)(wy0 + 3), fyB0 = (float)(wy0 + 4), fyB1 = (float)(wy0 + 7);
+  const float2 fy0 = make_float2((float)wy0, (float)(wy0 + 4)), fy1 = make_float2((float)(wy0 + 3), (float)(wy0 + 7));
   const float cx = (float)wx0 + 3.5f, cy = (float)wy0 + 3.5f;  // moments are taken about the sub-tile centre
   const size_t HW = (size_t)H * W;
 
@@ -525,8 +525,9 @@ blend_bwd3_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
     const float a = pf.r0.z, bb = pf.r0.w, c = pf.r1.x, o = pf.r1.y;
     if (q_mine >= 0) {
       const float tau = cull_tau(a, bb, c, o, INTERP);
-      keepA = q_mine < wmaxA && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyA0, fyA1);
-      keepB = q_mine < wmaxB && may_touch(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fyB0, fyB1);
+      may_touch2(pf.r0.x, pf.r0.y, a, bb, c, tau, fx0, fx1, fy0, fy1, keepA, keepB);
+      keepA = keepA && q_mine < wmaxA;
+      keepB = keepB && q_mine < wmaxB;
     }
     const uint32_t maskA = __ballot_sync(0xffffffffu, keepA), maskB = __ballot_sync(0xffffffffu, keepB);
     const uint32_t mask = maskA | maskB;
