@@ -706,6 +706,35 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
         for _ in range(warmup):
             step()
         torch.cuda.synchronize()
+        # Feedback on what the ranks then actually take for their views (the whole phase, CUDA events of two steps): the
+        # sum of separately timed views misses what a rank's host side adds between them, so every rank's pace is
+        # corrected by measured / predicted and the views are dealt again, at most three times.
+        rounds = []
+        for _ in range(int(os.environ.get("HG_BENCH_BALANCE_FEEDBACK", "3"))):
+            trainer.timing = []
+            step()
+            step()
+            torch.cuda.synchronize()
+            mine_ms = sum(e[0].elapsed_time(e[1]) for e in trainer.timing) / len(trainer.timing)
+            trainer.timing = None
+            got = [None] * world
+            dist.all_gather_object(got, mine_ms)
+            rounds.append([round(x, 3) for x in got])
+            pred = [speeds[r] * sum(cost[i] for i in sh) for r, sh in enumerate(shards)]
+            speeds = [speeds[r] * got[r] / pred[r] for r in range(world)]
+            norm = sum(speeds) / world
+            speeds = [x / norm for x in speeds]
+            new_shards = tr.balance_views(cost, world, speeds)
+            if new_shards == shards:
+                break
+            shards = new_shards
+            my_views = shards[rank]
+            cams[:] = [cams_all[i] for i in my_views]
+            trainer._gt_cache.clear()
+            step()  # (rebuilds the per-camera ground-truth caches)
+            torch.cuda.synchronize()
+        balance["views_ms_per_rank_measured_per_feedback_round"] = rounds
+        balance["rank_pace_final"] = [round(x, 3) for x in speeds]
     if ddp:
         dist.barrier()
     _lib.lib().hg_reset_launch_count()
