@@ -168,7 +168,12 @@ def run_gpu_arm(args, impl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ddp = world > 1 and impl == "ours"
+    host_placement = None
     if ddp:
+        # one process per GPU: keep each on the cores of its GPU's NUMA node (before NCCL and torch start their threads)
+        if os.environ.get("HG_BENCH_PIN", "1") != "0":
+            from hidegs_b200.parallel import pin_host_to_gpu_node
+            host_placement = pin_host_to_gpu_node(dev)
         dist.init_process_group("nccl", device_id=dev)
 
     if impl == "ours":
@@ -503,6 +508,7 @@ def run_gpu_arm(args, impl):
                                "REDUCED %d Gaussians %dx%d" % (N_GAUSS, WIDTH, HEIGHT),
                    "gaussians": N_GAUSS, "width": WIDTH, "height": HEIGHT, "visible": Nv, "num_rendered": R,
                    "outputs": "color+all_map+plane_depth+invdepth", "parallelism": "view-sharded dp%d" % world,
+                   "host_placement_rank0": host_placement,
                    "exchange": (None if not ddp else
                                 ("factored: %s; %d B per Gaussian through the fabric instead of 236"
                                  % ("ONE in-fabric kernel (hg_nvls_exchange_f32: 11 non-SH floats summed with "

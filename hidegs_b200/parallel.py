@@ -24,6 +24,36 @@ EXCHANGE_SYMBOLS = ("hg_nvls_flag_words", "hg_nvls_allreduce_f32", "hg_nvls_allr
 _MAX_BLOCKS = 1024
 
 
+def pin_host_to_gpu_node(device=None):
+    """Restrict this process (and the threads it starts afterwards) to the CPU cores NVML reports as local to `device`
+    — the cores of the NUMA node its PCIe root hangs off.  One process per GPU launches ~40 kernels per view; from the
+    far socket every launch and every event query crosses the inter-socket link, which shows as a slower "GPU" in
+    view-sharded steps (measured on an 8-GPU box: the four ranks of one half took 13.1 ms for views the other half ran in
+    12.3 ms, whatever views they were dealt).  Returns a dict for logs: {"pinned": bool, "cpus": n, ...}; never raises:
+    without NVML, without permission or with an empty intersection with the allowed set, the placement stays as it is."""
+    import os
+    info = {"pinned": False}
+    try:
+        import pynvml
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        pr = torch.cuda.get_device_properties(dev)
+        pynvml.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = allowed & local
+        info.update(cpus_allowed=len(allowed), cpus_local=len(local), cpus=len(want))
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+            info["pinned"] = True
+    except Exception as e:  # noqa: BLE001 — placement is an optimisation, never a failure
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def shard_views(views, rank=None, world=None):
     """The views of one step that belong to this rank: views[rank::world]."""
     rank = dist.get_rank() if rank is None else rank
