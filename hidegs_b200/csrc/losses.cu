@@ -149,6 +149,19 @@ training_image_grad_kernel(const float* __restrict__ color, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------- value of the composed training loss
+// (1 - l) L1 + l (1 - SSIM) + regulariser total + normal term, the operations of the Python expression in its order
+// (separately rounded), in one launch instead of six scalar torch kernels per view.
+__global__ void training_loss_value_kernel(const float* __restrict__ l1, const float* __restrict__ ssim,
+                                           const float* __restrict__ extra0, const float* __restrict__ extra1,
+                                           float lambda_dssim, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float v = __fadd_rn(__fmul_rn(1.0f - lambda_dssim, l1[0]), __fmul_rn(lambda_dssim, __fsub_rn(1.0f, ssim[0])));
+  if (extra0) v = __fadd_rn(v, extra0[0]);
+  if (extra1) v = __fadd_rn(v, extra1[0]);
+  out[0] = v;
+}
+
 // ---------------------------------------------------------------- SSIM
 // Separable 11-tap Gaussian (sigma 1.5) in shared memory: 32x32 output tile per 256-thread CTA, 42x42 input tile
 // (halo 5, zero padded as F.conv2d(padding=5)).  Both passes are register blocked — a thread produces 4 consecutive
@@ -643,6 +656,18 @@ int hg_freq_total(const float* freq_loss, const float* scale_loss, const float* 
   cudaStream_t st = (cudaStream_t)st_;
   freq_total_kernel<<<1, 32, 0, st>>>(freq_loss, scale_loss, hf_count, lambda_freq, lambda_scale, out3);
   HG_POST_LAUNCH(false, st, "freq_total");
+  return HG_OK;
+}
+
+int hg_training_loss_value(const float* l1, const float* ssim, const float* extra0, const float* extra1,
+                           float lambda_dssim, float* out, void* st_) {
+  if (!l1 || !ssim || !out) {
+    set_error("hg_training_loss_value: NULL pointer");
+    return HG_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)st_;
+  training_loss_value_kernel<<<1, 32, 0, st>>>(l1, ssim, extra0, extra1, lambda_dssim, out);
+  HG_POST_LAUNCH(false, st, "training_loss_value");
   return HG_OK;
 }
 

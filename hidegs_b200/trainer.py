@@ -434,8 +434,8 @@ class ViewShardedTrainer:
                 if cache is None:
                     cache = self._gt_cache[id(cam)] = (cam, GroundTruthCache(gt),
                                                        (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2)
-            loss = (1.0 - o.lambda_dssim) * l1 + o.lambda_dssim * (1.0 - ss)
             tF = tSc = tT = None
+            reg_total = normal_term = None
             if freq_on:  # frequency_regularization_pyramid_scale (same arithmetic, same order)
                 freq_loss = scale_loss = None
                 count = cache[1].count if cache is not None else None
@@ -452,13 +452,21 @@ class ViewShardedTrainer:
                     scale_loss = _ScaleReg.forward(tSc, scaling, visible)
                 if freq_loss is not None or scale_loss is not None:
                     tT = T(freq_loss is not None, scale_loss is not None, False, False, False)
-                    loss = loss + _FreqTotal.forward(tT, freq_loss, scale_loss, count, o.lambda_freq, o.lambda_scale)
+                    reg_total = _FreqTotal.forward(tT, freq_loss, scale_loss, count, o.lambda_freq, o.lambda_scale)
             tN = None
             if o.single_view_weight > 0:
                 image_weight = cache[2] if cache is not None else (1.0 - lu.get_img_grad_weight(gt)).clamp(0, 1) ** 2
                 tN = T(True, True, False, False, False)
-                loss = loss + gr._NormalConsistency.forward(tN, plane_depth, out_all_map, image_weight,
+                normal_term = gr._NormalConsistency.forward(tN, plane_depth, out_all_map, image_weight,
                                                             gr.camera_intrinsics(cam), o.single_view_weight)
+            # (1 - l) L1 + l (1 - SSIM) + regulariser total + normal term: one launch for the scalar bookkeeping
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                rc = lu._L().hg_training_loss_value(
+                    l1.data_ptr(), ss.data_ptr(), reg_total.data_ptr() if reg_total is not None else None,
+                    normal_term.data_ptr() if normal_term is not None else None, float(o.lambda_dssim), loss.data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "training_loss_value")
             # ---- backward (upstream gradient of the loss = 1)
             # dL/dcolor = [0 <= color <= 1] ((1 - l) dL1 - l dSSIM + gate lf dfreq) in ONE pass over the image
             if self._one is None:

@@ -60,6 +60,13 @@ HG_API int hg_freq_total(const float *freq_loss, const float *scale_loss, const 
 HG_API int hg_training_image_grad(const float *color, const float *gt, const float *g_ssim, const float *g_freq,
                                   int64_t n, float w_l1, float w_ssim, const float *w_freq, float *out, void *stream);
 
+/* Value of the composed training loss of one view (the sum a training loop forms from the reference's pieces:
+ * `(1.0 - lambda_dssim) * l1_loss(...) + lambda_dssim * (1.0 - ssim(...))` plus up to two more device scalars, e.g. the
+ * total of frequency_regularization_pyramid_scale and the normal term), the Python expression's operations in its
+ * order, one launch.  All pointers are DEVICE scalars; extra0 / extra1 nullable. */
+HG_API int hg_training_loss_value(const float *l1, const float *ssim, const float *extra0, const float *extra1,
+                                  float lambda_dssim, float *out, void *stream);
+
 /* SSIM with the reference's 11x11 sigma=1.5 window, zero padding 5, C1=1e-4, C2=9e-4.
  * img1/img2: [B,C,H,W].  out[b] = mean over (C,H,W) of the SSIM map of batch item b (the Python
  * wrapper averages over b for size_average=True).  If `maps` != NULL (3*B*C*H*W floats) the three
