@@ -135,3 +135,15 @@ def test_factored_exchange_moves_only_the_non_sh_blocks_and_the_factors():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_pin_host_to_gpu_node_never_raises_without_a_gpu():
+    """The placement helper is an optimisation: without NVML / a GPU it reports why and leaves the affinity alone."""
+    import os
+    from hidegs_b200.parallel import pin_host_to_gpu_node
+    before = os.sched_getaffinity(0)
+    info = pin_host_to_gpu_node("cuda:0")
+    assert isinstance(info, dict) and "pinned" in info
+    if not info["pinned"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
