@@ -644,7 +644,7 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
                                     start_iteration=tr.OptimizationParams.freq_warmup_iterations)
 
     # Ground-truth images travel host -> device on a copy stream, one event per view (the losses of a view wait for
-    # its image only), double buffered across steps so that uploads of step k+1 may start while step k still computes.
+    # its image only), double buffered across steps: the uploads of step k+1 are issued at the start of step k.
     copy_stream = torch.cuda.Stream(device=dev)
     gt_dev = [[torch.empty_like(g, device=dev) for g in gts] for _ in range(2)]
     step_done = [torch.cuda.Event() for _ in range(2)]
@@ -652,17 +652,32 @@ def train_leg(dev, rank, world, ddp, steps, warmup, views_per_rank, n_gauss, rec
         ev.record()
     counter = [0]
 
-    def step():
-        par = counter[0] & 1
-        counter[0] += 1
-        views = []
+    uploaded = [None, None]  # per buffer: the "image has arrived" events of the step whose images it holds
+
+    def upload(par):
+        """This rank's ground-truth images of ONE step -> buffer `par`, on the copy stream."""
+        evs = []
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(step_done[par])
-            for c, g, d in zip(cams, gts, gt_dev[par]):
+            copy_stream.wait_event(step_done[par])  # the step that last read this buffer has finished
+            for g, d in zip(gts, gt_dev[par]):
                 d.copy_(g, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
-                views.append((c, d, ready))
+                evs.append(ready)
+        uploaded[par] = evs
+
+    def step():
+        par = counter[0] & 1
+        counter[0] += 1
+        if uploaded[par] is None:  # first call only
+            upload(par)
+        views = list(zip(cams, gt_dev[par], uploaded[par]))
+        uploaded[par] = None
+        # The loader runs ONE STEP AHEAD: the images of the next step travel while this one computes (one upload set per
+        # step, inside the timed region, as before).  Issued at the start of their own step they arrive just in time at
+        # 25 GB/s, and late on ranks whose host link delivers less: on an 8-GPU box four ranks sat at 8 x 24.9 MB /
+        # 13.2 ms = 15 GB/s, whatever views they were dealt.
+        upload(par ^ 1)
         loss = trainer.step(views, total_views=total_views)
         step_done[par].record(torch.cuda.current_stream())
         return loss
